@@ -1,0 +1,153 @@
+"""The encoder block (reference layers.py:174-193) on top of the kernel primitives.
+
+Two layers:
+
+* ``block_forward`` -- the block written with the differentiable primitives of ``ops.py``.
+  Autograd through it supports first- and second-order derivatives.
+* ``EncoderBlockFn`` -- what the modules call.  It runs ``block_forward`` without recording a
+  graph and keeps only the block INPUTS (x, y); the backward recomputes the block from them
+  (activation memory per block drops from ~9 edge-sized tensors to 1, which is what lets
+  batch 2048 x depth 8 fit next to the 4+2 encoder passes of one GAN step).  The backward is
+  itself a Function (``EncoderBlockBwdFn``) so the gradient penalty's ``create_graph=True``
+  pass can differentiate it: its backward recomputes the block once more with a graph and
+  runs reverse-over-reverse through the primitives' hand-derived second-order kernels.
+
+Parameter order of a block (``BLOCK_PARAM_NAMES``) follows the reference state-dict keys.
+"""
+from __future__ import annotations
+
+import math
+from typing import Sequence
+
+import torch
+from torch.autograd import Function
+
+from . import ops
+
+BLOCK_PARAM_NAMES = (
+    "ln1.weight", "ln1.bias",
+    "attn.q.weight", "attn.q.bias", "attn.k.weight", "attn.k.bias", "attn.v.weight", "attn.v.bias",
+    "attn.e.weight", "attn.e.bias", "attn.out_e.weight", "attn.out_e.bias",
+    "attn.out_n.weight", "attn.out_n.bias",
+    "ln3.weight", "ln3.bias", "ln4.weight", "ln4.bias",
+    "mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight", "mlp.fc2.bias",
+    "mlp2.fc1.weight", "mlp2.fc1.bias", "mlp2.fc2.weight", "mlp2.fc2.bias",
+    "ln5.weight", "ln5.bias", "ln6.weight", "ln6.bias",
+)
+_IDX = {n: i for i, n in enumerate(BLOCK_PARAM_NAMES)}
+
+
+def block_forward(x, y, params: Sequence[torch.Tensor], heads: int, edge_out: bool = True):
+    """x:[B,N,D], y:[B,N,N,D] -> (x_out, y_out).  ``edge_out=False`` skips the edge half that has
+    no consumer (the last Discriminator block, models.py:202-207) and returns y_out=None."""
+    p = lambda n: params[_IDX[n]]  # noqa: E731
+    d = x.shape[-1]
+    c = 1.0 / math.sqrt(d // heads)                                          # layers.py:124
+    x1 = ops.add_ln(x, None, p("ln1.weight"), p("ln1.bias"))                 # :185
+    q = ops.linear(x1, p("attn.q.weight"), p("attn.q.bias"))                 # :111
+    k = ops.linear(x1, p("attn.k.weight"), p("attn.k.bias"))                 # :112
+    v = ops.linear(x1, p("attn.v.weight"), p("attn.v.bias"))                 # :113
+    e = ops.linear(y, p("attn.e.weight"), p("attn.e.bias"))                  # :116
+    a = ops.Modulate.apply(q, k, e, c)                                       # :123-125
+    g = ops.SoftmaxAgg.apply(a, v)                                           # :130-134
+    x3 = ops.add_ln(x1, ops.linear(g, p("attn.out_n.weight"), p("attn.out_n.bias")),
+                    p("ln3.weight"), p("ln3.bias"))                          # :135,187,189
+    hx = ops.linear(x3, p("mlp.fc1.weight"), p("mlp.fc1.bias"), relu=True)   # :51-52
+    x_out = ops.add_ln(x3, ops.linear(hx, p("mlp.fc2.weight"), p("mlp.fc2.bias")),
+                       p("ln5.weight"), p("ln5.bias"))                       # :53,191
+    if not edge_out:
+        return x_out, None
+    y1 = ops.linear(a, p("attn.out_e.weight"), p("attn.out_e.bias"))         # :127 (pre-softmax scores)
+    y3 = ops.add_ln(y, y1, p("ln4.weight"), p("ln4.bias"))                   # :188,190
+    hy = ops.linear(y3, p("mlp2.fc1.weight"), p("mlp2.fc1.bias"), relu=True)
+    y_out = ops.add_ln(y3, ops.linear(hy, p("mlp2.fc2.weight"), p("mlp2.fc2.bias")),
+                       p("ln6.weight"), p("ln6.bias"))                       # :192
+    return x_out, y_out
+
+
+def _leaf(t):
+    return t.detach().requires_grad_(True)
+
+
+def _recompute(x, y, dxo, dyo, params, heads, edge_out, leaf_grads: bool):
+    """Rebuild the block from its inputs on fresh leaves; returns (leaves, outs, gouts, gout_leaves)."""
+    leaves = (_leaf(x), _leaf(y)) + tuple(_leaf(p) for p in params)
+    xo, yo = block_forward(leaves[0], leaves[1], leaves[2:], heads, edge_out)
+    outs, gouts = [], []
+    for o, g in ((xo, dxo), (yo, dyo)):
+        if o is not None and g is not None:
+            outs.append(o)
+            gouts.append(_leaf(g.contiguous()) if leaf_grads else g.contiguous())
+    return leaves, outs, gouts
+
+
+class EncoderBlockFn(Function):
+    """(x, y, heads, edge_out, *params) -> (x_out, y_out); keeps only (x, y, params)."""
+
+    @staticmethod
+    def forward(ctx, x, y, heads, edge_out, *params):
+        ctx.heads, ctx.edge_out = heads, edge_out
+        ctx.save_for_backward(x, y, *params)
+        ctx.set_materialize_grads(False)
+        with torch.no_grad():
+            xo, yo = block_forward(x, y, params, heads, edge_out)
+        if yo is None:
+            yo = y.new_empty(0)
+            ctx.mark_non_differentiable(yo)
+        return xo, yo
+
+    @staticmethod
+    def backward(ctx, dxo, dyo):
+        x, y, *params = ctx.saved_tensors
+        if not ctx.edge_out:
+            dyo = None
+        if dxo is None and dyo is None:
+            return (None,) * (4 + len(params))
+        outs = EncoderBlockBwdFn.apply(x, y, dxo, dyo, ctx.heads, ctx.edge_out, *params)
+        return (outs[0], outs[1], None, None) + tuple(outs[2:])
+
+
+class EncoderBlockBwdFn(Function):
+    """First-order backward of the block by recomputation; differentiable once more.
+    Gradients of parameters the outputs do not depend on are returned as None (so, as in the
+    reference, ``.grad`` stays None and AdamW leaves those tensors untouched)."""
+
+    @staticmethod
+    def forward(ctx, x, y, dxo, dyo, heads, edge_out, *params):
+        ctx.heads, ctx.edge_out = heads, edge_out
+        ctx.save_for_backward(x, y, dxo, dyo, *params)
+        ctx.set_materialize_grads(False)
+        with torch.enable_grad():
+            leaves, outs, gouts = _recompute(x, y, dxo, dyo, params, heads, edge_out, False)
+            grads = torch.autograd.grad(outs, leaves, gouts, allow_unused=True)
+        return tuple(grads)
+
+    @staticmethod
+    def backward(ctx, *u):
+        x, y, dxo, dyo, *params = ctx.saved_tensors
+        heads, edge_out = ctx.heads, ctx.edge_out
+        with torch.enable_grad():
+            leaves, outs, gouts = _recompute(x, y, dxo, dyo, params, heads, edge_out, True)
+            grads = torch.autograd.grad(outs, leaves, gouts, create_graph=True, allow_unused=True)
+            pairs = [(g, ui) for g, ui in zip(grads, u) if g is not None and ui is not None and g.requires_grad]
+            wrt = leaves + tuple(gouts)
+            if pairs:
+                second = list(torch.autograd.grad([g for g, _ in pairs], wrt,
+                                                  [ui.contiguous() for _, ui in pairs], allow_unused=True))
+            else:
+                second = [None] * len(wrt)
+        n = len(params)
+        tail = second[2 + n:]
+        g_dxo = tail.pop(0) if dxo is not None else None
+        g_dyo = tail.pop(0) if (dyo is not None and edge_out) else None
+        return (second[0], second[1], g_dxo, g_dyo, None, None) + tuple(second[2:2 + n])
+
+
+def encoder_block(x, y, params: Sequence[torch.Tensor], heads: int, edge_out: bool = True):
+    """Checkpointed block used by ``layers.Encoder_Block``."""
+    needs_graph = torch.is_grad_enabled() and (
+        x.requires_grad or y.requires_grad or any(p.requires_grad for p in params))
+    if not needs_graph:
+        return block_forward(x, y, params, heads, edge_out)
+    xo, yo = EncoderBlockFn.apply(x, y, heads, edge_out, *params)
+    return xo, (yo if edge_out else None)

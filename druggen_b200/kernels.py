@@ -1,0 +1,218 @@
+"""Raw (non-autograd) kernel entry points of the encoder hot path.
+
+Every function here is one launch (or a fixed short sequence of launches) of a
+hand-written sm_100a kernel reached through the C-ABI in ``include/druggen_b200.h``.
+Tensors are fp32, contiguous, on one CUDA device; outputs are allocated with the torch
+caching allocator and the launch goes onto torch's current stream.  There is NO CPU or
+eager fallback: a missing ``libdruggen_b200.so`` or a non-CUDA tensor raises.
+
+Shapes use the reference's vocabulary: B molecules, N atoms (``vertexes``), D = ``dim``
+channels; "rows" are flattened node rows [B*N, D] or edge rows [B*N*N, D].
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+# precision of the dense contractions (GEMMs).  Everything else is always fp32.
+#   fp32   : CUDA-core fp32 FMA GEMM (parity mode; bit-for-bit fp32 accumulate)
+#   bf16   : tcgen05 bf16 x bf16 -> fp32 (TMEM accumulators)           -- throughput mode
+#   bf16x3 : tcgen05 three-pass split (hi*hi + hi*lo + lo*hi) -> ~fp32 accuracy
+PRECISIONS = ("fp32", "bf16", "bf16x3")
+_precision = os.environ.get("DRUGGEN_B200_PRECISION", "bf16")
+
+
+def set_precision(p: str) -> None:
+    global _precision
+    if p not in PRECISIONS:
+        raise ValueError(f"precision must be one of {PRECISIONS}, got {p!r}")
+    _precision = p
+
+
+def get_precision() -> str:
+    return _precision
+
+
+class precision:
+    """Context manager: ``with kernels.precision("fp32"): ...``"""
+
+    def __init__(self, p):
+        self.p = p
+
+    def __enter__(self):
+        self.old = get_precision()
+        set_precision(self.p)
+
+    def __exit__(self, *a):
+        set_precision(self.old)
+
+
+_test_backend = None
+
+
+def _install_backend_for_tests(backend) -> None:
+    """tests/ only: swap the launch table for a torch emulation so the autograd wiring can be
+    checked on a box without a GPU.  Never called by product code."""
+    global _test_backend
+    _test_backend = backend
+
+
+def _be():
+    if _test_backend is not None:
+        return _test_backend
+    return _lib.cuda_backend()
+
+
+def _chk(*ts):
+    if _test_backend is not None:
+        return
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("druggen_b200 kernels run on CUDA tensors only (no CPU fallback)")
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"druggen_b200 kernels take fp32 tensors, got {t.dtype}")
+        if not t.is_contiguous():
+            raise RuntimeError("druggen_b200 kernels take contiguous tensors")
+
+
+# ----------------------------------------------------------------------------- dense contractions
+def rows_gemm(a, w, w_is_nk: bool, bias=None, relu: bool = False, gate=None):
+    """out[R,N] = epi(a[R,K] . op(w) + bias).
+
+    w_is_nk: w is [N,K] (nn.Linear layout, out = a w^T) else w is [K,N] (out = a w).
+    relu: clamp at 0.  gate: optional [R,N]; out *= (gate > 0)   (ReLU backward fused).
+    """
+    _chk(a, w, bias, gate)
+    r, k = a.shape
+    n = w.shape[0] if w_is_nk else w.shape[1]
+    assert (w.shape[1] if w_is_nk else w.shape[0]) == k, (a.shape, w.shape, w_is_nk)
+    out = a.new_empty((r, n))
+    if r:
+        _be().rows_gemm(a, w, w_is_nk, bias, relu, gate, out, _precision)
+    return out
+
+
+def gemm_tn(a, b, out=None):
+    """out[M,N] (+)= a[R,M]^T . b[R,N]  -- weight-gradient contraction over rows.
+    ``out`` given => accumulate into it."""
+    _chk(a, b, out)
+    assert a.shape[0] == b.shape[0]
+    acc = out is not None
+    if out is None:
+        out = a.new_zeros((a.shape[1], b.shape[1]))
+    if a.shape[0]:
+        _be().gemm_tn(a, b, out, acc, _precision)
+    return out
+
+
+def colsum(a):
+    """out[N] = sum over rows of a[R,N] (bias gradient)."""
+    _chk(a)
+    out = a.new_zeros((a.shape[1],))
+    if a.shape[0]:
+        _be().colsum(a, out)
+    return out
+
+
+def gate_mul(x, ref):
+    """x * (ref > 0)."""
+    _chk(x, ref)
+    out = torch.empty_like(x)
+    if x.numel():
+        _be().gate_mul(x, ref, out)
+    return out
+
+
+# ----------------------------------------------------------------------------- residual + LayerNorm
+def add_ln_fwd(a, b, gamma, beta, eps: float = 1e-5):
+    """LN(a + b) * gamma + beta over the last dim; b may be None."""
+    _chk(a, b, gamma, beta)
+    out = torch.empty_like(a)
+    if a.numel():
+        _be().add_ln_fwd(a, b, gamma, beta, out, eps)
+    return out
+
+
+def add_ln_bwd(dy, a, b, gamma, eps: float = 1e-5):
+    """-> (dz, dgamma, dbeta) with z = a + b recomputed."""
+    _chk(dy, a, b, gamma)
+    dz = torch.empty_like(a)
+    dgamma = torch.zeros_like(gamma)
+    dbeta = torch.zeros_like(gamma)
+    if a.numel():
+        _be().add_ln_bwd(dy, a, b, gamma, dz, dgamma, dbeta, eps)
+    return dz, dgamma, dbeta
+
+
+def add_ln_bwd_bwd(u, vg, vb, dy, a, b, gamma, eps: float = 1e-5):
+    """Gradient of <u,dz> + <vg,dgamma> + <vb,dbeta> w.r.t. (dy, z, gamma).  vg/vb may be None."""
+    _chk(u, vg, vb, dy, a, b, gamma)
+    g_dy = torch.empty_like(a)
+    g_z = torch.empty_like(a)
+    g_gamma = torch.zeros_like(gamma)
+    if a.numel():
+        _be().add_ln_bwd_bwd(u, vg, vb, dy, a, b, gamma, g_dy, g_z, g_gamma, eps)
+    return g_dy, g_z, g_gamma
+
+
+# ----------------------------------------------------------------------------- edge-modulated scores
+def modulate_fwd(q, k, e, c: float):
+    """A[b,i,j,:] = c * q[b,i,:] * k[b,j,:] * (e^2 + e)[b,i,j,:]   (layers.py:123-125)."""
+    _chk(q, k, e)
+    out = torch.empty_like(e)
+    if e.numel():
+        _be().modulate_fwd(q, k, e, c, out)
+    return out
+
+
+def modulate_bwd(da, q, k, e, c: float):
+    """-> (dq, dk, de)."""
+    _chk(da, q, k, e)
+    dq, dk, de = torch.empty_like(q), torch.empty_like(k), torch.empty_like(e)
+    if e.numel():
+        _be().modulate_bwd(da, q, k, e, c, dq, dk, de)
+    return dq, dk, de
+
+
+def modulate_bwd_bwd(uq, uk, ue, da, q, k, e, c: float):
+    """Gradient of <uq,dq>+<uk,dk>+<ue,de> w.r.t. (da, q, k, e)."""
+    _chk(uq, uk, ue, da, q, k, e)
+    g_da, g_e = torch.empty_like(e), torch.empty_like(e)
+    g_q, g_k = torch.empty_like(q), torch.empty_like(k)
+    if e.numel():
+        _be().modulate_bwd_bwd(uq, uk, ue, da, q, k, e, c, g_da, g_q, g_k, g_e)
+    return g_da, g_q, g_k, g_e
+
+
+# ----------------------------------------------------------------------------- softmax over keys + aggregate
+def softmax_agg_fwd(a, v):
+    """g[b,i,:] = sum_j softmax_j(a[b,i,j,:]) * v[b,j,:]   (layers.py:130-134)."""
+    _chk(a, v)
+    out = torch.empty_like(v)
+    if a.numel():
+        _be().softmax_agg_fwd(a, v, out)
+    return out
+
+
+def softmax_agg_bwd(dg, a, v):
+    """-> (da, dv)."""
+    _chk(dg, a, v)
+    da, dv = torch.empty_like(a), torch.empty_like(v)
+    if a.numel():
+        _be().softmax_agg_bwd(dg, a, v, da, dv)
+    return da, dv
+
+
+def softmax_agg_bwd_bwd(ua, uv, dg, a, v):
+    """Gradient of <ua,da>+<uv,dv> w.r.t. (dg, a, v)."""
+    _chk(ua, uv, dg, a, v)
+    g_dg, g_a, g_v = torch.empty_like(dg), torch.empty_like(a), torch.empty_like(v)
+    if a.numel():
+        _be().softmax_agg_bwd_bwd(ua, uv, dg, a, v, g_dg, g_a, g_v)
+    return g_dg, g_a, g_v

@@ -1,0 +1,121 @@
+"""Host-side mirror of the reference encoder classes (src/model/layers.py) on the B200 kernels.
+
+Same class names, constructor signatures, sub-module / parameter names (so reference
+``state_dict`` checkpoints load unchanged: train.py:250-263, inference.py:135-139) and
+``forward`` signatures; the arithmetic runs in the hand-written kernels of ``csrc/``.
+
+  MLP                 reference layers.py:7-54
+  MHA                 reference layers.py:56-137
+  Encoder_Block       reference layers.py:139-193
+  TransformerEncoder  reference layers.py:195-234
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .block import BLOCK_PARAM_NAMES, encoder_block
+
+
+def _no_train_dropout(module: nn.Module, p: float):
+    if p > 0.0 and module.training:
+        raise NotImplementedError(
+            "druggen_b200: dropout > 0 in training mode is not implemented in the fused encoder "
+            "(the reference default is 0, train.py:419-420); call .eval() or use dropout=0")
+
+
+class MLP(nn.Module):
+    """fc2(relu(fc1(x))); output dropout (layers.py:41-54)."""
+
+    def __init__(self, in_feat, hid_feat=None, out_feat=None, dropout=0.):
+        super().__init__()
+        hid_feat = hid_feat or in_feat
+        out_feat = out_feat or in_feat
+        self.fc1 = nn.Linear(in_feat, hid_feat)
+        self.act = nn.ReLU()
+        self.fc2 = nn.Linear(hid_feat, out_feat)
+        self.droprateout = nn.Dropout(dropout)
+
+    def forward(self, x):
+        _no_train_dropout(self, self.droprateout.p)
+        h = ops.linear(x.contiguous(), self.fc1.weight, self.fc1.bias, relu=True)
+        return ops.linear(h, self.fc2.weight, self.fc2.bias)
+
+
+class MHA(nn.Module):
+    """Edge-modulated per-channel graph attention (layers.py:97-137)."""
+
+    def __init__(self, dim, heads, attention_dropout=0.):
+        super().__init__()
+        assert dim % heads == 0
+        self.heads = heads
+        self.scale = 1. / math.sqrt(dim)   # kept for API parity; unused by the reference too (layers.py:84)
+        self.q = nn.Linear(dim, dim)
+        self.k = nn.Linear(dim, dim)
+        self.v = nn.Linear(dim, dim)
+        self.e = nn.Linear(dim, dim)
+        self.d_k = dim // heads
+        self.out_e = nn.Linear(dim, dim)
+        self.out_n = nn.Linear(dim, dim)
+
+    def forward(self, node, edge):
+        node, edge = node.contiguous(), edge.contiguous()
+        q = ops.linear(node, self.q.weight, self.q.bias)
+        k = ops.linear(node, self.k.weight, self.k.bias)
+        v = ops.linear(node, self.v.weight, self.v.bias)
+        e = ops.linear(edge, self.e.weight, self.e.bias)
+        a = ops.Modulate.apply(q, k, e, 1.0 / math.sqrt(self.d_k))
+        edge_out = ops.linear(a, self.out_e.weight, self.out_e.bias)
+        node_out = ops.linear(ops.SoftmaxAgg.apply(a, v), self.out_n.weight, self.out_n.bias)
+        return node_out, edge_out
+
+
+class Encoder_Block(nn.Module):
+    """ln1 -> MHA -> residuals -> ln3/ln4 -> mlp/mlp2 residual -> ln5/ln6 (layers.py:174-193)."""
+
+    def __init__(self, dim, heads, act, mlp_ratio=4, drop_rate=0.):
+        super().__init__()
+        self.ln1 = nn.LayerNorm(dim)
+        self.attn = MHA(dim, heads, drop_rate)
+        self.ln3 = nn.LayerNorm(dim)
+        self.ln4 = nn.LayerNorm(dim)
+        self.mlp = MLP(dim, dim * mlp_ratio, dim, dropout=drop_rate)
+        self.mlp2 = MLP(dim, dim * mlp_ratio, dim, dropout=drop_rate)
+        self.ln5 = nn.LayerNorm(dim)
+        self.ln6 = nn.LayerNorm(dim)
+        self._drop = drop_rate
+        self._plist = None
+
+    def _params(self):
+        if self._plist is None:
+            named = dict(self.named_parameters())
+            self._plist = [named[n] for n in BLOCK_PARAM_NAMES]
+        return self._plist
+
+    def _apply(self, fn, *a, **k):          # .to()/.cuda() may replace Parameter objects
+        self._plist = None
+        return super()._apply(fn, *a, **k)
+
+    def forward(self, x, y, _edge_out: bool = True):
+        _no_train_dropout(self, self._drop)
+        return encoder_block(x.contiguous(), y.contiguous(), self._params(), self.attn.heads, _edge_out)
+
+
+class TransformerEncoder(nn.Module):
+    """``depth`` encoder blocks in sequence (layers.py:221-234)."""
+
+    def __init__(self, dim, depth, heads, act, mlp_ratio=4, drop_rate=0.1):
+        super().__init__()
+        self.Encoder_Blocks = nn.ModuleList([
+            Encoder_Block(dim, heads, act, mlp_ratio, drop_rate) for _ in range(depth)])
+        # set by Discriminator: its last block's edge output has no consumer (models.py:202-207)
+        self._discard_final_edge = False
+
+    def forward(self, x, y):
+        last = len(self.Encoder_Blocks) - 1
+        for i, block in enumerate(self.Encoder_Blocks):
+            x, y = block(x, y, not (self._discard_final_edge and i == last))
+        return x, y

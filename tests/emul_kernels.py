@@ -1,0 +1,137 @@
+"""TEST INFRASTRUCTURE ONLY: torch emulation of the C-ABI launch table.
+
+Each method states, in plain torch, exactly what the matching CUDA kernel in
+druggen_b200/csrc computes (including the hand-derived second-order formulas), so that
+  * on a CPU box the autograd wiring in druggen_b200/ops.py + block.py can be checked with
+    gradcheck / gradgradcheck and against the oracle, and
+  * on the GPU box each CUDA kernel can be unit-tested against its emulation.
+It is installed with kernels._install_backend_for_tests(); the product never uses it.
+"""
+import torch
+
+
+def _bf16r(t):
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
+class EmulBackend:
+    def __init__(self, emulate_bf16: bool = False):
+        self.emulate_bf16 = emulate_bf16
+
+    def _mm(self, a, b, prec):
+        if self.emulate_bf16 and prec == "bf16":
+            return _bf16r(a) @ _bf16r(b)
+        return a @ b
+
+    # ---- dense
+    def rows_gemm(self, a, w, w_is_nk, bias, relu, gate, out, prec):
+        r = self._mm(a, w.t() if w_is_nk else w, prec)
+        if bias is not None:
+            r = r + bias
+        if relu:
+            r = torch.relu(r)
+        if gate is not None:
+            r = r * (gate > 0).to(r.dtype)
+        out.copy_(r)
+
+    def gemm_tn(self, a, b, out, accumulate, prec):
+        r = self._mm(a.t(), b, prec)
+        if accumulate:
+            out.add_(r)
+        else:
+            out.copy_(r)
+
+    def colsum(self, a, out):
+        out.copy_(a.sum(0))
+
+    def gate_mul(self, x, ref, out):
+        out.copy_(x * (ref > 0).to(x.dtype))
+
+    # ---- residual + layernorm
+    @staticmethod
+    def _stats(a, b, eps):
+        z = a if b is None else a + b
+        mu = z.mean(-1, keepdim=True)
+        var = ((z - mu) ** 2).mean(-1, keepdim=True)
+        r = torch.rsqrt(var + eps)
+        return (z - mu) * r, r
+
+    @staticmethod
+    def _proj(w, xh):
+        """P(w) = w - mean(w) - xh * mean(w * xh)  (symmetric, per row)."""
+        return w - w.mean(-1, keepdim=True) - xh * (w * xh).mean(-1, keepdim=True)
+
+    def add_ln_fwd(self, a, b, gamma, beta, out, eps):
+        xh, _ = self._stats(a, b, eps)
+        out.copy_(xh * gamma + beta)
+
+    def add_ln_bwd(self, dy, a, b, gamma, dz, dgamma, dbeta, eps):
+        xh, r = self._stats(a, b, eps)
+        dz.copy_(r * self._proj(dy * gamma, xh))
+        d = a.shape[-1]
+        dgamma.copy_((dy * xh).reshape(-1, d).sum(0))
+        dbeta.copy_(dy.reshape(-1, d).sum(0))
+
+    def add_ln_bwd_bwd(self, u, vg, vb, dy, a, b, gamma, g_dy, g_z, g_gamma, eps):
+        xh, r = self._stats(a, b, eps)
+        gh = dy * gamma
+        pu = self._proj(u, xh)
+        pg = self._proj(gh, xh)
+        c2 = (gh * xh).mean(-1, keepdim=True)
+        am = (u * pg).mean(-1, keepdim=True)
+        bm = (u * xh).mean(-1, keepdim=True)
+        gdy = gamma * r * pu
+        gz = -(r * r) * (am * xh + c2 * pu + bm * pg)
+        if vg is not None:
+            gdy = gdy + vg * xh
+            gz = gz + r * self._proj(vg * dy, xh)
+        if vb is not None:
+            gdy = gdy + vb
+        g_dy.copy_(gdy)
+        g_z.copy_(gz)
+        g_gamma.copy_((dy * r * pu).reshape(-1, a.shape[-1]).sum(0))
+
+    # ---- modulate
+    def modulate_fwd(self, q, k, e, c, out):
+        out.copy_(c * q[:, :, None, :] * k[:, None, :, :] * (e * e + e))
+
+    def modulate_bwd(self, da, q, k, e, c, dq, dk, de):
+        qi, kj = q[:, :, None, :], k[:, None, :, :]
+        phi = e * e + e
+        de.copy_(da * c * qi * kj * (2 * e + 1))
+        dq.copy_((c * da * phi * kj).sum(2))
+        dk.copy_((c * da * phi * qi).sum(1))
+
+    def modulate_bwd_bwd(self, uq, uk, ue, da, q, k, e, c, g_da, g_q, g_k, g_e):
+        qi, kj = q[:, :, None, :], k[:, None, :, :]
+        uqi, ukj = uq[:, :, None, :], uk[:, None, :, :]
+        phi, dphi = e * e + e, 2 * e + 1
+        mix = kj * uqi + qi * ukj
+        g_da.copy_(c * (phi * mix + qi * kj * dphi * ue))
+        g_e.copy_(c * da * (dphi * mix + 2 * qi * kj * ue))
+        g_q.copy_((c * da * (phi * ukj + kj * dphi * ue)).sum(2))
+        g_k.copy_((c * da * (phi * uqi + qi * dphi * ue)).sum(1))
+
+    # ---- softmax over keys + aggregate
+    def softmax_agg_fwd(self, a, v, out):
+        out.copy_((torch.softmax(a, dim=2) * v[:, None, :, :]).sum(2))
+
+    def softmax_agg_bwd(self, dg, a, v, da, dv):
+        p = torch.softmax(a, dim=2)
+        vj = v[:, None, :, :]
+        g = (p * vj).sum(2, keepdim=True)
+        dgi = dg[:, :, None, :]
+        da.copy_(p * dgi * (vj - g))
+        dv.copy_((p * dgi).sum(1))
+
+    def softmax_agg_bwd_bwd(self, ua, uv, dg, a, v, g_dg, g_a, g_v):
+        p = torch.softmax(a, dim=2)
+        vj, uvj = v[:, None, :, :], uv[:, None, :, :]
+        g = (p * vj).sum(2, keepdim=True)
+        dgi = dg[:, :, None, :]
+        w = ua * (vj - g) + uvj
+        wbar = (p * w).sum(2, keepdim=True)
+        m = (p * ua).sum(2, keepdim=True)
+        g_dg.copy_(wbar.squeeze(2))
+        g_a.copy_(dgi * p * (w - wbar - m * (vj - g)))
+        g_v.copy_((dgi * p * (ua - m)).sum(1))

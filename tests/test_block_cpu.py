@@ -1,0 +1,167 @@
+"""Host logic (block composition, checkpointed block Functions, module API) on the torch
+emulation of the kernel table, checked against the oracle and the reference golden vectors.
+CPU only; the CUDA kernels themselves are covered by the -m gpu tests."""
+import pytest
+import torch
+
+import druggen_b200 as dg
+from druggen_b200 import kernels
+from druggen_b200.block import BLOCK_PARAM_NAMES, block_forward, encoder_block
+from conftest import load_golden, rel_l2, state_from
+from emul_kernels import EmulBackend
+from oracle import encoder_oracle as orc
+
+
+@pytest.fixture(autouse=True)
+def emul():
+    kernels._install_backend_for_tests(EmulBackend())
+    yield
+    kernels._install_backend_for_tests(None)
+
+
+def _block_params(dtype=torch.float64, seed=0, d=128, r=3):
+    g = torch.Generator().manual_seed(seed)
+    p = {}
+    for n in BLOCK_PARAM_NAMES:
+        if n.startswith("ln"):
+            shape, scale, shift = (d,), 0.1, (1.0 if n.endswith("weight") else 0.0)
+        elif "fc1.weight" in n:
+            shape, scale, shift = (r * d, d), d ** -0.5, 0.0
+        elif "fc1.bias" in n:
+            shape, scale, shift = (r * d,), 0.1, 0.0
+        elif "fc2.weight" in n:
+            shape, scale, shift = (d, r * d), (r * d) ** -0.5, 0.0
+        elif n.endswith("weight"):
+            shape, scale, shift = (d, d), d ** -0.5, 0.0
+        else:
+            shape, scale, shift = (d,), 0.1, 0.0
+        p[n] = (torch.randn(shape, generator=g, dtype=dtype) * scale + shift).requires_grad_(True)
+    return p
+
+
+@pytest.mark.parametrize("edge_out", [True, False])
+def test_block_first_and_second_order_vs_oracle(edge_out):
+    """block_forward and the recompute-checkpointed EncoderBlockFn give the oracle's outputs,
+    gradients and gradient-penalty-style second-order gradients (fp64)."""
+    d, n, b, heads = 32, 4, 2, 4
+    p = _block_params(d=d)
+    g = torch.Generator().manual_seed(5)
+    x0 = torch.randn(b, n, d, generator=g, dtype=torch.float64)
+    y0 = torch.randn(b, n, n, d, generator=g, dtype=torch.float64)
+    wx = torch.randn(b, n, d, generator=g, dtype=torch.float64)
+    wy = torch.randn(b, n, n, d, generator=g, dtype=torch.float64)
+
+    def run(kind):
+        x, y = x0.clone().requires_grad_(True), y0.clone().requires_grad_(True)
+        pp = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
+        if kind == "oracle":
+            xo, yo = orc.block_forward(x, y, {"blk." + k: v for k, v in pp.items()}, "blk.", heads)
+        elif kind == "prim":
+            xo, yo = block_forward(x, y, [pp[k] for k in BLOCK_PARAM_NAMES], heads, edge_out)
+        else:
+            xo, yo = encoder_block(x, y, [pp[k] for k in BLOCK_PARAM_NAMES], heads, edge_out)
+        out = (xo * wx).sum() + ((yo * wy).sum() if edge_out else 0.0)
+        gx, gy = torch.autograd.grad(out, [x, y], create_graph=True)
+        pen = ((torch.cat([gx.reshape(b, -1), gy.reshape(b, -1)], 1).norm(2, dim=1) - 1) ** 2).mean()
+        total = out + 3.0 * pen
+        total.backward()
+        return xo, yo, gx, gy, x.grad, y.grad, {k: v.grad for k, v in pp.items()}
+
+    ref = run("oracle")
+    for kind in ("prim", "ckpt"):
+        got = run(kind)
+        assert rel_l2(got[0], ref[0]) < 1e-10
+        if edge_out:
+            assert rel_l2(got[1], ref[1]) < 1e-10
+        for i in (2, 3, 4, 5):
+            assert rel_l2(got[i], ref[i]) < 1e-9, (kind, i)
+        for k in BLOCK_PARAM_NAMES:
+            if got[6][k] is None:      # parameter with no consumer (edge_out=False): reference grad is 0
+                assert not edge_out and (ref[6][k] is None or float(ref[6][k].abs().max()) == 0.0), k
+            else:
+                assert rel_l2(got[6][k], ref[6][k]) < 1e-8, (kind, k)
+
+
+def test_encoder_forward_golden_cfg1():
+    g = load_golden("enc_fwd_cfg1.npz")
+    enc = dg.TransformerEncoder(dim=128, depth=1, heads=8, act=None, mlp_ratio=3, drop_rate=0.0)
+    enc.load_state_dict(state_from(g, "w::"))          # reference state-dict keys load unchanged
+    with torch.no_grad():
+        xo, yo = enc(torch.from_numpy(g["x"]), torch.from_numpy(g["y"]))
+    assert rel_l2(xo, g["x_out"]) < 2e-5 and rel_l2(yo, g["y_out"]) < 2e-5
+    assert yo.is_contiguous() and xo.is_contiguous()
+
+
+def test_encoder_grads_golden():
+    g = load_golden("enc_grad.npz")
+    enc = dg.TransformerEncoder(dim=128, depth=2, heads=4, act=None, mlp_ratio=3, drop_rate=0.0)
+    enc.load_state_dict(state_from(g, "w::"))
+    x = torch.from_numpy(g["x"]).requires_grad_(True)
+    y = torch.from_numpy(g["y"]).requires_grad_(True)
+    xo, yo = enc(x, y)
+    ((xo * torch.from_numpy(g["wx"])).sum() + (yo * torch.from_numpy(g["wy"])).sum()).backward()
+    assert rel_l2(x.grad, g["dx"]) < 1e-4 and rel_l2(y.grad, g["dy"]) < 1e-4
+    for k, v in enc.named_parameters():
+        assert rel_l2(v.grad, g["g::" + k]) < 1e-4, k
+
+
+def _models(g):
+    n, m_dim, b_dim = int(g["n"]), int(g["m_dim"]), int(g["b_dim"])
+    G = dg.Generator("relu", n, b_dim, m_dim, 0.0, dim=128, depth=int(g["depth"]), heads=int(g["heads"]), mlp_ratio=3)
+    D = dg.Discriminator("relu", n, b_dim, m_dim, 0.0, dim=128, depth=int(g["depth"]), heads=int(g["heads"]), mlp_ratio=3)
+    G.load_state_dict(state_from(g, "wG::"))
+    D.load_state_dict(state_from(g, "wD::"))
+    return G, D
+
+
+def test_gan_losses_golden_with_unchanged_loss_logic():
+    """The GAN step of train.py:351-384 (losses restated in oracle, run ON OUR modules) reproduces
+    the reference's losses and every gradient, including the gradient-penalty double backward and
+    the None-gradient set of the Discriminator's dead last-block edge parameters."""
+    g = load_golden("gan_step.npz")
+    G, D = _models(g)
+    t = {k: torch.from_numpy(g[k]) for k in ("drug_a", "drug_x", "mol_a", "mol_x", "eps_edge", "eps_node")}
+    d_loss = orc.discriminator_loss(G, D, t["drug_a"], t["drug_x"], t["mol_a"], t["mol_x"],
+                                    t["eps_edge"], t["eps_node"], float(g["lambda_gp"]))
+    d_loss.backward()
+    assert abs(d_loss.item() - float(g["d_loss"])) < 1e-4 * max(1.0, abs(float(g["d_loss"])))
+    for k, v in D.named_parameters():
+        gold = g["gD_D::" + k]
+        if v.grad is None:
+            assert float(abs(gold).max()) == 0.0, k
+        else:
+            assert rel_l2(v.grad, gold) < 2e-3, k
+    assert all(p.grad is None for p in G.parameters())   # fake samples are detached (loss.py:62)
+    D.zero_grad(set_to_none=True)
+    g_loss = orc.generator_loss(G, D, t["mol_a"], t["mol_x"])
+    g_loss.backward()
+    assert abs(g_loss.item() - float(g["g_loss"])) < 1e-4 * max(1.0, abs(float(g["g_loss"])))
+    for k, v in G.named_parameters():
+        assert rel_l2(v.grad, g["gG_G::" + k]) < 1e-3, k
+    dead = [k for k, v in D.named_parameters() if v.grad is None]
+    assert sorted(dead) == sorted(k for k in dict(D.named_parameters())
+                                  if float(abs(g["gG_D::" + k]).max()) == 0.0)
+
+
+def test_decode_bit_exact_away_from_ties():
+    g = load_golden("gan_step.npz")
+    G, _ = _models(g)
+    with torch.inference_mode():
+        _, _, ns, es = G(torch.from_numpy(g["mol_a"]), torch.from_numpy(g["mol_x"]))
+    safe_n, safe_e = torch.from_numpy(g["node_gap"]) > 1e-4, torch.from_numpy(g["edge_gap"]) > 1e-4
+    assert torch.equal(ns.argmax(-1)[safe_n], torch.from_numpy(g["node_argmax"])[safe_n])
+    assert torch.equal(es.argmax(-1)[safe_e], torch.from_numpy(g["edge_argmax"])[safe_e])
+
+
+def test_product_refuses_cpu_without_test_backend():
+    kernels._install_backend_for_tests(None)
+    with pytest.raises(RuntimeError):
+        dg.TransformerEncoder(128, 1, 8, None, 3, 0.0)(torch.zeros(1, 2, 128), torch.zeros(1, 2, 2, 128))
+
+
+def test_training_dropout_raises():
+    enc = dg.TransformerEncoder(128, 1, 8, None, 3, 0.1)
+    with pytest.raises(NotImplementedError):
+        enc(torch.zeros(1, 2, 128), torch.zeros(1, 2, 2, 128))
+    enc.eval()
+    enc(torch.zeros(1, 2, 128), torch.zeros(1, 2, 2, 128))

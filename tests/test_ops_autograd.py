@@ -1,0 +1,54 @@
+"""Autograd wiring of druggen_b200/ops.py (first and second order) checked in fp64 on the torch
+emulation of the kernel table -- validates the hand-derived second-order formulas that the
+CUDA kernels implement.  CPU only."""
+import pytest
+import torch
+from torch.autograd import gradcheck, gradgradcheck
+
+from druggen_b200 import kernels, ops
+from emul_kernels import EmulBackend
+
+
+@pytest.fixture(autouse=True)
+def emul():
+    kernels._install_backend_for_tests(EmulBackend())
+    yield
+    kernels._install_backend_for_tests(None)
+
+
+def rnd(*shape, seed=0):
+    g = torch.Generator().manual_seed(seed + sum(shape))
+    return torch.randn(*shape, generator=g, dtype=torch.float64).requires_grad_(True)
+
+
+def both(fn, inputs):
+    assert gradcheck(fn, inputs, eps=1e-6, atol=1e-6)
+    assert gradgradcheck(fn, inputs, eps=1e-6, atol=1e-6)
+
+
+def test_linear():
+    both(lambda x, w, b: ops.Linear.apply(x, w, b, False), (rnd(5, 6), rnd(4, 6), rnd(4)))
+
+
+def test_linear_relu():
+    x = rnd(5, 6)
+    both(lambda x, w, b: ops.Linear.apply(x, w, b, True), (x, rnd(4, 6), rnd(4)))
+
+
+def test_rows_gemm_and_tn():
+    both(lambda a, w: ops.RowsGemm.apply(a, w, True), (rnd(5, 6), rnd(4, 6)))
+    both(lambda a, w: ops.RowsGemm.apply(a, w, False), (rnd(5, 6), rnd(6, 4)))
+    both(lambda a, b: ops.GemmTN.apply(a, b), (rnd(7, 3), rnd(7, 4)))
+
+
+def test_add_ln():
+    both(lambda a, b, g, be: ops.AddLN.apply(a, b, g, be), (rnd(4, 8), rnd(4, 8, seed=1), rnd(8), rnd(8, seed=2)))
+    both(lambda a, g, be: ops.AddLN.apply(a, None, g, be), (rnd(4, 8), rnd(8), rnd(8, seed=2)))
+
+
+def test_modulate():
+    both(lambda q, k, e: ops.Modulate.apply(q, k, e, 0.25), (rnd(2, 3, 4), rnd(2, 3, 4, seed=1), rnd(2, 3, 3, 4)))
+
+
+def test_softmax_agg():
+    both(lambda a, v: ops.SoftmaxAgg.apply(a, v), (rnd(2, 3, 3, 4), rnd(2, 3, 4)))

@@ -1,5 +1,140 @@
-"""ctypes loader placeholder (filled in with the C-ABI)."""
+"""ctypes binding of libdruggen_b200.so (the C-ABI declared in include/druggen_b200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` (``make -C druggen_b200/csrc``).
+There is no fallback: if the library is missing or a launch is rejected this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdruggen_b200.so")
+PREC = {"fp32": 0, "bf16": 1, "bf16x3": 2}
+
+_P, _LL, _I, _F = C.c_void_p, C.c_longlong, C.c_int, C.c_float
+
+# name -> argument ctypes (every entry returns int); mirrors include/druggen_b200.h
+SIGNATURES = {
+    "dg_rows_gemm": [_P, _P, _I, _P, _I, _P, _P, _LL, _I, _I, _I, _P],
+    "dg_gemm_tn": [_P, _P, _P, _LL, _I, _I, _I, _P],
+    "dg_colsum": [_P, _P, _LL, _I, _P],
+    "dg_gate_mul": [_P, _P, _P, _LL, _P],
+    "dg_add_ln_fwd": [_P, _P, _P, _P, _P, _LL, _I, _F, _P],
+    "dg_add_ln_bwd": [_P, _P, _P, _P, _P, _P, _P, _LL, _I, _F, _P],
+    "dg_add_ln_bwd_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _F, _P],
+    "dg_modulate_fwd": [_P, _P, _P, _F, _P, _I, _I, _I, _P],
+    "dg_modulate_bwd": [_P, _P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _P],
+    "dg_modulate_bwd_bwd": [_P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _I, _I, _I, _P],
+    "dg_softmax_agg_fwd": [_P, _P, _P, _I, _I, _I, _P],
+    "dg_softmax_agg_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "dg_softmax_agg_bwd_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+}
+INFO_SYMBOLS = ("dg_abi_version", "dg_last_error", "dg_has_tcgen05")
+
+_lib = None
+_backend = None
 
 
-def cuda_backend():
-    raise RuntimeError("libdruggen_b200.so is not built; run `python -c 'import __graft_entry__ as g; g.build()'`")
+def load():
+    """dlopen the library and type every symbol (no device work)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `make -C druggen_b200/csrc` "
+                "(or __graft_entry__.build()); druggen_b200 has no CPU / eager fallback")
+        lib = C.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes, fn.restype = args, _I
+        lib.dg_abi_version.restype = _I
+        lib.dg_has_tcgen05.restype = _I
+        lib.dg_last_error.restype = C.c_char_p
+        if lib.dg_abi_version() != 1:
+            raise RuntimeError("libdruggen_b200.so ABI version mismatch")
+        _lib = lib
+    return _lib
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class CudaBackend:
+    """Launch table used by kernels.py: torch tensors -> raw pointers + current stream."""
+
+    def __init__(self, lib):
+        self.lib = lib
+        self.launches = 0          # kernel launches issued through this table (bench.py reports it)
+
+    def _call(self, name, *args):
+        self.launches += 1
+        rc = getattr(self.lib, name)(*args, torch.cuda.current_stream().cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f"{name} rejected: {self.lib.dg_last_error().decode()}")
+
+    def rows_gemm(self, a, w, w_is_nk, bias, relu, gate, out, prec):
+        r, k = a.shape
+        self._call("dg_rows_gemm", _ptr(a), _ptr(w), int(w_is_nk), _ptr(bias), int(relu), _ptr(gate), _ptr(out),
+                   r, k, out.shape[1], PREC[prec])
+
+    def gemm_tn(self, a, b, out, accumulate, prec):
+        self._call("dg_gemm_tn", _ptr(a), _ptr(b), _ptr(out), a.shape[0], a.shape[1], b.shape[1], PREC[prec])
+
+    def colsum(self, a, out):
+        self._call("dg_colsum", _ptr(a), _ptr(out), a.shape[0], a.shape[1])
+
+    def gate_mul(self, x, ref, out):
+        self._call("dg_gate_mul", _ptr(x), _ptr(ref), _ptr(out), x.numel())
+
+    def add_ln_fwd(self, a, b, gamma, beta, out, eps):
+        d = a.shape[-1]
+        self._call("dg_add_ln_fwd", _ptr(a), _ptr(b), _ptr(gamma), _ptr(beta), _ptr(out), a.numel() // d, d, eps)
+
+    def add_ln_bwd(self, dy, a, b, gamma, dz, dgamma, dbeta, eps):
+        d = a.shape[-1]
+        self._call("dg_add_ln_bwd", _ptr(dy), _ptr(a), _ptr(b), _ptr(gamma), _ptr(dz), _ptr(dgamma), _ptr(dbeta),
+                   a.numel() // d, d, eps)
+
+    def add_ln_bwd_bwd(self, u, vg, vb, dy, a, b, gamma, g_dy, g_z, g_gamma, eps):
+        d = a.shape[-1]
+        self._call("dg_add_ln_bwd_bwd", _ptr(u), _ptr(vg), _ptr(vb), _ptr(dy), _ptr(a), _ptr(b), _ptr(gamma),
+                   _ptr(g_dy), _ptr(g_z), _ptr(g_gamma), a.numel() // d, d, eps)
+
+    def modulate_fwd(self, q, k, e, c, out):
+        b, n, d = q.shape
+        self._call("dg_modulate_fwd", _ptr(q), _ptr(k), _ptr(e), c, _ptr(out), b, n, d)
+
+    def modulate_bwd(self, da, q, k, e, c, dq, dk, de):
+        b, n, d = q.shape
+        self._call("dg_modulate_bwd", _ptr(da), _ptr(q), _ptr(k), _ptr(e), c, _ptr(dq), _ptr(dk), _ptr(de), b, n, d)
+
+    def modulate_bwd_bwd(self, uq, uk, ue, da, q, k, e, c, g_da, g_q, g_k, g_e):
+        b, n, d = q.shape
+        self._call("dg_modulate_bwd_bwd", _ptr(uq), _ptr(uk), _ptr(ue), _ptr(da), _ptr(q), _ptr(k), _ptr(e), c,
+                   _ptr(g_da), _ptr(g_q), _ptr(g_k), _ptr(g_e), b, n, d)
+
+    def softmax_agg_fwd(self, a, v, out):
+        b, n, d = v.shape
+        self._call("dg_softmax_agg_fwd", _ptr(a), _ptr(v), _ptr(out), b, n, d)
+
+    def softmax_agg_bwd(self, dg, a, v, da, dv):
+        b, n, d = v.shape
+        self._call("dg_softmax_agg_bwd", _ptr(dg), _ptr(a), _ptr(v), _ptr(da), _ptr(dv), b, n, d)
+
+    def softmax_agg_bwd_bwd(self, ua, uv, dg, a, v, g_dg, g_a, g_v):
+        b, n, d = v.shape
+        self._call("dg_softmax_agg_bwd_bwd", _ptr(ua), _ptr(uv), _ptr(dg), _ptr(a), _ptr(v), _ptr(g_dg), _ptr(g_a),
+                   _ptr(g_v), b, n, d)
+
+
+def cuda_backend() -> CudaBackend:
+    global _backend
+    if _backend is None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("druggen_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        _backend = CudaBackend(load())
+    return _backend

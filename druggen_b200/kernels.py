@@ -174,7 +174,7 @@ def modulate_fwd(q, k, e, c: float):
 def modulate_bwd(da, q, k, e, c: float):
     """-> (dq, dk, de)."""
     _chk(da, q, k, e)
-    dq, dk, de = torch.empty_like(q), torch.empty_like(k), torch.empty_like(e)
+    dq, dk, de = torch.empty_like(q), torch.zeros_like(k), torch.empty_like(e)
     if e.numel():
         _be().modulate_bwd(da, q, k, e, c, dq, dk, de)
     return dq, dk, de
@@ -184,7 +184,7 @@ def modulate_bwd_bwd(uq, uk, ue, da, q, k, e, c: float):
     """Gradient of <uq,dq>+<uk,dk>+<ue,de> w.r.t. (da, q, k, e)."""
     _chk(uq, uk, ue, da, q, k, e)
     g_da, g_e = torch.empty_like(e), torch.empty_like(e)
-    g_q, g_k = torch.empty_like(q), torch.empty_like(k)
+    g_q, g_k = torch.empty_like(q), torch.zeros_like(k)
     if e.numel():
         _be().modulate_bwd_bwd(uq, uk, ue, da, q, k, e, c, g_da, g_q, g_k, g_e)
     return g_da, g_q, g_k, g_e
@@ -203,7 +203,7 @@ def softmax_agg_fwd(a, v):
 def softmax_agg_bwd(dg, a, v):
     """-> (da, dv)."""
     _chk(dg, a, v)
-    da, dv = torch.empty_like(a), torch.empty_like(v)
+    da, dv = torch.empty_like(a), torch.zeros_like(v)
     if a.numel():
         _be().softmax_agg_bwd(dg, a, v, da, dv)
     return da, dv
@@ -212,7 +212,7 @@ def softmax_agg_bwd(dg, a, v):
 def softmax_agg_bwd_bwd(ua, uv, dg, a, v):
     """Gradient of <ua,da>+<uv,dv> w.r.t. (dg, a, v)."""
     _chk(ua, uv, dg, a, v)
-    g_dg, g_a, g_v = torch.empty_like(dg), torch.empty_like(a), torch.empty_like(v)
+    g_dg, g_a, g_v = torch.empty_like(dg), torch.empty_like(a), torch.zeros_like(v)
     if a.numel():
         _be().softmax_agg_bwd_bwd(ua, uv, dg, a, v, g_dg, g_a, g_v)
     return g_dg, g_a, g_v

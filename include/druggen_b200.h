@@ -1,0 +1,92 @@
+/* druggen_b200 -- C-ABI of the B200 (sm_100a) graph-transformer encoder hot path.
+ *
+ * The reference (HUBioDataLab/DrugGEN) has no FFI of its own: its hot path is reached through the
+ * Python class API of src/model/layers.py.  Each entry point below replaces the ATen kernels that
+ * one group of reference lines dispatches; the file:line it replaces is cited per function.
+ * INTEGRATION.md shows the ctypes binding (druggen_b200/_lib.py) a maintainer drops in.
+ *
+ * Conventions
+ *   - all tensors are fp32, row-major, contiguous, device pointers on the current device;
+ *   - the caller owns every buffer (outputs and accumulators included); kernels never allocate;
+ *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous, no hidden syncs;
+ *   - return value 0 = launched; non-zero = rejected (dg_last_error() has the reason), nothing ran;
+ *   - B molecules, N atoms per molecule ("vertexes"), D channels ("dim"); "rows" are the flattened
+ *     node rows [B*N] or edge rows [B*N*N];
+ *   - `prec` selects the arithmetic of the dense contractions only:
+ *       DG_PREC_FP32   CUDA-core fp32 FMA                     (parity mode)
+ *       DG_PREC_BF16   tcgen05.mma kind::f16 bf16 x bf16 -> fp32 in TMEM   (throughput mode)
+ *       DG_PREC_BF16X3 tcgen05 3-pass split bf16 (hi*hi+hi*lo+lo*hi) -> fp32-class accuracy
+ *     every other operation (LayerNorm, softmax, modulation, reductions) is fp32 in all modes.
+ */
+#ifndef DRUGGEN_B200_H
+#define DRUGGEN_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DG_ABI_VERSION 1
+#define DG_PREC_FP32 0
+#define DG_PREC_BF16 1
+#define DG_PREC_BF16X3 2
+
+int dg_abi_version(void);
+/* Thread-local text of the last rejected call. */
+const char* dg_last_error(void);
+/* 1 when the tcgen05 paths were compiled in and the current device is sm_100. */
+int dg_has_tcgen05(void);
+
+/* ---- dense contractions ------------------------------------------------------------------ */
+/* out[R,N] = epi(a[R,K] . op(w) + bias);  w is [N,K] when w_is_nk (nn.Linear layout) else [K,N].
+ * epi: optional ReLU, optional gate: out *= (gate[R,N] > 0).
+ * Replaces nn.Linear forward / addmm (layers.py:51,53,111-113,116,127,135) and the dgrad `mm`s. */
+int dg_rows_gemm(const float* a, const float* w, int w_is_nk, const float* bias, int relu,
+                 const float* gate, float* out, long long R, int K, int N, int prec, void* stream);
+/* out[M,N] += a[R,M]^T . b[R,N]   (split over rows, accumulated atomically: zero `out` first
+ * unless accumulating).  Replaces the weight-gradient `mm`s of autograd. */
+int dg_gemm_tn(const float* a, const float* b, float* out, long long R, int M, int N, int prec,
+               void* stream);
+/* out[N] += column sums of a[R,N]   (bias gradients). */
+int dg_colsum(const float* a, float* out, long long R, int N, void* stream);
+/* out = x * (ref > 0), n elements   (threshold_backward of layers.py:52). */
+int dg_gate_mul(const float* x, const float* ref, float* out, long long n, void* stream);
+
+/* ---- residual + LayerNorm (eps inside the sqrt, affine) : layers.py:185,187-192 -------------- */
+/* out = LN(a + b) * gamma + beta over D; b may be NULL. */
+int dg_add_ln_fwd(const float* a, const float* b, const float* gamma, const float* beta, float* out,
+                  long long R, int D, float eps, void* stream);
+/* dz[R,D]; dgamma[D] += , dbeta[D] +=   (z = a + b recomputed). */
+int dg_add_ln_bwd(const float* dy, const float* a, const float* b, const float* gamma, float* dz,
+                  float* dgamma, float* dbeta, long long R, int D, float eps, void* stream);
+/* Second order: gradient of <u,dz> + <vg,dgamma> + <vb,dbeta> w.r.t. dy, z, gamma.
+ * vg, vb may be NULL.  g_gamma[D] += . */
+int dg_add_ln_bwd_bwd(const float* u, const float* vg, const float* vb, const float* dy, const float* a,
+                      const float* b, const float* gamma, float* g_dy, float* g_z, float* g_gamma,
+                      long long R, int D, float eps, void* stream);
+
+/* ---- edge-modulated scores : layers.py:119-125 ---------------------------------------------- */
+/* A[b,i,j,:] = c * q[b,i,:] * k[b,j,:] * (e^2 + e)[b,i,j,:] */
+int dg_modulate_fwd(const float* q, const float* k, const float* e, float c, float* out, int B, int N, int D,
+                    void* stream);
+/* de written; dq, dk += (zero first). */
+int dg_modulate_bwd(const float* da, const float* q, const float* k, const float* e, float c, float* dq,
+                    float* dk, float* de, int B, int N, int D, void* stream);
+/* g_da, g_e written; g_q, g_k += (zero first). */
+int dg_modulate_bwd_bwd(const float* uq, const float* uk, const float* ue, const float* da, const float* q,
+                        const float* k, const float* e, float c, float* g_da, float* g_q, float* g_k,
+                        float* g_e, int B, int N, int D, void* stream);
+
+/* ---- softmax over key atoms + value aggregation : layers.py:130-134 ------------------------- */
+/* g[b,i,:] = sum_j softmax_j(a[b,i,j,:]) * v[b,j,:] */
+int dg_softmax_agg_fwd(const float* a, const float* v, float* g, int B, int N, int D, void* stream);
+/* da written; dv += (zero first). */
+int dg_softmax_agg_bwd(const float* dg, const float* a, const float* v, float* da, float* dv, int B, int N,
+                       int D, void* stream);
+/* g_dg, g_a written; g_v += (zero first). */
+int dg_softmax_agg_bwd_bwd(const float* ua, const float* uv, const float* dg, const float* a, const float* v,
+                           float* g_dg, float* g_a, float* g_v, int B, int N, int D, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRUGGEN_B200_H */

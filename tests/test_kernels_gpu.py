@@ -1,0 +1,126 @@
+"""Each CUDA kernel (through the C-ABI) against its plain-torch statement (tests/emul_kernels.py,
+run on the same device in fp64 where it matters).  Covers ragged row counts, N in {1, 9, 45},
+optional operands, and the atomically-accumulated outputs."""
+import pytest
+import torch
+
+from druggen_b200 import kernels as K
+from emul_kernels import EmulBackend
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+EM = EmulBackend()
+
+
+def rnd(dev, *shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed + len(shape) * 1000 + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(dev)
+
+
+@pytest.mark.parametrize("prec", ["fp32"])
+@pytest.mark.parametrize("R,Kd,Nd", [(1, 128, 128), (257, 128, 384), (1000, 384, 128), (2025 * 3, 128, 128), (77, 64, 32)])
+def test_rows_gemm(cuda_dev, prec, R, Kd, Nd):
+    a, bias = rnd(cuda_dev, R, Kd), rnd(cuda_dev, Nd, seed=3)
+    gate = rnd(cuda_dev, R, Nd, seed=4)
+    with K.precision(prec):
+        for w_is_nk in (True, False):
+            w = rnd(cuda_dev, Nd, Kd, seed=1) if w_is_nk else rnd(cuda_dev, Kd, Nd, seed=1)
+            ref = a.double() @ (w.double().t() if w_is_nk else w.double())
+            assert rel_l2(K.rows_gemm(a, w, w_is_nk), ref) < 2e-6
+            got = K.rows_gemm(a, w, w_is_nk, bias, True, gate)
+            want = torch.relu(ref + bias.double()) * (gate > 0)
+            assert rel_l2(got, want) < 2e-6
+
+
+@pytest.mark.parametrize("prec", ["fp32"])
+@pytest.mark.parametrize("R,M,N", [(1, 128, 128), (333, 128, 384), (2025 * 4 + 5, 384, 128), (50, 32, 64)])
+def test_gemm_tn(cuda_dev, prec, R, M, N):
+    a, b = rnd(cuda_dev, R, M), rnd(cuda_dev, R, N, seed=1)
+    with K.precision(prec):
+        got = K.gemm_tn(a, b)
+        ref = a.double().t() @ b.double()
+        assert rel_l2(got, ref) < 5e-6
+        acc = K.gemm_tn(a, b, out=got.clone())
+        assert rel_l2(acc, 2 * ref) < 5e-6
+
+
+def test_colsum_gate(cuda_dev):
+    for R, N in [(1, 128), (4099, 384), (100, 64)]:
+        a = rnd(cuda_dev, R, N)
+        assert rel_l2(K.colsum(a), a.double().sum(0)) < 2e-6
+    for n in [5, 128, 1000003]:
+        x, r = rnd(cuda_dev, n), rnd(cuda_dev, n, seed=1)
+        assert torch.equal(K.gate_mul(x, r), x * (r > 0))
+
+
+@pytest.mark.parametrize("R,D", [(1, 128), (7, 128), (1031, 128), (65, 384), (33, 32)])
+@pytest.mark.parametrize("has_b", [True, False])
+def test_add_ln(cuda_dev, R, D, has_b):
+    a, b = rnd(cuda_dev, R, D), (rnd(cuda_dev, R, D, seed=1) if has_b else None)
+    gamma, beta = rnd(cuda_dev, D, seed=2) + 1.0, rnd(cuda_dev, D, seed=3)
+    dy, u = rnd(cuda_dev, R, D, seed=4), rnd(cuda_dev, R, D, seed=5)
+    vg, vb = rnd(cuda_dev, D, seed=6), rnd(cuda_dev, D, seed=7)
+    d = lambda t: None if t is None else t.double()  # noqa: E731
+    out = torch.empty_like(a, dtype=torch.float64)
+    EM.add_ln_fwd(d(a), d(b), d(gamma), d(beta), out, 1e-5)
+    assert rel_l2(K.add_ln_fwd(a, b, gamma, beta), out) < 2e-6
+    dz, dgm, dbt = (torch.empty(R, D, dtype=torch.float64, device=cuda_dev), torch.empty(D, dtype=torch.float64, device=cuda_dev),
+                    torch.empty(D, dtype=torch.float64, device=cuda_dev))
+    EM.add_ln_bwd(d(dy), d(a), d(b), d(gamma), dz, dgm, dbt, 1e-5)
+    got = K.add_ln_bwd(dy, a, b, gamma)
+    for g_, w_ in zip(got, (dz, dgm, dbt)):
+        assert rel_l2(g_, w_) < 5e-6
+    for vgi, vbi in ((vg, vb), (None, None)):
+        gdy, gz, gg = torch.empty_like(dz), torch.empty_like(dz), torch.empty_like(dgm)
+        EM.add_ln_bwd_bwd(d(u), d(vgi), d(vbi), d(dy), d(a), d(b), d(gamma), gdy, gz, gg, 1e-5)
+        got = K.add_ln_bwd_bwd(u, vgi, vbi, dy, a, b, gamma)
+        for g_, w_ in zip(got, (gdy, gz, gg)):
+            assert rel_l2(g_, w_) < 2e-5
+
+
+@pytest.mark.parametrize("B,N,D", [(1, 1, 128), (3, 9, 128), (2, 45, 128), (300, 9, 128), (2, 5, 64)])
+def test_modulate(cuda_dev, B, N, D):
+    q, k, e = rnd(cuda_dev, B, N, D), rnd(cuda_dev, B, N, D, seed=1), rnd(cuda_dev, B, N, N, D, seed=2)
+    da = rnd(cuda_dev, B, N, N, D, seed=3)
+    uq, uk, ue = rnd(cuda_dev, B, N, D, seed=4), rnd(cuda_dev, B, N, D, seed=5), rnd(cuda_dev, B, N, N, D, seed=6)
+    c = 0.25
+    d = lambda t: t.double()  # noqa: E731
+    out = torch.empty_like(e, dtype=torch.float64)
+    EM.modulate_fwd(d(q), d(k), d(e), c, out)
+    assert rel_l2(K.modulate_fwd(q, k, e, c), out) < 2e-6
+    dq, dk, de = torch.empty_like(d(q)), torch.empty_like(d(k)), torch.empty_like(out)
+    EM.modulate_bwd(d(da), d(q), d(k), d(e), c, dq, dk, de)
+    for g_, w_ in zip(K.modulate_bwd(da, q, k, e, c), (dq, dk, de)):
+        assert rel_l2(g_, w_) < 5e-6
+    gda, gq, gk, ge = torch.empty_like(out), torch.empty_like(dq), torch.empty_like(dq), torch.empty_like(out)
+    EM.modulate_bwd_bwd(d(uq), d(uk), d(ue), d(da), d(q), d(k), d(e), c, gda, gq, gk, ge)
+    for g_, w_ in zip(K.modulate_bwd_bwd(uq, uk, ue, da, q, k, e, c), (gda, gq, gk, ge)):
+        assert rel_l2(g_, w_) < 5e-6
+
+
+@pytest.mark.parametrize("B,N,D", [(1, 1, 128), (3, 9, 128), (2, 45, 128), (300, 9, 128), (2, 5, 64)])
+def test_softmax_agg(cuda_dev, B, N, D):
+    a, v = rnd(cuda_dev, B, N, N, D, scale=3.0), rnd(cuda_dev, B, N, D, seed=1)
+    dg = rnd(cuda_dev, B, N, D, seed=2)
+    ua, uv = rnd(cuda_dev, B, N, N, D, seed=3), rnd(cuda_dev, B, N, D, seed=4)
+    d = lambda t: t.double()  # noqa: E731
+    g = torch.empty_like(d(v))
+    EM.softmax_agg_fwd(d(a), d(v), g)
+    assert rel_l2(K.softmax_agg_fwd(a, v), g) < 5e-6
+    da, dv = torch.empty_like(d(a)), torch.empty_like(g)
+    EM.softmax_agg_bwd(d(dg), d(a), d(v), da, dv)
+    for g_, w_ in zip(K.softmax_agg_bwd(dg, a, v), (da, dv)):
+        assert rel_l2(g_, w_) < 1e-5
+    gdg, ga, gv = torch.empty_like(g), torch.empty_like(da), torch.empty_like(g)
+    EM.softmax_agg_bwd_bwd(d(ua), d(uv), d(dg), d(a), d(v), gdg, ga, gv)
+    for g_, w_ in zip(K.softmax_agg_bwd_bwd(ua, uv, dg, a, v), (gdg, ga, gv)):
+        assert rel_l2(g_, w_) < 2e-5
+
+
+def test_rejects_cpu_and_bad_shapes(cuda_dev):
+    with pytest.raises(RuntimeError):
+        K.add_ln_fwd(torch.zeros(2, 128), None, torch.ones(128), torch.zeros(128))
+    with pytest.raises(RuntimeError):   # D not a multiple of 4
+        K.add_ln_fwd(torch.zeros(2, 6, device=cuda_dev), None, torch.ones(6, device=cuda_dev), torch.zeros(6, device=cuda_dev))
+    z = torch.zeros(0, 128, device=cuda_dev)   # empty inputs are legal no-ops
+    assert K.add_ln_fwd(z, None, torch.ones(128, device=cuda_dev), torch.zeros(128, device=cuda_dev)).shape == (0, 128)

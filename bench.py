@@ -1,0 +1,269 @@
+#!/usr/bin/env python
+"""bench.py -- molecules/sec per GAN step (G+D fwd+bwd, WGAN-GP) at N=45, 8-layer encoder.
+
+    python bench.py --gpus N --steps K --warmup W            # our B200 path (one rank per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU cores
+
+A "step" is one train.py:351-384 iteration on one synthetic batch: D loss (real, fake, gradient
+penalty with its double backward) -> backward -> AdamW; G loss -> backward -> AdamW; two .item() syncs.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+M_DIM, B_DIM, DIM, HEADS, MLP_RATIO = 13, 5, 128, 8, 3
+METRIC = "molecules/sec per GAN step (G+D fwd+bwd) at N=45, 8-layer encoder"
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def gan_flops_per_molecule(n, depth, d=DIM, r=MLP_RATIO, m=M_DIM, b=B_DIM):
+    """Necessary GEMM FLOPs of one GAN step per molecule (74.57 GF at N=45, L=8).
+    encoder fwd per layer F = d^2 [N^2 (4+4r) + N (8+4r)]; prologue P and heads counted too."""
+    f_enc = d * d * (n * n * (4 + 4 * r) + n * (8 + 4 * r)) * depth
+    f_d_last_dead = d * d * n * n * (2 + 4 * r)          # D's last block: out_e + mlp2 have no consumer
+    pro = 2 * (n * n * (b * 64 + 64 * d) + n * (m * 64 + 64 * d))
+    g_fwd = f_enc + pro + 2 * (n * d * m + n * n * d * b)
+    d_fwd = f_enc - f_d_last_dead + pro + 2 * (n * d * 64 + 64 * 32 + 32 * 16 + 16)
+    # D-step: D fwd x3 + G fwd; D bwd (dgrad+wgrad) x2; GP: input-bwd (1x) + double backward (~4x fwd)
+    d_step = 3 * d_fwd + g_fwd + 2 * 2 * d_fwd + (1 + 4) * d_fwd
+    # G-step: G fwd + D fwd + D dgrad-only bwd + G full bwd
+    g_step = g_fwd + d_fwd + d_fwd + 2 * g_fwd
+    return float(d_step + g_step)
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        load = sm[len(sm) // 2:] if sm else []          # upper half = samples under load
+        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_gan(depth, n, sample_b, threads):
+    """The reference algorithm on host cores: oracle port (PyTorch CPU fp32 + AdamW)."""
+    import druggen_b200 as dg
+    from oracle import encoder_oracle as orc
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    G = dg.Generator("relu", n, B_DIM, M_DIM, 0.0, dim=DIM, depth=depth, heads=HEADS, mlp_ratio=MLP_RATIO)
+    D = dg.Discriminator("relu", n, B_DIM, M_DIM, 0.0, dim=DIM, depth=depth, heads=HEADS, mlp_ratio=MLP_RATIO)
+    gan = orc.OracleGAN(dict(G.state_dict()), dict(D.state_dict()), depth, depth, HEADS)
+    a, x = orc.synthetic_batch(sample_b, n, M_DIM, B_DIM, seed=1)
+
+    def step():
+        return gan.step(a, x, a, x, torch.rand(sample_b, 1, 1, 1), torch.rand(sample_b, 1, 1))
+    return step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample_b = args.cpu_sample
+    step = cpu_gan(args.depth, args.atoms, sample_b, threads)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = sample_b / dt
+    sample = f"{sample_b} molecules per step (reference needs ~0.8 GB RAM per molecule at depth 8), fp32, AdamW"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "molecules/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, sample_b),
+        "cpu_baseline": {"value": val, "unit": "molecules/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args, batch_per_gpu):
+    return {"workload": f"DrugGEN-{args.workload} GAN train step (train.py:351-384), Generator+Discriminator, "
+                        f"{args.depth} encoder layers, N={args.atoms}, dim {DIM}, heads {HEADS}, mlp_ratio {MLP_RATIO}",
+            "batch_per_gpu": batch_per_gpu, "atoms": args.atoms, "depth": args.depth, "precision": args.precision,
+            "parallelism": f"dp{args.gpus}", "l2": "inputs_exceed_l2"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=512, help="molecules per GPU per step")
+    ap.add_argument("--atoms", type=int, default=45)
+    ap.add_argument("--depth", type=int, default=8)
+    ap.add_argument("--workload", default="NoTarget", choices=["NoTarget", "AKT1"])
+    ap.add_argument("--precision", default=os.environ.get("DRUGGEN_B200_PRECISION", "bf16"))
+    ap.add_argument("--cpu-sample", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import druggen_b200 as dg
+    from druggen_b200 import _lib, gan, parallel
+
+    rank, world, local = parallel.init_from_env("nccl")
+    assert world == args.gpus or world == 1, (world, args.gpus)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    dg.set_precision(args.precision)
+    be = _lib.cuda_backend()
+
+    torch.manual_seed(0)                      # replicated weights
+    n, bsz = args.atoms, args.batch
+    G = dg.Generator("relu", n, B_DIM, M_DIM, 0.0, dim=DIM, depth=args.depth, heads=HEADS, mlp_ratio=MLP_RATIO).to(dev)
+    D = dg.Discriminator("relu", n, B_DIM, M_DIM, 0.0, dim=DIM, depth=args.depth, heads=HEADS, mlp_ratio=MLP_RATIO).to(dev)
+    trainer = gan.GANTrainer(G, D)
+    torch.manual_seed(1234 + rank)            # per-rank GP eps stream
+    mol_a_h, mol_x_h = gan.synthetic_molecules(bsz, n, M_DIM, B_DIM, seed=1 + rank)
+    host = [mol_a_h.pin_memory(), mol_x_h.pin_memory()]
+    if args.workload == "AKT1":               # DrugGEN submodel: independent "real drug" batch (train.py:340-342)
+        da, dx = gan.synthetic_molecules(bsz, n, M_DIM, B_DIM, seed=1001 + rank)
+        host += [da.pin_memory(), dx.pin_memory()]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host)
+
+    def upload():
+        t = [h.to(dev, non_blocking=True) for h in host]
+        return (t[2], t[3], t[0], t[1]) if len(t) == 4 else (t[0], t[1], t[0], t[1])
+
+    resident = upload()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (first step also profiles every kernel name to find the dominant one)
+    be.profile_all = True
+    for i in range(args.warmup):
+        trainer.step(*resident)
+        if i == 0:
+            torch.cuda.synchronize()
+            table = be.profile_summary()
+            be.profile_all = False
+            dominant = max(table, key=lambda k: table[k]["ms"]) if table else None
+            be.profile_only = dominant
+            be.profile_reset()
+    barrier()
+
+    # ---- timed: device-resident inputs
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = be.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        losses = trainer.step(*resident)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    launches = (be.launches - launches0) // args.steps
+    dom = be.profile_summary().get(be.profile_only) if be.profile_only else None
+    be.profile_only = None
+
+    # ---- timed: end to end through the public API with host (pinned) inputs
+    barrier()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev2.record()
+    for _ in range(args.steps):
+        losses = trainer.step(*upload())
+    ev3.record()
+    barrier()
+    ms_e2e = ev2.elapsed_time(ev3) / args.steps
+    clk = clocks.stop() if rank == 0 else None
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    if rank != 0:
+        return
+    total = bsz * world
+    pk, pk_kind = peaks()
+    flops_mol = gan_flops_per_molecule(n, args.depth)
+    out = {
+        "metric": METRIC, "value": total / (ms / 1e3), "unit": "molecules/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"bf16": "bf16", "fp32": "f32", "bf16x3": "bf16x3"}[args.precision], "data": "synthetic",
+        "config": workload_config(args, bsz), "clocks": clk,
+        "e2e": {"value": total / (ms_e2e / 1e3), "unit": "molecules/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8},
+        "gpu_launches": launches,
+        "losses": {"d": losses[0], "g": losses[1]},
+        "step_tflops": flops_mol * bsz / (ms / 1e3) / 1e12,
+        "step_frac_of_bf16_sustained": flops_mol * bsz / (ms / 1e3) / 1e12 / pk["bf16_tflops_sustained"],
+    }
+    if dom:
+        sec = dom["ms"] / 1e3
+        if dom["bound"] == "hbm":
+            ach, peak, unit = dom["bytes"] / sec / 1e9, pk["hbm_gbs"], "GB/s"
+        else:
+            ach, peak, unit = dom["flops"] / sec / 1e12, pk["bf16_tflops_sustained"], "TFLOP/s"
+        out["roofline"] = {"kernel": be.profile_name(dom), "bound": dom["bound"], "achieved": ach, "peak": peak, "unit": unit,
+                           "frac": ach / peak, "traffic": None, "peak_source": pk_kind, "launches": dom["n"],
+                           "avg_launch_ms": dom["ms"] / dom["n"], "share_of_step": dom["ms"] / (ms * args.steps),
+                           "algorithmic_bytes_per_launch": dom["bytes"] / dom["n"], "algorithmic_flops_per_launch": dom["flops"] / dom["n"]}
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        step = cpu_gan(args.depth, n, args.cpu_sample, threads)
+        step()
+        t0 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            step()
+        dt = (time.perf_counter() - t0) / reps
+        out["cpu_baseline"] = {"value": args.cpu_sample / dt, "unit": "molecules/s", "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": f"{reps} steps of {args.cpu_sample} molecules (same GAN step, depth {args.depth}, N={n}, fp32 PyTorch CPU + AdamW)"}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

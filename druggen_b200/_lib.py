@@ -63,72 +63,119 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+def _nbytes(*ts):
+    return sum(t.numel() * t.element_size() for t in ts if t is not None)
+
+
 class CudaBackend:
-    """Launch table used by kernels.py: torch tensors -> raw pointers + current stream."""
+    """Launch table used by kernels.py: torch tensors -> raw pointers + current stream.
+
+    Optional per-kernel timing (bench.py): with ``profile_all`` or ``profile_only == key`` every
+    matching launch is bracketed by CUDA events on the launching stream; ``profile_summary()``
+    returns, per key, launches / total ms / algorithmic bytes and FLOPs."""
 
     def __init__(self, lib):
         self.lib = lib
         self.launches = 0          # kernel launches issued through this table (bench.py reports it)
+        self.profile_all = False
+        self.profile_only = None
+        self._prof = {}
 
-    def _call(self, name, *args):
+    def profile_reset(self):
+        self._prof = {}
+
+    def profile_summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for key, rec in self._prof.items():
+            ms = sum(a.elapsed_time(b) for a, b in rec["events"])
+            out[key] = {"key": key, "n": len(rec["events"]), "ms": ms, "bytes": rec["bytes"], "flops": rec["flops"],
+                        "bound": rec["bound"]}
+        return out
+
+    @staticmethod
+    def profile_name(rec):
+        return rec["key"]
+
+    def _call(self, name, meta, *args):
         self.launches += 1
-        rc = getattr(self.lib, name)(*args, torch.cuda.current_stream().cuda_stream)
+        key, flops, nbytes, bound = meta
+        timed = self.profile_all or (self.profile_only is not None and self.profile_only == key)
+        stream = torch.cuda.current_stream()
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+        rc = getattr(self.lib, name)(*args, stream.cuda_stream)
         if rc != 0:
             raise RuntimeError(f"{name} rejected: {self.lib.dg_last_error().decode()}")
+        if timed:
+            e1.record(stream)
+            rec = self._prof.setdefault(key, {"events": [], "bytes": 0, "flops": 0, "bound": bound})
+            rec["events"].append((e0, e1))
+            rec["bytes"] += nbytes
+            rec["flops"] += flops
 
     def rows_gemm(self, a, w, w_is_nk, bias, relu, gate, out, prec):
         r, k = a.shape
-        self._call("dg_rows_gemm", _ptr(a), _ptr(w), int(w_is_nk), _ptr(bias), int(relu), _ptr(gate), _ptr(out),
-                   r, k, out.shape[1], PREC[prec])
+        n = out.shape[1]
+        meta = (f"rows_gemm[K={k},N={n},{prec}]", 2 * r * k * n, _nbytes(a, out, gate), "hbm")
+        self._call("dg_rows_gemm", meta, _ptr(a), _ptr(w), int(w_is_nk), _ptr(bias), int(relu), _ptr(gate), _ptr(out),
+                   r, k, n, PREC[prec])
 
     def gemm_tn(self, a, b, out, accumulate, prec):
-        self._call("dg_gemm_tn", _ptr(a), _ptr(b), _ptr(out), a.shape[0], a.shape[1], b.shape[1], PREC[prec])
+        r, m, n = a.shape[0], a.shape[1], b.shape[1]
+        meta = (f"gemm_tn[M={m},N={n},{prec}]", 2 * r * m * n, _nbytes(a, b), "hbm")
+        self._call("dg_gemm_tn", meta, _ptr(a), _ptr(b), _ptr(out), r, m, n, PREC[prec])
 
     def colsum(self, a, out):
-        self._call("dg_colsum", _ptr(a), _ptr(out), a.shape[0], a.shape[1])
+        self._call("dg_colsum", ("colsum", 0, _nbytes(a), "hbm"), _ptr(a), _ptr(out), a.shape[0], a.shape[1])
 
     def gate_mul(self, x, ref, out):
-        self._call("dg_gate_mul", _ptr(x), _ptr(ref), _ptr(out), x.numel())
+        self._call("dg_gate_mul", ("gate_mul", 0, _nbytes(x, ref, out), "hbm"), _ptr(x), _ptr(ref), _ptr(out), x.numel())
 
     def add_ln_fwd(self, a, b, gamma, beta, out, eps):
         d = a.shape[-1]
-        self._call("dg_add_ln_fwd", _ptr(a), _ptr(b), _ptr(gamma), _ptr(beta), _ptr(out), a.numel() // d, d, eps)
+        self._call("dg_add_ln_fwd", ("add_ln_fwd", 0, _nbytes(a, b, out), "hbm"), _ptr(a), _ptr(b), _ptr(gamma), _ptr(beta),
+                   _ptr(out), a.numel() // d, d, eps)
 
     def add_ln_bwd(self, dy, a, b, gamma, dz, dgamma, dbeta, eps):
         d = a.shape[-1]
-        self._call("dg_add_ln_bwd", _ptr(dy), _ptr(a), _ptr(b), _ptr(gamma), _ptr(dz), _ptr(dgamma), _ptr(dbeta),
-                   a.numel() // d, d, eps)
+        self._call("dg_add_ln_bwd", ("add_ln_bwd", 0, _nbytes(dy, a, b, dz), "hbm"), _ptr(dy), _ptr(a), _ptr(b), _ptr(gamma),
+                   _ptr(dz), _ptr(dgamma), _ptr(dbeta), a.numel() // d, d, eps)
 
     def add_ln_bwd_bwd(self, u, vg, vb, dy, a, b, gamma, g_dy, g_z, g_gamma, eps):
         d = a.shape[-1]
-        self._call("dg_add_ln_bwd_bwd", _ptr(u), _ptr(vg), _ptr(vb), _ptr(dy), _ptr(a), _ptr(b), _ptr(gamma),
-                   _ptr(g_dy), _ptr(g_z), _ptr(g_gamma), a.numel() // d, d, eps)
+        self._call("dg_add_ln_bwd_bwd", ("add_ln_bwd_bwd", 0, _nbytes(u, dy, a, b, g_dy, g_z), "hbm"), _ptr(u), _ptr(vg),
+                   _ptr(vb), _ptr(dy), _ptr(a), _ptr(b), _ptr(gamma), _ptr(g_dy), _ptr(g_z), _ptr(g_gamma),
+                   a.numel() // d, d, eps)
 
     def modulate_fwd(self, q, k, e, c, out):
         b, n, d = q.shape
-        self._call("dg_modulate_fwd", _ptr(q), _ptr(k), _ptr(e), c, _ptr(out), b, n, d)
+        self._call("dg_modulate_fwd", ("modulate_fwd", 0, _nbytes(e, out), "hbm"), _ptr(q), _ptr(k), _ptr(e), c, _ptr(out), b, n, d)
 
     def modulate_bwd(self, da, q, k, e, c, dq, dk, de):
         b, n, d = q.shape
-        self._call("dg_modulate_bwd", _ptr(da), _ptr(q), _ptr(k), _ptr(e), c, _ptr(dq), _ptr(dk), _ptr(de), b, n, d)
+        self._call("dg_modulate_bwd", ("modulate_bwd", 0, _nbytes(da, e, de), "hbm"), _ptr(da), _ptr(q), _ptr(k), _ptr(e), c,
+                   _ptr(dq), _ptr(dk), _ptr(de), b, n, d)
 
     def modulate_bwd_bwd(self, uq, uk, ue, da, q, k, e, c, g_da, g_q, g_k, g_e):
         b, n, d = q.shape
-        self._call("dg_modulate_bwd_bwd", _ptr(uq), _ptr(uk), _ptr(ue), _ptr(da), _ptr(q), _ptr(k), _ptr(e), c,
-                   _ptr(g_da), _ptr(g_q), _ptr(g_k), _ptr(g_e), b, n, d)
+        self._call("dg_modulate_bwd_bwd", ("modulate_bwd_bwd", 0, _nbytes(ue, da, e, g_da, g_e), "hbm"), _ptr(uq), _ptr(uk),
+                   _ptr(ue), _ptr(da), _ptr(q), _ptr(k), _ptr(e), c, _ptr(g_da), _ptr(g_q), _ptr(g_k), _ptr(g_e), b, n, d)
 
     def softmax_agg_fwd(self, a, v, out):
         b, n, d = v.shape
-        self._call("dg_softmax_agg_fwd", _ptr(a), _ptr(v), _ptr(out), b, n, d)
+        self._call("dg_softmax_agg_fwd", ("softmax_agg_fwd", 0, _nbytes(a), "hbm"), _ptr(a), _ptr(v), _ptr(out), b, n, d)
 
     def softmax_agg_bwd(self, dg, a, v, da, dv):
         b, n, d = v.shape
-        self._call("dg_softmax_agg_bwd", _ptr(dg), _ptr(a), _ptr(v), _ptr(da), _ptr(dv), b, n, d)
+        self._call("dg_softmax_agg_bwd", ("softmax_agg_bwd", 0, _nbytes(a, da), "hbm"), _ptr(dg), _ptr(a), _ptr(v), _ptr(da),
+                   _ptr(dv), b, n, d)
 
     def softmax_agg_bwd_bwd(self, ua, uv, dg, a, v, g_dg, g_a, g_v):
         b, n, d = v.shape
-        self._call("dg_softmax_agg_bwd_bwd", _ptr(ua), _ptr(uv), _ptr(dg), _ptr(a), _ptr(v), _ptr(g_dg), _ptr(g_a),
-                   _ptr(g_v), b, n, d)
+        self._call("dg_softmax_agg_bwd_bwd", ("softmax_agg_bwd_bwd", 0, _nbytes(ua, a, g_a), "hbm"), _ptr(ua), _ptr(uv),
+                   _ptr(dg), _ptr(a), _ptr(v), _ptr(g_dg), _ptr(g_a), _ptr(g_v), b, n, d)
 
 
 def cuda_backend() -> CudaBackend:

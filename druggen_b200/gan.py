@@ -1,0 +1,92 @@
+"""The GAN step that calls the hot path (reference loss.py:4-84 and train.py:351-384), restated
+as a small trainer so bench.py / tests can run "one training iteration" without the reference's
+PyG / RDKit data pipeline.  The reference's own ``loss.py`` runs unchanged on our modules too
+(INTEGRATION.md); this file only exists because the reference tree is absent on the GPU box.
+
+Multi-GPU: one process per GPU, the molecule batch sharded by rank, one flat-bucket NCCL
+all-reduce of the Discriminator grads after ``d_loss.backward()`` and one of the Generator grads
+after ``g_loss.backward()`` (parallel.py).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import parallel
+
+
+def gradient_penalty(D, real_node, real_edge, fake_node, fake_edge, batch_size, device):
+    """WGAN-GP term, loss.py:4-49 (eps_edge is drawn before eps_node, as there)."""
+    eps_edge = torch.rand(batch_size, 1, 1, 1, device=device)
+    eps_node = torch.rand(batch_size, 1, 1, device=device)
+    int_node = (eps_node * real_node + (1 - eps_node) * fake_node).requires_grad_(True)
+    int_edge = (eps_edge * real_edge + (1 - eps_edge) * fake_edge).requires_grad_(True)
+    logits = D(int_edge, int_node)
+    g_node, g_edge = torch.autograd.grad(logits, [int_node, int_edge], torch.ones_like(logits),
+                                         create_graph=True, retain_graph=True)
+    g = torch.cat([g_node.reshape(batch_size, -1), g_edge.reshape(batch_size, -1)], dim=1)
+    return ((g.norm(2, dim=1) - 1) ** 2).mean()
+
+
+def discriminator_loss(G, D, drug_adj, drug_annot, mol_adj, mol_annot, batch_size, device, lambda_gp):
+    """loss.py:52-72 -> (node, edge, d_loss)."""
+    real = -D(drug_adj, drug_annot).mean()
+    node, edge, node_sample, edge_sample = G(mol_adj, mol_annot)
+    node_sample, edge_sample = node_sample.detach(), edge_sample.detach()
+    fake = D(edge_sample, node_sample).mean()
+    gp = gradient_penalty(D, drug_annot, drug_adj, node_sample, edge_sample, batch_size, device)
+    return node, edge, fake + real + lambda_gp * gp
+
+
+def generator_loss(G, D, mol_adj, mol_annot, batch_size):
+    """loss.py:75-84 -> (g_loss, node, edge, node_sample, edge_sample)."""
+    node, edge, node_sample, edge_sample = G(mol_adj, mol_annot)
+    return -D(edge_sample, node_sample).mean(), node, edge, node_sample, edge_sample
+
+
+def synthetic_molecules(batch: int, n: int, m_dim: int = 13, b_dim: int = 5, seed: int = 1, device="cpu"):
+    """Synthetic one-hot molecules in the layout ``load_molecules`` produces (src/data/utils.py:128-143):
+    a[B,N,N,b] symmetric with a zero (class 0) diagonal, x[B,N,m]; fp32."""
+    g = torch.Generator().manual_seed(seed)
+    atoms = torch.randint(0, m_dim, (batch, n), generator=g)
+    upper = torch.triu(torch.randint(0, b_dim, (batch, n, n), generator=g), diagonal=1)
+    bonds = upper + upper.transpose(1, 2)
+    x = torch.nn.functional.one_hot(atoms, m_dim).float()
+    a = torch.nn.functional.one_hot(bonds, b_dim).float()
+    return a.to(device), x.to(device)
+
+
+class GANTrainer:
+    """Generator + Discriminator + two AdamW optimizers, stepped as train.py:351-384."""
+
+    def __init__(self, G, D, lr_g: float = 1e-5, lr_d: float = 1e-5, betas=(0.9, 0.999), lambda_gp: float = 10.0,
+                 process_group: Optional[object] = None):
+        self.G, self.D, self.lambda_gp = G, D, lambda_gp
+        self.g_optimizer = torch.optim.AdamW(G.parameters(), lr_g, betas)      # train.py:213
+        self.d_optimizer = torch.optim.AdamW(D.parameters(), lr_d, betas)      # train.py:214
+        self.pg = process_group
+        self.reducer_g = parallel.FlatGradReducer(G.parameters(), process_group)
+        self.reducer_d = parallel.FlatGradReducer(D.parameters(), process_group)
+
+    def reset_grad(self):
+        self.g_optimizer.zero_grad(set_to_none=True)
+        self.d_optimizer.zero_grad(set_to_none=True)
+
+    def step(self, drug_adj, drug_annot, mol_adj, mol_annot):
+        """One iteration on this rank's shard; returns (d_loss, g_loss) as Python floats
+        (the two ``.item()`` syncs of train.py:364,380 included)."""
+        bsz, dev = mol_annot.shape[0], mol_annot.device
+        self.reset_grad()
+        _, _, d_loss = discriminator_loss(self.G, self.D, drug_adj, drug_annot, mol_adj, mol_annot, bsz, dev, self.lambda_gp)
+        d_val = d_loss.item()
+        d_loss.backward()
+        self.reducer_d.all_reduce_mean()
+        self.d_optimizer.step()
+        self.reset_grad()
+        g_loss = generator_loss(self.G, self.D, mol_adj, mol_annot, bsz)[0]
+        g_val = g_loss.item()
+        g_loss.backward()
+        self.reducer_g.all_reduce_mean()
+        self.g_optimizer.step()
+        return d_val, g_val

@@ -1,10 +1,383 @@
-// tcgen05 contractions (placeholder until the tensor-core kernels land: rejects loudly).
-#include "common.cuh"
+// tcgen05 contractions (DG_PREC_BF16): bf16 operands, fp32 accumulation in TMEM.
+//
+//   rows_gemm_tc : out[R,N] = epi(a[R,K] . op(w) + bias)   K,N in {64..384}, multiples of 64 / 128
+//   gemm_tn_tc   : out[M,N] += a[R,M]^T . b[R,N]           split over rows, atomics at the end
+//
+// Both are persistent, warp-specialised kernels (one CTA per SM):
+//   warps 0-3  epilogue : tcgen05.ld (thread = accumulator row) -> smem transpose -> coalesced stores
+//   warps 4-7  loaders  : coalesced fp32 LDG.128 -> bf16 -> 128B-swizzled operand blocks in smem
+//   warp  8    MMA      : one elected thread issues tcgen05.mma, tcgen05.commit signals mbarriers
+// Activations are fp32 in HBM in this (unfused) form, so both kernels are HBM-bound: the roofline
+// that governs them is bytes moved (a + out, or a + b), not the tensor pipe.
+#include "tc_common.cuh"
+#include "../../include/druggen_b200.h"
+
 namespace dg {
-int rows_gemm_tc(const float*, const float*, int, const float*, int, const float*, float*, long long, int, int, int, cudaStream_t) {
-  return fail("tcgen05 rows_gemm is not built in this library");
+namespace tc {
+
+constexpr int kThreads = 288;
+constexpr int kBlk = 128 * 128;           // [128 rows][64 bf16] operand block, bytes
+constexpr int kStage = 36;                // epilogue transpose row pitch (floats): conflict-free v4 access
+
+// =============================================================================================
+// rows_gemm
+// =============================================================================================
+constexpr int kRingA = 4;                 // A ring: blocks of [128 rows][64 ch]
+constexpr int kAccBufs = 4;               // 4 x 128 TMEM columns
+
+struct RowsSmem {                         // offsets into dynamic smem (1024-aligned base)
+  int w, a, stage, bars, total;
+};
+__host__ __device__ inline RowsSmem rows_smem(int K, int N) {
+  RowsSmem s;
+  s.w = 0;
+  s.a = N * K * 2;
+  s.stage = s.a + kRingA * kBlk;
+  s.bars = s.stage + 4 * 32 * kStage * 4;
+  s.total = s.bars + 256;
+  return s;
 }
-int gemm_tn_tc(const float*, const float*, float*, long long, int, int, int, cudaStream_t) {
-  return fail("tcgen05 gemm_tn is not built in this library");
+
+__global__ void __launch_bounds__(kThreads, 1)
+rows_gemm_tc_kernel(const float* __restrict__ a, const float* __restrict__ w, int w_is_nk,
+                    const float* __restrict__ bias, int relu, const float* __restrict__ gate,
+                    float* __restrict__ out, long long R, int K, int N) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const RowsSmem L = rows_smem(K, N);
+  uint8_t* sW = smem + L.w;
+  uint8_t* sA = smem + L.a;
+  float* sStage = reinterpret_cast<float*>(smem + L.stage);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + L.bars);
+  uint64_t* a_empty = a_full + kRingA;
+  uint64_t* acc_full = a_empty + kRingA;
+  uint64_t* acc_empty = acc_full + kAccBufs;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccBufs);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int KB = K / 64, NC = N / 128;
+  const long long num_tiles = (R + 127) / 128;
+
+  if (tid == 0) {
+    for (int i = 0; i < kRingA; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < kAccBufs; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  // weights: fp32 (L2-resident) -> bf16 -> [kb][N rows][128 B] swizzled, resident for the whole kernel
+  for (int idx = tid; idx < N * (K / 8); idx += kThreads) {
+    int n, c8;
+    float4 lo, hi;
+    if (w_is_nk) {
+      n = idx / (K / 8); c8 = idx % (K / 8);
+      const float* p = w + (long long)n * K + c8 * 8;
+      lo = ld4(p); hi = ld4(p + 4);
+    } else {
+      n = idx % N; c8 = idx / N;
+      const float* p = w + (long long)(c8 * 8) * N + n;
+      lo = make_float4(p[0], p[N], p[2 * N], p[3 * N]);
+      hi = make_float4(p[4 * N], p[5 * N], p[6 * N], p[7 * N]);
+    }
+    st_block_chunk(sW + (c8 >> 3) * (N * 128), n, c8 & 7, lo, hi);
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 4 && warp < 8) {
+    // ------------------------------------------------------------------ loaders
+    const int lt = tid - 128;
+    uint32_t chunk = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const long long row0 = tile * 128;
+      for (int kb = 0; kb < KB; ++kb, ++chunk) {
+        const int st = chunk % kRingA;
+        mbar_wait(&a_empty[st], ((chunk / kRingA) & 1) ^ 1);
+        uint8_t* blk = sA + st * kBlk;
+        float4 v[16];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          int item = it * 128 + lt, r = item >> 3, j = item & 7;
+          if (row0 + r < R) {
+            const float* p = a + (row0 + r) * K + kb * 64 + j * 8;
+            v[2 * it] = ld4(p); v[2 * it + 1] = ld4(p + 4);
+          } else {
+            v[2 * it] = v[2 * it + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          int item = it * 128 + lt;
+          st_block_chunk(blk, item >> 3, item & 7, v[2 * it], v[2 * it + 1]);
+        }
+        fence_async_smem();
+        mbar_arrive(&a_full[st]);
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, 128, 0, 0);
+      uint32_t chunk0 = 0, unit = 0;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, chunk0 += KB) {
+        for (int nc = 0; nc < NC; ++nc, ++unit) {
+          const int buf = unit % kAccBufs;
+          mbar_wait(&acc_empty[buf], ((unit / kAccBufs) & 1) ^ 1);
+          tc_fence_after();
+          for (int kb = 0; kb < KB; ++kb) {
+            const uint32_t chunk = chunk0 + kb;
+            const int st = chunk % kRingA;
+            if (nc == 0) {
+              mbar_wait(&a_full[st], (chunk / kRingA) & 1);
+              tc_fence_after();
+            }
+            const uint32_t a_addr = smem_u32(sA + st * kBlk);
+            const uint32_t b_addr = smem_u32(sW + kb * (N * 128) + nc * kBlk);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + buf * 128, make_sdesc(a_addr + k * 32, 16, 1024), make_sdesc(b_addr + k * 32, 16, 1024),
+                        idesc, (kb | k) ? 1u : 0u);
+            if (nc == NC - 1) umma_commit(&a_empty[st]);
+          }
+          umma_commit(&acc_full[buf]);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 0-3)
+    float* stg = sStage + warp * 32 * kStage;
+    uint32_t unit = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const long long row0 = tile * 128 + warp * 32;
+      for (int nc = 0; nc < NC; ++nc, ++unit) {
+        const int buf = unit % kAccBufs;
+        mbar_wait(&acc_full[buf], (unit / kAccBufs) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cg = 0; cg < 4; ++cg) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 128 + cg * 32, v);
+          tmem_ld_wait();
+          if (cg == 3) {                      // accumulator fully read: hand the TMEM buffer back
+            tc_fence_before();
+            mbar_arrive(&acc_empty[buf]);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) st4(stg + lane * kStage + i * 4, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+          __syncwarp();
+          const int col = nc * 128 + cg * 32 + (lane & 7) * 4;
+          const float4 bz = bias ? ld4(bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) {
+            const int r = rr * 4 + (lane >> 3);
+            const long long grow = row0 + r;
+            if (grow < R) {
+              float4 o = ld4(stg + r * kStage + (lane & 7) * 4);
+              o.x += bz.x; o.y += bz.y; o.z += bz.z; o.w += bz.w;
+              if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              if (gate) {
+                float4 g = ld4(gate + grow * N + col);
+                o.x = g.x > 0.f ? o.x : 0.f; o.y = g.y > 0.f ? o.y : 0.f; o.z = g.z > 0.f ? o.z : 0.f; o.w = g.w > 0.f ? o.w : 0.f;
+              }
+              st4(out + grow * N + col, o);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
 }
+
+// =============================================================================================
+// gemm_tn : out[M,N] += a[R,M]^T b[R,N]
+// =============================================================================================
+constexpr int kTnRows = 64;               // rows (= MMA K extent) per stage
+constexpr int kTnBlk = kTnRows * 128;     // [64 rows][64 ch] block, bytes
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tn_tc_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                  long long R, int M, int N, long long tiles_per_cta, int stages) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nblk = (M + N) / 64;                       // operand blocks per stage: a's first, then b's
+  const int stage_bytes = nblk * kTnBlk;
+  uint8_t* sOp = smem;
+  float* sStage = reinterpret_cast<float*>(smem + stages * stage_bytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes + 4 * 32 * kStage * 4);
+  uint64_t* empty = full + 8;
+  uint64_t* done = empty + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long num_tiles = (R + kTnRows - 1) / kTnRows;
+  const long long t0 = (long long)blockIdx.x * tiles_per_cta;
+  const long long t1 = t0 + tiles_per_cta < num_tiles ? t0 + tiles_per_cta : num_tiles;
+  const int MB = M / 128;
+
+  if (tid == 0) {
+    for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 4 && warp < 8) {
+    const int lt = tid - 128;
+    uint32_t it_ = 0;
+    for (long long tile = t0; tile < t1; ++tile, ++it_) {
+      const int st = it_ % stages;
+      mbar_wait(&empty[st], ((it_ / stages) & 1) ^ 1);
+      uint8_t* base = sOp + st * stage_bytes;
+      const long long row0 = tile * kTnRows;
+      // items: (block, row, chunk j); 64 rows x 8 chunks = 512 items per block, 4 per thread
+      for (int blk = 0; blk < nblk; ++blk) {
+        const bool is_a = blk < M / 64;
+        const float* src = is_a ? a : b;
+        const int ld = is_a ? M : N, cb = is_a ? blk : blk - M / 64;
+        float4 v[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          int item = q * 128 + lt, r = item >> 3, j = item & 7;
+          if (row0 + r < R) {
+            const float* p = src + (row0 + r) * ld + cb * 64 + j * 8;
+            v[2 * q] = ld4(p); v[2 * q + 1] = ld4(p + 4);
+          } else {
+            v[2 * q] = v[2 * q + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          int item = q * 128 + lt;
+          st_block_chunk(base + blk * kTnBlk, item >> 3, item & 7, v[2 * q], v[2 * q + 1]);
+        }
+      }
+      fence_async_smem();
+      mbar_arrive(&full[st]);
+    }
+  } else if (warp == 8) {
+    if (lane == 0) {
+      uint32_t it_ = 0;
+      for (long long tile = t0; tile < t1; ++tile, ++it_) {
+        const int st = it_ % stages;
+        mbar_wait(&full[st], (it_ / stages) & 1);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(sOp + st * stage_bytes);
+        const uint32_t b_addr = a_addr + (M / 64) * kTnBlk;
+#pragma unroll 1
+        for (int ks = 0; ks < kTnRows / 16; ++ks) {
+          for (int mb = 0; mb < MB; ++mb) {
+            // A: MN-major, M = 128 channels = 2 blocks (LBO = block pitch), K = 16 rows = 2 atoms (SBO = 1024)
+            const uint64_t da = make_sdesc(a_addr + mb * 2 * kTnBlk + ks * 2048, kTnBlk, 1024);
+            for (int n0 = 0; n0 < N; n0 += 256) {
+              const int nn = N - n0 < 256 ? N - n0 : 256;
+              const uint64_t db = make_sdesc(b_addr + (n0 / 64) * kTnBlk + ks * 2048, kTnBlk, 1024);
+              umma_bf16(tmem_base + mb * N + n0, da, db, make_idesc(128, nn, 1, 1), (it_ | ks) ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit(&empty[st]);
+      }
+      umma_commit(done);
+    }
+    __syncwarp();
+  } else {
+    // epilogue: once, after the last tile of this CTA
+    if (t1 > t0) {
+      mbar_wait(done, 0);
+      tc_fence_after();
+      float* stg = sStage + warp * 32 * kStage;
+      for (int mb = 0; mb < MB; ++mb) {
+        for (int cg = 0; cg < N / 32; ++cg) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + mb * N + cg * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) st4(stg + lane * kStage + i * 4, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+          __syncwarp();
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) {
+            const int r = rr * 4 + (lane >> 3);
+            const int m = mb * 128 + warp * 32 + r;
+            float4 o = ld4(stg + r * kStage + (lane & 7) * 4);
+            float* dst = out + (long long)m * N + cg * 32 + (lane & 7) * 4;
+            atomicAdd(dst + 0, o.x); atomicAdd(dst + 1, o.y); atomicAdd(dst + 2, o.z); atomicAdd(dst + 3, o.w);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace tc
+
+int rows_gemm_fp32(const float*, const float*, int, const float*, int, const float*, float*, long long, int, int, cudaStream_t);
+int gemm_tn_fp32(const float*, const float*, float*, long long, int, int, cudaStream_t);
+
+// Shapes the tensor-core kernels take; anything else (tiny / odd node-side shapes) runs the fp32
+// CUDA-core kernel -- still on the GPU, never a CPU path.
+static bool rows_tc_ok(int K, int N) {
+  if (K % 64 || N % 128 || K < 64 || N < 128 || K > 384 || N > 384) return false;
+  if (N > 128 && K / 64 > tc::kRingA) return false;        // a row tile must stay resident across N chunks
+  return tc::rows_smem(K, N).total + 1024 <= 227 * 1024;
+}
+
+int rows_gemm_tc(const float* a, const float* w, int w_is_nk, const float* bias, int relu, const float* gate,
+                 float* out, long long R, int K, int N, int prec, cudaStream_t s) {
+  if (prec == DG_PREC_BF16X3 || !rows_tc_ok(K, N)) return rows_gemm_fp32(a, w, w_is_nk, bias, relu, gate, out, R, K, N, s);
+  const int smem = tc::rows_smem(K, N).total + 1024;
+  static int configured = 0;
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(tc::rows_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return fail("cudaFuncSetAttribute(rows_gemm_tc): %s", cudaGetErrorString(e));
+    configured = 227 * 1024;
+  }
+  long long tiles = (R + 127) / 128;
+  int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  tc::rows_gemm_tc_kernel<<<grid, tc::kThreads, smem, s>>>(a, w, w_is_nk, bias, relu, gate, out, R, K, N);
+  return check_launch("dg_rows_gemm(bf16)");
+}
+
+int gemm_tn_tc(const float* a, const float* b, float* out, long long R, int M, int N, int prec, cudaStream_t s) {
+  const bool ok = M % 128 == 0 && N % 128 == 0 && M >= 128 && N >= 128 && (M / 128) * N <= 512 && N <= 384 && M <= 384;
+  if (prec == DG_PREC_BF16X3 || !ok) return gemm_tn_fp32(a, b, out, R, M, N, s);
+  const int stage_bytes = (M + N) / 64 * tc::kTnBlk;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) return gemm_tn_fp32(a, b, out, R, M, N, s);
+  const int smem = stages * stage_bytes + 4 * 32 * tc::kStage * 4 + 256 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc::gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return fail("cudaFuncSetAttribute(gemm_tn_tc): %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  long long tiles = (R + tc::kTnRows - 1) / tc::kTnRows;
+  long long ctas = tiles < sm_count() ? tiles : sm_count();
+  long long per = (tiles + ctas - 1) / ctas;
+  ctas = (tiles + per - 1) / per;
+  tc::gemm_tn_tc_kernel<<<(int)ctas, tc::kThreads, smem, s>>>(a, b, out, R, M, N, per, stages);
+  return check_launch("dg_gemm_tn(bf16)");
+}
+
 }  // namespace dg

@@ -17,28 +17,38 @@ def rnd(dev, *shape, seed=0, scale=1.0):
     return (torch.randn(*shape, generator=g) * scale).to(dev)
 
 
-@pytest.mark.parametrize("prec", ["fp32"])
-@pytest.mark.parametrize("R,Kd,Nd", [(1, 128, 128), (257, 128, 384), (1000, 384, 128), (2025 * 3, 128, 128), (77, 64, 32)])
+def _opr(t, tc):
+    """operand as the kernel sees it: bf16-rounded when the tcgen05 kernel takes the shape (other
+    shapes -- channel counts that are not multiples of 64/128 -- run the fp32 CUDA-core kernel)"""
+    return (t.to(torch.bfloat16) if tc else t).double()
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("R,Kd,Nd", [(1, 128, 128), (257, 128, 384), (1000, 384, 128), (2025 * 3, 128, 128), (77, 32, 32),
+                                     (128 * 148 * 3 + 5, 128, 128), (40000, 128, 384), (40000, 384, 128)])
 def test_rows_gemm(cuda_dev, prec, R, Kd, Nd):
     a, bias = rnd(cuda_dev, R, Kd), rnd(cuda_dev, Nd, seed=3)
     gate = rnd(cuda_dev, R, Nd, seed=4)
     with K.precision(prec):
         for w_is_nk in (True, False):
             w = rnd(cuda_dev, Nd, Kd, seed=1) if w_is_nk else rnd(cuda_dev, Kd, Nd, seed=1)
-            ref = a.double() @ (w.double().t() if w_is_nk else w.double())
+            tc = prec == "bf16" and Kd % 64 == 0 and Nd % 128 == 0
+            ref = _opr(a, tc) @ (_opr(w, tc).t() if w_is_nk else _opr(w, tc))
             assert rel_l2(K.rows_gemm(a, w, w_is_nk), ref) < 2e-6
             got = K.rows_gemm(a, w, w_is_nk, bias, True, gate)
             want = torch.relu(ref + bias.double()) * (gate > 0)
             assert rel_l2(got, want) < 2e-6
 
 
-@pytest.mark.parametrize("prec", ["fp32"])
-@pytest.mark.parametrize("R,M,N", [(1, 128, 128), (333, 128, 384), (2025 * 4 + 5, 384, 128), (50, 32, 64)])
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("R,M,N", [(1, 128, 128), (333, 128, 384), (2025 * 4 + 5, 384, 128), (50, 32, 64),
+                                   (64 * 148 * 5 + 3, 128, 128), (100000, 128, 384), (100000, 384, 128)])
 def test_gemm_tn(cuda_dev, prec, R, M, N):
     a, b = rnd(cuda_dev, R, M), rnd(cuda_dev, R, N, seed=1)
     with K.precision(prec):
         got = K.gemm_tn(a, b)
-        ref = a.double().t() @ b.double()
+        tc = prec == "bf16" and M % 128 == 0 and N % 128 == 0
+        ref = _opr(a, tc).t() @ _opr(b, tc)
         assert rel_l2(got, ref) < 5e-6
         acc = K.gemm_tn(a, b, out=got.clone())
         assert rel_l2(acc, 2 * ref) < 5e-6

@@ -143,6 +143,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("DRUGGEN_B200_PRECISION", "bf16"))
     ap.add_argument("--cpu-sample", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-table", action="store_true", help="add the per-kernel time table of one warm-up step")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -188,6 +189,8 @@ def main():
         if i == 0:
             torch.cuda.synchronize()
             table = be.profile_summary()
+            first_step_table = {k: {"n": v["n"], "ms": round(v["ms"], 3), "GBps": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1),
+                                    "TFLOPs": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 1)} for k, v in table.items()}
             be.profile_all = False
             dominant = max(table, key=lambda k: table[k]["ms"]) if table else None
             be.profile_only = dominant
@@ -241,6 +244,8 @@ def main():
         "step_tflops": flops_mol * bsz / (ms / 1e3) / 1e12,
         "step_frac_of_bf16_sustained": flops_mol * bsz / (ms / 1e3) / 1e12 / pk["bf16_tflops_sustained"],
     }
+    if args.kernel_table:
+        out["kernel_table"] = dict(sorted(first_step_table.items(), key=lambda kv: -kv[1]["ms"]))
     if dom:
         sec = dom["ms"] / 1e3
         if dom["bound"] == "hbm":

@@ -31,6 +31,7 @@ SIGNATURES = {
     "dg_softmax_agg_fwd": [_P, _P, _P, _I, _I, _I, _P],
     "dg_softmax_agg_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
     "dg_softmax_agg_bwd_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "dg_mlp_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _F, _P, _LL, _P],
 }
 INFO_SYMBOLS = ("dg_abi_version", "dg_last_error", "dg_has_tcgen05")
 
@@ -176,6 +177,17 @@ class CudaBackend:
         b, n, d = v.shape
         self._call("dg_softmax_agg_bwd_bwd", ("softmax_agg_bwd_bwd", 0, _nbytes(ua, a, g_a), "hbm"), _ptr(ua), _ptr(uv),
                    _ptr(dg), _ptr(a), _ptr(v), _ptr(g_dg), _ptr(g_a), _ptr(g_v), b, n, d)
+
+
+def _mlp_fwd(self, x, w1, b1, w2, b2, gamma, beta, out, eps, workspace):
+    r, d = x.shape
+    h = w1.shape[0]
+    meta = (f"mlp_fwd[H={h},fused]", 4 * r * d * h, _nbytes(x, out), "hbm")
+    self._call("dg_mlp_fwd", meta, _ptr(x), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(gamma), _ptr(beta), _ptr(out),
+               r, d, h, eps, _ptr(workspace), workspace.numel())
+
+
+CudaBackend.mlp_fwd = _mlp_fwd
 
 
 def cuda_backend() -> CudaBackend:

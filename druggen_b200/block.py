@@ -22,6 +22,7 @@ from typing import Sequence
 import torch
 from torch.autograd import Function
 
+from . import kernels as K
 from . import ops
 
 BLOCK_PARAM_NAMES = (
@@ -65,6 +66,39 @@ def block_forward(x, y, params: Sequence[torch.Tensor], heads: int, edge_out: bo
     return x_out, y_out
 
 
+def block_forward_nograd(x, y, params: Sequence[torch.Tensor], heads: int, edge_out: bool = True):
+    """Same function as ``block_forward`` for callers that need no graph (inference, the checkpointed
+    forward): uses the fused tcgen05 kernels where they exist, raw kernels otherwise."""
+    p = lambda n: params[_IDX[n]]  # noqa: E731
+    b, n, d = x.shape
+    hid = p("mlp.fc1.weight").shape[0]
+    if not K.fused_available(d, hid):
+        return block_forward(x, y, params, heads, edge_out)
+    c = 1.0 / math.sqrt(d // heads)
+    x1 = K.add_ln_fwd(x.reshape(-1, d), None, p("ln1.weight"), p("ln1.bias"))
+    q = K.rows_gemm(x1, p("attn.q.weight"), True, p("attn.q.bias")).view(b, n, d)
+    k = K.rows_gemm(x1, p("attn.k.weight"), True, p("attn.k.bias")).view(b, n, d)
+    v = K.rows_gemm(x1, p("attn.v.weight"), True, p("attn.v.bias")).view(b, n, d)
+    y2d = y.reshape(-1, d)
+    e = K.rows_gemm(y2d, p("attn.e.weight"), True, p("attn.e.bias"))
+    a = K.modulate_fwd(q, k, e.view(b, n, n, d), c)
+    del e
+    g = K.softmax_agg_fwd(a, v)
+    on = K.rows_gemm(g.view(-1, d), p("attn.out_n.weight"), True, p("attn.out_n.bias"))
+    x3 = K.add_ln_fwd(x1, on, p("ln3.weight"), p("ln3.bias"))
+    x_out = K.mlp_fwd(x3, p("mlp.fc1.weight"), p("mlp.fc1.bias"), p("mlp.fc2.weight"), p("mlp.fc2.bias"),
+                      p("ln5.weight"), p("ln5.bias")).view(b, n, d)
+    if not edge_out:
+        return x_out, None
+    y1 = K.rows_gemm(a.view(-1, d), p("attn.out_e.weight"), True, p("attn.out_e.bias"))
+    del a
+    y3 = K.add_ln_fwd(y2d, y1, p("ln4.weight"), p("ln4.bias"))
+    del y1
+    y_out = K.mlp_fwd(y3, p("mlp2.fc1.weight"), p("mlp2.fc1.bias"), p("mlp2.fc2.weight"), p("mlp2.fc2.bias"),
+                      p("ln6.weight"), p("ln6.bias")).view(b, n, n, d)
+    return x_out, y_out
+
+
 def _leaf(t):
     return t.detach().requires_grad_(True)
 
@@ -90,7 +124,7 @@ class EncoderBlockFn(Function):
         ctx.save_for_backward(x, y, *params)
         ctx.set_materialize_grads(False)
         with torch.no_grad():
-            xo, yo = block_forward(x, y, params, heads, edge_out)
+            xo, yo = block_forward_nograd(x, y, params, heads, edge_out)
         if yo is None:
             yo = y.new_empty(0)
             ctx.mark_non_differentiable(yo)
@@ -148,6 +182,7 @@ def encoder_block(x, y, params: Sequence[torch.Tensor], heads: int, edge_out: bo
     needs_graph = torch.is_grad_enabled() and (
         x.requires_grad or y.requires_grad or any(p.requires_grad for p in params))
     if not needs_graph:
-        return block_forward(x, y, params, heads, edge_out)
+        with torch.no_grad():
+            return block_forward_nograd(x, y, params, heads, edge_out)
     xo, yo = EncoderBlockFn.apply(x, y, heads, edge_out, *params)
     return xo, (yo if edge_out else None)

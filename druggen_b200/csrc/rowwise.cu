@@ -12,17 +12,18 @@
 
 namespace dg {
 
-constexpr int kMaxV = 4;          // float4s per lane -> D <= 512
+constexpr int kMaxV = 4;          // float4s per lane -> D <= 512 (kernels are templated on V <= kMaxV)
 constexpr int kRowWarps = 8;      // warps (rows in flight) per CTA
 
-struct RowVec {
-  float4 v[kMaxV];
+template <int V>
+struct RowVecT {
+  float4 v[V];
 };
 
-template <typename F>
-__device__ __forceinline__ void for_each_chunk(int D, int lane, F f) {
+template <int V, typename F>
+__device__ __forceinline__ void for_each_chunk_t(int D, int lane, F f) {
 #pragma unroll
-  for (int t = 0; t < kMaxV; ++t) {
+  for (int t = 0; t < V; ++t) {
     int c = (t * 32 + lane) * 4;
     if (c < D) f(t, c);
   }
@@ -32,10 +33,11 @@ __device__ __forceinline__ float sum4(float4 a) { return (a.x + a.y) + (a.z + a.
 __device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 
 // loads z = a (+ b), returns xhat in-place and rstd
-__device__ __forceinline__ float load_normalise(RowVec& z, const float* a, const float* b, long long row,
+template <int V>
+__device__ __forceinline__ float load_normalise(RowVecT<V>& z, const float* a, const float* b, long long row,
                                                 int D, int lane, float eps) {
   float s = 0.f;
-  for_each_chunk(D, lane, [&](int t, int c) {
+  for_each_chunk_t<V>(D, lane, [&](int t, int c) {
     float4 x = ld4(a + row * D + c);
     if (b) {
       float4 y = ld4(b + row * D + c);
@@ -46,27 +48,28 @@ __device__ __forceinline__ float load_normalise(RowVec& z, const float* a, const
   });
   float mu = warp_sum(s) / D;
   float q = 0.f;
-  for_each_chunk(D, lane, [&](int t, int) {
+  for_each_chunk_t<V>(D, lane, [&](int t, int) {
     float4& x = z.v[t];
     x.x -= mu; x.y -= mu; x.z -= mu; x.w -= mu;
     q += dot4(x, x);
   });
   float r = rsqrtf(warp_sum(q) / D + eps);
-  for_each_chunk(D, lane, [&](int t, int) {
+  for_each_chunk_t<V>(D, lane, [&](int t, int) {
     float4& x = z.v[t];
     x.x *= r; x.y *= r; x.z *= r; x.w *= r;
   });
   return r;
 }
 
+template <int V>
 __global__ void __launch_bounds__(kRowWarps * 32)
 add_ln_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ gamma,
                   const float* __restrict__ beta, float* __restrict__ out, long long R, int D, float eps) {
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (long long row = (long long)blockIdx.x * kRowWarps + warp; row < R; row += (long long)gridDim.x * kRowWarps) {
-    RowVec z;
+    RowVecT<V> z;
     load_normalise(z, a, b, row, D, lane, eps);
-    for_each_chunk(D, lane, [&](int t, int c) {
+    for_each_chunk_t<V>(D, lane, [&](int t, int c) {
       float4 g = ld4(gamma + c), be = ld4(beta + c), x = z.v[t];
       st4(out + row * D + c, make_float4(x.x * g.x + be.x, x.y * g.y + be.y, x.z * g.z + be.z, x.w * g.w + be.w));
     });
@@ -74,9 +77,10 @@ add_ln_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, cons
 }
 
 // accumulate per-lane column partials across the CTA and flush with one atomic per channel
-__device__ __forceinline__ void flush_columns(const RowVec& acc, float* dst, int D, int lane, int warp, float* sm) {
+template <int V>
+__device__ __forceinline__ void flush_columns(const RowVecT<V>& acc, float* dst, int D, int lane, int warp, float* sm) {
   // sm: [kRowWarps][D]
-  for_each_chunk(D, lane, [&](int t, int c) { st4(sm + warp * D + c, acc.v[t]); });
+  for_each_chunk_t<V>(D, lane, [&](int t, int c) { st4(sm + warp * D + c, acc.v[t]); });
   __syncthreads();
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
     float s = 0.f;
@@ -87,19 +91,20 @@ __device__ __forceinline__ void flush_columns(const RowVec& acc, float* dst, int
   __syncthreads();
 }
 
+template <int V>
 __global__ void __launch_bounds__(kRowWarps * 32)
 add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ a, const float* __restrict__ b,
                   const float* __restrict__ gamma, float* __restrict__ dz, float* __restrict__ dgamma,
                   float* __restrict__ dbeta, long long R, int D, float eps) {
   extern __shared__ float sm[];
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  RowVec accg, accb;
-  for (int t = 0; t < kMaxV; ++t) accg.v[t] = accb.v[t] = make_float4(0, 0, 0, 0);
+  RowVecT<V> accg, accb;
+  for (int t = 0; t < V; ++t) accg.v[t] = accb.v[t] = make_float4(0, 0, 0, 0);
   for (long long row = (long long)blockIdx.x * kRowWarps + warp; row < R; row += (long long)gridDim.x * kRowWarps) {
-    RowVec xh, gh;
+    RowVecT<V> xh, gh;
     float r = load_normalise(xh, a, b, row, D, lane, eps);
     float s1 = 0.f, s2 = 0.f;
-    for_each_chunk(D, lane, [&](int t, int c) {
+    for_each_chunk_t<V>(D, lane, [&](int t, int c) {
       float4 d = ld4(dy + row * D + c), g = ld4(gamma + c), x = xh.v[t];
       accg.v[t].x += d.x * x.x; accg.v[t].y += d.y * x.y; accg.v[t].z += d.z * x.z; accg.v[t].w += d.w * x.w;
       accb.v[t].x += d.x; accb.v[t].y += d.y; accb.v[t].z += d.z; accb.v[t].w += d.w;
@@ -109,7 +114,7 @@ add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ a, con
       s2 += dot4(h, x);
     });
     float c1 = warp_sum(s1) / D, c2 = warp_sum(s2) / D;
-    for_each_chunk(D, lane, [&](int t, int c) {
+    for_each_chunk_t<V>(D, lane, [&](int t, int c) {
       float4 h = gh.v[t], x = xh.v[t];
       st4(dz + row * D + c, make_float4(r * (h.x - c1 - x.x * c2), r * (h.y - c1 - x.y * c2),
                                         r * (h.z - c1 - x.z * c2), r * (h.w - c1 - x.w * c2)));
@@ -124,6 +129,7 @@ __device__ __forceinline__ float4 proj4(float4 w, float4 x, float m1, float m2) 
   return make_float4(w.x - m1 - x.x * m2, w.y - m1 - x.y * m2, w.z - m1 - x.z * m2, w.w - m1 - x.w * m2);
 }
 
+template <int V>
 __global__ void __launch_bounds__(kRowWarps * 32)
 add_ln_bwd_bwd_kernel(const float* __restrict__ u, const float* __restrict__ vg, const float* __restrict__ vb,
                       const float* __restrict__ dy, const float* __restrict__ a, const float* __restrict__ b,
@@ -131,13 +137,13 @@ add_ln_bwd_bwd_kernel(const float* __restrict__ u, const float* __restrict__ vg,
                       float* __restrict__ g_gamma, long long R, int D, float eps) {
   extern __shared__ float sm[];
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  RowVec accg;
-  for (int t = 0; t < kMaxV; ++t) accg.v[t] = make_float4(0, 0, 0, 0);
+  RowVecT<V> accg;
+  for (int t = 0; t < V; ++t) accg.v[t] = make_float4(0, 0, 0, 0);
   for (long long row = (long long)blockIdx.x * kRowWarps + warp; row < R; row += (long long)gridDim.x * kRowWarps) {
-    RowVec xh, gh, uu;
+    RowVecT<V> xh, gh, uu;
     float r = load_normalise(xh, a, b, row, D, lane, eps);
     float sg = 0.f, sgx = 0.f, su = 0.f, sux = 0.f, sw = 0.f, swx = 0.f;
-    for_each_chunk(D, lane, [&](int t, int c) {
+    for_each_chunk_t<V>(D, lane, [&](int t, int c) {
       float4 d = ld4(dy + row * D + c), g = ld4(gamma + c), x = xh.v[t], uv = ld4(u + row * D + c);
       float4 h = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
       gh.v[t] = h;
@@ -155,10 +161,10 @@ add_ln_bwd_bwd_kernel(const float* __restrict__ u, const float* __restrict__ vg,
     if (vg) { mw = warp_sum(sw) / D; mwx = warp_sum(swx) / D; }
     // am = mean(u * P(gh))
     float sa = 0.f;
-    for_each_chunk(D, lane, [&](int t, int) { sa += dot4(uu.v[t], proj4(gh.v[t], xh.v[t], mg, c2)); });
+    for_each_chunk_t<V>(D, lane, [&](int t, int) { sa += dot4(uu.v[t], proj4(gh.v[t], xh.v[t], mg, c2)); });
     float am = warp_sum(sa) / D;
     float r2 = r * r;
-    for_each_chunk(D, lane, [&](int t, int c) {
+    for_each_chunk_t<V>(D, lane, [&](int t, int c) {
       float4 x = xh.v[t], g = ld4(gamma + c), d = ld4(dy + row * D + c);
       float4 pu = proj4(uu.v[t], x, mu_, bm), pg = proj4(gh.v[t], x, mg, c2);
       float4 od = make_float4(g.x * r * pu.x, g.y * r * pu.y, g.z * r * pu.z, g.w * r * pu.w);
@@ -207,9 +213,16 @@ __global__ void colsum_kernel(const float* __restrict__ a, float* __restrict__ o
   if (threadIdx.y == 0 && col < N) atomicAdd(out + col, sm[0][threadIdx.x] + sm[1][threadIdx.x] + sm[2][threadIdx.x] + sm[3][threadIdx.x]);
 }
 
+#define DG_DISPATCH_V(D, CALL)                                  \
+  do {                                                          \
+    if ((D) <= 128) { constexpr int V = 1; CALL; }              \
+    else if ((D) <= 256) { constexpr int V = 2; CALL; }         \
+    else { constexpr int V = 4; CALL; }                         \
+  } while (0)
+
 static int row_grid(long long R) {
   long long want = (R + kRowWarps - 1) / kRowWarps;
-  long long cap = (long long)sm_count() * 8;   // 8 CTAs x 8 warps = 64 resident warps per SM
+  long long cap = (long long)sm_count() * 16;  // a few waves of 8-warp CTAs; rows are grid-strided
   return (int)(want < cap ? want : cap);
 }
 static int ln_ok(long long R, int D) {
@@ -225,15 +238,15 @@ using namespace dg;
 extern "C" int dg_add_ln_fwd(const float* a, const float* b, const float* gamma, const float* beta, float* out,
                              long long R, int D, float eps, void* stream) {
   if (ln_ok(R, D)) return 1;
-  add_ln_fwd_kernel<<<row_grid(R), kRowWarps * 32, 0, (cudaStream_t)stream>>>(a, b, gamma, beta, out, R, D, eps);
+  DG_DISPATCH_V(D, (add_ln_fwd_kernel<V><<<row_grid(R), kRowWarps * 32, 0, (cudaStream_t)stream>>>(a, b, gamma, beta, out, R, D, eps)));
   return check_launch("dg_add_ln_fwd");
 }
 
 extern "C" int dg_add_ln_bwd(const float* dy, const float* a, const float* b, const float* gamma, float* dz,
                              float* dgamma, float* dbeta, long long R, int D, float eps, void* stream) {
   if (ln_ok(R, D)) return 1;
-  add_ln_bwd_kernel<<<row_grid(R), kRowWarps * 32, kRowWarps * D * sizeof(float), (cudaStream_t)stream>>>(
-      dy, a, b, gamma, dz, dgamma, dbeta, R, D, eps);
+  DG_DISPATCH_V(D, (add_ln_bwd_kernel<V><<<row_grid(R), kRowWarps * 32, kRowWarps * D * sizeof(float), (cudaStream_t)stream>>>(
+      dy, a, b, gamma, dz, dgamma, dbeta, R, D, eps)));
   return check_launch("dg_add_ln_bwd");
 }
 
@@ -241,8 +254,8 @@ extern "C" int dg_add_ln_bwd_bwd(const float* u, const float* vg, const float* v
                                  const float* b, const float* gamma, float* g_dy, float* g_z, float* g_gamma,
                                  long long R, int D, float eps, void* stream) {
   if (ln_ok(R, D)) return 1;
-  add_ln_bwd_bwd_kernel<<<row_grid(R), kRowWarps * 32, kRowWarps * D * sizeof(float), (cudaStream_t)stream>>>(
-      u, vg, vb, dy, a, b, gamma, g_dy, g_z, g_gamma, R, D, eps);
+  DG_DISPATCH_V(D, (add_ln_bwd_bwd_kernel<V><<<row_grid(R), kRowWarps * 32, kRowWarps * D * sizeof(float), (cudaStream_t)stream>>>(
+      u, vg, vb, dy, a, b, gamma, g_dy, g_z, g_gamma, R, D, eps)));
   return check_launch("dg_add_ln_bwd_bwd");
 }
 

@@ -216,3 +216,19 @@ def softmax_agg_bwd_bwd(ua, uv, dg, a, v):
     if a.numel():
         _be().softmax_agg_bwd_bwd(ua, uv, dg, a, v, g_dg, g_a, g_v)
     return g_dg, g_a, g_v
+
+
+# ----------------------------------------------------------------------------- fused tcgen05 kernels
+def fused_available(d: int, h: int) -> bool:
+    """The fused tensor-core kernels exist for the throughput mode and the reference's width."""
+    return _precision == "bf16" and d == 128 and h % 128 == 0 and 128 <= h <= 384
+
+
+def mlp_fwd(x, w1, b1, w2, b2, gamma, beta, eps: float = 1e-5):
+    """LN(x + fc2(relu(fc1(x)+b1)) + b2) * gamma + beta in one kernel; x:[R,128]."""
+    _chk(x, w1, b1, w2, b2, gamma, beta)
+    out = torch.empty_like(x)
+    if x.numel():
+        ws = torch.empty(2 * (w1.shape[0] // 128) * 32768, dtype=torch.uint8, device=x.device)
+        _be().mlp_fwd(x, w1, b1, w2, b2, gamma, beta, out, eps, ws)
+    return out

@@ -86,6 +86,14 @@ int dg_softmax_agg_bwd(const float* dg, const float* a, const float* v, float* d
 int dg_softmax_agg_bwd_bwd(const float* ua, const float* uv, const float* dg, const float* a, const float* v,
                            float* g_dg, float* g_a, float* g_v, int B, int N, int D, void* stream);
 
+/* ---- fused tcgen05 kernels (bf16 operands, fp32 accumulate / epilogue) ----------------------------- */
+/* out = LN(x + fc2(relu(fc1(x) + b1)) + b2) * gamma + beta   -- the whole residual MLP of one stream in one
+ * kernel (layers.py:41-54 + :191 / :192); x,out:[R,D] with D == 128, hidden width H in {128,256,384}.
+ * workspace: >= 2 * (H/128) * 32768 bytes, 128-byte aligned (bf16 swizzled weight stages are packed there). */
+int dg_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+               const float* gamma, const float* beta, float* out, long long R, int D, int H, float eps,
+               void* workspace, long long workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -135,3 +135,9 @@ class EmulBackend:
         g_dg.copy_(wbar.squeeze(2))
         g_a.copy_(dgi * p * (w - wbar - m * (vj - g)))
         g_v.copy_((dgi * p * (ua - m)).sum(1))
+
+    # ---- fused
+    def mlp_fwd(self, x, w1, b1, w2, b2, gamma, beta, out, eps, workspace):
+        h = torch.relu(self._mm(x, w1.t(), "bf16") + b1)
+        z = x + self._mm(h, w2.t(), "bf16") + b2
+        self.add_ln_fwd(z, None, gamma, beta, out, eps)

@@ -134,3 +134,22 @@ def test_rejects_cpu_and_bad_shapes(cuda_dev):
         K.add_ln_fwd(torch.zeros(2, 6, device=cuda_dev), None, torch.ones(6, device=cuda_dev), torch.zeros(6, device=cuda_dev))
     z = torch.zeros(0, 128, device=cuda_dev)   # empty inputs are legal no-ops
     assert K.add_ln_fwd(z, None, torch.ones(128, device=cuda_dev), torch.zeros(128, device=cuda_dev)).shape == (0, 128)
+
+
+@pytest.mark.parametrize("R", [1, 127, 128, 129, 2025, 128 * 148 + 77, 128 * 148 * 3 + 5])
+@pytest.mark.parametrize("H", [384, 128])
+def test_fused_mlp_fwd(cuda_dev, R, H):
+    """fused tcgen05 residual-MLP vs the same arithmetic in fp64 on bf16-rounded operands (x, W, hidden)."""
+    x = rnd(cuda_dev, R, 128)
+    w1, b1 = rnd(cuda_dev, H, 128, seed=1, scale=128 ** -0.5), rnd(cuda_dev, H, seed=2, scale=0.1)
+    w2, b2 = rnd(cuda_dev, 128, H, seed=3, scale=H ** -0.5), rnd(cuda_dev, 128, seed=4, scale=0.1)
+    gamma, beta = rnd(cuda_dev, 128, seed=5, scale=0.1) + 1.0, rnd(cuda_dev, 128, seed=6, scale=0.1)
+    bf = lambda t: t.to(torch.bfloat16).double()  # noqa: E731
+    h = torch.relu(bf(x) @ bf(w1).t() + b1.double())
+    z = x.double() + bf(h.float()) @ bf(w2).t() + b2.double()
+    mu, var = z.mean(-1, keepdim=True), z.var(-1, unbiased=False, keepdim=True)
+    want = (z - mu) / torch.sqrt(var + 1e-5) * gamma.double() + beta.double()
+    with K.precision("bf16"):
+        got = K.mlp_fwd(x, w1, b1, w2, b2, gamma, beta)
+    assert rel_l2(got, want) < 2e-4, rel_l2(got, want)   # bf16 rounding of the hidden can flip by 1 ulp vs fp64 emulation
+    assert float((got.double() - want).abs().max()) < 5e-2

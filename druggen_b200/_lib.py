@@ -18,8 +18,8 @@ _P, _LL, _I, _F = C.c_void_p, C.c_longlong, C.c_int, C.c_float
 
 # name -> argument ctypes (every entry returns int); mirrors include/druggen_b200.h
 SIGNATURES = {
-    "dg_rows_gemm": [_P, _P, _I, _P, _I, _P, _P, _LL, _I, _I, _I, _P],
-    "dg_gemm_tn": [_P, _P, _P, _LL, _I, _I, _I, _P],
+    "dg_rows_gemm": [_P, _P, _I, _P, _I, _P, _P, _P, _LL, _I, _I, _I, _P],
+    "dg_gemm_tn": [_P, _P, _P, _P, _LL, _I, _I, _I, _P],
     "dg_colsum": [_P, _P, _LL, _I, _P],
     "dg_gate_mul": [_P, _P, _P, _LL, _P],
     "dg_add_ln_fwd": [_P, _P, _P, _P, _P, _LL, _I, _F, _P],
@@ -29,7 +29,7 @@ SIGNATURES = {
     "dg_modulate_bwd": [_P, _P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _P],
     "dg_modulate_bwd_bwd": [_P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _I, _I, _I, _P],
     "dg_softmax_agg_fwd": [_P, _P, _P, _I, _I, _I, _P],
-    "dg_softmax_agg_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "dg_softmax_agg_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "dg_softmax_agg_bwd_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "dg_mlp_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _F, _P, _LL, _P],
 }
@@ -116,17 +116,17 @@ class CudaBackend:
             rec["bytes"] += nbytes
             rec["flops"] += flops
 
-    def rows_gemm(self, a, w, w_is_nk, bias, relu, gate, out, prec):
+    def rows_gemm(self, a, w, w_is_nk, bias, relu, gate, out, prec, resid=None):
         r, k = a.shape
         n = out.shape[1]
-        meta = (f"rows_gemm[K={k},N={n},{prec}]", 2 * r * k * n, _nbytes(a, out, gate), "hbm")
-        self._call("dg_rows_gemm", meta, _ptr(a), _ptr(w), int(w_is_nk), _ptr(bias), int(relu), _ptr(gate), _ptr(out),
-                   r, k, n, PREC[prec])
+        meta = (f"rows_gemm[K={k},N={n},{prec}]", 2 * r * k * n, _nbytes(a, out, gate, resid), "hbm")
+        self._call("dg_rows_gemm", meta, _ptr(a), _ptr(w), int(w_is_nk), _ptr(bias), int(relu), _ptr(gate), _ptr(resid),
+                   _ptr(out), r, k, n, PREC[prec])
 
-    def gemm_tn(self, a, b, out, accumulate, prec):
+    def gemm_tn(self, a, b, out, accumulate, prec, colsum_a=None):
         r, m, n = a.shape[0], a.shape[1], b.shape[1]
         meta = (f"gemm_tn[M={m},N={n},{prec}]", 2 * r * m * n, _nbytes(a, b), "hbm")
-        self._call("dg_gemm_tn", meta, _ptr(a), _ptr(b), _ptr(out), r, m, n, PREC[prec])
+        self._call("dg_gemm_tn", meta, _ptr(a), _ptr(b), _ptr(out), _ptr(colsum_a), r, m, n, PREC[prec])
 
     def colsum(self, a, out):
         self._call("dg_colsum", ("colsum", 0, _nbytes(a), "hbm"), _ptr(a), _ptr(out), a.shape[0], a.shape[1])
@@ -168,10 +168,10 @@ class CudaBackend:
         b, n, d = v.shape
         self._call("dg_softmax_agg_fwd", ("softmax_agg_fwd", 0, _nbytes(a), "hbm"), _ptr(a), _ptr(v), _ptr(out), b, n, d)
 
-    def softmax_agg_bwd(self, dg, a, v, da, dv):
+    def softmax_agg_bwd(self, dg, a, v, da, dv, accumulate=False):
         b, n, d = v.shape
-        self._call("dg_softmax_agg_bwd", ("softmax_agg_bwd", 0, _nbytes(a, da), "hbm"), _ptr(dg), _ptr(a), _ptr(v), _ptr(da),
-                   _ptr(dv), b, n, d)
+        self._call("dg_softmax_agg_bwd", ("softmax_agg_bwd", 0, _nbytes(a, da) * (2 if accumulate else 1), "hbm"), _ptr(dg),
+                   _ptr(a), _ptr(v), _ptr(da), _ptr(dv), int(accumulate), b, n, d)
 
     def softmax_agg_bwd_bwd(self, ua, uv, dg, a, v, g_dg, g_a, g_v):
         b, n, d = v.shape

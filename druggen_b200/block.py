@@ -99,6 +99,113 @@ def block_forward_nograd(x, y, params: Sequence[torch.Tensor], heads: int, edge_
     return x_out, y_out
 
 
+def block_backward(x, y, dxo, dyo, params: Sequence[torch.Tensor], heads: int, edge_out: bool = True,
+                   want_params: bool = True):
+    """First-order backward of the block as a hand-sequenced list of raw kernel launches (no autograd
+    graph): recompute from the block inputs, then the chain of Appendix-B of SURVEY.md.  Gradient
+    accumulation is fused into GEMM epilogues (``resid``), the ReLU derivative into the dgrad epilogue
+    (``gate``), bias gradients into the weight-gradient pass (``colsum_a``), and the softmax path adds
+    into the out_e path in place.  Returns (dx, dy, [param grads aligned with BLOCK_PARAM_NAMES]);
+    parameter grads are None when ``want_params`` is False or the parameter has no consumer."""
+    p = lambda n: params[_IDX[n]]  # noqa: E731
+    b, n, d = x.shape
+    c = 1.0 / math.sqrt(d // heads)
+    grads = [None] * len(BLOCK_PARAM_NAMES)
+
+    def put(name, t):
+        grads[_IDX[name]] = t
+
+    def wgrad(prefix, dy2d, x2d):
+        """dW = dy^T x and db = colsum(dy) of the Linear `prefix` in one pass over dy."""
+        if not want_params:
+            return
+        w = p(prefix + ".weight")
+        gw, gb = torch.zeros_like(w), torch.zeros_like(p(prefix + ".bias"))
+        K.gemm_tn(dy2d, x2d, out=gw, colsum_a=gb)
+        put(prefix + ".weight", gw)
+        put(prefix + ".bias", gb)
+
+    def ln_bwd(prefix, dy2d, a2d, b2d):
+        dz, dgam, dbet = K.add_ln_bwd(dy2d, a2d, b2d, p(prefix + ".weight"))
+        if want_params:
+            put(prefix + ".weight", dgam)
+            put(prefix + ".bias", dbet)
+        return dz
+
+    x2d, y2d = x.reshape(-1, d), y.reshape(-1, d)
+    # ---- recompute (node stream, attention scores)
+    x1 = K.add_ln_fwd(x2d, None, p("ln1.weight"), p("ln1.bias"))
+    q = K.rows_gemm(x1, p("attn.q.weight"), True, p("attn.q.bias")).view(b, n, d)
+    k = K.rows_gemm(x1, p("attn.k.weight"), True, p("attn.k.bias")).view(b, n, d)
+    v = K.rows_gemm(x1, p("attn.v.weight"), True, p("attn.v.bias")).view(b, n, d)
+    e = K.rows_gemm(y2d, p("attn.e.weight"), True, p("attn.e.bias"))
+    a = K.modulate_fwd(q, k, e.view(b, n, n, d), c)
+    a2d = a.view(-1, d)
+    g = K.softmax_agg_fwd(a, v)
+    g2d = g.view(-1, d)
+    on = K.rows_gemm(g2d, p("attn.out_n.weight"), True, p("attn.out_n.bias"))
+    x3 = K.add_ln_fwd(x1, on, p("ln3.weight"), p("ln3.bias"))
+    hx = K.rows_gemm(x3, p("mlp.fc1.weight"), True, p("mlp.fc1.bias"), relu=True)
+    mx = K.rows_gemm(hx, p("mlp.fc2.weight"), True, p("mlp.fc2.bias"))
+    # ---- node MLP + LN5, LN3, out_n
+    dxo2d = (dxo if dxo is not None else torch.zeros_like(x)).reshape(-1, d).contiguous()
+    dz5 = ln_bwd("ln5", dxo2d, x3, mx)
+    del mx
+    wgrad("mlp.fc2", dz5, hx)
+    dhx = K.rows_gemm(dz5, p("mlp.fc2.weight"), False, gate=hx)
+    wgrad("mlp.fc1", dhx, x3)
+    dx3 = K.rows_gemm(dhx, p("mlp.fc1.weight"), False, resid=dz5)
+    del dhx, hx, dz5
+    dz3 = ln_bwd("ln3", dx3, x1, on)                       # gradient of both x1 (residual) and out_n(g)
+    wgrad("attn.out_n", dz3, g2d)
+    dg = K.rows_gemm(dz3, p("attn.out_n.weight"), False).view(b, n, d)
+    # ---- edge stream: MLP2 + LN6, LN4, out_e
+    da = dz4 = None
+    if edge_out and dyo is not None:
+        y1 = K.rows_gemm(a2d, p("attn.out_e.weight"), True, p("attn.out_e.bias"))
+        y3 = K.add_ln_fwd(y2d, y1, p("ln4.weight"), p("ln4.bias"))
+        hy = K.rows_gemm(y3, p("mlp2.fc1.weight"), True, p("mlp2.fc1.bias"), relu=True)
+        my = K.rows_gemm(hy, p("mlp2.fc2.weight"), True, p("mlp2.fc2.bias"))
+        dz6 = ln_bwd("ln6", dyo.reshape(-1, d).contiguous(), y3, my)
+        del my
+        wgrad("mlp2.fc2", dz6, hy)
+        dhy = K.rows_gemm(dz6, p("mlp2.fc2.weight"), False, gate=hy)
+        del hy
+        wgrad("mlp2.fc1", dhy, y3)
+        dy3 = K.rows_gemm(dhy, p("mlp2.fc1.weight"), False, resid=dz6)
+        del dhy, dz6
+        dz4 = ln_bwd("ln4", dy3, y2d, y1)                  # gradient of both y (residual) and out_e(a)
+        del dy3, y1, y3
+        wgrad("attn.out_e", dz4, a2d)
+        da = K.rows_gemm(dz4, p("attn.out_e.weight"), False).view(b, n, n, d)
+    # ---- attention: softmax-aggregate, modulation, q/k/v/e projections
+    da, dv = K.softmax_agg_bwd(dg, a, v, da_accum=da)
+    dq, dk, de = K.modulate_bwd(da, q, k, e.view(b, n, n, d), c)
+    del da, a, e
+    de2d = de.view(-1, d)
+    wgrad("attn.e", de2d, y2d)
+    dy = K.rows_gemm(de2d, p("attn.e.weight"), False, resid=dz4)
+    del de, dz4
+    dx1 = dz3
+    for name, dt in (("attn.q", dq), ("attn.k", dk), ("attn.v", dv)):
+        dt2d = dt.view(-1, d)
+        wgrad(name, dt2d, x1)
+        dx1 = K.rows_gemm(dt2d, p(name + ".weight"), False, resid=dx1)
+    dx = ln_bwd("ln1", dx1, x2d, None)
+    return dx.view(b, n, d), dy.view(b, n, n, d), grads
+
+
+def _params_wanted(ctx_node, first_param_input: int) -> bool:
+    """Inside a backward: will the engine consume any parameter gradient of this node?  During the
+    gradient penalty's ``autograd.grad(inputs=[int_node, int_edge])`` (loss.py:32-39) it will not, and
+    the weight-gradient contractions of that pass are skipped.  Conservative (True) when unknown."""
+    try:
+        nxt = ctx_node.next_functions[first_param_input:]
+        return any(fn is not None and torch._C._will_engine_execute_node(fn) for fn, _ in nxt)
+    except Exception:
+        return True
+
+
 def _leaf(t):
     return t.detach().requires_grad_(True)
 
@@ -137,7 +244,8 @@ class EncoderBlockFn(Function):
             dyo = None
         if dxo is None and dyo is None:
             return (None,) * (4 + len(params))
-        outs = EncoderBlockBwdFn.apply(x, y, dxo, dyo, ctx.heads, ctx.edge_out, *params)
+        want = _params_wanted(ctx, 4) if torch.is_grad_enabled() else any(ctx.needs_input_grad[4:])
+        outs = EncoderBlockBwdFn.apply(x, y, dxo, dyo, ctx.heads, ctx.edge_out, want, *params)
         return (outs[0], outs[1], None, None) + tuple(outs[2:])
 
 
@@ -147,14 +255,12 @@ class EncoderBlockBwdFn(Function):
     reference, ``.grad`` stays None and AdamW leaves those tensors untouched)."""
 
     @staticmethod
-    def forward(ctx, x, y, dxo, dyo, heads, edge_out, *params):
+    def forward(ctx, x, y, dxo, dyo, heads, edge_out, want_params, *params):
         ctx.heads, ctx.edge_out = heads, edge_out
         ctx.save_for_backward(x, y, dxo, dyo, *params)
         ctx.set_materialize_grads(False)
-        with torch.enable_grad():
-            leaves, outs, gouts = _recompute(x, y, dxo, dyo, params, heads, edge_out, False)
-            grads = torch.autograd.grad(outs, leaves, gouts, allow_unused=True)
-        return tuple(grads)
+        dx, dy, pgrads = block_backward(x, y, dxo, dyo, params, heads, edge_out, want_params)
+        return (dx, dy) + tuple(pgrads)
 
     @staticmethod
     def backward(ctx, *u):
@@ -174,7 +280,22 @@ class EncoderBlockBwdFn(Function):
         tail = second[2 + n:]
         g_dxo = tail.pop(0) if dxo is not None else None
         g_dyo = tail.pop(0) if (dyo is not None and edge_out) else None
-        return (second[0], second[1], g_dxo, g_dyo, None, None) + tuple(second[2:2 + n])
+        return (second[0], second[1], g_dxo, g_dyo, None, None, None) + tuple(second[2:2 + n])
+
+
+class _ParamGate(Function):
+    """Identity on the block's parameters.  It puts ONE non-leaf node between the block and the
+    parameter leaves so that the block's backward can ask the engine whether any parameter gradient is
+    wanted at all (``_params_wanted``); leaves themselves cannot be queried under autograd.grad()."""
+
+    @staticmethod
+    def forward(ctx, *params):
+        ctx.set_materialize_grads(False)      # a parameter without a gradient must stay None, not become zeros
+        return tuple(p.view_as(p) for p in params)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        return grads
 
 
 def encoder_block(x, y, params: Sequence[torch.Tensor], heads: int, edge_out: bool = True):
@@ -184,5 +305,5 @@ def encoder_block(x, y, params: Sequence[torch.Tensor], heads: int, edge_out: bo
     if not needs_graph:
         with torch.no_grad():
             return block_forward_nograd(x, y, params, heads, edge_out)
-    xo, yo = EncoderBlockFn.apply(x, y, heads, edge_out, *params)
+    xo, yo = EncoderBlockFn.apply(x, y, heads, edge_out, *_ParamGate.apply(*params))
     return xo, (yo if edge_out else None)

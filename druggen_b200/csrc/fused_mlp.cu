@@ -8,11 +8,12 @@
 // -> 128B-swizzled smem operand blocks -> second contraction.  HBM traffic is the algorithmic
 // minimum: read x once (plus an L2-resident re-read for the fp32 residual), write out once.
 //
-// Persistent CTA per SM, 320 threads, warp-specialised:
-//   warps 0-3  epilogue  : thread = one row; TMEM accumulator -> h chunk (bf16 operand) / final LN
-//   warps 4-7  x loader  : fp32 LDG.128 -> bf16 -> swizzled operand blocks (double-buffered tiles)
-//   warp  8    MMA       : one thread issues tcgen05.mma; fc2 of tile t interleaved with fc1 of t+1
-//   warp  9    W loader  : one thread streams pre-packed bf16 weight stages (32 KB) with
+// Persistent CTA per SM, 448 threads, warp-specialised:
+//   warps 0-7   epilogue : thread = half a row (TMEM lane quarter w&3, column half w>>2);
+//                          TMEM accumulator -> h chunk (bf16 operand block) / final residual + LayerNorm
+//   warps 8-11  x loader : fp32 LDG.128 -> bf16 -> swizzled operand blocks (double-buffered tiles)
+//   warp  12    MMA      : one thread issues tcgen05.mma; fc2 of tile t interleaved with fc1 of t+1
+//   warp  13    W loader : one thread streams pre-packed bf16 weight stages (32 KB) with
 //                          cp.async.bulk into a 2-stage ring (weights live in L2: 192 KB per net)
 // TMEM: columns [0,384) three fc1 chunk accumulators, [384,512) the fc2 accumulator.
 #include "tc_common.cuh"
@@ -21,8 +22,9 @@
 namespace dg {
 namespace tc {
 
-constexpr int kMlpThreads = 320;
+constexpr int kMlpThreads = 448;         // warps 0-7 epilogue, 8-11 x loader, 12 MMA, 13 weight streamer
 constexpr int kWStage = 2 * kBlkBytes;   // one packed weight stage: [2 kb][128 rows][128 B] = 32 KB
+constexpr int kStgPitch = 20;            // epilogue transpose: 32 rows x 16 cols per warp, pitch 20 floats
 
 // ---- weight pre-pack: fp32 nn.Linear weights -> bf16 swizzled operand stages in a workspace ------
 // stage c        (c < HC): fc1 rows [c*128, c*128+128) of W1[H,128]        (B operand: N = hidden unit, K = in)
@@ -44,11 +46,53 @@ struct MlpSmem {
   static constexpr int xb = 0;                          // 2 x 32 KB
   static constexpr int hb = xb + 2 * kWStage;           // 2 x 32 KB
   static constexpr int wb = hb + 2 * kWStage;           // 2 x 32 KB
-  static constexpr int stage = wb + 2 * kWStage;        // 4 warps x 32 x 36 floats
-  static constexpr int vec = stage + 4 * 32 * 36 * 4;   // b1[384] b2[128] gamma[128] beta[128]
+  static constexpr int stage = wb + 2 * kWStage;        // 8 warps x 32 x kStgPitch floats
+  static constexpr int stats = stage + 8 * 32 * kStgPitch * 4;   // [2 parity][2 halves][128 rows] float2
+  static constexpr int vec = stats + 2 * 2 * 128 * 8;   // b1[384] b2[128] gamma[128] beta[128]
   static constexpr int bars = vec + (384 + 3 * 128) * 4;
   static constexpr int total = bars + 256;
 };
+
+// warp-cooperative transposes through a [32][kStgPitch] staging tile (16 columns at a time):
+// global rows -> "thread = row" registers, and back.  Global accesses are 64 B contiguous per row.
+// gather = issue (all 16 coalesced LDG.128 of a 32-row x 64-col panel in flight at once) + finish (transpose)
+__device__ __forceinline__ void gather_issue64(const float* __restrict__ src, long long row_base, long long R, int col,
+                                               int lane, float4* xq) {
+#pragma unroll
+  for (int g16 = 0; g16 < 4; ++g16)
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int r = it * 8 + (lane >> 2);
+      xq[g16 * 4 + it] = (row_base + r < R) ? ld4(src + (row_base + r) * 128 + col + g16 * 16 + (lane & 3) * 4)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+__device__ __forceinline__ void gather_finish64(const float4* xq, float* stg, int lane, float* dst64) {
+#pragma unroll
+  for (int g16 = 0; g16 < 4; ++g16) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) st4(stg + (it * 8 + (lane >> 2)) * kStgPitch + (lane & 3) * 4, xq[g16 * 4 + it]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 v = ld4(stg + lane * kStgPitch + i * 4);
+      dst64[g16 * 16 + 4 * i] = v.x; dst64[g16 * 16 + 4 * i + 1] = v.y; dst64[g16 * 16 + 4 * i + 2] = v.z; dst64[g16 * 16 + 4 * i + 3] = v.w;
+    }
+    __syncwarp();
+  }
+}
+__device__ __forceinline__ void scatter_rows16(float* __restrict__ dst, long long row_base, long long R, int col, float* stg,
+                                               int lane, const float* src16) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) st4(stg + lane * kStgPitch + i * 4, make_float4(src16[4 * i], src16[4 * i + 1], src16[4 * i + 2], src16[4 * i + 3]));
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int r = it * 8 + (lane >> 2);
+    if (row_base + r < R) st4(dst + (row_base + r) * 128 + col + (lane & 3) * 4, ld4(stg + r * kStgPitch + (lane & 3) * 4));
+  }
+  __syncwarp();
+}
 
 __global__ void __launch_bounds__(kMlpThreads, 1)
 mlp_fwd_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wpack, const float* __restrict__ b1,
@@ -60,6 +104,7 @@ mlp_fwd_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wpack
   uint8_t* sH = smem + MlpSmem::hb;
   uint8_t* sW = smem + MlpSmem::wb;
   float* sStage = reinterpret_cast<float*>(smem + MlpSmem::stage);
+  float2* sStats = reinterpret_cast<float2*>(smem + MlpSmem::stats);
   float* sB1 = reinterpret_cast<float*>(smem + MlpSmem::vec);
   float* sB2 = sB1 + 384;
   float* sG = sB2 + 128;
@@ -77,13 +122,13 @@ mlp_fwd_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wpack
     for (int i = 0; i < 2; ++i) {
       mbar_init(&x_full[i], 128); mbar_init(&x_empty[i], 1);
       mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1);
-      mbar_init(&hb_full[i], 128); mbar_init(&hb_empty[i], 1);
+      mbar_init(&hb_full[i], 256); mbar_init(&hb_empty[i], 1);
     }
-    for (int i = 0; i < 3; ++i) { mbar_init(&hacc_full[i], 1); mbar_init(&hacc_empty[i], 128); }
-    mbar_init(z_full, 1); mbar_init(z_empty, 128);
+    for (int i = 0; i < 3; ++i) { mbar_init(&hacc_full[i], 1); mbar_init(&hacc_empty[i], 256); }
+    mbar_init(z_full, 1); mbar_init(z_empty, 256);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  if (warp == 12) tmem_alloc(tmem_slot, 512);
   for (int i = tid; i < HC * 128; i += kMlpThreads) sB1[i] = b1[i];
   for (int i = tid; i < 128; i += kMlpThreads) { sB2[i] = b2[i]; sG[i] = gamma[i]; sBe[i] = beta[i]; }
   tc_fence_before();
@@ -91,9 +136,9 @@ mlp_fwd_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wpack
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 4 && warp < 8) {
+  if (warp >= 8 && warp < 12) {
     // ------------------------------------------------------------------ x loader
-    const int lt = tid - 128;
+    const int lt = tid - 256;
     for (long long ti = 0; ti < my_tiles; ++ti) {
       const long long row0 = (blockIdx.x + ti * gridDim.x) * 128;
       const int xs = ti & 1;
@@ -121,7 +166,7 @@ mlp_fwd_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wpack
       fence_async_smem();
       mbar_arrive(&x_full[xs]);
     }
-  } else if (warp == 9) {
+  } else if (warp == 13) {
     // ------------------------------------------------------------------ weight streamer (one thread)
     if (lane == 0 && my_tiles > 0) {
       uint32_t wcount = 0;
@@ -140,7 +185,7 @@ mlp_fwd_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wpack
         }
     }
     __syncwarp();
-  } else if (warp == 8) {
+  } else if (warp == 12) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0 && my_tiles > 0) {
       const uint32_t idesc = make_idesc(128, 128, 0, 0);
@@ -185,10 +230,12 @@ mlp_fwd_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wpack
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 0-3), thread = row
-    float* stg = sStage + warp * 32 * 36;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    const int row = warp * 32 + lane;
+    // ------------------------------------------------------------------ epilogue (warps 0-7)
+    // warp w: TMEM lane quarter q = w & 3 (rows 32q..32q+31 of the tile), column half hf = w >> 2
+    const int q = warp & 3, hf = warp >> 2;
+    float* stg = sStage + warp * 32 * kStgPitch;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const int row = q * 32 + lane;
     uint32_t hcount = 0;
     for (long long ti = 0; ti < my_tiles; ++ti) {
       const long long row0 = (blockIdx.x + ti * gridDim.x) * 128;
@@ -197,79 +244,65 @@ mlp_fwd_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wpack
         const int hs = hcount & 1;
         mbar_wait(&hb_empty[hs], ((hcount >> 1) & 1) ^ 1);
         tc_fence_after();
-        uint8_t* hblk = sH + hs * kWStage;
-#pragma unroll 1
-        for (int cg = 0; cg < 4; ++cg) {
-          float v[32];
-          tmem_ld32(tmem_base + lane_base + c * 128 + cg * 32, v);
-          tmem_ld_wait();
-          if (cg == 3) { tc_fence_before(); mbar_arrive(&hacc_empty[c]); }
-          const float* bb = sB1 + c * 128 + cg * 32;
+        uint8_t* hblk = sH + hs * kWStage + hf * kBlkBytes;          // this half's 64 hidden columns = one operand block
+        float v[64];
+        tmem_ld32(tmem_base + lane_base + c * 128 + hf * 64, v);
+        tmem_ld32(tmem_base + lane_base + c * 128 + hf * 64 + 32, v + 32);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&hacc_empty[c]);
+        const float* bb = sB1 + c * 128 + hf * 64;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bb[i], 0.f);
+        for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i] + bb[i], 0.f);
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            st_block_chunk(hblk + (cg >> 1) * kBlkBytes, row, (cg & 1) * 4 + q, make_float4(v[8 * q], v[8 * q + 1], v[8 * q + 2], v[8 * q + 3]),
-                           make_float4(v[8 * q + 4], v[8 * q + 5], v[8 * q + 6], v[8 * q + 7]));
-        }
+        for (int j = 0; j < 8; ++j)
+          st_block_chunk(hblk, row, j, make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
+                         make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]));
         fence_async_smem();
         mbar_arrive(&hb_full[hs]);
         ++hcount;
       }
-      // ---- final: z + b2 + x -> LayerNorm -> out
+      // ---- final: a = z + b2 + x (this thread: one row, 64 columns) -> LayerNorm -> out
+      float a[64];
+      {
+        float4 xq[16];
+        gather_issue64(x, row0 + q * 32, R, hf * 64, lane, xq);
+        gather_finish64(xq, stg, lane, a);
+      }
       mbar_wait(z_full, ti & 1);
       tc_fence_after();
-      const long long grow = row0 + row;
-      const bool live = grow < R;
-      const float* xr = x + (live ? grow : 0) * 128;
-      float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-      for (int cg = 0; cg < 4; ++cg) {
-        float v[32];
-        tmem_ld32(tmem_base + lane_base + 384 + cg * 32, v);
-        tmem_ld_wait();
+      float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float4 xv = ld4(xr + cg * 32 + i * 4);
-          float a0 = v[4 * i] + sB2[cg * 32 + 4 * i] + xv.x, a1 = v[4 * i + 1] + sB2[cg * 32 + 4 * i + 1] + xv.y;
-          float a2 = v[4 * i + 2] + sB2[cg * 32 + 4 * i + 2] + xv.z, a3 = v[4 * i + 3] + sB2[cg * 32 + 4 * i + 3] + xv.w;
-          s1 += (a0 + a1) + (a2 + a3);
-          s2 += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+      for (int cgl = 0; cgl < 2; ++cgl) {
+        float v[32];
+        tmem_ld32(tmem_base + lane_base + 384 + hf * 64 + cgl * 32, v);
+        tmem_ld_wait();
+        if (cgl == 1) { tc_fence_before(); mbar_arrive(z_empty); }
+        const float* bb = sB2 + hf * 64 + cgl * 32;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float t0 = a[cgl * 32 + i] + v[i] + bb[i], t1 = a[cgl * 32 + i + 1] + v[i + 1] + bb[i + 1];
+          a[cgl * 32 + i] = t0; a[cgl * 32 + i + 1] = t1;
+          s1a += t0; s1b += t1; s2a = fmaf(t0, t0, s2a); s2b = fmaf(t1, t1, s2b);
         }
       }
-      const float mean = s1 * (1.f / 128.f);
-      const float rstd = rsqrtf(fmaxf(s2 * (1.f / 128.f) - mean * mean, 0.f) + eps);
-#pragma unroll 1
-      for (int cg = 0; cg < 4; ++cg) {
-        float v[32];
-        tmem_ld32(tmem_base + lane_base + 384 + cg * 32, v);
-        tmem_ld_wait();
-        if (cg == 3) { tc_fence_before(); mbar_arrive(z_empty); }
+      float2* st = sStats + (ti & 1) * 256;
+      st[hf * 128 + row] = make_float2(s1a + s1b, s2a + s2b);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float2 other = st[(hf ^ 1) * 128 + row];
+      const float mean = (s1a + s1b + other.x) * (1.f / 128.f);
+      const float rstd = rsqrtf(fmaxf((s2a + s2b + other.y) * (1.f / 128.f) - mean * mean, 0.f) + eps);
+      const float* gg = sG + hf * 64;
+      const float* be = sBe + hf * 64;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float4 xv = ld4(xr + cg * 32 + i * 4);
-          const int cc = cg * 32 + 4 * i;
-          float4 o;
-          o.x = (v[4 * i] + sB2[cc] + xv.x - mean) * rstd * sG[cc] + sBe[cc];
-          o.y = (v[4 * i + 1] + sB2[cc + 1] + xv.y - mean) * rstd * sG[cc + 1] + sBe[cc + 1];
-          o.z = (v[4 * i + 2] + sB2[cc + 2] + xv.z - mean) * rstd * sG[cc + 2] + sBe[cc + 2];
-          o.w = (v[4 * i + 3] + sB2[cc + 3] + xv.w - mean) * rstd * sG[cc + 3] + sBe[cc + 3];
-          st4(stg + lane * 36 + i * 4, o);
-        }
-        __syncwarp();
+      for (int i = 0; i < 64; ++i) a[i] = (a[i] - mean) * rstd * gg[i] + be[i];
 #pragma unroll
-        for (int rr = 0; rr < 8; ++rr) {
-          const int r = rr * 4 + (lane >> 3);
-          const long long gr = row0 + warp * 32 + r;
-          if (gr < R) st4(out + gr * 128 + cg * 32 + (lane & 7) * 4, ld4(stg + r * 36 + (lane & 7) * 4));
-        }
-        __syncwarp();
-      }
+      for (int g16 = 0; g16 < 4; ++g16) scatter_rows16(out, row0 + q * 32, R, hf * 64 + g16 * 16, stg, lane, a + g16 * 16);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 12) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }

@@ -15,7 +15,7 @@ constexpr int BM = 128, BN = 64, BK = 16;
 __global__ void __launch_bounds__(256)
 rows_gemm_fp32_kernel(const float* __restrict__ a, const float* __restrict__ w, int w_is_nk,
                       const float* __restrict__ bias, int relu, const float* __restrict__ gate,
-                      float* __restrict__ out, long long R, int K, int N) {
+                      const float* __restrict__ resid, float* __restrict__ out, long long R, int K, int N) {
   __shared__ float As[BK][BM + 4];
   __shared__ float Ws[BK][BN + 4];
   const int tid = threadIdx.x;
@@ -78,6 +78,10 @@ rows_gemm_fp32_kernel(const float* __restrict__ a, const float* __restrict__ w, 
       float4 g = ld4(gate + r * N + c);
       o.x = g.x > 0.f ? o.x : 0.f; o.y = g.y > 0.f ? o.y : 0.f; o.z = g.z > 0.f ? o.z : 0.f; o.w = g.w > 0.f ? o.w : 0.f;
     }
+    if (resid) {
+      float4 z = ld4(resid + r * N + c);
+      o.x += z.x; o.y += z.y; o.z += z.z; o.w += z.w;
+    }
     st4(out + r * N + c, o);
   }
 }
@@ -86,7 +90,7 @@ constexpr int TM = 64, TN = 64, TK = 16;
 
 __global__ void __launch_bounds__(256)
 gemm_tn_fp32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
-                    long long R, int M, int N, long long rows_per_split) {
+                    float* __restrict__ colsum_a, long long R, int M, int N, long long rows_per_split) {
   __shared__ float As[TK][TM];
   __shared__ float Bs[TK][TN];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -99,6 +103,8 @@ gemm_tn_fp32_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   const int lr = tid >> 4, lc = (tid & 15) * 4;          // 16 rows x 16 float4
+  const bool do_colsum = colsum_a != nullptr && blockIdx.y == 0;   // one N-tile column of CTAs sums a's columns
+  float csum = 0.f;
   for (long long r = r0; r < r1; r += TK) {
     float4 va = make_float4(0, 0, 0, 0), vb = make_float4(0, 0, 0, 0);
     if (r + lr < r1) {
@@ -108,6 +114,10 @@ gemm_tn_fp32_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
     *reinterpret_cast<float4*>(&As[lr][lc]) = va;
     *reinterpret_cast<float4*>(&Bs[lr][lc]) = vb;
     __syncthreads();
+    if (do_colsum && tid < TM) {
+#pragma unroll
+      for (int kk = 0; kk < TK; ++kk) csum += As[kk][tid];
+    }
 #pragma unroll
     for (int kk = 0; kk < TK; ++kk) {
       float4 x = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
@@ -120,6 +130,7 @@ gemm_tn_fp32_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
     }
     __syncthreads();
   }
+  if (do_colsum && tid < TM && m0 + tid < M) atomicAdd(colsum_a + m0 + tid, csum);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     int m = m0 + ty * 4 + i;
@@ -133,16 +144,16 @@ gemm_tn_fp32_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
 }
 
 int rows_gemm_fp32(const float* a, const float* w, int w_is_nk, const float* bias, int relu, const float* gate,
-                   float* out, long long R, int K, int N, cudaStream_t s) {
+                   const float* resid, float* out, long long R, int K, int N, cudaStream_t s) {
   if (K % 4 || N % 4) return fail("rows_gemm(fp32): K=%d and N=%d must be multiples of 4", K, N);
   long long gx = (R + BM - 1) / BM;
   if (gx > 2147483647LL) return fail("too many rows");
   dim3 grid((unsigned)gx, (N + BN - 1) / BN);
-  rows_gemm_fp32_kernel<<<grid, 256, 0, s>>>(a, w, w_is_nk, bias, relu, gate, out, R, K, N);
+  rows_gemm_fp32_kernel<<<grid, 256, 0, s>>>(a, w, w_is_nk, bias, relu, gate, resid, out, R, K, N);
   return check_launch("dg_rows_gemm(fp32)");
 }
 
-int gemm_tn_fp32(const float* a, const float* b, float* out, long long R, int M, int N, cudaStream_t s) {
+int gemm_tn_fp32(const float* a, const float* b, float* out, float* colsum_a, long long R, int M, int N, cudaStream_t s) {
   if (M % 4 || N % 4) return fail("gemm_tn(fp32): M=%d and N=%d must be multiples of 4", M, N);
   int tiles = ((M + TM - 1) / TM) * ((N + TN - 1) / TN);
   long long splits = (sm_count() * 4 + tiles - 1) / tiles;
@@ -154,7 +165,7 @@ int gemm_tn_fp32(const float* a, const float* b, float* out, long long R, int M,
   rps = (rps + TK - 1) / TK * TK;
   splits = (R + rps - 1) / rps;
   dim3 grid((M + TM - 1) / TM, (N + TN - 1) / TN, (unsigned)splits);
-  gemm_tn_fp32_kernel<<<grid, 256, 0, s>>>(a, b, out, R, M, N, rps);
+  gemm_tn_fp32_kernel<<<grid, 256, 0, s>>>(a, b, out, colsum_a, R, M, N, rps);
   return check_launch("dg_gemm_tn(fp32)");
 }
 

@@ -4,9 +4,12 @@
 //   gemm_tn_tc   : out[M,N] += a[R,M]^T . b[R,N]           split over rows, atomics at the end
 //
 // Both are persistent, warp-specialised kernels (one CTA per SM):
-//   warps 0-3  epilogue : tcgen05.ld (thread = accumulator row) -> smem transpose -> coalesced stores
-//   warps 4-7  loaders  : coalesced fp32 LDG.128 -> bf16 -> 128B-swizzled operand blocks in smem
-//   warp  8    MMA      : one elected thread issues tcgen05.mma, tcgen05.commit signals mbarriers
+//   epilogue warps : tcgen05.ld (thread = accumulator row) -> smem transpose -> coalesced stores
+//   loader warps   : coalesced fp32 LDG.128 -> bf16 -> 128B-swizzled operand blocks in smem
+//   MMA warp       : one elected thread issues tcgen05.mma, tcgen05.commit signals mbarriers
+// Two loader groups (alternate ring stages) and, in rows_gemm, two epilogue groups (alternate
+// accumulator buffers) keep >= 64 KB of loads in flight per SM: with ~2 us of loaded HBM latency a
+// single 4-warp group caps the kernel at ~4 TB/s.
 // Activations are fp32 in HBM in this (unfused) form, so both kernels are HBM-bound: the roofline
 // that governs them is bytes moved (a + out, or a + b), not the tensor pipe.
 #include "tc_common.cuh"
@@ -15,7 +18,8 @@
 namespace dg {
 namespace tc {
 
-constexpr int kThreads = 288;
+constexpr int kThreads = 544;            // rows_gemm: warps 0-7 epilogue, 8-15 loaders, 16 MMA
+constexpr int kTnThreads = 416;          // gemm_tn : warps 0-3 epilogue, 4-11 loaders, 12 MMA
 constexpr int kBlk = 128 * 128;           // [128 rows][64 bf16] operand block, bytes
 constexpr int kStage = 36;                // epilogue transpose row pitch (floats): conflict-free v4 access
 
@@ -33,7 +37,7 @@ __host__ __device__ inline RowsSmem rows_smem(int K, int N) {
   s.w = 0;
   s.a = N * K * 2;
   s.stage = s.a + kRingA * kBlk;
-  s.bars = s.stage + 4 * 32 * kStage * 4;
+  s.bars = s.stage + 8 * 32 * kStage * 4;
   s.total = s.bars + 256;
   return s;
 }
@@ -41,7 +45,7 @@ __host__ __device__ inline RowsSmem rows_smem(int K, int N) {
 __global__ void __launch_bounds__(kThreads, 1)
 rows_gemm_tc_kernel(const float* __restrict__ a, const float* __restrict__ w, int w_is_nk,
                     const float* __restrict__ bias, int relu, const float* __restrict__ gate,
-                    float* __restrict__ out, long long R, int K, int N) {
+                    const float* __restrict__ resid, float* __restrict__ out, long long R, int K, int N) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const RowsSmem L = rows_smem(K, N);
@@ -63,7 +67,7 @@ rows_gemm_tc_kernel(const float* __restrict__ a, const float* __restrict__ w, in
     for (int i = 0; i < kAccBufs; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  if (warp == 16) tmem_alloc(tmem_slot, 512);
   // weights: fp32 (L2-resident) -> bf16 -> [kb][N rows][128 B] swizzled, resident for the whole kernel
   for (int idx = tid; idx < N * (K / 8); idx += kThreads) {
     int n, c8;
@@ -86,13 +90,14 @@ rows_gemm_tc_kernel(const float* __restrict__ a, const float* __restrict__ w, in
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 4 && warp < 8) {
-    // ------------------------------------------------------------------ loaders
-    const int lt = tid - 128;
+  if (warp >= 8 && warp < 16) {
+    // ------------------------------------------------------------------ loaders (two groups, alternate chunks)
+    const int lt = (tid - 256) & 127, grp = (tid - 256) >> 7;
     uint32_t chunk = 0;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const long long row0 = tile * 128;
       for (int kb = 0; kb < KB; ++kb, ++chunk) {
+        if ((int)(chunk & 1) != grp) continue;
         const int st = chunk % kRingA;
         mbar_wait(&a_empty[st], ((chunk / kRingA) & 1) ^ 1);
         uint8_t* blk = sA + st * kBlk;
@@ -116,7 +121,7 @@ rows_gemm_tc_kernel(const float* __restrict__ a, const float* __restrict__ w, in
         mbar_arrive(&a_full[st]);
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == 16) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc(128, 128, 0, 0);
@@ -147,19 +152,21 @@ rows_gemm_tc_kernel(const float* __restrict__ a, const float* __restrict__ w, in
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 0-3)
+    // ------------------------------------------------------------------ epilogue (warps 0-7: two groups, alternate units)
     float* stg = sStage + warp * 32 * kStage;
+    const int qw = warp & 3, egrp = warp >> 2;
     uint32_t unit = 0;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const long long row0 = tile * 128 + warp * 32;
+      const long long row0 = tile * 128 + qw * 32;
       for (int nc = 0; nc < NC; ++nc, ++unit) {
+        if ((int)(unit & 1) != egrp) continue;
         const int buf = unit % kAccBufs;
         mbar_wait(&acc_full[buf], (unit / kAccBufs) & 1);
         tc_fence_after();
 #pragma unroll 1
         for (int cg = 0; cg < 4; ++cg) {
           float v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 128 + cg * 32, v);
+          tmem_ld32(tmem_base + ((uint32_t)(qw * 32) << 16) + buf * 128 + cg * 32, v);
           tmem_ld_wait();
           if (cg == 3) {                      // accumulator fully read: hand the TMEM buffer back
             tc_fence_before();
@@ -182,6 +189,10 @@ rows_gemm_tc_kernel(const float* __restrict__ a, const float* __restrict__ w, in
                 float4 g = ld4(gate + grow * N + col);
                 o.x = g.x > 0.f ? o.x : 0.f; o.y = g.y > 0.f ? o.y : 0.f; o.z = g.z > 0.f ? o.z : 0.f; o.w = g.w > 0.f ? o.w : 0.f;
               }
+              if (resid) {
+                float4 z = ld4(resid + grow * N + col);
+                o.x += z.x; o.y += z.y; o.z += z.z; o.w += z.w;
+              }
               st4(out + grow * N + col, o);
             }
           }
@@ -192,7 +203,7 @@ rows_gemm_tc_kernel(const float* __restrict__ a, const float* __restrict__ w, in
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 16) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -204,9 +215,9 @@ rows_gemm_tc_kernel(const float* __restrict__ a, const float* __restrict__ w, in
 constexpr int kTnRows = 64;               // rows (= MMA K extent) per stage
 constexpr int kTnBlk = kTnRows * 128;     // [64 rows][64 ch] block, bytes
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kTnThreads, 1)
 gemm_tn_tc_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
-                  long long R, int M, int N, long long tiles_per_cta, int stages) {
+                  float* __restrict__ colsum_a, long long R, int M, int N, long long tiles_per_cta, int stages) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nblk = (M + N) / 64;                       // operand blocks per stage: a's first, then b's
@@ -229,22 +240,32 @@ gemm_tn_tc_kernel(const float* __restrict__ a, const float* __restrict__ b, floa
     mbar_init(done, 1);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  if (warp == 12) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 4 && warp < 8) {
-    const int lt = tid - 128;
+  if (warp >= 4 && warp < 12) {
+    const int lt = (tid - 128) & 127, grp = (tid - 128) >> 7;     // two loader groups, alternate stages
     uint32_t it_ = 0;
+    // bias gradient on the side: this thread always loads the same 8 channels (j = lt & 7) of every a-block,
+    // so exact fp32 column sums of `a` accumulate in registers for free
+    float cs[6][8];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) cs[i][e] = 0.f;
     for (long long tile = t0; tile < t1; ++tile, ++it_) {
+      if ((int)(it_ & 1) != grp) continue;
       const int st = it_ % stages;
       mbar_wait(&empty[st], ((it_ / stages) & 1) ^ 1);
       uint8_t* base = sOp + st * stage_bytes;
       const long long row0 = tile * kTnRows;
       // items: (block, row, chunk j); 64 rows x 8 chunks = 512 items per block, 4 per thread
-      for (int blk = 0; blk < nblk; ++blk) {
+#pragma unroll
+      for (int blk = 0; blk < 12; ++blk) {
+        if (blk >= nblk) break;
         const bool is_a = blk < M / 64;
         const float* src = is_a ? a : b;
         const int ld = is_a ? M : N, cb = is_a ? blk : blk - M / 64;
@@ -264,11 +285,31 @@ gemm_tn_tc_kernel(const float* __restrict__ a, const float* __restrict__ b, floa
           int item = q * 128 + lt;
           st_block_chunk(base + blk * kTnBlk, item >> 3, item & 7, v[2 * q], v[2 * q + 1]);
         }
+        if (colsum_a != nullptr && blk < 6 && is_a) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            cs[blk][0] += v[2 * q].x; cs[blk][1] += v[2 * q].y; cs[blk][2] += v[2 * q].z; cs[blk][3] += v[2 * q].w;
+            cs[blk][4] += v[2 * q + 1].x; cs[blk][5] += v[2 * q + 1].y; cs[blk][6] += v[2 * q + 1].z; cs[blk][7] += v[2 * q + 1].w;
+          }
+        }
       }
       fence_async_smem();
       mbar_arrive(&full[st]);
     }
-  } else if (warp == 8) {
+    if (colsum_a != nullptr) {
+#pragma unroll
+      for (int blk = 0; blk < 6; ++blk) {
+        if (blk >= M / 64) break;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float s = cs[blk][e];
+          s += __shfl_xor_sync(0xffffffffu, s, 8);
+          s += __shfl_xor_sync(0xffffffffu, s, 16);
+          if (lane < 8 && s != 0.f) atomicAdd(colsum_a + blk * 64 + lane * 8 + e, s);
+        }
+      }
+    }
+  } else if (warp == 12) {
     if (lane == 0) {
       uint32_t it_ = 0;
       for (long long tile = t0; tile < t1; ++tile, ++it_) {
@@ -323,7 +364,7 @@ gemm_tn_tc_kernel(const float* __restrict__ a, const float* __restrict__ b, floa
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 12) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -331,8 +372,8 @@ gemm_tn_tc_kernel(const float* __restrict__ a, const float* __restrict__ b, floa
 
 }  // namespace tc
 
-int rows_gemm_fp32(const float*, const float*, int, const float*, int, const float*, float*, long long, int, int, cudaStream_t);
-int gemm_tn_fp32(const float*, const float*, float*, long long, int, int, cudaStream_t);
+int rows_gemm_fp32(const float*, const float*, int, const float*, int, const float*, const float*, float*, long long, int, int, cudaStream_t);
+int gemm_tn_fp32(const float*, const float*, float*, float*, long long, int, int, cudaStream_t);
 
 // Shapes the tensor-core kernels take; anything else (tiny / odd node-side shapes) runs the fp32
 // CUDA-core kernel -- still on the GPU, never a CPU path.
@@ -343,8 +384,8 @@ static bool rows_tc_ok(int K, int N) {
 }
 
 int rows_gemm_tc(const float* a, const float* w, int w_is_nk, const float* bias, int relu, const float* gate,
-                 float* out, long long R, int K, int N, int prec, cudaStream_t s) {
-  if (prec == DG_PREC_BF16X3 || !rows_tc_ok(K, N)) return rows_gemm_fp32(a, w, w_is_nk, bias, relu, gate, out, R, K, N, s);
+                 const float* resid, float* out, long long R, int K, int N, int prec, cudaStream_t s) {
+  if (prec == DG_PREC_BF16X3 || !rows_tc_ok(K, N)) return rows_gemm_fp32(a, w, w_is_nk, bias, relu, gate, resid, out, R, K, N, s);
   const int smem = tc::rows_smem(K, N).total + 1024;
   static int configured = 0;
   if (configured < smem) {
@@ -354,17 +395,17 @@ int rows_gemm_tc(const float* a, const float* w, int w_is_nk, const float* bias,
   }
   long long tiles = (R + 127) / 128;
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  tc::rows_gemm_tc_kernel<<<grid, tc::kThreads, smem, s>>>(a, w, w_is_nk, bias, relu, gate, out, R, K, N);
+  tc::rows_gemm_tc_kernel<<<grid, tc::kThreads, smem, s>>>(a, w, w_is_nk, bias, relu, gate, resid, out, R, K, N);
   return check_launch("dg_rows_gemm(bf16)");
 }
 
-int gemm_tn_tc(const float* a, const float* b, float* out, long long R, int M, int N, int prec, cudaStream_t s) {
+int gemm_tn_tc(const float* a, const float* b, float* out, float* colsum_a, long long R, int M, int N, int prec, cudaStream_t s) {
   const bool ok = M % 128 == 0 && N % 128 == 0 && M >= 128 && N >= 128 && (M / 128) * N <= 512 && N <= 384 && M <= 384;
-  if (prec == DG_PREC_BF16X3 || !ok) return gemm_tn_fp32(a, b, out, R, M, N, s);
+  if (prec == DG_PREC_BF16X3 || !ok) return gemm_tn_fp32(a, b, out, colsum_a, R, M, N, s);
   const int stage_bytes = (M + N) / 64 * tc::kTnBlk;
   int stages = (200 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
-  if (stages < 2) return gemm_tn_fp32(a, b, out, R, M, N, s);
+  if (stages < 2) return gemm_tn_fp32(a, b, out, colsum_a, R, M, N, s);
   const int smem = stages * stage_bytes + 4 * 32 * tc::kStage * 4 + 256 + 1024;
   static bool configured = false;
   if (!configured) {
@@ -376,7 +417,7 @@ int gemm_tn_tc(const float* a, const float* b, float* out, long long R, int M, i
   long long ctas = tiles < sm_count() ? tiles : sm_count();
   long long per = (tiles + ctas - 1) / ctas;
   ctas = (tiles + per - 1) / per;
-  tc::gemm_tn_tc_kernel<<<(int)ctas, tc::kThreads, smem, s>>>(a, b, out, R, M, N, per, stages);
+  tc::gemm_tn_tc_kernel<<<(int)ctas, tc::kTnThreads, smem, s>>>(a, b, out, colsum_a, R, M, N, per, stages);
   return check_launch("dg_gemm_tn(bf16)");
 }
 

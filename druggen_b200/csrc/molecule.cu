@@ -112,7 +112,7 @@ __global__ void softmax_agg_fwd_kernel(const float* __restrict__ a, const float*
 
 __global__ void softmax_agg_bwd_kernel(const float* __restrict__ dg, const float* __restrict__ a,
                                        const float* __restrict__ v, float* __restrict__ da, float* __restrict__ dv,
-                                       int N, int D, int irows) {
+                                       int accumulate, int N, int D, int irows) {
   extern __shared__ float acc[];
   int t = threadIdx.x, b = blockIdx.y;
   int i0 = blockIdx.x * irows, i1 = min(N, i0 + irows);
@@ -134,7 +134,8 @@ __global__ void softmax_agg_bwd_kernel(const float* __restrict__ dg, const float
 #pragma unroll 4
     for (int j = 0; j < N; ++j) {
       float p = __expf(a[base + (long long)j * D] - m) * inv;
-      da[base + (long long)j * D] = p * dgi * (vb[j * D + t] - gi);
+      const float val = p * dgi * (vb[j * D + t] - gi);
+      da[base + (long long)j * D] = accumulate ? da[base + (long long)j * D] + val : val;
       acc[j * D + t] += p * dgi;
     }
   }
@@ -249,14 +250,14 @@ extern "C" int dg_softmax_agg_fwd(const float* a, const float* v, float* g, int 
   return check_launch("dg_softmax_agg_fwd");
 }
 
-extern "C" int dg_softmax_agg_bwd(const float* dg_, const float* a, const float* v, float* da, float* dv, int B, int N,
-                                  int D, void* stream) {
+extern "C" int dg_softmax_agg_bwd(const float* dg_, const float* a, const float* v, float* da, float* dv, int accumulate,
+                                  int B, int N, int D, void* stream) {
   if (mol_ok(B, N, D, true)) return 1;
   int irows = pick_irows(B, N);
   size_t smem = (size_t)N * D * 4;
   if (set_smem(softmax_agg_bwd_kernel, smem)) return 1;
   dim3 grid((N + irows - 1) / irows, B);
-  softmax_agg_bwd_kernel<<<grid, D, smem, (cudaStream_t)stream>>>(dg_, a, v, da, dv, N, D, irows);
+  softmax_agg_bwd_kernel<<<grid, D, smem, (cudaStream_t)stream>>>(dg_, a, v, da, dv, accumulate, N, D, irows);
   return check_launch("dg_softmax_agg_bwd");
 }
 

@@ -82,32 +82,34 @@ def _chk(*ts):
 
 
 # ----------------------------------------------------------------------------- dense contractions
-def rows_gemm(a, w, w_is_nk: bool, bias=None, relu: bool = False, gate=None):
-    """out[R,N] = epi(a[R,K] . op(w) + bias).
+def rows_gemm(a, w, w_is_nk: bool, bias=None, relu: bool = False, gate=None, resid=None):
+    """out[R,N] = epi(a[R,K] . op(w) + bias) + resid.
 
     w_is_nk: w is [N,K] (nn.Linear layout, out = a w^T) else w is [K,N] (out = a w).
     relu: clamp at 0.  gate: optional [R,N]; out *= (gate > 0)   (ReLU backward fused).
+    resid: optional [R,N] added in the store (gradient accumulation without an extra pass).
     """
-    _chk(a, w, bias, gate)
+    _chk(a, w, bias, gate, resid)
     r, k = a.shape
     n = w.shape[0] if w_is_nk else w.shape[1]
     assert (w.shape[1] if w_is_nk else w.shape[0]) == k, (a.shape, w.shape, w_is_nk)
     out = a.new_empty((r, n))
     if r:
-        _be().rows_gemm(a, w, w_is_nk, bias, relu, gate, out, _precision)
+        _be().rows_gemm(a, w, w_is_nk, bias, relu, gate, out, _precision, resid)
     return out
 
 
-def gemm_tn(a, b, out=None):
+def gemm_tn(a, b, out=None, colsum_a=None):
     """out[M,N] (+)= a[R,M]^T . b[R,N]  -- weight-gradient contraction over rows.
-    ``out`` given => accumulate into it."""
-    _chk(a, b, out)
+    ``out`` given => accumulate into it.  ``colsum_a`` [M] given => += column sums of a (bias gradient,
+    same pass over a)."""
+    _chk(a, b, out, colsum_a)
     assert a.shape[0] == b.shape[0]
     acc = out is not None
     if out is None:
         out = a.new_zeros((a.shape[1], b.shape[1]))
     if a.shape[0]:
-        _be().gemm_tn(a, b, out, acc, _precision)
+        _be().gemm_tn(a, b, out, acc, _precision, colsum_a)
     return out
 
 
@@ -200,12 +202,13 @@ def softmax_agg_fwd(a, v):
     return out
 
 
-def softmax_agg_bwd(dg, a, v):
-    """-> (da, dv)."""
-    _chk(dg, a, v)
-    da, dv = torch.empty_like(a), torch.zeros_like(v)
+def softmax_agg_bwd(dg, a, v, da_accum=None):
+    """-> (da, dv).  ``da_accum`` given => the result is added into it in place (and returned)."""
+    _chk(dg, a, v, da_accum)
+    da = torch.empty_like(a) if da_accum is None else da_accum
+    dv = torch.zeros_like(v)
     if a.numel():
-        _be().softmax_agg_bwd(dg, a, v, da, dv)
+        _be().softmax_agg_bwd(dg, a, v, da, dv, da_accum is not None)
     return da, dv
 
 

@@ -37,15 +37,18 @@ const char* dg_last_error(void);
 int dg_has_tcgen05(void);
 
 /* ---- dense contractions ------------------------------------------------------------------ */
-/* out[R,N] = epi(a[R,K] . op(w) + bias);  w is [N,K] when w_is_nk (nn.Linear layout) else [K,N].
- * epi: optional ReLU, optional gate: out *= (gate[R,N] > 0).
+/* out[R,N] = epi(a[R,K] . op(w) + bias) + resid;  w is [N,K] when w_is_nk (nn.Linear layout) else [K,N].
+ * epi: optional ReLU, optional gate: out *= (gate[R,N] > 0) (ReLU backward); resid[R,N] optional
+ * (gradient accumulation / residual fused into the store).
  * Replaces nn.Linear forward / addmm (layers.py:51,53,111-113,116,127,135) and the dgrad `mm`s. */
 int dg_rows_gemm(const float* a, const float* w, int w_is_nk, const float* bias, int relu,
-                 const float* gate, float* out, long long R, int K, int N, int prec, void* stream);
+                 const float* gate, const float* resid, float* out, long long R, int K, int N, int prec,
+                 void* stream);
 /* out[M,N] += a[R,M]^T . b[R,N]   (split over rows, accumulated atomically: zero `out` first
- * unless accumulating).  Replaces the weight-gradient `mm`s of autograd. */
-int dg_gemm_tn(const float* a, const float* b, float* out, long long R, int M, int N, int prec,
-               void* stream);
+ * unless accumulating); colsum_a[M] += column sums of a (the bias gradient, same pass), optional.
+ * Replaces the weight-gradient `mm`s and bias-gradient `sum`s of autograd. */
+int dg_gemm_tn(const float* a, const float* b, float* out, float* colsum_a, long long R, int M, int N,
+               int prec, void* stream);
 /* out[N] += column sums of a[R,N]   (bias gradients). */
 int dg_colsum(const float* a, float* out, long long R, int N, void* stream);
 /* out = x * (ref > 0), n elements   (threshold_backward of layers.py:52). */
@@ -79,9 +82,9 @@ int dg_modulate_bwd_bwd(const float* uq, const float* uk, const float* ue, const
 /* ---- softmax over key atoms + value aggregation : layers.py:130-134 ------------------------- */
 /* g[b,i,:] = sum_j softmax_j(a[b,i,j,:]) * v[b,j,:] */
 int dg_softmax_agg_fwd(const float* a, const float* v, float* g, int B, int N, int D, void* stream);
-/* da written; dv += (zero first). */
-int dg_softmax_agg_bwd(const float* dg, const float* a, const float* v, float* da, float* dv, int B, int N,
-                       int D, void* stream);
+/* da written (da += when `accumulate`); dv += (zero first). */
+int dg_softmax_agg_bwd(const float* dg, const float* a, const float* v, float* da, float* dv, int accumulate,
+                       int B, int N, int D, void* stream);
 /* g_dg, g_a written; g_v += (zero first). */
 int dg_softmax_agg_bwd_bwd(const float* ua, const float* uv, const float* dg, const float* a, const float* v,
                            float* g_dg, float* g_a, float* g_v, int B, int N, int D, void* stream);

@@ -24,7 +24,7 @@ class EmulBackend:
         return a @ b
 
     # ---- dense
-    def rows_gemm(self, a, w, w_is_nk, bias, relu, gate, out, prec):
+    def rows_gemm(self, a, w, w_is_nk, bias, relu, gate, out, prec, resid=None):
         r = self._mm(a, w.t() if w_is_nk else w, prec)
         if bias is not None:
             r = r + bias
@@ -32,14 +32,18 @@ class EmulBackend:
             r = torch.relu(r)
         if gate is not None:
             r = r * (gate > 0).to(r.dtype)
+        if resid is not None:
+            r = r + resid
         out.copy_(r)
 
-    def gemm_tn(self, a, b, out, accumulate, prec):
+    def gemm_tn(self, a, b, out, accumulate, prec, colsum_a=None):
         r = self._mm(a.t(), b, prec)
         if accumulate:
             out.add_(r)
         else:
             out.copy_(r)
+        if colsum_a is not None:
+            colsum_a.add_(a.sum(0))
 
     def colsum(self, a, out):
         out.copy_(a.sum(0))
@@ -116,12 +120,16 @@ class EmulBackend:
     def softmax_agg_fwd(self, a, v, out):
         out.copy_((torch.softmax(a, dim=2) * v[:, None, :, :]).sum(2))
 
-    def softmax_agg_bwd(self, dg, a, v, da, dv):
+    def softmax_agg_bwd(self, dg, a, v, da, dv, accumulate=False):
         p = torch.softmax(a, dim=2)
         vj = v[:, None, :, :]
         g = (p * vj).sum(2, keepdim=True)
         dgi = dg[:, :, None, :]
-        da.copy_(p * dgi * (vj - g))
+        val = p * dgi * (vj - g)
+        if accumulate:
+            da.add_(val)
+        else:
+            da.copy_(val)
         dv.copy_((p * dgi).sum(1))
 
     def softmax_agg_bwd_bwd(self, ua, uv, dg, a, v, g_dg, g_a, g_v):

@@ -38,6 +38,8 @@ def test_rows_gemm(cuda_dev, prec, R, Kd, Nd):
             got = K.rows_gemm(a, w, w_is_nk, bias, True, gate)
             want = torch.relu(ref + bias.double()) * (gate > 0)
             assert rel_l2(got, want) < 2e-6
+            got = K.rows_gemm(a, w, w_is_nk, None, False, gate, resid=gate)      # fused gradient accumulation
+            assert rel_l2(got, ref * (gate > 0) + gate.double()) < 2e-6
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
@@ -50,8 +52,10 @@ def test_gemm_tn(cuda_dev, prec, R, M, N):
         tc = prec == "bf16" and M % 128 == 0 and N % 128 == 0
         ref = _opr(a, tc).t() @ _opr(b, tc)
         assert rel_l2(got, ref) < 5e-6
-        acc = K.gemm_tn(a, b, out=got.clone())
+        cs = torch.zeros(M, device=cuda_dev)
+        acc = K.gemm_tn(a, b, out=got.clone(), colsum_a=cs)
         assert rel_l2(acc, 2 * ref) < 5e-6
+        assert rel_l2(cs, a.double().sum(0)) < 5e-6          # bias gradient from the same pass, exact fp32 inputs
 
 
 def test_colsum_gate(cuda_dev):
@@ -121,6 +125,8 @@ def test_softmax_agg(cuda_dev, B, N, D):
     EM.softmax_agg_bwd(d(dg), d(a), d(v), da, dv)
     for g_, w_ in zip(K.softmax_agg_bwd(dg, a, v), (da, dv)):
         assert rel_l2(g_, w_) < 1e-5
+    got_da, _ = K.softmax_agg_bwd(dg, a, v, da_accum=ua.clone())
+    assert rel_l2(got_da, da + ua.double()) < 1e-5
     gdg, ga, gv = torch.empty_like(g), torch.empty_like(da), torch.empty_like(g)
     EM.softmax_agg_bwd_bwd(d(ua), d(uv), d(dg), d(a), d(v), gdg, ga, gv)
     for g_, w_ in zip(K.softmax_agg_bwd_bwd(ua, uv, dg, a, v), (gdg, ga, gv)):

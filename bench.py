@@ -136,10 +136,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=512, help="molecules per GPU per step")
+    ap.add_argument("--batch", type=int, default=2048, help="molecules per GPU per step")
     ap.add_argument("--atoms", type=int, default=45)
     ap.add_argument("--depth", type=int, default=8)
-    ap.add_argument("--workload", default="NoTarget", choices=["NoTarget", "AKT1"])
+    ap.add_argument("--workload", default="AKT1", choices=["NoTarget", "AKT1"])
     ap.add_argument("--precision", default=os.environ.get("DRUGGEN_B200_PRECISION", "bf16"))
     ap.add_argument("--cpu-sample", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -239,7 +239,7 @@ def main():
         "dtype": {"bf16": "bf16", "fp32": "f32", "bf16x3": "bf16x3"}[args.precision], "data": "synthetic",
         "config": workload_config(args, bsz), "clocks": clk,
         "e2e": {"value": total / (ms_e2e / 1e3), "unit": "molecules/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8},
-        "gpu_launches": launches,
+        "gpu_launches": launches, "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
         "losses": {"d": losses[0], "g": losses[1]},
         "step_tflops": flops_mol * bsz / (ms / 1e3) / 1e12,
         "step_frac_of_bf16_sustained": flops_mol * bsz / (ms / 1e3) / 1e12 / pk["bf16_tflops_sustained"],

@@ -31,6 +31,8 @@ SIGNATURES = {
     "dg_softmax_agg_fwd": [_P, _P, _P, _I, _I, _I, _P],
     "dg_softmax_agg_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "dg_softmax_agg_bwd_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "dg_attn_scores_fwd": [_P, _P, _P, _P, _F, _P, _P, _I, _I, _I, _P],
+    "dg_attn_scores_bwd": [_P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _I, _I, _I, _P],
     "dg_mlp_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _F, _P, _LL, _P],
 }
 INFO_SYMBOLS = ("dg_abi_version", "dg_last_error", "dg_has_tcgen05")
@@ -119,13 +121,14 @@ class CudaBackend:
     def rows_gemm(self, a, w, w_is_nk, bias, relu, gate, out, prec, resid=None):
         r, k = a.shape
         n = out.shape[1]
-        meta = (f"rows_gemm[K={k},N={n},{prec}]", 2 * r * k * n, _nbytes(a, out, gate, resid), "hbm")
+        tag = ("+gate" if gate is not None else "") + ("+resid" if resid is not None else "") + ("+relu" if relu else "")
+        meta = (f"rows_gemm[R={r},K={k},N={n},{prec}{tag}]", 2 * r * k * n, _nbytes(a, out, gate, resid), "hbm")
         self._call("dg_rows_gemm", meta, _ptr(a), _ptr(w), int(w_is_nk), _ptr(bias), int(relu), _ptr(gate), _ptr(resid),
                    _ptr(out), r, k, n, PREC[prec])
 
     def gemm_tn(self, a, b, out, accumulate, prec, colsum_a=None):
         r, m, n = a.shape[0], a.shape[1], b.shape[1]
-        meta = (f"gemm_tn[M={m},N={n},{prec}]", 2 * r * m * n, _nbytes(a, b), "hbm")
+        meta = (f"gemm_tn[R={r},M={m},N={n},{prec}]", 2 * r * m * n, _nbytes(a, b), "hbm")
         self._call("dg_gemm_tn", meta, _ptr(a), _ptr(b), _ptr(out), _ptr(colsum_a), r, m, n, PREC[prec])
 
     def colsum(self, a, out):
@@ -187,7 +190,21 @@ def _mlp_fwd(self, x, w1, b1, w2, b2, gamma, beta, out, eps, workspace):
                r, d, h, eps, _ptr(workspace), workspace.numel())
 
 
+def _attn_scores_fwd(self, q, k, v, e, c, a, g):
+    b, n, d = q.shape
+    self._call("dg_attn_scores_fwd", ("attn_scores_fwd[fused]", 0, _nbytes(e, a), "hbm"), _ptr(q), _ptr(k), _ptr(v), _ptr(e), c,
+               _ptr(a), _ptr(g), b, n, d)
+
+
+def _attn_scores_bwd(self, dg, da_in, q, k, v, e, c, de, dq, dk, dv):
+    b, n, d = q.shape
+    self._call("dg_attn_scores_bwd", ("attn_scores_bwd[fused]", 0, _nbytes(e, da_in, de), "hbm"), _ptr(dg), _ptr(da_in), _ptr(q),
+               _ptr(k), _ptr(v), _ptr(e), c, _ptr(de), _ptr(dq), _ptr(dk), _ptr(dv), b, n, d)
+
+
 CudaBackend.mlp_fwd = _mlp_fwd
+CudaBackend.attn_scores_fwd = _attn_scores_fwd
+CudaBackend.attn_scores_bwd = _attn_scores_bwd
 
 
 def cuda_backend() -> CudaBackend:

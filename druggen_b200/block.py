@@ -66,6 +66,21 @@ def block_forward(x, y, params: Sequence[torch.Tensor], heads: int, edge_out: bo
     return x_out, y_out
 
 
+def _scores_fwd(q, k, v, e, c):
+    if K.attn_fused_available(q.shape[1], q.shape[2]):
+        return K.attn_scores_fwd(q, k, v, e, c)
+    a = K.modulate_fwd(q, k, e, c)
+    return a, K.softmax_agg_fwd(a, v)
+
+
+def _scores_bwd(dg, da_in, a, q, k, v, e, c):
+    if K.attn_fused_available(q.shape[1], q.shape[2]):
+        return K.attn_scores_bwd(dg, da_in, q, k, v, e, c)
+    da, dv = K.softmax_agg_bwd(dg, a, v, da_accum=da_in)
+    dq, dk, de = K.modulate_bwd(da, q, k, e, c)
+    return de, dq, dk, dv
+
+
 def block_forward_nograd(x, y, params: Sequence[torch.Tensor], heads: int, edge_out: bool = True):
     """Same function as ``block_forward`` for callers that need no graph (inference, the checkpointed
     forward): uses the fused tcgen05 kernels where they exist, raw kernels otherwise."""
@@ -81,9 +96,8 @@ def block_forward_nograd(x, y, params: Sequence[torch.Tensor], heads: int, edge_
     v = K.rows_gemm(x1, p("attn.v.weight"), True, p("attn.v.bias")).view(b, n, d)
     y2d = y.reshape(-1, d)
     e = K.rows_gemm(y2d, p("attn.e.weight"), True, p("attn.e.bias"))
-    a = K.modulate_fwd(q, k, e.view(b, n, n, d), c)
+    a, g = _scores_fwd(q, k, v, e.view(b, n, n, d), c)
     del e
-    g = K.softmax_agg_fwd(a, v)
     on = K.rows_gemm(g.view(-1, d), p("attn.out_n.weight"), True, p("attn.out_n.bias"))
     x3 = K.add_ln_fwd(x1, on, p("ln3.weight"), p("ln3.bias"))
     x_out = K.mlp_fwd(x3, p("mlp.fc1.weight"), p("mlp.fc1.bias"), p("mlp.fc2.weight"), p("mlp.fc2.bias"),
@@ -139,9 +153,8 @@ def block_backward(x, y, dxo, dyo, params: Sequence[torch.Tensor], heads: int, e
     k = K.rows_gemm(x1, p("attn.k.weight"), True, p("attn.k.bias")).view(b, n, d)
     v = K.rows_gemm(x1, p("attn.v.weight"), True, p("attn.v.bias")).view(b, n, d)
     e = K.rows_gemm(y2d, p("attn.e.weight"), True, p("attn.e.bias"))
-    a = K.modulate_fwd(q, k, e.view(b, n, n, d), c)
+    a, g = _scores_fwd(q, k, v, e.view(b, n, n, d), c)
     a2d = a.view(-1, d)
-    g = K.softmax_agg_fwd(a, v)
     g2d = g.view(-1, d)
     on = K.rows_gemm(g2d, p("attn.out_n.weight"), True, p("attn.out_n.bias"))
     x3 = K.add_ln_fwd(x1, on, p("ln3.weight"), p("ln3.bias"))
@@ -179,8 +192,7 @@ def block_backward(x, y, dxo, dyo, params: Sequence[torch.Tensor], heads: int, e
         wgrad("attn.out_e", dz4, a2d)
         da = K.rows_gemm(dz4, p("attn.out_e.weight"), False).view(b, n, n, d)
     # ---- attention: softmax-aggregate, modulation, q/k/v/e projections
-    da, dv = K.softmax_agg_bwd(dg, a, v, da_accum=da)
-    dq, dk, de = K.modulate_bwd(da, q, k, e.view(b, n, n, d), c)
+    de, dq, dk, dv = _scores_bwd(dg, da, a, q, k, v, e.view(b, n, n, d), c)
     del da, a, e
     de2d = de.view(-1, d)
     wgrad("attn.e", de2d, y2d)

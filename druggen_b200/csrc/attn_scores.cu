@@ -1,0 +1,221 @@
+// Fused per-molecule attention-score kernels (fp32), forward and first-order backward of
+//   a_ij = c * q_i * k_j * (e_ij^2 + e_ij)          (layers.py:119-125)
+//   g_i  = sum_j softmax_j(a_ij) * v_j              (layers.py:130-134)
+// in one pass over the edge tensor each:
+//   forward : reads e once, writes a (operand of out_e) and g          -- was modulate_fwd + softmax_agg_fwd
+//   backward: reads e and the incoming da (out_e path) once, writes de; dq, dk, dv reduced on chip
+//                                                                       -- was softmax_agg_bwd + modulate_bwd
+// The scores are recomputed from e, q, k (three FMAs) instead of being re-read; the softmax runs
+// online (running max / rescaled sums), so statistics are one sweep and the gradient sweep's second
+// visit of e hits L2.
+//
+// Decomposition (D == 128): CTA = (molecule b, chunk of query atoms i), 4 warps; a lane owns 4
+// channels (16-byte loads: a warp instruction moves one whole 512-byte edge row), warp w owns a quarter
+// of the key atoms j.  Per query atom the four warps combine their softmax partials through shared
+// memory; dk_j / dv_j accumulators are exclusive to the warp that owns j (shared memory, no atomics
+// inside the loop) and are flushed to global with one atomicAdd per element per CTA.
+#include "common.cuh"
+#include "../../include/druggen_b200.h"
+
+namespace dg {
+
+constexpr int kJU = 4;   // key atoms per load batch: 4 rows x (e, da) x 16 B in flight per lane
+
+struct F4 {
+  float x, y, z, w;
+};
+__device__ __forceinline__ float4 f4mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float4 f4s(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+
+// one channel of the online-softmax update with `n` new scores
+#define DG_ONLINE(ch)                                                            \
+  {                                                                              \
+    float mx = m.ch;                                                             \
+    _Pragma("unroll") for (int u = 0; u < kJU; ++u) if (u < n) mx = fmaxf(mx, av[u].ch); \
+    const float sc = __expf(m.ch - mx);                                          \
+    float ss = s.ch * sc, aa = acc.ch * sc;                                      \
+    _Pragma("unroll") for (int u = 0; u < kJU; ++u) if (u < n) {                  \
+      const float p = __expf(av[u].ch - mx);                                     \
+      ss += p;                                                                   \
+      aa = fmaf(p, vv[u].ch, aa);                                                \
+    }                                                                            \
+    m.ch = mx; s.ch = ss; acc.ch = aa;                                           \
+  }
+
+// combine the 4 warps' (m, s, acc) partials of one channel
+__device__ __forceinline__ void combine4(const float* pm, const float* ps, const float* pa, float& M, float& inv, float& g) {
+  M = fmaxf(fmaxf(pm[0], pm[128]), fmaxf(pm[256], pm[384]));
+  float S = 0.f, A = 0.f;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const float sc = __expf(pm[w * 128] - M);
+    S = fmaf(ps[w * 128], sc, S);
+    A = fmaf(pa[w * 128], sc, A);
+  }
+  inv = 1.f / S;
+  g = A * inv;
+}
+
+template <bool kBwd>
+__global__ void __launch_bounds__(128)
+attn_scores_kernel(const float* __restrict__ dg, const float* __restrict__ da_in, const float* __restrict__ q,
+                   const float* __restrict__ k, const float* __restrict__ v, const float* __restrict__ e, float c,
+                   float* __restrict__ a_out, float* __restrict__ g_out, float* __restrict__ de, float* __restrict__ dq,
+                   float* __restrict__ dk, float* __restrict__ dv, int N, int irows) {
+  constexpr int D = 128;
+  extern __shared__ __align__(16) float sm[];
+  float* red = sm;                       // [2 parity][3 (m,s,acc) | 1 (dq)][4 warps][128]
+  float* sdk = sm + 2 * 3 * 4 * D;       // [N][128]   (backward only)
+  float* sdv = sdk + N * D;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, b = blockIdx.y;
+  const int ch = lane * 4;
+  const int i0 = blockIdx.x * irows, i1 = min(N, i0 + irows);
+  const int jlo = (w * N) / 4, jhi = ((w + 1) * N) / 4;
+  if (kBwd) {
+    for (int j = jlo; j < jhi; ++j) {
+      st4(sdk + j * D + ch, make_float4(0.f, 0.f, 0.f, 0.f));
+      st4(sdv + j * D + ch, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+  }
+  const float* kb = k + (long long)b * N * D + ch;
+  const float* vb = v + (long long)b * N * D + ch;
+  for (int i = i0; i < i1; ++i) {
+    const long long bi = ((long long)b * N + i) * D + ch;
+    const float4 cq = f4s(ld4(q + bi), c);
+    const long long base = (((long long)b * N + i) * N) * D + ch;
+    float* rd = red + ((i - i0) & 1) * 3 * 4 * D;
+    // ---- sweep 1: scores of my key atoms, online softmax partials
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), s = make_float4(0.f, 0.f, 0.f, 0.f), acc = s;
+    for (int j = jlo; j < jhi; j += kJU) {
+      const int n = min(kJU, jhi - j);
+      float4 ev[kJU], av[kJU], vv[kJU];
+#pragma unroll
+      for (int u = 0; u < kJU; ++u)
+        if (u < n) ev[u] = ld4(e + base + (long long)(j + u) * D);
+#pragma unroll
+      for (int u = 0; u < kJU; ++u)
+        if (u < n) {
+          const float4 kj = ld4(kb + (j + u) * D);
+          vv[u] = ld4(vb + (j + u) * D);
+          av[u] = make_float4(cq.x * kj.x * (ev[u].x * ev[u].x + ev[u].x), cq.y * kj.y * (ev[u].y * ev[u].y + ev[u].y),
+                              cq.z * kj.z * (ev[u].z * ev[u].z + ev[u].z), cq.w * kj.w * (ev[u].w * ev[u].w + ev[u].w));
+          if (!kBwd) st4(a_out + base + (long long)(j + u) * D, av[u]);
+        }
+      DG_ONLINE(x) DG_ONLINE(y) DG_ONLINE(z) DG_ONLINE(w)
+    }
+    st4(rd + (0 * 4 + w) * D + ch, m);
+    st4(rd + (1 * 4 + w) * D + ch, s);
+    st4(rd + (2 * 4 + w) * D + ch, acc);
+    __syncthreads();
+    float4 M, inv, g;
+    combine4(rd + ch + 0, rd + 4 * D + ch + 0, rd + 8 * D + ch + 0, M.x, inv.x, g.x);
+    combine4(rd + ch + 1, rd + 4 * D + ch + 1, rd + 8 * D + ch + 1, M.y, inv.y, g.y);
+    combine4(rd + ch + 2, rd + 4 * D + ch + 2, rd + 8 * D + ch + 2, M.z, inv.z, g.z);
+    combine4(rd + ch + 3, rd + 4 * D + ch + 3, rd + 8 * D + ch + 3, M.w, inv.w, g.w);
+    if (!kBwd) {
+      if (w == 0) st4(g_out + bi, g);
+      continue;                                      // next i uses the other parity of `red`
+    }
+    // ---- sweep 2 (backward): gradients for my key atoms
+    const float4 dgi = ld4(dg + bi);
+    float4 sq = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = jlo; j < jhi; j += kJU) {
+      const int n = min(kJU, jhi - j);
+      float4 ev[kJU], din[kJU];
+#pragma unroll
+      for (int u = 0; u < kJU; ++u)
+        if (u < n) {
+          ev[u] = ld4(e + base + (long long)(j + u) * D);
+          din[u] = da_in ? ld4(da_in + base + (long long)(j + u) * D) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+      for (int u = 0; u < kJU; ++u)
+        if (u < n) {
+          const float4 kj = ld4(kb + (j + u) * D), vj = ld4(vb + (j + u) * D);
+          float4 o, gk, gv;
+#define DG_GRAD(chn)                                                              \
+  {                                                                               \
+    const float phi = ev[u].chn * ev[u].chn + ev[u].chn;                          \
+    const float p = __expf(cq.chn * kj.chn * phi - M.chn) * inv.chn;              \
+    const float da = din[u].chn + p * dgi.chn * (vj.chn - g.chn);                 \
+    o.chn = da * cq.chn * kj.chn * (2.f * ev[u].chn + 1.f);                       \
+    sq.chn = fmaf(da * phi, kj.chn, sq.chn);                                      \
+    gk.chn = da * phi * cq.chn;                                                   \
+    gv.chn = p * dgi.chn;                                                         \
+  }
+          DG_GRAD(x) DG_GRAD(y) DG_GRAD(z) DG_GRAD(w)
+#undef DG_GRAD
+          st4(de + base + (long long)(j + u) * D, o);
+          float4 ak = ld4(sdk + (j + u) * D + ch), avv = ld4(sdv + (j + u) * D + ch);
+          st4(sdk + (j + u) * D + ch, make_float4(ak.x + gk.x, ak.y + gk.y, ak.z + gk.z, ak.w + gk.w));
+          st4(sdv + (j + u) * D + ch, make_float4(avv.x + gv.x, avv.y + gv.y, avv.z + gv.z, avv.w + gv.w));
+        }
+    }
+    // dq_i = c * sum over all key atoms: combine the 4 warps (reuse the m-slot of the other parity)
+    float* rq = red + (((i - i0) & 1) ^ 1) * 3 * 4 * D;
+    st4(rq + w * D + ch, sq);
+    __syncthreads();
+    if (w == 0) {
+      float4 t0 = ld4(rq + ch), t1 = ld4(rq + D + ch), t2 = ld4(rq + 2 * D + ch), t3 = ld4(rq + 3 * D + ch);
+      st4(dq + bi, make_float4(c * (t0.x + t1.x + t2.x + t3.x), c * (t0.y + t1.y + t2.y + t3.y), c * (t0.z + t1.z + t2.z + t3.z),
+                               c * (t0.w + t1.w + t2.w + t3.w)));
+    }
+    __syncthreads();                                  // rq is the next query atom's statistics buffer
+  }
+  if (kBwd) {
+    for (int j = jlo; j < jhi; ++j) {
+      const float4 ak = ld4(sdk + j * D + ch), avv = ld4(sdv + j * D + ch);
+      float* pk = dk + ((long long)b * N + j) * D + ch;
+      float* pv = dv + ((long long)b * N + j) * D + ch;
+      atomicAdd(pk, ak.x); atomicAdd(pk + 1, ak.y); atomicAdd(pk + 2, ak.z); atomicAdd(pk + 3, ak.w);
+      atomicAdd(pv, avv.x); atomicAdd(pv + 1, avv.y); atomicAdd(pv + 2, avv.z); atomicAdd(pv + 3, avv.w);
+    }
+  }
+}
+
+static int attn_ok(int B, int N, int D) {
+  if (B <= 0 || N <= 0) return fail("bad shape B=%d N=%d", B, N);
+  if (D != 128) return fail("fused attention-score kernels need D == 128 (got %d)", D);
+  if (B > 65535) return fail("B=%d exceeds the grid.y limit; split the batch", B);
+  if (N < 4) return fail("fused attention-score kernels need N >= 4 (got %d)", N);
+  if ((size_t)(2 * N + 24) * D * 4 > 220 * 1024) return fail("N=%d too large for the per-CTA accumulators", N);
+  return 0;
+}
+static int attn_irows(int B, int N, int ctas_per_sm) {
+  int want = sm_count() * ctas_per_sm;
+  int chunks = (want + B - 1) / B;
+  if (chunks < 1) chunks = 1;
+  if (chunks > N) chunks = N;
+  return (N + chunks - 1) / chunks;
+}
+
+}  // namespace dg
+
+using namespace dg;
+
+extern "C" int dg_attn_scores_fwd(const float* q, const float* k, const float* v, const float* e, float c, float* a,
+                                  float* g, int B, int N, int D, void* stream) {
+  if (attn_ok(B, N, D)) return 1;
+  const size_t smem = (size_t)24 * D * 4;
+  const int irows = attn_irows(B, N, 8);
+  dim3 grid((N + irows - 1) / irows, B);
+  attn_scores_kernel<false><<<grid, 128, smem, (cudaStream_t)stream>>>(nullptr, nullptr, q, k, v, e, c, a, g, nullptr, nullptr,
+                                                                        nullptr, nullptr, N, irows);
+  return check_launch("dg_attn_scores_fwd");
+}
+
+extern "C" int dg_attn_scores_bwd(const float* dg_, const float* da_in, const float* q, const float* k, const float* v,
+                                  const float* e, float c, float* de, float* dq, float* dk, float* dv, int B, int N, int D,
+                                  void* stream) {
+  if (attn_ok(B, N, D)) return 1;
+  const size_t smem = (size_t)(24 + 2 * N) * D * 4;
+  if (smem > 48 * 1024) {
+    cudaError_t er = cudaFuncSetAttribute(attn_scores_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (er != cudaSuccess) return fail("cudaFuncSetAttribute: %s", cudaGetErrorString(er));
+  }
+  const int irows = attn_irows(B, N, 4);
+  dim3 grid((N + irows - 1) / irows, B);
+  attn_scores_kernel<true><<<grid, 128, smem, (cudaStream_t)stream>>>(dg_, da_in, q, k, v, e, c, nullptr, nullptr, de, dq, dk, dv,
+                                                                       N, irows);
+  return check_launch("dg_attn_scores_bwd");
+}

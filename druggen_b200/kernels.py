@@ -235,3 +235,27 @@ def mlp_fwd(x, w1, b1, w2, b2, gamma, beta, eps: float = 1e-5):
         ws = torch.empty(2 * (w1.shape[0] // 128) * 32768, dtype=torch.uint8, device=x.device)
         _be().mlp_fwd(x, w1, b1, w2, b2, gamma, beta, out, eps, ws)
     return out
+
+
+# ----------------------------------------------------------------------------- fused attention scores (fp32)
+def attn_fused_available(n: int, d: int) -> bool:
+    return d == 128 and n >= 4
+
+
+def attn_scores_fwd(q, k, v, e, c: float):
+    """-> (a, g): modulated scores (layers.py:123-125) and softmax-aggregate (layers.py:130-134), e read once."""
+    _chk(q, k, v, e)
+    a, g = torch.empty_like(e), torch.empty_like(q)
+    if e.numel():
+        _be().attn_scores_fwd(q, k, v, e, c, a, g)
+    return a, g
+
+
+def attn_scores_bwd(dg, da_in, q, k, v, e, c: float):
+    """-> (de, dq, dk, dv) from dg (softmax path) and da_in (out_e path; may be None)."""
+    _chk(dg, da_in, q, k, v, e)
+    de, dq = torch.empty_like(e), torch.empty_like(q)
+    dk, dv = torch.zeros_like(k), torch.zeros_like(v)
+    if e.numel():
+        _be().attn_scores_bwd(dg, da_in, q, k, v, e, c, de, dq, dk, dv)
+    return de, dq, dk, dv

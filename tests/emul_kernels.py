@@ -149,3 +149,16 @@ class EmulBackend:
         h = torch.relu(self._mm(x, w1.t(), "bf16") + b1)
         z = x + self._mm(h, w2.t(), "bf16") + b2
         self.add_ln_fwd(z, None, gamma, beta, out, eps)
+
+    def attn_scores_fwd(self, q, k, v, e, c, a, g):
+        self.modulate_fwd(q, k, e, c, a)
+        self.softmax_agg_fwd(a, v, g)
+
+    def attn_scores_bwd(self, dg, da_in, q, k, v, e, c, de, dq, dk, dv):
+        a = torch.empty_like(e)
+        self.modulate_fwd(q, k, e, c, a)
+        da = torch.empty_like(e)
+        self.softmax_agg_bwd(dg, a, v, da, dv)
+        if da_in is not None:
+            da = da + da_in
+        self.modulate_bwd(da, q, k, e, c, dq, dk, de)

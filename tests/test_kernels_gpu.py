@@ -159,3 +159,20 @@ def test_fused_mlp_fwd(cuda_dev, R, H):
         got = K.mlp_fwd(x, w1, b1, w2, b2, gamma, beta)
     assert rel_l2(got, want) < 2e-4, rel_l2(got, want)   # bf16 rounding of the hidden can flip by 1 ulp vs fp64 emulation
     assert float((got.double() - want).abs().max()) < 5e-2
+
+
+@pytest.mark.parametrize("B,N", [(1, 4), (3, 9), (2, 45), (300, 9), (5, 90), (40, 45)])
+def test_fused_attn_scores(cuda_dev, B, N):
+    D, c = 128, 0.25
+    q, k, v = rnd(cuda_dev, B, N, D), rnd(cuda_dev, B, N, D, seed=1), rnd(cuda_dev, B, N, D, seed=2)
+    e, dg, da_in = rnd(cuda_dev, B, N, N, D, seed=3), rnd(cuda_dev, B, N, D, seed=4), rnd(cuda_dev, B, N, N, D, seed=5)
+    d = lambda t: t.double()  # noqa: E731
+    a64, g64 = torch.empty_like(d(e)), torch.empty_like(d(q))
+    EM.attn_scores_fwd(d(q), d(k), d(v), d(e), c, a64, g64)
+    a, g = K.attn_scores_fwd(q, k, v, e, c)
+    assert rel_l2(a, a64) < 2e-6 and rel_l2(g, g64) < 1e-5
+    for din in (da_in, None):
+        de64, dq64, dk64, dv64 = torch.empty_like(a64), torch.empty_like(g64), torch.empty_like(g64), torch.empty_like(g64)
+        EM.attn_scores_bwd(d(dg), None if din is None else d(din), d(q), d(k), d(v), d(e), c, de64, dq64, dk64, dv64)
+        for got, want in zip(K.attn_scores_bwd(dg, din, q, k, v, e, c), (de64, dq64, dk64, dv64)):
+            assert rel_l2(got, want) < 2e-5

@@ -177,23 +177,30 @@ rows_gemm_tc_kernel(const float* __restrict__ a, const float* __restrict__ w, in
           __syncwarp();
           const int col = nc * 128 + cg * 32 + (lane & 7) * 4;
           const float4 bz = bias ? ld4(bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+          // two batches of 4 rows: all global loads of a batch (gate, resid) are issued before any is used
 #pragma unroll
-          for (int rr = 0; rr < 8; ++rr) {
-            const int r = rr * 4 + (lane >> 3);
-            const long long grow = row0 + r;
-            if (grow < R) {
-              float4 o = ld4(stg + r * kStage + (lane & 7) * 4);
-              o.x += bz.x; o.y += bz.y; o.z += bz.z; o.w += bz.w;
-              if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-              if (gate) {
-                float4 g = ld4(gate + grow * N + col);
-                o.x = g.x > 0.f ? o.x : 0.f; o.y = g.y > 0.f ? o.y : 0.f; o.z = g.z > 0.f ? o.z : 0.f; o.w = g.w > 0.f ? o.w : 0.f;
-              }
-              if (resid) {
-                float4 z = ld4(resid + grow * N + col);
-                o.x += z.x; o.y += z.y; o.z += z.z; o.w += z.w;
-              }
-              st4(out + grow * N + col, o);
+          for (int half = 0; half < 2; ++half) {
+            float4 o[4], gz[4], rz[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int r = (half * 4 + u) * 4 + (lane >> 3);
+              const long long grow = row0 + r;
+              o[u] = ld4(stg + r * kStage + (lane & 7) * 4);
+              gz[u] = (gate && grow < R) ? ld4(gate + grow * N + col) : make_float4(1.f, 1.f, 1.f, 1.f);
+              rz[u] = (resid && grow < R) ? ld4(resid + grow * N + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int r = (half * 4 + u) * 4 + (lane >> 3);
+              const long long grow = row0 + r;
+              float4 v4 = o[u];
+              v4.x += bz.x; v4.y += bz.y; v4.z += bz.z; v4.w += bz.w;
+              if (relu) { v4.x = fmaxf(v4.x, 0.f); v4.y = fmaxf(v4.y, 0.f); v4.z = fmaxf(v4.z, 0.f); v4.w = fmaxf(v4.w, 0.f); }
+              v4.x = (gz[u].x > 0.f ? v4.x : 0.f) + rz[u].x;
+              v4.y = (gz[u].y > 0.f ? v4.y : 0.f) + rz[u].y;
+              v4.z = (gz[u].z > 0.f ? v4.z : 0.f) + rz[u].z;
+              v4.w = (gz[u].w > 0.f ? v4.w : 0.f) + rz[u].w;
+              if (grow < R) st4(out + grow * N + col, v4);
             }
           }
           __syncwarp();
@@ -263,33 +270,42 @@ gemm_tn_tc_kernel(const float* __restrict__ a, const float* __restrict__ b, floa
       uint8_t* base = sOp + st * stage_bytes;
       const long long row0 = tile * kTnRows;
       // items: (block, row, chunk j); 64 rows x 8 chunks = 512 items per block, 4 per thread
+      // blocks are loaded in pairs (nblk is even): 16 independent 16-byte loads in flight per thread
 #pragma unroll
-      for (int blk = 0; blk < 12; ++blk) {
-        if (blk >= nblk) break;
-        const bool is_a = blk < M / 64;
-        const float* src = is_a ? a : b;
-        const int ld = is_a ? M : N, cb = is_a ? blk : blk - M / 64;
-        float4 v[8];
+      for (int bp = 0; bp < 6; ++bp) {
+        if (2 * bp >= nblk) break;
+        float4 v[16];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          int item = q * 128 + lt, r = item >> 3, j = item & 7;
-          if (row0 + r < R) {
-            const float* p = src + (row0 + r) * ld + cb * 64 + j * 8;
-            v[2 * q] = ld4(p); v[2 * q + 1] = ld4(p + 4);
-          } else {
-            v[2 * q] = v[2 * q + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int h = 0; h < 2; ++h) {
+          const int blk = 2 * bp + h;
+          const bool is_a = blk < M / 64;
+          const float* src = is_a ? a : b;
+          const int ld = is_a ? M : N, cb = is_a ? blk : blk - M / 64;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            int item = q * 128 + lt, r = item >> 3, j = item & 7;
+            if (row0 + r < R) {
+              const float* p = src + (row0 + r) * ld + cb * 64 + j * 8;
+              v[h * 8 + 2 * q] = ld4(p); v[h * 8 + 2 * q + 1] = ld4(p + 4);
+            } else {
+              v[h * 8 + 2 * q] = v[h * 8 + 2 * q + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
           }
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          int item = q * 128 + lt;
-          st_block_chunk(base + blk * kTnBlk, item >> 3, item & 7, v[2 * q], v[2 * q + 1]);
-        }
-        if (colsum_a != nullptr && blk < 6 && is_a) {
+        for (int h = 0; h < 2; ++h) {
+          const int blk = 2 * bp + h;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            cs[blk][0] += v[2 * q].x; cs[blk][1] += v[2 * q].y; cs[blk][2] += v[2 * q].z; cs[blk][3] += v[2 * q].w;
-            cs[blk][4] += v[2 * q + 1].x; cs[blk][5] += v[2 * q + 1].y; cs[blk][6] += v[2 * q + 1].z; cs[blk][7] += v[2 * q + 1].w;
+            int item = q * 128 + lt;
+            st_block_chunk(base + blk * kTnBlk, item >> 3, item & 7, v[h * 8 + 2 * q], v[h * 8 + 2 * q + 1]);
+          }
+          if (colsum_a != nullptr && blk < 6 && blk < M / 64) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              cs[blk][0] += v[h * 8 + 2 * q].x; cs[blk][1] += v[h * 8 + 2 * q].y; cs[blk][2] += v[h * 8 + 2 * q].z; cs[blk][3] += v[h * 8 + 2 * q].w;
+              cs[blk][4] += v[h * 8 + 2 * q + 1].x; cs[blk][5] += v[h * 8 + 2 * q + 1].y; cs[blk][6] += v[h * 8 + 2 * q + 1].z; cs[blk][7] += v[h * 8 + 2 * q + 1].w;
+            }
           }
         }
       }

@@ -18,8 +18,8 @@ _P, _LL, _I, _F = C.c_void_p, C.c_longlong, C.c_int, C.c_float
 
 # name -> argument ctypes (every entry returns int); mirrors include/druggen_b200.h
 SIGNATURES = {
-    "dg_rows_gemm": [_P, _P, _I, _P, _I, _P, _P, _P, _LL, _I, _I, _I, _P],
-    "dg_gemm_tn": [_P, _P, _P, _P, _LL, _I, _I, _I, _P],
+    "dg_rows_gemm": [_P, _P, _I, _P, _I, _P, _P, _P, _LL, _I, _I, _I, _I, _P],
+    "dg_gemm_tn": [_P, _P, _P, _P, _LL, _I, _I, _I, _I, _P],
     "dg_colsum": [_P, _P, _LL, _I, _P],
     "dg_gate_mul": [_P, _P, _P, _LL, _P],
     "dg_add_ln_fwd": [_P, _P, _P, _P, _P, _LL, _I, _F, _P],
@@ -122,14 +122,19 @@ class CudaBackend:
         r, k = a.shape
         n = out.shape[1]
         tag = ("+gate" if gate is not None else "") + ("+resid" if resid is not None else "") + ("+relu" if relu else "")
+        tag += (",a16" if a.dtype == torch.bfloat16 else "") + (",o16" if out.dtype == torch.bfloat16 else "")
         meta = (f"rows_gemm[R={r},K={k},N={n},{prec}{tag}]", 2 * r * k * n, _nbytes(a, out, gate, resid), "hbm")
+        bf = torch.bfloat16
+        flags = (1 if a.dtype == bf else 0) | (2 if out.dtype == bf else 0) | (4 if gate is not None and gate.dtype == bf else 0)
         self._call("dg_rows_gemm", meta, _ptr(a), _ptr(w), int(w_is_nk), _ptr(bias), int(relu), _ptr(gate), _ptr(resid),
-                   _ptr(out), r, k, n, PREC[prec])
+                   _ptr(out), r, k, n, PREC[prec], flags)
 
     def gemm_tn(self, a, b, out, accumulate, prec, colsum_a=None):
         r, m, n = a.shape[0], a.shape[1], b.shape[1]
-        meta = (f"gemm_tn[R={r},M={m},N={n},{prec}]", 2 * r * m * n, _nbytes(a, b), "hbm")
-        self._call("dg_gemm_tn", meta, _ptr(a), _ptr(b), _ptr(out), _ptr(colsum_a), r, m, n, PREC[prec])
+        tag = (",a16" if a.dtype == torch.bfloat16 else "") + (",b16" if b.dtype == torch.bfloat16 else "")
+        meta = (f"gemm_tn[R={r},M={m},N={n},{prec}{tag}]", 2 * r * m * n, _nbytes(a, b), "hbm")
+        flags = (1 if a.dtype == torch.bfloat16 else 0) | (2 if b.dtype == torch.bfloat16 else 0)
+        self._call("dg_gemm_tn", meta, _ptr(a), _ptr(b), _ptr(out), _ptr(colsum_a), r, m, n, PREC[prec], flags)
 
     def colsum(self, a, out):
         self._call("dg_colsum", ("colsum", 0, _nbytes(a), "hbm"), _ptr(a), _ptr(out), a.shape[0], a.shape[1])

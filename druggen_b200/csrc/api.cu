@@ -5,8 +5,8 @@
 namespace dg {
 int rows_gemm_fp32(const float*, const float*, int, const float*, int, const float*, const float*, float*, long long, int, int, cudaStream_t);
 int gemm_tn_fp32(const float*, const float*, float*, float*, long long, int, int, cudaStream_t);
-int rows_gemm_tc(const float*, const float*, int, const float*, int, const float*, const float*, float*, long long, int, int, int, cudaStream_t);
-int gemm_tn_tc(const float*, const float*, float*, float*, long long, int, int, int, cudaStream_t);
+int rows_gemm_tc(const void*, const float*, int, const float*, int, const void*, const float*, void*, long long, int, int, int, int, cudaStream_t);
+int gemm_tn_tc(const void*, const void*, float*, float*, long long, int, int, int, int, cudaStream_t);
 }  // namespace dg
 
 using namespace dg;
@@ -21,21 +21,27 @@ extern "C" int dg_has_tcgen05(void) {
   return major == 10;
 }
 
-extern "C" int dg_rows_gemm(const float* a, const float* w, int w_is_nk, const float* bias, int relu,
-                            const float* gate, const float* resid, float* out, long long R, int K, int N, int prec,
-                            void* stream) {
+extern "C" int dg_rows_gemm(const void* a, const float* w, int w_is_nk, const float* bias, int relu,
+                            const void* gate, const float* resid, void* out, long long R, int K, int N, int prec,
+                            int flags, void* stream) {
   if (R <= 0 || K <= 0 || N <= 0) return fail("dg_rows_gemm: bad shape R=%lld K=%d N=%d", R, K, N);
-  if (prec == DG_PREC_FP32) return rows_gemm_fp32(a, w, w_is_nk, bias, relu, gate, resid, out, R, K, N, (cudaStream_t)stream);
+  if (prec == DG_PREC_FP32) {
+    if (flags) return fail("dg_rows_gemm: bf16 storage flags need the tensor-core precision");
+    return rows_gemm_fp32((const float*)a, w, w_is_nk, bias, relu, (const float*)gate, resid, (float*)out, R, K, N, (cudaStream_t)stream);
+  }
   if (prec == DG_PREC_BF16 || prec == DG_PREC_BF16X3)
-    return rows_gemm_tc(a, w, w_is_nk, bias, relu, gate, resid, out, R, K, N, prec, (cudaStream_t)stream);
+    return rows_gemm_tc(a, w, w_is_nk, bias, relu, gate, resid, out, R, K, N, prec, flags, (cudaStream_t)stream);
   return fail("dg_rows_gemm: unknown precision %d", prec);
 }
 
-extern "C" int dg_gemm_tn(const float* a, const float* b, float* out, float* colsum_a, long long R, int M, int N,
-                          int prec, void* stream) {
+extern "C" int dg_gemm_tn(const void* a, const void* b, float* out, float* colsum_a, long long R, int M, int N,
+                          int prec, int flags, void* stream) {
   if (R <= 0 || M <= 0 || N <= 0) return fail("dg_gemm_tn: bad shape R=%lld M=%d N=%d", R, M, N);
-  if (prec == DG_PREC_FP32) return gemm_tn_fp32(a, b, out, colsum_a, R, M, N, (cudaStream_t)stream);
+  if (prec == DG_PREC_FP32) {
+    if (flags) return fail("dg_gemm_tn: bf16 storage flags need the tensor-core precision");
+    return gemm_tn_fp32((const float*)a, (const float*)b, out, colsum_a, R, M, N, (cudaStream_t)stream);
+  }
   if (prec == DG_PREC_BF16 || prec == DG_PREC_BF16X3)
-    return gemm_tn_tc(a, b, out, colsum_a, R, M, N, prec, (cudaStream_t)stream);
+    return gemm_tn_tc(a, b, out, colsum_a, R, M, N, prec, flags, (cudaStream_t)stream);
   return fail("dg_gemm_tn: unknown precision %d", prec);
 }

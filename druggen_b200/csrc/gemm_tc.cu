@@ -45,7 +45,10 @@ __host__ __device__ inline RowsSmem rows_smem(int K, int N) {
 __global__ void __launch_bounds__(kThreads, 1)
 rows_gemm_tc_kernel(const float* __restrict__ a, const float* __restrict__ w, int w_is_nk,
                     const float* __restrict__ bias, int relu, const float* __restrict__ gate,
-                    const float* __restrict__ resid, float* __restrict__ out, long long R, int K, int N) {
+                    const float* __restrict__ resid, float* __restrict__ out, long long R, int K, int N, int flags) {
+  const uint16_t* a16 = reinterpret_cast<const uint16_t*>(a);        // bf16 views (flags select which are live)
+  const uint16_t* gate16 = reinterpret_cast<const uint16_t*>(gate);
+  uint16_t* out16 = reinterpret_cast<uint16_t*>(out);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const RowsSmem L = rows_smem(K, N);
@@ -101,6 +104,22 @@ rows_gemm_tc_kernel(const float* __restrict__ a, const float* __restrict__ w, in
         const int st = chunk % kRingA;
         mbar_wait(&a_empty[st], ((chunk / kRingA) & 1) ^ 1);
         uint8_t* blk = sA + st * kBlk;
+        if (flags & DG_A_BF16) {            // operand already bf16 in HBM: plain 16-byte chunk copies
+          uint4 c16[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            int item = it * 128 + lt, r = item >> 3, j = item & 7;
+            c16[it] = (row0 + r < R) ? *reinterpret_cast<const uint4*>(a16 + (row0 + r) * K + kb * 64 + j * 8) : make_uint4(0, 0, 0, 0);
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            int item = it * 128 + lt, r = item >> 3, j = item & 7;
+            *reinterpret_cast<uint4*>(blk + r * 128 + ((j ^ (r & 7)) << 4)) = c16[it];
+          }
+          fence_async_smem();
+          mbar_arrive(&a_full[st]);
+          continue;
+        }
         float4 v[16];
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
@@ -161,6 +180,62 @@ rows_gemm_tc_kernel(const float* __restrict__ a, const float* __restrict__ w, in
       for (int nc = 0; nc < NC; ++nc, ++unit) {
         if ((int)(unit & 1) != egrp) continue;
         const int buf = unit % kAccBufs;
+        if (flags & DG_OUT_BF16) {
+          // bf16 output (+ optional bf16 sign gate): lane = (row it*8 + lane/4, 8 columns); the whole unit's gate
+          // (32 rows x 128 cols) is requested before the accumulator is even waited for
+          const int c8 = (lane & 3) * 8;
+          uint4 gq[8];                      // ring over column groups: cg and cg+1 in flight
+          auto gate_fetch = [&](int cg) {
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const long long grow = row0 + it * 8 + (lane >> 2);
+              gq[(cg & 1) * 4 + it] = (grow < R) ? *reinterpret_cast<const uint4*>(gate16 + grow * N + nc * 128 + cg * 32 + c8)
+                                                 : make_uint4(0, 0, 0, 0);
+            }
+          };
+          if (gate) { gate_fetch(0); gate_fetch(1); }
+          mbar_wait(&acc_full[buf], (unit / kAccBufs) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int cg = 0; cg < 4; ++cg) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(qw * 32) << 16) + buf * 128 + cg * 32, v);
+            tmem_ld_wait();
+            if (cg == 3) { tc_fence_before(); mbar_arrive(&acc_empty[buf]); }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) st4(stg + lane * kStage + i * 4, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+            __syncwarp();
+            const int col = nc * 128 + cg * 32 + c8;
+            const float4 b0 = bias ? ld4(bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 b1 = bias ? ld4(bias + col + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int r = it * 8 + (lane >> 2);
+              const long long grow = row0 + r;
+              float4 lo = ld4(stg + r * kStage + c8), hi = ld4(stg + r * kStage + c8 + 4);
+              float f[8] = {lo.x + b0.x, lo.y + b0.y, lo.z + b0.z, lo.w + b0.w, hi.x + b1.x, hi.y + b1.y, hi.z + b1.z, hi.w + b1.w};
+              if (relu) {
+#pragma unroll
+                for (int e8 = 0; e8 < 8; ++e8) f[e8] = fmaxf(f[e8], 0.f);
+              }
+              if (gate) {       // bf16 > 0  <=>  its 16 bits, read as a signed short, are > 0
+                const uint4 gb = gq[(cg & 1) * 4 + it];
+                const uint32_t gw[4] = {gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+                for (int e8 = 0; e8 < 8; ++e8) {
+                  const short bits = (short)((gw[e8 >> 1] >> ((e8 & 1) * 16)) & 0xFFFF);
+                  f[e8] = bits > 0 ? f[e8] : 0.f;
+                }
+              }
+              if (grow < R)
+                *reinterpret_cast<uint4*>(out16 + grow * N + col) =
+                    make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+            }
+            if (gate && cg + 2 < 4) gate_fetch(cg + 2);
+            __syncwarp();
+          }
+          continue;
+        }
         mbar_wait(&acc_full[buf], (unit / kAccBufs) & 1);
         tc_fence_after();
 #pragma unroll 1
@@ -224,7 +299,7 @@ constexpr int kTnBlk = kTnRows * 128;     // [64 rows][64 ch] block, bytes
 
 __global__ void __launch_bounds__(kTnThreads, 1)
 gemm_tn_tc_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
-                  float* __restrict__ colsum_a, long long R, int M, int N, long long tiles_per_cta, int stages) {
+                  float* __restrict__ colsum_a, long long R, int M, int N, long long tiles_per_cta, int stages, int flags) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nblk = (M + N) / 64;                       // operand blocks per stage: a's first, then b's
@@ -281,14 +356,32 @@ gemm_tn_tc_kernel(const float* __restrict__ a, const float* __restrict__ b, floa
           const bool is_a = blk < M / 64;
           const float* src = is_a ? a : b;
           const int ld = is_a ? M : N, cb = is_a ? blk : blk - M / 64;
+          const bool src16 = is_a ? (flags & DG_A_BF16) : (flags & DG_OUT_BF16);
+          if (src16) {                // bf16 in HBM: issue the four 16-byte loads, then widen (exactly)
+            uint4 c16[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            int item = q * 128 + lt, r = item >> 3, j = item & 7;
-            if (row0 + r < R) {
-              const float* p = src + (row0 + r) * ld + cb * 64 + j * 8;
-              v[h * 8 + 2 * q] = ld4(p); v[h * 8 + 2 * q + 1] = ld4(p + 4);
-            } else {
-              v[h * 8 + 2 * q] = v[h * 8 + 2 * q + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = 0; q < 4; ++q) {
+              int item = q * 128 + lt, r = item >> 3, j = item & 7;
+              c16[q] = (row0 + r < R) ? *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(src) + (row0 + r) * ld + cb * 64 + j * 8)
+                                      : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              v[h * 8 + 2 * q] = make_float4(__uint_as_float(c16[q].x << 16), __uint_as_float(c16[q].x & 0xFFFF0000u),
+                                             __uint_as_float(c16[q].y << 16), __uint_as_float(c16[q].y & 0xFFFF0000u));
+              v[h * 8 + 2 * q + 1] = make_float4(__uint_as_float(c16[q].z << 16), __uint_as_float(c16[q].z & 0xFFFF0000u),
+                                                 __uint_as_float(c16[q].w << 16), __uint_as_float(c16[q].w & 0xFFFF0000u));
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              int item = q * 128 + lt, r = item >> 3, j = item & 7;
+              if (row0 + r < R) {
+                const float* p = src + (row0 + r) * ld + cb * 64 + j * 8;
+                v[h * 8 + 2 * q] = ld4(p); v[h * 8 + 2 * q + 1] = ld4(p + 4);
+              } else {
+                v[h * 8 + 2 * q] = v[h * 8 + 2 * q + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
             }
           }
         }
@@ -399,9 +492,18 @@ static bool rows_tc_ok(int K, int N) {
   return tc::rows_smem(K, N).total + 1024 <= 227 * 1024;
 }
 
-int rows_gemm_tc(const float* a, const float* w, int w_is_nk, const float* bias, int relu, const float* gate,
-                 const float* resid, float* out, long long R, int K, int N, int prec, cudaStream_t s) {
-  if (prec == DG_PREC_BF16X3 || !rows_tc_ok(K, N)) return rows_gemm_fp32(a, w, w_is_nk, bias, relu, gate, resid, out, R, K, N, s);
+int rows_gemm_tc(const void* a_, const float* w, int w_is_nk, const float* bias, int relu, const void* gate_,
+                 const float* resid, void* out_, long long R, int K, int N, int prec, int flags, cudaStream_t s) {
+  const float* a = (const float*)a_;
+  const float* gate = (const float*)gate_;
+  float* out = (float*)out_;
+  if (prec == DG_PREC_BF16X3 || !rows_tc_ok(K, N)) {
+    if (flags) return fail("dg_rows_gemm: bf16 storage is only available for the tcgen05 shapes (K=%d N=%d)", K, N);
+    return rows_gemm_fp32(a, w, w_is_nk, bias, relu, gate, resid, out, R, K, N, s);
+  }
+  if ((flags & DG_OUT_BF16) && (resid || (gate && !(flags & DG_GATE_BF16))))
+    return fail("dg_rows_gemm: a bf16 output takes no resid and only a bf16 gate");
+  if (!(flags & DG_OUT_BF16) && (flags & DG_GATE_BF16)) return fail("dg_rows_gemm: a bf16 gate needs a bf16 output");
   const int smem = tc::rows_smem(K, N).total + 1024;
   static int configured = 0;
   if (configured < smem) {
@@ -411,17 +513,23 @@ int rows_gemm_tc(const float* a, const float* w, int w_is_nk, const float* bias,
   }
   long long tiles = (R + 127) / 128;
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  tc::rows_gemm_tc_kernel<<<grid, tc::kThreads, smem, s>>>(a, w, w_is_nk, bias, relu, gate, resid, out, R, K, N);
+  tc::rows_gemm_tc_kernel<<<grid, tc::kThreads, smem, s>>>(a, w, w_is_nk, bias, relu, gate, resid, out, R, K, N, flags);
   return check_launch("dg_rows_gemm(bf16)");
 }
 
-int gemm_tn_tc(const float* a, const float* b, float* out, float* colsum_a, long long R, int M, int N, int prec, cudaStream_t s) {
+int gemm_tn_tc(const void* a_, const void* b_, float* out, float* colsum_a, long long R, int M, int N, int prec, int flags,
+               cudaStream_t s) {
+  const float* a = (const float*)a_;
+  const float* b = (const float*)b_;
   const bool ok = M % 128 == 0 && N % 128 == 0 && M >= 128 && N >= 128 && (M / 128) * N <= 512 && N <= 384 && M <= 384;
-  if (prec == DG_PREC_BF16X3 || !ok) return gemm_tn_fp32(a, b, out, colsum_a, R, M, N, s);
+  if (prec == DG_PREC_BF16X3 || !ok) {
+    if (flags) return fail("dg_gemm_tn: bf16 storage is only available for the tcgen05 shapes (M=%d N=%d)", M, N);
+    return gemm_tn_fp32(a, b, out, colsum_a, R, M, N, s);
+  }
   const int stage_bytes = (M + N) / 64 * tc::kTnBlk;
   int stages = (200 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
-  if (stages < 2) return gemm_tn_fp32(a, b, out, colsum_a, R, M, N, s);
+  if (stages < 2) return fail("dg_gemm_tn: shape does not fit shared memory");
   const int smem = stages * stage_bytes + 4 * 32 * tc::kStage * 4 + 256 + 1024;
   static bool configured = false;
   if (!configured) {
@@ -433,7 +541,7 @@ int gemm_tn_tc(const float* a, const float* b, float* out, float* colsum_a, long
   long long ctas = tiles < sm_count() ? tiles : sm_count();
   long long per = (tiles + ctas - 1) / ctas;
   ctas = (tiles + per - 1) / per;
-  tc::gemm_tn_tc_kernel<<<(int)ctas, tc::kTnThreads, smem, s>>>(a, b, out, colsum_a, R, M, N, per, stages);
+  tc::gemm_tn_tc_kernel<<<(int)ctas, tc::kTnThreads, smem, s>>>(a, b, out, colsum_a, R, M, N, per, stages, flags);
   return check_launch("dg_gemm_tn(bf16)");
 }
 

@@ -67,7 +67,7 @@ def _be():
     return _lib.cuda_backend()
 
 
-def _chk(*ts):
+def _chk(*ts, bf16_ok=False):
     if _test_backend is not None:
         return
     for t in ts:
@@ -75,25 +75,29 @@ def _chk(*ts):
             continue
         if not t.is_cuda:
             raise RuntimeError("druggen_b200 kernels run on CUDA tensors only (no CPU fallback)")
-        if t.dtype != torch.float32:
+        if t.dtype != torch.float32 and not (bf16_ok and t.dtype == torch.bfloat16):
             raise RuntimeError(f"druggen_b200 kernels take fp32 tensors, got {t.dtype}")
         if not t.is_contiguous():
             raise RuntimeError("druggen_b200 kernels take contiguous tensors")
 
 
 # ----------------------------------------------------------------------------- dense contractions
-def rows_gemm(a, w, w_is_nk: bool, bias=None, relu: bool = False, gate=None, resid=None):
+def rows_gemm(a, w, w_is_nk: bool, bias=None, relu: bool = False, gate=None, resid=None, out_bf16: bool = False):
     """out[R,N] = epi(a[R,K] . op(w) + bias) + resid.
 
     w_is_nk: w is [N,K] (nn.Linear layout, out = a w^T) else w is [K,N] (out = a w).
     relu: clamp at 0.  gate: optional [R,N]; out *= (gate > 0)   (ReLU backward fused).
     resid: optional [R,N] added in the store (gradient accumulation without an extra pass).
+    bf16 storage (tensor-core mode, shapes the tcgen05 kernel takes): ``a`` and ``gate`` may be bf16 tensors and
+    ``out_bf16`` stores the result as bf16 -- for tensors that are only ever contraction operands or sign masks
+    (the MLP hidden activation and its gradient) this loses nothing: the contraction rounds them to bf16 anyway.
     """
-    _chk(a, w, bias, gate, resid)
+    _chk(w, bias, resid)
+    _chk(a, gate, bf16_ok=True)
     r, k = a.shape
     n = w.shape[0] if w_is_nk else w.shape[1]
     assert (w.shape[1] if w_is_nk else w.shape[0]) == k, (a.shape, w.shape, w_is_nk)
-    out = a.new_empty((r, n))
+    out = torch.empty((r, n), dtype=torch.bfloat16 if out_bf16 else w.dtype, device=a.device)
     if r:
         _be().rows_gemm(a, w, w_is_nk, bias, relu, gate, out, _precision, resid)
     return out
@@ -103,11 +107,13 @@ def gemm_tn(a, b, out=None, colsum_a=None):
     """out[M,N] (+)= a[R,M]^T . b[R,N]  -- weight-gradient contraction over rows.
     ``out`` given => accumulate into it.  ``colsum_a`` [M] given => += column sums of a (bias gradient,
     same pass over a)."""
-    _chk(a, b, out, colsum_a)
+    _chk(out, colsum_a)
+    _chk(a, b, bf16_ok=True)
     assert a.shape[0] == b.shape[0]
     acc = out is not None
     if out is None:
-        out = a.new_zeros((a.shape[1], b.shape[1]))
+        wide = [t.dtype for t in (a, b) if t.dtype != torch.bfloat16]
+        out = torch.zeros((a.shape[1], b.shape[1]), dtype=wide[0] if wide else torch.float32, device=a.device)
     if a.shape[0]:
         _be().gemm_tn(a, b, out, acc, _precision, colsum_a)
     return out

@@ -41,14 +41,19 @@ int dg_has_tcgen05(void);
  * epi: optional ReLU, optional gate: out *= (gate[R,N] > 0) (ReLU backward); resid[R,N] optional
  * (gradient accumulation / residual fused into the store).
  * Replaces nn.Linear forward / addmm (layers.py:51,53,111-113,116,127,135) and the dgrad `mm`s. */
-int dg_rows_gemm(const float* a, const float* w, int w_is_nk, const float* bias, int relu,
-                 const float* gate, const float* resid, float* out, long long R, int K, int N, int prec,
-                 void* stream);
+int dg_rows_gemm(const void* a, const float* w, int w_is_nk, const float* bias, int relu,
+                 const void* gate, const float* resid, void* out, long long R, int K, int N, int prec,
+                 int flags, void* stream);
+/* storage flags (tensor-core mode only): tensors that are consumed solely as contraction operands / sign
+ * masks may live in HBM as bf16 -- the contraction rounds them to bf16 anyway, so no accuracy is lost */
+#define DG_A_BF16 1     /* rows_gemm: a is bf16      | gemm_tn: a is bf16 */
+#define DG_OUT_BF16 2   /* rows_gemm: out is bf16    | gemm_tn: b is bf16 */
+#define DG_GATE_BF16 4  /* rows_gemm: gate is bf16 */
 /* out[M,N] += a[R,M]^T . b[R,N]   (split over rows, accumulated atomically: zero `out` first
  * unless accumulating); colsum_a[M] += column sums of a (the bias gradient, same pass), optional.
  * Replaces the weight-gradient `mm`s and bias-gradient `sum`s of autograd. */
-int dg_gemm_tn(const float* a, const float* b, float* out, float* colsum_a, long long R, int M, int N,
-               int prec, void* stream);
+int dg_gemm_tn(const void* a, const void* b, float* out, float* colsum_a, long long R, int M, int N,
+               int prec, int flags, void* stream);
 /* out[N] += column sums of a[R,N]   (bias gradients). */
 int dg_colsum(const float* a, float* out, long long R, int N, void* stream);
 /* out = x * (ref > 0), n elements   (threshold_backward of layers.py:52). */

@@ -25,6 +25,7 @@ class EmulBackend:
 
     # ---- dense
     def rows_gemm(self, a, w, w_is_nk, bias, relu, gate, out, prec, resid=None):
+        a = a.to(w.dtype)
         r = self._mm(a, w.t() if w_is_nk else w, prec)
         if bias is not None:
             r = r + bias
@@ -37,6 +38,7 @@ class EmulBackend:
         out.copy_(r)
 
     def gemm_tn(self, a, b, out, accumulate, prec, colsum_a=None):
+        a, b = a.to(out.dtype), b.to(out.dtype)
         r = self._mm(a.t(), b, prec)
         if accumulate:
             out.add_(r)

@@ -176,3 +176,28 @@ def test_fused_attn_scores(cuda_dev, B, N):
         EM.attn_scores_bwd(d(dg), None if din is None else d(din), d(q), d(k), d(v), d(e), c, de64, dq64, dk64, dv64)
         for got, want in zip(K.attn_scores_bwd(dg, din, q, k, v, e, c), (de64, dq64, dk64, dv64)):
             assert rel_l2(got, want) < 2e-5
+
+
+@pytest.mark.parametrize("R", [1, 300, 128 * 148 + 77])
+def test_bf16_storage_gemms(cuda_dev, R):
+    """bf16-stored hidden activation / gradient: relu->bf16 out, bf16 A operand, bf16 gate, bf16 wgrad inputs."""
+    x, dz = rnd(cuda_dev, R, 128), rnd(cuda_dev, R, 128, seed=9)
+    w1, b1, w2 = rnd(cuda_dev, 384, 128, seed=1, scale=0.1), rnd(cuda_dev, 384, seed=2, scale=0.1), rnd(cuda_dev, 128, 384, seed=3, scale=0.1)
+    bf = lambda t: t.to(torch.bfloat16).double()  # noqa: E731
+    with K.precision("bf16"):
+        h16 = K.rows_gemm(x, w1, True, b1, relu=True, out_bf16=True)
+        assert h16.dtype == torch.bfloat16
+        h_ref = torch.relu(bf(x) @ bf(w1).t() + b1.double())
+        assert rel_l2(h16.double(), bf(h_ref.float())) < 3e-3          # 1-ulp bf16 flips vs the fp64 emulation
+        m = K.rows_gemm(h16, w2, True)                                  # bf16 A operand
+        assert rel_l2(m, h16.double() @ bf(w2).t()) < 2e-5
+        dh16 = K.rows_gemm(dz, w2, False, gate=h16, out_bf16=True)      # bf16 sign gate + bf16 out
+        dh_ref = (bf(dz) @ bf(w2)) * (h16.double() > 0)
+        assert rel_l2(dh16.double(), bf(dh_ref.float())) < 3e-3
+        assert torch.equal(dh16 == 0, (h16 <= 0) | (dh16 == 0))
+        gb = torch.zeros(384, device=cuda_dev)
+        gw1 = K.gemm_tn(dh16, x, colsum_a=gb)                           # bf16 a (with fused bias grad), fp32 b
+        assert rel_l2(gw1, dh16.double().t() @ bf(x)) < 2e-5
+        assert rel_l2(gb, dh16.double().sum(0)) < 1e-5
+        gw2 = K.gemm_tn(dz, h16)                                        # fp32 a, bf16 b
+        assert rel_l2(gw2, bf(dz).t() @ h16.double()) < 2e-5

@@ -12,7 +12,10 @@ from emul_kernels import EmulBackend
 @pytest.fixture(autouse=True)
 def emul():
     kernels._install_backend_for_tests(EmulBackend())
+    old = kernels.get_precision()
+    kernels.set_precision("fp32")          # the emulation computes exactly; bf16 storage would only add rounding
     yield
+    kernels.set_precision(old)
     kernels._install_backend_for_tests(None)
 
 

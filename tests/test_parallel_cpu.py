@@ -34,6 +34,7 @@ def _worker(rank, world, port, out_dir):
     from druggen_b200 import gan, kernels, parallel
     from emul_kernels import EmulBackend
     kernels._install_backend_for_tests(EmulBackend())
+    kernels.set_precision("fp32")
     torch.set_num_threads(1)
     parallel.init_from_env("gloo")
     G, D = _build()
@@ -55,6 +56,7 @@ def test_two_rank_gloo_matches_single_process(tmp_path):
     from druggen_b200 import gan, kernels
     from emul_kernels import EmulBackend
     kernels._install_backend_for_tests(EmulBackend())
+    kernels.set_precision("fp32")
     try:
         G, D = _build()
         a, x = gan.synthetic_molecules(8, 5, 13, 5, seed=7)

@@ -229,6 +229,7 @@ def main():
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
     if rank != 0:
+        torch.distributed.destroy_process_group()
         return
     total = bsz * world
     pk, pk_kind = peaks()
@@ -268,6 +269,8 @@ def main():
         out["cpu_baseline"] = {"value": args.cpu_sample / dt, "unit": "molecules/s", "cores": torch.get_num_threads(), "kind": "port",
                                "sample": f"{reps} steps of {args.cpu_sample} molecules (same GAN step, depth {args.depth}, N={n}, fp32 PyTorch CPU + AdamW)"}
     print(json.dumps(out))
+    if world > 1:
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":

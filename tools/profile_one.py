@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Launch one hot-path kernel a few times at the bench size so ncu can capture it:
-    ncu --set full --clock-control none --import-source on -k regex:<name> -s 2 -c 1 -o gpurun_out/prof python tools/profile_one.py mlp_fwd
+"""Launch each hot-path kernel twice at the bench size (B=512, N=45) so ncu can capture it:
+    ncu --set full --clock-control none --import-source on \\
+        -k regex:'mlp_fwd_tc|rows_gemm_tc|gemm_tn_tc|attn_scores|add_ln_bwd_kernel' -c 12 -o gpurun_out/prof python tools/profile_one.py
 """
 import os
 import sys
@@ -12,22 +13,28 @@ sys.path.insert(0, ROOT)
 import druggen_b200 as dg  # noqa: E402
 from druggen_b200 import kernels as K  # noqa: E402
 
-which = sys.argv[1] if len(sys.argv) > 1 else "mlp_fwd"
-b = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+b = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+n = 45
 dev = torch.device("cuda:0")
-r, d, h = b * 45 * 45, 128, 384
+r, d, h = b * n * n, 128, 384
 g = torch.Generator().manual_seed(0)
 rn = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc).to(dev)  # noqa: E731
-x = rn(r, d)
+x, dy = rn(r, d), rn(r, d)
 w1, b1, w2, b2 = rn(h, d, sc=d ** -0.5), rn(h, sc=0.1), rn(d, h, sc=h ** -0.5), rn(d, sc=0.1)
+wd = rn(d, d, sc=d ** -0.5)
 gamma, beta = torch.ones(d, device=dev), torch.zeros(d, device=dev)
+q, k, v, dg_ = rn(b, n, d), rn(b, n, d), rn(b, n, d), rn(b, n, d)
 with dg.precision("bf16"):
-    for _ in range(4):
-        if which == "mlp_fwd":
-            K.mlp_fwd(x, w1, b1, w2, b2, gamma, beta)
-        elif which == "rows_gemm":
-            K.rows_gemm(x, w1, True, b1, True)
-        elif which == "gemm_tn":
-            K.gemm_tn(x, x)
+    for _ in range(2):
+        K.mlp_fwd(x, w1, b1, w2, b2, gamma, beta)                       # fused residual MLP forward
+        K.rows_gemm(x, wd, True, b2)                                    # 128x128 projection
+        h16 = K.rows_gemm(x, w1, True, b1, relu=True, out_bf16=True)    # fc1 + ReLU -> bf16 hidden
+        K.rows_gemm(dy, w2, False, gate=h16, out_bf16=True)             # dgrad with fused ReLU gate
+        K.gemm_tn(dy, x)                                                # weight gradient 128x128
+        K.gemm_tn(dy, h16)                                              # weight gradient 128x384 (bf16 operand)
+        K.add_ln_bwd(dy, x, x, gamma)
+        e4 = x.view(b, n, n, d)
+        K.attn_scores_fwd(q, k, v, e4, 0.25)
+        K.attn_scores_bwd(dg_, dy.view(b, n, n, d), q, k, v, e4, 0.25)
 torch.cuda.synchronize()
 print("done")

@@ -33,6 +33,8 @@ SIGNATURES = {
     "dg_softmax_agg_bwd_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "dg_attn_scores_fwd": [_P, _P, _P, _P, _F, _P, _P, _I, _I, _I, _P],
     "dg_attn_scores_bwd": [_P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _I, _I, _I, _P],
+    "dg_mlp_bwd_ln": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _F, _P, _LL, _P],
+    "dg_mlp_bwd_dgrad": [_P, _P, _P, _P, _P, _P, _LL, _I, _I, _P, _LL, _P],
     "dg_mlp_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _F, _P, _LL, _P],
 }
 INFO_SYMBOLS = ("dg_abi_version", "dg_last_error", "dg_has_tcgen05")
@@ -207,7 +209,25 @@ def _attn_scores_bwd(self, dg, da_in, q, k, v, e, c, de, dq, dk, dv):
                _ptr(k), _ptr(v), _ptr(e), c, _ptr(de), _ptr(dq), _ptr(dk), _ptr(dv), b, n, d)
 
 
+def _mlp_bwd_ln(self, x, dout, w1, b1, w2, b2, gamma, dz, h16, dgamma, dbeta, eps, workspace):
+    r, d = x.shape
+    h = w1.shape[0]
+    meta = (f"mlp_bwd_ln[H={h},fused]", 4 * r * d * h, _nbytes(x, dout, dz, h16), "hbm")
+    self._call("dg_mlp_bwd_ln", meta, _ptr(x), _ptr(dout), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(gamma), _ptr(dz),
+               _ptr(h16), _ptr(dgamma), _ptr(dbeta), r, d, h, eps, _ptr(workspace), workspace.numel())
+
+
+def _mlp_bwd_dgrad(self, dz, h16, w1, w2, dx, dh16, workspace):
+    r, d = dz.shape
+    h = w1.shape[0]
+    meta = (f"mlp_bwd_dgrad[H={h},fused]", 4 * r * d * h, _nbytes(dz, h16, dx, dh16), "hbm")
+    self._call("dg_mlp_bwd_dgrad", meta, _ptr(dz), _ptr(h16), _ptr(w1), _ptr(w2), _ptr(dx), _ptr(dh16), r, d, h,
+               _ptr(workspace), workspace.numel())
+
+
 CudaBackend.mlp_fwd = _mlp_fwd
+CudaBackend.mlp_bwd_ln = _mlp_bwd_ln
+CudaBackend.mlp_bwd_dgrad = _mlp_bwd_dgrad
 CudaBackend.attn_scores_fwd = _attn_scores_fwd
 CudaBackend.attn_scores_bwd = _attn_scores_bwd
 

@@ -150,6 +150,29 @@ def block_backward(x, y, dxo, dyo, params: Sequence[torch.Tensor], heads: int, e
     # the MLP hidden activation and its gradient are only ever contraction operands / a sign mask: in the
     # tensor-core mode they are kept in HBM as bf16 (half the traffic of the widest tensors, zero extra error)
     h16 = K.fused_available(d, p("mlp.fc1.weight").shape[0])
+
+    def mlp_bwd(mlp, ln, xin, dout2d):
+        """Backward of  LN(xin + fc2(relu(fc1(xin))))  given d(out): returns d(xin); fills the six parameter grads."""
+        w1, b1, w2, b2 = p(mlp + ".fc1.weight"), p(mlp + ".fc1.bias"), p(mlp + ".fc2.weight"), p(mlp + ".fc2.bias")
+        if h16:      # two fused tcgen05 chains; h and dh cross HBM once each, as bf16, for the weight gradients
+            dz, hh, dgam, dbet = K.mlp_bwd_ln(xin, dout2d, w1, b1, w2, b2, p(ln + ".weight"))
+            if want_params:
+                put(ln + ".weight", dgam)
+                put(ln + ".bias", dbet)
+            wgrad(mlp + ".fc2", dz, hh)
+            dxin, dh = K.mlp_bwd_dgrad(dz, hh, w1, w2)
+            del hh
+            wgrad(mlp + ".fc1", dh, xin)
+            return dxin
+        hh = K.rows_gemm(xin, w1, True, b1, relu=True)
+        mm = K.rows_gemm(hh, w2, True, b2)
+        dz = ln_bwd(ln, dout2d, xin, mm)
+        del mm
+        wgrad(mlp + ".fc2", dz, hh)
+        dh = K.rows_gemm(dz, w2, False, gate=hh)
+        del hh
+        wgrad(mlp + ".fc1", dh, xin)
+        return K.rows_gemm(dh, w1, False, resid=dz)
     # ---- recompute (node stream, attention scores)
     x1 = K.add_ln_fwd(x2d, None, p("ln1.weight"), p("ln1.bias"))
     q = K.rows_gemm(x1, p("attn.q.weight"), True, p("attn.q.bias")).view(b, n, d)
@@ -161,17 +184,9 @@ def block_backward(x, y, dxo, dyo, params: Sequence[torch.Tensor], heads: int, e
     g2d = g.view(-1, d)
     on = K.rows_gemm(g2d, p("attn.out_n.weight"), True, p("attn.out_n.bias"))
     x3 = K.add_ln_fwd(x1, on, p("ln3.weight"), p("ln3.bias"))
-    hx = K.rows_gemm(x3, p("mlp.fc1.weight"), True, p("mlp.fc1.bias"), relu=True, out_bf16=h16)
-    mx = K.rows_gemm(hx, p("mlp.fc2.weight"), True, p("mlp.fc2.bias"))
     # ---- node MLP + LN5, LN3, out_n
     dxo2d = (dxo if dxo is not None else torch.zeros_like(x)).reshape(-1, d).contiguous()
-    dz5 = ln_bwd("ln5", dxo2d, x3, mx)
-    del mx
-    wgrad("mlp.fc2", dz5, hx)
-    dhx = K.rows_gemm(dz5, p("mlp.fc2.weight"), False, gate=hx, out_bf16=h16)
-    wgrad("mlp.fc1", dhx, x3)
-    dx3 = K.rows_gemm(dhx, p("mlp.fc1.weight"), False, resid=dz5)
-    del dhx, hx, dz5
+    dx3 = mlp_bwd("mlp", "ln5", x3, dxo2d)
     dz3 = ln_bwd("ln3", dx3, x1, on)                       # gradient of both x1 (residual) and out_n(g)
     wgrad("attn.out_n", dz3, g2d)
     dg = K.rows_gemm(dz3, p("attn.out_n.weight"), False).view(b, n, d)
@@ -180,16 +195,7 @@ def block_backward(x, y, dxo, dyo, params: Sequence[torch.Tensor], heads: int, e
     if edge_out and dyo is not None:
         y1 = K.rows_gemm(a2d, p("attn.out_e.weight"), True, p("attn.out_e.bias"))
         y3 = K.add_ln_fwd(y2d, y1, p("ln4.weight"), p("ln4.bias"))
-        hy = K.rows_gemm(y3, p("mlp2.fc1.weight"), True, p("mlp2.fc1.bias"), relu=True, out_bf16=h16)
-        my = K.rows_gemm(hy, p("mlp2.fc2.weight"), True, p("mlp2.fc2.bias"))
-        dz6 = ln_bwd("ln6", dyo.reshape(-1, d).contiguous(), y3, my)
-        del my
-        wgrad("mlp2.fc2", dz6, hy)
-        dhy = K.rows_gemm(dz6, p("mlp2.fc2.weight"), False, gate=hy, out_bf16=h16)
-        del hy
-        wgrad("mlp2.fc1", dhy, y3)
-        dy3 = K.rows_gemm(dhy, p("mlp2.fc1.weight"), False, resid=dz6)
-        del dhy, dz6
+        dy3 = mlp_bwd("mlp2", "ln6", y3, dyo.reshape(-1, d).contiguous())
         dz4 = ln_bwd("ln4", dy3, y2d, y1)                  # gradient of both y (residual) and out_e(a)
         del dy3, y1, y3
         wgrad("attn.out_e", dz4, a2d)

@@ -1,44 +1,85 @@
-// Fused residual-MLP forward of the encoder block (layers.py:41-54 + the residual and LayerNorm of
-// layers.py:191/192) in ONE tcgen05 kernel:
+// Fused residual-MLP chain of the encoder block (layers.py:41-54 + the residual and LayerNorm of
+// layers.py:191/192) as ONE tcgen05 kernel skeleton with three epilogue personalities:
 //
-//      out = LayerNorm( x + fc2( relu( fc1(x) + b1 ) ) + b2 ) * gamma + beta
+//   FWD    out = LayerNorm( x + fc2( relu( fc1(x) + b1 ) ) + b2 ) * gamma + beta
+//   BWD_A  recompute h = relu(fc1(x)+b1), z = x + fc2(h) + b2, then the LayerNorm BACKWARD of `dout`
+//          through z:  out = dz [R,128] fp32,  spill = h [R,H] bf16,  dgamma/dbeta += column sums
+//   BWD_B  dh = (dz . W2) * (h > 0)   (spilled as bf16 for the weight-gradient pass),
+//          out = dx = dz + dh . W1
 //
-// x:[R,128] fp32 rows (edge rows B*N*N, or node rows B*N), hidden width H = 128*HC (HC <= 3).
-// The 128 x H hidden activation never leaves the SM: it goes TMEM -> registers (bias, ReLU, bf16)
-// -> 128B-swizzled smem operand blocks -> second contraction.  HBM traffic is the algorithmic
-// minimum: read x once (plus an L2-resident re-read for the fp32 residual), write out once.
+// All three are "GEMM1 per 128-wide hidden chunk -> per-row epilogue -> bf16 operand block in smem -> GEMM2
+// accumulating over chunks -> per-row final epilogue": the 128 x H intermediate never round-trips HBM as
+// fp32 (it is spilled once as bf16 only where the weight gradient needs it).
 //
 // Persistent CTA per SM, 448 threads, warp-specialised:
-//   warps 0-7   epilogue : thread = half a row (TMEM lane quarter w&3, column half w>>2);
-//                          TMEM accumulator -> h chunk (bf16 operand block) / final residual + LayerNorm
-//   warps 8-11  x loader : fp32 LDG.128 -> bf16 -> swizzled operand blocks (double-buffered tiles)
-//   warp  12    MMA      : one thread issues tcgen05.mma; fc2 of tile t interleaved with fc1 of t+1
+//   warps 0-7   epilogue : thread = half a row (TMEM lane quarter w&3, column half w>>2)
+//   warps 8-11  loader   : fp32 LDG.128 -> bf16 -> swizzled operand blocks (double-buffered tiles)
+//   warp  12    MMA      : one thread issues tcgen05.mma; GEMM2 of tile t interleaved with GEMM1 of t+1
 //   warp  13    W loader : one thread streams pre-packed bf16 weight stages (32 KB) with
 //                          cp.async.bulk into a 2-stage ring (weights live in L2: 192 KB per net)
-// TMEM: columns [0,384) three fc1 chunk accumulators, [384,512) the fc2 accumulator.
+// TMEM: columns [0,384) three GEMM1 chunk accumulators, [384,512) the GEMM2 accumulator.
 #include "tc_common.cuh"
 #include "../../include/druggen_b200.h"
 
 namespace dg {
 namespace tc {
 
-constexpr int kMlpThreads = 448;         // warps 0-7 epilogue, 8-11 x loader, 12 MMA, 13 weight streamer
+constexpr int kMlpThreads = 448;
 constexpr int kWStage = 2 * kBlkBytes;   // one packed weight stage: [2 kb][128 rows][128 B] = 32 KB
-constexpr int kStgPitch = 20;            // epilogue transpose: 32 rows x 16 cols per warp, pitch 20 floats
+constexpr int kStgPitch = 20;            // epilogue transpose: 32 rows x 16 words per warp, pitch 20 words
+
+enum { kFwd = 0, kBwdA = 1, kBwdB = 2 };
+
+struct MlpArgs {
+  const float* x;          // FWD/BWD_A: block input [R,128];  BWD_B: dz [R,128]
+  const uint8_t* wpack;    // packed bf16 weight stages
+  const float* b1;         // [H]      (FWD/BWD_A)
+  const float* b2;         // [128]    (FWD/BWD_A)
+  const float* gamma;      // [128]    (FWD/BWD_A)
+  const float* beta;       // [128]    (FWD)
+  const float* dout;       // BWD_A: upstream gradient [R,128]
+  float* out;              // FWD: y;  BWD_A: dz;  BWD_B: dx     [R,128]
+  uint16_t* spill;         // BWD_A: h out [R,H] bf16;  BWD_B: dh out [R,H] bf16
+  const uint16_t* gate;    // BWD_B: h in [R,H] bf16
+  float* dgamma;           // BWD_A: += [128]
+  float* dbeta;            // BWD_A: += [128]
+  long long R;
+  int HC;
+  float eps;
+};
 
 // ---- weight pre-pack: fp32 nn.Linear weights -> bf16 swizzled operand stages in a workspace ------
-// stage c        (c < HC): fc1 rows [c*128, c*128+128) of W1[H,128]        (B operand: N = hidden unit, K = in)
-// stage HC + c           : fc2 columns [c*128, c*128+128) of W2[128,H]      (B operand: N = out, K = hidden slice)
+// forward orientation (FWD, BWD_A):
+//   stage c      : fc1 rows [c*128, +128) of W1[H,128]            B operand: N = hidden unit, K = in
+//   stage HC + c : fc2 columns [c*128, +128) of W2[128,H]         B operand: N = out,         K = hidden slice
+// transposed orientation (BWD_B):
+//   stage c      : W2^T slice: element (n, o) = W2[o, c*128+n]    B operand: N = hidden unit, K = out
+//   stage HC + c : W1^T slice: element (k, n) = W1[c*128+n, k]    B operand: N = in,          K = hidden slice
 __global__ void mlp_pack_weights_kernel(const float* __restrict__ w1, const float* __restrict__ w2, uint8_t* __restrict__ ws,
-                                        int H) {
+                                        int H, int transposed) {
   const int HC = H / 128;
   const int total = 2 * HC * 128 * 16;          // (stage, row, kb*8 + j)
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     int c16 = idx & 15, row = (idx >> 4) & 127, stage = idx >> 11;
     int kb = c16 >> 3, j = c16 & 7;
-    const float* src = stage < HC ? w1 + (long long)(stage * 128 + row) * 128 + kb * 64 + j * 8
-                                  : w2 + (long long)row * H + (stage - HC) * 128 + kb * 64 + j * 8;
-    st_block_chunk(ws + (long long)stage * kWStage + kb * kBlkBytes, row, j, ld4(src), ld4(src + 4));
+    const int k0 = kb * 64 + j * 8;              // first of 8 consecutive K indices
+    float4 lo, hi;
+    if (!transposed) {
+      const float* src = stage < HC ? w1 + (long long)(stage * 128 + row) * 128 + k0
+                                    : w2 + (long long)row * H + (stage - HC) * 128 + k0;
+      lo = ld4(src); hi = ld4(src + 4);
+    } else {
+      float t[8];
+      if (stage < HC) {                          // (n=row, o=k0+i) = W2[o, stage*128 + n]
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = w2[(long long)(k0 + i) * H + stage * 128 + row];
+      } else {                                   // (k=row, n=k0+i) = W1[(stage-HC)*128 + n, k]
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = w1[(long long)((stage - HC) * 128 + k0 + i) * 128 + row];
+      }
+      lo = make_float4(t[0], t[1], t[2], t[3]); hi = make_float4(t[4], t[5], t[6], t[7]);
+    }
+    st_block_chunk(ws + (long long)stage * kWStage + kb * kBlkBytes, row, j, lo, hi);
   }
 }
 
@@ -46,58 +87,58 @@ struct MlpSmem {
   static constexpr int xb = 0;                          // 2 x 32 KB
   static constexpr int hb = xb + 2 * kWStage;           // 2 x 32 KB
   static constexpr int wb = hb + 2 * kWStage;           // 2 x 32 KB
-  static constexpr int stage = wb + 2 * kWStage;        // 8 warps x 32 x kStgPitch floats
-  static constexpr int stats = stage + 8 * 32 * kStgPitch * 4;   // [2 parity][2 halves][128 rows] float2
-  static constexpr int vec = stats + 2 * 2 * 128 * 8;   // b1[384] b2[128] gamma[128] beta[128]
+  static constexpr int stage = wb + 2 * kWStage;        // 8 warps x 32 x kStgPitch words
+  static constexpr int stats = stage + 8 * 32 * kStgPitch * 4;   // [2 parity][2 halves][128 rows] float2, twice (BWD_A)
+  static constexpr int vec = stats + 2 * 2 * 2 * 128 * 8;        // b1[384] b2[128] gamma[128] beta[128]
   static constexpr int bars = vec + (384 + 3 * 128) * 4;
   static constexpr int total = bars + 256;
 };
 
-// warp-cooperative transposes through a [32][kStgPitch] staging tile (16 columns at a time):
-// global rows -> "thread = row" registers, and back.  Global accesses are 64 B contiguous per row.
-// gather = issue (all 16 coalesced LDG.128 of a 32-row x 64-col panel in flight at once) + finish (transpose)
-__device__ __forceinline__ void gather_issue64(const float* __restrict__ src, long long row_base, long long R, int col,
-                                               int lane, float4* xq) {
+// warp-cooperative transposes through a [32][kStgPitch] staging tile, 16 words (columns) at a time:
+// global rows <-> "thread = row" registers.  Global accesses are 64 B contiguous per row (pitch in words).
+__device__ __forceinline__ void gather_issue(const float* __restrict__ src, long long row_base, long long R, int pitch, int col,
+                                             int ngroups, int lane, float4* xq) {
 #pragma unroll
   for (int g16 = 0; g16 < 4; ++g16)
+    if (g16 < ngroups) {
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int r = it * 8 + (lane >> 2);
-      xq[g16 * 4 + it] = (row_base + r < R) ? ld4(src + (row_base + r) * 128 + col + g16 * 16 + (lane & 3) * 4)
-                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int it = 0; it < 4; ++it) {
+        const int r = it * 8 + (lane >> 2);
+        xq[g16 * 4 + it] = (row_base + r < R) ? ld4(src + (row_base + r) * pitch + col + g16 * 16 + (lane & 3) * 4)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
 }
-__device__ __forceinline__ void gather_finish64(const float4* xq, float* stg, int lane, float* dst64) {
+__device__ __forceinline__ void gather_finish(const float4* xq, int ngroups, float* stg, int lane, float* dst) {
 #pragma unroll
-  for (int g16 = 0; g16 < 4; ++g16) {
+  for (int g16 = 0; g16 < 4; ++g16)
+    if (g16 < ngroups) {
 #pragma unroll
-    for (int it = 0; it < 4; ++it) st4(stg + (it * 8 + (lane >> 2)) * kStgPitch + (lane & 3) * 4, xq[g16 * 4 + it]);
-    __syncwarp();
+      for (int it = 0; it < 4; ++it) st4(stg + (it * 8 + (lane >> 2)) * kStgPitch + (lane & 3) * 4, xq[g16 * 4 + it]);
+      __syncwarp();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float4 v = ld4(stg + lane * kStgPitch + i * 4);
-      dst64[g16 * 16 + 4 * i] = v.x; dst64[g16 * 16 + 4 * i + 1] = v.y; dst64[g16 * 16 + 4 * i + 2] = v.z; dst64[g16 * 16 + 4 * i + 3] = v.w;
+      for (int i = 0; i < 4; ++i) {
+        float4 v = ld4(stg + lane * kStgPitch + i * 4);
+        dst[g16 * 16 + 4 * i] = v.x; dst[g16 * 16 + 4 * i + 1] = v.y; dst[g16 * 16 + 4 * i + 2] = v.z; dst[g16 * 16 + 4 * i + 3] = v.w;
+      }
+      __syncwarp();
     }
-    __syncwarp();
-  }
 }
-__device__ __forceinline__ void scatter_rows16(float* __restrict__ dst, long long row_base, long long R, int col, float* stg,
-                                               int lane, const float* src16) {
+__device__ __forceinline__ void scatter_rows16(float* __restrict__ dst, long long row_base, long long R, int pitch, int col,
+                                               float* stg, int lane, const float* src16) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) st4(stg + lane * kStgPitch + i * 4, make_float4(src16[4 * i], src16[4 * i + 1], src16[4 * i + 2], src16[4 * i + 3]));
   __syncwarp();
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
     const int r = it * 8 + (lane >> 2);
-    if (row_base + r < R) st4(dst + (row_base + r) * 128 + col + (lane & 3) * 4, ld4(stg + r * kStgPitch + (lane & 3) * 4));
+    if (row_base + r < R) st4(dst + (row_base + r) * pitch + col + (lane & 3) * 4, ld4(stg + r * kStgPitch + (lane & 3) * 4));
   }
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(kMlpThreads, 1)
-mlp_fwd_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wpack, const float* __restrict__ b1,
-                  const float* __restrict__ b2, const float* __restrict__ gamma, const float* __restrict__ beta,
-                  float* __restrict__ out, long long R, int HC, float eps) {
+template <int kMode>
+__global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpArgs A) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sX = smem + MlpSmem::xb;
@@ -114,6 +155,9 @@ mlp_fwd_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wpack
            *hacc_empty = bars + 11, *hb_full = bars + 14, *hb_empty = bars + 16, *z_full = bars + 18, *z_empty = bars + 19;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
+  const float* __restrict__ x = A.x;
+  const long long R = A.R;
+  const int HC = A.HC, H = HC * 128;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long num_tiles = (R + 127) / 128;
   const long long my_tiles = blockIdx.x < num_tiles ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -129,15 +173,21 @@ mlp_fwd_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wpack
     fence_barrier_init();
   }
   if (warp == 12) tmem_alloc(tmem_slot, 512);
-  for (int i = tid; i < HC * 128; i += kMlpThreads) sB1[i] = b1[i];
-  for (int i = tid; i < 128; i += kMlpThreads) { sB2[i] = b2[i]; sG[i] = gamma[i]; sBe[i] = beta[i]; }
+  if (kMode != kBwdB) {
+    for (int i = tid; i < H; i += kMlpThreads) sB1[i] = A.b1[i];
+    for (int i = tid; i < 128; i += kMlpThreads) {
+      sB2[i] = A.b2[i];
+      sG[i] = A.gamma[i];
+      sBe[i] = kMode == kFwd ? A.beta[i] : 0.f;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= 8 && warp < 12) {
-    // ------------------------------------------------------------------ x loader
+    // ------------------------------------------------------------------ input-tile loader
     const int lt = tid - 256;
     for (long long ti = 0; ti < my_tiles; ++ti) {
       const long long row0 = (blockIdx.x + ti * gridDim.x) * 128;
@@ -174,14 +224,14 @@ mlp_fwd_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wpack
         const int ws = wcount & 1;
         mbar_wait(&w_empty[ws], ((wcount >> 1) & 1) ^ 1);
         mbar_expect_tx(&w_full[ws], kWStage);
-        bulk_g2s(sW + ws * kWStage, wpack + (long long)stage * kWStage, kWStage, &w_full[ws]);
+        bulk_g2s(sW + ws * kWStage, A.wpack + (long long)stage * kWStage, kWStage, &w_full[ws]);
         ++wcount;
       };
-      for (int c = 0; c < HC; ++c) push(c);                         // fc1 of the first tile
+      for (int c = 0; c < HC; ++c) push(c);                         // GEMM1 of the first tile
       for (long long ti = 0; ti < my_tiles; ++ti)
         for (int c = 0; c < HC; ++c) {
-          push(HC + c);                                             // fc2 chunk c of tile ti
-          if (ti + 1 < my_tiles) push(c);                           // fc1 chunk c of tile ti+1
+          push(HC + c);                                             // GEMM2 chunk c of tile ti
+          if (ti + 1 < my_tiles) push(c);                           // GEMM1 chunk c of tile ti+1
         }
     }
     __syncwarp();
@@ -204,7 +254,7 @@ mlp_fwd_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wpack
         umma_commit(&w_empty[ws]);
         ++wcount;
       };
-      auto fc1 = [&](long long ti, int c) {
+      auto gemm1 = [&](long long ti, int c) {
         const int xs = ti & 1;
         if (c == 0) { mbar_wait(&x_full[xs], (ti >> 1) & 1); tc_fence_after(); }
         mbar_wait(&hacc_empty[c], (ti & 1) ^ 1);
@@ -213,7 +263,7 @@ mlp_fwd_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wpack
         umma_commit(&hacc_full[c]);
         if (c == HC - 1) umma_commit(&x_empty[xs]);
       };
-      for (int c = 0; c < HC; ++c) fc1(0, c);
+      for (int c = 0; c < HC; ++c) gemm1(0, c);
       for (long long ti = 0; ti < my_tiles; ++ti) {
         for (int c = 0; c < HC; ++c) {
           const int hs = hcount & 1;
@@ -223,7 +273,7 @@ mlp_fwd_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wpack
           mma_chunk(smem_u32(sH + hs * kWStage), 384, c == 0);
           umma_commit(&hb_empty[hs]);
           ++hcount;
-          if (ti + 1 < my_tiles) fc1(ti + 1, c);
+          if (ti + 1 < my_tiles) gemm1(ti + 1, c);
         }
         umma_commit(z_full);
       }
@@ -237,9 +287,15 @@ mlp_fwd_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wpack
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int row = q * 32 + lane;
     uint32_t hcount = 0;
+    float cs_g[4] = {0.f, 0.f, 0.f, 0.f}, cs_b[4] = {0.f, 0.f, 0.f, 0.f};   // BWD_A: column sums, lane<16 owns col g16*16+lane
     for (long long ti = 0; ti < my_tiles; ++ti) {
       const long long row0 = (blockIdx.x + ti * gridDim.x) * 128;
+      const long long wrow0 = row0 + q * 32;                          // first global row of this warp
       for (int c = 0; c < HC; ++c) {
+        // bf16 [R,H] side tensors viewed as 32-bit words: pitch H/2, this warp-half's 64 columns = 32 words
+        const int wcol = (c * 128 + hf * 64) >> 1;
+        float4 gq[8];
+        if (kMode == kBwdB) gather_issue(reinterpret_cast<const float*>(A.gate), wrow0, R, H >> 1, wcol, 2, lane, gq);
         mbar_wait(&hacc_full[c], ti & 1);
         const int hs = hcount & 1;
         mbar_wait(&hb_empty[hs], ((hcount >> 1) & 1) ^ 1);
@@ -251,9 +307,20 @@ mlp_fwd_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wpack
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&hacc_empty[c]);
-        const float* bb = sB1 + c * 128 + hf * 64;
+        if (kMode == kBwdB) {
+          float gw[32];                                              // 64 bf16 sign masks of this row
+          gather_finish(gq, 2, stg, lane, gw);
 #pragma unroll
-        for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i] + bb[i], 0.f);
+          for (int i = 0; i < 32; ++i) {
+            const uint32_t bits = __float_as_uint(gw[i]);
+            v[2 * i] = (short)(bits & 0xFFFF) > 0 ? v[2 * i] : 0.f;
+            v[2 * i + 1] = (short)(bits >> 16) > 0 ? v[2 * i + 1] : 0.f;
+          }
+        } else {
+          const float* bb = sB1 + c * 128 + hf * 64;
+#pragma unroll
+          for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i] + bb[i], 0.f);
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           st_block_chunk(hblk, row, j, make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
@@ -261,13 +328,20 @@ mlp_fwd_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wpack
         fence_async_smem();
         mbar_arrive(&hb_full[hs]);
         ++hcount;
+        if (kMode != kFwd) {                                          // spill the chunk as bf16 for the weight-gradient pass
+          float pk[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) pk[i] = __uint_as_float(pack_bf16(v[2 * i], v[2 * i + 1]));
+          scatter_rows16(reinterpret_cast<float*>(A.spill), wrow0, R, H >> 1, wcol, stg, lane, pk);
+          scatter_rows16(reinterpret_cast<float*>(A.spill), wrow0, R, H >> 1, wcol + 16, stg, lane, pk + 16);
+        }
       }
-      // ---- final: a = z + b2 + x (this thread: one row, 64 columns) -> LayerNorm -> out
+      // ---- final epilogue: this thread = one row, 64 columns [hf*64, +64)
       float a[64];
       {
         float4 xq[16];
-        gather_issue64(x, row0 + q * 32, R, hf * 64, lane, xq);
-        gather_finish64(xq, stg, lane, a);
+        gather_issue(x, wrow0, R, 128, hf * 64, 4, lane, xq);      // FWD/BWD_A: residual x;  BWD_B: residual dz
+        gather_finish(xq, 4, stg, lane, a);
       }
       mbar_wait(z_full, ti & 1);
       tc_fence_after();
@@ -281,23 +355,99 @@ mlp_fwd_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wpack
         const float* bb = sB2 + hf * 64 + cgl * 32;
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float t0 = a[cgl * 32 + i] + v[i] + bb[i], t1 = a[cgl * 32 + i + 1] + v[i + 1] + bb[i + 1];
+          float t0 = a[cgl * 32 + i] + v[i], t1 = a[cgl * 32 + i + 1] + v[i + 1];
+          if (kMode != kBwdB) { t0 += bb[i]; t1 += bb[i + 1]; }
           a[cgl * 32 + i] = t0; a[cgl * 32 + i + 1] = t1;
           s1a += t0; s1b += t1; s2a = fmaf(t0, t0, s2a); s2b = fmaf(t1, t1, s2b);
         }
       }
-      float2* st = sStats + (ti & 1) * 256;
+      if (kMode == kBwdB) {                                           // dx = dz + dh . W1
+#pragma unroll
+        for (int g16 = 0; g16 < 4; ++g16) scatter_rows16(A.out, wrow0, R, 128, hf * 64 + g16 * 16, stg, lane, a + g16 * 16);
+        continue;
+      }
+      float2* st = sStats + (ti & 1) * 512;
       st[hf * 128 + row] = make_float2(s1a + s1b, s2a + s2b);
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const float2 other = st[(hf ^ 1) * 128 + row];
       const float mean = (s1a + s1b + other.x) * (1.f / 128.f);
-      const float rstd = rsqrtf(fmaxf((s2a + s2b + other.y) * (1.f / 128.f) - mean * mean, 0.f) + eps);
+      const float rstd = rsqrtf(fmaxf((s2a + s2b + other.y) * (1.f / 128.f) - mean * mean, 0.f) + A.eps);
       const float* gg = sG + hf * 64;
-      const float* be = sBe + hf * 64;
+      if (kMode == kFwd) {
+        const float* be = sBe + hf * 64;
 #pragma unroll
-      for (int i = 0; i < 64; ++i) a[i] = (a[i] - mean) * rstd * gg[i] + be[i];
+        for (int i = 0; i < 64; ++i) a[i] = (a[i] - mean) * rstd * gg[i] + be[i];
 #pragma unroll
-      for (int g16 = 0; g16 < 4; ++g16) scatter_rows16(out, row0 + q * 32, R, hf * 64 + g16 * 16, stg, lane, a + g16 * 16);
+        for (int g16 = 0; g16 < 4; ++g16) scatter_rows16(A.out, wrow0, R, 128, hf * 64 + g16 * 16, stg, lane, a + g16 * 16);
+        continue;
+      }
+      // ---- BWD_A: LayerNorm backward.  xh = (z - mean) rstd;  gh = gamma * dout;
+      //      dz = rstd * (gh - mean(gh) - xh * mean(gh * xh));  dgamma += dout * xh, dbeta += dout (column sums)
+#pragma unroll
+      for (int i = 0; i < 64; ++i) a[i] = (a[i] - mean) * rstd;      // a := xh
+      float sg = 0.f, sgx = 0.f;
+#pragma unroll
+      for (int g16 = 0; g16 < 4; ++g16) {
+        float4 dq4[4];
+        float dd[16];
+        gather_issue(A.dout, wrow0, R, 128, hf * 64 + g16 * 16, 1, lane, dq4);
+        // gather_finish, but keep the staged [32 rows][16 cols] block for the column sums
+#pragma unroll
+        for (int it = 0; it < 4; ++it) st4(stg + (it * 8 + (lane >> 2)) * kStgPitch + (lane & 3) * 4, dq4[it]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 t = ld4(stg + lane * kStgPitch + i * 4);
+          dd[4 * i] = t.x; dd[4 * i + 1] = t.y; dd[4 * i + 2] = t.z; dd[4 * i + 3] = t.w;
+        }
+        if (lane < 16) {                                              // dbeta: column `lane` of the staged dout block
+          float sb = 0.f;
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) sb += stg[r * kStgPitch + lane];
+          cs_b[g16] += sb;
+        }
+        __syncwarp();
+        float px[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float gh = gg[g16 * 16 + i] * dd[i];
+          px[i] = dd[i] * a[g16 * 16 + i];
+          sg += gh;
+          sgx = fmaf(gh, a[g16 * 16 + i], sgx);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) st4(stg + lane * kStgPitch + i * 4, make_float4(px[4 * i], px[4 * i + 1], px[4 * i + 2], px[4 * i + 3]));
+        __syncwarp();
+        if (lane < 16) {                                              // dgamma: column sums of dout * xh
+          float sgm = 0.f;
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) sgm += stg[r * kStgPitch + lane];
+          cs_g[g16] += sgm;
+        }
+        __syncwarp();
+      }
+      float2* st2 = sStats + (ti & 1) * 512 + 256;
+      st2[hf * 128 + row] = make_float2(sg, sgx);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float2 o2 = st2[(hf ^ 1) * 128 + row];
+      const float c1 = (sg + o2.x) * (1.f / 128.f), c2 = (sgx + o2.y) * (1.f / 128.f);
+#pragma unroll
+      for (int g16 = 0; g16 < 4; ++g16) {
+        float4 dq4[4];
+        float dd[16];
+        gather_issue(A.dout, wrow0, R, 128, hf * 64 + g16 * 16, 1, lane, dq4);   // second visit: L2
+        gather_finish(dq4, 1, stg, lane, dd);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dd[i] = rstd * (gg[g16 * 16 + i] * dd[i] - c1 - a[g16 * 16 + i] * c2);
+        scatter_rows16(A.out, wrow0, R, 128, hf * 64 + g16 * 16, stg, lane, dd);
+      }
+    }
+    if (kMode == kBwdA && lane < 16) {
+#pragma unroll
+      for (int g16 = 0; g16 < 4; ++g16) {
+        atomicAdd(A.dgamma + hf * 64 + g16 * 16 + lane, cs_g[g16]);
+        atomicAdd(A.dbeta + hf * 64 + g16 * 16 + lane, cs_b[g16]);
+      }
     }
   }
   tc_fence_before();
@@ -308,30 +458,60 @@ mlp_fwd_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wpack
   }
 }
 
+template <int kMode>
+static int launch_chain(const MlpArgs& a, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_chain_tc_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpSmem::total + 1024);
+    if (e != cudaSuccess) return fail("cudaFuncSetAttribute(mlp_chain): %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  long long tiles = (a.R + 127) / 128;
+  int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  mlp_chain_tc_kernel<kMode><<<grid, kMlpThreads, MlpSmem::total + 1024, s>>>(a);
+  return check_launch("dg_mlp_chain");
+}
+
 }  // namespace tc
 }  // namespace dg
 
 using namespace dg;
 
+static int mlp_check(const char* who, long long R, int D, int H, const void* ws, long long ws_bytes) {
+  if (R <= 0) return fail("%s: rows must be > 0", who);
+  if (D != 128 || H % 128 || H < 128 || H > 384) return fail("%s: needs D == 128 and H in {128,256,384}, got D=%d H=%d", who, D, H);
+  if (ws_bytes < (long long)2 * (H / 128) * tc::kWStage) return fail("%s: workspace too small (%lld bytes)", who, ws_bytes);
+  if (reinterpret_cast<uintptr_t>(ws) & 127) return fail("%s: workspace must be 128-byte aligned", who);
+  return 0;
+}
+
 extern "C" int dg_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                           const float* gamma, const float* beta, float* out, long long R, int D, int H, float eps,
                           void* workspace, long long workspace_bytes, void* stream) {
-  if (R <= 0) return fail("dg_mlp_fwd: rows must be > 0");
-  if (D != 128 || H % 128 || H < 128 || H > 384) return fail("dg_mlp_fwd: needs D == 128 and H in {128,256,384}, got D=%d H=%d", D, H);
-  const int HC = H / 128;
-  if (workspace_bytes < (long long)2 * HC * tc::kWStage) return fail("dg_mlp_fwd: workspace too small (%lld bytes)", workspace_bytes);
-  if (reinterpret_cast<uintptr_t>(workspace) & 127) return fail("dg_mlp_fwd: workspace must be 128-byte aligned");
+  if (mlp_check("dg_mlp_fwd", R, D, H, workspace, workspace_bytes)) return 1;
   cudaStream_t s = (cudaStream_t)stream;
-  tc::mlp_pack_weights_kernel<<<48, 256, 0, s>>>(w1, w2, (uint8_t*)workspace, H);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc::mlp_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::MlpSmem::total + 1024);
-    if (e != cudaSuccess) return fail("cudaFuncSetAttribute(mlp_fwd): %s", cudaGetErrorString(e));
-    configured = true;
-  }
-  long long tiles = (R + 127) / 128;
-  int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  tc::mlp_fwd_tc_kernel<<<grid, tc::kMlpThreads, tc::MlpSmem::total + 1024, s>>>(x, (const uint8_t*)workspace, b1, b2, gamma, beta,
-                                                                               out, R, HC, eps);
-  return check_launch("dg_mlp_fwd");
+  tc::mlp_pack_weights_kernel<<<48, 256, 0, s>>>(w1, w2, (uint8_t*)workspace, H, 0);
+  tc::MlpArgs a{x, (const uint8_t*)workspace, b1, b2, gamma, beta, nullptr, out, nullptr, nullptr, nullptr, nullptr, R, H / 128, eps};
+  return tc::launch_chain<tc::kFwd>(a, s);
+}
+
+extern "C" int dg_mlp_bwd_ln(const float* x, const float* dout, const float* w1, const float* b1, const float* w2,
+                             const float* b2, const float* gamma, float* dz, void* h_bf16, float* dgamma, float* dbeta,
+                             long long R, int D, int H, float eps, void* workspace, long long workspace_bytes, void* stream) {
+  if (mlp_check("dg_mlp_bwd_ln", R, D, H, workspace, workspace_bytes)) return 1;
+  cudaStream_t s = (cudaStream_t)stream;
+  tc::mlp_pack_weights_kernel<<<48, 256, 0, s>>>(w1, w2, (uint8_t*)workspace, H, 0);
+  tc::MlpArgs a{x, (const uint8_t*)workspace, b1, b2, gamma, nullptr, dout, dz, (uint16_t*)h_bf16, nullptr, dgamma, dbeta, R, H / 128, eps};
+  return tc::launch_chain<tc::kBwdA>(a, s);
+}
+
+extern "C" int dg_mlp_bwd_dgrad(const float* dz, const void* h_bf16, const float* w1, const float* w2, float* dx,
+                                void* dh_bf16, long long R, int D, int H, void* workspace, long long workspace_bytes,
+                                void* stream) {
+  if (mlp_check("dg_mlp_bwd_dgrad", R, D, H, workspace, workspace_bytes)) return 1;
+  cudaStream_t s = (cudaStream_t)stream;
+  tc::mlp_pack_weights_kernel<<<48, 256, 0, s>>>(w1, w2, (uint8_t*)workspace, H, 1);
+  tc::MlpArgs a{dz, (const uint8_t*)workspace, nullptr, nullptr, nullptr, nullptr, nullptr, dx, (uint16_t*)dh_bf16,
+                (const uint16_t*)h_bf16, nullptr, nullptr, R, H / 128, 0.f};
+  return tc::launch_chain<tc::kBwdB>(a, s);
 }

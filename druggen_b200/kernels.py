@@ -243,6 +243,33 @@ def mlp_fwd(x, w1, b1, w2, b2, gamma, beta, eps: float = 1e-5):
     return out
 
 
+def _mlp_ws(w1):
+    return torch.empty(2 * (w1.shape[0] // 128) * 32768, dtype=torch.uint8, device=w1.device)
+
+
+def mlp_bwd_ln(x, dout, w1, b1, w2, b2, gamma, eps: float = 1e-5):
+    """Recompute the residual MLP from x and take the LayerNorm backward of ``dout``.
+    -> (dz [R,128] fp32, h [R,H] bf16, dgamma, dbeta)."""
+    _chk(x, dout, w1, b1, w2, b2, gamma)
+    dz = torch.empty_like(x)
+    h16 = torch.empty((x.shape[0], w1.shape[0]), dtype=torch.bfloat16, device=x.device)
+    dgamma, dbeta = torch.zeros_like(gamma), torch.zeros_like(gamma)
+    if x.numel():
+        _be().mlp_bwd_ln(x, dout, w1, b1, w2, b2, gamma, dz, h16, dgamma, dbeta, eps, _mlp_ws(w1))
+    return dz, h16, dgamma, dbeta
+
+
+def mlp_bwd_dgrad(dz, h16, w1, w2):
+    """-> (dx = dz + dh.W1 [R,128] fp32, dh = (dz.W2)*(h>0) [R,H] bf16)."""
+    _chk(dz, w1, w2)
+    _chk(h16, bf16_ok=True)
+    dx = torch.empty_like(dz)
+    dh16 = torch.empty_like(h16)
+    if dz.numel():
+        _be().mlp_bwd_dgrad(dz, h16, w1, w2, dx, dh16, _mlp_ws(w1))
+    return dx, dh16
+
+
 # ----------------------------------------------------------------------------- fused attention scores (fp32)
 def attn_fused_available(n: int, d: int) -> bool:
     return d == 128 and n >= 4

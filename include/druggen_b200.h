@@ -112,6 +112,18 @@ int dg_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2
                const float* gamma, const float* beta, float* out, long long R, int D, int H, float eps,
                void* workspace, long long workspace_bytes, void* stream);
 
+/* First half of the residual-MLP backward in one kernel: recompute h = relu(fc1(x)+b1) and z = x + fc2(h) + b2,
+ * then the LayerNorm backward of `dout` through z.  Writes dz[R,D] (fp32), h_bf16[R,H] (bf16, for the dgrad and
+ * weight-gradient passes); dgamma[D], dbeta[D] += (zero first).  Same workspace contract as dg_mlp_fwd. */
+int dg_mlp_bwd_ln(const float* x, const float* dout, const float* w1, const float* b1, const float* w2,
+                  const float* b2, const float* gamma, float* dz, void* h_bf16, float* dgamma, float* dbeta,
+                  long long R, int D, int H, float eps, void* workspace, long long workspace_bytes, void* stream);
+/* Second half: dh = (dz . W2) * (h > 0) written as bf16 [R,H]; dx = dz + dh . W1 written [R,D] (fp32).
+ * (threshold_backward + the two dgrad `mm`s + the residual add of layers.py:51-54,191-192.) */
+int dg_mlp_bwd_dgrad(const float* dz, const void* h_bf16, const float* w1, const float* w2, float* dx,
+                     void* dh_bf16, long long R, int D, int H, void* workspace, long long workspace_bytes,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -164,3 +164,14 @@ class EmulBackend:
         if da_in is not None:
             da = da + da_in
         self.modulate_bwd(da, q, k, e, c, dq, dk, de)
+
+    def mlp_bwd_ln(self, x, dout, w1, b1, w2, b2, gamma, dz, h16, dgamma, dbeta, eps, workspace):
+        h = torch.relu(self._mm(x, w1.t(), "bf16") + b1)
+        h16.copy_(h)
+        m = self._mm(h16.to(x.dtype), w2.t(), "bf16") + b2
+        self.add_ln_bwd(dout, x, m, gamma, dz, dgamma, dbeta, eps)
+
+    def mlp_bwd_dgrad(self, dz, h16, w1, w2, dx, dh16, workspace):
+        dh = self._mm(dz, w2, "bf16") * (h16 > 0).to(dz.dtype)
+        dh16.copy_(dh)
+        dx.copy_(dz + self._mm(dh16.to(dz.dtype), w1, "bf16"))

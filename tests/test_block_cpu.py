@@ -168,3 +168,31 @@ def test_training_dropout_raises():
         enc(torch.zeros(1, 2, 128), torch.zeros(1, 2, 2, 128))
     enc.eval()
     enc(torch.zeros(1, 2, 128), torch.zeros(1, 2, 2, 128))
+
+
+def test_fused_branch_wiring_in_throughput_mode():
+    """With precision 'bf16' the block routes through the fused-kernel entry points (mlp_fwd, mlp_bwd_ln,
+    mlp_bwd_dgrad, attn_scores_*, bf16-stored hidden).  On the emulation the only difference from the oracle is the
+    bf16 rounding of the stored hidden activation, so gradients agree to ~1e-2."""
+    kernels.set_precision("bf16")
+    d, n, b, heads = 128, 5, 2, 8
+    p = _block_params(dtype=torch.float32, d=d)
+    g = torch.Generator().manual_seed(6)
+    x0, y0 = torch.randn(b, n, d, generator=g), torch.randn(b, n, n, d, generator=g)
+    wx, wy = torch.randn(b, n, d, generator=g), torch.randn(b, n, n, d, generator=g)
+
+    def run(kind):
+        x, y = x0.clone().requires_grad_(True), y0.clone().requires_grad_(True)
+        pp = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
+        if kind == "oracle":
+            xo, yo = orc.block_forward(x, y, {"blk." + k: v for k, v in pp.items()}, "blk.", heads)
+        else:
+            xo, yo = encoder_block(x, y, [pp[k] for k in BLOCK_PARAM_NAMES], heads, True)
+        ((xo * wx).sum() + (yo * wy).sum()).backward()
+        return xo, yo, x.grad, y.grad, {k: v.grad for k, v in pp.items()}
+
+    ref, got = run("oracle"), run("ckpt")
+    for i in range(4):
+        assert rel_l2(got[i], ref[i]) < 2e-2, i
+    for k in BLOCK_PARAM_NAMES:
+        assert rel_l2(got[4][k], ref[4][k]) < 3e-2, k

@@ -201,3 +201,30 @@ def test_bf16_storage_gemms(cuda_dev, R):
         assert rel_l2(gb, dh16.double().sum(0)) < 1e-5
         gw2 = K.gemm_tn(dz, h16)                                        # fp32 a, bf16 b
         assert rel_l2(gw2, bf(dz).t() @ h16.double()) < 2e-5
+
+
+@pytest.mark.parametrize("R", [1, 129, 2025, 128 * 148 + 77, 128 * 148 * 2 + 5])
+@pytest.mark.parametrize("H", [384, 128])
+def test_fused_mlp_bwd(cuda_dev, R, H):
+    """the two fused backward chains vs fp64 on bf16-rounded operands: LN backward + h spill, gated dgrad + dh spill"""
+    x, dout = rnd(cuda_dev, R, 128), rnd(cuda_dev, R, 128, seed=7)
+    w1, b1 = rnd(cuda_dev, H, 128, seed=1, scale=128 ** -0.5), rnd(cuda_dev, H, seed=2, scale=0.1)
+    w2, b2 = rnd(cuda_dev, 128, H, seed=3, scale=H ** -0.5), rnd(cuda_dev, 128, seed=4, scale=0.1)
+    gamma = rnd(cuda_dev, 128, seed=5, scale=0.1) + 1.0
+    bf = lambda t: t.to(torch.bfloat16).double()  # noqa: E731
+    with K.precision("bf16"):
+        dz, h16, dgam, dbet = K.mlp_bwd_ln(x, dout, w1, b1, w2, b2, gamma)
+        h_ref = torch.relu(bf(x) @ bf(w1).t() + b1.double())
+        assert rel_l2(h16.double(), bf(h_ref.float())) < 3e-3
+        z = x.double() + h16.double() @ bf(w2).t() + b2.double()          # from the kernel's own h: isolates the LN math
+        mu, var = z.mean(-1, keepdim=True), z.var(-1, unbiased=False, keepdim=True)
+        r = torch.rsqrt(var + 1e-5)
+        xh = (z - mu) * r
+        gh = dout.double() * gamma.double()
+        dz_ref = r * (gh - gh.mean(-1, keepdim=True) - xh * (gh * xh).mean(-1, keepdim=True))
+        assert rel_l2(dz, dz_ref) < 2e-4
+        assert rel_l2(dgam, (dout.double() * xh).sum(0)) < 2e-4 and rel_l2(dbet, dout.double().sum(0)) < 1e-5
+        dx, dh16 = K.mlp_bwd_dgrad(dz, h16, w1, w2)
+        dh_ref = (bf(dz) @ bf(w2)) * (h16.double() > 0)
+        assert rel_l2(dh16.double(), bf(dh_ref.float())) < 3e-3
+        assert rel_l2(dx, dz.double() + dh16.double() @ bf(w1)) < 2e-5

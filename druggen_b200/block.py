@@ -289,14 +289,17 @@ class EncoderBlockBwdFn(Function):
         heads, edge_out = ctx.heads, ctx.edge_out
         with torch.enable_grad():
             leaves, outs, gouts = _recompute(x, y, dxo, dyo, params, heads, edge_out, True)
-            grads = torch.autograd.grad(outs, leaves, gouts, create_graph=True, allow_unused=True)
-            pairs = [(g, ui) for g, ui in zip(grads, u) if g is not None and ui is not None and g.requires_grad]
+            # only the first-order gradients that actually received a cotangent are rebuilt with a graph: in the
+            # gradient penalty that is (dx, dy) -- the weight-gradient contractions are not even launched
+            live = [i for i, ui in enumerate(u) if ui is not None and i < len(leaves)]
             wrt = leaves + tuple(gouts)
-            if pairs:
-                second = list(torch.autograd.grad([g for g, _ in pairs], wrt,
-                                                  [ui.contiguous() for _, ui in pairs], allow_unused=True))
-            else:
-                second = [None] * len(wrt)
+            second = [None] * len(wrt)
+            if live:
+                grads = torch.autograd.grad(outs, [leaves[i] for i in live], gouts, create_graph=True, allow_unused=True)
+                pairs = [(g, u[i]) for g, i in zip(grads, live) if g is not None and g.requires_grad]
+                if pairs:
+                    second = list(torch.autograd.grad([g for g, _ in pairs], wrt, [ui.contiguous() for _, ui in pairs],
+                                                      allow_unused=True))
         n = len(params)
         tail = second[2 + n:]
         g_dxo = tail.pop(0) if dxo is not None else None

@@ -57,15 +57,18 @@ __device__ __forceinline__ void combine4(const float* pm, const float* ps, const
 }
 
 template <bool kBwd>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 attn_scores_kernel(const float* __restrict__ dg, const float* __restrict__ da_in, const float* __restrict__ q,
                    const float* __restrict__ k, const float* __restrict__ v, const float* __restrict__ e, float c,
                    float* __restrict__ a_out, float* __restrict__ g_out, float* __restrict__ de, float* __restrict__ dq,
                    float* __restrict__ dk, float* __restrict__ dv, int N, int irows) {
   constexpr int D = 128;
   extern __shared__ __align__(16) float sm[];
-  float* red = sm;                       // [2 parity][3 (m,s,acc) | 1 (dq)][4 warps][128]
-  float* sdk = sm + 2 * 3 * 4 * D;       // [N][128]   (backward only)
+  // forward : red = [2 parity][3 (m,s,acc)][4 warps][128]   (one barrier per query atom)
+  // backward: red = [3 (m,s,acc)][4 warps][128] + [4 warps][128] for the dq partials (three barriers per query atom),
+  //           then the dk / dv accumulators [N][128] each -> 54 KB at N = 45, four CTAs per SM
+  float* red = sm;
+  float* sdk = sm + 16 * D;              // (backward only)
   float* sdv = sdk + N * D;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, b = blockIdx.y;
   const int ch = lane * 4;
@@ -83,7 +86,7 @@ attn_scores_kernel(const float* __restrict__ dg, const float* __restrict__ da_in
     const long long bi = ((long long)b * N + i) * D + ch;
     const float4 cq = f4s(ld4(q + bi), c);
     const long long base = (((long long)b * N + i) * N) * D + ch;
-    float* rd = red + ((i - i0) & 1) * 3 * 4 * D;
+    float* rd = kBwd ? red : red + ((i - i0) & 1) * 3 * 4 * D;
     // ---- sweep 1: scores of my key atoms, online softmax partials
     float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), s = make_float4(0.f, 0.f, 0.f, 0.f), acc = s;
     for (int j = jlo; j < jhi; j += kJU) {
@@ -152,7 +155,7 @@ attn_scores_kernel(const float* __restrict__ dg, const float* __restrict__ da_in
         }
     }
     // dq_i = c * sum over all key atoms: combine the 4 warps (reuse the m-slot of the other parity)
-    float* rq = red + (((i - i0) & 1) ^ 1) * 3 * 4 * D;
+    float* rq = red + 12 * D;
     st4(rq + w * D + ch, sq);
     __syncthreads();
     if (w == 0) {
@@ -160,7 +163,7 @@ attn_scores_kernel(const float* __restrict__ dg, const float* __restrict__ da_in
       st4(dq + bi, make_float4(c * (t0.x + t1.x + t2.x + t3.x), c * (t0.y + t1.y + t2.y + t3.y), c * (t0.z + t1.z + t2.z + t3.z),
                                c * (t0.w + t1.w + t2.w + t3.w)));
     }
-    __syncthreads();                                  // rq is the next query atom's statistics buffer
+    __syncthreads();                                  // statistics / dq buffers are reused by the next query atom
   }
   if (kBwd) {
     for (int j = jlo; j < jhi; ++j) {
@@ -178,7 +181,7 @@ static int attn_ok(int B, int N, int D) {
   if (D != 128) return fail("fused attention-score kernels need D == 128 (got %d)", D);
   if (B > 65535) return fail("B=%d exceeds the grid.y limit; split the batch", B);
   if (N < 4) return fail("fused attention-score kernels need N >= 4 (got %d)", N);
-  if ((size_t)(2 * N + 24) * D * 4 > 220 * 1024) return fail("N=%d too large for the per-CTA accumulators", N);
+  if ((size_t)(2 * N + 16) * D * 4 > 220 * 1024) return fail("N=%d too large for the per-CTA accumulators", N);
   return 0;
 }
 static int attn_irows(int B, int N, int ctas_per_sm) {
@@ -208,7 +211,7 @@ extern "C" int dg_attn_scores_bwd(const float* dg_, const float* da_in, const fl
                                   const float* e, float c, float* de, float* dq, float* dk, float* dv, int B, int N, int D,
                                   void* stream) {
   if (attn_ok(B, N, D)) return 1;
-  const size_t smem = (size_t)(24 + 2 * N) * D * 4;
+  const size_t smem = (size_t)(16 + 2 * N) * D * 4;
   if (smem > 48 * 1024) {
     cudaError_t er = cudaFuncSetAttribute(attn_scores_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (er != cudaSuccess) return fail("cudaFuncSetAttribute: %s", cudaGetErrorString(er));

@@ -31,8 +31,8 @@ SIGNATURES = {
     "dg_softmax_agg_fwd": [_P, _P, _P, _I, _I, _I, _P],
     "dg_softmax_agg_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "dg_softmax_agg_bwd_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
-    "dg_attn_scores_fwd": [_P, _P, _P, _P, _F, _P, _P, _I, _I, _I, _P],
-    "dg_attn_scores_bwd": [_P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _I, _I, _I, _P],
+    "dg_attn_scores_fwd": [_P, _P, _P, _P, _F, _P, _P, _P, _P, _I, _I, _I, _P],
+    "dg_attn_scores_bwd": [_P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "dg_mlp_bwd_ln": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _F, _P, _LL, _P],
     "dg_mlp_bwd_dgrad": [_P, _P, _P, _P, _P, _P, _LL, _I, _I, _P, _LL, _P],
     "dg_mlp_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _F, _P, _LL, _P],
@@ -197,16 +197,18 @@ def _mlp_fwd(self, x, w1, b1, w2, b2, gamma, beta, out, eps, workspace):
                r, d, h, eps, _ptr(workspace), workspace.numel())
 
 
-def _attn_scores_fwd(self, q, k, v, e, c, a, g):
+def _attn_scores_fwd(self, q, k, v, e, c, a, g, stats=None):
     b, n, d = q.shape
+    sm, si = stats if stats is not None else (None, None)
     self._call("dg_attn_scores_fwd", ("attn_scores_fwd[fused]", 0, _nbytes(e, a), "hbm"), _ptr(q), _ptr(k), _ptr(v), _ptr(e), c,
-               _ptr(a), _ptr(g), b, n, d)
+               _ptr(a), _ptr(g), _ptr(sm), _ptr(si), b, n, d)
 
 
-def _attn_scores_bwd(self, dg, da_in, q, k, v, e, c, de, dq, dk, dv):
+def _attn_scores_bwd(self, dg, da_in, q, k, v, e, c, de, dq, dk, dv, stats=None):
     b, n, d = q.shape
+    sm, si, g = stats if stats is not None else (None, None, None)
     self._call("dg_attn_scores_bwd", ("attn_scores_bwd[fused]", 0, _nbytes(e, da_in, de), "hbm"), _ptr(dg), _ptr(da_in), _ptr(q),
-               _ptr(k), _ptr(v), _ptr(e), c, _ptr(de), _ptr(dq), _ptr(dk), _ptr(dv), b, n, d)
+               _ptr(k), _ptr(v), _ptr(e), c, _ptr(sm), _ptr(si), _ptr(g), _ptr(de), _ptr(dq), _ptr(dk), _ptr(dv), b, n, d)
 
 
 def _mlp_bwd_ln(self, x, dout, w1, b1, w2, b2, gamma, dz, h16, dgamma, dbeta, eps, workspace):

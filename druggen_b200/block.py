@@ -66,16 +66,16 @@ def block_forward(x, y, params: Sequence[torch.Tensor], heads: int, edge_out: bo
     return x_out, y_out
 
 
-def _scores_fwd(q, k, v, e, c):
+def _scores_fwd(q, k, v, e, c, want_stats=False):
     if K.attn_fused_available(q.shape[1], q.shape[2]):
-        return K.attn_scores_fwd(q, k, v, e, c)
+        return K.attn_scores_fwd(q, k, v, e, c, want_stats)
     a = K.modulate_fwd(q, k, e, c)
-    return a, K.softmax_agg_fwd(a, v)
+    return (a, K.softmax_agg_fwd(a, v), None) if want_stats else (a, K.softmax_agg_fwd(a, v))
 
 
-def _scores_bwd(dg, da_in, a, q, k, v, e, c):
+def _scores_bwd(dg, da_in, a, q, k, v, e, c, stats=None):
     if K.attn_fused_available(q.shape[1], q.shape[2]):
-        return K.attn_scores_bwd(dg, da_in, q, k, v, e, c)
+        return K.attn_scores_bwd(dg, da_in, q, k, v, e, c, stats)
     da, dv = K.softmax_agg_bwd(dg, a, v, da_accum=da_in)
     dq, dk, de = K.modulate_bwd(da, q, k, e, c)
     return de, dq, dk, dv
@@ -179,7 +179,7 @@ def block_backward(x, y, dxo, dyo, params: Sequence[torch.Tensor], heads: int, e
     k = K.rows_gemm(x1, p("attn.k.weight"), True, p("attn.k.bias")).view(b, n, d)
     v = K.rows_gemm(x1, p("attn.v.weight"), True, p("attn.v.bias")).view(b, n, d)
     e = K.rows_gemm(y2d, p("attn.e.weight"), True, p("attn.e.bias"))
-    a, g = _scores_fwd(q, k, v, e.view(b, n, n, d), c)
+    a, g, sm_stats = _scores_fwd(q, k, v, e.view(b, n, n, d), c, want_stats=True)
     a2d = a.view(-1, d)
     g2d = g.view(-1, d)
     on = K.rows_gemm(g2d, p("attn.out_n.weight"), True, p("attn.out_n.bias"))
@@ -201,7 +201,7 @@ def block_backward(x, y, dxo, dyo, params: Sequence[torch.Tensor], heads: int, e
         wgrad("attn.out_e", dz4, a2d)
         da = K.rows_gemm(dz4, p("attn.out_e.weight"), False).view(b, n, n, d)
     # ---- attention: softmax-aggregate, modulation, q/k/v/e projections
-    de, dq, dk, dv = _scores_bwd(dg, da, a, q, k, v, e.view(b, n, n, d), c)
+    de, dq, dk, dv = _scores_bwd(dg, da, a, q, k, v, e.view(b, n, n, d), c, sm_stats)
     del da, a, e
     de2d = de.view(-1, d)
     wgrad("attn.e", de2d, y2d)

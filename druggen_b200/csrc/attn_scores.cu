@@ -61,7 +61,8 @@ __global__ void __launch_bounds__(128, 4)
 attn_scores_kernel(const float* __restrict__ dg, const float* __restrict__ da_in, const float* __restrict__ q,
                    const float* __restrict__ k, const float* __restrict__ v, const float* __restrict__ e, float c,
                    float* __restrict__ a_out, float* __restrict__ g_out, float* __restrict__ de, float* __restrict__ dq,
-                   float* __restrict__ dk, float* __restrict__ dv, int N, int irows) {
+                   float* __restrict__ dk, float* __restrict__ dv, float* __restrict__ stat_m, float* __restrict__ stat_inv,
+                   const float* __restrict__ g_in, int N, int irows) {
   constexpr int D = 128;
   extern __shared__ __align__(16) float sm[];
   // forward : red = [2 parity][3 (m,s,acc)][4 warps][128]   (one barrier per query atom)
@@ -87,6 +88,11 @@ attn_scores_kernel(const float* __restrict__ dg, const float* __restrict__ da_in
     const float4 cq = f4s(ld4(q + bi), c);
     const long long base = (((long long)b * N + i) * N) * D + ch;
     float* rd = kBwd ? red : red + ((i - i0) & 1) * 3 * 4 * D;
+    float4 M, inv, g;
+    const bool have_stats = kBwd && stat_m != nullptr;
+    if (have_stats) {                                // statistics saved by the forward kernel: no sweep, no barrier
+      M = ld4(stat_m + bi); inv = ld4(stat_inv + bi); g = ld4(g_in + bi);
+    } else {
     // ---- sweep 1: scores of my key atoms, online softmax partials
     float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), s = make_float4(0.f, 0.f, 0.f, 0.f), acc = s;
     for (int j = jlo; j < jhi; j += kJU) {
@@ -110,13 +116,16 @@ attn_scores_kernel(const float* __restrict__ dg, const float* __restrict__ da_in
     st4(rd + (1 * 4 + w) * D + ch, s);
     st4(rd + (2 * 4 + w) * D + ch, acc);
     __syncthreads();
-    float4 M, inv, g;
     combine4(rd + ch + 0, rd + 4 * D + ch + 0, rd + 8 * D + ch + 0, M.x, inv.x, g.x);
     combine4(rd + ch + 1, rd + 4 * D + ch + 1, rd + 8 * D + ch + 1, M.y, inv.y, g.y);
     combine4(rd + ch + 2, rd + 4 * D + ch + 2, rd + 8 * D + ch + 2, M.z, inv.z, g.z);
     combine4(rd + ch + 3, rd + 4 * D + ch + 3, rd + 8 * D + ch + 3, M.w, inv.w, g.w);
+    }
     if (!kBwd) {
-      if (w == 0) st4(g_out + bi, g);
+      if (w == 0) {
+        st4(g_out + bi, g);
+        if (stat_m != nullptr) { st4(stat_m + bi, M); st4(stat_inv + bi, inv); }
+      }
       continue;                                      // next i uses the other parity of `red`
     }
     // ---- sweep 2 (backward): gradients for my key atoms
@@ -197,19 +206,20 @@ static int attn_irows(int B, int N, int ctas_per_sm) {
 using namespace dg;
 
 extern "C" int dg_attn_scores_fwd(const float* q, const float* k, const float* v, const float* e, float c, float* a,
-                                  float* g, int B, int N, int D, void* stream) {
+                                  float* g, float* stat_m, float* stat_inv, int B, int N, int D, void* stream) {
   if (attn_ok(B, N, D)) return 1;
   const size_t smem = (size_t)24 * D * 4;
   const int irows = attn_irows(B, N, 8);
   dim3 grid((N + irows - 1) / irows, B);
+  if ((stat_m == nullptr) != (stat_inv == nullptr)) return fail("dg_attn_scores_fwd: pass both statistics buffers or neither");
   attn_scores_kernel<false><<<grid, 128, smem, (cudaStream_t)stream>>>(nullptr, nullptr, q, k, v, e, c, a, g, nullptr, nullptr,
-                                                                        nullptr, nullptr, N, irows);
+                                                                        nullptr, nullptr, stat_m, stat_inv, nullptr, N, irows);
   return check_launch("dg_attn_scores_fwd");
 }
 
 extern "C" int dg_attn_scores_bwd(const float* dg_, const float* da_in, const float* q, const float* k, const float* v,
-                                  const float* e, float c, float* de, float* dq, float* dk, float* dv, int B, int N, int D,
-                                  void* stream) {
+                                  const float* e, float c, const float* stat_m, const float* stat_inv, const float* g,
+                                  float* de, float* dq, float* dk, float* dv, int B, int N, int D, void* stream) {
   if (attn_ok(B, N, D)) return 1;
   const size_t smem = (size_t)(16 + 2 * N) * D * 4;
   if (smem > 48 * 1024) {
@@ -218,7 +228,8 @@ extern "C" int dg_attn_scores_bwd(const float* dg_, const float* da_in, const fl
   }
   const int irows = attn_irows(B, N, 4);
   dim3 grid((N + irows - 1) / irows, B);
+  if (stat_m != nullptr && (stat_inv == nullptr || g == nullptr)) return fail("dg_attn_scores_bwd: statistics need stat_inv and g too");
   attn_scores_kernel<true><<<grid, 128, smem, (cudaStream_t)stream>>>(dg_, da_in, q, k, v, e, c, nullptr, nullptr, de, dq, dk, dv,
-                                                                       N, irows);
+                                                                       const_cast<float*>(stat_m), const_cast<float*>(stat_inv), g, N, irows);
   return check_launch("dg_attn_scores_bwd");
 }

@@ -275,20 +275,23 @@ def attn_fused_available(n: int, d: int) -> bool:
     return d == 128 and n >= 4
 
 
-def attn_scores_fwd(q, k, v, e, c: float):
-    """-> (a, g): modulated scores (layers.py:123-125) and softmax-aggregate (layers.py:130-134), e read once."""
+def attn_scores_fwd(q, k, v, e, c: float, want_stats: bool = False):
+    """-> (a, g[, stats]): modulated scores (layers.py:123-125) and softmax-aggregate (layers.py:130-134), e read once.
+    ``want_stats`` also returns (max, 1/sum, g) per (b, i, channel) for ``attn_scores_bwd``."""
     _chk(q, k, v, e)
     a, g = torch.empty_like(e), torch.empty_like(q)
+    stats = (torch.empty_like(q), torch.empty_like(q)) if want_stats else None
     if e.numel():
-        _be().attn_scores_fwd(q, k, v, e, c, a, g)
-    return a, g
+        _be().attn_scores_fwd(q, k, v, e, c, a, g, stats)
+    return (a, g, stats + (g,)) if want_stats else (a, g)
 
 
-def attn_scores_bwd(dg, da_in, q, k, v, e, c: float):
-    """-> (de, dq, dk, dv) from dg (softmax path) and da_in (out_e path; may be None)."""
+def attn_scores_bwd(dg, da_in, q, k, v, e, c: float, stats=None):
+    """-> (de, dq, dk, dv) from dg (softmax path) and da_in (out_e path; may be None).  ``stats`` from the forward
+    skips the statistics sweep."""
     _chk(dg, da_in, q, k, v, e)
     de, dq = torch.empty_like(e), torch.empty_like(q)
     dk, dv = torch.zeros_like(k), torch.zeros_like(v)
     if e.numel():
-        _be().attn_scores_bwd(dg, da_in, q, k, v, e, c, de, dq, dk, dv)
+        _be().attn_scores_bwd(dg, da_in, q, k, v, e, c, de, dq, dk, dv, stats)
     return de, dq, dk, dv

@@ -97,12 +97,14 @@ int dg_softmax_agg_bwd_bwd(const float* ua, const float* uv, const float* dg, co
 /* ---- fused attention scores (fp32; D == 128, N >= 4) : layers.py:119-125 + :130-134 in one pass ------------ */
 /* a[b,i,j,:] = c q_i k_j (e^2+e) written (operand of out_e) and g[b,i,:] = sum_j softmax_j(a) v_j; e read once. */
 int dg_attn_scores_fwd(const float* q, const float* k, const float* v, const float* e, float c, float* a,
-                       float* g, int B, int N, int D, void* stream);
-/* First-order backward of the pair: de written from dg (softmax path) + da_in (out_e path, may be NULL);
- * dq written; dk, dv += (zero first).  Scores are recomputed from e, q, k. */
+                       float* g, float* stat_m, float* stat_inv, int B, int N, int D, void* stream);
+/* (stat_m, stat_inv: optional [B,N,D] outputs = per-channel softmax max and 1/sum, for the backward.)
+ * First-order backward of the pair: de written from dg (softmax path) + da_in (out_e path, may be NULL);
+ * dq written; dk, dv += (zero first).  Scores are recomputed from e, q, k; with (stat_m, stat_inv, g) from the
+ * forward the statistics sweep is skipped, with NULLs it is redone. */
 int dg_attn_scores_bwd(const float* dg, const float* da_in, const float* q, const float* k, const float* v,
-                       const float* e, float c, float* de, float* dq, float* dk, float* dv, int B, int N, int D,
-                       void* stream);
+                       const float* e, float c, const float* stat_m, const float* stat_inv, const float* g,
+                       float* de, float* dq, float* dk, float* dv, int B, int N, int D, void* stream);
 
 /* ---- fused tcgen05 kernels (bf16 operands, fp32 accumulate / epilogue) ----------------------------- */
 /* out = LN(x + fc2(relu(fc1(x) + b1)) + b2) * gamma + beta   -- the whole residual MLP of one stream in one

@@ -152,11 +152,15 @@ class EmulBackend:
         z = x + self._mm(h, w2.t(), "bf16") + b2
         self.add_ln_fwd(z, None, gamma, beta, out, eps)
 
-    def attn_scores_fwd(self, q, k, v, e, c, a, g):
+    def attn_scores_fwd(self, q, k, v, e, c, a, g, stats=None):
         self.modulate_fwd(q, k, e, c, a)
         self.softmax_agg_fwd(a, v, g)
+        if stats is not None:
+            m = a.max(dim=2).values
+            stats[0].copy_(m)
+            stats[1].copy_(1.0 / torch.exp(a - m[:, :, None, :]).sum(2))
 
-    def attn_scores_bwd(self, dg, da_in, q, k, v, e, c, de, dq, dk, dv):
+    def attn_scores_bwd(self, dg, da_in, q, k, v, e, c, de, dq, dk, dv, stats=None):
         a = torch.empty_like(e)
         self.modulate_fwd(q, k, e, c, a)
         da = torch.empty_like(e)

@@ -169,13 +169,14 @@ def test_fused_attn_scores(cuda_dev, B, N):
     d = lambda t: t.double()  # noqa: E731
     a64, g64 = torch.empty_like(d(e)), torch.empty_like(d(q))
     EM.attn_scores_fwd(d(q), d(k), d(v), d(e), c, a64, g64)
-    a, g = K.attn_scores_fwd(q, k, v, e, c)
+    a, g, stats = K.attn_scores_fwd(q, k, v, e, c, want_stats=True)
     assert rel_l2(a, a64) < 2e-6 and rel_l2(g, g64) < 1e-5
     for din in (da_in, None):
         de64, dq64, dk64, dv64 = torch.empty_like(a64), torch.empty_like(g64), torch.empty_like(g64), torch.empty_like(g64)
         EM.attn_scores_bwd(d(dg), None if din is None else d(din), d(q), d(k), d(v), d(e), c, de64, dq64, dk64, dv64)
-        for got, want in zip(K.attn_scores_bwd(dg, din, q, k, v, e, c), (de64, dq64, dk64, dv64)):
-            assert rel_l2(got, want) < 2e-5
+        for st in (None, stats):           # statistics recomputed in-kernel / taken from the forward
+            for got, want in zip(K.attn_scores_bwd(dg, din, q, k, v, e, c, st), (de64, dq64, dk64, dv64)):
+                assert rel_l2(got, want) < 2e-5
 
 
 @pytest.mark.parametrize("R", [1, 300, 128 * 148 + 77])

@@ -291,6 +291,11 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
     for (long long ti = 0; ti < my_tiles; ++ti) {
       const long long row0 = (blockIdx.x + ti * gridDim.x) * 128;
       const long long wrow0 = row0 + q * 32;                          // first global row of this warp
+      if (kMode == kBwdA && wrow0 + lane < R) {                       // the LayerNorm-backward gathers of dout come from L2
+        const float* pd = A.dout + (wrow0 + lane) * 128 + hf * 64;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pd));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pd + 32));
+      }
       for (int c = 0; c < HC; ++c) {
         // bf16 [R,H] side tensors viewed as 32-bit words: pitch H/2, this warp-half's 64 columns = 32 words
         const int wcol = (c * 128 + hf * 64) >> 1;

@@ -32,6 +32,22 @@ def peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def ncu_traffic(kernel_key, rows):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/r01_traffic.json, taken at 1 036 800 edge rows), scaled linearly to this run's rows; None if not captured."""
+    try:
+        tab = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+    except Exception:
+        return None
+    import re
+    base = re.sub(r"R=\d+,", "", kernel_key)
+    base = base.replace(",bf16", "")        # variant tags (+gate, +resid, a16 ...) stay: only the plain captured kernels match
+    for k, v in tab.items():
+        if not k.startswith("_") and k == base:
+            return v * rows / tab["_rows"]
+    return None
+
+
 def gan_flops_per_molecule(n, depth, d=DIM, r=MLP_RATIO, m=M_DIM, b=B_DIM):
     """Necessary GEMM FLOPs of one GAN step per molecule (74.57 GF at N=45, L=8).
     encoder fwd per layer F = d^2 [N^2 (4+4r) + N (8+4r)]; prologue P and heads counted too."""
@@ -117,7 +133,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "molecules/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, sample_b),
+        "config": workload_config(args, args.batch),      # the arm's config; the CPU runs a bounded sample of it (below)
         "cpu_baseline": {"value": val, "unit": "molecules/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -254,7 +270,8 @@ def main():
         else:
             ach, peak, unit = dom["flops"] / sec / 1e12, pk["bf16_tflops_sustained"], "TFLOP/s"
         out["roofline"] = {"kernel": be.profile_name(dom), "bound": dom["bound"], "achieved": ach, "peak": peak, "unit": unit,
-                           "frac": ach / peak, "traffic": None, "peak_source": pk_kind, "launches": dom["n"],
+                           "frac": ach / peak, "traffic": ncu_traffic(be.profile_name(dom), bsz * n * n), "peak_source": pk_kind,
+                           "launches": dom["n"],
                            "avg_launch_ms": dom["ms"] / dom["n"], "share_of_step": dom["ms"] / (ms * args.steps),
                            "algorithmic_bytes_per_launch": dom["bytes"] / dom["n"], "algorithmic_flops_per_launch": dom["flops"] / dom["n"]}
     if world == 1 and not args.no_cpu_baseline:

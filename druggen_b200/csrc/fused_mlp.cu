@@ -166,10 +166,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
     for (int i = 0; i < 2; ++i) {
       mbar_init(&x_full[i], 128); mbar_init(&x_empty[i], 1);
       mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1);
-      mbar_init(&hb_full[i], 256); mbar_init(&hb_empty[i], 1);
+      mbar_init(&hb_full[i], 8); mbar_init(&hb_empty[i], 1);
     }
-    for (int i = 0; i < 3; ++i) { mbar_init(&hacc_full[i], 1); mbar_init(&hacc_empty[i], 256); }
-    mbar_init(z_full, 1); mbar_init(z_empty, 256);
+    for (int i = 0; i < 3; ++i) { mbar_init(&hacc_full[i], 1); mbar_init(&hacc_empty[i], 8); }
+    mbar_init(z_full, 1); mbar_init(z_empty, 8);     // epilogue barriers: one elected arrival per warp
     fence_barrier_init();
   }
   if (warp == 12) tmem_alloc(tmem_slot, 512);
@@ -311,7 +311,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
         tmem_ld32(tmem_base + lane_base + c * 128 + hf * 64 + 32, v + 32);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(&hacc_empty[c]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&hacc_empty[c]);
         if (kMode == kBwdB) {
           float gw[32];                                              // 64 bf16 sign masks of this row
           gather_finish(gq, 2, stg, lane, gw);
@@ -324,14 +325,19 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
         } else {
           const float* bb = sB1 + c * 128 + hf * 64;
 #pragma unroll
-          for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i] + bb[i], 0.f);
+          for (int i = 0; i < 64; i += 4) {
+            const float4 b4 = ld4(bb + i);
+            v[i] = fmaxf(v[i] + b4.x, 0.f); v[i + 1] = fmaxf(v[i + 1] + b4.y, 0.f);
+            v[i + 2] = fmaxf(v[i + 2] + b4.z, 0.f); v[i + 3] = fmaxf(v[i + 3] + b4.w, 0.f);
+          }
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           st_block_chunk(hblk, row, j, make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
                          make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]));
         fence_async_smem();
-        mbar_arrive(&hb_full[hs]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&hb_full[hs]);
         ++hcount;
         if (kMode != kFwd) {                                          // spill the chunk as bf16 for the weight-gradient pass
           float pk[32];
@@ -356,7 +362,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
         float v[32];
         tmem_ld32(tmem_base + lane_base + 384 + hf * 64 + cgl * 32, v);
         tmem_ld_wait();
-        if (cgl == 1) { tc_fence_before(); mbar_arrive(z_empty); }
+        if (cgl == 1) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(z_empty); }
         const float* bb = sB2 + hf * 64 + cgl * 32;
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
@@ -381,7 +387,11 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
       if (kMode == kFwd) {
         const float* be = sBe + hf * 64;
 #pragma unroll
-        for (int i = 0; i < 64; ++i) a[i] = (a[i] - mean) * rstd * gg[i] + be[i];
+        for (int i = 0; i < 64; i += 4) {
+          const float4 g4 = ld4(gg + i), e4 = ld4(be + i);
+          a[i] = (a[i] - mean) * rstd * g4.x + e4.x; a[i + 1] = (a[i + 1] - mean) * rstd * g4.y + e4.y;
+          a[i + 2] = (a[i + 2] - mean) * rstd * g4.z + e4.z; a[i + 3] = (a[i + 3] - mean) * rstd * g4.w + e4.w;
+        }
 #pragma unroll
         for (int g16 = 0; g16 < 4; ++g16) scatter_rows16(A.out, wrow0, R, 128, hf * 64 + g16 * 16, stg, lane, a + g16 * 16);
         continue;

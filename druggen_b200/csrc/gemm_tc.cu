@@ -345,59 +345,79 @@ gemm_tn_tc_kernel(const float* __restrict__ a, const float* __restrict__ b, floa
       uint8_t* base = sOp + st * stage_bytes;
       const long long row0 = tile * kTnRows;
       // items: (block, row, chunk j); 64 rows x 8 chunks = 512 items per block, 4 per thread
-      // blocks are loaded in pairs (nblk is even): 16 independent 16-byte loads in flight per thread
+      // Blocks are loaded in batches that keep 16 independent 16-byte loads in flight per thread:
+      // two fp32 blocks (8 x float4 each) or four bf16 blocks (4 x uint4 each, copied to smem without conversion).
+      const int MA = M / 64;
 #pragma unroll
-      for (int bp = 0; bp < 6; ++bp) {
-        if (2 * bp >= nblk) break;
-        float4 v[16];
+      for (int seg = 0; seg < 2; ++seg) {
+        const float* src = seg == 0 ? a : b;
+        const int ld = seg == 0 ? M : N, nb = seg == 0 ? MA : nblk - MA, blk_off = seg == 0 ? 0 : MA;
+        const bool src16 = seg == 0 ? (flags & DG_A_BF16) : (flags & DG_OUT_BF16);
+        const bool sum = seg == 0 && colsum_a != nullptr;
+        if (src16) {
+          const uint16_t* s16 = reinterpret_cast<const uint16_t*>(src);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int blk = 2 * bp + h;
-          const bool is_a = blk < M / 64;
-          const float* src = is_a ? a : b;
-          const int ld = is_a ? M : N, cb = is_a ? blk : blk - M / 64;
-          const bool src16 = is_a ? (flags & DG_A_BF16) : (flags & DG_OUT_BF16);
-          if (src16) {                // bf16 in HBM: issue the four 16-byte loads, then widen (exactly)
-            uint4 c16[4];
+          for (int g0 = 0; g0 < 6; g0 += 4) {
+            if (g0 >= nb) break;
+            uint4 c16[16];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              int item = q * 128 + lt, r = item >> 3, j = item & 7;
-              c16[q] = (row0 + r < R) ? *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(src) + (row0 + r) * ld + cb * 64 + j * 8)
-                                      : make_uint4(0, 0, 0, 0);
-            }
+            for (int h = 0; h < 4; ++h)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              v[h * 8 + 2 * q] = make_float4(__uint_as_float(c16[q].x << 16), __uint_as_float(c16[q].x & 0xFFFF0000u),
-                                             __uint_as_float(c16[q].y << 16), __uint_as_float(c16[q].y & 0xFFFF0000u));
-              v[h * 8 + 2 * q + 1] = make_float4(__uint_as_float(c16[q].z << 16), __uint_as_float(c16[q].z & 0xFFFF0000u),
-                                                 __uint_as_float(c16[q].w << 16), __uint_as_float(c16[q].w & 0xFFFF0000u));
-            }
-          } else {
+              for (int q = 0; q < 4; ++q) {
+                int item = q * 128 + lt, r = item >> 3, j = item & 7;
+                c16[h * 4 + q] = (g0 + h < nb && row0 + r < R) ? *reinterpret_cast<const uint4*>(s16 + (row0 + r) * ld + (g0 + h) * 64 + j * 8)
+                                                                : make_uint4(0, 0, 0, 0);
+              }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              int item = q * 128 + lt, r = item >> 3, j = item & 7;
-              if (row0 + r < R) {
-                const float* p = src + (row0 + r) * ld + cb * 64 + j * 8;
-                v[h * 8 + 2 * q] = ld4(p); v[h * 8 + 2 * q + 1] = ld4(p + 4);
-              } else {
-                v[h * 8 + 2 * q] = v[h * 8 + 2 * q + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int h = 0; h < 4; ++h) {
+              if (g0 + h >= nb) break;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                int item = q * 128 + lt, r = item >> 3, j = item & 7;
+                *reinterpret_cast<uint4*>(base + (blk_off + g0 + h) * kTnBlk + r * 128 + ((j ^ (r & 7)) << 4)) = c16[h * 4 + q];
+                if (sum && g0 + h < 6) {
+                  const uint4 c = c16[h * 4 + q];
+                  float* acc = cs[g0 + h];
+                  acc[0] += __uint_as_float(c.x << 16); acc[1] += __uint_as_float(c.x & 0xFFFF0000u);
+                  acc[2] += __uint_as_float(c.y << 16); acc[3] += __uint_as_float(c.y & 0xFFFF0000u);
+                  acc[4] += __uint_as_float(c.z << 16); acc[5] += __uint_as_float(c.z & 0xFFFF0000u);
+                  acc[6] += __uint_as_float(c.w << 16); acc[7] += __uint_as_float(c.w & 0xFFFF0000u);
+                }
               }
             }
           }
-        }
+        } else {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int blk = 2 * bp + h;
+          for (int g0 = 0; g0 < 6; g0 += 2) {
+            if (g0 >= nb) break;
+            float4 v[16];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            int item = q * 128 + lt;
-            st_block_chunk(base + blk * kTnBlk, item >> 3, item & 7, v[h * 8 + 2 * q], v[h * 8 + 2 * q + 1]);
-          }
-          if (colsum_a != nullptr && blk < 6 && blk < M / 64) {
+            for (int h = 0; h < 2; ++h)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              cs[blk][0] += v[h * 8 + 2 * q].x; cs[blk][1] += v[h * 8 + 2 * q].y; cs[blk][2] += v[h * 8 + 2 * q].z; cs[blk][3] += v[h * 8 + 2 * q].w;
-              cs[blk][4] += v[h * 8 + 2 * q + 1].x; cs[blk][5] += v[h * 8 + 2 * q + 1].y; cs[blk][6] += v[h * 8 + 2 * q + 1].z; cs[blk][7] += v[h * 8 + 2 * q + 1].w;
+              for (int q = 0; q < 4; ++q) {
+                int item = q * 128 + lt, r = item >> 3, j = item & 7;
+                if (row0 + r < R) {
+                  const float* p = src + (row0 + r) * ld + (g0 + h) * 64 + j * 8;
+                  v[h * 8 + 2 * q] = ld4(p); v[h * 8 + 2 * q + 1] = ld4(p + 4);
+                } else {
+                  v[h * 8 + 2 * q] = v[h * 8 + 2 * q + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+              }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                int item = q * 128 + lt;
+                st_block_chunk(base + (blk_off + g0 + h) * kTnBlk, item >> 3, item & 7, v[h * 8 + 2 * q], v[h * 8 + 2 * q + 1]);
+              }
+              if (sum && g0 + h < 6) {
+                float* acc = cs[g0 + h];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  acc[0] += v[h * 8 + 2 * q].x; acc[1] += v[h * 8 + 2 * q].y; acc[2] += v[h * 8 + 2 * q].z; acc[3] += v[h * 8 + 2 * q].w;
+                  acc[4] += v[h * 8 + 2 * q + 1].x; acc[5] += v[h * 8 + 2 * q + 1].y; acc[6] += v[h * 8 + 2 * q + 1].z; acc[7] += v[h * 8 + 2 * q + 1].w;
+                }
+              }
             }
           }
         }

@@ -16,7 +16,8 @@ import sys
 import threading
 import time
 
-import torch
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")   # B=2048 peaks at ~143 GB: avoid fragmentation
+import torch  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -257,6 +258,7 @@ def main():
         "config": workload_config(args, bsz), "clocks": clk,
         "e2e": {"value": total / (ms_e2e / 1e3), "unit": "molecules/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8},
         "gpu_launches": launches, "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
+        "reserved_mem_gb": round(torch.cuda.max_memory_reserved() / 2 ** 30, 1),
         "losses": {"d": losses[0], "g": losses[1]},
         "step_tflops": flops_mol * bsz / (ms / 1e3) / 1e12,
         "step_frac_of_bf16_sustained": flops_mol * bsz / (ms / 1e3) / 1e12 / pk["bf16_tflops_sustained"],
@@ -291,4 +293,12 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except torch.cuda.OutOfMemoryError:
+        # the default batch (2048 molecules per GPU, ~143 GB peak) did not fit next to whatever else holds memory on
+        # this device: re-run the same workload at half the batch in a fresh process (the JSON's config says which batch ran)
+        if "--batch" in sys.argv or os.environ.get("DRUGGEN_BENCH_RETRY") or int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            raise
+        os.environ["DRUGGEN_BENCH_RETRY"] = "1"
+        os.execv(sys.executable, [sys.executable] + sys.argv + ["--batch", "1024"])

@@ -254,7 +254,7 @@ def main():
     out = {
         "metric": METRIC, "value": total / (ms / 1e3), "unit": "molecules/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"bf16": "bf16", "fp32": "f32", "bf16x3": "bf16x3"}[args.precision], "data": "synthetic",
+        "dtype": {"bf16": "bf16", "fp32": "f32"}[args.precision], "data": "synthetic",
         "config": workload_config(args, bsz), "clocks": clk,
         "e2e": {"value": total / (ms_e2e / 1e3), "unit": "molecules/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8},
         "gpu_launches": launches, "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),

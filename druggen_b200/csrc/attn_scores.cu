@@ -21,10 +21,6 @@ namespace dg {
 
 constexpr int kJU = 4;   // key atoms per load batch: 4 rows x (e, da) x 16 B in flight per lane
 
-struct F4 {
-  float x, y, z, w;
-};
-__device__ __forceinline__ float4 f4mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
 __device__ __forceinline__ float4 f4s(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
 
 // one channel of the online-softmax update with `n` new scores

@@ -14,7 +14,6 @@ namespace v4 {
 constexpr int D = 128;
 constexpr int JU = 4;
 
-#define DG_F4(expr_x, expr_y, expr_z, expr_w) make_float4(expr_x, expr_y, expr_z, expr_w)
 #define DG_EACH(OP) OP(x) OP(y) OP(z) OP(w)
 
 __device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
@@ -146,11 +145,7 @@ modulate_bwd_bwd_kernel(const float* __restrict__ uq, const float* __restrict__ 
   flush_acc(sgk, g_k, N, c);
 }
 
-// online-softmax partial of one channel over a batch (NEXTRA extra running sums, all rescaled together)
-template <int NS>
-struct Run {
-  float m, s[NS];
-};
+// combine the four warps' online-softmax partials of one channel: running max M and NS rescaled running sums
 template <int NS>
 __device__ __forceinline__ void combine_runs(const float* pm, const float* ps, int stride, float& M, float* S) {
   // pm: [4 warps][128]; ps: [NS][4 warps][128] (stride between sums = `stride` floats)

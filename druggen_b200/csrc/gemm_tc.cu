@@ -517,7 +517,7 @@ int rows_gemm_tc(const void* a_, const float* w, int w_is_nk, const float* bias,
   const float* a = (const float*)a_;
   const float* gate = (const float*)gate_;
   float* out = (float*)out_;
-  if (prec == DG_PREC_BF16X3 || !rows_tc_ok(K, N)) {
+  if (!rows_tc_ok(K, N)) {
     if (flags) return fail("dg_rows_gemm: bf16 storage is only available for the tcgen05 shapes (K=%d N=%d)", K, N);
     return rows_gemm_fp32(a, w, w_is_nk, bias, relu, gate, resid, out, R, K, N, s);
   }
@@ -542,7 +542,7 @@ int gemm_tn_tc(const void* a_, const void* b_, float* out, float* colsum_a, long
   const float* a = (const float*)a_;
   const float* b = (const float*)b_;
   const bool ok = M % 128 == 0 && N % 128 == 0 && M >= 128 && N >= 128 && (M / 128) * N <= 512 && N <= 384 && M <= 384;
-  if (prec == DG_PREC_BF16X3 || !ok) {
+  if (!ok) {
     if (flags) return fail("dg_gemm_tn: bf16 storage is only available for the tcgen05 shapes (M=%d N=%d)", M, N);
     return gemm_tn_fp32(a, b, out, colsum_a, R, M, N, s);
   }

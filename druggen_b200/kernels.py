@@ -12,7 +12,6 @@ channels; "rows" are flattened node rows [B*N, D] or edge rows [B*N*N, D].
 from __future__ import annotations
 
 import os
-from typing import Optional
 
 import torch
 
@@ -21,8 +20,7 @@ from . import _lib
 # precision of the dense contractions (GEMMs).  Everything else is always fp32.
 #   fp32   : CUDA-core fp32 FMA GEMM (parity mode; bit-for-bit fp32 accumulate)
 #   bf16   : tcgen05 bf16 x bf16 -> fp32 (TMEM accumulators)           -- throughput mode
-#   bf16x3 : tcgen05 three-pass split (hi*hi + hi*lo + lo*hi) -> ~fp32 accuracy
-PRECISIONS = ("fp32", "bf16", "bf16x3")
+PRECISIONS = ("fp32", "bf16")
 _precision = os.environ.get("DRUGGEN_B200_PRECISION", "bf16")
 
 

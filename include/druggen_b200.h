@@ -15,7 +15,6 @@
  *   - `prec` selects the arithmetic of the dense contractions only:
  *       DG_PREC_FP32   CUDA-core fp32 FMA                     (parity mode)
  *       DG_PREC_BF16   tcgen05.mma kind::f16 bf16 x bf16 -> fp32 in TMEM   (throughput mode)
- *       DG_PREC_BF16X3 tcgen05 3-pass split bf16 (hi*hi+hi*lo+lo*hi) -> fp32-class accuracy
  *     every other operation (LayerNorm, softmax, modulation, reductions) is fp32 in all modes.
  */
 #ifndef DRUGGEN_B200_H
@@ -28,7 +27,6 @@ extern "C" {
 #define DG_ABI_VERSION 1
 #define DG_PREC_FP32 0
 #define DG_PREC_BF16 1
-#define DG_PREC_BF16X3 2
 
 int dg_abi_version(void);
 /* Thread-local text of the last rejected call. */

@@ -1,7 +1,7 @@
 """Parity of the CUDA path (through the C-ABI) with the CPU oracle and the reference golden vectors.
 
 Tolerances (relative L2 against the fp32 CPU oracle / reference):
-  fp32 and bf16x3 precision : 1e-3  (north_star bar; measured ~1e-6 / ~1e-5)
+  fp32 precision (parity mode) : 1e-3  (north_star bar; measured ~1e-6)
   bf16 precision            : reported, bounded at 5e-2 for outputs (bf16 operand rounding, ~7e-3 expected)
 argmax decode: identical wherever the reference top-1/top-2 logit gap exceeds 1e-4.
 """
@@ -16,10 +16,6 @@ pytestmark = pytest.mark.gpu
 PARITY_TOL = 1e-3
 
 
-def _parity_modes():
-    return ["fp32"] + (["bf16x3"] if dg.kernels._lib.load().dg_has_tcgen05() and _tc_built() else [])
-
-
 def _tc_built():
     try:
         with dg.precision("bf16"):
@@ -30,7 +26,7 @@ def _tc_built():
         return False
 
 
-@pytest.fixture(params=["fp32", "bf16x3"])
+@pytest.fixture(params=["fp32"])
 def parity_mode(request):
     if request.param != "fp32" and not _tc_built():
         pytest.skip("tcgen05 contractions not built")

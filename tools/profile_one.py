@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Launch each hot-path kernel twice at the bench size (B=512, N=45) so ncu can capture it:
     ncu --set full --clock-control none --import-source on \\
-        -k regex:'mlp_fwd_tc|rows_gemm_tc|gemm_tn_tc|attn_scores|add_ln_bwd_kernel' -c 12 -o gpurun_out/prof python tools/profile_one.py
+        -k regex:'mlp_chain|rows_gemm_tc|gemm_tn_tc|attn_scores|add_ln_bwd_kernel|bwd_bwd' -c 13 -o gpurun_out/prof python tools/profile_one.py
 """
 import os
 import sys
@@ -30,11 +30,15 @@ with dg.precision("bf16"):
         K.rows_gemm(x, wd, True, b2)                                    # 128x128 projection
         h16 = K.rows_gemm(x, w1, True, b1, relu=True, out_bf16=True)    # fc1 + ReLU -> bf16 hidden
         K.rows_gemm(dy, w2, False, gate=h16, out_bf16=True)             # dgrad with fused ReLU gate
+        dz, hh, _, _ = K.mlp_bwd_ln(x, dy, w1, b1, w2, b2, gamma)        # fused: recompute + LayerNorm backward + h spill
+        K.mlp_bwd_dgrad(dz, hh, w1, w2)                                 # fused: gated dgrad + residual + dh spill
         K.gemm_tn(dy, x)                                                # weight gradient 128x128
         K.gemm_tn(dy, h16)                                              # weight gradient 128x384 (bf16 operand)
         K.add_ln_bwd(dy, x, x, gamma)
         e4 = x.view(b, n, n, d)
         K.attn_scores_fwd(q, k, v, e4, 0.25)
         K.attn_scores_bwd(dg_, dy.view(b, n, n, d), q, k, v, e4, 0.25)
+        K.modulate_bwd_bwd(q, k, e4, dy.view(b, n, n, d), q, k, e4, 0.25)   # second-order kernels of the gradient penalty
+        K.softmax_agg_bwd_bwd(dy.view(b, n, n, d), v, dg_, e4, v)
 torch.cuda.synchronize()
 print("done")

@@ -87,17 +87,17 @@ class Encoder_Block(nn.Module):
         self.ln5 = nn.LayerNorm(dim)
         self.ln6 = nn.LayerNorm(dim)
         self._drop = drop_rate
-        self._plist = None
 
     def _params(self):
-        if self._plist is None:
-            named = dict(self.named_parameters())
-            self._plist = [named[n] for n in BLOCK_PARAM_NAMES]
-        return self._plist
-
-    def _apply(self, fn, *a, **k):          # .to()/.cuda() may replace Parameter objects
-        self._plist = None
-        return super()._apply(fn, *a, **k)
+        """The block's 30 tensors in BLOCK_PARAM_NAMES order, looked up by attribute on every call so it stays correct
+        after .to()/.cuda(), load_state_dict and in nn.DataParallel replicas (whose parameters are plain attributes)."""
+        out = []
+        for name in BLOCK_PARAM_NAMES:
+            obj = self
+            for part in name.split("."):
+                obj = getattr(obj, part)
+            out.append(obj)
+        return out
 
     def forward(self, x, y, _edge_out: bool = True):
         _no_train_dropout(self, self._drop)

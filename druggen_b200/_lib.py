@@ -32,12 +32,16 @@ SIGNATURES = {
     "dg_softmax_agg_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "dg_softmax_agg_bwd_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "dg_attn_scores_fwd": [_P, _P, _P, _P, _F, _P, _P, _P, _P, _I, _I, _I, _P],
-    "dg_attn_scores_bwd": [_P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "dg_attn_scores_bwd": [_P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "dg_softmax_agg16_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "dg_attn_edge_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _I, _I, _I, _F, _P, _LL, _P],
     "dg_mlp_bwd_ln": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _F, _P, _LL, _P],
     "dg_mlp_bwd_dgrad": [_P, _P, _P, _P, _P, _P, _LL, _I, _I, _P, _LL, _P],
     "dg_mlp_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _F, _P, _LL, _P],
 }
-INFO_SYMBOLS = ("dg_abi_version", "dg_last_error", "dg_has_tcgen05")
+INFO_SYMBOLS = ("dg_abi_version", "dg_last_error", "dg_has_tcgen05", "dg_set_option", "dg_get_option")
+ABI_VERSION = 2
+OPT_L2_PREFETCH = 0
 
 _lib = None
 _backend = None
@@ -58,8 +62,12 @@ def load():
         lib.dg_abi_version.restype = _I
         lib.dg_has_tcgen05.restype = _I
         lib.dg_last_error.restype = C.c_char_p
-        if lib.dg_abi_version() != 1:
+        lib.dg_set_option.argtypes, lib.dg_set_option.restype = [_I, _I], _I
+        lib.dg_get_option.argtypes, lib.dg_get_option.restype = [_I], _I
+        if lib.dg_abi_version() != ABI_VERSION:
             raise RuntimeError("libdruggen_b200.so ABI version mismatch")
+        if os.environ.get("DRUGGEN_B200_L2_PREFETCH") is not None:       # tuning switch, default on
+            lib.dg_set_option(OPT_L2_PREFETCH, int(os.environ["DRUGGEN_B200_L2_PREFETCH"]))
         _lib = lib
     return _lib
 
@@ -200,15 +208,33 @@ def _mlp_fwd(self, x, w1, b1, w2, b2, gamma, beta, out, eps, workspace):
 def _attn_scores_fwd(self, q, k, v, e, c, a, g, stats=None):
     b, n, d = q.shape
     sm, si = stats if stats is not None else (None, None)
-    self._call("dg_attn_scores_fwd", ("attn_scores_fwd[fused]", 0, _nbytes(e, a), "hbm"), _ptr(q), _ptr(k), _ptr(v), _ptr(e), c,
+    self._call("dg_attn_scores_fwd", ("attn_scores_fwd[fused]" if a is not None else "attn_scores_fwd[stats only]", 0, _nbytes(e, a), "hbm"), _ptr(q), _ptr(k), _ptr(v), _ptr(e), c,
                _ptr(a), _ptr(g), _ptr(sm), _ptr(si), b, n, d)
 
 
 def _attn_scores_bwd(self, dg, da_in, q, k, v, e, c, de, dq, dk, dv, stats=None):
     b, n, d = q.shape
     sm, si, g = stats if stats is not None else (None, None, None)
-    self._call("dg_attn_scores_bwd", ("attn_scores_bwd[fused]", 0, _nbytes(e, da_in, de), "hbm"), _ptr(dg), _ptr(da_in), _ptr(q),
-               _ptr(k), _ptr(v), _ptr(e), c, _ptr(sm), _ptr(si), _ptr(g), _ptr(de), _ptr(dq), _ptr(dk), _ptr(dv), b, n, d)
+    de16 = de.dtype == torch.bfloat16
+    self._call("dg_attn_scores_bwd", ("attn_scores_bwd[fused%s]" % (",de16" if de16 else ""), 0, _nbytes(e, da_in, de), "hbm"), _ptr(dg),
+               _ptr(da_in), _ptr(q), _ptr(k), _ptr(v), _ptr(e), c, _ptr(sm), _ptr(si), _ptr(g), _ptr(de), _ptr(dq), _ptr(dk), _ptr(dv),
+               b, n, d, int(de16))
+
+
+def _softmax_agg16_fwd(self, a16, v, g, stats=None):
+    b, n, d = v.shape
+    sm, si = stats if stats is not None else (None, None)
+    self._call("dg_softmax_agg16_fwd", ("softmax_agg16_fwd", 0, _nbytes(a16), "hbm"), _ptr(a16), _ptr(v), _ptr(g), _ptr(sm), _ptr(si),
+               b, n, d)
+
+
+def _attn_edge_fwd(self, y, q, k, we, be, woe, boe, gamma, beta, c, out, a16, e_out, z_out, eps, workspace):
+    b, n, d = q.shape
+    r = b * n * n
+    tag = ("+a16" if a16 is not None else "") + ("+e" if e_out is not None else "") + ("+z" if z_out is not None else "")
+    meta = (f"attn_edge_fwd[fused{tag}]", 4 * r * d * d, _nbytes(y, out, a16, e_out, z_out), "hbm")
+    self._call("dg_attn_edge_fwd", meta, _ptr(y), _ptr(q), _ptr(k), _ptr(we), _ptr(be), _ptr(woe), _ptr(boe), _ptr(gamma), _ptr(beta),
+               c, _ptr(out), _ptr(a16), _ptr(e_out), _ptr(z_out), b, n, d, eps, _ptr(workspace), workspace.numel())
 
 
 def _mlp_bwd_ln(self, x, dout, w1, b1, w2, b2, gamma, dz, h16, dgamma, dbeta, eps, workspace):
@@ -232,6 +258,8 @@ CudaBackend.mlp_bwd_ln = _mlp_bwd_ln
 CudaBackend.mlp_bwd_dgrad = _mlp_bwd_dgrad
 CudaBackend.attn_scores_fwd = _attn_scores_fwd
 CudaBackend.attn_scores_bwd = _attn_scores_bwd
+CudaBackend.softmax_agg16_fwd = _softmax_agg16_fwd
+CudaBackend.attn_edge_fwd = _attn_edge_fwd
 
 
 def cuda_backend() -> CudaBackend:

@@ -95,19 +95,28 @@ def block_forward_nograd(x, y, params: Sequence[torch.Tensor], heads: int, edge_
     k = K.rows_gemm(x1, p("attn.k.weight"), True, p("attn.k.bias")).view(b, n, d)
     v = K.rows_gemm(x1, p("attn.v.weight"), True, p("attn.v.bias")).view(b, n, d)
     y2d = y.reshape(-1, d)
-    e = K.rows_gemm(y2d, p("attn.e.weight"), True, p("attn.e.bias"))
-    a, g = _scores_fwd(q, k, v, e.view(b, n, n, d), c)
-    del e
+    chain = edge_out and K.attn_chain_available(b, n, d)
+    if chain:
+        # one tcgen05 kernel: E-projection, modulation, out_e projection, residual, LN4; the scores leave the SM once, as bf16
+        y3, a16, _, _ = K.attn_edge_fwd(y2d, q, k, p("attn.e.weight"), p("attn.e.bias"), p("attn.out_e.weight"),
+                                        p("attn.out_e.bias"), p("ln4.weight"), p("ln4.bias"), c)
+        g = K.softmax_agg16_fwd(a16, v)
+        del a16
+    else:
+        e = K.rows_gemm(y2d, p("attn.e.weight"), True, p("attn.e.bias"))
+        a, g = _scores_fwd(q, k, v, e.view(b, n, n, d), c)
+        del e
     on = K.rows_gemm(g.view(-1, d), p("attn.out_n.weight"), True, p("attn.out_n.bias"))
     x3 = K.add_ln_fwd(x1, on, p("ln3.weight"), p("ln3.bias"))
     x_out = K.mlp_fwd(x3, p("mlp.fc1.weight"), p("mlp.fc1.bias"), p("mlp.fc2.weight"), p("mlp.fc2.bias"),
                       p("ln5.weight"), p("ln5.bias")).view(b, n, d)
     if not edge_out:
         return x_out, None
-    y1 = K.rows_gemm(a.view(-1, d), p("attn.out_e.weight"), True, p("attn.out_e.bias"))
-    del a
-    y3 = K.add_ln_fwd(y2d, y1, p("ln4.weight"), p("ln4.bias"))
-    del y1
+    if not chain:
+        y1 = K.rows_gemm(a.view(-1, d), p("attn.out_e.weight"), True, p("attn.out_e.bias"))
+        del a
+        y3 = K.add_ln_fwd(y2d, y1, p("ln4.weight"), p("ln4.bias"))
+        del y1
     y_out = K.mlp_fwd(y3, p("mlp2.fc1.weight"), p("mlp2.fc1.bias"), p("mlp2.fc2.weight"), p("mlp2.fc2.bias"),
                       p("ln6.weight"), p("ln6.bias")).view(b, n, n, d)
     return x_out, y_out
@@ -178,9 +187,20 @@ def block_backward(x, y, dxo, dyo, params: Sequence[torch.Tensor], heads: int, e
     q = K.rows_gemm(x1, p("attn.q.weight"), True, p("attn.q.bias")).view(b, n, d)
     k = K.rows_gemm(x1, p("attn.k.weight"), True, p("attn.k.bias")).view(b, n, d)
     v = K.rows_gemm(x1, p("attn.v.weight"), True, p("attn.v.bias")).view(b, n, d)
-    e = K.rows_gemm(y2d, p("attn.e.weight"), True, p("attn.e.bias"))
-    a, g, sm_stats = _scores_fwd(q, k, v, e.view(b, n, n, d), c, want_stats=True)
-    a2d = a.view(-1, d)
+    live_edge = edge_out and dyo is not None
+    chain = live_edge and K.attn_chain_available(b, n, d)
+    if chain:
+        # recompute of the edge half in one tcgen05 kernel; side outputs: E (fp32), the scores (bf16: only ever an
+        # operand) and y + out_e(A) (fp32, what LN4's backward needs); g and the softmax statistics from E in fp32
+        y3, a2d, e, z4 = K.attn_edge_fwd(y2d, q, k, p("attn.e.weight"), p("attn.e.bias"), p("attn.out_e.weight"),
+                                         p("attn.out_e.bias"), p("ln4.weight"), p("ln4.bias"), c, want_a16=True, want_e=True,
+                                         want_z=True)
+        a = None
+        _, g, sm_stats = K.attn_scores_fwd(q, k, v, e.view(b, n, n, d), c, want_stats=True, store_a=False)
+    else:
+        e = K.rows_gemm(y2d, p("attn.e.weight"), True, p("attn.e.bias"))
+        a, g, sm_stats = _scores_fwd(q, k, v, e.view(b, n, n, d), c, want_stats=True)
+        a2d = a.view(-1, d)
     g2d = g.view(-1, d)
     on = K.rows_gemm(g2d, p("attn.out_n.weight"), True, p("attn.out_n.bias"))
     x3 = K.add_ln_fwd(x1, on, p("ln3.weight"), p("ln3.bias"))
@@ -192,17 +212,26 @@ def block_backward(x, y, dxo, dyo, params: Sequence[torch.Tensor], heads: int, e
     dg = K.rows_gemm(dz3, p("attn.out_n.weight"), False).view(b, n, d)
     # ---- edge stream: MLP2 + LN6, LN4, out_e
     da = dz4 = None
-    if edge_out and dyo is not None:
-        y1 = K.rows_gemm(a2d, p("attn.out_e.weight"), True, p("attn.out_e.bias"))
-        y3 = K.add_ln_fwd(y2d, y1, p("ln4.weight"), p("ln4.bias"))
-        dy3 = mlp_bwd("mlp2", "ln6", y3, dyo.reshape(-1, d).contiguous())
-        dz4 = ln_bwd("ln4", dy3, y2d, y1)                  # gradient of both y (residual) and out_e(a)
-        del dy3, y1, y3
+    if live_edge:
+        if chain:
+            dy3 = mlp_bwd("mlp2", "ln6", y3, dyo.reshape(-1, d).contiguous())
+            dz4 = ln_bwd("ln4", dy3, z4, None)
+            del dy3, y3, z4
+        else:
+            y1 = K.rows_gemm(a2d, p("attn.out_e.weight"), True, p("attn.out_e.bias"))
+            y3 = K.add_ln_fwd(y2d, y1, p("ln4.weight"), p("ln4.bias"))
+            dy3 = mlp_bwd("mlp2", "ln6", y3, dyo.reshape(-1, d).contiguous())
+            dz4 = ln_bwd("ln4", dy3, y2d, y1)              # gradient of both y (residual) and out_e(a)
+            del dy3, y1, y3
         wgrad("attn.out_e", dz4, a2d)
         da = K.rows_gemm(dz4, p("attn.out_e.weight"), False).view(b, n, n, d)
     # ---- attention: softmax-aggregate, modulation, q/k/v/e projections
-    de, dq, dk, dv = _scores_bwd(dg, da, a, q, k, v, e.view(b, n, n, d), c, sm_stats)
-    del da, a, e
+    if h16 and K.attn_fused_available(n, d):
+        # de is only ever a contraction operand (dWe, dy): bf16 storage in the tensor-core mode
+        de, dq, dk, dv = K.attn_scores_bwd(dg, da, q, k, v, e.view(b, n, n, d), c, sm_stats, de_bf16=True)
+    else:
+        de, dq, dk, dv = _scores_bwd(dg, da, a, q, k, v, e.view(b, n, n, d), c, sm_stats)
+    del da, a, a2d, e
     de2d = de.view(-1, d)
     wgrad("attn.e", de2d, y2d)
     dy = K.rows_gemm(de2d, p("attn.e.weight"), False, resid=dz4)

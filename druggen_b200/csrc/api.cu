@@ -11,6 +11,18 @@ int gemm_tn_tc(const void*, const void*, float*, float*, long long, int, int, in
 
 using namespace dg;
 
+// run-time options: plain process-wide ints, read on the host at launch time and passed to the kernel by value
+static int g_opts[DG_OPT_COUNT] = {/*DG_OPT_L2_PREFETCH*/ 1};
+namespace dg {
+int opt_get(int key) { return key >= 0 && key < DG_OPT_COUNT ? g_opts[key] : 0; }
+}  // namespace dg
+extern "C" int dg_set_option(int key, int value) {
+  if (key < 0 || key >= DG_OPT_COUNT) return fail("dg_set_option: unknown key %d", key);
+  g_opts[key] = value;
+  return 0;
+}
+extern "C" int dg_get_option(int key) { return opt_get(key); }
+
 extern "C" int dg_abi_version(void) { return DG_ABI_VERSION; }
 extern "C" const char* dg_last_error(void) { return err_buf(); }
 

@@ -14,6 +14,7 @@
 // of the key atoms j.  Per query atom the four warps combine their softmax partials through shared
 // memory; dk_j / dv_j accumulators are exclusive to the warp that owns j (shared memory, no atomics
 // inside the loop) and are flushed to global with one atomicAdd per element per CTA.
+#include <cuda_bf16.h>
 #include "common.cuh"
 #include "../../include/druggen_b200.h"
 
@@ -21,6 +22,10 @@ namespace dg {
 
 constexpr int kJU = 4;   // key atoms per load batch: 4 rows x (e, da) x 16 B in flight per lane
 
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
 __device__ __forceinline__ float4 f4s(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
 
 // one channel of the online-softmax update with `n` new scores
@@ -52,14 +57,18 @@ __device__ __forceinline__ void combine4(const float* pm, const float* ps, const
   g = A * inv;
 }
 
-template <bool kBwd>
+// kMode 0: forward from e (a_out optional);  1: backward;  2: forward from the bf16 scores a16 that the fused
+// tcgen05 edge chain (dg_attn_edge_fwd) spilled -- `e` then points at bf16 [B,N,N,128] and nothing is recomputed.
+template <int kMode>
 __global__ void __launch_bounds__(128, 4)
 attn_scores_kernel(const float* __restrict__ dg, const float* __restrict__ da_in, const float* __restrict__ q,
                    const float* __restrict__ k, const float* __restrict__ v, const float* __restrict__ e, float c,
                    float* __restrict__ a_out, float* __restrict__ g_out, float* __restrict__ de, float* __restrict__ dq,
                    float* __restrict__ dk, float* __restrict__ dv, float* __restrict__ stat_m, float* __restrict__ stat_inv,
-                   const float* __restrict__ g_in, int N, int irows) {
+                   const float* __restrict__ g_in, int N, int irows, int prefetch, int de_bf16) {
   constexpr int D = 128;
+  constexpr bool kBwd = kMode == 1;
+  const uint16_t* a16 = reinterpret_cast<const uint16_t*>(e);
   extern __shared__ __align__(16) float sm[];
   // forward : red = [2 parity][3 (m,s,acc)][4 warps][128]   (one barrier per query atom)
   // backward: red = [3 (m,s,acc)][4 warps][128] + [4 warps][128] for the dq partials (three barriers per query atom),
@@ -83,6 +92,12 @@ attn_scores_kernel(const float* __restrict__ dg, const float* __restrict__ da_in
     const long long bi = ((long long)b * N + i) * D + ch;
     const float4 cq = f4s(ld4(q + bi), c);
     const long long base = (((long long)b * N + i) * N) * D + ch;
+    if (prefetch && threadIdx.x == 0 && i + 2 < i1) {     // the rows of query atom i+2 -> L2 (TMA engine; contiguous N rows)
+      const long long pb = (((long long)b * N + i + 2) * N) * D;
+      if (kMode == 2) bulk_prefetch_l2(a16 + pb, (long long)N * D * 2);
+      else bulk_prefetch_l2(e + pb, (long long)N * D * 4);
+      if (kBwd && da_in) bulk_prefetch_l2(da_in + pb, (long long)N * D * 4);
+    }
     float* rd = kBwd ? red : red + ((i - i0) & 1) * 3 * 4 * D;
     float4 M, inv, g;
     const bool have_stats = kBwd && stat_m != nullptr;
@@ -94,6 +109,19 @@ attn_scores_kernel(const float* __restrict__ dg, const float* __restrict__ da_in
     for (int j = jlo; j < jhi; j += kJU) {
       const int n = min(kJU, jhi - j);
       float4 ev[kJU], av[kJU], vv[kJU];
+      if (kMode == 2) {
+        uint2 raw[kJU];
+#pragma unroll
+        for (int u = 0; u < kJU; ++u)
+          if (u < n) raw[u] = *reinterpret_cast<const uint2*>(a16 + base + (long long)(j + u) * D);
+#pragma unroll
+        for (int u = 0; u < kJU; ++u)
+          if (u < n) {
+            vv[u] = ld4(vb + (j + u) * D);
+            av[u] = make_float4(__uint_as_float(raw[u].x << 16), __uint_as_float(raw[u].x & 0xFFFF0000u),
+                                __uint_as_float(raw[u].y << 16), __uint_as_float(raw[u].y & 0xFFFF0000u));
+          }
+      } else {
 #pragma unroll
       for (int u = 0; u < kJU; ++u)
         if (u < n) ev[u] = ld4(e + base + (long long)(j + u) * D);
@@ -104,8 +132,9 @@ attn_scores_kernel(const float* __restrict__ dg, const float* __restrict__ da_in
           vv[u] = ld4(vb + (j + u) * D);
           av[u] = make_float4(cq.x * kj.x * (ev[u].x * ev[u].x + ev[u].x), cq.y * kj.y * (ev[u].y * ev[u].y + ev[u].y),
                               cq.z * kj.z * (ev[u].z * ev[u].z + ev[u].z), cq.w * kj.w * (ev[u].w * ev[u].w + ev[u].w));
-          if (!kBwd) st4(a_out + base + (long long)(j + u) * D, av[u]);
+          if (kMode == 0 && a_out != nullptr) st4(a_out + base + (long long)(j + u) * D, av[u]);
         }
+      }
       DG_ONLINE(x) DG_ONLINE(y) DG_ONLINE(z) DG_ONLINE(w)
     }
     st4(rd + (0 * 4 + w) * D + ch, m);
@@ -153,7 +182,11 @@ attn_scores_kernel(const float* __restrict__ dg, const float* __restrict__ da_in
   }
           DG_GRAD(x) DG_GRAD(y) DG_GRAD(z) DG_GRAD(w)
 #undef DG_GRAD
-          st4(de + base + (long long)(j + u) * D, o);
+          if (de_bf16)      // de is only ever a contraction operand (dWe, dy): bf16 storage loses nothing in the tensor-core mode
+            *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(de) + base + (long long)(j + u) * D) =
+                make_uint2(pack2_bf16(o.x, o.y), pack2_bf16(o.z, o.w));
+          else
+            st4(de + base + (long long)(j + u) * D, o);
           float4 ak = ld4(sdk + (j + u) * D + ch), avv = ld4(sdv + (j + u) * D + ch);
           st4(sdk + (j + u) * D + ch, make_float4(ak.x + gk.x, ak.y + gk.y, ak.z + gk.z, ak.w + gk.w));
           st4(sdv + (j + u) * D + ch, make_float4(avv.x + gv.x, avv.y + gv.y, avv.z + gv.z, avv.w + gv.w));
@@ -208,24 +241,39 @@ extern "C" int dg_attn_scores_fwd(const float* q, const float* k, const float* v
   const int irows = attn_irows(B, N, 8);
   dim3 grid((N + irows - 1) / irows, B);
   if ((stat_m == nullptr) != (stat_inv == nullptr)) return fail("dg_attn_scores_fwd: pass both statistics buffers or neither");
-  attn_scores_kernel<false><<<grid, 128, smem, (cudaStream_t)stream>>>(nullptr, nullptr, q, k, v, e, c, a, g, nullptr, nullptr,
-                                                                        nullptr, nullptr, stat_m, stat_inv, nullptr, N, irows);
+  attn_scores_kernel<0><<<grid, 128, smem, (cudaStream_t)stream>>>(nullptr, nullptr, q, k, v, e, c, a, g, nullptr, nullptr,
+                                                                    nullptr, nullptr, stat_m, stat_inv, nullptr, N, irows,
+                                                                    opt_get(DG_OPT_L2_PREFETCH), 0);
   return check_launch("dg_attn_scores_fwd");
+}
+
+extern "C" int dg_softmax_agg16_fwd(const void* a_bf16, const float* v, float* g, float* stat_m, float* stat_inv, int B, int N,
+                                    int D, void* stream) {
+  if (attn_ok(B, N, D)) return 1;
+  const size_t smem = (size_t)24 * D * 4;
+  const int irows = attn_irows(B, N, 8);
+  dim3 grid((N + irows - 1) / irows, B);
+  if ((stat_m == nullptr) != (stat_inv == nullptr)) return fail("dg_softmax_agg16_fwd: pass both statistics buffers or neither");
+  attn_scores_kernel<2><<<grid, 128, smem, (cudaStream_t)stream>>>(nullptr, nullptr, v, v, v, (const float*)a_bf16, 1.f, nullptr, g,
+                                                                    nullptr, nullptr, nullptr, nullptr, stat_m, stat_inv, nullptr, N,
+                                                                    irows, opt_get(DG_OPT_L2_PREFETCH), 0);
+  return check_launch("dg_softmax_agg16_fwd");
 }
 
 extern "C" int dg_attn_scores_bwd(const float* dg_, const float* da_in, const float* q, const float* k, const float* v,
                                   const float* e, float c, const float* stat_m, const float* stat_inv, const float* g,
-                                  float* de, float* dq, float* dk, float* dv, int B, int N, int D, void* stream) {
+                                  void* de, float* dq, float* dk, float* dv, int B, int N, int D, int de_bf16, void* stream) {
   if (attn_ok(B, N, D)) return 1;
   const size_t smem = (size_t)(16 + 2 * N) * D * 4;
   if (smem > 48 * 1024) {
-    cudaError_t er = cudaFuncSetAttribute(attn_scores_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t er = cudaFuncSetAttribute(attn_scores_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (er != cudaSuccess) return fail("cudaFuncSetAttribute: %s", cudaGetErrorString(er));
   }
   const int irows = attn_irows(B, N, 4);
   dim3 grid((N + irows - 1) / irows, B);
   if (stat_m != nullptr && (stat_inv == nullptr || g == nullptr)) return fail("dg_attn_scores_bwd: statistics need stat_inv and g too");
-  attn_scores_kernel<true><<<grid, 128, smem, (cudaStream_t)stream>>>(dg_, da_in, q, k, v, e, c, nullptr, nullptr, de, dq, dk, dv,
-                                                                       const_cast<float*>(stat_m), const_cast<float*>(stat_inv), g, N, irows);
+  attn_scores_kernel<1><<<grid, 128, smem, (cudaStream_t)stream>>>(dg_, da_in, q, k, v, e, c, nullptr, nullptr, (float*)de, dq, dk, dv,
+                                                                    const_cast<float*>(stat_m), const_cast<float*>(stat_inv), g, N, irows,
+                                                                    opt_get(DG_OPT_L2_PREFETCH), de_bf16);
   return check_launch("dg_attn_scores_bwd");
 }

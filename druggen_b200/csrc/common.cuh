@@ -35,7 +35,16 @@ inline int sm_count() {
   return n;
 }
 
+// ---- run-time options (dg_set_option) --------------------------------------------------------
+int opt_get(int key);   // api.cu
+
 // ---- device helpers --------------------------------------------------------------------------
+// L2 prefetch of a contiguous global range by the TMA engine (UBLKPF.L2: no registers, no shared memory, the
+// issuing thread does not wait).  `src` 16-byte aligned, `bytes` a multiple of 16.  Used one or two tiles ahead of
+// the register-staged loaders so that their loads see L2 latency instead of loaded HBM latency.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, long long bytes) {
+  if (bytes > 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)bytes) : "memory");
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -6,6 +6,10 @@
 //          through z:  out = dz [R,128] fp32,  spill = h [R,H] bf16,  dgamma/dbeta += column sums
 //   BWD_B  dh = (dz . W2) * (h > 0)   (spilled as bf16 for the weight-gradient pass),
 //          out = dx = dz + dh . W1
+//   ATTN   the edge half of the attention (layers.py:116,123-127 + the residual and LayerNorm of :188/:190):
+//          E = y . We^T + be;  A = c q_i k_j (E^2 + E);  out = LN4( y + A . Woe^T + boe ) -- one hidden chunk (H = 128),
+//          "fc1" = We with the modulation as its epilogue, "fc2" = Woe.  Optional side outputs: A as bf16 (operand of the
+//          softmax-aggregate and of dWoe), E fp32 and the pre-LayerNorm sum fp32 (for the backward).
 //
 // All three are "GEMM1 per 128-wide hidden chunk -> per-row epilogue -> bf16 operand block in smem -> GEMM2
 // accumulating over chunks -> per-row final epilogue": the 128 x H intermediate never round-trips HBM as
@@ -28,7 +32,7 @@ constexpr int kMlpThreads = 448;
 constexpr int kWStage = 2 * kBlkBytes;   // one packed weight stage: [2 kb][128 rows][128 B] = 32 KB
 constexpr int kStgPitch = 20;            // epilogue transpose: 32 rows x 16 words per warp, pitch 20 words
 
-enum { kFwd = 0, kBwdA = 1, kBwdB = 2 };
+enum { kFwd = 0, kBwdA = 1, kBwdB = 2, kAttn = 3 };
 
 struct MlpArgs {
   const float* x;          // FWD/BWD_A: block input [R,128];  BWD_B: dz [R,128]
@@ -46,6 +50,14 @@ struct MlpArgs {
   long long R;
   int HC;
   float eps;
+  // ---- ATTN only
+  const float* q;          // [B*N,128]
+  const float* k;          // [B*N,128]
+  float* e_out;            // optional E [R,128] fp32
+  float* z_out;            // optional y + out_e(A) [R,128] fp32 (input of LN4)
+  int natoms;              // N: edge row r = ((b N + i) N + j)
+  float cscale;            // 1 / sqrt(d_k)
+  int prefetch;            // DG_OPT_L2_PREFETCH
 };
 
 // ---- weight pre-pack: fp32 nn.Linear weights -> bf16 swizzled operand stages in a workspace ------
@@ -178,7 +190,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
     for (int i = tid; i < 128; i += kMlpThreads) {
       sB2[i] = A.b2[i];
       sG[i] = A.gamma[i];
-      sBe[i] = kMode == kFwd ? A.beta[i] : 0.f;
+      sBe[i] = (kMode == kFwd || kMode == kAttn) ? A.beta[i] : 0.f;
     }
   }
   tc_fence_before();
@@ -192,6 +204,18 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
     for (long long ti = 0; ti < my_tiles; ++ti) {
       const long long row0 = (blockIdx.x + ti * gridDim.x) * 128;
       const int xs = ti & 1;
+      if (A.prefetch && (lt == 0 || lt == 32)) {
+        // TMA-engine L2 prefetch of whole (contiguous) row tiles ahead of the register-staged loads:
+        // thread 0: the input tiles ti+1, ti+2;  thread 32: what the epilogue gathers for tile ti+1 (dout / bf16 gate)
+        for (long long tp = ti + 1; tp <= ti + 2; ++tp) {
+          if (tp >= my_tiles || (tp == ti + 1 && ti != 0 && lt == 0) || (tp == ti + 2 && lt == 32)) continue;
+          const long long prow0 = (blockIdx.x + tp * gridDim.x) * 128;
+          const long long prows = R - prow0 < 128 ? R - prow0 : 128;
+          if (lt == 0) bulk_prefetch_l2(x + prow0 * 128, prows * 512);
+          else if (kMode == kBwdA) bulk_prefetch_l2(A.dout + prow0 * 128, prows * 512);
+          else if (kMode == kBwdB) bulk_prefetch_l2(A.gate + prow0 * H, prows * H * 2);
+        }
+      }
       mbar_wait(&x_empty[xs], ((ti >> 1) & 1) ^ 1);
 #pragma unroll 1
       for (int kb = 0; kb < 2; ++kb) {
@@ -322,6 +346,33 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
             v[2 * i] = (short)(bits & 0xFFFF) > 0 ? v[2 * i] : 0.f;
             v[2 * i + 1] = (short)(bits >> 16) > 0 ? v[2 * i + 1] : 0.f;
           }
+        } else if (kMode == kAttn) {
+          // E = acc + be;  A = ((q_i k_j) c) (E + 1) E   (layers.py:116,123-125);  this thread's row r = ((b N + i) N + j)
+          const float* bb = sB1 + hf * 64;
+#pragma unroll
+          for (int i = 0; i < 64; i += 4) {
+            const float4 b4 = ld4(bb + i);
+            v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+          }
+          if (A.e_out != nullptr) {
+#pragma unroll
+            for (int g16 = 0; g16 < 4; ++g16) scatter_rows16(A.e_out, wrow0, R, 128, hf * 64 + g16 * 16, stg, lane, v + g16 * 16);
+          }
+          long long r = wrow0 + lane;
+          if (r >= R) r = R - 1;
+          const long long bi = r / A.natoms;
+          const long long bj = (bi / A.natoms) * A.natoms + (r - bi * A.natoms);
+          const float* qr = A.q + bi * 128 + hf * 64;      // q_i: shared by the ~N consecutive rows of (b, i) -> L1 broadcast
+          const float* kr = A.k + bj * 128 + hf * 64;      // k_j: N rows of molecule b, L1/L2 resident
+          const float cs = A.cscale;
+#pragma unroll
+          for (int i = 0; i < 64; i += 4) {
+            const float4 q4 = __ldg(reinterpret_cast<const float4*>(qr + i)), k4 = __ldg(reinterpret_cast<const float4*>(kr + i));
+            v[i] = q4.x * k4.x * cs * fmaf(v[i], v[i], v[i]);
+            v[i + 1] = q4.y * k4.y * cs * fmaf(v[i + 1], v[i + 1], v[i + 1]);
+            v[i + 2] = q4.z * k4.z * cs * fmaf(v[i + 2], v[i + 2], v[i + 2]);
+            v[i + 3] = q4.w * k4.w * cs * fmaf(v[i + 3], v[i + 3], v[i + 3]);
+          }
         } else {
           const float* bb = sB1 + c * 128 + hf * 64;
 #pragma unroll
@@ -339,7 +390,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
         __syncwarp();
         if (lane == 0) mbar_arrive(&hb_full[hs]);
         ++hcount;
-        if (kMode != kFwd) {                                          // spill the chunk as bf16 for the weight-gradient pass
+        if (kMode == kBwdA || kMode == kBwdB || (kMode == kAttn && A.spill != nullptr)) {   // spill the chunk as bf16 (weight-gradient pass / softmax)
           float pk[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) pk[i] = __uint_as_float(pack_bf16(v[2 * i], v[2 * i + 1]));
@@ -384,7 +435,11 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
       const float mean = (s1a + s1b + other.x) * (1.f / 128.f);
       const float rstd = rsqrtf(fmaxf((s2a + s2b + other.y) * (1.f / 128.f) - mean * mean, 0.f) + A.eps);
       const float* gg = sG + hf * 64;
-      if (kMode == kFwd) {
+      if (kMode == kAttn && A.z_out != nullptr) {                     // pre-LayerNorm sum, for the LayerNorm backward
+#pragma unroll
+        for (int g16 = 0; g16 < 4; ++g16) scatter_rows16(A.z_out, wrow0, R, 128, hf * 64 + g16 * 16, stg, lane, a + g16 * 16);
+      }
+      if (kMode == kFwd || kMode == kAttn) {
         const float* be = sBe + hf * 64;
 #pragma unroll
         for (int i = 0; i < 64; i += 4) {
@@ -474,7 +529,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
 }
 
 template <int kMode>
-static int launch_chain(const MlpArgs& a, cudaStream_t s) {
+static int launch_chain(const MlpArgs& a, cudaStream_t s) {   // (one `configured` flag per instantiation)
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(mlp_chain_tc_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpSmem::total + 1024);
@@ -483,7 +538,9 @@ static int launch_chain(const MlpArgs& a, cudaStream_t s) {
   }
   long long tiles = (a.R + 127) / 128;
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  mlp_chain_tc_kernel<kMode><<<grid, kMlpThreads, MlpSmem::total + 1024, s>>>(a);
+  MlpArgs b = a;
+  b.prefetch = opt_get(DG_OPT_L2_PREFETCH);
+  mlp_chain_tc_kernel<kMode><<<grid, kMlpThreads, MlpSmem::total + 1024, s>>>(b);
   return check_launch("dg_mlp_chain");
 }
 
@@ -529,4 +586,18 @@ extern "C" int dg_mlp_bwd_dgrad(const float* dz, const void* h_bf16, const float
   tc::MlpArgs a{dz, (const uint8_t*)workspace, nullptr, nullptr, nullptr, nullptr, nullptr, dx, (uint16_t*)dh_bf16,
                 (const uint16_t*)h_bf16, nullptr, nullptr, R, H / 128, 0.f};
   return tc::launch_chain<tc::kBwdB>(a, s);
+}
+
+extern "C" int dg_attn_edge_fwd(const float* y, const float* q, const float* k, const float* we, const float* be,
+                                const float* woe, const float* boe, const float* gamma, const float* beta, float c,
+                                float* out, void* a_bf16, float* e_out, float* z_out, int B, int N, int D, float eps,
+                                void* workspace, long long workspace_bytes, void* stream) {
+  if (B <= 0 || N <= 0) return fail("dg_attn_edge_fwd: bad shape B=%d N=%d", B, N);
+  const long long R = (long long)B * N * N;
+  if (mlp_check("dg_attn_edge_fwd", R, D, 128, workspace, workspace_bytes)) return 1;
+  cudaStream_t s = (cudaStream_t)stream;
+  tc::mlp_pack_weights_kernel<<<48, 256, 0, s>>>(we, woe, (uint8_t*)workspace, 128, 0);
+  tc::MlpArgs a{y, (const uint8_t*)workspace, be, boe, gamma, beta, nullptr, out, (uint16_t*)a_bf16, nullptr, nullptr, nullptr, R, 1, eps,
+                q, k, e_out, z_out, N, c, 0};
+  return tc::launch_chain<tc::kAttn>(a, s);
 }

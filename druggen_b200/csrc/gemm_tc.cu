@@ -45,7 +45,8 @@ __host__ __device__ inline RowsSmem rows_smem(int K, int N) {
 __global__ void __launch_bounds__(kThreads, 1)
 rows_gemm_tc_kernel(const float* __restrict__ a, const float* __restrict__ w, int w_is_nk,
                     const float* __restrict__ bias, int relu, const float* __restrict__ gate,
-                    const float* __restrict__ resid, float* __restrict__ out, long long R, int K, int N, int flags) {
+                    const float* __restrict__ resid, float* __restrict__ out, long long R, int K, int N, int flags,
+                    int prefetch) {
   const uint16_t* a16 = reinterpret_cast<const uint16_t*>(a);        // bf16 views (flags select which are live)
   const uint16_t* gate16 = reinterpret_cast<const uint16_t*>(gate);
   uint16_t* out16 = reinterpret_cast<uint16_t*>(out);
@@ -99,6 +100,22 @@ rows_gemm_tc_kernel(const float* __restrict__ a, const float* __restrict__ w, in
     uint32_t chunk = 0;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const long long row0 = tile * 128;
+      if (prefetch && lt == 0) {
+        // TMA-engine L2 prefetch of whole contiguous row tiles: group 0 -> the operand rows two tiles ahead,
+        // group 1 -> what the epilogue reads (resid / gate) one tile ahead
+        const long long first = (tile == (long long)blockIdx.x) ? 1 : (grp == 0 ? 2 : 1), last = grp == 0 ? 2 : 1;
+        for (long long ahead = first; ahead <= last; ++ahead) {
+          const long long prow0 = (tile + ahead * gridDim.x) * 128;
+          if (prow0 >= R) break;
+          const long long prows = R - prow0 < 128 ? R - prow0 : 128;
+          if (grp == 0) {
+            bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(a) + prow0 * K * ((flags & DG_A_BF16) ? 2 : 4), prows * K * ((flags & DG_A_BF16) ? 2 : 4));
+          } else {
+            if (resid) bulk_prefetch_l2(resid + prow0 * N, prows * N * 4);
+            if (gate) bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(gate) + prow0 * N * ((flags & DG_GATE_BF16) ? 2 : 4), prows * N * ((flags & DG_GATE_BF16) ? 2 : 4));
+          }
+        }
+      }
       for (int kb = 0; kb < KB; ++kb, ++chunk) {
         if ((int)(chunk & 1) != grp) continue;
         const int st = chunk % kRingA;
@@ -299,7 +316,8 @@ constexpr int kTnBlk = kTnRows * 128;     // [64 rows][64 ch] block, bytes
 
 __global__ void __launch_bounds__(kTnThreads, 1)
 gemm_tn_tc_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
-                  float* __restrict__ colsum_a, long long R, int M, int N, long long tiles_per_cta, int stages, int flags) {
+                  float* __restrict__ colsum_a, long long R, int M, int N, long long tiles_per_cta, int stages, int flags,
+                  int prefetch) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nblk = (M + N) / 64;                       // operand blocks per stage: a's first, then b's
@@ -340,6 +358,14 @@ gemm_tn_tc_kernel(const float* __restrict__ a, const float* __restrict__ b, floa
       for (int e = 0; e < 8; ++e) cs[i][e] = 0.f;
     for (long long tile = t0; tile < t1; ++tile, ++it_) {
       if ((int)(it_ & 1) != grp) continue;
+      if (prefetch && lt == 0) {        // L2 prefetch (TMA engine) of this group's tile after next (contiguous a / b rows)
+        const long long p0 = (tile + (it_ < 2 ? 1 : 4)) * kTnRows, p1 = (tile + 5 < t1 ? tile + 5 : t1) * kTnRows;
+        const long long pe = p1 < R ? p1 : R;
+        if (pe > p0) {
+          bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(a) + p0 * M * ((flags & DG_A_BF16) ? 2 : 4), (pe - p0) * M * ((flags & DG_A_BF16) ? 2 : 4));
+          bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(b) + p0 * N * ((flags & DG_OUT_BF16) ? 2 : 4), (pe - p0) * N * ((flags & DG_OUT_BF16) ? 2 : 4));
+        }
+      }
       const int st = it_ % stages;
       mbar_wait(&empty[st], ((it_ / stages) & 1) ^ 1);
       uint8_t* base = sOp + st * stage_bytes;
@@ -533,7 +559,8 @@ int rows_gemm_tc(const void* a_, const float* w, int w_is_nk, const float* bias,
   }
   long long tiles = (R + 127) / 128;
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  tc::rows_gemm_tc_kernel<<<grid, tc::kThreads, smem, s>>>(a, w, w_is_nk, bias, relu, gate, resid, out, R, K, N, flags);
+  tc::rows_gemm_tc_kernel<<<grid, tc::kThreads, smem, s>>>(a, w, w_is_nk, bias, relu, gate, resid, out, R, K, N, flags,
+                                                           opt_get(DG_OPT_L2_PREFETCH));
   return check_launch("dg_rows_gemm(bf16)");
 }
 
@@ -561,7 +588,8 @@ int gemm_tn_tc(const void* a_, const void* b_, float* out, float* colsum_a, long
   long long ctas = tiles < sm_count() ? tiles : sm_count();
   long long per = (tiles + ctas - 1) / ctas;
   ctas = (tiles + per - 1) / per;
-  tc::gemm_tn_tc_kernel<<<(int)ctas, tc::kTnThreads, smem, s>>>(a, b, out, colsum_a, R, M, N, per, stages, flags);
+  tc::gemm_tn_tc_kernel<<<(int)ctas, tc::kTnThreads, smem, s>>>(a, b, out, colsum_a, R, M, N, per, stages, flags,
+                                                                opt_get(DG_OPT_L2_PREFETCH));
   return check_launch("dg_gemm_tn(bf16)");
 }
 

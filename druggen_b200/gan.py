@@ -9,6 +9,7 @@ after ``g_loss.backward()`` (parallel.py).
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Optional
 
 import torch
@@ -57,12 +58,30 @@ def synthetic_molecules(batch: int, n: int, m_dim: int = 13, b_dim: int = 5, see
     return a.to(device), x.to(device)
 
 
+@contextlib.contextmanager
+def frozen(module):
+    """``requires_grad_(False)`` on a module's parameters for the duration of the block."""
+    ps = [p for p in module.parameters() if p.requires_grad]
+    for p in ps:
+        p.requires_grad_(False)
+    try:
+        yield
+    finally:
+        for p in ps:
+            p.requires_grad_(True)
+
+
 class GANTrainer:
     """Generator + Discriminator + two AdamW optimizers, stepped as train.py:351-384."""
 
     def __init__(self, G, D, lr_g: float = 1e-5, lr_d: float = 1e-5, betas=(0.9, 0.999), lambda_gp: float = 10.0,
-                 process_group: Optional[object] = None):
+                 process_group: Optional[object] = None, skip_dead_d_grads: bool = True):
         self.G, self.D, self.lambda_gp = G, D, lambda_gp
+        # train.py:371-377: g_loss.backward() also fills D's .grad, which nothing consumes (reset_grad, train.py:352,
+        # zeroes it before the next D step; d_optimizer is not stepped).  With skip_dead_d_grads the Discriminator is
+        # frozen while the G-step graph is built: the gradient still flows THROUGH D to G (dgrad), D's weight-gradient
+        # contractions are not launched.  G's update is bit-identical either way (SURVEY 8d "necessary FLOPs").
+        self.skip_dead_d_grads = skip_dead_d_grads
         self.g_optimizer = torch.optim.AdamW(G.parameters(), lr_g, betas)      # train.py:213
         self.d_optimizer = torch.optim.AdamW(D.parameters(), lr_d, betas)      # train.py:214
         self.pg = process_group
@@ -84,7 +103,8 @@ class GANTrainer:
         self.reducer_d.all_reduce_mean()
         self.d_optimizer.step()
         self.reset_grad()
-        g_loss = generator_loss(self.G, self.D, mol_adj, mol_annot, bsz)[0]
+        with (frozen(self.D) if self.skip_dead_d_grads else contextlib.nullcontext()):
+            g_loss = generator_loss(self.G, self.D, mol_adj, mol_annot, bsz)[0]
         g_val = g_loss.item()
         g_loss.backward()
         self.reducer_g.all_reduce_mean()

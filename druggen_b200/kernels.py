@@ -273,23 +273,64 @@ def attn_fused_available(n: int, d: int) -> bool:
     return d == 128 and n >= 4
 
 
-def attn_scores_fwd(q, k, v, e, c: float, want_stats: bool = False):
+def attn_scores_fwd(q, k, v, e, c: float, want_stats: bool = False, store_a: bool = True):
     """-> (a, g[, stats]): modulated scores (layers.py:123-125) and softmax-aggregate (layers.py:130-134), e read once.
-    ``want_stats`` also returns (max, 1/sum, g) per (b, i, channel) for ``attn_scores_bwd``."""
+    ``want_stats`` also returns (max, 1/sum, g) per (b, i, channel) for ``attn_scores_bwd``.
+    ``store_a=False``: the scores are not written (a is None) -- only g and the statistics are wanted."""
     _chk(q, k, v, e)
-    a, g = torch.empty_like(e), torch.empty_like(q)
+    a, g = (torch.empty_like(e) if store_a else None), torch.empty_like(q)
     stats = (torch.empty_like(q), torch.empty_like(q)) if want_stats else None
     if e.numel():
         _be().attn_scores_fwd(q, k, v, e, c, a, g, stats)
     return (a, g, stats + (g,)) if want_stats else (a, g)
 
 
-def attn_scores_bwd(dg, da_in, q, k, v, e, c: float, stats=None):
+def attn_scores_bwd(dg, da_in, q, k, v, e, c: float, stats=None, de_bf16: bool = False):
     """-> (de, dq, dk, dv) from dg (softmax path) and da_in (out_e path; may be None).  ``stats`` from the forward
-    skips the statistics sweep."""
+    skips the statistics sweep.  ``de_bf16``: de is stored as bf16 (it is only ever a contraction operand)."""
     _chk(dg, da_in, q, k, v, e)
-    de, dq = torch.empty_like(e), torch.empty_like(q)
+    de, dq = torch.empty_like(e, dtype=torch.bfloat16 if de_bf16 else e.dtype), torch.empty_like(q)
     dk, dv = torch.zeros_like(k), torch.zeros_like(v)
     if e.numel():
         _be().attn_scores_bwd(dg, da_in, q, k, v, e, c, de, dq, dk, dv, stats)
     return de, dq, dk, dv
+
+
+# ----------------------------------------------------------------------------- fused tcgen05 edge-attention chain
+def attn_chain_available(b: int, n: int, d: int) -> bool:
+    """E-projection -> modulation -> out_e projection -> residual -> LN4 as one tcgen05 kernel (throughput mode)."""
+    return _precision == "bf16" and d == 128 and n >= 4 and b <= 65535 and os.environ.get("DRUGGEN_B200_ATTN_CHAIN", "1") != "0"
+
+
+def attn_edge_fwd(y, q, k, we, be, woe, boe, gamma, beta, c: float, want_a16: bool = True, want_e: bool = False,
+                  want_z: bool = False, eps: float = 1e-5):
+    """y:[B*N*N,128], q,k:[B,N,128] -> (y3 = LN4(y + out_e(A)), a16 | None, e | None, z | None)   (layers.py:116,123-127,188,190).
+    a16: the scores A = c q_i k_j (E^2+E) as bf16; e: E = y We^T + be fp32; z: y + out_e(A) fp32 (input of LN4)."""
+    _chk(y, q, k, we, be, woe, boe, gamma, beta)
+    b, n, d = q.shape
+    assert y.shape == (b * n * n, d), (y.shape, q.shape)
+    out = torch.empty_like(y)
+    a16 = torch.empty_like(y, dtype=torch.bfloat16) if want_a16 else None
+    e = torch.empty_like(y) if want_e else None
+    z = torch.empty_like(y) if want_z else None
+    if y.numel():
+        ws = torch.empty(2 * 32768, dtype=torch.uint8, device=y.device)
+        _be().attn_edge_fwd(y, q, k, we, be, woe, boe, gamma, beta, c, out, a16, e, z, eps, ws)
+    return out, a16, e, z
+
+
+def softmax_agg16_fwd(a16, v, want_stats: bool = False):
+    """g[b,i,:] = sum_j softmax_j(a16[b,i,j,:]) v[b,j,:] from bf16 scores (fp32 arithmetic) -> g | (g, (max, 1/sum, g))."""
+    _chk(v)
+    _chk(a16, bf16_ok=True)
+    g = torch.empty_like(v)
+    stats = (torch.empty_like(v), torch.empty_like(v)) if want_stats else None
+    if a16.numel():
+        _be().softmax_agg16_fwd(a16, v, g, stats)
+    return (g, stats + (g,)) if want_stats else g
+
+
+def set_option(key: int, value: int) -> None:
+    """Process-wide tuning switches of the library (``_lib.OPT_*``)."""
+    if _test_backend is None:
+        _lib.load().dg_set_option(key, value)

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DG_ABI_VERSION 1
+#define DG_ABI_VERSION 2
 #define DG_PREC_FP32 0
 #define DG_PREC_BF16 1
 
@@ -33,6 +33,12 @@ int dg_abi_version(void);
 const char* dg_last_error(void);
 /* 1 when the tcgen05 paths were compiled in and the current device is sm_100. */
 int dg_has_tcgen05(void);
+
+/* Run-time options (process-wide; read at launch time).  Returns 0 / the value. */
+#define DG_OPT_L2_PREFETCH 0 /* 1 (default): loaders issue bulk L2 prefetches (cp.async.bulk.prefetch.L2) ahead of their loads */
+#define DG_OPT_COUNT 1
+int dg_set_option(int key, int value);
+int dg_get_option(int key);
 
 /* ---- dense contractions ------------------------------------------------------------------ */
 /* out[R,N] = epi(a[R,K] . op(w) + bias) + resid;  w is [N,K] when w_is_nk (nn.Linear layout) else [K,N].
@@ -102,7 +108,13 @@ int dg_attn_scores_fwd(const float* q, const float* k, const float* v, const flo
  * forward the statistics sweep is skipped, with NULLs it is redone. */
 int dg_attn_scores_bwd(const float* dg, const float* da_in, const float* q, const float* k, const float* v,
                        const float* e, float c, const float* stat_m, const float* stat_inv, const float* g,
-                       float* de, float* dq, float* dk, float* dv, int B, int N, int D, void* stream);
+                       void* de, float* dq, float* dk, float* dv, int B, int N, int D, int de_bf16, void* stream);
+/* (de_bf16 != 0: de is written as bf16 [B,N,N,D] -- it is only ever a contraction operand (dWe, dy), so in the
+ * tensor-core mode nothing is lost.)
+ * g and the statistics from bf16 scores a[B,N,N,D] (the side output of dg_attn_edge_fwd) -- the forward's
+ * softmax-aggregate (layers.py:130-134) at 256 B per edge row. */
+int dg_softmax_agg16_fwd(const void* a_bf16, const float* v, float* g, float* stat_m, float* stat_inv, int B, int N,
+                         int D, void* stream);
 
 /* ---- fused tcgen05 kernels (bf16 operands, fp32 accumulate / epilogue) ----------------------------- */
 /* out = LN(x + fc2(relu(fc1(x) + b1)) + b2) * gamma + beta   -- the whole residual MLP of one stream in one
@@ -123,6 +135,17 @@ int dg_mlp_bwd_ln(const float* x, const float* dout, const float* w1, const floa
 int dg_mlp_bwd_dgrad(const float* dz, const void* h_bf16, const float* w1, const float* w2, float* dx,
                      void* dh_bf16, long long R, int D, int H, void* workspace, long long workspace_bytes,
                      void* stream);
+
+/* The edge half of the attention block in one tcgen05 kernel (layers.py:116,123-127 + the residual and LayerNorm of
+ * :188/:190):  E = y.We^T + be;  A = c q_i k_j (E^2 + E);  out = LN4(y + A.Woe^T + boe) * gamma + beta.
+ * y,out:[B*N*N,D] fp32 (D == 128), q,k:[B,N,D] fp32.  Optional side outputs (NULL to skip): a_bf16 [B*N*N,D] bf16
+ * (scores: operand of dg_softmax_agg16_fwd and of the out_e weight gradient), e_out [B*N*N,D] fp32 and z_out
+ * [B*N*N,D] fp32 = y + out_e(A), the input of LN4 (both for the backward).  E and A never reach HBM as fp32
+ * unless asked for.  workspace: >= 65536 bytes, 128-byte aligned. */
+int dg_attn_edge_fwd(const float* y, const float* q, const float* k, const float* we, const float* be,
+                     const float* woe, const float* boe, const float* gamma, const float* beta, float c,
+                     float* out, void* a_bf16, float* e_out, float* z_out, int B, int N, int D, float eps,
+                     void* workspace, long long workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

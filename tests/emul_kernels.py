@@ -153,6 +153,8 @@ class EmulBackend:
         self.add_ln_fwd(z, None, gamma, beta, out, eps)
 
     def attn_scores_fwd(self, q, k, v, e, c, a, g, stats=None):
+        if a is None:
+            a = torch.empty_like(e)
         self.modulate_fwd(q, k, e, c, a)
         self.softmax_agg_fwd(a, v, g)
         if stats is not None:
@@ -167,7 +169,12 @@ class EmulBackend:
         self.softmax_agg_bwd(dg, a, v, da, dv)
         if da_in is not None:
             da = da + da_in
-        self.modulate_bwd(da, q, k, e, c, dq, dk, de)
+        if de.dtype != e.dtype:
+            de32 = torch.empty_like(e)
+            self.modulate_bwd(da, q, k, e, c, dq, dk, de32)
+            de.copy_(de32)
+        else:
+            self.modulate_bwd(da, q, k, e, c, dq, dk, de)
 
     def mlp_bwd_ln(self, x, dout, w1, b1, w2, b2, gamma, dz, h16, dgamma, dbeta, eps, workspace):
         h = torch.relu(self._mm(x, w1.t(), "bf16") + b1)
@@ -179,3 +186,26 @@ class EmulBackend:
         dh = self._mm(dz, w2, "bf16") * (h16 > 0).to(dz.dtype)
         dh16.copy_(dh)
         dx.copy_(dz + self._mm(dh16.to(dz.dtype), w1, "bf16"))
+
+    def softmax_agg16_fwd(self, a16, v, g, stats=None):
+        a = a16.to(v.dtype).view(v.shape[0], v.shape[1], v.shape[1], v.shape[2])
+        self.softmax_agg_fwd(a, v, g)
+        if stats is not None:
+            m = a.max(dim=2).values
+            stats[0].copy_(m)
+            stats[1].copy_(1.0 / torch.exp(a - m[:, :, None, :]).sum(2))
+
+    def attn_edge_fwd(self, y, q, k, we, be, woe, boe, gamma, beta, c, out, a16, e_out, z_out, eps, workspace):
+        b, n, d = q.shape
+        e = self._mm(y, we.t(), "bf16") + be
+        a = torch.empty_like(e).view(b, n, n, d)
+        self.modulate_fwd(q, k, e.view(b, n, n, d), c, a)
+        a = a.view(-1, d)
+        if e_out is not None:
+            e_out.copy_(e)
+        if a16 is not None:
+            a16.copy_(a)
+        z = y + self._mm(a, woe.t(), "bf16") + boe
+        if z_out is not None:
+            z_out.copy_(z)
+        self.add_ln_fwd(z, None, gamma, beta, out, eps)

@@ -1,0 +1,174 @@
+"""The fused tcgen05 edge-attention chain (dg_attn_edge_fwd), the bf16-score softmax-aggregate, bf16 `de` storage and
+the L2-prefetch option, each against its plain-torch statement in fp64 on bf16-rounded operands (the tensor-core
+kernels round contraction operands to bf16; everything else is fp32)."""
+import os
+
+import pytest
+import torch
+
+from druggen_b200 import _lib
+from druggen_b200 import kernels as K
+from druggen_b200.block import BLOCK_PARAM_NAMES, encoder_block
+from emul_kernels import EmulBackend
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+EM = EmulBackend()
+
+
+def rnd(dev, *shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed + len(shape) * 1000 + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(dev)
+
+
+def bf(t):
+    return t.to(torch.bfloat16).double()
+
+
+def _ln(z, gamma, beta):
+    mu, var = z.mean(-1, keepdim=True), z.var(-1, unbiased=False, keepdim=True)
+    return (z - mu) / torch.sqrt(var + 1e-5) * gamma.double() + beta.double()
+
+
+@pytest.mark.parametrize("B,N", [(1, 4), (3, 9), (2, 45), (40, 45), (300, 9), (5, 90), (148 * 3 + 1, 8)])
+@pytest.mark.parametrize("side", ["none", "a16", "all"])
+def test_attn_edge_fwd(cuda_dev, B, N, side):
+    D, c = 128, 0.25
+    R = B * N * N
+    y = rnd(cuda_dev, R, D)
+    q, k = rnd(cuda_dev, B, N, D, seed=1), rnd(cuda_dev, B, N, D, seed=2)
+    we, be = rnd(cuda_dev, D, D, seed=3, scale=D ** -0.5), rnd(cuda_dev, D, seed=4, scale=0.1)
+    woe, boe = rnd(cuda_dev, D, D, seed=5, scale=D ** -0.5), rnd(cuda_dev, D, seed=6, scale=0.1)
+    gamma, beta = rnd(cuda_dev, D, seed=7, scale=0.1) + 1.0, rnd(cuda_dev, D, seed=8, scale=0.1)
+    with K.precision("bf16"):
+        out, a16, e, z = K.attn_edge_fwd(y, q, k, we, be, woe, boe, gamma, beta, c, want_a16=side != "none",
+                                         want_e=side == "all", want_z=side == "all")
+    e_ref = bf(y) @ bf(we).t() + be.double()
+    qi = q.double().view(B, N, 1, D)
+    kj = k.double().view(B, 1, N, D)
+    e4 = e_ref.view(B, N, N, D)
+    a_ref = (c * qi * kj * (e4 * e4 + e4)).reshape(R, D)
+    if side == "none":
+        assert a16 is None and e is None and z is None
+        a_op = bf(a_ref.float())
+    else:
+        assert a16.dtype == torch.bfloat16
+        assert rel_l2(a16.double(), bf(a_ref.float())) < 4e-3          # 1-ulp bf16 flips vs the fp64 emulation
+        a_op = a16.double()                                             # the kernel's own operand isolates GEMM2 + LN
+    z_ref = y.double() + a_op @ bf(woe).t() + boe.double()
+    tol = 2e-4 if side != "none" else 3e-3
+    assert rel_l2(out, _ln(z_ref, gamma, beta)) < tol, rel_l2(out, _ln(z_ref, gamma, beta))
+    if side == "all":
+        assert rel_l2(e, e_ref) < 2e-5
+        assert rel_l2(z, z_ref) < 2e-5
+
+
+@pytest.mark.parametrize("B,N", [(1, 4), (3, 9), (2, 45), (300, 9), (5, 90), (40, 45)])
+def test_softmax_agg16(cuda_dev, B, N):
+    D = 128
+    a16 = rnd(cuda_dev, B, N, N, D, seed=3, scale=2.0).to(torch.bfloat16)
+    v = rnd(cuda_dev, B, N, D, seed=2)
+    a = a16.double()
+    p = torch.softmax(a, dim=2)
+    g_ref = (p * v.double().view(B, 1, N, D)).sum(2)
+    g, stats = K.softmax_agg16_fwd(a16.view(-1, D), v, want_stats=True)
+    assert rel_l2(g, g_ref) < 1e-5
+    m = a.max(dim=2).values
+    assert rel_l2(stats[0], m) < 1e-6
+    assert rel_l2(stats[1], 1.0 / torch.exp(a - m[:, :, None, :]).sum(2)) < 1e-5
+    assert rel_l2(K.softmax_agg16_fwd(a16.view(-1, D), v), g_ref) < 1e-5
+
+
+@pytest.mark.parametrize("B,N", [(3, 9), (2, 45), (40, 45)])
+def test_attn_scores_stats_only_and_bf16_de(cuda_dev, B, N):
+    D, c = 128, 0.25
+    q, k, v = rnd(cuda_dev, B, N, D), rnd(cuda_dev, B, N, D, seed=1), rnd(cuda_dev, B, N, D, seed=2)
+    e, dg, da_in = rnd(cuda_dev, B, N, N, D, seed=3), rnd(cuda_dev, B, N, D, seed=4), rnd(cuda_dev, B, N, N, D, seed=5)
+    a, g, stats = K.attn_scores_fwd(q, k, v, e, c, want_stats=True)
+    a2, g2, stats2 = K.attn_scores_fwd(q, k, v, e, c, want_stats=True, store_a=False)
+    assert a2 is None and torch.equal(g, g2) and torch.equal(stats[0], stats2[0]) and torch.equal(stats[1], stats2[1])
+    de, dq, dk, dv = K.attn_scores_bwd(dg, da_in, q, k, v, e, c, stats)
+    de16, dq2, dk2, dv2 = K.attn_scores_bwd(dg, da_in, q, k, v, e, c, stats, de_bf16=True)
+    assert de16.dtype == torch.bfloat16 and torch.equal(de16, de.to(torch.bfloat16))
+    assert torch.equal(dq, dq2) and rel_l2(dk2, dk) < 1e-6 and rel_l2(dv2, dv) < 1e-6
+
+
+def test_l2_prefetch_option_is_numerically_inert(cuda_dev):
+    """DG_OPT_L2_PREFETCH only moves data into L2 early: results with and without it are identical."""
+    R = 128 * 148 * 2 + 77
+    x, dout = rnd(cuda_dev, R, 128), rnd(cuda_dev, R, 128, seed=7)
+    w1, b1 = rnd(cuda_dev, 384, 128, seed=1, scale=128 ** -0.5), rnd(cuda_dev, 384, seed=2, scale=0.1)
+    w2, b2 = rnd(cuda_dev, 128, 384, seed=3, scale=384 ** -0.5), rnd(cuda_dev, 128, seed=4, scale=0.1)
+    gamma, beta = rnd(cuda_dev, 128, seed=5, scale=0.1) + 1.0, rnd(cuda_dev, 128, seed=6, scale=0.1)
+    B, N = 37, 45
+    q, k, v = rnd(cuda_dev, B, N, 128), rnd(cuda_dev, B, N, 128, seed=1), rnd(cuda_dev, B, N, 128, seed=2)
+    e, dg, da_in = rnd(cuda_dev, B, N, N, 128, seed=3), rnd(cuda_dev, B, N, 128, seed=4), rnd(cuda_dev, B, N, N, 128, seed=5)
+
+    def run():
+        with K.precision("bf16"):
+            o = [K.mlp_fwd(x, w1, b1, w2, b2, gamma, beta)]
+            dz, h16, dgam, dbet = K.mlp_bwd_ln(x, dout, w1, b1, w2, b2, gamma)
+            dx, dh16 = K.mlp_bwd_dgrad(dz, h16, w1, w2)
+            o += [dz, h16.float(), dx, dh16.float()]
+            o.append(K.rows_gemm(x, w1, True, b1, relu=True))
+            o.append(K.rows_gemm(x, w2[:, :128].contiguous(), True, None, False, gate=dout, resid=dout))
+            o.append(K.gemm_tn(x, dout))
+            a, g, st = K.attn_scores_fwd(q, k, v, e, 0.25, want_stats=True)
+            o += [a, g] + list(K.attn_scores_bwd(dg, da_in, q, k, v, e, 0.25, st))
+            o += [t.float() for t in K.attn_edge_fwd(e.view(-1, 128), q, k, w1[:128].contiguous(), b1[:128].contiguous(),
+                                                     w2[:, :128].contiguous(), b2, gamma, beta, 0.25, True, True, True)]
+        return o
+    try:
+        K.set_option(_lib.OPT_L2_PREFETCH, 0)
+        off = run()
+        K.set_option(_lib.OPT_L2_PREFETCH, 1)
+        on = run()
+    finally:
+        K.set_option(_lib.OPT_L2_PREFETCH, 1)
+    for i, (a, b) in enumerate(zip(off, on)):
+        assert rel_l2(a, b) < 1e-6, i          # (atomically accumulated outputs differ in summation order only)
+
+
+def _block_params(dev, d=128, r=3, seed=11):
+    g = torch.Generator().manual_seed(seed)
+    shapes = {"weight2": None}
+    out = []
+    for name in BLOCK_PARAM_NAMES:
+        if name.startswith("ln"):
+            t = torch.ones(d) + 0.1 * torch.randn(d, generator=g) if name.endswith("weight") else 0.1 * torch.randn(d, generator=g)
+        elif "fc1" in name:
+            t = torch.randn(r * d, d, generator=g) * d ** -0.5 if name.endswith("weight") else 0.1 * torch.randn(r * d, generator=g)
+        elif "fc2" in name:
+            t = torch.randn(d, r * d, generator=g) * (r * d) ** -0.5 if name.endswith("weight") else 0.1 * torch.randn(d, generator=g)
+        else:
+            t = torch.randn(d, d, generator=g) * d ** -0.5 if name.endswith("weight") else 0.1 * torch.randn(d, generator=g)
+        out.append(t.to(dev))
+    del shapes
+    return out
+
+
+@pytest.mark.parametrize("B,N", [(3, 9), (4, 45)])
+def test_block_chain_vs_unfused_attention(cuda_dev, B, N):
+    """The checkpointed block in the throughput mode with and without the fused edge-attention chain: same function,
+    different rounding points (bf16 scores feed the forward's softmax) -> outputs and all gradients agree to bf16 level."""
+    d, heads = 128, 8
+    params = _block_params(cuda_dev)
+    x0, y0 = rnd(cuda_dev, B, N, d, seed=1), rnd(cuda_dev, B, N, N, d, seed=2)
+    wx, wy = rnd(cuda_dev, B, N, d, seed=3), rnd(cuda_dev, B, N, N, d, seed=4)
+
+    def run(chain):
+        os.environ["DRUGGEN_B200_ATTN_CHAIN"] = "1" if chain else "0"
+        try:
+            with K.precision("bf16"):
+                x, y = x0.clone().requires_grad_(True), y0.clone().requires_grad_(True)
+                pp = [p.detach().clone().requires_grad_(True) for p in params]
+                xo, yo = encoder_block(x, y, pp, heads, True)
+                ((xo * wx).sum() + (yo * wy).sum()).backward()
+                with torch.no_grad():
+                    xn, yn = encoder_block(x0, y0, params, heads, True)
+            return [xo.detach(), yo.detach(), xn, yn, x.grad, y.grad] + [p.grad for p in pp]
+        finally:
+            os.environ.pop("DRUGGEN_B200_ATTN_CHAIN", None)
+    ref, got = run(False), run(True)
+    for i, (a, b) in enumerate(zip(got, ref)):
+        assert rel_l2(a, b) < 2e-2, (i, rel_l2(a, b))

@@ -24,4 +24,4 @@ def test_header_symbols_exported():
     for n in names:
         assert hasattr(lib, n), n
     assert set(names) == set(_lib.SIGNATURES) | set(_lib.INFO_SYMBOLS)
-    assert lib.dg_abi_version() == 1
+    assert lib.dg_abi_version() == _lib.ABI_VERSION

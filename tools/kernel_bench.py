@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--batch", type=int, default=512)
     ap.add_argument("--atoms", type=int, default=45)
     ap.add_argument("--depth", type=int, default=8)
+    ap.add_argument("--prefetch-ab", action="store_true", help="time every kernel with the L2-prefetch option off and on")
     args = ap.parse_args()
     try:
         pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -59,25 +60,65 @@ def main():
         rec.update(extra)
         print(json.dumps(rec), flush=True)
 
+    from druggen_b200 import _lib
+    dout = rn(r, d)
+    w = rn(d, d, sc=d ** -0.5)
+    q, k, v = rn(b, n, d), rn(b, n, d), rn(b, n, d)
+    dgn = rn(b, n, d)
+    x4 = x.view(b, n, n, d)
+
     with dg.precision("bf16"):
-        ms = timeit(lambda: K.mlp_fwd(x, w1, b1, w2, b2, gamma, beta))
-        report("mlp_fwd[fused,H=384]", ms, 2 * r * d * 4, 4.0 * r * d * h)
+        dz, h16, _, _ = K.mlp_bwd_ln(x, dout, w1, b1, w2, b2, gamma)
+        _, a16, _, _ = K.attn_edge_fwd(x, q, k, w, b2, w, b2, gamma, beta, 0.25)
+        _, _, stats = K.attn_scores_fwd(q, k, v, x4, 0.25, want_stats=True, store_a=False)
 
         def unfused():
             hh = K.rows_gemm(x, w1, True, b1, True)
             m = K.rows_gemm(hh, w2, True, b2)
             return K.add_ln_fwd(x, m, gamma, beta)
-        ms = timeit(unfused)
-        report("mlp_fwd[unfused: 2 rows_gemm + add_ln]", ms, 2 * r * d * 4, 4.0 * r * d * h)
-        w = rn(d, d, sc=d ** -0.5)
-        ms = timeit(lambda: K.rows_gemm(x, w, True, b2))
-        report("rows_gemm[K=128,N=128]", ms, 2 * r * d * 4, 2.0 * r * d * d)
-        ms = timeit(lambda: K.gemm_tn(x, x))
-        report("gemm_tn[M=128,N=128]", ms, 2 * r * d * 4, 2.0 * r * d * d)
-        ms = timeit(lambda: K.add_ln_fwd(x, x, gamma, beta))
-        report("add_ln_fwd", ms, 3 * r * d * 4, 0.0)
-        ms = timeit(lambda: K.add_ln_bwd(x, x, x, gamma))
-        report("add_ln_bwd", ms, 4 * r * d * 4, 0.0)
+
+        def unfused_attn_edge():
+            e = K.rows_gemm(x, w, True, b2)
+            a, g = K.attn_scores_fwd(q, k, v, e.view(b, n, n, d), 0.25)
+            y1 = K.rows_gemm(a.view(-1, d), w, True, b2)
+            return K.add_ln_fwd(x, y1, gamma, beta)
+
+        def fused_attn_edge():
+            y3, a16_, _, _ = K.attn_edge_fwd(x, q, k, w, b2, w, b2, gamma, beta, 0.25)
+            return K.softmax_agg16_fwd(a16_, v)
+
+        benches = [
+            ("mlp_fwd[fused,H=384]", lambda: K.mlp_fwd(x, w1, b1, w2, b2, gamma, beta), 2 * r * d * 4, 4.0 * r * d * h),
+            ("mlp_bwd_ln[fused,H=384]", lambda: K.mlp_bwd_ln(x, dout, w1, b1, w2, b2, gamma), r * (3 * d * 4 + h * 2), 4.0 * r * d * h),
+            ("mlp_bwd_dgrad[fused,H=384]", lambda: K.mlp_bwd_dgrad(dz, h16, w1, w2), r * (2 * d * 4 + 2 * h * 2), 4.0 * r * d * h),
+            ("attn_edge_fwd[fused,+a16]", lambda: K.attn_edge_fwd(x, q, k, w, b2, w, b2, gamma, beta, 0.25), r * d * 10, 4.0 * r * d * d),
+            ("attn_edge_fwd[fused,+a16+e+z]", lambda: K.attn_edge_fwd(x, q, k, w, b2, w, b2, gamma, beta, 0.25, True, True, True),
+             r * d * 18, 4.0 * r * d * d),
+            ("softmax_agg16_fwd", lambda: K.softmax_agg16_fwd(a16, v), r * d * 2, 0.0),
+            ("attn_edge forward pair [attn_edge_fwd + softmax_agg16]", fused_attn_edge, r * d * 8, 4.0 * r * d * d),
+            ("attn_edge forward unfused [rows_gemm, attn_scores_fwd, rows_gemm, add_ln]", unfused_attn_edge, r * d * 8, 4.0 * r * d * d),
+            ("attn_scores_fwd[fused]", lambda: K.attn_scores_fwd(q, k, v, x4, 0.25), 2 * r * d * 4, 0.0),
+            ("attn_scores_fwd[stats only]", lambda: K.attn_scores_fwd(q, k, v, x4, 0.25, True, False), r * d * 4, 0.0),
+            ("attn_scores_bwd[fused,stats]", lambda: K.attn_scores_bwd(dgn, dout.view(b, n, n, d), q, k, v, x4, 0.25, stats), 3 * r * d * 4, 0.0),
+            ("attn_scores_bwd[fused,stats,de16]", lambda: K.attn_scores_bwd(dgn, dout.view(b, n, n, d), q, k, v, x4, 0.25, stats, True),
+             r * d * 10, 0.0),
+            ("mlp_fwd[unfused: 2 rows_gemm + add_ln]", unfused, 2 * r * d * 4, 4.0 * r * d * h),
+            ("rows_gemm[K=128,N=128]", lambda: K.rows_gemm(x, w, True, b2), 2 * r * d * 4, 2.0 * r * d * d),
+            ("rows_gemm[K=128,N=128,+resid]", lambda: K.rows_gemm(x, w, True, b2, resid=dout), 3 * r * d * 4, 2.0 * r * d * d),
+            ("rows_gemm[K=128,N=128,a16,+resid]", lambda: K.rows_gemm(a16, w, False, resid=dout), r * d * 10, 2.0 * r * d * d),
+            ("rows_gemm[K=128,N=384,+relu]", lambda: K.rows_gemm(x, w1, True, b1, True), r * (d + h) * 4, 2.0 * r * d * h),
+            ("gemm_tn[M=128,N=128]", lambda: K.gemm_tn(x, dout), 2 * r * d * 4, 2.0 * r * d * d),
+            ("gemm_tn[M=128,N=128,b16]", lambda: K.gemm_tn(x, a16), r * d * 6, 2.0 * r * d * d),
+            ("gemm_tn[M=384,N=128,a16]", lambda: K.gemm_tn(h16, x), r * (h * 2 + d * 4), 2.0 * r * d * h),
+            ("add_ln_fwd", lambda: K.add_ln_fwd(x, dout, gamma, beta), 3 * r * d * 4, 0.0),
+            ("add_ln_bwd", lambda: K.add_ln_bwd(x, dout, None, gamma), 3 * r * d * 4, 0.0),
+        ]
+        for pf in ((0, 1) if args.prefetch_ab else (1,)):
+            K.set_option(_lib.OPT_L2_PREFETCH, pf)
+            for name, fn, nbytes, flops in benches:
+                report(name, timeit(fn), nbytes, flops, l2_prefetch=pf)
+        K.set_option(_lib.OPT_L2_PREFETCH, 1)
+        del dout, dz, h16, a16, x4
         del x
         # encoder-only forward (BASELINE config 5): molecules/s
         torch.manual_seed(0)

@@ -39,9 +39,10 @@ SIGNATURES = {
     "dg_mlp_bwd_dgrad": [_P, _P, _P, _P, _P, _P, _LL, _I, _I, _P, _LL, _P],
     "dg_mlp_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _F, _P, _LL, _P],
 }
-INFO_SYMBOLS = ("dg_abi_version", "dg_last_error", "dg_has_tcgen05", "dg_set_option", "dg_get_option")
+INFO_SYMBOLS = ("dg_abi_version", "dg_last_error", "dg_has_tcgen05", "dg_set_option", "dg_get_option", "dg_debug_chain_profile")
 ABI_VERSION = 2
 OPT_L2_PREFETCH = 0
+PF_ALL, PF_DEFAULT = 63, 12        # DG_PF_* bit masks (include/druggen_b200.h)
 
 _lib = None
 _backend = None
@@ -64,6 +65,7 @@ def load():
         lib.dg_last_error.restype = C.c_char_p
         lib.dg_set_option.argtypes, lib.dg_set_option.restype = [_I, _I], _I
         lib.dg_get_option.argtypes, lib.dg_get_option.restype = [_I], _I
+        lib.dg_debug_chain_profile.argtypes, lib.dg_debug_chain_profile.restype = [_P], _I
         if lib.dg_abi_version() != ABI_VERSION:
             raise RuntimeError("libdruggen_b200.so ABI version mismatch")
         if os.environ.get("DRUGGEN_B200_L2_PREFETCH") is not None:       # tuning switch, default on

@@ -243,7 +243,7 @@ extern "C" int dg_attn_scores_fwd(const float* q, const float* k, const float* v
   if ((stat_m == nullptr) != (stat_inv == nullptr)) return fail("dg_attn_scores_fwd: pass both statistics buffers or neither");
   attn_scores_kernel<0><<<grid, 128, smem, (cudaStream_t)stream>>>(nullptr, nullptr, q, k, v, e, c, a, g, nullptr, nullptr,
                                                                     nullptr, nullptr, stat_m, stat_inv, nullptr, N, irows,
-                                                                    opt_get(DG_OPT_L2_PREFETCH), 0);
+                                                                    opt_get(DG_OPT_L2_PREFETCH) & DG_PF_ATTN_FWD, 0);
   return check_launch("dg_attn_scores_fwd");
 }
 
@@ -256,7 +256,7 @@ extern "C" int dg_softmax_agg16_fwd(const void* a_bf16, const float* v, float* g
   if ((stat_m == nullptr) != (stat_inv == nullptr)) return fail("dg_softmax_agg16_fwd: pass both statistics buffers or neither");
   attn_scores_kernel<2><<<grid, 128, smem, (cudaStream_t)stream>>>(nullptr, nullptr, v, v, v, (const float*)a_bf16, 1.f, nullptr, g,
                                                                     nullptr, nullptr, nullptr, nullptr, stat_m, stat_inv, nullptr, N,
-                                                                    irows, opt_get(DG_OPT_L2_PREFETCH), 0);
+                                                                    irows, opt_get(DG_OPT_L2_PREFETCH) & DG_PF_ATTN_FWD, 0);
   return check_launch("dg_softmax_agg16_fwd");
 }
 
@@ -274,6 +274,6 @@ extern "C" int dg_attn_scores_bwd(const float* dg_, const float* da_in, const fl
   if (stat_m != nullptr && (stat_inv == nullptr || g == nullptr)) return fail("dg_attn_scores_bwd: statistics need stat_inv and g too");
   attn_scores_kernel<1><<<grid, 128, smem, (cudaStream_t)stream>>>(dg_, da_in, q, k, v, e, c, nullptr, nullptr, (float*)de, dq, dk, dv,
                                                                     const_cast<float*>(stat_m), const_cast<float*>(stat_inv), g, N, irows,
-                                                                    opt_get(DG_OPT_L2_PREFETCH), de_bf16);
+                                                                    opt_get(DG_OPT_L2_PREFETCH) & DG_PF_ATTN_BWD, de_bf16);
   return check_launch("dg_attn_scores_bwd");
 }

@@ -58,7 +58,16 @@ struct MlpArgs {
   int natoms;              // N: edge row r = ((b N + i) N + j)
   float cscale;            // 1 / sqrt(d_k)
   int prefetch;            // DG_OPT_L2_PREFETCH
+  long long* prof;         // debug: per-CTA phase cycle counters [grid][4 roles][16] (dg_debug_chain_profile), or NULL
 };
+
+// phase timing (debug): lane 0 of four role-leader warps accumulates clock64() deltas per phase into shared memory
+#define DG_PROF(id)                                            \
+  if (prof_on) {                                              \
+    const long long t_now = clock64();                        \
+    sProf[prof_slot * 16 + (id)] += t_now - t_prev;           \
+    t_prev = t_now;                                           \
+  }
 
 // ---- weight pre-pack: fp32 nn.Linear weights -> bf16 swizzled operand stages in a workspace ------
 // forward orientation (FWD, BWD_A):
@@ -103,7 +112,8 @@ struct MlpSmem {
   static constexpr int stats = stage + 8 * 32 * kStgPitch * 4;   // [2 parity][2 halves][128 rows] float2, twice (BWD_A)
   static constexpr int vec = stats + 2 * 2 * 2 * 128 * 8;        // b1[384] b2[128] gamma[128] beta[128]
   static constexpr int bars = vec + (384 + 3 * 128) * 4;
-  static constexpr int total = bars + 256;
+  static constexpr int prof = bars + 256;                        // 4 roles x 16 counters (debug)
+  static constexpr int total = prof + 4 * 16 * 8;
 };
 
 // warp-cooperative transposes through a [32][kStgPitch] staging tile, 16 words (columns) at a time:
@@ -152,7 +162,9 @@ __device__ __forceinline__ void scatter_rows16(float* __restrict__ dst, long lon
 template <int kMode>
 __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpArgs A) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment as an OFFSET from the __shared__ array: a pointer rebuilt from an integer loses its address
+  // space and every access through it compiles to generic LD/ST (LSU long-scoreboard path) instead of LDS/STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sX = smem + MlpSmem::xb;
   uint8_t* sH = smem + MlpSmem::hb;
   uint8_t* sW = smem + MlpSmem::wb;
@@ -166,6 +178,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
   uint64_t *x_full = bars, *x_empty = bars + 2, *w_full = bars + 4, *w_empty = bars + 6, *hacc_full = bars + 8,
            *hacc_empty = bars + 11, *hb_full = bars + 14, *hb_empty = bars + 16, *z_full = bars + 18, *z_empty = bars + 19;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  long long* sProf = reinterpret_cast<long long*>(smem + MlpSmem::prof);
 
   const float* __restrict__ x = A.x;
   const long long R = A.R;
@@ -185,6 +198,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
     fence_barrier_init();
   }
   if (warp == 12) tmem_alloc(tmem_slot, 512);
+  if (tid < 64) sProf[tid] = 0;
+  const int prof_slot = warp == 0 ? 0 : warp == 4 ? 1 : warp == 8 ? 2 : 3;   // (only those warps and the MMA warp record)
+  const bool prof_on = A.prof != nullptr && lane == 0 && (warp == 0 || warp == 4 || warp == 8 || warp == 12);
+  long long t_prev = clock64();
   if (kMode != kBwdB) {
     for (int i = tid; i < H; i += kMlpThreads) sB1[i] = A.b1[i];
     for (int i = tid; i < 128; i += kMlpThreads) {
@@ -216,7 +233,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
           else if (kMode == kBwdB) bulk_prefetch_l2(A.gate + prow0 * H, prows * H * 2);
         }
       }
+      DG_PROF(0)
       mbar_wait(&x_empty[xs], ((ti >> 1) & 1) ^ 1);
+      DG_PROF(1)
 #pragma unroll 1
       for (int kb = 0; kb < 2; ++kb) {
         uint8_t* blk = sX + xs * kWStage + kb * kBlkBytes;
@@ -239,6 +258,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
       }
       fence_async_smem();
       mbar_arrive(&x_full[xs]);
+      DG_PROF(2)
     }
   } else if (warp == 13) {
     // ------------------------------------------------------------------ weight streamer (one thread)
@@ -266,7 +286,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
       uint32_t wcount = 0, hcount = 0;
       auto mma_chunk = [&](uint32_t a_base, uint32_t d_col, bool first_clears) {
         const int ws = wcount & 1;
+        DG_PROF(0)
         mbar_wait(&w_full[ws], (wcount >> 1) & 1);
+        DG_PROF(1)
         tc_fence_after();
         const uint32_t b_base = smem_u32(sW + ws * kWStage);
 #pragma unroll
@@ -280,8 +302,11 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
       };
       auto gemm1 = [&](long long ti, int c) {
         const int xs = ti & 1;
+        DG_PROF(0)
         if (c == 0) { mbar_wait(&x_full[xs], (ti >> 1) & 1); tc_fence_after(); }
+        DG_PROF(2)
         mbar_wait(&hacc_empty[c], (ti & 1) ^ 1);
+        DG_PROF(3)
         tc_fence_after();
         mma_chunk(smem_u32(sX + xs * kWStage), c * 128, true);
         umma_commit(&hacc_full[c]);
@@ -291,15 +316,18 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
       for (long long ti = 0; ti < my_tiles; ++ti) {
         for (int c = 0; c < HC; ++c) {
           const int hs = hcount & 1;
+          DG_PROF(0)
           mbar_wait(&hb_full[hs], (hcount >> 1) & 1);
+          DG_PROF(4)
           if (c == 0) mbar_wait(z_empty, (ti & 1) ^ 1);
+          DG_PROF(5)
           tc_fence_after();
           mma_chunk(smem_u32(sH + hs * kWStage), 384, c == 0);
           umma_commit(&hb_empty[hs]);
           ++hcount;
+          if (c == HC - 1) umma_commit(z_full);      // before the next tile's GEMM1 is even issued: the final epilogue does not wait for it
           if (ti + 1 < my_tiles) gemm1(ti + 1, c);
         }
-        umma_commit(z_full);
       }
     }
     __syncwarp();
@@ -325,9 +353,12 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
         const int wcol = (c * 128 + hf * 64) >> 1;
         float4 gq[8];
         if (kMode == kBwdB) gather_issue(reinterpret_cast<const float*>(A.gate), wrow0, R, H >> 1, wcol, 2, lane, gq);
+        DG_PROF(0)
         mbar_wait(&hacc_full[c], ti & 1);
+        DG_PROF(1)
         const int hs = hcount & 1;
         mbar_wait(&hb_empty[hs], ((hcount >> 1) & 1) ^ 1);
+        DG_PROF(2)
         tc_fence_after();
         uint8_t* hblk = sH + hs * kWStage + hf * kBlkBytes;          // this half's 64 hidden columns = one operand block
         float v[64];
@@ -337,6 +368,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&hacc_empty[c]);
+        DG_PROF(3)
         if (kMode == kBwdB) {
           float gw[32];                                              // 64 bf16 sign masks of this row
           gather_finish(gq, 2, stg, lane, gw);
@@ -389,6 +421,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&hb_full[hs]);
+        DG_PROF(4)
         ++hcount;
         if (kMode == kBwdA || kMode == kBwdB || (kMode == kAttn && A.spill != nullptr)) {   // spill the chunk as bf16 (weight-gradient pass / softmax)
           float pk[32];
@@ -396,16 +429,20 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
           for (int i = 0; i < 32; ++i) pk[i] = __uint_as_float(pack_bf16(v[2 * i], v[2 * i + 1]));
           scatter_rows16(reinterpret_cast<float*>(A.spill), wrow0, R, H >> 1, wcol, stg, lane, pk);
           scatter_rows16(reinterpret_cast<float*>(A.spill), wrow0, R, H >> 1, wcol + 16, stg, lane, pk + 16);
+          DG_PROF(12)
         }
       }
       // ---- final epilogue: this thread = one row, 64 columns [hf*64, +64)
+      DG_PROF(5)
       float a[64];
       {
         float4 xq[16];
         gather_issue(x, wrow0, R, 128, hf * 64, 4, lane, xq);      // FWD/BWD_A: residual x;  BWD_B: residual dz
         gather_finish(xq, 4, stg, lane, a);
       }
+      DG_PROF(6)
       mbar_wait(z_full, ti & 1);
+      DG_PROF(7)
       tc_fence_after();
       float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
 #pragma unroll
@@ -423,14 +460,17 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
           s1a += t0; s1b += t1; s2a = fmaf(t0, t0, s2a); s2b = fmaf(t1, t1, s2b);
         }
       }
+      DG_PROF(8)
       if (kMode == kBwdB) {                                           // dx = dz + dh . W1
 #pragma unroll
         for (int g16 = 0; g16 < 4; ++g16) scatter_rows16(A.out, wrow0, R, 128, hf * 64 + g16 * 16, stg, lane, a + g16 * 16);
+        DG_PROF(11)
         continue;
       }
       float2* st = sStats + (ti & 1) * 512;
       st[hf * 128 + row] = make_float2(s1a + s1b, s2a + s2b);
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      DG_PROF(9)
       const float2 other = st[(hf ^ 1) * 128 + row];
       const float mean = (s1a + s1b + other.x) * (1.f / 128.f);
       const float rstd = rsqrtf(fmaxf((s2a + s2b + other.y) * (1.f / 128.f) - mean * mean, 0.f) + A.eps);
@@ -449,6 +489,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
         }
 #pragma unroll
         for (int g16 = 0; g16 < 4; ++g16) scatter_rows16(A.out, wrow0, R, 128, hf * 64 + g16 * 16, stg, lane, a + g16 * 16);
+        DG_PROF(11)
         continue;
       }
       // ---- BWD_A: LayerNorm backward.  xh = (z - mean) rstd;  gh = gamma * dout;
@@ -496,9 +537,11 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
         }
         __syncwarp();
       }
+      DG_PROF(10)
       float2* st2 = sStats + (ti & 1) * 512 + 256;
       st2[hf * 128 + row] = make_float2(sg, sgx);
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      DG_PROF(9)
       const float2 o2 = st2[(hf ^ 1) * 128 + row];
       const float c1 = (sg + o2.x) * (1.f / 128.f), c2 = (sgx + o2.y) * (1.f / 128.f);
 #pragma unroll
@@ -511,6 +554,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
         for (int i = 0; i < 16; ++i) dd[i] = rstd * (gg[g16 * 16 + i] * dd[i] - c1 - a[g16 * 16 + i] * c2);
         scatter_rows16(A.out, wrow0, R, 128, hf * 64 + g16 * 16, stg, lane, dd);
       }
+      DG_PROF(11)
     }
     if (kMode == kBwdA && lane < 16) {
 #pragma unroll
@@ -526,7 +570,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+  if (A.prof != nullptr && tid < 64) A.prof[(long long)blockIdx.x * 64 + tid] = sProf[tid];
 }
+
+static long long* g_chain_prof = nullptr;
 
 template <int kMode>
 static int launch_chain(const MlpArgs& a, cudaStream_t s) {   // (one `configured` flag per instantiation)
@@ -539,7 +586,8 @@ static int launch_chain(const MlpArgs& a, cudaStream_t s) {   // (one `configure
   long long tiles = (a.R + 127) / 128;
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   MlpArgs b = a;
-  b.prefetch = opt_get(DG_OPT_L2_PREFETCH);
+  b.prefetch = opt_get(DG_OPT_L2_PREFETCH) & DG_PF_CHAIN;
+  b.prof = g_chain_prof;
   mlp_chain_tc_kernel<kMode><<<grid, kMlpThreads, MlpSmem::total + 1024, s>>>(b);
   return check_launch("dg_mlp_chain");
 }
@@ -600,4 +648,10 @@ extern "C" int dg_attn_edge_fwd(const float* y, const float* q, const float* k, 
   tc::MlpArgs a{y, (const uint8_t*)workspace, be, boe, gamma, beta, nullptr, out, (uint16_t*)a_bf16, nullptr, nullptr, nullptr, R, 1, eps,
                 q, k, e_out, z_out, N, c, 0};
   return tc::launch_chain<tc::kAttn>(a, s);
+}
+
+/* debug: phase cycle counters of the chain kernels ([148 CTAs][4 roles][16] int64 device buffer, or NULL to stop) */
+extern "C" int dg_debug_chain_profile(void* device_buf) {
+  tc::g_chain_prof = (long long*)device_buf;
+  return 0;
 }

@@ -51,7 +51,9 @@ rows_gemm_tc_kernel(const float* __restrict__ a, const float* __restrict__ w, in
   const uint16_t* gate16 = reinterpret_cast<const uint16_t*>(gate);
   uint16_t* out16 = reinterpret_cast<uint16_t*>(out);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment as an OFFSET from the __shared__ array: a pointer rebuilt from an integer loses its address
+  // space and every access through it compiles to generic LD/ST (LSU long-scoreboard path) instead of LDS/STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const RowsSmem L = rows_smem(K, N);
   uint8_t* sW = smem + L.w;
   uint8_t* sA = smem + L.a;
@@ -319,7 +321,9 @@ gemm_tn_tc_kernel(const float* __restrict__ a, const float* __restrict__ b, floa
                   float* __restrict__ colsum_a, long long R, int M, int N, long long tiles_per_cta, int stages, int flags,
                   int prefetch) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment as an OFFSET from the __shared__ array: a pointer rebuilt from an integer loses its address
+  // space and every access through it compiles to generic LD/ST (LSU long-scoreboard path) instead of LDS/STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int nblk = (M + N) / 64;                       // operand blocks per stage: a's first, then b's
   const int stage_bytes = nblk * kTnBlk;
   uint8_t* sOp = smem;
@@ -560,7 +564,7 @@ int rows_gemm_tc(const void* a_, const float* w, int w_is_nk, const float* bias,
   long long tiles = (R + 127) / 128;
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   tc::rows_gemm_tc_kernel<<<grid, tc::kThreads, smem, s>>>(a, w, w_is_nk, bias, relu, gate, resid, out, R, K, N, flags,
-                                                           opt_get(DG_OPT_L2_PREFETCH));
+                                                           opt_get(DG_OPT_L2_PREFETCH) & DG_PF_ROWS_GEMM);
   return check_launch("dg_rows_gemm(bf16)");
 }
 
@@ -589,7 +593,7 @@ int gemm_tn_tc(const void* a_, const void* b_, float* out, float* colsum_a, long
   long long per = (tiles + ctas - 1) / ctas;
   ctas = (tiles + per - 1) / per;
   tc::gemm_tn_tc_kernel<<<(int)ctas, tc::kTnThreads, smem, s>>>(a, b, out, colsum_a, R, M, N, per, stages, flags,
-                                                                opt_get(DG_OPT_L2_PREFETCH));
+                                                                opt_get(DG_OPT_L2_PREFETCH) & (M + N == 256 ? DG_PF_GEMM_TN : DG_PF_GEMM_TN_WIDE));
   return check_launch("dg_gemm_tn(bf16)");
 }
 

@@ -35,7 +35,14 @@ const char* dg_last_error(void);
 int dg_has_tcgen05(void);
 
 /* Run-time options (process-wide; read at launch time).  Returns 0 / the value. */
-#define DG_OPT_L2_PREFETCH 0 /* 1 (default): loaders issue bulk L2 prefetches (cp.async.bulk.prefetch.L2) ahead of their loads */
+#define DG_OPT_L2_PREFETCH 0 /* bit mask: which kernels issue bulk L2 prefetches (cp.async.bulk.prefetch.L2) ahead of their
+                              * loads.  Default DG_PF_GEMM_TN | DG_PF_ATTN_FWD: the kernels where it measured faster on B200. */
+#define DG_PF_CHAIN 1      /* dg_mlp_*, dg_attn_edge_fwd */
+#define DG_PF_ROWS_GEMM 2  /* dg_rows_gemm */
+#define DG_PF_GEMM_TN 4    /* dg_gemm_tn with M = N = 128 */
+#define DG_PF_ATTN_FWD 8   /* dg_attn_scores_fwd, dg_softmax_agg16_fwd */
+#define DG_PF_ATTN_BWD 16  /* dg_attn_scores_bwd */
+#define DG_PF_GEMM_TN_WIDE 32 /* dg_gemm_tn with M or N > 128 */
 #define DG_OPT_COUNT 1
 int dg_set_option(int key, int value);
 int dg_get_option(int key);
@@ -146,6 +153,10 @@ int dg_attn_edge_fwd(const float* y, const float* q, const float* k, const float
                      const float* woe, const float* boe, const float* gamma, const float* beta, float c,
                      float* out, void* a_bf16, float* e_out, float* z_out, int B, int N, int D, float eps,
                      void* workspace, long long workspace_bytes, void* stream);
+
+/* debug: with a device buffer of 148*64 int64 set, every chain-kernel launch (dg_mlp_*, dg_attn_edge_fwd) writes
+ * per-CTA phase cycle counters [CTA][4 roles][16 phases] (tools/chain_profile.py); NULL switches it off. */
+int dg_debug_chain_profile(void* device_buf);
 
 #ifdef __cplusplus
 }

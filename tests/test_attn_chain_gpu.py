@@ -121,10 +121,10 @@ def test_l2_prefetch_option_is_numerically_inert(cuda_dev):
     try:
         K.set_option(_lib.OPT_L2_PREFETCH, 0)
         off = run()
-        K.set_option(_lib.OPT_L2_PREFETCH, 1)
+        K.set_option(_lib.OPT_L2_PREFETCH, _lib.PF_ALL)
         on = run()
     finally:
-        K.set_option(_lib.OPT_L2_PREFETCH, 1)
+        K.set_option(_lib.OPT_L2_PREFETCH, _lib.PF_DEFAULT)
     for i, (a, b) in enumerate(zip(off, on)):
         assert rel_l2(a, b) < 1e-6, i          # (atomically accumulated outputs differ in summation order only)
 

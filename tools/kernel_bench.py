@@ -113,11 +113,11 @@ def main():
             ("add_ln_fwd", lambda: K.add_ln_fwd(x, dout, gamma, beta), 3 * r * d * 4, 0.0),
             ("add_ln_bwd", lambda: K.add_ln_bwd(x, dout, None, gamma), 3 * r * d * 4, 0.0),
         ]
-        for pf in ((0, 1) if args.prefetch_ab else (1,)):
+        for pf in ((0, _lib.PF_ALL) if args.prefetch_ab else (_lib.PF_DEFAULT,)):
             K.set_option(_lib.OPT_L2_PREFETCH, pf)
             for name, fn, nbytes, flops in benches:
                 report(name, timeit(fn), nbytes, flops, l2_prefetch=pf)
-        K.set_option(_lib.OPT_L2_PREFETCH, 1)
+        K.set_option(_lib.OPT_L2_PREFETCH, _lib.PF_DEFAULT)
         del dout, dz, h16, a16, x4
         del x
         # encoder-only forward (BASELINE config 5): molecules/s

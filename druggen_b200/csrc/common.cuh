@@ -57,5 +57,12 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// 32 contiguous bytes in ONE request (LDG.E.256, sm_100): the register-staged operand loaders read 8 channels per thread;
+// as two LDG.128 every warp instruction touched each 32-byte sector half-used (2x the L1<->L2 sector requests)
+__device__ __forceinline__ void ld8(const float* p, float4& lo, float4& hi) {
+  asm("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+      : "l"(p));
+}
 
 }  // namespace dg

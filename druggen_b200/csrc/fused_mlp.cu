@@ -30,7 +30,10 @@ namespace tc {
 
 constexpr int kMlpThreads = 448;
 constexpr int kWStage = 2 * kBlkBytes;   // one packed weight stage: [2 kb][128 rows][128 B] = 32 KB
-constexpr int kStgPitch = 20;            // epilogue transpose: 32 rows x 16 words per warp, pitch 20 words
+constexpr int kStgPitch = 16;            // epilogue transpose: 32 rows x 16 words per warp, XOR-swizzled (no padding)
+// word offset of the 4-float chunk c4 of row r in a staging tile: conflict-free both for the coalesced side (8 lanes = 2
+// rows x 4 chunks) and for the thread-per-row side (8 lanes = 8 consecutive rows, same chunk)
+__device__ __forceinline__ int stg_off(int r, int c4) { return r * kStgPitch + ((c4 ^ ((r >> 1) & 3)) << 2); }
 
 enum { kFwd = 0, kBwdA = 1, kBwdB = 2, kAttn = 3 };
 
@@ -136,11 +139,11 @@ __device__ __forceinline__ void gather_finish(const float4* xq, int ngroups, flo
   for (int g16 = 0; g16 < 4; ++g16)
     if (g16 < ngroups) {
 #pragma unroll
-      for (int it = 0; it < 4; ++it) st4(stg + (it * 8 + (lane >> 2)) * kStgPitch + (lane & 3) * 4, xq[g16 * 4 + it]);
+      for (int it = 0; it < 4; ++it) st4(stg + stg_off(it * 8 + (lane >> 2), lane & 3), xq[g16 * 4 + it]);
       __syncwarp();
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        float4 v = ld4(stg + lane * kStgPitch + i * 4);
+        float4 v = ld4(stg + stg_off(lane, i));
         dst[g16 * 16 + 4 * i] = v.x; dst[g16 * 16 + 4 * i + 1] = v.y; dst[g16 * 16 + 4 * i + 2] = v.z; dst[g16 * 16 + 4 * i + 3] = v.w;
       }
       __syncwarp();
@@ -149,12 +152,12 @@ __device__ __forceinline__ void gather_finish(const float4* xq, int ngroups, flo
 __device__ __forceinline__ void scatter_rows16(float* __restrict__ dst, long long row_base, long long R, int pitch, int col,
                                                float* stg, int lane, const float* src16) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) st4(stg + lane * kStgPitch + i * 4, make_float4(src16[4 * i], src16[4 * i + 1], src16[4 * i + 2], src16[4 * i + 3]));
+  for (int i = 0; i < 4; ++i) st4(stg + stg_off(lane, i), make_float4(src16[4 * i], src16[4 * i + 1], src16[4 * i + 2], src16[4 * i + 3]));
   __syncwarp();
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
     const int r = it * 8 + (lane >> 2);
-    if (row_base + r < R) st4(dst + (row_base + r) * pitch + col + (lane & 3) * 4, ld4(stg + r * kStgPitch + (lane & 3) * 4));
+    if (row_base + r < R) st4(dst + (row_base + r) * pitch + col + (lane & 3) * 4, ld4(stg + stg_off(r, lane & 3)));
   }
   __syncwarp();
 }
@@ -244,8 +247,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
         for (int it = 0; it < 8; ++it) {
           int item = it * 128 + lt, r = item >> 3, j = item & 7;
           if (row0 + r < R) {
-            const float* p = x + (row0 + r) * 128 + kb * 64 + j * 8;
-            v[2 * it] = ld4(p); v[2 * it + 1] = ld4(p + 4);
+            ld8(x + (row0 + r) * 128 + kb * 64 + j * 8, v[2 * it], v[2 * it + 1]);
           } else {
             v[2 * it] = v[2 * it + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
@@ -504,17 +506,17 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
         gather_issue(A.dout, wrow0, R, 128, hf * 64 + g16 * 16, 1, lane, dq4);
         // gather_finish, but keep the staged [32 rows][16 cols] block for the column sums
 #pragma unroll
-        for (int it = 0; it < 4; ++it) st4(stg + (it * 8 + (lane >> 2)) * kStgPitch + (lane & 3) * 4, dq4[it]);
+        for (int it = 0; it < 4; ++it) st4(stg + stg_off(it * 8 + (lane >> 2), lane & 3), dq4[it]);
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          float4 t = ld4(stg + lane * kStgPitch + i * 4);
+          float4 t = ld4(stg + stg_off(lane, i));
           dd[4 * i] = t.x; dd[4 * i + 1] = t.y; dd[4 * i + 2] = t.z; dd[4 * i + 3] = t.w;
         }
         if (lane < 16) {                                              // dbeta: column `lane` of the staged dout block
           float sb = 0.f;
 #pragma unroll 8
-          for (int r = 0; r < 32; ++r) sb += stg[r * kStgPitch + lane];
+          for (int r = 0; r < 32; ++r) sb += stg[stg_off(r, lane >> 2) + (lane & 3)];
           cs_b[g16] += sb;
         }
         __syncwarp();
@@ -527,12 +529,12 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
           sgx = fmaf(gh, a[g16 * 16 + i], sgx);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) st4(stg + lane * kStgPitch + i * 4, make_float4(px[4 * i], px[4 * i + 1], px[4 * i + 2], px[4 * i + 3]));
+        for (int i = 0; i < 4; ++i) st4(stg + stg_off(lane, i), make_float4(px[4 * i], px[4 * i + 1], px[4 * i + 2], px[4 * i + 3]));
         __syncwarp();
         if (lane < 16) {                                              // dgamma: column sums of dout * xh
           float sgm = 0.f;
 #pragma unroll 8
-          for (int r = 0; r < 32; ++r) sgm += stg[r * kStgPitch + lane];
+          for (int r = 0; r < 32; ++r) sgm += stg[stg_off(r, lane >> 2) + (lane & 3)];
           cs_g[g16] += sgm;
         }
         __syncwarp();
@@ -597,8 +599,9 @@ static int launch_chain(const MlpArgs& a, cudaStream_t s) {   // (one `configure
 
 using namespace dg;
 
-static int mlp_check(const char* who, long long R, int D, int H, const void* ws, long long ws_bytes) {
+static int mlp_check(const char* who, const void* x, long long R, int D, int H, const void* ws, long long ws_bytes) {
   if (R <= 0) return fail("%s: rows must be > 0", who);
+  if (reinterpret_cast<uintptr_t>(x) & 31) return fail("%s: the row input must be 32-byte aligned (256-bit loads)", who);
   if (D != 128 || H % 128 || H < 128 || H > 384) return fail("%s: needs D == 128 and H in {128,256,384}, got D=%d H=%d", who, D, H);
   if (ws_bytes < (long long)2 * (H / 128) * tc::kWStage) return fail("%s: workspace too small (%lld bytes)", who, ws_bytes);
   if (reinterpret_cast<uintptr_t>(ws) & 127) return fail("%s: workspace must be 128-byte aligned", who);
@@ -608,7 +611,7 @@ static int mlp_check(const char* who, long long R, int D, int H, const void* ws,
 extern "C" int dg_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                           const float* gamma, const float* beta, float* out, long long R, int D, int H, float eps,
                           void* workspace, long long workspace_bytes, void* stream) {
-  if (mlp_check("dg_mlp_fwd", R, D, H, workspace, workspace_bytes)) return 1;
+  if (mlp_check("dg_mlp_fwd", x, R, D, H, workspace, workspace_bytes)) return 1;
   cudaStream_t s = (cudaStream_t)stream;
   tc::mlp_pack_weights_kernel<<<48, 256, 0, s>>>(w1, w2, (uint8_t*)workspace, H, 0);
   tc::MlpArgs a{x, (const uint8_t*)workspace, b1, b2, gamma, beta, nullptr, out, nullptr, nullptr, nullptr, nullptr, R, H / 128, eps};
@@ -618,7 +621,7 @@ extern "C" int dg_mlp_fwd(const float* x, const float* w1, const float* b1, cons
 extern "C" int dg_mlp_bwd_ln(const float* x, const float* dout, const float* w1, const float* b1, const float* w2,
                              const float* b2, const float* gamma, float* dz, void* h_bf16, float* dgamma, float* dbeta,
                              long long R, int D, int H, float eps, void* workspace, long long workspace_bytes, void* stream) {
-  if (mlp_check("dg_mlp_bwd_ln", R, D, H, workspace, workspace_bytes)) return 1;
+  if (mlp_check("dg_mlp_bwd_ln", x, R, D, H, workspace, workspace_bytes)) return 1;
   cudaStream_t s = (cudaStream_t)stream;
   tc::mlp_pack_weights_kernel<<<48, 256, 0, s>>>(w1, w2, (uint8_t*)workspace, H, 0);
   tc::MlpArgs a{x, (const uint8_t*)workspace, b1, b2, gamma, nullptr, dout, dz, (uint16_t*)h_bf16, nullptr, dgamma, dbeta, R, H / 128, eps};
@@ -628,7 +631,7 @@ extern "C" int dg_mlp_bwd_ln(const float* x, const float* dout, const float* w1,
 extern "C" int dg_mlp_bwd_dgrad(const float* dz, const void* h_bf16, const float* w1, const float* w2, float* dx,
                                 void* dh_bf16, long long R, int D, int H, void* workspace, long long workspace_bytes,
                                 void* stream) {
-  if (mlp_check("dg_mlp_bwd_dgrad", R, D, H, workspace, workspace_bytes)) return 1;
+  if (mlp_check("dg_mlp_bwd_dgrad", dz, R, D, H, workspace, workspace_bytes)) return 1;
   cudaStream_t s = (cudaStream_t)stream;
   tc::mlp_pack_weights_kernel<<<48, 256, 0, s>>>(w1, w2, (uint8_t*)workspace, H, 1);
   tc::MlpArgs a{dz, (const uint8_t*)workspace, nullptr, nullptr, nullptr, nullptr, nullptr, dx, (uint16_t*)dh_bf16,
@@ -642,7 +645,7 @@ extern "C" int dg_attn_edge_fwd(const float* y, const float* q, const float* k, 
                                 void* workspace, long long workspace_bytes, void* stream) {
   if (B <= 0 || N <= 0) return fail("dg_attn_edge_fwd: bad shape B=%d N=%d", B, N);
   const long long R = (long long)B * N * N;
-  if (mlp_check("dg_attn_edge_fwd", R, D, 128, workspace, workspace_bytes)) return 1;
+  if (mlp_check("dg_attn_edge_fwd", y, R, D, 128, workspace, workspace_bytes)) return 1;
   cudaStream_t s = (cudaStream_t)stream;
   tc::mlp_pack_weights_kernel<<<48, 256, 0, s>>>(we, woe, (uint8_t*)workspace, 128, 0);
   tc::MlpArgs a{y, (const uint8_t*)workspace, be, boe, gamma, beta, nullptr, out, (uint16_t*)a_bf16, nullptr, nullptr, nullptr, R, 1, eps,

@@ -144,8 +144,7 @@ rows_gemm_tc_kernel(const float* __restrict__ a, const float* __restrict__ w, in
         for (int it = 0; it < 8; ++it) {
           int item = it * 128 + lt, r = item >> 3, j = item & 7;
           if (row0 + r < R) {
-            const float* p = a + (row0 + r) * K + kb * 64 + j * 8;
-            v[2 * it] = ld4(p); v[2 * it + 1] = ld4(p + 4);
+            ld8(a + (row0 + r) * K + kb * 64 + j * 8, v[2 * it], v[2 * it + 1]);
           } else {
             v[2 * it] = v[2 * it + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
@@ -427,8 +426,7 @@ gemm_tn_tc_kernel(const float* __restrict__ a, const float* __restrict__ b, floa
               for (int q = 0; q < 4; ++q) {
                 int item = q * 128 + lt, r = item >> 3, j = item & 7;
                 if (row0 + r < R) {
-                  const float* p = src + (row0 + r) * ld + (g0 + h) * 64 + j * 8;
-                  v[h * 8 + 2 * q] = ld4(p); v[h * 8 + 2 * q + 1] = ld4(p + 4);
+                  ld8(src + (row0 + r) * ld + (g0 + h) * 64 + j * 8, v[h * 8 + 2 * q], v[h * 8 + 2 * q + 1]);
                 } else {
                   v[h * 8 + 2 * q] = v[h * 8 + 2 * q + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
@@ -554,6 +552,7 @@ int rows_gemm_tc(const void* a_, const float* w, int w_is_nk, const float* bias,
   if ((flags & DG_OUT_BF16) && (resid || (gate && !(flags & DG_GATE_BF16))))
     return fail("dg_rows_gemm: a bf16 output takes no resid and only a bf16 gate");
   if (!(flags & DG_OUT_BF16) && (flags & DG_GATE_BF16)) return fail("dg_rows_gemm: a bf16 gate needs a bf16 output");
+  if (!(flags & DG_A_BF16) && (reinterpret_cast<uintptr_t>(a) & 31)) return fail("dg_rows_gemm: a must be 32-byte aligned (256-bit loads)");
   const int smem = tc::rows_smem(K, N).total + 1024;
   static int configured = 0;
   if (configured < smem) {
@@ -577,6 +576,8 @@ int gemm_tn_tc(const void* a_, const void* b_, float* out, float* colsum_a, long
     if (flags) return fail("dg_gemm_tn: bf16 storage is only available for the tcgen05 shapes (M=%d N=%d)", M, N);
     return gemm_tn_fp32(a, b, out, colsum_a, R, M, N, s);
   }
+  if ((!(flags & DG_A_BF16) && (reinterpret_cast<uintptr_t>(a) & 31)) || (!(flags & DG_OUT_BF16) && (reinterpret_cast<uintptr_t>(b) & 31)))
+    return fail("dg_gemm_tn: fp32 operands must be 32-byte aligned (256-bit loads)");
   const int stage_bytes = (M + N) / 64 * tc::kTnBlk;
   int stages = (200 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;

@@ -22,6 +22,7 @@
 //   warp  13    W loader : one thread streams pre-packed bf16 weight stages (32 KB) with
 //                          cp.async.bulk into a 2-stage ring (weights live in L2: 192 KB per net)
 // TMEM: columns [0,384) three GEMM1 chunk accumulators, [384,512) the GEMM2 accumulator.
+#include <cuda.h>
 #include "tc_common.cuh"
 #include "../../include/druggen_b200.h"
 
@@ -62,6 +63,11 @@ struct MlpArgs {
   float cscale;            // 1 / sqrt(d_k)
   int prefetch;            // DG_OPT_L2_PREFETCH
   long long* prof;         // debug: per-CTA phase cycle counters [grid][4 roles][16] (dg_debug_chain_profile), or NULL
+  // tensor maps of the [R,128] fp32 row tensors that cross the final epilogue through TMA: box = [128 rows][32 channels],
+  // 128-byte swizzle (tm_x: residual input = x;  tm_out: out;  tm_z: z_out of ATTN)
+  alignas(64) CUtensorMap tm_x;
+  alignas(64) CUtensorMap tm_out;
+  alignas(64) CUtensorMap tm_z;
 };
 
 // phase timing (debug): lane 0 of four role-leader warps accumulates clock64() deltas per phase into shared memory
@@ -163,7 +169,7 @@ __device__ __forceinline__ void scatter_rows16(float* __restrict__ dst, long lon
 }
 
 template <int kMode>
-__global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpArgs A) {
+__global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __grid_constant__ MlpArgs A) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment as an OFFSET from the __shared__ array: a pointer rebuilt from an integer loses its address
   // space and every access through it compiles to generic LD/ST (LSU long-scoreboard path) instead of LDS/STS
@@ -179,8 +185,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
   float* sBe = sG + 128;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MlpSmem::bars);
   uint64_t *x_full = bars, *x_empty = bars + 2, *w_full = bars + 4, *w_empty = bars + 6, *hacc_full = bars + 8,
-           *hacc_empty = bars + 11, *hb_full = bars + 14, *hb_empty = bars + 16, *z_full = bars + 18, *z_empty = bars + 19;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+           *hacc_empty = bars + 11, *hb_full = bars + 14, *hb_empty = bars + 16, *z_full = bars + 18, *z_empty = bars + 19,
+           *io_full = bars + 20;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
   long long* sProf = reinterpret_cast<long long*>(smem + MlpSmem::prof);
 
   const float* __restrict__ x = A.x;
@@ -198,6 +205,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
     }
     for (int i = 0; i < 3; ++i) { mbar_init(&hacc_full[i], 1); mbar_init(&hacc_empty[i], 8); }
     mbar_init(z_full, 1); mbar_init(z_empty, 8);     // epilogue barriers: one elected arrival per warp
+    mbar_init(io_full, 1);
     fence_barrier_init();
   }
   if (warp == 12) tmem_alloc(tmem_slot, 512);
@@ -416,6 +424,12 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
             v[i + 2] = fmaxf(v[i + 2] + b4.z, 0.f); v[i + 3] = fmaxf(v[i + 3] + b4.w, 0.f);
           }
         }
+        if (c == 0 && ti > 0 && kMode != kBwdA) {
+          // the previous tile's output left through TMA out of the operand buffers (see the final epilogue): they may be
+          // overwritten once that store has finished READING shared memory
+          if (warp == 0 && lane == 0) bulk_wait_read0();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           st_block_chunk(hblk, row, j, make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
@@ -436,16 +450,27 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
       }
       // ---- final epilogue: this thread = one row, 64 columns [hf*64, +64)
       DG_PROF(5)
+      // The residual rows come in, and the output rows leave, as a TMA tile: 4 boxes [128 rows][32 channels] with the
+      // 128-byte swizzle, staged in the two operand buffers sH[0..1] (64 KB), which are idle from the completion of the
+      // tile's last GEMM2 (z_full) until the next tile's first chunk is stored.  A thread reads and later overwrites only
+      // its own row halves, so the tile needs no transposition and no bank conflicts (8 consecutive rows = 8 swizzle slots).
       float a[64];
-      {
-        float4 xq[16];
-        gather_issue(x, wrow0, R, 128, hf * 64, 4, lane, xq);      // FWD/BWD_A: residual x;  BWD_B: residual dz
-        gather_finish(xq, 4, stg, lane, a);
-      }
-      DG_PROF(6)
       mbar_wait(z_full, ti & 1);
       DG_PROF(7)
       tc_fence_after();
+      if (warp == 0 && lane == 0) {
+        mbar_expect_tx(io_full, 4 * kBlkBytes);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) tma_load_2d(sH + g * kBlkBytes, &A.tm_x, g * 32, (int)row0, io_full);   // FWD/BWD_A/ATTN: x;  BWD_B: dz
+      }
+      mbar_wait(io_full, ti & 1);
+      uint8_t* iorow = sH + (2 * hf) * kBlkBytes + row * 128;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float4 t = ld4(reinterpret_cast<const float*>(iorow + (j >> 3) * kBlkBytes + (((j & 7) ^ (row & 7)) << 4)));
+        a[4 * j] = t.x; a[4 * j + 1] = t.y; a[4 * j + 2] = t.z; a[4 * j + 3] = t.w;
+      }
+      DG_PROF(6)
       float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
 #pragma unroll
       for (int cgl = 0; cgl < 2; ++cgl) {
@@ -463,9 +488,24 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
         }
       }
       DG_PROF(8)
-      if (kMode == kBwdB) {                                           // dx = dz + dh . W1
+      // rows -> the I/O tile (own row, in place) -> one elected thread issues the TMA store of the 4 boxes
+      auto store_tile = [&](const CUtensorMap* tm, bool wait_read) {
 #pragma unroll
-        for (int g16 = 0; g16 < 4; ++g16) scatter_rows16(A.out, wrow0, R, 128, hf * 64 + g16 * 16, stg, lane, a + g16 * 16);
+        for (int j = 0; j < 16; ++j)
+          st4(reinterpret_cast<float*>(iorow + (j >> 3) * kBlkBytes + (((j & 7) ^ (row & 7)) << 4)),
+              make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]));
+        fence_async_smem();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (warp == 0 && lane == 0) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) tma_store_2d(tm, g * 32, (int)row0, sH + g * kBlkBytes);
+          bulk_commit();
+          if (wait_read) bulk_wait_read0();
+        }
+        if (wait_read) asm volatile("bar.sync 1, 256;" ::: "memory");
+      };
+      if (kMode == kBwdB) {                                           // dx = dz + dh . W1
+        store_tile(&A.tm_out, false);
         DG_PROF(11)
         continue;
       }
@@ -477,10 +517,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
       const float mean = (s1a + s1b + other.x) * (1.f / 128.f);
       const float rstd = rsqrtf(fmaxf((s2a + s2b + other.y) * (1.f / 128.f) - mean * mean, 0.f) + A.eps);
       const float* gg = sG + hf * 64;
-      if (kMode == kAttn && A.z_out != nullptr) {                     // pre-LayerNorm sum, for the LayerNorm backward
-#pragma unroll
-        for (int g16 = 0; g16 < 4; ++g16) scatter_rows16(A.z_out, wrow0, R, 128, hf * 64 + g16 * 16, stg, lane, a + g16 * 16);
-      }
+      if (kMode == kAttn && A.z_out != nullptr) store_tile(&A.tm_z, true);   // pre-LayerNorm sum, for the LayerNorm backward
       if (kMode == kFwd || kMode == kAttn) {
         const float* be = sBe + hf * 64;
 #pragma unroll
@@ -489,8 +526,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
           a[i] = (a[i] - mean) * rstd * g4.x + e4.x; a[i + 1] = (a[i + 1] - mean) * rstd * g4.y + e4.y;
           a[i + 2] = (a[i + 2] - mean) * rstd * g4.z + e4.z; a[i + 3] = (a[i + 3] - mean) * rstd * g4.w + e4.w;
         }
-#pragma unroll
-        for (int g16 = 0; g16 < 4; ++g16) scatter_rows16(A.out, wrow0, R, 128, hf * 64 + g16 * 16, stg, lane, a + g16 * 16);
+        store_tile(&A.tm_out, false);
         DG_PROF(11)
         continue;
       }
@@ -558,6 +594,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
       }
       DG_PROF(11)
     }
+    if (kMode != kBwdA && warp == 0 && lane == 0) bulk_wait0();       // outstanding TMA stores complete before the CTA retires
     if (kMode == kBwdA && lane < 16) {
 #pragma unroll
       for (int g16 = 0; g16 < 4; ++g16) {
@@ -577,6 +614,28 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const MlpA
 
 static long long* g_chain_prof = nullptr;
 
+// [R,128] fp32 row tensor -> tensor map with box [128 rows][32 channels], 128-byte swizzle (driver entry point, no libcuda link)
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_row_tmap(CUtensorMap* tm, const float* base, long long R) {
+  static TmapEncodeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p)
+      return fail("cuTensorMapEncodeTiled is not available from this driver");
+    fn = (TmapEncodeFn)p;
+  }
+  if (reinterpret_cast<uintptr_t>(base) & 15) return fail("TMA row tensors must be 16-byte aligned");
+  const cuuint64_t dims[2] = {128, (cuuint64_t)R}, strides[1] = {512};
+  const cuuint32_t box[2] = {32, 128}, estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
 template <int kMode>
 static int launch_chain(const MlpArgs& a, cudaStream_t s) {   // (one `configured` flag per instantiation)
   static bool configured = false;
@@ -588,6 +647,9 @@ static int launch_chain(const MlpArgs& a, cudaStream_t s) {   // (one `configure
   long long tiles = (a.R + 127) / 128;
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   MlpArgs b = a;
+  if (make_row_tmap(&b.tm_x, a.x, a.R)) return 1;
+  if (kMode != kBwdA && make_row_tmap(&b.tm_out, a.out, a.R)) return 1;
+  if (kMode == kAttn && a.z_out != nullptr && make_row_tmap(&b.tm_z, a.z_out, a.R)) return 1;
   b.prefetch = opt_get(DG_OPT_L2_PREFETCH) & DG_PF_CHAIN;
   b.prof = g_chain_prof;
   mlp_chain_tc_kernel<kMode><<<grid, kMlpThreads, MlpSmem::total + 1024, s>>>(b);

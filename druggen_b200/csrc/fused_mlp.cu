@@ -68,6 +68,9 @@ struct MlpArgs {
   alignas(64) CUtensorMap tm_x;
   alignas(64) CUtensorMap tm_out;
   alignas(64) CUtensorMap tm_z;
+  // the bf16 side output [R,H] (h / dh / the scores): box = [128 rows][64 channels] = one operand block, 128-byte swizzle --
+  // it leaves straight out of the GEMM2 operand buffer the epilogue has just filled
+  alignas(64) CUtensorMap tm_spill;
 };
 
 // phase timing (debug): lane 0 of four role-leader warps accumulates clock64() deltas per phase into shared memory
@@ -196,15 +199,16 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long num_tiles = (R + 127) / 128;
   const long long my_tiles = blockIdx.x < num_tiles ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const bool spill = kMode == kBwdA || kMode == kBwdB || (kMode == kAttn && A.spill != nullptr);
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&x_full[i], 128); mbar_init(&x_empty[i], 1);
       mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1);
-      mbar_init(&hb_full[i], 8); mbar_init(&hb_empty[i], 1);
+      mbar_init(&hb_full[i], 8); mbar_init(&hb_empty[i], spill ? 2 : 1);   // + the spill store's read-completion
     }
     for (int i = 0; i < 3; ++i) { mbar_init(&hacc_full[i], 1); mbar_init(&hacc_empty[i], 8); }
-    mbar_init(z_full, 1); mbar_init(z_empty, 8);     // epilogue barriers: one elected arrival per warp
+    mbar_init(z_full, spill ? 2 : 1); mbar_init(z_empty, 8);     // epilogue barriers: one elected arrival per warp
     mbar_init(io_full, 1);
     fence_barrier_init();
   }
@@ -334,12 +338,24 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
           tc_fence_after();
           mma_chunk(smem_u32(sH + hs * kWStage), 384, c == 0);
           umma_commit(&hb_empty[hs]);
+          const int hs_ = hs;
           ++hcount;
           if (c == HC - 1) umma_commit(z_full);      // before the next tile's GEMM1 is even issued: the final epilogue does not wait for it
+          if (spill) {
+            // the bf16 operand block the epilogue just wrote IS the side output (h / dh / scores): TMA-store it from here
+            const int srow0 = (int)((blockIdx.x + ti * gridDim.x) * 128);
+            tma_store_2d(&A.tm_spill, c * 128, srow0, sH + hs_ * kWStage);
+            tma_store_2d(&A.tm_spill, c * 128 + 64, srow0, sH + hs_ * kWStage + kBlkBytes);
+            bulk_commit();
+            bulk_wait_read0();                       // (a few hundred cycles; nothing downstream of this thread is urgent)
+            mbar_arrive(&hb_empty[hs_]);
+            if (c == HC - 1) mbar_arrive(z_full);    // the final epilogue reuses both operand buffers as its I/O tile
+          }
           if (ti + 1 < my_tiles) gemm1(ti + 1, c);
         }
       }
     }
+    if (lane == 0 && spill) bulk_wait0();
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue (warps 0-7)
@@ -439,14 +455,6 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
         if (lane == 0) mbar_arrive(&hb_full[hs]);
         DG_PROF(4)
         ++hcount;
-        if (kMode == kBwdA || kMode == kBwdB || (kMode == kAttn && A.spill != nullptr)) {   // spill the chunk as bf16 (weight-gradient pass / softmax)
-          float pk[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) pk[i] = __uint_as_float(pack_bf16(v[2 * i], v[2 * i + 1]));
-          scatter_rows16(reinterpret_cast<float*>(A.spill), wrow0, R, H >> 1, wcol, stg, lane, pk);
-          scatter_rows16(reinterpret_cast<float*>(A.spill), wrow0, R, H >> 1, wcol + 16, stg, lane, pk + 16);
-          DG_PROF(12)
-        }
       }
       // ---- final epilogue: this thread = one row, 64 columns [hf*64, +64)
       DG_PROF(5)
@@ -636,6 +644,21 @@ static int make_row_tmap(CUtensorMap* tm, const float* base, long long R) {
   return 0;
 }
 
+static int make_spill_tmap(CUtensorMap* tm, const uint16_t* base, long long R, int H) {
+  CUtensorMap probe;
+  if (make_row_tmap(&probe, reinterpret_cast<const float*>(base), 1)) return 1;    // resolves the entry point / checks alignment
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+  const cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)R}, strides[1] = {(cuuint64_t)H * 2};
+  const cuuint32_t box[2] = {64, 128}, estr[2] = {1, 1};
+  CUresult r = ((TmapEncodeFn)p)(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<uint16_t*>(base), dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(bf16 side output) failed (%d)", (int)r);
+  return 0;
+}
+
 template <int kMode>
 static int launch_chain(const MlpArgs& a, cudaStream_t s) {   // (one `configured` flag per instantiation)
   static bool configured = false;
@@ -650,6 +673,7 @@ static int launch_chain(const MlpArgs& a, cudaStream_t s) {   // (one `configure
   if (make_row_tmap(&b.tm_x, a.x, a.R)) return 1;
   if (kMode != kBwdA && make_row_tmap(&b.tm_out, a.out, a.R)) return 1;
   if (kMode == kAttn && a.z_out != nullptr && make_row_tmap(&b.tm_z, a.z_out, a.R)) return 1;
+  if (a.spill != nullptr && make_spill_tmap(&b.tm_spill, a.spill, a.R, a.HC * 128)) return 1;
   b.prefetch = opt_get(DG_OPT_L2_PREFETCH) & DG_PF_CHAIN;
   b.prof = g_chain_prof;
   mlp_chain_tc_kernel<kMode><<<grid, kMlpThreads, MlpSmem::total + 1024, s>>>(b);

@@ -189,8 +189,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MlpSmem::bars);
   uint64_t *x_full = bars, *x_empty = bars + 2, *w_full = bars + 4, *w_empty = bars + 6, *hacc_full = bars + 8,
            *hacc_empty = bars + 11, *hb_full = bars + 14, *hb_empty = bars + 16, *z_full = bars + 18, *z_empty = bars + 19,
-           *io_full = bars + 20;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+           *io_full = bars + 20 /* [8]: one per epilogue warp */, *sp_done = bars + 28;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
   long long* sProf = reinterpret_cast<long long*>(smem + MlpSmem::prof);
 
   const float* __restrict__ x = A.x;
@@ -205,11 +205,12 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
     for (int i = 0; i < 2; ++i) {
       mbar_init(&x_full[i], 128); mbar_init(&x_empty[i], 1);
       mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1);
-      mbar_init(&hb_full[i], 8); mbar_init(&hb_empty[i], spill ? 2 : 1);   // + the spill store's read-completion
+      mbar_init(&hb_full[i], 8); mbar_init(&hb_empty[i], 1);
     }
     for (int i = 0; i < 3; ++i) { mbar_init(&hacc_full[i], 1); mbar_init(&hacc_empty[i], 8); }
-    mbar_init(z_full, spill ? 2 : 1); mbar_init(z_empty, 8);     // epilogue barriers: one elected arrival per warp
-    mbar_init(io_full, 1);
+    mbar_init(z_full, 1); mbar_init(z_empty, 8);     // epilogue barriers: one elected arrival per warp
+    for (int i = 0; i < 8; ++i) mbar_init(&io_full[i], 1);
+    mbar_init(sp_done, 8);
     fence_barrier_init();
   }
   if (warp == 12) tmem_alloc(tmem_slot, 512);
@@ -338,24 +339,12 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
           tc_fence_after();
           mma_chunk(smem_u32(sH + hs * kWStage), 384, c == 0);
           umma_commit(&hb_empty[hs]);
-          const int hs_ = hs;
           ++hcount;
           if (c == HC - 1) umma_commit(z_full);      // before the next tile's GEMM1 is even issued: the final epilogue does not wait for it
-          if (spill) {
-            // the bf16 operand block the epilogue just wrote IS the side output (h / dh / scores): TMA-store it from here
-            const int srow0 = (int)((blockIdx.x + ti * gridDim.x) * 128);
-            tma_store_2d(&A.tm_spill, c * 128, srow0, sH + hs_ * kWStage);
-            tma_store_2d(&A.tm_spill, c * 128 + 64, srow0, sH + hs_ * kWStage + kBlkBytes);
-            bulk_commit();
-            bulk_wait_read0();                       // (a few hundred cycles; nothing downstream of this thread is urgent)
-            mbar_arrive(&hb_empty[hs_]);
-            if (c == HC - 1) mbar_arrive(z_full);    // the final epilogue reuses both operand buffers as its I/O tile
-          }
           if (ti + 1 < my_tiles) gemm1(ti + 1, c);
         }
       }
     }
-    if (lane == 0 && spill) bulk_wait0();
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue (warps 0-7)
@@ -442,9 +431,12 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
         }
         if (c == 0 && ti > 0 && kMode != kBwdA) {
           // the previous tile's output left through TMA out of the operand buffers (see the final epilogue): they may be
-          // overwritten once that store has finished READING shared memory
-          if (warp == 0 && lane == 0) bulk_wait_read0();
+          // overwritten once every warp's store has finished READING shared memory
+          if (lane == 0) bulk_wait_read0();
           asm volatile("bar.sync 1, 256;" ::: "memory");
+        } else if (spill) {
+          if (lane == 0) bulk_wait_read1();          // my side-output store out of this buffer (two chunks ago) has been read
+          __syncwarp();
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -452,7 +444,15 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
                          make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]));
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&hb_full[hs]);
+        if (lane == 0) {
+          mbar_arrive(&hb_full[hs]);
+          if (spill) {
+            // the bf16 operand rows this warp just wrote ARE its rows of the side output (h / dh / scores): TMA-store them
+            // from here -- box [32 rows][64 channels], nothing else to wait for
+            tma_store_2d(&A.tm_spill, c * 128 + hf * 64, (int)wrow0, hblk + q * 32 * 128);
+            bulk_commit();
+          }
+        }
         DG_PROF(4)
         ++hcount;
       }
@@ -466,12 +466,17 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
       mbar_wait(z_full, ti & 1);
       DG_PROF(7)
       tc_fence_after();
-      if (warp == 0 && lane == 0) {
-        mbar_expect_tx(io_full, 4 * kBlkBytes);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) tma_load_2d(sH + g * kBlkBytes, &A.tm_x, g * 32, (int)row0, io_full);   // FWD/BWD_A/ATTN: x;  BWD_B: dz
+      if (spill) {                                   // every warp's side-output stores have finished reading the operand buffers
+        if (lane == 0) { bulk_wait_read0(); mbar_arrive(sp_done); }
+        mbar_wait(sp_done, ti & 1);
       }
-      mbar_wait(io_full, ti & 1);
+      uint8_t* ioslab = sH + (2 * hf) * kBlkBytes + q * 32 * 128;     // this warp's rows of its two boxes
+      if (lane == 0) {
+        mbar_expect_tx(&io_full[warp], 2 * 32 * 128);
+        tma_load_2d(ioslab, &A.tm_x, hf * 64, (int)wrow0, &io_full[warp]);            // FWD/BWD_A/ATTN: x;  BWD_B: dz
+        tma_load_2d(ioslab + kBlkBytes, &A.tm_x, hf * 64 + 32, (int)wrow0, &io_full[warp]);
+      }
+      mbar_wait(&io_full[warp], ti & 1);
       uint8_t* iorow = sH + (2 * hf) * kBlkBytes + row * 128;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
@@ -503,14 +508,14 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
           st4(reinterpret_cast<float*>(iorow + (j >> 3) * kBlkBytes + (((j & 7) ^ (row & 7)) << 4)),
               make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]));
         fence_async_smem();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (warp == 0 && lane == 0) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) tma_store_2d(tm, g * 32, (int)row0, sH + g * kBlkBytes);
+        __syncwarp();
+        if (lane == 0) {                             // this warp's rows only: no CTA-wide barrier on the way out
+          tma_store_2d(tm, hf * 64, (int)wrow0, ioslab);
+          tma_store_2d(tm, hf * 64 + 32, (int)wrow0, ioslab + kBlkBytes);
           bulk_commit();
           if (wait_read) bulk_wait_read0();
         }
-        if (wait_read) asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (wait_read) __syncwarp();
       };
       if (kMode == kBwdB) {                                           // dx = dz + dh . W1
         store_tile(&A.tm_out, false);
@@ -602,7 +607,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
       }
       DG_PROF(11)
     }
-    if (kMode != kBwdA && warp == 0 && lane == 0) bulk_wait0();       // outstanding TMA stores complete before the CTA retires
+    if (lane == 0) bulk_wait0();                                      // outstanding TMA stores complete before the CTA retires
     if (kMode == kBwdA && lane < 16) {
 #pragma unroll
       for (int g16 = 0; g16 < 4; ++g16) {
@@ -622,7 +627,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
 
 static long long* g_chain_prof = nullptr;
 
-// [R,128] fp32 row tensor -> tensor map with box [128 rows][32 channels], 128-byte swizzle (driver entry point, no libcuda link)
+// [R,128] fp32 row tensor -> tensor map with box [32 rows][32 channels], 128-byte swizzle (driver entry point, no libcuda link)
 typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -637,7 +642,7 @@ static int make_row_tmap(CUtensorMap* tm, const float* base, long long R) {
   }
   if (reinterpret_cast<uintptr_t>(base) & 15) return fail("TMA row tensors must be 16-byte aligned");
   const cuuint64_t dims[2] = {128, (cuuint64_t)R}, strides[1] = {512};
-  const cuuint32_t box[2] = {32, 128}, estr[2] = {1, 1};
+  const cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};       // one epilogue warp's rows of a 32-channel column group
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -651,7 +656,7 @@ static int make_spill_tmap(CUtensorMap* tm, const uint16_t* base, long long R, i
   cudaDriverEntryPointQueryResult q;
   cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
   const cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)R}, strides[1] = {(cuuint64_t)H * 2};
-  const cuuint32_t box[2] = {64, 128}, estr[2] = {1, 1};
+  const cuuint32_t box[2] = {64, 32}, estr[2] = {1, 1};
   CUresult r = ((TmapEncodeFn)p)(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<uint16_t*>(base), dims, strides, box, estr,
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -68,6 +68,7 @@ struct MlpArgs {
   alignas(64) CUtensorMap tm_x;
   alignas(64) CUtensorMap tm_out;
   alignas(64) CUtensorMap tm_z;
+  alignas(64) CUtensorMap tm_dout;   // BWD_A: the upstream gradient rows
   // the bf16 side output [R,H] (h / dh / the scores): box = [128 rows][64 channels] = one operand block, 128-byte swizzle --
   // it leaves straight out of the GEMM2 operand buffer the epilogue has just filled
   alignas(64) CUtensorMap tm_spill;
@@ -354,7 +355,11 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int row = q * 32 + lane;
     uint32_t hcount = 0;
-    float cs_g[4] = {0.f, 0.f, 0.f, 0.f}, cs_b[4] = {0.f, 0.f, 0.f, 0.f};   // BWD_A: column sums, lane<16 owns col g16*16+lane
+    // BWD_A column sums, kept per lane over all tiles: dgamma -- lane = (4-column chunk lane&3, row group lane>>2) of each
+    // 16-column group; dbeta -- lane = (4-column chunk lane&15 of this warp's 64 columns, row half lane>>4)
+    float4 acc_g[4], acc_b = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc_g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (long long ti = 0; ti < my_tiles; ++ti) {
       const long long row0 = (blockIdx.x + ti * gridDim.x) * 128;
       const long long wrow0 = row0 + q * 32;                          // first global row of this warp
@@ -429,7 +434,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
             v[i + 2] = fmaxf(v[i + 2] + b4.z, 0.f); v[i + 3] = fmaxf(v[i + 3] + b4.w, 0.f);
           }
         }
-        if (c == 0 && ti > 0 && kMode != kBwdA) {
+        if (c == 0 && ti > 0) {
           // the previous tile's output left through TMA out of the operand buffers (see the final epilogue): they may be
           // overwritten once every warp's store has finished READING shared memory
           if (lane == 0) bulk_wait_read0();
@@ -463,6 +468,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
       // tile's last GEMM2 (z_full) until the next tile's first chunk is stored.  A thread reads and later overwrites only
       // its own row halves, so the tile needs no transposition and no bank conflicts (8 consecutive rows = 8 swizzle slots).
       float a[64];
+      float4 xq[kMode == kBwdA ? 16 : 1];
+      if (kMode == kBwdA) gather_issue(x, wrow0, R, 128, hf * 64, 4, lane, xq);   // residual x: in flight across the wait below
       mbar_wait(z_full, ti & 1);
       DG_PROF(7)
       tc_fence_after();
@@ -473,15 +480,23 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
       uint8_t* ioslab = sH + (2 * hf) * kBlkBytes + q * 32 * 128;     // this warp's rows of its two boxes
       if (lane == 0) {
         mbar_expect_tx(&io_full[warp], 2 * 32 * 128);
-        tma_load_2d(ioslab, &A.tm_x, hf * 64, (int)wrow0, &io_full[warp]);            // FWD/BWD_A/ATTN: x;  BWD_B: dz
-        tma_load_2d(ioslab + kBlkBytes, &A.tm_x, hf * 64 + 32, (int)wrow0, &io_full[warp]);
+        const CUtensorMap* tin = kMode == kBwdA ? &A.tm_dout : &A.tm_x;   // FWD/ATTN: residual x;  BWD_B: residual dz;  BWD_A: dout
+        tma_load_2d(ioslab, tin, hf * 64, (int)wrow0, &io_full[warp]);
+        tma_load_2d(ioslab + kBlkBytes, tin, hf * 64 + 32, (int)wrow0, &io_full[warp]);
       }
-      mbar_wait(&io_full[warp], ti & 1);
       uint8_t* iorow = sH + (2 * hf) * kBlkBytes + row * 128;
+      auto io_chunk = [&](int j) -> float* {         // 16-byte chunk j (4 channels) of this thread's row half in the I/O tile
+        return reinterpret_cast<float*>(iorow + (j >> 3) * kBlkBytes + (((j & 7) ^ (row & 7)) << 4));
+      };
+      if (kMode == kBwdA) {
+        gather_finish(xq, 4, stg, lane, a);          // (the dout tile lands meanwhile)
+      } else {
+        mbar_wait(&io_full[warp], ti & 1);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float4 t = ld4(reinterpret_cast<const float*>(iorow + (j >> 3) * kBlkBytes + (((j & 7) ^ (row & 7)) << 4)));
-        a[4 * j] = t.x; a[4 * j + 1] = t.y; a[4 * j + 2] = t.z; a[4 * j + 3] = t.w;
+        for (int j = 0; j < 16; ++j) {
+          const float4 t = ld4(io_chunk(j));
+          a[4 * j] = t.x; a[4 * j + 1] = t.y; a[4 * j + 2] = t.z; a[4 * j + 3] = t.w;
+        }
       }
       DG_PROF(6)
       float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
@@ -504,9 +519,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
       // rows -> the I/O tile (own row, in place) -> one elected thread issues the TMA store of the 4 boxes
       auto store_tile = [&](const CUtensorMap* tm, bool wait_read) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          st4(reinterpret_cast<float*>(iorow + (j >> 3) * kBlkBytes + (((j & 7) ^ (row & 7)) << 4)),
-              make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]));
+        for (int j = 0; j < 16; ++j) st4(io_chunk(j), make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]));
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {                             // this warp's rows only: no CTA-wide barrier on the way out
@@ -548,45 +561,34 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
 #pragma unroll
       for (int i = 0; i < 64; ++i) a[i] = (a[i] - mean) * rstd;      // a := xh
       float sg = 0.f, sgx = 0.f;
+      mbar_wait(&io_full[warp], ti & 1);                              // this warp's dout rows are in the I/O tile
+      // pass 1: row sums of gh and gh*xh; dout*xh goes through the warp's staging tile for the dgamma column sums
 #pragma unroll
       for (int g16 = 0; g16 < 4; ++g16) {
-        float4 dq4[4];
-        float dd[16];
-        gather_issue(A.dout, wrow0, R, 128, hf * 64 + g16 * 16, 1, lane, dq4);
-        // gather_finish, but keep the staged [32 rows][16 cols] block for the column sums
-#pragma unroll
-        for (int it = 0; it < 4; ++it) st4(stg + stg_off(it * 8 + (lane >> 2), lane & 3), dq4[it]);
-        __syncwarp();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          float4 t = ld4(stg + stg_off(lane, i));
-          dd[4 * i] = t.x; dd[4 * i + 1] = t.y; dd[4 * i + 2] = t.z; dd[4 * i + 3] = t.w;
-        }
-        if (lane < 16) {                                              // dbeta: column `lane` of the staged dout block
-          float sb = 0.f;
-#pragma unroll 8
-          for (int r = 0; r < 32; ++r) sb += stg[stg_off(r, lane >> 2) + (lane & 3)];
-          cs_b[g16] += sb;
+          const float4 d4 = ld4(io_chunk(g16 * 4 + i));
+          const float* xh = a + g16 * 16 + 4 * i;
+          const float4 g4 = ld4(gg + g16 * 16 + 4 * i);
+          const float h0 = g4.x * d4.x, h1 = g4.y * d4.y, h2 = g4.z * d4.z, h3 = g4.w * d4.w;
+          sg += (h0 + h1) + (h2 + h3);
+          sgx = fmaf(h0, xh[0], fmaf(h1, xh[1], fmaf(h2, xh[2], fmaf(h3, xh[3], sgx))));
+          st4(stg + stg_off(lane, i), make_float4(d4.x * xh[0], d4.y * xh[1], d4.z * xh[2], d4.w * xh[3]));
         }
         __syncwarp();
-        float px[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float gh = gg[g16 * 16 + i] * dd[i];
-          px[i] = dd[i] * a[g16 * 16 + i];
-          sg += gh;
-          sgx = fmaf(gh, a[g16 * 16 + i], sgx);
+        for (int rr = 0; rr < 4; ++rr) {                              // lane: chunk lane&3, rows (lane>>2)*4 .. +3
+          const float4 t = ld4(stg + stg_off((lane >> 2) * 4 + rr, lane & 3));
+          acc_g[g16].x += t.x; acc_g[g16].y += t.y; acc_g[g16].z += t.z; acc_g[g16].w += t.w;
         }
+        __syncwarp();
+      }
+      // dbeta: column sums of this warp's own dout slab, straight from the tile (lane: chunk lane&15, rows (lane>>4)*16 .. +15)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) st4(stg + stg_off(lane, i), make_float4(px[4 * i], px[4 * i + 1], px[4 * i + 2], px[4 * i + 3]));
-        __syncwarp();
-        if (lane < 16) {                                              // dgamma: column sums of dout * xh
-          float sgm = 0.f;
-#pragma unroll 8
-          for (int r = 0; r < 32; ++r) sgm += stg[stg_off(r, lane >> 2) + (lane & 3)];
-          cs_g[g16] += sgm;
-        }
-        __syncwarp();
+      for (int rr = 0; rr < 16; ++rr) {
+        const int r = (lane >> 4) * 16 + rr, j = lane & 15;
+        const float4 t = ld4(reinterpret_cast<const float*>(ioslab + (j >> 3) * kBlkBytes + r * 128 + (((j & 7) ^ (r & 7)) << 4)));
+        acc_b.x += t.x; acc_b.y += t.y; acc_b.z += t.z; acc_b.w += t.w;
       }
       DG_PROF(10)
       float2* st2 = sStats + (ti & 1) * 512 + 256;
@@ -595,24 +597,40 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
       DG_PROF(9)
       const float2 o2 = st2[(hf ^ 1) * 128 + row];
       const float c1 = (sg + o2.x) * (1.f / 128.f), c2 = (sgx + o2.y) * (1.f / 128.f);
+      // pass 2: dz over dout, in place, then out through TMA
+      __syncwarp();                                                   // (the dbeta readers of this slab are done)
 #pragma unroll
-      for (int g16 = 0; g16 < 4; ++g16) {
-        float4 dq4[4];
-        float dd[16];
-        gather_issue(A.dout, wrow0, R, 128, hf * 64 + g16 * 16, 1, lane, dq4);   // second visit: L2
-        gather_finish(dq4, 1, stg, lane, dd);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) dd[i] = rstd * (gg[g16 * 16 + i] * dd[i] - c1 - a[g16 * 16 + i] * c2);
-        scatter_rows16(A.out, wrow0, R, 128, hf * 64 + g16 * 16, stg, lane, dd);
+      for (int j = 0; j < 16; ++j) {
+        const float4 d4 = ld4(io_chunk(j)), g4 = ld4(gg + 4 * j);
+        st4(io_chunk(j), make_float4(rstd * (g4.x * d4.x - c1 - a[4 * j] * c2), rstd * (g4.y * d4.y - c1 - a[4 * j + 1] * c2),
+                                     rstd * (g4.z * d4.z - c1 - a[4 * j + 2] * c2), rstd * (g4.w * d4.w - c1 - a[4 * j + 3] * c2)));
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&A.tm_out, hf * 64, (int)wrow0, ioslab);
+        tma_store_2d(&A.tm_out, hf * 64 + 32, (int)wrow0, ioslab + kBlkBytes);
+        bulk_commit();
       }
       DG_PROF(11)
     }
     if (lane == 0) bulk_wait0();                                      // outstanding TMA stores complete before the CTA retires
-    if (kMode == kBwdA && lane < 16) {
+    if (kMode == kBwdA) {
 #pragma unroll
-      for (int g16 = 0; g16 < 4; ++g16) {
-        atomicAdd(A.dgamma + hf * 64 + g16 * 16 + lane, cs_g[g16]);
-        atomicAdd(A.dbeta + hf * 64 + g16 * 16 + lane, cs_b[g16]);
+      for (int g16 = 0; g16 < 4; ++g16) {                            // dgamma: fold the 8 row groups (lane>>2), lanes 0-3 flush
+        float v4[4] = {acc_g[g16].x, acc_g[g16].y, acc_g[g16].z, acc_g[g16].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float t = v4[e];
+          t += __shfl_xor_sync(0xffffffffu, t, 4); t += __shfl_xor_sync(0xffffffffu, t, 8); t += __shfl_xor_sync(0xffffffffu, t, 16);
+          if (lane < 4) atomicAdd(A.dgamma + hf * 64 + g16 * 16 + lane * 4 + e, t);
+        }
+      }
+      float b4[4] = {acc_b.x, acc_b.y, acc_b.z, acc_b.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {                                  // dbeta: fold the two row halves, lanes 0-15 flush
+        const float t = b4[e] + __shfl_xor_sync(0xffffffffu, b4[e], 16);
+        if (lane < 16) atomicAdd(A.dbeta + hf * 64 + lane * 4 + e, t);
       }
     }
   }
@@ -676,7 +694,8 @@ static int launch_chain(const MlpArgs& a, cudaStream_t s) {   // (one `configure
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   MlpArgs b = a;
   if (make_row_tmap(&b.tm_x, a.x, a.R)) return 1;
-  if (kMode != kBwdA && make_row_tmap(&b.tm_out, a.out, a.R)) return 1;
+  if (make_row_tmap(&b.tm_out, a.out, a.R)) return 1;
+  if (kMode == kBwdA && make_row_tmap(&b.tm_dout, a.dout, a.R)) return 1;
   if (kMode == kAttn && a.z_out != nullptr && make_row_tmap(&b.tm_z, a.z_out, a.R)) return 1;
   if (a.spill != nullptr && make_spill_tmap(&b.tm_spill, a.spill, a.R, a.HC * 128)) return 1;
   b.prefetch = opt_get(DG_OPT_L2_PREFETCH) & DG_PF_CHAIN;

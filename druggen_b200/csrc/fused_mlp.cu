@@ -373,6 +373,22 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
         const int wcol = (c * 128 + hf * 64) >> 1;
         float4 gq[8];
         if (kMode == kBwdB) gather_issue(reinterpret_cast<const float*>(A.gate), wrow0, R, H >> 1, wcol, 2, lane, gq);
+        // ATTN: q / k rows of the 4 staged rows this lane serves (row r = ((b N + i) N + j) -> q row b N + i, k row b N + j),
+        // and the first 16-channel group of both, requested before the accumulator is waited for
+        unsigned qoff[4], koff[4];                     // element offsets (B N 128 < 2^31)
+        float4 qc[4], kc[4];
+        if (kMode == kAttn) {
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            long long r = wrow0 + it * 8 + (lane >> 2);
+            if (r >= R) r = R - 1;
+            const unsigned n = (unsigned)A.natoms, bi = (unsigned)r / n, jj = (unsigned)r - bi * n;
+            qoff[it] = bi * 128u + hf * 64 + (lane & 3) * 4;
+            koff[it] = ((bi / n) * n + jj) * 128u + hf * 64 + (lane & 3) * 4;
+            qc[it] = __ldg(reinterpret_cast<const float4*>(A.q + qoff[it]));
+            kc[it] = __ldg(reinterpret_cast<const float4*>(A.k + koff[it]));
+          }
+        }
         DG_PROF(0)
         mbar_wait(&hacc_full[c], ti & 1);
         DG_PROF(1)
@@ -410,20 +426,37 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
 #pragma unroll
             for (int g16 = 0; g16 < 4; ++g16) scatter_rows16(A.e_out, wrow0, R, 128, hf * 64 + g16 * 16, stg, lane, v + g16 * 16);
           }
-          long long r = wrow0 + lane;
-          if (r >= R) r = R - 1;
-          const long long bi = r / A.natoms;
-          const long long bj = (bi / A.natoms) * A.natoms + (r - bi * A.natoms);
-          const float* qr = A.q + bi * 128 + hf * 64;      // q_i: shared by the ~N consecutive rows of (b, i) -> L1 broadcast
-          const float* kr = A.k + bj * 128 + hf * 64;      // k_j: N rows of molecule b, L1/L2 resident
+          // S = c q_i k_j is formed on the COALESCED side of the staging transpose (lane = 16 bytes of one of 8 rows: the
+          // k rows of consecutive j are consecutive in memory, the q row is shared by ~N rows), 16 channels at a time, the
+          // next group's loads in flight; a thread-per-row read of k would touch 32 different lines per instruction
           const float cs = A.cscale;
 #pragma unroll
-          for (int i = 0; i < 64; i += 4) {
-            const float4 q4 = __ldg(reinterpret_cast<const float4*>(qr + i)), k4 = __ldg(reinterpret_cast<const float4*>(kr + i));
-            v[i] = q4.x * k4.x * cs * fmaf(v[i], v[i], v[i]);
-            v[i + 1] = q4.y * k4.y * cs * fmaf(v[i + 1], v[i + 1], v[i + 1]);
-            v[i + 2] = q4.z * k4.z * cs * fmaf(v[i + 2], v[i + 2], v[i + 2]);
-            v[i + 3] = q4.w * k4.w * cs * fmaf(v[i + 3], v[i + 3], v[i + 3]);
+          for (int g16 = 0; g16 < 4; ++g16) {
+            float4 qn[4], kn[4];
+            if (g16 < 3) {
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                qn[it] = __ldg(reinterpret_cast<const float4*>(A.q + qoff[it] + (g16 + 1) * 16));
+                kn[it] = __ldg(reinterpret_cast<const float4*>(A.k + koff[it] + (g16 + 1) * 16));
+              }
+            }
+#pragma unroll
+            for (int it = 0; it < 4; ++it)
+              st4(stg + stg_off(it * 8 + (lane >> 2), lane & 3), make_float4(qc[it].x * kc[it].x * cs, qc[it].y * kc[it].y * cs,
+                                                                            qc[it].z * kc[it].z * cs, qc[it].w * kc[it].w * cs));
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 s4 = ld4(stg + stg_off(lane, i));
+              float* vv = v + g16 * 16 + 4 * i;
+              vv[0] = s4.x * fmaf(vv[0], vv[0], vv[0]); vv[1] = s4.y * fmaf(vv[1], vv[1], vv[1]);
+              vv[2] = s4.z * fmaf(vv[2], vv[2], vv[2]); vv[3] = s4.w * fmaf(vv[3], vv[3], vv[3]);
+            }
+            __syncwarp();
+            if (g16 < 3) {
+#pragma unroll
+              for (int it = 0; it < 4; ++it) { qc[it] = qn[it]; kc[it] = kn[it]; }
+            }
           }
         } else {
           const float* bb = sB1 + c * 128 + hf * 64;
@@ -754,6 +787,7 @@ extern "C" int dg_attn_edge_fwd(const float* y, const float* q, const float* k, 
                                 float* out, void* a_bf16, float* e_out, float* z_out, int B, int N, int D, float eps,
                                 void* workspace, long long workspace_bytes, void* stream) {
   if (B <= 0 || N <= 0) return fail("dg_attn_edge_fwd: bad shape B=%d N=%d", B, N);
+  if ((long long)B * N * N >= (1ll << 31) || (long long)B * N * 128 >= (1ll << 31)) return fail("dg_attn_edge_fwd: B*N*N and B*N*128 must be < 2^31 (split the batch)");
   const long long R = (long long)B * N * N;
   if (mlp_check("dg_attn_edge_fwd", y, R, D, 128, workspace, workspace_bytes)) return 1;
   cudaStream_t s = (cudaStream_t)stream;

@@ -116,6 +116,102 @@ def linear(x, w, b, relu: bool = False):
     return y.reshape(*shp[:-1], w.shape[0])
 
 
+# ----------------------------------------------------------------------------- the two-layer MLP as one primitive
+class MLP(Function):
+    """m = fc2(relu(fc1(x) + b1)) + b2   (layers.py:51-53) as ONE twice-differentiable primitive.
+
+    Same arithmetic as two ``Linear`` primitives; what it buys is storage: the hidden activation h and its gradient
+    dh -- the widest tensors of the block ([rows, mlp_ratio*dim]) -- are only ever contraction operands or a sign
+    mask, so with ``narrow`` (tensor-core mode) they live in HBM as bf16, and the ReLU mask is applied in the GEMM
+    epilogue instead of a separate pass.  The gradient penalty's double backward runs on these primitives."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, narrow):
+        h = K.rows_gemm(x, w1, True, b1, relu=True, out_bf16=narrow)
+        ctx.save_for_backward(x, h, w1, b1, w2)
+        ctx.narrow = narrow
+        return K.rows_gemm(h, w2, True, b2)
+
+    @staticmethod
+    def backward(ctx, dm):
+        x, h, w1, b1, w2 = ctx.saved_tensors
+        nx, nw1, nb1, nw2, nb2 = ctx.needs_input_grad[:5]
+        dx, dw1, db1, dw2, db2 = MLPBwd.apply(_c(dm), x, h, w1, b1, w2, ctx.narrow, nx, nw1 or nb1, nw2 or nb2)
+        return dx, dw1, db1, dw2, db2, None
+
+
+class MLPBwd(Function):
+    """(dm, x, h, w1, b1, w2) -> (dx, dW1, db1, dW2, db2):  dh = (dm W2) * (h > 0);  dx = dh W1;  dW1 = dh^T x;  dW2 = dm^T h.
+    Its backward is the hand-derived second order (the mask is piecewise constant):
+      t = u_dx W1^T + x u_dW1^T + u_db1,  tM = t * (h > 0)
+      d/d dm = tM W2^T + h u_dW2^T + u_db2      d/d W2 = dm^T tM       d/d W1 = dh^T u_dx + p^T x
+      d/d x  = dh u_dW1 + p W1                  d/d b1 = colsum(p)      with p = (dm u_dW2) * (h > 0)."""
+
+    @staticmethod
+    def forward(ctx, dm, x, h, w1, b1, w2, narrow, want_x, want_p1, want_p2):
+        ctx.set_materialize_grads(False)
+        dh = K.rows_gemm(dm, w2, False, gate=h, out_bf16=narrow)
+        ctx.save_for_backward(dm, x, h, dh, w1, w2)
+        ctx.narrow = narrow
+        dx = K.rows_gemm(dh, w1, False) if want_x else None
+        dw1 = db1 = dw2 = db2 = None
+        if want_p1:
+            dw1, db1 = torch.zeros_like(w1), torch.zeros_like(b1)
+            K.gemm_tn(dh, x, out=dw1, colsum_a=db1)
+        if want_p2:
+            dw2, db2 = torch.zeros_like(w2), torch.zeros(w2.shape[0], dtype=w2.dtype, device=w2.device)
+            K.gemm_tn(dm, h, out=dw2, colsum_a=db2)
+        return dx, dw1, db1, dw2, db2
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, u_dx, u_dw1, u_db1, u_dw2, u_db2):
+        dm, x, h, dh, w1, w2 = ctx.saved_tensors
+        narrow = ctx.narrow
+        g_dm = g_x = g_w1 = g_b1 = g_w2 = None
+        u_dx, u_dw1, u_dw2 = _c(u_dx), _c(u_dw1), _c(u_dw2)
+        tm = None
+        if u_dx is not None and u_dw1 is None and u_db1 is None:          # the gradient-penalty case: one gated GEMM, narrow
+            tm = K.rows_gemm(u_dx, w1, True, gate=h, out_bf16=narrow)
+        elif u_dx is not None or u_dw1 is not None or u_db1 is not None:
+            t = None
+            for term in (K.rows_gemm(u_dx, w1, True) if u_dx is not None else None,
+                         K.rows_gemm(x, u_dw1, True) if u_dw1 is not None else None, u_db1):
+                if term is not None:
+                    t = term if t is None else t + term
+            if t.dim() == 1:
+                t = t.unsqueeze(0).expand(dm.shape[0], -1)
+            tm = K.gate_mul(t.contiguous(), h.to(t.dtype))
+        if tm is not None:
+            g_dm = K.rows_gemm(tm, w2, True)
+            g_w2 = K.gemm_tn(dm, tm)
+        if u_dx is not None:
+            g_w1 = K.gemm_tn(dh, u_dx)
+        if u_dw1 is not None:
+            g_x = K.rows_gemm(dh, u_dw1, False)
+        if u_dw2 is not None:
+            hu = K.rows_gemm(h, u_dw2, True)
+            g_dm = hu if g_dm is None else g_dm + hu
+            p = K.rows_gemm(dm, u_dw2, False, gate=h, out_bf16=narrow)
+            px = K.rows_gemm(p, w1, False)
+            g_x = px if g_x is None else g_x + px
+            pw = K.gemm_tn(p, x)
+            g_w1 = pw if g_w1 is None else g_w1 + pw
+            g_b1 = K.colsum(p.to(w1.dtype))
+        if u_db2 is not None:
+            ub = u_db2.unsqueeze(0).expand(dm.shape[0], -1)
+            g_dm = ub.contiguous() if g_dm is None else g_dm + ub
+        return g_dm, g_x, None, g_w1, g_b1, g_w2, None, None, None, None
+
+
+def mlp(x, w1, b1, w2, b2):
+    """fc2(relu(fc1(x))) on the last dim; hidden stored as bf16 in the tensor-core mode."""
+    shp = x.shape
+    narrow = K.fused_available(shp[-1], w1.shape[0])
+    y = MLP.apply(x.reshape(-1, shp[-1]), w1, b1, w2, b2, narrow)
+    return y.reshape(*shp[:-1], w2.shape[0])
+
+
 # ----------------------------------------------------------------------------- residual + LayerNorm
 class AddLN(Function):
     """LN(a + b) (b optional) -- the four residual+LayerNorm sites of layers.py:187-192 and ln1."""

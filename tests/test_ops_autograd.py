@@ -55,3 +55,11 @@ def test_modulate():
 
 def test_softmax_agg():
     both(lambda a, v: ops.SoftmaxAgg.apply(a, v), (rnd(2, 3, 3, 4), rnd(2, 3, 4)))
+
+
+def test_mlp_primitive():
+    """the fused two-layer MLP primitive: first and second order incl. the weight / bias cotangent paths"""
+    x, w1, b1, w2, b2 = rnd(5, 6), rnd(8, 6, seed=1), rnd(8, seed=2), rnd(6, 8, seed=3), rnd(6, seed=4)
+    both(lambda x, w1, b1, w2, b2: ops.MLP.apply(x, w1, b1, w2, b2, False), (x, w1, b1, w2, b2))
+    ref = torch.relu(x @ w1.t() + b1) @ w2.t() + b2
+    assert torch.allclose(ops.mlp(x, w1, b1, w2, b2), ref, atol=1e-12)

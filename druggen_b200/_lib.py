@@ -214,13 +214,13 @@ def _attn_scores_fwd(self, q, k, v, e, c, a, g, stats=None):
                _ptr(a), _ptr(g), _ptr(sm), _ptr(si), b, n, d)
 
 
-def _attn_scores_bwd(self, dg, da_in, q, k, v, e, c, de, dq, dk, dv, stats=None):
+def _attn_scores_bwd(self, dg, da_in, q, k, v, e, c, de, dq, dk, dv, stats=None, scores_bf16=False):
     b, n, d = q.shape
     sm, si, g = stats if stats is not None else (None, None, None)
     de16 = de.dtype == torch.bfloat16
     self._call("dg_attn_scores_bwd", ("attn_scores_bwd[fused%s]" % (",de16" if de16 else ""), 0, _nbytes(e, da_in, de), "hbm"), _ptr(dg),
                _ptr(da_in), _ptr(q), _ptr(k), _ptr(v), _ptr(e), c, _ptr(sm), _ptr(si), _ptr(g), _ptr(de), _ptr(dq), _ptr(dk), _ptr(dv),
-               b, n, d, int(de16))
+               b, n, d, int(de16) | (2 if scores_bf16 else 0))
 
 
 def _softmax_agg16_fwd(self, a16, v, g, stats=None):

@@ -189,12 +189,12 @@ def block_backward(x, y, dxo, dyo, params: Sequence[torch.Tensor], heads: int, e
     chain = live_edge and K.attn_chain_available(b, n, d)
     if chain:
         # recompute of the edge half in one tcgen05 kernel; side outputs: E (fp32), the scores (bf16: only ever an
-        # operand) and y + out_e(A) (fp32, what LN4's backward needs); g and the softmax statistics from E in fp32
+        # operand) and y + out_e(A) (fp32, what LN4's backward needs); g and the softmax statistics from the bf16 scores
         y3, a2d, e, z4 = K.attn_edge_fwd(y2d, q, k, p("attn.e.weight"), p("attn.e.bias"), p("attn.out_e.weight"),
                                          p("attn.out_e.bias"), p("ln4.weight"), p("ln4.bias"), c, want_a16=True, want_e=True,
                                          want_z=True)
         a = None
-        _, g, sm_stats = K.attn_scores_fwd(q, k, v, e.view(b, n, n, d), c, want_stats=True, store_a=False)
+        g, sm_stats = K.softmax_agg16_fwd(a2d, v, want_stats=True)     # the same bf16 scores the forward's softmax saw
     else:
         e = K.rows_gemm(y2d, p("attn.e.weight"), True, p("attn.e.bias"))
         a, g, sm_stats = _scores_fwd(q, k, v, e.view(b, n, n, d), c, want_stats=True)
@@ -226,7 +226,7 @@ def block_backward(x, y, dxo, dyo, params: Sequence[torch.Tensor], heads: int, e
     # ---- attention: softmax-aggregate, modulation, q/k/v/e projections
     if h16 and K.attn_fused_available(n, d):
         # de is only ever a contraction operand (dWe, dy): bf16 storage in the tensor-core mode
-        de, dq, dk, dv = K.attn_scores_bwd(dg, da, q, k, v, e.view(b, n, n, d), c, sm_stats, de_bf16=True)
+        de, dq, dk, dv = K.attn_scores_bwd(dg, da, q, k, v, e.view(b, n, n, d), c, sm_stats, de_bf16=True, scores_bf16=chain)
     else:
         de, dq, dk, dv = _scores_bwd(dg, da, a, q, k, v, e.view(b, n, n, d), c, sm_stats)
     del da, a, a2d, e

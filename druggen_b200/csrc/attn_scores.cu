@@ -173,7 +173,9 @@ attn_scores_kernel(const float* __restrict__ dg, const float* __restrict__ da_in
 #define DG_GRAD(chn)                                                              \
   {                                                                               \
     const float phi = ev[u].chn * ev[u].chn + ev[u].chn;                          \
-    const float p = __expf(cq.chn * kj.chn * phi - M.chn) * inv.chn;              \
+    float ar = cq.chn * kj.chn * phi;                                             \
+    if (de_bf16 & 2) ar = __bfloat162float(__float2bfloat16_rn(ar));              \
+    const float p = __expf(ar - M.chn) * inv.chn;                                 \
     const float da = din[u].chn + p * dgi.chn * (vj.chn - g.chn);                 \
     o.chn = da * cq.chn * kj.chn * (2.f * ev[u].chn + 1.f);                       \
     sq.chn = fmaf(da * phi, kj.chn, sq.chn);                                      \
@@ -182,7 +184,7 @@ attn_scores_kernel(const float* __restrict__ dg, const float* __restrict__ da_in
   }
           DG_GRAD(x) DG_GRAD(y) DG_GRAD(z) DG_GRAD(w)
 #undef DG_GRAD
-          if (de_bf16)      // de is only ever a contraction operand (dWe, dy): bf16 storage loses nothing in the tensor-core mode
+          if (de_bf16 & 1)  // de is only ever a contraction operand (dWe, dy): bf16 storage loses nothing in the tensor-core mode
             *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(de) + base + (long long)(j + u) * D) =
                 make_uint2(pack2_bf16(o.x, o.y), pack2_bf16(o.z, o.w));
           else
@@ -214,6 +216,74 @@ attn_scores_kernel(const float* __restrict__ dg, const float* __restrict__ da_in
   }
 }
 
+// Forward, warp per query atom: one warp owns all N key atoms of its (b, i) -- no shared memory, no barrier; lane = 4
+// channels; rows in batches of kFU with the NEXT batch's loads issued before the current batch is reduced (the exp-heavy
+// reduction of one batch covers the latency of the next).  kSrc 0: scores recomputed from e (a_out optional); 1: bf16 a16.
+constexpr int kFU = 4;
+template <int kSrc>
+__global__ void __launch_bounds__(128, 5)
+attn_fwd_warp_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, const float* __restrict__ e,
+                     float c, float* __restrict__ a_out, float* __restrict__ g_out, float* __restrict__ stat_m,
+                     float* __restrict__ stat_inv, int N, int irows, int prefetch) {
+  constexpr int D = 128;
+  const uint16_t* a16 = reinterpret_cast<const uint16_t*>(e);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, b = blockIdx.y;
+  const int ch = lane * 4;
+  const int i0 = blockIdx.x * irows, i1 = min(N, i0 + irows);
+  const float* kb = k + (long long)b * N * D + ch;
+  const float* vb = v + (long long)b * N * D + ch;
+  for (int i = i0 + w; i < i1; i += 4) {
+    const long long bi = ((long long)b * N + i) * D + ch;
+    const long long base = (((long long)b * N + i) * N) * D + ch;
+    if (prefetch && lane == 0 && i + 4 < i1) {       // my next query atom's rows -> L2
+      const long long pb = (((long long)b * N + i + 4) * N) * D;
+      if (kSrc == 1) bulk_prefetch_l2(a16 + pb, (long long)N * D * 2);
+      else bulk_prefetch_l2(e + pb, (long long)N * D * 4);
+    }
+    float4 cq = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kSrc == 0) cq = f4s(ld4(q + bi), c);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), s = make_float4(0.f, 0.f, 0.f, 0.f), acc = s;
+    float4 nx[kFU];                                   // raw rows of the next batch (fp32 e, or bf16 a16 in .x/.y)
+    auto fetch = [&](int j) {
+#pragma unroll
+      for (int u = 0; u < kFU; ++u)
+        if (j + u < N) {
+          if (kSrc == 1) {
+            const uint2 r = *reinterpret_cast<const uint2*>(a16 + base + (long long)(j + u) * D);
+            nx[u].x = __uint_as_float(r.x); nx[u].y = __uint_as_float(r.y);
+          } else {
+            nx[u] = ld4(e + base + (long long)(j + u) * D);
+          }
+        }
+    };
+    fetch(0);
+    for (int j = 0; j < N; j += kFU) {
+      const int n = min(kFU, N - j);
+      float4 av[kFU], vv[kFU];
+#pragma unroll
+      for (int u = 0; u < kFU; ++u)
+        if (u < n) {
+          vv[u] = ld4(vb + (j + u) * D);
+          if (kSrc == 1) {
+            const uint32_t lo = __float_as_uint(nx[u].x), hi = __float_as_uint(nx[u].y);
+            av[u] = make_float4(__uint_as_float(lo << 16), __uint_as_float(lo & 0xFFFF0000u), __uint_as_float(hi << 16),
+                                __uint_as_float(hi & 0xFFFF0000u));
+          } else {
+            const float4 kj = ld4(kb + (j + u) * D), ev = nx[u];
+            av[u] = make_float4(cq.x * kj.x * (ev.x * ev.x + ev.x), cq.y * kj.y * (ev.y * ev.y + ev.y),
+                                cq.z * kj.z * (ev.z * ev.z + ev.z), cq.w * kj.w * (ev.w * ev.w + ev.w));
+            if (a_out != nullptr) st4(a_out + base + (long long)(j + u) * D, av[u]);
+          }
+        }
+      if (j + kFU < N) fetch(j + kFU);
+      DG_ONLINE(x) DG_ONLINE(y) DG_ONLINE(z) DG_ONLINE(w)
+    }
+    const float4 inv = make_float4(1.f / s.x, 1.f / s.y, 1.f / s.z, 1.f / s.w);
+    st4(g_out + bi, make_float4(acc.x * inv.x, acc.y * inv.y, acc.z * inv.z, acc.w * inv.w));
+    if (stat_m != nullptr) { st4(stat_m + bi, m); st4(stat_inv + bi, inv); }
+  }
+}
+
 static int attn_ok(int B, int N, int D) {
   if (B <= 0 || N <= 0) return fail("bad shape B=%d N=%d", B, N);
   if (D != 128) return fail("fused attention-score kernels need D == 128 (got %d)", D);
@@ -238,12 +308,19 @@ extern "C" int dg_attn_scores_fwd(const float* q, const float* k, const float* v
                                   float* g, float* stat_m, float* stat_inv, int B, int N, int D, void* stream) {
   if (attn_ok(B, N, D)) return 1;
   const size_t smem = (size_t)24 * D * 4;
-  const int irows = attn_irows(B, N, 8);
+  const int irows = max(4, attn_irows(B, N, 8));        // one query atom per warp at a time: at least 4 per CTA
   dim3 grid((N + irows - 1) / irows, B);
   if ((stat_m == nullptr) != (stat_inv == nullptr)) return fail("dg_attn_scores_fwd: pass both statistics buffers or neither");
-  attn_scores_kernel<0><<<grid, 128, smem, (cudaStream_t)stream>>>(nullptr, nullptr, q, k, v, e, c, a, g, nullptr, nullptr,
-                                                                    nullptr, nullptr, stat_m, stat_inv, nullptr, N, irows,
+  if (a != nullptr) {       // scores written: the 4-warps-per-query-atom kernel measured faster (0.38 vs 0.43 ms at 1.04 M rows)
+    const int ir = attn_irows(B, N, 8);
+    dim3 g4((N + ir - 1) / ir, B);
+    attn_scores_kernel<0><<<g4, 128, smem, (cudaStream_t)stream>>>(nullptr, nullptr, q, k, v, e, c, a, g, nullptr, nullptr, nullptr, nullptr,
+                                                                    stat_m, stat_inv, nullptr, N, ir,
                                                                     opt_get(DG_OPT_L2_PREFETCH) & DG_PF_ATTN_FWD, 0);
+  } else {
+    attn_fwd_warp_kernel<0><<<grid, 128, 0, (cudaStream_t)stream>>>(q, k, v, e, c, a, g, stat_m, stat_inv, N, irows,
+                                                                     opt_get(DG_OPT_L2_PREFETCH) & DG_PF_ATTN_FWD);
+  }
   return check_launch("dg_attn_scores_fwd");
 }
 
@@ -251,12 +328,12 @@ extern "C" int dg_softmax_agg16_fwd(const void* a_bf16, const float* v, float* g
                                     int D, void* stream) {
   if (attn_ok(B, N, D)) return 1;
   const size_t smem = (size_t)24 * D * 4;
-  const int irows = attn_irows(B, N, 8);
+  const int irows = max(4, attn_irows(B, N, 8));        // one query atom per warp at a time: at least 4 per CTA
   dim3 grid((N + irows - 1) / irows, B);
   if ((stat_m == nullptr) != (stat_inv == nullptr)) return fail("dg_softmax_agg16_fwd: pass both statistics buffers or neither");
-  attn_scores_kernel<2><<<grid, 128, smem, (cudaStream_t)stream>>>(nullptr, nullptr, v, v, v, (const float*)a_bf16, 1.f, nullptr, g,
-                                                                    nullptr, nullptr, nullptr, nullptr, stat_m, stat_inv, nullptr, N,
-                                                                    irows, opt_get(DG_OPT_L2_PREFETCH) & DG_PF_ATTN_FWD, 0);
+  (void)smem;
+  attn_fwd_warp_kernel<1><<<grid, 128, 0, (cudaStream_t)stream>>>(v, v, v, (const float*)a_bf16, 1.f, nullptr, g, stat_m, stat_inv, N, irows,
+                                                                   opt_get(DG_OPT_L2_PREFETCH) & DG_PF_ATTN_FWD);
   return check_launch("dg_softmax_agg16_fwd");
 }
 

@@ -285,14 +285,15 @@ def attn_scores_fwd(q, k, v, e, c: float, want_stats: bool = False, store_a: boo
     return (a, g, stats + (g,)) if want_stats else (a, g)
 
 
-def attn_scores_bwd(dg, da_in, q, k, v, e, c: float, stats=None, de_bf16: bool = False):
+def attn_scores_bwd(dg, da_in, q, k, v, e, c: float, stats=None, de_bf16: bool = False, scores_bf16: bool = False):
     """-> (de, dq, dk, dv) from dg (softmax path) and da_in (out_e path; may be None).  ``stats`` from the forward
-    skips the statistics sweep.  ``de_bf16``: de is stored as bf16 (it is only ever a contraction operand)."""
+    skips the statistics sweep.  ``de_bf16``: de is stored as bf16 (it is only ever a contraction operand).
+    ``scores_bf16``: the statistics were taken from bf16-stored scores (softmax_agg16_fwd); the recomputed scores are rounded alike."""
     _chk(dg, da_in, q, k, v, e)
     de, dq = torch.empty_like(e, dtype=torch.bfloat16 if de_bf16 else e.dtype), torch.empty_like(q)
     dk, dv = torch.zeros_like(k), torch.zeros_like(v)
     if e.numel():
-        _be().attn_scores_bwd(dg, da_in, q, k, v, e, c, de, dq, dk, dv, stats)
+        _be().attn_scores_bwd(dg, da_in, q, k, v, e, c, de, dq, dk, dv, stats, scores_bf16)
     return de, dq, dk, dv
 
 

@@ -116,8 +116,9 @@ int dg_attn_scores_fwd(const float* q, const float* k, const float* v, const flo
 int dg_attn_scores_bwd(const float* dg, const float* da_in, const float* q, const float* k, const float* v,
                        const float* e, float c, const float* stat_m, const float* stat_inv, const float* g,
                        void* de, float* dq, float* dk, float* dv, int B, int N, int D, int de_bf16, void* stream);
-/* (de_bf16 != 0: de is written as bf16 [B,N,N,D] -- it is only ever a contraction operand (dWe, dy), so in the
- * tensor-core mode nothing is lost.)
+/* (de_bf16 bit 0: de is written as bf16 [B,N,N,D] -- it is only ever a contraction operand (dWe, dy), so in the
+ * tensor-core mode nothing is lost.  bit 1: the recomputed scores are rounded to bf16 before the softmax term, matching
+ * statistics that were taken from the bf16 scores of dg_attn_edge_fwd / dg_softmax_agg16_fwd.)
  * g and the statistics from bf16 scores a[B,N,N,D] (the side output of dg_attn_edge_fwd) -- the forward's
  * softmax-aggregate (layers.py:130-134) at 256 B per edge row. */
 int dg_softmax_agg16_fwd(const void* a_bf16, const float* v, float* g, float* stat_m, float* stat_inv, int B, int N,

@@ -162,9 +162,11 @@ class EmulBackend:
             stats[0].copy_(m)
             stats[1].copy_(1.0 / torch.exp(a - m[:, :, None, :]).sum(2))
 
-    def attn_scores_bwd(self, dg, da_in, q, k, v, e, c, de, dq, dk, dv, stats=None):
+    def attn_scores_bwd(self, dg, da_in, q, k, v, e, c, de, dq, dk, dv, stats=None, scores_bf16=False):
         a = torch.empty_like(e)
         self.modulate_fwd(q, k, e, c, a)
+        if scores_bf16:
+            a = _bf16r(a)
         da = torch.empty_like(e)
         self.softmax_agg_bwd(dg, a, v, da, dv)
         if da_in is not None:

@@ -91,6 +91,15 @@ def test_attn_scores_stats_only_and_bf16_de(cuda_dev, B, N):
     de16, dq2, dk2, dv2 = K.attn_scores_bwd(dg, da_in, q, k, v, e, c, stats, de_bf16=True)
     assert de16.dtype == torch.bfloat16 and torch.equal(de16, de.to(torch.bfloat16))
     assert torch.equal(dq, dq2) and rel_l2(dk2, dk) < 1e-6 and rel_l2(dv2, dv) < 1e-6
+    # statistics taken from bf16-stored scores (the chain path): the kernel rounds its recomputed scores alike
+    a16 = a.to(torch.bfloat16)
+    g16, st16 = K.softmax_agg16_fwd(a16.view(-1, D), v, want_stats=True)
+    got = K.attn_scores_bwd(dg, da_in, q, k, v, e, c, st16, scores_bf16=True)
+    d = lambda t: t.double()  # noqa: E731
+    want = [torch.empty_like(d(e)), torch.empty_like(d(q)), torch.zeros_like(d(q)), torch.zeros_like(d(q))]
+    EM.attn_scores_bwd(d(dg), d(da_in), d(q), d(k), d(v), d(e), c, want[0], want[1], want[2], want[3], None, True)
+    for x_, w_ in zip(got, want):
+        assert rel_l2(x_, w_) < 2e-3      # (1-ulp bf16 flips of individual scores between the fp32 kernel and the fp64 emulation)
 
 
 def test_l2_prefetch_option_is_numerically_inert(cuda_dev):

@@ -96,10 +96,11 @@ def block_forward_nograd(x, y, params: Sequence[torch.Tensor], heads: int, edge_
     chain = edge_out and K.attn_chain_available(b, n, d)
     if chain:
         # one tcgen05 kernel: E-projection, modulation, out_e projection, residual, LN4; the scores leave the SM once, as bf16
-        y3, a16, _, _ = K.attn_edge_fwd(y2d, q, k, p("attn.e.weight"), p("attn.e.bias"), p("attn.out_e.weight"),
-                                        p("attn.out_e.bias"), p("ln4.weight"), p("ln4.bias"), c)
-        g = K.softmax_agg16_fwd(a16, v)
-        del a16
+        s16 = K.softmax_scores_bf16()
+        y3, a16, e, _ = K.attn_edge_fwd(y2d, q, k, p("attn.e.weight"), p("attn.e.bias"), p("attn.out_e.weight"),
+                                        p("attn.out_e.bias"), p("ln4.weight"), p("ln4.bias"), c, want_a16=s16, want_e=not s16)
+        g = K.softmax_agg16_fwd(a16, v) if s16 else K.attn_scores_fwd(q, k, v, e.view(b, n, n, d), c, store_a=False)[1]
+        del a16, e
     else:
         e = K.rows_gemm(y2d, p("attn.e.weight"), True, p("attn.e.bias"))
         a, g = _scores_fwd(q, k, v, e.view(b, n, n, d), c)
@@ -194,7 +195,10 @@ def block_backward(x, y, dxo, dyo, params: Sequence[torch.Tensor], heads: int, e
                                          p("attn.out_e.bias"), p("ln4.weight"), p("ln4.bias"), c, want_a16=True, want_e=True,
                                          want_z=True)
         a = None
-        g, sm_stats = K.softmax_agg16_fwd(a2d, v, want_stats=True)     # the same bf16 scores the forward's softmax saw
+        if K.softmax_scores_bf16():
+            g, sm_stats = K.softmax_agg16_fwd(a2d, v, want_stats=True)     # the same bf16 scores the forward's softmax saw
+        else:
+            _, g, sm_stats = K.attn_scores_fwd(q, k, v, e.view(b, n, n, d), c, want_stats=True, store_a=False)
     else:
         e = K.rows_gemm(y2d, p("attn.e.weight"), True, p("attn.e.bias"))
         a, g, sm_stats = _scores_fwd(q, k, v, e.view(b, n, n, d), c, want_stats=True)
@@ -226,7 +230,8 @@ def block_backward(x, y, dxo, dyo, params: Sequence[torch.Tensor], heads: int, e
     # ---- attention: softmax-aggregate, modulation, q/k/v/e projections
     if h16 and K.attn_fused_available(n, d):
         # de is only ever a contraction operand (dWe, dy): bf16 storage in the tensor-core mode
-        de, dq, dk, dv = K.attn_scores_bwd(dg, da, q, k, v, e.view(b, n, n, d), c, sm_stats, de_bf16=True, scores_bf16=chain)
+        de, dq, dk, dv = K.attn_scores_bwd(dg, da, q, k, v, e.view(b, n, n, d), c, sm_stats, de_bf16=True,
+                                           scores_bf16=chain and K.softmax_scores_bf16())
     else:
         de, dq, dk, dv = _scores_bwd(dg, da, a, q, k, v, e.view(b, n, n, d), c, sm_stats)
     del da, a, a2d, e

@@ -303,6 +303,14 @@ def attn_chain_available(b: int, n: int, d: int) -> bool:
     return _precision == "bf16" and d == 128 and n >= 4 and b <= 65535 and os.environ.get("DRUGGEN_B200_ATTN_CHAIN", "1") != "0"
 
 
+def softmax_scores_bf16() -> bool:
+    """Throughput-mode choice for the softmax over key atoms on the fused-chain path: True (default) = its input is the
+    bf16 copy of the scores that the chain kernel spills anyway (256 B per edge row; the exp amplifies the 2^-9 relative
+    rounding to |a| * 2^-9 relative error in each probability); DRUGGEN_B200_SOFTMAX_SCORES=fp32 = the chain spills
+    E in fp32 and the softmax recomputes the scores in fp32 (+~5 % step time), as the non-chain path always does."""
+    return os.environ.get("DRUGGEN_B200_SOFTMAX_SCORES", "bf16") != "fp32"
+
+
 def attn_edge_fwd(y, q, k, we, be, woe, boe, gamma, beta, c: float, want_a16: bool = True, want_e: bool = False,
                   want_z: bool = False, eps: float = 1e-5):
     """y:[B*N*N,128], q,k:[B,N,128] -> (y3 = LN4(y + out_e(A)), a16 | None, e | None, z | None)   (layers.py:116,123-127,188,190).

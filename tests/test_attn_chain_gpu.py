@@ -86,7 +86,8 @@ def test_attn_scores_stats_only_and_bf16_de(cuda_dev, B, N):
     e, dg, da_in = rnd(cuda_dev, B, N, N, D, seed=3), rnd(cuda_dev, B, N, D, seed=4), rnd(cuda_dev, B, N, N, D, seed=5)
     a, g, stats = K.attn_scores_fwd(q, k, v, e, c, want_stats=True)
     a2, g2, stats2 = K.attn_scores_fwd(q, k, v, e, c, want_stats=True, store_a=False)
-    assert a2 is None and torch.equal(g, g2) and torch.equal(stats[0], stats2[0]) and torch.equal(stats[1], stats2[1])
+    # (the stats-only variant is the warp-per-query-atom kernel: same values up to the summation order)
+    assert a2 is None and torch.equal(stats[0], stats2[0]) and rel_l2(g2, g) < 1e-6 and rel_l2(stats2[1], stats[1]) < 1e-6
     de, dq, dk, dv = K.attn_scores_bwd(dg, da_in, q, k, v, e, c, stats)
     de16, dq2, dk2, dv2 = K.attn_scores_bwd(dg, da_in, q, k, v, e, c, stats, de_bf16=True)
     assert de16.dtype == torch.bfloat16 and torch.equal(de16, de.to(torch.bfloat16))
@@ -156,8 +157,9 @@ def _block_params(dev, d=128, r=3, seed=11):
     return out
 
 
+@pytest.mark.parametrize("scores", ["bf16", "fp32"])
 @pytest.mark.parametrize("B,N", [(3, 9), (4, 45)])
-def test_block_chain_vs_unfused_attention(cuda_dev, B, N):
+def test_block_chain_vs_unfused_attention(cuda_dev, B, N, scores):
     """The checkpointed block in the throughput mode with and without the fused edge-attention chain: same function,
     different rounding points (bf16 scores feed the forward's softmax) -> outputs and all gradients agree to bf16 level."""
     d, heads = 128, 8
@@ -167,6 +169,7 @@ def test_block_chain_vs_unfused_attention(cuda_dev, B, N):
 
     def run(chain):
         os.environ["DRUGGEN_B200_ATTN_CHAIN"] = "1" if chain else "0"
+        os.environ["DRUGGEN_B200_SOFTMAX_SCORES"] = scores
         try:
             with K.precision("bf16"):
                 x, y = x0.clone().requires_grad_(True), y0.clone().requires_grad_(True)
@@ -178,6 +181,10 @@ def test_block_chain_vs_unfused_attention(cuda_dev, B, N):
             return [xo.detach(), yo.detach(), xn, yn, x.grad, y.grad] + [p.grad for p in pp]
         finally:
             os.environ.pop("DRUGGEN_B200_ATTN_CHAIN", None)
+            os.environ.pop("DRUGGEN_B200_SOFTMAX_SCORES", None)
     ref, got = run(False), run(True)
+    # N(0,1) edge inputs make heavy-tailed scores (|a| up to ~20): with the softmax fed by bf16-stored scores each
+    # probability carries |a| * 2^-9 relative error -- the bound is looser there than with fp32 scores
+    tol = 4e-2 if scores == "bf16" else 1.5e-2
     for i, (a, b) in enumerate(zip(got, ref)):
-        assert rel_l2(a, b) < 2e-2, (i, rel_l2(a, b))
+        assert rel_l2(a, b) < tol, (i, scores, rel_l2(a, b))

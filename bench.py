@@ -35,10 +35,15 @@ def peaks():
 
 def ncu_traffic(kernel_key, rows):
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-    (profiles/r01_traffic.json, taken at 1 036 800 edge rows), scaled linearly to this run's rows; None if not captured."""
-    try:
-        tab = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-    except Exception:
+    (profiles/r01b_traffic.json, taken at 1 036 800 edge rows), scaled linearly to this run's rows; None if not captured."""
+    tab = None
+    for name in ("r01b_traffic.json", "r01_traffic.json"):         # newest capture first
+        try:
+            tab = json.load(open(os.path.join(ROOT, "profiles", name)))
+            break
+        except Exception:
+            continue
+    if tab is None:
         return None
     import re
     base = re.sub(r"R=\d+,", "", kernel_key)

@@ -53,14 +53,14 @@ def block_forward(x, y, params: Sequence[torch.Tensor], heads: int, edge_out: bo
     g = ops.SoftmaxAgg.apply(a, v)                                           # :130-134
     x3 = ops.add_ln(x1, ops.linear(g, p("attn.out_n.weight"), p("attn.out_n.bias")),
                     p("ln3.weight"), p("ln3.bias"))                          # :135,187,189
-    x_out = ops.add_ln(x3, ops.mlp(x3, p("mlp.fc1.weight"), p("mlp.fc1.bias"), p("mlp.fc2.weight"), p("mlp.fc2.bias")),
-                       p("ln5.weight"), p("ln5.bias"))                       # :51-53,191
+    x_out = ops.add_ln(ops.mlp(x3, p("mlp.fc1.weight"), p("mlp.fc1.bias"), p("mlp.fc2.weight"), p("mlp.fc2.bias"), residual=True),
+                       None, p("ln5.weight"), p("ln5.bias"))                 # :51-53,191 (x3 + mlp(x3): one primitive)
     if not edge_out:
         return x_out, None
     y1 = ops.linear(a, p("attn.out_e.weight"), p("attn.out_e.bias"))         # :127 (pre-softmax scores)
     y3 = ops.add_ln(y, y1, p("ln4.weight"), p("ln4.bias"))                   # :188,190
-    y_out = ops.add_ln(y3, ops.mlp(y3, p("mlp2.fc1.weight"), p("mlp2.fc1.bias"), p("mlp2.fc2.weight"), p("mlp2.fc2.bias")),
-                       p("ln6.weight"), p("ln6.bias"))                       # :192
+    y_out = ops.add_ln(ops.mlp(y3, p("mlp2.fc1.weight"), p("mlp2.fc1.bias"), p("mlp2.fc2.weight"), p("mlp2.fc2.bias"), residual=True),
+                       None, p("ln6.weight"), p("ln6.bias"))                 # :192
     return x_out, y_out
 
 

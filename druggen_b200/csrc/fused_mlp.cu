@@ -521,31 +521,49 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
       auto io_chunk = [&](int j) -> float* {         // 16-byte chunk j (4 channels) of this thread's row half in the I/O tile
         return reinterpret_cast<float*>(iorow + (j >> 3) * kBlkBytes + (((j & 7) ^ (row & 7)) << 4));
       };
+      float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
       if (kMode == kBwdA) {
         gather_finish(xq, 4, stg, lane, a);          // (the dout tile lands meanwhile)
+        DG_PROF(6)
+#pragma unroll
+        for (int cgl = 0; cgl < 2; ++cgl) {
+          float v[32];
+          tmem_ld32(tmem_base + lane_base + 384 + hf * 64 + cgl * 32, v);
+          tmem_ld_wait();
+          if (cgl == 1) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(z_empty); }
+          const float* bb = sB2 + hf * 64 + cgl * 32;
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float t0 = a[cgl * 32 + i] + v[i] + bb[i], t1 = a[cgl * 32 + i + 1] + v[i + 1] + bb[i + 1];
+            a[cgl * 32 + i] = t0; a[cgl * 32 + i + 1] = t1;
+            s1a += t0; s1b += t1; s2a = fmaf(t0, t0, s2a); s2b = fmaf(t1, t1, s2b);
+          }
+        }
       } else {
+        // accumulator (+ bias) into registers while the residual tile is in flight, then the residual on top of it
+        tmem_ld32(tmem_base + lane_base + 384 + hf * 64, a);
+        tmem_ld32(tmem_base + lane_base + 384 + hf * 64 + 32, a + 32);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(z_empty);
+        if (kMode != kBwdB) {
+          const float* bb = sB2 + hf * 64;
+#pragma unroll
+          for (int i = 0; i < 64; i += 4) {
+            const float4 b4 = ld4(bb + i);
+            a[i] += b4.x; a[i + 1] += b4.y; a[i + 2] += b4.z; a[i + 3] += b4.w;
+          }
+        }
         mbar_wait(&io_full[warp], ti & 1);
+        DG_PROF(6)
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float4 t = ld4(io_chunk(j));
-          a[4 * j] = t.x; a[4 * j + 1] = t.y; a[4 * j + 2] = t.z; a[4 * j + 3] = t.w;
-        }
-      }
-      DG_PROF(6)
-      float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-#pragma unroll
-      for (int cgl = 0; cgl < 2; ++cgl) {
-        float v[32];
-        tmem_ld32(tmem_base + lane_base + 384 + hf * 64 + cgl * 32, v);
-        tmem_ld_wait();
-        if (cgl == 1) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(z_empty); }
-        const float* bb = sB2 + hf * 64 + cgl * 32;
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float t0 = a[cgl * 32 + i] + v[i], t1 = a[cgl * 32 + i + 1] + v[i + 1];
-          if (kMode != kBwdB) { t0 += bb[i]; t1 += bb[i + 1]; }
-          a[cgl * 32 + i] = t0; a[cgl * 32 + i + 1] = t1;
-          s1a += t0; s1b += t1; s2a = fmaf(t0, t0, s2a); s2b = fmaf(t1, t1, s2b);
+          const float t0 = a[4 * j] + t.x, t1 = a[4 * j + 1] + t.y, t2 = a[4 * j + 2] + t.z, t3 = a[4 * j + 3] + t.w;
+          a[4 * j] = t0; a[4 * j + 1] = t1; a[4 * j + 2] = t2; a[4 * j + 3] = t3;
+          s1a += t0 + t2; s1b += t1 + t3;
+          s2a = fmaf(t0, t0, fmaf(t2, t2, s2a)); s2b = fmaf(t1, t1, fmaf(t3, t3, s2b));
         }
       }
       DG_PROF(8)

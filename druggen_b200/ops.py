@@ -126,18 +126,18 @@ class MLP(Function):
     epilogue instead of a separate pass.  The gradient penalty's double backward runs on these primitives."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, narrow):
+    def forward(ctx, x, w1, b1, w2, b2, narrow, residual):
         h = K.rows_gemm(x, w1, True, b1, relu=True, out_bf16=narrow)
         ctx.save_for_backward(x, h, w1, b1, w2)
-        ctx.narrow = narrow
-        return K.rows_gemm(h, w2, True, b2)
+        ctx.narrow, ctx.residual = narrow, residual
+        return K.rows_gemm(h, w2, True, b2, resid=x if residual else None)      # residual: x + mlp(x), the add in the store
 
     @staticmethod
     def backward(ctx, dm):
         x, h, w1, b1, w2 = ctx.saved_tensors
         nx, nw1, nb1, nw2, nb2 = ctx.needs_input_grad[:5]
-        dx, dw1, db1, dw2, db2 = MLPBwd.apply(_c(dm), x, h, w1, b1, w2, ctx.narrow, nx, nw1 or nb1, nw2 or nb2)
-        return dx, dw1, db1, dw2, db2, None
+        dx, dw1, db1, dw2, db2 = MLPBwd.apply(_c(dm), x, h, w1, b1, w2, ctx.narrow, ctx.residual, nx, nw1 or nb1, nw2 or nb2)
+        return dx, dw1, db1, dw2, db2, None, None
 
 
 class MLPBwd(Function):
@@ -145,15 +145,16 @@ class MLPBwd(Function):
     Its backward is the hand-derived second order (the mask is piecewise constant):
       t = u_dx W1^T + x u_dW1^T + u_db1,  tM = t * (h > 0)
       d/d dm = tM W2^T + h u_dW2^T + u_db2      d/d W2 = dm^T tM       d/d W1 = dh^T u_dx + p^T x
-      d/d x  = dh u_dW1 + p W1                  d/d b1 = colsum(p)      with p = (dm u_dW2) * (h > 0)."""
+      d/d x  = dh u_dW1 + p W1                  d/d b1 = colsum(p)      with p = (dm u_dW2) * (h > 0).
+    ``residual`` (the primitive computes x + mlp(x)): dx = dm + dh W1 and d/d dm gains u_dx -- both adds ride in a GEMM store."""
 
     @staticmethod
-    def forward(ctx, dm, x, h, w1, b1, w2, narrow, want_x, want_p1, want_p2):
+    def forward(ctx, dm, x, h, w1, b1, w2, narrow, residual, want_x, want_p1, want_p2):
         ctx.set_materialize_grads(False)
         dh = K.rows_gemm(dm, w2, False, gate=h, out_bf16=narrow)
         ctx.save_for_backward(dm, x, h, dh, w1, w2)
-        ctx.narrow = narrow
-        dx = K.rows_gemm(dh, w1, False) if want_x else None
+        ctx.narrow, ctx.residual = narrow, residual
+        dx = K.rows_gemm(dh, w1, False, resid=dm if residual else None) if want_x else None      # residual: dx = dm + dh W1
         dw1 = db1 = dw2 = db2 = None
         if want_p1:
             dw1, db1 = torch.zeros_like(w1), torch.zeros_like(b1)
@@ -182,9 +183,12 @@ class MLPBwd(Function):
             if t.dim() == 1:
                 t = t.unsqueeze(0).expand(dm.shape[0], -1)
             tm = K.gate_mul(t.contiguous(), h.to(t.dtype))
+        res_u = u_dx if ctx.residual else None        # residual form: dx = dm + dh W1  =>  d/d dm += u_dx (added in the store)
         if tm is not None:
-            g_dm = K.rows_gemm(tm, w2, True)
+            g_dm = K.rows_gemm(tm, w2, True, resid=res_u)
             g_w2 = K.gemm_tn(dm, tm)
+        elif res_u is not None:
+            g_dm = res_u
         if u_dx is not None:
             g_w1 = K.gemm_tn(dh, u_dx)
         if u_dw1 is not None:
@@ -201,14 +205,14 @@ class MLPBwd(Function):
         if u_db2 is not None:
             ub = u_db2.unsqueeze(0).expand(dm.shape[0], -1)
             g_dm = ub.contiguous() if g_dm is None else g_dm + ub
-        return g_dm, g_x, None, g_w1, g_b1, g_w2, None, None, None, None
+        return g_dm, g_x, None, g_w1, g_b1, g_w2, None, None, None, None, None
 
 
-def mlp(x, w1, b1, w2, b2):
-    """fc2(relu(fc1(x))) on the last dim; hidden stored as bf16 in the tensor-core mode."""
+def mlp(x, w1, b1, w2, b2, residual: bool = False):
+    """fc2(relu(fc1(x))) (+ x when ``residual``) on the last dim; hidden stored as bf16 in the tensor-core mode."""
     shp = x.shape
     narrow = K.fused_available(shp[-1], w1.shape[0])
-    y = MLP.apply(x.reshape(-1, shp[-1]), w1, b1, w2, b2, narrow)
+    y = MLP.apply(x.reshape(-1, shp[-1]), w1, b1, w2, b2, narrow, residual)
     return y.reshape(*shp[:-1], w2.shape[0])
 
 

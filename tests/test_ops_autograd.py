@@ -60,6 +60,8 @@ def test_softmax_agg():
 def test_mlp_primitive():
     """the fused two-layer MLP primitive: first and second order incl. the weight / bias cotangent paths"""
     x, w1, b1, w2, b2 = rnd(5, 6), rnd(8, 6, seed=1), rnd(8, seed=2), rnd(6, 8, seed=3), rnd(6, seed=4)
-    both(lambda x, w1, b1, w2, b2: ops.MLP.apply(x, w1, b1, w2, b2, False), (x, w1, b1, w2, b2))
+    both(lambda x, w1, b1, w2, b2: ops.MLP.apply(x, w1, b1, w2, b2, False, False), (x, w1, b1, w2, b2))
+    both(lambda x, w1, b1, w2, b2: ops.MLP.apply(x, w1, b1, w2, b2, False, True), (x, w1, b1, w2, b2))      # x + mlp(x)
     ref = torch.relu(x @ w1.t() + b1) @ w2.t() + b2
     assert torch.allclose(ops.mlp(x, w1, b1, w2, b2), ref, atol=1e-12)
+    assert torch.allclose(ops.mlp(x, w1, b1, w2, b2, residual=True), ref + x, atol=1e-12)

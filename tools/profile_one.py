@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Launch each hot-path kernel twice at the bench size (B=512, N=45) so ncu can capture it:
     ncu --set full --clock-control none --import-source on \\
-        -k regex:'mlp_chain|rows_gemm_tc|gemm_tn_tc|attn_scores|add_ln_bwd_kernel|bwd_bwd' -c 13 -o gpurun_out/prof python tools/profile_one.py
+        -k regex:'mlp_chain|rows_gemm_tc|gemm_tn_tc|attn_scores|attn_fwd_warp|add_ln_bwd_kernel|bwd_bwd' -s 18 -c 18 -o gpurun_out/prof python tools/profile_one.py
 """
 import os
 import sys
@@ -38,6 +38,11 @@ with dg.precision("bf16"):
         e4 = x.view(b, n, n, d)
         K.attn_scores_fwd(q, k, v, e4, 0.25)
         K.attn_scores_bwd(dg_, dy.view(b, n, n, d), q, k, v, e4, 0.25)
+        y3, a16, _, _ = K.attn_edge_fwd(x, q, k, wd, b2, wd, b2, gamma, beta, 0.25)            # fused edge attention chain (forward)
+        K.attn_edge_fwd(x, q, k, wd, b2, wd, b2, gamma, beta, 0.25, True, True, True)          # ... with the backward's side outputs
+        _, st = K.softmax_agg16_fwd(a16, v, want_stats=True)                                    # softmax-aggregate from the bf16 scores
+        K.attn_scores_bwd(dg_, dy.view(b, n, n, d), q, k, v, e4, 0.25, st, de_bf16=True, scores_bf16=True)
+        K.rows_gemm(a16, wd, False, resid=dy)                                                    # dgrad with bf16 operand + fused accumulation
         K.modulate_bwd_bwd(q, k, e4, dy.view(b, n, n, d), q, k, e4, 0.25)   # second-order kernels of the gradient penalty
         K.softmax_agg_bwd_bwd(dy.view(b, n, n, d), v, dg_, e4, v)
 torch.cuda.synchronize()

@@ -42,7 +42,7 @@ SIGNATURES = {
 INFO_SYMBOLS = ("dg_abi_version", "dg_last_error", "dg_has_tcgen05", "dg_set_option", "dg_get_option", "dg_debug_chain_profile")
 ABI_VERSION = 2
 OPT_L2_PREFETCH = 0
-PF_ALL, PF_DEFAULT = 63, 12        # DG_PF_* bit masks (include/druggen_b200.h)
+PF_ALL, PF_DEFAULT, PF_CHAIN_KEEP = 63, 12, 64        # DG_PF_* bit masks (include/druggen_b200.h)
 
 _lib = None
 _backend = None

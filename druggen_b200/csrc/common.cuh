@@ -64,5 +64,12 @@ __device__ __forceinline__ void ld8(const float* p, float4& lo, float4& hi) {
       : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
       : "l"(p));
 }
+// same, with the L2 evict_last priority: rows that the same kernel reads again a tile or two later (the residual)
+__device__ __forceinline__ void ld8_keep(const float* p, float4& lo, float4& hi) {
+  asm("ld.global.L2::evict_last.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+      : "l"(p));
+}
+
 
 }  // namespace dg

@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
     for (long long ti = 0; ti < my_tiles; ++ti) {
       const long long row0 = (blockIdx.x + ti * gridDim.x) * 128;
       const int xs = ti & 1;
-      if (A.prefetch && (lt == 0 || lt == 32)) {
+      if ((A.prefetch & 1) && (lt == 0 || lt == 32)) {
         // TMA-engine L2 prefetch of whole (contiguous) row tiles ahead of the register-staged loads:
         // thread 0: the input tiles ti+1, ti+2;  thread 32: what the epilogue gathers for tile ti+1 (dout / bf16 gate)
         for (long long tp = ti + 1; tp <= ti + 2; ++tp) {
@@ -261,7 +261,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
         for (int it = 0; it < 8; ++it) {
           int item = it * 128 + lt, r = item >> 3, j = item & 7;
           if (row0 + r < R) {
-            ld8(x + (row0 + r) * 128 + kb * 64 + j * 8, v[2 * it], v[2 * it + 1]);
+            if (A.prefetch & 2) ld8_keep(x + (row0 + r) * 128 + kb * 64 + j * 8, v[2 * it], v[2 * it + 1]);   // x is re-read as the residual
+            else ld8(x + (row0 + r) * 128 + kb * 64 + j * 8, v[2 * it], v[2 * it + 1]);
           } else {
             v[2 * it] = v[2 * it + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
@@ -749,7 +750,7 @@ static int launch_chain(const MlpArgs& a, cudaStream_t s) {   // (one `configure
   if (kMode == kBwdA && make_row_tmap(&b.tm_dout, a.dout, a.R)) return 1;
   if (kMode == kAttn && a.z_out != nullptr && make_row_tmap(&b.tm_z, a.z_out, a.R)) return 1;
   if (a.spill != nullptr && make_spill_tmap(&b.tm_spill, a.spill, a.R, a.HC * 128)) return 1;
-  b.prefetch = opt_get(DG_OPT_L2_PREFETCH) & DG_PF_CHAIN;
+  b.prefetch = (opt_get(DG_OPT_L2_PREFETCH) & DG_PF_CHAIN) | ((opt_get(DG_OPT_L2_PREFETCH) & DG_PF_CHAIN_KEEP) ? 2 : 0);
   b.prof = g_chain_prof;
   mlp_chain_tc_kernel<kMode><<<grid, kMlpThreads, MlpSmem::total + 1024, s>>>(b);
   return check_launch("dg_mlp_chain");

@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--batch", type=int, default=512)
     ap.add_argument("--atoms", type=int, default=45)
     ap.add_argument("--depth", type=int, default=8)
+    ap.add_argument("--keep-ab", action="store_true", help="time every kernel without / with L2::evict_last on the chain loaders' x reads")
     ap.add_argument("--prefetch-ab", action="store_true", help="time every kernel with the L2-prefetch option off and on")
     args = ap.parse_args()
     try:
@@ -113,7 +114,7 @@ def main():
             ("add_ln_fwd", lambda: K.add_ln_fwd(x, dout, gamma, beta), 3 * r * d * 4, 0.0),
             ("add_ln_bwd", lambda: K.add_ln_bwd(x, dout, None, gamma), 3 * r * d * 4, 0.0),
         ]
-        for pf in ((0, _lib.PF_ALL) if args.prefetch_ab else (_lib.PF_DEFAULT,)):
+        for pf in ((0, _lib.PF_ALL) if args.prefetch_ab else ((_lib.PF_DEFAULT, _lib.PF_DEFAULT | _lib.PF_CHAIN_KEEP) if args.keep_ab else (_lib.PF_DEFAULT,))):
             K.set_option(_lib.OPT_L2_PREFETCH, pf)
             for name, fn, nbytes, flops in benches:
                 report(name, timeit(fn), nbytes, flops, l2_prefetch=pf)

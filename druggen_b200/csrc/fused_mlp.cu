@@ -178,9 +178,15 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
   // 1024-byte alignment as an OFFSET from the __shared__ array: a pointer rebuilt from an integer loses its address
   // space and every access through it compiles to generic LD/ST (LSU long-scoreboard path) instead of LDS/STS
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  // ATTN has ONE hidden chunk and two weight stages in all: its 192 KB of tile buffers are cut differently -- x and the
+  // operand block single-buffered, both weight stages resident, and a DEDICATED 64 KB I/O tile, so the residual rows of a
+  // tile are requested a whole chunk phase before they are needed (in the other modes the I/O tile aliases the two operand
+  // buffers and can only be requested after the tile's last GEMM2: ~3 k cycles of exposed TMA latency per tile)
+  constexpr bool kDedIO = kMode == kAttn;
   uint8_t* sX = smem + MlpSmem::xb;
-  uint8_t* sH = smem + MlpSmem::hb;
-  uint8_t* sW = smem + MlpSmem::wb;
+  uint8_t* sH = smem + (kDedIO ? kWStage : MlpSmem::hb);
+  uint8_t* sW = smem + (kDedIO ? 2 * kWStage : MlpSmem::wb);
+  uint8_t* sIO = kDedIO ? smem + 4 * kWStage : sH;
   float* sStage = reinterpret_cast<float*>(smem + MlpSmem::stage);
   float2* sStats = reinterpret_cast<float2*>(smem + MlpSmem::stats);
   float* sB1 = reinterpret_cast<float*>(smem + MlpSmem::vec);
@@ -237,7 +243,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
     const int lt = tid - 256;
     for (long long ti = 0; ti < my_tiles; ++ti) {
       const long long row0 = (blockIdx.x + ti * gridDim.x) * 128;
-      const int xs = ti & 1;
+      const int xs = kDedIO ? 0 : (ti & 1);
       if ((A.prefetch & 1) && (lt == 0 || lt == 32)) {
         // TMA-engine L2 prefetch of whole (contiguous) row tiles ahead of the register-staged loads:
         // thread 0: the input tiles ti+1, ti+2;  thread 32: what the epilogue gathers for tile ti+1 (dout / bf16 gate)
@@ -251,7 +257,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
         }
       }
       DG_PROF(0)
-      mbar_wait(&x_empty[xs], ((ti >> 1) & 1) ^ 1);
+      mbar_wait(&x_empty[xs], (kDedIO ? (ti & 1) : ((ti >> 1) & 1)) ^ 1);
       DG_PROF(1)
 #pragma unroll 1
       for (int kb = 0; kb < 2; ++kb) {
@@ -289,7 +295,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
         ++wcount;
       };
       for (int c = 0; c < HC; ++c) push(c);                         // GEMM1 of the first tile
-      for (long long ti = 0; ti < my_tiles; ++ti)
+      if (kDedIO) push(1);                                          // ATTN: stage 1 (out_e) into slot 1 -- both stay resident
+      for (long long ti = 0; !kDedIO && ti < my_tiles; ++ti)
         for (int c = 0; c < HC; ++c) {
           push(HC + c);                                             // GEMM2 chunk c of tile ti
           if (ti + 1 < my_tiles) push(c);                           // GEMM1 chunk c of tile ti+1
@@ -302,9 +309,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
       const uint32_t idesc = make_idesc(128, 128, 0, 0);
       uint32_t wcount = 0, hcount = 0;
       auto mma_chunk = [&](uint32_t a_base, uint32_t d_col, bool first_clears) {
-        const int ws = wcount & 1;
+        const int ws = kDedIO ? (d_col == 384 ? 1 : 0) : (wcount & 1);      // ATTN: resident stages, slot = which GEMM
         DG_PROF(0)
-        mbar_wait(&w_full[ws], (wcount >> 1) & 1);
+        mbar_wait(&w_full[ws], kDedIO ? 0 : ((wcount >> 1) & 1));
         DG_PROF(1)
         tc_fence_after();
         const uint32_t b_base = smem_u32(sW + ws * kWStage);
@@ -314,13 +321,13 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
           umma_bf16(tmem_base + d_col, make_sdesc(a_base + off, 16, 1024), make_sdesc(b_base + off, 16, 1024), idesc,
                     (first_clears && kk == 0) ? 0u : 1u);
         }
-        umma_commit(&w_empty[ws]);
+        if (!kDedIO) umma_commit(&w_empty[ws]);
         ++wcount;
       };
       auto gemm1 = [&](long long ti, int c) {
-        const int xs = ti & 1;
+        const int xs = kDedIO ? 0 : (ti & 1);
         DG_PROF(0)
-        if (c == 0) { mbar_wait(&x_full[xs], (ti >> 1) & 1); tc_fence_after(); }
+        if (c == 0) { mbar_wait(&x_full[xs], kDedIO ? (ti & 1) : ((ti >> 1) & 1)); tc_fence_after(); }
         DG_PROF(2)
         mbar_wait(&hacc_empty[c], (ti & 1) ^ 1);
         DG_PROF(3)
@@ -332,9 +339,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
       for (int c = 0; c < HC; ++c) gemm1(0, c);
       for (long long ti = 0; ti < my_tiles; ++ti) {
         for (int c = 0; c < HC; ++c) {
-          const int hs = hcount & 1;
+          const int hs = kDedIO ? 0 : (hcount & 1);
           DG_PROF(0)
-          mbar_wait(&hb_full[hs], (hcount >> 1) & 1);
+          mbar_wait(&hb_full[hs], kDedIO ? (hcount & 1) : ((hcount >> 1) & 1));
           DG_PROF(4)
           if (c == 0) mbar_wait(z_empty, (ti & 1) ^ 1);
           DG_PROF(5)
@@ -364,6 +371,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
     for (long long ti = 0; ti < my_tiles; ++ti) {
       const long long row0 = (blockIdx.x + ti * gridDim.x) * 128;
       const long long wrow0 = row0 + q * 32;                          // first global row of this warp
+      uint8_t* ioslab = sIO + (2 * hf) * kBlkBytes + q * 32 * 128;    // this warp's rows of its two boxes of the I/O tile
       if (kMode == kBwdA && wrow0 + lane < R) {                       // the LayerNorm-backward gathers of dout come from L2
         const float* pd = A.dout + (wrow0 + lane) * 128 + hf * 64;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(pd));
@@ -393,8 +401,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
         DG_PROF(0)
         mbar_wait(&hacc_full[c], ti & 1);
         DG_PROF(1)
-        const int hs = hcount & 1;
-        mbar_wait(&hb_empty[hs], ((hcount >> 1) & 1) ^ 1);
+        const int hs = kDedIO ? 0 : (hcount & 1);
+        mbar_wait(&hb_empty[hs], (kDedIO ? (hcount & 1) : ((hcount >> 1) & 1)) ^ 1);
         DG_PROF(2)
         tc_fence_after();
         uint8_t* hblk = sH + hs * kWStage + hf * kBlkBytes;          // this half's 64 hidden columns = one operand block
@@ -427,6 +435,16 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
 #pragma unroll
             for (int g16 = 0; g16 < 4; ++g16) scatter_rows16(A.e_out, wrow0, R, 128, hf * 64 + g16 * 16, stg, lane, v + g16 * 16);
           }
+          // dedicated I/O tile: this tile's residual rows are requested here -- the previous tile's stores (issued >= 1.5 k
+          // cycles ago) have been read by now, and the rows land while the modulation below runs.  The same wait makes this
+          // warp's operand rows reusable.
+          if (lane == 0) {
+            if (ti > 0) bulk_wait_read0();
+            mbar_expect_tx(&io_full[warp], 2 * 32 * 128);
+            tma_load_2d(ioslab, &A.tm_x, hf * 64, (int)wrow0, &io_full[warp]);
+            tma_load_2d(ioslab + kBlkBytes, &A.tm_x, hf * 64 + 32, (int)wrow0, &io_full[warp]);
+          }
+          __syncwarp();
           // S = c q_i k_j is formed on the COALESCED side of the staging transpose (lane = 16 bytes of one of 8 rows: the
           // k rows of consecutive j are consecutive in memory, the q row is shared by ~N rows), 16 channels at a time, the
           // next group's loads in flight; a thread-per-row read of k would touch 32 different lines per instruction
@@ -468,7 +486,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
             v[i + 2] = fmaxf(v[i + 2] + b4.z, 0.f); v[i + 3] = fmaxf(v[i + 3] + b4.w, 0.f);
           }
         }
-        if (c == 0 && ti > 0) {
+        if (kDedIO) {
+          // (own stores of the previous tile were waited for at the top of the tile; nothing is shared across warps)
+        } else if (c == 0 && ti > 0) {
           // the previous tile's output left through TMA out of the operand buffers (see the final epilogue): they may be
           // overwritten once every warp's store has finished READING shared memory
           if (lane == 0) bulk_wait_read0();
@@ -507,18 +527,17 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
       mbar_wait(z_full, ti & 1);
       DG_PROF(7)
       tc_fence_after();
-      if (spill) {                                   // every warp's side-output stores have finished reading the operand buffers
+      if (spill && !kDedIO) {                        // every warp's side-output stores have finished reading the operand buffers
         if (lane == 0) { bulk_wait_read0(); mbar_arrive(sp_done); }
         mbar_wait(sp_done, ti & 1);
       }
-      uint8_t* ioslab = sH + (2 * hf) * kBlkBytes + q * 32 * 128;     // this warp's rows of its two boxes
-      if (lane == 0) {
+      if (!kDedIO && lane == 0) {
         mbar_expect_tx(&io_full[warp], 2 * 32 * 128);
         const CUtensorMap* tin = kMode == kBwdA ? &A.tm_dout : &A.tm_x;   // FWD/ATTN: residual x;  BWD_B: residual dz;  BWD_A: dout
         tma_load_2d(ioslab, tin, hf * 64, (int)wrow0, &io_full[warp]);
         tma_load_2d(ioslab + kBlkBytes, tin, hf * 64 + 32, (int)wrow0, &io_full[warp]);
       }
-      uint8_t* iorow = sH + (2 * hf) * kBlkBytes + row * 128;
+      uint8_t* iorow = sIO + (2 * hf) * kBlkBytes + row * 128;
       auto io_chunk = [&](int j) -> float* {         // 16-byte chunk j (4 channels) of this thread's row half in the I/O tile
         return reinterpret_cast<float*>(iorow + (j >> 3) * kBlkBytes + (((j & 7) ^ (row & 7)) << 4));
       };

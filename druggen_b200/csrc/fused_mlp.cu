@@ -296,11 +296,16 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
       };
       for (int c = 0; c < HC; ++c) push(c);                         // GEMM1 of the first tile
       if (kDedIO) push(1);                                          // ATTN: stage 1 (out_e) into slot 1 -- both stay resident
-      for (long long ti = 0; !kDedIO && ti < my_tiles; ++ti)
-        for (int c = 0; c < HC; ++c) {
-          push(HC + c);                                             // GEMM2 chunk c of tile ti
-          if (ti + 1 < my_tiles) push(c);                           // GEMM1 chunk c of tile ti+1
-        }
+      // consumption order per tile: GEMM2(0), GEMM1'(0), GEMM2(1..), GEMM1'(1..)  ('= next tile).  With the GEMM2 stages of the
+      // later chunks AHEAD of the next tile's GEMM1 stages, the tile's last GEMM2 finds its weights resident a chunk early
+      // instead of waiting ~2-3 k cycles of TMA latency on the critical path to z_full.
+      for (long long ti = 0; !kDedIO && ti < my_tiles; ++ti) {
+        push(HC);                                                   // GEMM2 chunk 0 of tile ti
+        if (ti + 1 < my_tiles) push(0);                             // GEMM1 chunk 0 of tile ti+1
+        for (int c = 1; c < HC; ++c) push(HC + c);
+        if (ti + 1 < my_tiles)
+          for (int c = 1; c < HC; ++c) push(c);
+      }
     }
     __syncwarp();
   } else if (warp == 12) {
@@ -350,8 +355,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
           umma_commit(&hb_empty[hs]);
           ++hcount;
           if (c == HC - 1) umma_commit(z_full);      // before the next tile's GEMM1 is even issued: the final epilogue does not wait for it
-          if (ti + 1 < my_tiles) gemm1(ti + 1, c);
+          if (c == 0 && ti + 1 < my_tiles) gemm1(ti + 1, 0);
         }
+        if (ti + 1 < my_tiles)
+          for (int c = 1; c < HC; ++c) gemm1(ti + 1, c);
       }
     }
     __syncwarp();

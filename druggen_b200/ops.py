@@ -151,10 +151,13 @@ class MLPBwd(Function):
     @staticmethod
     def forward(ctx, dm, x, h, w1, b1, w2, narrow, residual, want_x, want_p1, want_p2):
         ctx.set_materialize_grads(False)
-        dh = K.rows_gemm(dm, w2, False, gate=h, out_bf16=narrow)
-        ctx.save_for_backward(dm, x, h, dh, w1, w2)
         ctx.narrow, ctx.residual = narrow, residual
-        dx = K.rows_gemm(dh, w1, False, resid=dm if residual else None) if want_x else None      # residual: dx = dm + dh W1
+        if narrow and residual and want_x:          # both GEMMs, the mask and the residual add in ONE tcgen05 chain launch
+            dx, dh = K.mlp_bwd_dgrad(dm, h, w1, w2)
+        else:
+            dh = K.rows_gemm(dm, w2, False, gate=h, out_bf16=narrow)
+            dx = K.rows_gemm(dh, w1, False, resid=dm if residual else None) if want_x else None  # residual: dx = dm + dh W1
+        ctx.save_for_backward(dm, x, h, dh, w1, w2)
         dw1 = db1 = dw2 = db2 = None
         if want_p1:
             dw1, db1 = torch.zeros_like(w1), torch.zeros_like(b1)
@@ -172,7 +175,13 @@ class MLPBwd(Function):
         g_dm = g_x = g_w1 = g_b1 = g_w2 = None
         u_dx, u_dw1, u_dw2 = _c(u_dx), _c(u_dw1), _c(u_dw2)
         tm = None
-        if u_dx is not None and u_dw1 is None and u_db1 is None:          # the gradient-penalty case: one gated GEMM, narrow
+        if u_dx is not None and u_dw1 is None and u_db1 is None and narrow and ctx.residual:
+            # the gradient-penalty case in the tensor-core mode: tM = (u W1^T) * M and d/d dm = u + tM W2^T are the dgrad chain
+            # with the two weights transposed into each other's role -- one launch
+            g_dm, tm = K.mlp_bwd_dgrad(u_dx, h, w2.t().contiguous(), w1.t().contiguous())
+            g_w2 = K.gemm_tn(dm, tm)
+            tm = None
+        elif u_dx is not None and u_dw1 is None and u_db1 is None:        # the gradient-penalty case: one gated GEMM
             tm = K.rows_gemm(u_dx, w1, True, gate=h, out_bf16=narrow)
         elif u_dx is not None or u_dw1 is not None or u_db1 is not None:
             t = None
@@ -187,7 +196,7 @@ class MLPBwd(Function):
         if tm is not None:
             g_dm = K.rows_gemm(tm, w2, True, resid=res_u)
             g_w2 = K.gemm_tn(dm, tm)
-        elif res_u is not None:
+        elif res_u is not None and g_dm is None:
             g_dm = res_u
         if u_dx is not None:
             g_w1 = K.gemm_tn(dh, u_dx)

@@ -196,3 +196,30 @@ def test_fused_branch_wiring_in_throughput_mode():
         assert rel_l2(got[i], ref[i]) < 2e-2, i
     for k in BLOCK_PARAM_NAMES:
         assert rel_l2(got[4][k], ref[4][k]) < 3e-2, k
+
+
+def test_mlp_primitive_chain_wiring():
+    """In the throughput mode the residual MLP primitive runs its first- and second-order backward on the fused dgrad chain
+    (second order with the two weights transposed into each other's role): same gradients as the unfused fp32 primitive up to
+    the bf16 storage of h / dh."""
+    from druggen_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x0 = torch.randn(40, 128, generator=g)
+    w1, b1 = torch.randn(384, 128, generator=g) * 128 ** -0.5, torch.randn(384, generator=g) * 0.1
+    w2, b2 = torch.randn(128, 384, generator=g) * 384 ** -0.5, torch.randn(128, generator=g) * 0.1
+    wgt, u = torch.randn(40, 128, generator=g), torch.randn(40, 128, generator=g)
+
+    def run(narrow):
+        kernels.set_precision("bf16" if narrow else "fp32")
+        x = x0.clone().requires_grad_(True)
+        pp = [t.clone().requires_grad_(True) for t in (w1, b1, w2, b2)]
+        m = ops.MLP.apply(x, pp[0], pp[1], pp[2], pp[3], narrow, True)
+        (dx,) = torch.autograd.grad(m, x, wgt, create_graph=True)            # first order, with a graph (gradient penalty)
+        second = torch.autograd.grad(dx, [x] + pp, u, allow_unused=True)      # second order w.r.t. everything
+        return [m.detach(), dx.detach()] + [t for t in second]
+    ref, got = run(False), run(True)
+    for i, (a, b) in enumerate(zip(got, ref)):
+        if b is None:
+            assert a is None or float(a.abs().max()) == 0.0, i
+        else:
+            assert rel_l2(a, b) < 2e-2, (i, rel_l2(a, b))

@@ -204,11 +204,12 @@ def main():
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (first step also profiles every kernel name to find the dominant one)
-    be.profile_all = True
-    for i in range(args.warmup):
+    # ---- warm-up (one of these steps also times every launch, to find the dominant kernel)
+    prof_step = min(1, args.warmup - 1)       # not the very first step: its lazy initialisations (allocator growth, module
+    for i in range(args.warmup):              # loads) would be billed to whichever launches happen to follow them
+        be.profile_all = i == prof_step
         trainer.step(*resident)
-        if i == 0:
+        if i == prof_step:
             torch.cuda.synchronize()
             table = be.profile_summary()
             first_step_table = {k: {"n": v["n"], "ms": round(v["ms"], 3), "GBps": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1),

@@ -202,7 +202,7 @@ class CudaBackend:
 def _mlp_fwd(self, x, w1, b1, w2, b2, gamma, beta, out, eps, workspace):
     r, d = x.shape
     h = w1.shape[0]
-    meta = (f"mlp_fwd[H={h},fused]", 4 * r * d * h, _nbytes(x, out), "hbm")
+    meta = (f"mlp_fwd[R={r},H={h},fused]", 4 * r * d * h, _nbytes(x, out), "hbm")
     self._call("dg_mlp_fwd", meta, _ptr(x), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(gamma), _ptr(beta), _ptr(out),
                r, d, h, eps, _ptr(workspace), workspace.numel())
 
@@ -242,7 +242,7 @@ def _attn_edge_fwd(self, y, q, k, we, be, woe, boe, gamma, beta, c, out, a16, e_
 def _mlp_bwd_ln(self, x, dout, w1, b1, w2, b2, gamma, dz, h16, dgamma, dbeta, eps, workspace):
     r, d = x.shape
     h = w1.shape[0]
-    meta = (f"mlp_bwd_ln[H={h},fused]", 4 * r * d * h, _nbytes(x, dout, dz, h16), "hbm")
+    meta = (f"mlp_bwd_ln[R={r},H={h},fused]", 4 * r * d * h, _nbytes(x, dout, dz, h16), "hbm")
     self._call("dg_mlp_bwd_ln", meta, _ptr(x), _ptr(dout), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(gamma), _ptr(dz),
                _ptr(h16), _ptr(dgamma), _ptr(dbeta), r, d, h, eps, _ptr(workspace), workspace.numel())
 
@@ -250,7 +250,7 @@ def _mlp_bwd_ln(self, x, dout, w1, b1, w2, b2, gamma, dz, h16, dgamma, dbeta, ep
 def _mlp_bwd_dgrad(self, dz, h16, w1, w2, dx, dh16, workspace):
     r, d = dz.shape
     h = w1.shape[0]
-    meta = (f"mlp_bwd_dgrad[H={h},fused]", 4 * r * d * h, _nbytes(dz, h16, dx, dh16), "hbm")
+    meta = (f"mlp_bwd_dgrad[R={r},H={h},fused]", 4 * r * d * h, _nbytes(dz, h16, dx, dh16), "hbm")
     self._call("dg_mlp_bwd_dgrad", meta, _ptr(dz), _ptr(h16), _ptr(w1), _ptr(w2), _ptr(dx), _ptr(dh16), r, d, h,
                _ptr(workspace), workspace.numel())
 

@@ -205,6 +205,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---- warm-up (one of these steps also times every launch, to find the dominant kernel)
+    first_step_table, dominant = {}, None
     prof_step = min(1, args.warmup - 1)       # not the very first step: its lazy initialisations (allocator growth, module
     for i in range(args.warmup):              # loads) would be billed to whichever launches happen to follow them
         be.profile_all = i == prof_step

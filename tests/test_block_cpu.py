@@ -223,3 +223,30 @@ def test_mlp_primitive_chain_wiring():
             assert a is None or float(a.abs().max()) == 0.0, i
         else:
             assert rel_l2(a, b) < 2e-2, (i, rel_l2(a, b))
+
+
+def test_frozen_discriminator_in_g_step_changes_nothing_that_is_read():
+    """GANTrainer(skip_dead_d_grads=True) freezes D while the G-step graph is built (train.py:371-377 computes D weight
+    gradients that reset_grad, train.py:352, discards).  One full step with and without the freeze: identical losses,
+    identical G and D weights afterwards; with the freeze D.grad is simply never populated by the G-step."""
+    from druggen_b200 import gan
+
+    def run(skip):
+        torch.manual_seed(0)
+        G = dg.Generator("relu", 5, 5, 13, 0.0, dim=32, depth=2, heads=4, mlp_ratio=3)
+        D = dg.Discriminator("relu", 5, 5, 13, 0.0, dim=32, depth=2, heads=4, mlp_ratio=3)
+        tr = gan.GANTrainer(G, D, lr_g=1e-3, lr_d=1e-3, skip_dead_d_grads=skip)
+        a, x = gan.synthetic_molecules(4, 5, 13, 5, seed=7)
+        da, dx = gan.synthetic_molecules(4, 5, 13, 5, seed=8)
+        torch.manual_seed(5)                      # the gradient penalty's eps draws
+        losses = tr.step(da, dx, a, x)
+        d_grads = [p.grad is not None for p in D.parameters()]
+        assert all(p.requires_grad for p in D.parameters())          # the freeze is undone when the G-step graph is built
+        return losses, [p.detach().clone() for p in G.parameters()], [p.detach().clone() for p in D.parameters()], d_grads
+
+    l0, g0, d0, dg0 = run(False)
+    l1, g1, d1, dg1 = run(True)
+    assert l0 == l1
+    for a_, b_ in zip(g0 + d0, g1 + d1):
+        assert torch.equal(a_, b_)
+    assert any(dg0) and not any(dg1)              # reference behaviour leaves dead D grads behind; the freeze leaves none

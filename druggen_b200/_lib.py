@@ -38,6 +38,8 @@ SIGNATURES = {
     "dg_mlp_bwd_ln": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _F, _P, _LL, _P],
     "dg_mlp_bwd_dgrad": [_P, _P, _P, _P, _P, _P, _LL, _I, _I, _P, _LL, _P],
     "dg_mlp_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _F, _P, _LL, _P],
+    "dg_label2onehot": [_P, _I, _P, _LL, _I, _P],
+    "dg_argmax_last": [_P, _P, _LL, _I, _P],
 }
 INFO_SYMBOLS = ("dg_abi_version", "dg_last_error", "dg_has_tcgen05", "dg_set_option", "dg_get_option", "dg_debug_chain_profile")
 ABI_VERSION = 2
@@ -255,6 +257,18 @@ def _mlp_bwd_dgrad(self, dz, h16, w1, w2, dx, dh16, workspace):
                _ptr(workspace), workspace.numel())
 
 
+def _label2onehot(self, labels, out, classes):
+    self._call("dg_label2onehot", ("label2onehot", 0, _nbytes(labels, out), "hbm"), _ptr(labels), labels.element_size(), _ptr(out),
+               labels.numel(), classes)
+
+
+def _argmax_last(self, x, out):
+    c = x.shape[-1]
+    self._call("dg_argmax_last", ("argmax_last", 0, _nbytes(x, out), "hbm"), _ptr(x), _ptr(out), x.numel() // c, c)
+
+
+CudaBackend.label2onehot = _label2onehot
+CudaBackend.argmax_last = _argmax_last
 CudaBackend.mlp_fwd = _mlp_fwd
 CudaBackend.mlp_bwd_ln = _mlp_bwd_ln
 CudaBackend.mlp_bwd_dgrad = _mlp_bwd_dgrad

@@ -343,3 +343,29 @@ def set_option(key: int, value: int) -> None:
     """Process-wide tuning switches of the library (``_lib.OPT_*``)."""
     if _test_backend is None:
         _lib.load().dg_set_option(key, value)
+
+
+# ----------------------------------------------------------------------------- either side of the encoder path
+def label2onehot(labels, dim: int, device=None):
+    """src/data/utils.py:15-23, same signature: integer labels [...] -> fp32 one-hot [..., dim] on the labels' CUDA device
+    (``device`` given: labels are moved there first -- as uint8 this is the 1-byte-per-edge wire format)."""
+    if device is not None:
+        labels = labels.to(device, non_blocking=True)
+    if _test_backend is None and not labels.is_cuda:
+        raise RuntimeError("druggen_b200 kernels run on CUDA tensors only (no CPU fallback)")
+    if labels.dtype not in (torch.int64, torch.uint8):
+        raise RuntimeError(f"label2onehot takes int64 or uint8 labels, got {labels.dtype}")
+    labels = labels.contiguous()
+    out = torch.empty(tuple(labels.shape) + (dim,), dtype=torch.float32, device=labels.device)
+    if labels.numel():
+        _be().label2onehot(labels, out, dim)
+    return out
+
+
+def argmax_last(t):
+    """inference.py:197-198 ``torch.max(t, -1)[1]``: int64 index of the first maximum over the last dim."""
+    _chk(t)
+    out = torch.empty(t.shape[:-1], dtype=torch.int64, device=t.device)
+    if t.numel():
+        _be().argmax_last(t, out)
+    return out

@@ -156,6 +156,15 @@ int dg_attn_edge_fwd(const float* y, const float* q, const float* k, const float
                      float* out, void* a_bf16, float* e_out, float* z_out, int B, int N, int D, float eps,
                      void* workspace, long long workspace_bytes, void* stream);
 
+/* ---- either side of the encoder path ----------------------------------------------------------------- */
+/* src/data/utils.py:15-23 label2onehot: out[n, classes] fp32 = one-hot of labels[n]; labels are int64 (label_bytes 8, what
+ * the reference's to_dense_adj produces) or uint8 (label_bytes 1: a 1-byte-per-edge wire format for the host->device copy).
+ * A label outside [0, classes) gives an all-zero row (torch's scatter_ would raise). */
+int dg_label2onehot(const void* labels, int label_bytes, float* out, long long n, int classes, void* stream);
+/* inference.py:197-198 torch.max(t, -1)[1]: out[rows] int64 = index of the first maximum of each row of x[rows, C]
+ * (a NaN wins; the first NaN), i.e. ATen's CPU result, bit for bit. */
+int dg_argmax_last(const float* x, long long* out, long long rows, int C, void* stream);
+
 /* debug: with a device buffer of 148*64 int64 set, every chain-kernel launch (dg_mlp_*, dg_attn_edge_fwd) writes
  * per-CTA phase cycle counters [CTA][4 roles][16 phases] (tools/chain_profile.py); NULL switches it off. */
 int dg_debug_chain_profile(void* device_buf);

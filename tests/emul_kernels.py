@@ -211,3 +211,10 @@ class EmulBackend:
         if z_out is not None:
             z_out.copy_(z)
         self.add_ln_fwd(z, None, gamma, beta, out, eps)
+
+    def label2onehot(self, labels, out, classes):
+        out.zero_()
+        out.scatter_(out.dim() - 1, labels.long().unsqueeze(-1), 1.0)
+
+    def argmax_last(self, x, out):
+        out.copy_(torch.max(x, -1)[1])

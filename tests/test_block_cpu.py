@@ -250,3 +250,15 @@ def test_frozen_discriminator_in_g_step_changes_nothing_that_is_read():
     for a_, b_ in zip(g0 + d0, g1 + d1):
         assert torch.equal(a_, b_)
     assert any(dg0) and not any(dg1)              # reference behaviour leaves dead D grads behind; the freeze leaves none
+
+
+def test_io_wrappers_on_the_emulation():
+    """label2onehot / argmax_last host wrappers (shapes, dtypes, reference signature) on the CPU emulation"""
+    labels = torch.randint(0, 5, (2, 4, 4))
+    want = torch.zeros(2, 4, 4, 5).scatter_(3, labels.unsqueeze(-1), 1.0)
+    assert torch.equal(dg.label2onehot(labels, 5), want)
+    assert torch.equal(dg.label2onehot(labels.to(torch.uint8), 5), want)
+    with pytest.raises(RuntimeError):
+        dg.label2onehot(labels.float(), 5)
+    t = torch.randn(3, 7, 5)
+    assert torch.equal(dg.argmax_last(t), torch.max(t, -1)[1])

@@ -1,5 +1,5 @@
 // Fused residual-MLP chain of the encoder block (layers.py:41-54 + the residual and LayerNorm of
-// layers.py:191/192) as ONE tcgen05 kernel skeleton with three epilogue personalities:
+// layers.py:191/192) as ONE tcgen05 kernel skeleton with four epilogue personalities:
 //
 //   FWD    out = LayerNorm( x + fc2( relu( fc1(x) + b1 ) ) + b2 ) * gamma + beta
 //   BWD_A  recompute h = relu(fc1(x)+b1), z = x + fc2(h) + b2, then the LayerNorm BACKWARD of `dout`
@@ -11,16 +11,18 @@
 //          "fc1" = We with the modulation as its epilogue, "fc2" = Woe.  Optional side outputs: A as bf16 (operand of the
 //          softmax-aggregate and of dWoe), E fp32 and the pre-LayerNorm sum fp32 (for the backward).
 //
-// All three are "GEMM1 per 128-wide hidden chunk -> per-row epilogue -> bf16 operand block in smem -> GEMM2
+// All four are "GEMM1 per 128-wide hidden chunk -> per-row epilogue -> bf16 operand block in smem -> GEMM2
 // accumulating over chunks -> per-row final epilogue": the 128 x H intermediate never round-trips HBM as
-// fp32 (it is spilled once as bf16 only where the weight gradient needs it).
+// fp32 (it leaves once as bf16 -- TMA-stored straight from the operand block -- only where something downstream needs it).
+// The final epilogue's rows come in (residual / upstream gradient) and go out as 128-byte-swizzled TMA boxes that each
+// epilogue warp loads, rewrites in place and stores for its own 32 rows.
 //
 // Persistent CTA per SM, 448 threads, warp-specialised:
 //   warps 0-7   epilogue : thread = half a row (TMEM lane quarter w&3, column half w>>2)
-//   warps 8-11  loader   : fp32 LDG.128 -> bf16 -> swizzled operand blocks (double-buffered tiles)
+//   warps 8-11  loader   : fp32 LDG.E.256 -> bf16 -> swizzled operand blocks (double-buffered tiles; single in ATTN)
 //   warp  12    MMA      : one thread issues tcgen05.mma; GEMM2 of tile t interleaved with GEMM1 of t+1
 //   warp  13    W loader : one thread streams pre-packed bf16 weight stages (32 KB) with
-//                          cp.async.bulk into a 2-stage ring (weights live in L2: 192 KB per net)
+//                          cp.async.bulk into a 2-stage ring (weights live in L2: 192 KB per net; ATTN: both stages resident)
 // TMEM: columns [0,384) three GEMM1 chunk accumulators, [384,512) the GEMM2 accumulator.
 #include <cuda.h>
 #include "tc_common.cuh"
@@ -118,7 +120,7 @@ __global__ void mlp_pack_weights_kernel(const float* __restrict__ w1, const floa
 }
 
 struct MlpSmem {
-  static constexpr int xb = 0;                          // 2 x 32 KB
+  static constexpr int xb = 0;                          // 2 x 32 KB   (ATTN cuts these 192 KB differently: see kDedIO)
   static constexpr int hb = xb + 2 * kWStage;           // 2 x 32 KB
   static constexpr int wb = hb + 2 * kWStage;           // 2 x 32 KB
   static constexpr int stage = wb + 2 * kWStage;        // 8 warps x 32 x kStgPitch words

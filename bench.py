@@ -149,7 +149,9 @@ def workload_config(args, batch_per_gpu):
     return {"workload": f"DrugGEN-{args.workload} GAN train step (train.py:351-384), Generator+Discriminator, "
                         f"{args.depth} encoder layers, N={args.atoms}, dim {DIM}, heads {HEADS}, mlp_ratio {MLP_RATIO}",
             "batch_per_gpu": batch_per_gpu, "atoms": args.atoms, "depth": args.depth, "precision": args.precision,
-            "parallelism": f"dp{args.gpus}", "l2": "inputs_exceed_l2"}
+            "parallelism": f"dp{args.gpus}", "l2": "inputs_exceed_l2",
+            # train.py:371-377 also fills D's .grad in the G-step; reset_grad (train.py:352) discards it unread
+            "dead_d_wgrads_in_g_step": "computed" if getattr(args, "keep_dead_d_grads", False) else "not launched"}
 
 
 def main():
@@ -166,6 +168,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-table", action="store_true", help="add the per-kernel time table of one warm-up step")
+    ap.add_argument("--keep-dead-d-grads", action="store_true",
+                    help="also launch the Discriminator weight gradients of the G-step that train.py computes and never reads")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -184,7 +188,7 @@ def main():
     n, bsz = args.atoms, args.batch
     G = dg.Generator("relu", n, B_DIM, M_DIM, 0.0, dim=DIM, depth=args.depth, heads=HEADS, mlp_ratio=MLP_RATIO).to(dev)
     D = dg.Discriminator("relu", n, B_DIM, M_DIM, 0.0, dim=DIM, depth=args.depth, heads=HEADS, mlp_ratio=MLP_RATIO).to(dev)
-    trainer = gan.GANTrainer(G, D)
+    trainer = gan.GANTrainer(G, D, skip_dead_d_grads=not args.keep_dead_d_grads)
     torch.manual_seed(1234 + rank)            # per-rank GP eps stream
     mol_a_h, mol_x_h = gan.synthetic_molecules(bsz, n, M_DIM, B_DIM, seed=1 + rank)
     host = [mol_a_h.pin_memory(), mol_x_h.pin_memory()]

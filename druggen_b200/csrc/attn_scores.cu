@@ -57,8 +57,8 @@ __device__ __forceinline__ void combine4(const float* pm, const float* ps, const
   g = A * inv;
 }
 
-// kMode 0: forward from e (a_out optional);  1: backward;  2: forward from the bf16 scores a16 that the fused
-// tcgen05 edge chain (dg_attn_edge_fwd) spilled -- `e` then points at bf16 [B,N,N,128] and nothing is recomputed.
+// kMode 0: forward from e, scores written (a_out);  1: backward.  (The forward variants that do not write the scores --
+// from e, or from the bf16 scores of dg_attn_edge_fwd -- are attn_fwd_warp_kernel below.)
 template <int kMode>
 __global__ void __launch_bounds__(128, 4)
 attn_scores_kernel(const float* __restrict__ dg, const float* __restrict__ da_in, const float* __restrict__ q,
@@ -68,7 +68,6 @@ attn_scores_kernel(const float* __restrict__ dg, const float* __restrict__ da_in
                    const float* __restrict__ g_in, int N, int irows, int prefetch, int de_bf16) {
   constexpr int D = 128;
   constexpr bool kBwd = kMode == 1;
-  const uint16_t* a16 = reinterpret_cast<const uint16_t*>(e);
   extern __shared__ __align__(16) float sm[];
   // forward : red = [2 parity][3 (m,s,acc)][4 warps][128]   (one barrier per query atom)
   // backward: red = [3 (m,s,acc)][4 warps][128] + [4 warps][128] for the dq partials (three barriers per query atom),
@@ -94,8 +93,7 @@ attn_scores_kernel(const float* __restrict__ dg, const float* __restrict__ da_in
     const long long base = (((long long)b * N + i) * N) * D + ch;
     if (prefetch && threadIdx.x == 0 && i + 2 < i1) {     // the rows of query atom i+2 -> L2 (TMA engine; contiguous N rows)
       const long long pb = (((long long)b * N + i + 2) * N) * D;
-      if (kMode == 2) bulk_prefetch_l2(a16 + pb, (long long)N * D * 2);
-      else bulk_prefetch_l2(e + pb, (long long)N * D * 4);
+      bulk_prefetch_l2(e + pb, (long long)N * D * 4);
       if (kBwd && da_in) bulk_prefetch_l2(da_in + pb, (long long)N * D * 4);
     }
     float* rd = kBwd ? red : red + ((i - i0) & 1) * 3 * 4 * D;
@@ -109,19 +107,7 @@ attn_scores_kernel(const float* __restrict__ dg, const float* __restrict__ da_in
     for (int j = jlo; j < jhi; j += kJU) {
       const int n = min(kJU, jhi - j);
       float4 ev[kJU], av[kJU], vv[kJU];
-      if (kMode == 2) {
-        uint2 raw[kJU];
-#pragma unroll
-        for (int u = 0; u < kJU; ++u)
-          if (u < n) raw[u] = *reinterpret_cast<const uint2*>(a16 + base + (long long)(j + u) * D);
-#pragma unroll
-        for (int u = 0; u < kJU; ++u)
-          if (u < n) {
-            vv[u] = ld4(vb + (j + u) * D);
-            av[u] = make_float4(__uint_as_float(raw[u].x << 16), __uint_as_float(raw[u].x & 0xFFFF0000u),
-                                __uint_as_float(raw[u].y << 16), __uint_as_float(raw[u].y & 0xFFFF0000u));
-          }
-      } else {
+      {
 #pragma unroll
       for (int u = 0; u < kJU; ++u)
         if (u < n) ev[u] = ld4(e + base + (long long)(j + u) * D);
@@ -220,6 +206,7 @@ attn_scores_kernel(const float* __restrict__ dg, const float* __restrict__ da_in
 // channels; rows in batches of kFU with the NEXT batch's loads issued before the current batch is reduced (the exp-heavy
 // reduction of one batch covers the latency of the next).  kSrc 0: scores recomputed from e (a_out optional); 1: bf16 a16.
 constexpr int kFU = 4;
+static_assert(kFU == kJU, "DG_ONLINE reduces kJU rows per batch");
 template <int kSrc>
 __global__ void __launch_bounds__(128, 5)
 attn_fwd_warp_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, const float* __restrict__ e,

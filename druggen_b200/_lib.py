@@ -40,9 +40,17 @@ SIGNATURES = {
     "dg_mlp_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _F, _P, _LL, _P],
     "dg_label2onehot": [_P, _I, _P, _LL, _I, _P],
     "dg_argmax_last": [_P, _P, _LL, _I, _P],
+    "dg_embed_labels_fwd": [_P, _I, _P, _P, _LL, _I, _I, _I, _I, _P],
+    "dg_embed_labels_bwd": [_P, _I, _P, _P, _LL, _I, _I, _I, _I, _P],
+    "dg_gp_interp": [_P, _I, _P, _P, _P, _LL, _LL, _I, _P],
+    "dg_gp_penalty": [_P, _P, _P, _P, _P, _I, _LL, _LL, _P],
+    "dg_gp_penalty_bwd": [_P, _P, _P, _P, _I, _LL, _P],
+    "dg_readout_argmax": [_P, _P, _P, _P, _P, _I, _LL, _I, _I, _P],
+    "dg_adamw_flat": [_P, _P, _P, _P, _P, _I, _F, _F, _F, _F, _F, _P],
 }
-INFO_SYMBOLS = ("dg_abi_version", "dg_last_error", "dg_has_tcgen05", "dg_set_option", "dg_get_option", "dg_debug_chain_profile")
-ABI_VERSION = 2
+INFO_SYMBOLS = ("dg_abi_version", "dg_last_error", "dg_has_tcgen05", "dg_set_option", "dg_get_option", "dg_debug_chain_profile",
+                "dg_label_error")
+ABI_VERSION = 3
 OPT_L2_PREFETCH = 0
 PF_ALL, PF_DEFAULT, PF_CHAIN_KEEP = 63, 12, 64        # DG_PF_* bit masks (include/druggen_b200.h)
 
@@ -68,6 +76,7 @@ def load():
         lib.dg_set_option.argtypes, lib.dg_set_option.restype = [_I, _I], _I
         lib.dg_get_option.argtypes, lib.dg_get_option.restype = [_I], _I
         lib.dg_debug_chain_profile.argtypes, lib.dg_debug_chain_profile.restype = [_P], _I
+        lib.dg_label_error.argtypes, lib.dg_label_error.restype = [_I], _I
         if lib.dg_abi_version() != ABI_VERSION:
             raise RuntimeError("libdruggen_b200.so ABI version mismatch")
         if os.environ.get("DRUGGEN_B200_L2_PREFETCH") is not None:       # tuning switch, default on
@@ -94,6 +103,7 @@ class CudaBackend:
     def __init__(self, lib):
         self.lib = lib
         self.launches = 0          # kernel launches issued through this table (bench.py reports it)
+        self.device = None         # device of the tensors of the launch being issued (set by kernels._chk)
         self.profile_all = False
         self.profile_only = None
         self._prof = {}
@@ -106,8 +116,8 @@ class CudaBackend:
         out = {}
         for key, rec in self._prof.items():
             ms = sum(a.elapsed_time(b) for a, b in rec["events"])
-            out[key] = {"key": key, "n": len(rec["events"]), "ms": ms, "bytes": rec["bytes"], "flops": rec["flops"],
-                        "bound": rec["bound"]}
+            out[key] = {"key": key, "n": len(rec["events"]), "ms": ms, "bytes": rec["bytes"], "alg_bytes": rec["alg_bytes"],
+                        "flops": rec["flops"], "bound": rec["bound"]}
         return out
 
     @staticmethod
@@ -116,8 +126,18 @@ class CudaBackend:
 
     def _call(self, name, meta, *args):
         self.launches += 1
-        key, flops, nbytes, bound = meta
+        key, flops, nbytes, bound = meta[:4]
+        alg = meta[4] if len(meta) > 4 else nbytes          # SURVEY 8(d) bytes: the kernel's inputs and outputs, no operand spills
         timed = self.profile_all or (self.profile_only is not None and self.profile_only == key)
+        dev = self.device
+        if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+            # tensors on a device that is not the current one (nn.DataParallel replicas, models on cuda:1 without
+            # set_device): launch there, on that device's current stream
+            with torch.cuda.device(dev):
+                return self._launch(name, key, flops, nbytes, alg, bound, timed, args)
+        return self._launch(name, key, flops, nbytes, alg, bound, timed, args)
+
+    def _launch(self, name, key, flops, nbytes, alg, bound, timed, args):
         stream = torch.cuda.current_stream()
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -127,9 +147,10 @@ class CudaBackend:
             raise RuntimeError(f"{name} rejected: {self.lib.dg_last_error().decode()}")
         if timed:
             e1.record(stream)
-            rec = self._prof.setdefault(key, {"events": [], "bytes": 0, "flops": 0, "bound": bound})
+            rec = self._prof.setdefault(key, {"events": [], "bytes": 0, "alg_bytes": 0, "flops": 0, "bound": bound})
             rec["events"].append((e0, e1))
             rec["bytes"] += nbytes
+            rec["alg_bytes"] += alg
             rec["flops"] += flops
 
     def rows_gemm(self, a, w, w_is_nk, bias, relu, gate, out, prec, resid=None):
@@ -204,7 +225,7 @@ class CudaBackend:
 def _mlp_fwd(self, x, w1, b1, w2, b2, gamma, beta, out, eps, workspace):
     r, d = x.shape
     h = w1.shape[0]
-    meta = (f"mlp_fwd[R={r},H={h},fused]", 4 * r * d * h, _nbytes(x, out), "hbm")
+    meta = (f"mlp_fwd[R={r},H={h},fused]", 4 * r * d * h, _nbytes(x, out), "hbm", _nbytes(x, out))
     self._call("dg_mlp_fwd", meta, _ptr(x), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(gamma), _ptr(beta), _ptr(out),
                r, d, h, eps, _ptr(workspace), workspace.numel())
 
@@ -236,7 +257,7 @@ def _attn_edge_fwd(self, y, q, k, we, be, woe, boe, gamma, beta, c, out, a16, e_
     b, n, d = q.shape
     r = b * n * n
     tag = ("+a16" if a16 is not None else "") + ("+e" if e_out is not None else "") + ("+z" if z_out is not None else "")
-    meta = (f"attn_edge_fwd[fused{tag}]", 4 * r * d * d, _nbytes(y, out, a16, e_out, z_out), "hbm")
+    meta = (f"attn_edge_fwd[fused{tag}]", 4 * r * d * d, _nbytes(y, out, a16, e_out, z_out), "hbm", _nbytes(y, out))
     self._call("dg_attn_edge_fwd", meta, _ptr(y), _ptr(q), _ptr(k), _ptr(we), _ptr(be), _ptr(woe), _ptr(boe), _ptr(gamma), _ptr(beta),
                c, _ptr(out), _ptr(a16), _ptr(e_out), _ptr(z_out), b, n, d, eps, _ptr(workspace), workspace.numel())
 
@@ -244,7 +265,7 @@ def _attn_edge_fwd(self, y, q, k, we, be, woe, boe, gamma, beta, c, out, a16, e_
 def _mlp_bwd_ln(self, x, dout, w1, b1, w2, b2, gamma, dz, h16, dgamma, dbeta, eps, workspace):
     r, d = x.shape
     h = w1.shape[0]
-    meta = (f"mlp_bwd_ln[R={r},H={h},fused]", 4 * r * d * h, _nbytes(x, dout, dz, h16), "hbm")
+    meta = (f"mlp_bwd_ln[R={r},H={h},fused]", 4 * r * d * h, _nbytes(x, dout, dz, h16), "hbm", _nbytes(x, dout, dz))
     self._call("dg_mlp_bwd_ln", meta, _ptr(x), _ptr(dout), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(gamma), _ptr(dz),
                _ptr(h16), _ptr(dgamma), _ptr(dbeta), r, d, h, eps, _ptr(workspace), workspace.numel())
 
@@ -252,7 +273,7 @@ def _mlp_bwd_ln(self, x, dout, w1, b1, w2, b2, gamma, dz, h16, dgamma, dbeta, ep
 def _mlp_bwd_dgrad(self, dz, h16, w1, w2, dx, dh16, workspace):
     r, d = dz.shape
     h = w1.shape[0]
-    meta = (f"mlp_bwd_dgrad[R={r},H={h},fused]", 4 * r * d * h, _nbytes(dz, h16, dx, dh16), "hbm")
+    meta = (f"mlp_bwd_dgrad[R={r},H={h},fused]", 4 * r * d * h, _nbytes(dz, h16, dx, dh16), "hbm", _nbytes(dz, dx))
     self._call("dg_mlp_bwd_dgrad", meta, _ptr(dz), _ptr(h16), _ptr(w1), _ptr(w2), _ptr(dx), _ptr(dh16), r, d, h,
                _ptr(workspace), workspace.numel())
 
@@ -267,6 +288,56 @@ def _argmax_last(self, x, out):
     self._call("dg_argmax_last", ("argmax_last", 0, _nbytes(x, out), "hbm"), _ptr(x), _ptr(out), x.numel() // c, c)
 
 
+def _embed_labels_fwd(self, labels, lut, y, n, sym):
+    self._call("dg_embed_labels_fwd", ("embed_labels_fwd", 0, _nbytes(labels, y), "hbm"), _ptr(labels), labels.element_size(), _ptr(lut),
+               _ptr(y), labels.numel(), n, lut.shape[0], lut.shape[1], int(sym))
+
+
+def _embed_labels_bwd(self, labels, dy, dlut, n, sym):
+    self._call("dg_embed_labels_bwd", ("embed_labels_bwd", 0, _nbytes(labels, dy), "hbm"), _ptr(labels), labels.element_size(), _ptr(dy),
+               _ptr(dlut), labels.numel(), n, dlut.shape[0], dlut.shape[1], int(sym))
+
+
+def _gp_interp(self, labels, fake, eps, out, rows_per_mol):
+    self._call("dg_gp_interp", ("gp_interp", 0, _nbytes(labels, fake, out), "hbm"), _ptr(labels), labels.element_size(), _ptr(fake),
+               _ptr(eps), _ptr(out), labels.numel(), rows_per_mol, fake.shape[-1])
+
+
+def _gp_penalty(self, g_node, g_edge, penalty, coef, scratch):
+    b = g_node.shape[0]
+    self._call("dg_gp_penalty", ("gp_penalty", 0, _nbytes(g_node, g_edge), "hbm"), _ptr(g_node), _ptr(g_edge), _ptr(penalty), _ptr(coef),
+               _ptr(scratch), b, g_node.numel() // b, g_edge.numel() // b)
+
+
+def _gp_penalty_bwd(self, g, coef, upstream, out):
+    b = g.shape[0]
+    self._call("dg_gp_penalty_bwd", ("gp_penalty_bwd", 0, _nbytes(g, out), "hbm"), _ptr(g), _ptr(coef), _ptr(upstream), _ptr(out), b,
+               g.numel() // b)
+
+
+def _readout_argmax(self, x, w, bias, logits, idx):
+    rows = x.numel() // x.shape[-1]
+    self._call("dg_readout_argmax", ("readout_argmax", 2 * rows * x.shape[-1] * w.shape[0], _nbytes(x, logits, idx), "hbm"), _ptr(x), _ptr(w),
+               _ptr(bias), _ptr(logits), _ptr(idx), idx.element_size() if idx is not None else 8, rows, x.shape[-1], w.shape[0])
+
+
+def _adamw_flat(self, p, g, m, v, segs, nseg, lr, beta1, beta2, eps, wd):
+    self._call("dg_adamw_flat", ("adamw_flat", 0, _nbytes(p, g, m, v) + _nbytes(p, m, v), "hbm"), _ptr(p), _ptr(g), _ptr(m), _ptr(v),
+               _ptr(segs), nseg, lr, beta1, beta2, eps, wd)
+
+
+def _label_error(self, clear=True):
+    return self.lib.dg_label_error(int(clear))
+
+
+CudaBackend.embed_labels_fwd = _embed_labels_fwd
+CudaBackend.embed_labels_bwd = _embed_labels_bwd
+CudaBackend.gp_interp = _gp_interp
+CudaBackend.gp_penalty = _gp_penalty
+CudaBackend.gp_penalty_bwd = _gp_penalty_bwd
+CudaBackend.readout_argmax = _readout_argmax
+CudaBackend.adamw_flat = _adamw_flat
+CudaBackend.label_error = _label_error
 CudaBackend.label2onehot = _label2onehot
 CudaBackend.argmax_last = _argmax_last
 CudaBackend.mlp_fwd = _mlp_fwd

@@ -24,15 +24,17 @@ inline int check_launch(const char* what) {
   if (e != cudaSuccess) return fail("%s: %s", what, cudaGetErrorString(e));
   return 0;
 }
-inline int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+inline int sm_count() {           // of the CURRENT device (one process may drive several: nn.DataParallel replicas)
+  static int n[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!n[dev]) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v > 0 ? v : 148;
   }
-  return n;
+  return n[dev];
 }
 
 // ---- run-time options (dg_set_option) --------------------------------------------------------

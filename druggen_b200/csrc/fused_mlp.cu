@@ -763,12 +763,10 @@ static int make_spill_tmap(CUtensorMap* tm, const uint16_t* base, long long R, i
 }
 
 template <int kMode>
-static int launch_chain(const MlpArgs& a, cudaStream_t s) {   // (one `configured` flag per instantiation)
-  static bool configured = false;
-  if (!configured) {
+static int launch_chain(const MlpArgs& a, cudaStream_t s) {
+  {   // per-device attribute: set on every launch so that every device of the process is configured
     cudaError_t e = cudaFuncSetAttribute(mlp_chain_tc_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpSmem::total + 1024);
     if (e != cudaSuccess) return fail("cudaFuncSetAttribute(mlp_chain): %s", cudaGetErrorString(e));
-    configured = true;
   }
   long long tiles = (a.R + 127) / 128;
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());

@@ -554,11 +554,9 @@ int rows_gemm_tc(const void* a_, const float* w, int w_is_nk, const float* bias,
   if (!(flags & DG_OUT_BF16) && (flags & DG_GATE_BF16)) return fail("dg_rows_gemm: a bf16 gate needs a bf16 output");
   if (!(flags & DG_A_BF16) && (reinterpret_cast<uintptr_t>(a) & 31)) return fail("dg_rows_gemm: a must be 32-byte aligned (256-bit loads)");
   const int smem = tc::rows_smem(K, N).total + 1024;
-  static int configured = 0;
-  if (configured < smem) {
+  {   // per-device attribute: set on every launch (a host-side table lookup) so that every device of the process is configured
     cudaError_t e = cudaFuncSetAttribute(tc::rows_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail("cudaFuncSetAttribute(rows_gemm_tc): %s", cudaGetErrorString(e));
-    configured = 227 * 1024;
   }
   long long tiles = (R + 127) / 128;
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
@@ -583,11 +581,9 @@ int gemm_tn_tc(const void* a_, const void* b_, float* out, float* colsum_a, long
   if (stages > 8) stages = 8;
   if (stages < 2) return fail("dg_gemm_tn: shape does not fit shared memory");
   const int smem = stages * stage_bytes + 4 * 32 * tc::kStage * 4 + 256 + 1024;
-  static bool configured = false;
-  if (!configured) {
+  {   // (per-device attribute, see rows_gemm_tc)
     cudaError_t e = cudaFuncSetAttribute(tc::gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail("cudaFuncSetAttribute(gemm_tn_tc): %s", cudaGetErrorString(e));
-    configured = true;
   }
   long long tiles = (R + tc::kTnRows - 1) / tc::kTnRows;
   long long ctas = tiles < sm_count() ? tiles : sm_count();

@@ -1,0 +1,389 @@
+// The callers and data formats either side of the encoder path, all HBM-bound byte / fp32 streaming work:
+//
+//   dg_embed_labels_fwd/bwd : models.py:91-94,196-199 for ONE-HOT inputs.  edge_layers / node_layers applied to a one-hot row
+//                             is a row of a [classes,128] table (computed from the weights by the host, 5 / 13 rows), so the
+//                             prologue + symmetrisation of a label batch is  y_ij = (T[a_ij] + T[a_ji]) / 2  written once from
+//                             1-byte labels (instead of two SIMT sgemms + ReLU + permute + add + div over [B,N,N,128]); the backward
+//                             is a segmented row sum  dT[l] = sum_ij dy_ij ([a_ij = l] + [a_ji = l]) / 2.
+//   dg_gp_interp            : loss.py:21-26  eps * real + (1 - eps) * fake with `real` given as labels (bit-exact with torch's
+//                             three elementwise kernels on the one-hot tensor: no contraction into an FMA).
+//   dg_gp_penalty / _bwd    : loss.py:42-47  per-sample L2 norm over concat(node, edge gradients), mean((|g| - 1)^2), and its
+//                             gradient 2 (|g| - 1) / (B |g|) g.
+//   dg_readout_argmax       : models.py:100-101 + inference.py:197-198  logits = x W^T + b over 5 / 13 classes and their argmax
+//                             (first maximum) in one pass over the [rows,128] stream; labels leave as int64 or uint8.
+//   dg_label2onehot         : src/data/utils.py:15-23 label2onehot from int64 or uint8 (1-byte wire format) labels; a label outside
+//                             [0, classes) raises the device flag dg_label_error() reads (torch's scatter_ raises).
+//   dg_argmax_last          : inference.py:197-198 torch.max(t, -1)[1], first maximum, a NaN wins -- ATen-CPU's result bit for bit.
+//   dg_adamw_flat           : train.py:213-214 torch.optim.AdamW on ONE flat parameter / gradient / moment buffer per network
+//                             (decoupled weight decay, bias correction with a per-tensor step count, tensors without a gradient
+//                             skipped exactly as torch skips `grad is None`).
+#include "common.cuh"
+#include "../../include/druggen_b200.h"
+
+namespace dg {
+
+__device__ int g_label_error = 0;      // set by any kernel that meets a label outside [0, classes); read by dg_label_error()
+
+constexpr int kEmbD = 128;             // channel width of the prologue tables (dim)
+constexpr int kEmbMaxC = 16;           // label classes: 5 bond types, 13 atom types
+
+template <typename L>
+__global__ void __launch_bounds__(256) embed_fwd_kernel(const L* __restrict__ labels, const float* __restrict__ lut,
+                                                        float* __restrict__ y, long long rows, int n, int classes, int sym) {
+  __shared__ __align__(16) float sT[kEmbMaxC * kEmbD];
+  for (int i = threadIdx.x; i < classes * kEmbD; i += blockDim.x) sT[i] = lut[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long nn = (long long)n * n;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    long long l1 = (long long)labels[r], l2 = l1;
+    if (sym) {                                                    // r = (b n + i) n + j  ->  (b n + j) n + i
+      const long long b = r / nn, ij = r - b * nn;
+      const int i = (int)(ij / n), j = (int)(ij - (long long)i * n);
+      l2 = (long long)labels[b * nn + (long long)j * n + i];
+    }
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (l1 < 0 || l1 >= classes || l2 < 0 || l2 >= classes) {
+      if (lane == 0) atomicOr(&g_label_error, 1);
+    } else if (sym) {
+      const float4 a = ld4(sT + l1 * kEmbD + lane * 4), c = ld4(sT + l2 * kEmbD + lane * 4);
+      o = make_float4((a.x + c.x) / 2.f, (a.y + c.y) / 2.f, (a.z + c.z) / 2.f, (a.w + c.w) / 2.f);   // models.py:94, same two roundings
+    } else {
+      o = ld4(sT + l1 * kEmbD + lane * 4);
+    }
+    st4(y + r * kEmbD + lane * 4, o);
+  }
+}
+
+// dT[l] += sum over rows with that label; warp-private shared accumulators (lane owns its 4 channels), one atomic flush per block
+template <typename L>
+__global__ void __launch_bounds__(128) embed_bwd_kernel(const L* __restrict__ labels, const float* __restrict__ dy,
+                                                        float* __restrict__ dlut, long long rows, int n, int classes, int sym) {
+  __shared__ __align__(16) float sAcc[4][kEmbMaxC * kEmbD];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = lane * 4; i < classes * kEmbD; i += 128) st4(&sAcc[warp][i], make_float4(0.f, 0.f, 0.f, 0.f));
+  __syncwarp();
+  const long long warp0 = (long long)blockIdx.x * 4 + warp, nwarps = (long long)gridDim.x * 4;
+  const long long nn = (long long)n * n;
+  const float wgt = sym ? 0.5f : 1.f;
+  for (long long r0 = warp0 * 4; r0 < rows; r0 += nwarps * 4) {        // 4 rows per trip: their loads are all in flight together
+    float4 v[4];
+    int l1[4], l2[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long r = r0 + u;
+      l1[u] = l2[u] = -1;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < rows) {
+        v[u] = ld4(dy + r * kEmbD + lane * 4);
+        long long a = (long long)labels[r], c = a;
+        if (sym) {
+          const long long b = r / nn, ij = r - b * nn;
+          const int i = (int)(ij / n), j = (int)(ij - (long long)i * n);
+          c = (long long)labels[b * nn + (long long)j * n + i];
+        }
+        if (a >= 0 && a < classes && c >= 0 && c < classes) { l1[u] = (int)a; l2[u] = (int)c; }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (l1[u] < 0) continue;
+      float* p = &sAcc[warp][l1[u] * kEmbD + lane * 4];
+      float4 t = ld4(p);
+      t.x += wgt * v[u].x; t.y += wgt * v[u].y; t.z += wgt * v[u].z; t.w += wgt * v[u].w;
+      st4(p, t);
+      if (sym) {
+        p = &sAcc[warp][l2[u] * kEmbD + lane * 4];
+        t = ld4(p);
+        t.x += wgt * v[u].x; t.y += wgt * v[u].y; t.z += wgt * v[u].z; t.w += wgt * v[u].w;
+        st4(p, t);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < classes * kEmbD; i += 128) {
+    const float s = (sAcc[0][i] + sAcc[1][i]) + (sAcc[2][i] + sAcc[3][i]);
+    if (s != 0.f) atomicAdd(dlut + i, s);
+  }
+}
+
+// out[row, c] = eps_b * [label == c] + (1 - eps_b) * fake[row, c]; each product / sum rounded as torch's separate kernels round them
+template <typename L>
+__global__ void gp_interp_kernel(const L* __restrict__ labels, const float* __restrict__ fake, const float* __restrict__ eps,
+                                 float* __restrict__ out, long long total, long long rows_per_mol, int classes) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / classes;
+    const int c = (int)(idx - row * classes);
+    const long long lab = (long long)labels[row];
+    if (c == 0 && (lab < 0 || lab >= classes)) atomicOr(&g_label_error, 1);
+    const float e = eps[row / rows_per_mol];
+    const float real_term = __fmul_rn(e, lab == (long long)c ? 1.f : 0.f);
+    out[idx] = __fadd_rn(real_term, __fmul_rn(__fsub_rn(1.f, e), fake[idx]));
+  }
+}
+
+// per-sample sum of squares over the node and edge gradient rows: one block per molecule
+__global__ void __launch_bounds__(256) gp_sqnorm_kernel(const float* __restrict__ g_node, const float* __restrict__ g_edge,
+                                                        float* __restrict__ sq, long long len_node, long long len_edge) {
+  __shared__ float sred[8];
+  const long long b = blockIdx.x;
+  float s = 0.f;
+  const float* pn = g_node + b * len_node;
+  for (long long i = threadIdx.x; i < len_node; i += 256) s = fmaf(pn[i], pn[i], s);
+  const float* pe = g_edge + b * len_edge;
+  for (long long i = threadIdx.x; i < len_edge; i += 256) s = fmaf(pe[i], pe[i], s);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < 8 ? sred[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) sq[b] = t;
+  }
+}
+
+// penalty = mean_b (sqrt(sq_b) - 1)^2;  coef_b = 2 (|g_b| - 1) / (B |g_b|)   (0 where |g_b| = 0: torch's norm subgradient)
+__global__ void __launch_bounds__(256) gp_finish_kernel(const float* __restrict__ sq, float* __restrict__ penalty,
+                                                        float* __restrict__ coef, int batch) {
+  __shared__ float sred[8];
+  float s = 0.f;
+  for (int b = threadIdx.x; b < batch; b += 256) {
+    const float nrm = sqrtf(sq[b]);
+    const float d = nrm - 1.f;
+    s = fmaf(d, d, s);
+    coef[b] = nrm > 0.f ? 2.f * d / ((float)batch * nrm) : 0.f;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < 8 ? sred[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) penalty[0] = t / (float)batch;
+  }
+}
+
+// out[b, i] = upstream * coef_b * g[b, i]
+__global__ void gp_scale_kernel(const float* __restrict__ g, const float* __restrict__ coef, const float* __restrict__ upstream,
+                                float* __restrict__ out, long long total, long long per_mol) {
+  const float up = upstream[0];
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
+    out[idx] = up * coef[idx / per_mol] * g[idx];
+}
+
+// logits[r, c] = x[r, :] . w[c, :] + b[c]; idx[r] = first maximal c.  8 lanes per row (16 channels each), 4 rows per warp trip.
+template <typename I>
+__global__ void __launch_bounds__(256) readout_argmax_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, float* __restrict__ logits,
+                                                             I* __restrict__ idx_out, long long rows, int classes) {
+  __shared__ __align__(16) float sW[kEmbMaxC * kEmbD];
+  __shared__ float sB[kEmbMaxC];
+  for (int i = threadIdx.x; i < classes * kEmbD; i += blockDim.x) sW[i] = w[i];
+  if (threadIdx.x < classes) sB[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, sub = lane >> 3, part = lane & 7;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r0 = warp0 * 4; r0 < rows; r0 += nwarps * 4) {
+    const long long r = r0 + sub;
+    float4 xv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      xv[u] = r < rows ? ld4(x + r * kEmbD + u * 32 + part * 4) : make_float4(0.f, 0.f, 0.f, 0.f);   // 8 lanes x 16 B contiguous per request
+    float best = 0.f;
+    int bi = 0;
+    for (int c = 0; c < classes; ++c) {
+      float s = 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 wv = ld4(sW + c * kEmbD + u * 32 + part * 4);
+        s = fmaf(xv[u].x, wv.x, fmaf(xv[u].y, wv.y, fmaf(xv[u].z, wv.z, fmaf(xv[u].w, wv.w, s))));
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      s += sB[c];
+      if (part == 0 && r < rows && logits != nullptr) logits[r * classes + c] = s;
+      // strictly greater keeps the FIRST maximum; a NaN beats every number and the first NaN is kept (dg_argmax_last's rule)
+      if (c == 0 || (s > best && best == best) || (s != s && best == best)) { best = s; bi = c; }
+    }
+    if (part == 0 && r < rows && idx_out != nullptr) idx_out[r] = (I)bi;
+  }
+}
+
+// torch.optim.AdamW (single-tensor formulas, applied per element of a flat buffer); seg: per-tensor [begin, end) and step counts
+struct AdamSeg { long long begin, end; float bc1, bc2_sqrt; int active; int pad; };
+__global__ void __launch_bounds__(256) adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                         float* __restrict__ v, const AdamSeg* __restrict__ segs, int nseg,
+                                                         float lr, float beta1, float beta2, float eps, float wd) {
+  // one block per (segment, 4096-element chunk) would need a prefix table; segments are few hundred and tiny, so: blockIdx.y = segment
+  const AdamSeg s = segs[blockIdx.y];
+  if (!s.active) return;
+  const float step_size = lr / s.bc1;
+  for (long long i = s.begin + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < s.end; i += (long long)gridDim.x * blockDim.x) {
+    const float grad = g[i];
+    float param = p[i];
+    param *= 1.f - lr * wd;                                         // decoupled weight decay first (torch _single_tensor_adamw)
+    const float mi = m[i] + (grad - m[i]) * (1.f - beta1);          // exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = v[i] * beta2 + (1.f - beta2) * grad * grad;    // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    const float denom = sqrtf(vi) / s.bc2_sqrt + eps;
+    param -= step_size * (mi / denom);
+    m[i] = mi; v[i] = vi; p[i] = param;
+  }
+}
+
+// src/data/utils.py:15-23  out = zeros(labels.shape + [dim]); out.scatter_(-1, labels.unsqueeze(-1), 1.)
+template <typename L>
+__global__ void onehot_kernel(const L* __restrict__ labels, float* __restrict__ out, long long total, int classes) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / classes;
+    const int c = (int)(idx - row * classes);
+    const long long lab = (long long)labels[row];
+    if (c == 0 && (lab < 0 || lab >= classes)) atomicOr(&g_label_error, 1);   // scatter_ raises: the host turns the flag into an error
+    out[idx] = lab == (long long)c ? 1.f : 0.f;     // consecutive threads: consecutive floats; labels via L1
+  }
+}
+
+// inference.py:197-198  torch.max(t, -1)[1]
+__global__ void argmax_last_kernel(const float* __restrict__ x, long long* __restrict__ out, long long rows, int C) {
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+    const float* p = x + r * C;
+    float best = p[0];
+    int bi = 0;
+    for (int c = 1; c < C; ++c) {
+      const float v = p[c];
+      // strictly greater keeps the FIRST maximum; a NaN beats every number and the first NaN is kept
+      if ((v > best && best == best) || (v != v && best == best)) { best = v; bi = c; }
+    }
+    out[r] = bi;
+  }
+}
+
+static int grid_for(long long work_items, int per_block) {
+  long long blocks = (work_items + per_block - 1) / per_block;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
+}  // namespace dg
+
+using namespace dg;
+
+extern "C" int dg_label_error(int clear) {
+  int v = 0;
+  if (cudaMemcpyFromSymbol(&v, g_label_error, sizeof(int)) != cudaSuccess) {
+    fail("dg_label_error: cannot read the device flag");
+    return -1;
+  }
+  if (v && clear) {
+    const int z = 0;
+    cudaMemcpyToSymbol(g_label_error, &z, sizeof(int));
+  }
+  return v;
+}
+
+static int embed_check(const char* who, long long rows, int n, int classes, int D, int label_bytes, int sym) {
+  if (rows < 0 || n <= 0 || classes <= 0 || classes > kEmbMaxC) return fail("%s: bad shape rows=%lld n=%d classes=%d (classes <= %d)", who, rows, n, classes, kEmbMaxC);
+  if (D != kEmbD) return fail("%s: needs D == 128, got %d", who, D);
+  if (label_bytes != 1 && label_bytes != 8) return fail("%s: labels are uint8 or int64 (label_bytes=%d)", who, label_bytes);
+  if (sym && rows % ((long long)n * n)) return fail("%s: symmetric rows must be a multiple of n*n", who);
+  return 0;
+}
+
+extern "C" int dg_embed_labels_fwd(const void* labels, int label_bytes, const float* lut, float* y, long long rows, int n,
+                                   int classes, int D, int sym, void* stream) {
+  if (embed_check("dg_embed_labels_fwd", rows, n, classes, D, label_bytes, sym)) return 1;
+  if (rows == 0) return 0;
+  const int grid = grid_for(rows, 8 * 4);
+  if (label_bytes == 1)
+    embed_fwd_kernel<unsigned char><<<grid, 256, 0, (cudaStream_t)stream>>>((const unsigned char*)labels, lut, y, rows, n, classes, sym);
+  else
+    embed_fwd_kernel<long long><<<grid, 256, 0, (cudaStream_t)stream>>>((const long long*)labels, lut, y, rows, n, classes, sym);
+  return check_launch("dg_embed_labels_fwd");
+}
+
+extern "C" int dg_embed_labels_bwd(const void* labels, int label_bytes, const float* dy, float* dlut, long long rows, int n,
+                                   int classes, int D, int sym, void* stream) {
+  if (embed_check("dg_embed_labels_bwd", rows, n, classes, D, label_bytes, sym)) return 1;
+  if (rows == 0) return 0;
+  int grid = grid_for(rows, 4 * 4 * 8);
+  if (grid > sm_count() * 4) grid = sm_count() * 4;
+  if (label_bytes == 1)
+    embed_bwd_kernel<unsigned char><<<grid, 128, 0, (cudaStream_t)stream>>>((const unsigned char*)labels, dy, dlut, rows, n, classes, sym);
+  else
+    embed_bwd_kernel<long long><<<grid, 128, 0, (cudaStream_t)stream>>>((const long long*)labels, dy, dlut, rows, n, classes, sym);
+  return check_launch("dg_embed_labels_bwd");
+}
+
+extern "C" int dg_gp_interp(const void* labels, int label_bytes, const float* fake, const float* eps, float* out, long long rows,
+                            long long rows_per_mol, int classes, void* stream) {
+  if (rows < 0 || rows_per_mol <= 0 || classes <= 0 || rows % rows_per_mol) return fail("dg_gp_interp: bad shape rows=%lld rows_per_mol=%lld classes=%d", rows, rows_per_mol, classes);
+  if (label_bytes != 1 && label_bytes != 8) return fail("dg_gp_interp: labels are uint8 or int64 (label_bytes=%d)", label_bytes);
+  if (rows == 0) return 0;
+  const long long total = rows * classes;
+  const int grid = grid_for(total, 256 * 4);
+  if (label_bytes == 1)
+    gp_interp_kernel<unsigned char><<<grid, 256, 0, (cudaStream_t)stream>>>((const unsigned char*)labels, fake, eps, out, total, rows_per_mol, classes);
+  else
+    gp_interp_kernel<long long><<<grid, 256, 0, (cudaStream_t)stream>>>((const long long*)labels, fake, eps, out, total, rows_per_mol, classes);
+  return check_launch("dg_gp_interp");
+}
+
+extern "C" int dg_gp_penalty(const float* g_node, const float* g_edge, float* penalty, float* coef, float* sq_scratch, int batch,
+                             long long len_node, long long len_edge, void* stream) {
+  if (batch <= 0 || len_node < 0 || len_edge < 0) return fail("dg_gp_penalty: bad shape batch=%d", batch);
+  gp_sqnorm_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(g_node, g_edge, sq_scratch, len_node, len_edge);
+  gp_finish_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(sq_scratch, penalty, coef, batch);
+  return check_launch("dg_gp_penalty");
+}
+
+extern "C" int dg_gp_penalty_bwd(const float* g, const float* coef, const float* upstream, float* out, int batch, long long per_mol,
+                                 void* stream) {
+  if (batch <= 0 || per_mol <= 0) return fail("dg_gp_penalty_bwd: bad shape batch=%d per_mol=%lld", batch, per_mol);
+  const long long total = (long long)batch * per_mol;
+  gp_scale_kernel<<<grid_for(total, 256 * 4), 256, 0, (cudaStream_t)stream>>>(g, coef, upstream, out, total, per_mol);
+  return check_launch("dg_gp_penalty_bwd");
+}
+
+extern "C" int dg_readout_argmax(const float* x, const float* w, const float* bias, float* logits, void* idx, int idx_bytes,
+                                 long long rows, int D, int classes, void* stream) {
+  if (rows < 0 || classes <= 0 || classes > kEmbMaxC) return fail("dg_readout_argmax: bad shape rows=%lld classes=%d (classes <= %d)", rows, classes, kEmbMaxC);
+  if (D != kEmbD) return fail("dg_readout_argmax: needs D == 128, got %d", D);
+  if (idx != nullptr && idx_bytes != 1 && idx_bytes != 8) return fail("dg_readout_argmax: indices are uint8 or int64 (idx_bytes=%d)", idx_bytes);
+  if (rows == 0) return 0;
+  const int grid = grid_for(rows, 8 * 4 * 4);
+  if (idx_bytes == 1)
+    readout_argmax_kernel<unsigned char><<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, bias, logits, (unsigned char*)idx, rows, classes);
+  else
+    readout_argmax_kernel<long long><<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, bias, logits, (long long*)idx, rows, classes);
+  return check_launch("dg_readout_argmax");
+}
+
+extern "C" int dg_adamw_flat(float* p, const float* g, float* m, float* v, const void* segs, int nseg, float lr, float beta1,
+                             float beta2, float eps, float weight_decay, void* stream) {
+  if (nseg <= 0 || nseg > 65535) return fail("dg_adamw_flat: segments must be in [1, 65535], got %d", nseg);
+  dim3 grid(8, nseg);
+  adamw_flat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (const AdamSeg*)segs, nseg, lr, beta1, beta2, eps, weight_decay);
+  return check_launch("dg_adamw_flat");
+}
+
+extern "C" int dg_label2onehot(const void* labels, int label_bytes, float* out, long long n, int classes, void* stream) {
+  if (n < 0 || classes <= 0) return fail("dg_label2onehot: bad shape n=%lld classes=%d", n, classes);
+  if (label_bytes != 1 && label_bytes != 8) return fail("dg_label2onehot: labels are uint8 or int64 (label_bytes=%d)", label_bytes);
+  if (n == 0) return 0;
+  const long long total = n * classes;
+  const int grid = grid_for(total, 256);
+  if (label_bytes == 1)
+    onehot_kernel<unsigned char><<<grid, 256, 0, (cudaStream_t)stream>>>((const unsigned char*)labels, out, total, classes);
+  else
+    onehot_kernel<long long><<<grid, 256, 0, (cudaStream_t)stream>>>((const long long*)labels, out, total, classes);
+  return check_launch("dg_label2onehot");
+}
+
+extern "C" int dg_argmax_last(const float* x, long long* out, long long rows, int C, void* stream) {
+  if (rows < 0 || C <= 0) return fail("dg_argmax_last: bad shape rows=%lld C=%d", rows, C);
+  if (rows == 0) return 0;
+  argmax_last_kernel<<<grid_for(rows, 256), 256, 0, (cudaStream_t)stream>>>(x, out, rows, C);
+  return check_launch("dg_argmax_last");
+}

@@ -14,20 +14,28 @@ from typing import Optional
 
 import torch
 
-from . import parallel
+from . import kernels as K
+from . import ops, parallel
+from .optim import FlatAdamW
 
 
 def gradient_penalty(D, real_node, real_edge, fake_node, fake_edge, batch_size, device):
-    """WGAN-GP term, loss.py:4-49 (eps_edge is drawn before eps_node, as there)."""
+    """WGAN-GP term, loss.py:4-49 (eps_edge is drawn before eps_node, as there).  The glue around the double backward runs in
+    three small kernels: the interpolation straight from the real side's labels when those are what the
+    caller holds (``dg_gp_interp``, bit-identical to loss.py:21-26 on the one-hot tensor), and the per-sample norm /
+    ``mean((|g| - 1)^2)`` with its gradient (``dg_gp_penalty``, ``dg_gp_penalty_bwd``: loss.py:42-47)."""
     eps_edge = torch.rand(batch_size, 1, 1, 1, device=device)
     eps_node = torch.rand(batch_size, 1, 1, device=device)
-    int_node = (eps_node * real_node + (1 - eps_node) * fake_node).requires_grad_(True)
-    int_edge = (eps_edge * real_edge + (1 - eps_edge) * fake_edge).requires_grad_(True)
+    if torch.is_floating_point(real_node):
+        int_node = (eps_node * real_node + (1 - eps_node) * fake_node).requires_grad_(True)
+        int_edge = (eps_edge * real_edge + (1 - eps_edge) * fake_edge).requires_grad_(True)
+    else:
+        int_node = K.gp_interp(real_node, fake_node.contiguous(), eps_node).requires_grad_(True)
+        int_edge = K.gp_interp(real_edge, fake_edge.contiguous(), eps_edge).requires_grad_(True)
     logits = D(int_edge, int_node)
     g_node, g_edge = torch.autograd.grad(logits, [int_node, int_edge], torch.ones_like(logits),
                                          create_graph=True, retain_graph=True)
-    g = torch.cat([g_node.reshape(batch_size, -1), g_edge.reshape(batch_size, -1)], dim=1)
-    return ((g.norm(2, dim=1) - 1) ** 2).mean()
+    return ops.GradPenalty.apply(g_node, g_edge)
 
 
 def discriminator_loss(G, D, drug_adj, drug_annot, mol_adj, mol_annot, batch_size, device, lambda_gp):
@@ -46,13 +54,17 @@ def generator_loss(G, D, mol_adj, mol_annot, batch_size):
     return -D(edge_sample, node_sample).mean(), node, edge, node_sample, edge_sample
 
 
-def synthetic_molecules(batch: int, n: int, m_dim: int = 13, b_dim: int = 5, seed: int = 1, device="cpu"):
+def synthetic_molecules(batch: int, n: int, m_dim: int = 13, b_dim: int = 5, seed: int = 1, device="cpu", labels: bool = False):
     """Synthetic one-hot molecules in the layout ``load_molecules`` produces (src/data/utils.py:128-143):
-    a[B,N,N,b] symmetric with a zero (class 0) diagonal, x[B,N,m]; fp32."""
+    a[B,N,N,b] symmetric with a zero (class 0) diagonal, x[B,N,m]; fp32.  ``labels=True``: the same molecules in the
+    label wire format -- uint8 bond labels [B,N,N] and atom labels [B,N] (what ``to_dense_adj`` holds before
+    ``label2onehot``, src/data/utils.py:130-141), 1 byte per edge instead of 4 * b_dim."""
     g = torch.Generator().manual_seed(seed)
     atoms = torch.randint(0, m_dim, (batch, n), generator=g)
     upper = torch.triu(torch.randint(0, b_dim, (batch, n, n), generator=g), diagonal=1)
     bonds = upper + upper.transpose(1, 2)
+    if labels:
+        return bonds.to(torch.uint8).to(device), atoms.to(torch.uint8).to(device)
     x = torch.nn.functional.one_hot(atoms, m_dim).float()
     a = torch.nn.functional.one_hot(bonds, b_dim).float()
     return a.to(device), x.to(device)
@@ -82,11 +94,11 @@ class GANTrainer:
         # frozen while the G-step graph is built: the gradient still flows THROUGH D to G (dgrad), D's weight-gradient
         # contractions are not launched.  G's update is bit-identical either way (SURVEY 8d "necessary FLOPs").
         self.skip_dead_d_grads = skip_dead_d_grads
-        self.g_optimizer = torch.optim.AdamW(G.parameters(), lr_g, betas)      # train.py:213
-        self.d_optimizer = torch.optim.AdamW(D.parameters(), lr_d, betas)      # train.py:214
+        # train.py:213-214 AdamW, as ONE fused launch per network over flat buckets; the data-parallel all-reduce (one per
+        # backward) runs on the optimizer's own gradient bucket (optim.FlatAdamW)
+        self.g_optimizer = FlatAdamW(G.parameters(), lr_g, betas, process_group=process_group)
+        self.d_optimizer = FlatAdamW(D.parameters(), lr_d, betas, process_group=process_group)
         self.pg = process_group
-        self.reducer_g = parallel.FlatGradReducer(G.parameters(), process_group)
-        self.reducer_d = parallel.FlatGradReducer(D.parameters(), process_group)
 
     def reset_grad(self):
         self.g_optimizer.zero_grad(set_to_none=True)
@@ -94,19 +106,18 @@ class GANTrainer:
 
     def step(self, drug_adj, drug_annot, mol_adj, mol_annot):
         """One iteration on this rank's shard; returns (d_loss, g_loss) as Python floats
-        (the two ``.item()`` syncs of train.py:364,380 included)."""
+        (the two ``.item()`` syncs of train.py:364,380 included).  The four tensors are the reference's fp32 one-hots
+        (``load_molecules``' output) or, equivalently, integer labels [B,N,N] / [B,N] -- the 1-byte wire format."""
         bsz, dev = mol_annot.shape[0], mol_annot.device
         self.reset_grad()
         _, _, d_loss = discriminator_loss(self.G, self.D, drug_adj, drug_annot, mol_adj, mol_annot, bsz, dev, self.lambda_gp)
         d_val = d_loss.item()
         d_loss.backward()
-        self.reducer_d.all_reduce_mean()
-        self.d_optimizer.step()
+        self.d_optimizer.step()                 # (all-reduce of the D gradients inside, world > 1)
         self.reset_grad()
         with (frozen(self.D) if self.skip_dead_d_grads else contextlib.nullcontext()):
             g_loss = generator_loss(self.G, self.D, mol_adj, mol_annot, bsz)[0]
         g_val = g_loss.item()
         g_loss.backward()
-        self.reducer_g.all_reduce_mean()
-        self.g_optimizer.step()
+        self.g_optimizer.step()                 # (all-reduce of the G gradients inside, world > 1)
         return d_val, g_val

@@ -68,11 +68,17 @@ def _be():
 def _chk(*ts, bf16_ok=False):
     if _test_backend is not None:
         return
+    dev = None
     for t in ts:
         if t is None:
             continue
         if not t.is_cuda:
             raise RuntimeError("druggen_b200 kernels run on CUDA tensors only (no CPU fallback)")
+        if dev is None:
+            dev = t.device
+            _lib.cuda_backend().device = dev       # the launch goes to the tensors' device, not merely the current one
+        elif t.device != dev:
+            raise RuntimeError(f"druggen_b200 kernels take tensors of one device, got {dev} and {t.device}")
         if t.dtype != torch.float32 and not (bf16_ok and t.dtype == torch.bfloat16):
             raise RuntimeError(f"druggen_b200 kernels take fp32 tensors, got {t.dtype}")
         if not t.is_contiguous():
@@ -346,19 +352,33 @@ def set_option(key: int, value: int) -> None:
 
 
 # ----------------------------------------------------------------------------- either side of the encoder path
-def label2onehot(labels, dim: int, device=None):
-    """src/data/utils.py:15-23, same signature: integer labels [...] -> fp32 one-hot [..., dim] on the labels' CUDA device
-    (``device`` given: labels are moved there first -- as uint8 this is the 1-byte-per-edge wire format)."""
-    if device is not None:
-        labels = labels.to(device, non_blocking=True)
+def _chk_labels(labels):
     if _test_backend is None and not labels.is_cuda:
         raise RuntimeError("druggen_b200 kernels run on CUDA tensors only (no CPU fallback)")
     if labels.dtype not in (torch.int64, torch.uint8):
-        raise RuntimeError(f"label2onehot takes int64 or uint8 labels, got {labels.dtype}")
-    labels = labels.contiguous()
+        raise RuntimeError(f"labels are int64 or uint8, got {labels.dtype}")
+    return labels.contiguous()
+
+
+def check_labels() -> None:
+    """Raise if any label-consuming launch since the last check met a label outside [0, classes) -- where the reference's
+    ``scatter_`` (src/data/utils.py:21) raises.  Synchronises with the device."""
+    if _test_backend is None and _be().label_error(True) == 1:
+        raise RuntimeError("druggen_b200: label outside [0, classes) (the reference's label2onehot scatter_ raises here)")
+
+
+def label2onehot(labels, dim: int, device=None, validate: bool = True):
+    """src/data/utils.py:15-23, same signature: integer labels [...] -> fp32 one-hot [..., dim] on the labels' CUDA device
+    (``device`` given: labels are moved there first -- as uint8 this is the 1-byte-per-edge wire format).  Like the
+    reference's ``scatter_`` an out-of-range label raises (``validate=False`` defers that to ``check_labels()``: no sync here)."""
+    if device is not None:
+        labels = labels.to(device, non_blocking=True)
+    labels = _chk_labels(labels)
     out = torch.empty(tuple(labels.shape) + (dim,), dtype=torch.float32, device=labels.device)
     if labels.numel():
         _be().label2onehot(labels, out, dim)
+        if validate:
+            check_labels()
     return out
 
 
@@ -369,3 +389,72 @@ def argmax_last(t):
     if t.numel():
         _be().argmax_last(t, out)
     return out
+
+
+def embed_labels_fwd(labels, lut, sym: bool):
+    """Prologue of a one-hot batch given as labels (models.py:91-94): labels [B,N] -> lut[labels] [B,N,D]; ``sym`` (edges,
+    labels [B,N,N]) -> (lut[a_ij] + lut[a_ji]) / 2 [B,N,N,D].  lut:[classes,D] = the prologue MLP applied to the identity."""
+    _chk(lut)
+    labels = _chk_labels(labels)
+    assert labels.dim() == (3 if sym else 2) and (not sym or labels.shape[1] == labels.shape[2]), labels.shape
+    y = torch.empty(tuple(labels.shape) + (lut.shape[1],), dtype=lut.dtype, device=lut.device)
+    if labels.numel():
+        _be().embed_labels_fwd(labels, lut, y, labels.shape[1], sym)
+    return y
+
+
+def embed_labels_bwd(labels, dy, classes: int, sym: bool):
+    """-> dlut [classes,D]: segmented sum of dy rows by label (both labels of the symmetrised pair get half)."""
+    _chk(dy)
+    labels = _chk_labels(labels)
+    dlut = torch.zeros((classes, dy.shape[-1]), dtype=dy.dtype, device=dy.device)
+    if labels.numel():
+        _be().embed_labels_bwd(labels, dy, dlut, labels.shape[1], sym)
+    return dlut
+
+
+def gp_interp(labels, fake, eps):
+    """loss.py:21-26 ``eps * real + (1 - eps) * fake`` with ``real`` as labels [B,...] and ``fake`` [B,...,classes];
+    eps:[B] (or [B,1,..]).  Bit-identical to torch's elementwise kernels on the one-hot tensor."""
+    _chk(fake, eps)
+    labels = _chk_labels(labels)
+    assert tuple(fake.shape[:-1]) == tuple(labels.shape), (fake.shape, labels.shape)
+    out = torch.empty_like(fake)
+    if labels.numel():
+        _be().gp_interp(labels, fake, eps.reshape(-1), out, labels.numel() // labels.shape[0])
+    return out
+
+
+def gp_penalty(g_node, g_edge):
+    """loss.py:42-47 -> (penalty [1], coef [B]): mean_b (|concat(g_node_b, g_edge_b)| - 1)^2 and d penalty / d g = coef_b g."""
+    _chk(g_node, g_edge)
+    b = g_node.shape[0]
+    pen = torch.empty(1, dtype=g_node.dtype, device=g_node.device)
+    coef = torch.empty(b, dtype=g_node.dtype, device=g_node.device)
+    _be().gp_penalty(g_node, g_edge, pen, coef, torch.empty_like(coef))
+    return pen, coef
+
+
+def gp_penalty_bwd(g, coef, upstream):
+    _chk(g, coef, upstream)
+    out = torch.empty_like(g)
+    _be().gp_penalty_bwd(g, coef, upstream.reshape(1), out)
+    return out
+
+
+def readout_argmax(x, w, bias, want_logits: bool = False, idx_dtype=torch.int64):
+    """models.py:100-101 + inference.py:197-198: x:[...,128] -> (idx [...], logits [...,classes] | None) in one pass:
+    logits = x w^T + bias, idx = their first maximum (int64, or uint8 for a 1-byte-per-edge result)."""
+    _chk(x, w, bias)
+    assert idx_dtype in (torch.int64, torch.uint8)
+    idx = torch.empty(x.shape[:-1], dtype=idx_dtype, device=x.device)
+    logits = torch.empty(tuple(x.shape[:-1]) + (w.shape[0],), dtype=x.dtype, device=x.device) if want_logits else None
+    if x.numel():
+        _be().readout_argmax(x, w, bias, logits, idx)
+    return idx, logits
+
+
+def adamw_flat(p, g, m, v, segs, nseg: int, lr: float, beta1: float, beta2: float, eps: float, weight_decay: float) -> None:
+    """One fused AdamW launch over a network's flat parameter / gradient / moment buffers (train.py:213-214)."""
+    _chk(p, g, m, v)
+    _be().adamw_flat(p, g, m, v, segs, nseg, lr, beta1, beta2, eps, weight_decay)

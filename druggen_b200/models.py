@@ -11,6 +11,8 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from . import kernels as K
+from . import ops
 from .layers import TransformerEncoder
 
 
@@ -36,6 +38,20 @@ class _GraphNet(nn.Module):
                                                      mlp_ratio=mlp_ratio, drop_rate=dropout)
 
     def _embed(self, z_e, z_n):
+        """Prologue + encoder.  ``z_e`` / ``z_n`` are the reference's fp32 tensors [B,N,N,edges] / [B,N,nodes], or -- the
+        label wire format -- integer (uint8 / int64) labels [B,N,N] / [B,N] of one-hot molecules:
+        the prologue MLP of a one-hot row is a row of a [classes, dim] table, so edges are written once as
+        (T[a_ij] + T[a_ji]) / 2 straight from the 1-byte labels (``dg_embed_labels_fwd``)."""
+        if not torch.is_floating_point(z_e):
+            if self.dim == 128 and not (self.training and self.dropout > 0):
+                w = self.edge_layers[0].weight
+                lut_e = self.edge_layers(torch.eye(self.edges, dtype=w.dtype, device=w.device))    # models.py:92 on the identity
+                lut_n = self.node_layers(torch.eye(self.nodes, dtype=w.dtype, device=w.device))    # models.py:91
+                edge = ops.EmbedLabels.apply(lut_e, z_e, True)                                     # + models.py:94
+                node = ops.EmbedLabels.apply(lut_n, z_n, False)
+                return self.TransformerEncoder(node, edge)
+            z_e = K.label2onehot(z_e, self.edges, validate=False)
+            z_n = K.label2onehot(z_n, self.nodes, validate=False)
         node = self.node_layers(z_n)                       # models.py:91
         edge = self.edge_layers(z_e)                       # models.py:92
         edge = (edge + edge.permute(0, 2, 1, 3)) / 2       # models.py:94
@@ -54,6 +70,18 @@ class Generator(_GraphNet):
     def forward(self, z_e, z_n):
         node, edge = self._embed(z_e, z_n)
         return node, edge, self.readout_n(node), self.readout_e(edge)
+
+    @torch.no_grad()
+    def decode(self, z_e, z_n, idx_dtype=torch.int64):
+        """inference.py:195-198 in one call: G forward, then the readouts fused with ``torch.max(.., -1)[1]``
+        (``dg_readout_argmax``: the [B,N,N,dim] stream is read once, the logits never reach HBM) ->
+        (node labels [B,N], edge labels [B,N,N]) as int64, or uint8 for a 1-byte-per-edge result."""
+        node, edge = self._embed(z_e, z_n)
+        if self.dim != 128:
+            return torch.max(self.readout_n(node), -1)[1], torch.max(self.readout_e(edge), -1)[1]
+        n_idx, _ = K.readout_argmax(node.contiguous(), self.readout_n.weight, self.readout_n.bias, idx_dtype=idx_dtype)
+        e_idx, _ = K.readout_argmax(edge.contiguous(), self.readout_e.weight, self.readout_e.bias, idx_dtype=idx_dtype)
+        return n_idx, e_idx
 
 
 class Discriminator(_GraphNet):

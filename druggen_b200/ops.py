@@ -319,3 +319,41 @@ class SoftmaxAggBwd(Function):
     def backward(ctx, ua, uv):
         dg, a, v = ctx.saved_tensors
         return K.softmax_agg_bwd_bwd(_c(ua), _c(uv), dg, a, v)
+
+
+# ----------------------------------------------------------------------------- either side of the encoder
+class EmbedLabels(Function):
+    """Prologue of a one-hot batch given as integer labels (models.py:91-94,196-199): ``lut`` [classes, D] is the prologue
+    MLP applied to the identity (built with ordinary torch ops by the caller, so the weights get their gradients through it);
+    forward = table rows (+ the symmetrisation of models.py:94 for edges), backward = a segmented row sum into ``dlut``."""
+
+    @staticmethod
+    def forward(ctx, lut, labels, sym):
+        ctx.save_for_backward(labels)
+        ctx.sym, ctx.classes = sym, lut.shape[0]
+        return K.embed_labels_fwd(labels, lut.contiguous(), sym)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        (labels,) = ctx.saved_tensors
+        return K.embed_labels_bwd(labels, _c(dy), ctx.classes, ctx.sym), None, None
+
+
+class GradPenalty(Function):
+    """loss.py:42-47: (g_node [B,...], g_edge [B,...]) -> mean_b (|concat(g_node_b, g_edge_b)|_2 - 1)^2 in two small
+    launches; its backward scales the two gradient tensors by 2 (|g_b| - 1) / (B |g_b|)."""
+
+    @staticmethod
+    def forward(ctx, g_node, g_edge):
+        g_node, g_edge = g_node.contiguous(), g_edge.contiguous()
+        pen, coef = K.gp_penalty(g_node, g_edge)
+        ctx.save_for_backward(g_node, g_edge, coef)
+        return pen.reshape(())
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, up):
+        g_node, g_edge, coef = ctx.saved_tensors
+        up = up.contiguous()
+        return K.gp_penalty_bwd(g_node, coef, up), K.gp_penalty_bwd(g_edge, coef, up)

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DG_ABI_VERSION 2
+#define DG_ABI_VERSION 3
 #define DG_PREC_FP32 0
 #define DG_PREC_BF16 1
 
@@ -156,14 +156,45 @@ int dg_attn_edge_fwd(const float* y, const float* q, const float* k, const float
                      float* out, void* a_bf16, float* e_out, float* z_out, int B, int N, int D, float eps,
                      void* workspace, long long workspace_bytes, void* stream);
 
-/* ---- either side of the encoder path ----------------------------------------------------------------- */
+/* ---- either side of the encoder path -------------------------------------------------------- */
 /* src/data/utils.py:15-23 label2onehot: out[n, classes] fp32 = one-hot of labels[n]; labels are int64 (label_bytes 8, what
  * the reference's to_dense_adj produces) or uint8 (label_bytes 1: a 1-byte-per-edge wire format for the host->device copy).
- * A label outside [0, classes) gives an all-zero row (torch's scatter_ would raise). */
+ * A label outside [0, classes) raises the device flag that dg_label_error() reads (torch's scatter_ raises); its row is all zero. */
 int dg_label2onehot(const void* labels, int label_bytes, float* out, long long n, int classes, void* stream);
+/* Reads (and with `clear` resets) the out-of-range-label flag set by dg_label2onehot / dg_embed_labels_* / dg_gp_interp since the
+ * last clear.  Synchronises with the device.  1 = some label was outside [0, classes); 0 = none; -1 = the flag could not be read. */
+int dg_label_error(int clear);
 /* inference.py:197-198 torch.max(t, -1)[1]: out[rows] int64 = index of the first maximum of each row of x[rows, C]
  * (a NaN wins; the first NaN), i.e. ATen's CPU result, bit for bit. */
 int dg_argmax_last(const float* x, long long* out, long long rows, int C, void* stream);
+/* models.py:91-94 / 196-199 for one-hot inputs given as labels: y[r,:] = lut[labels[r],:] (node rows, sym = 0) or, for edge rows
+ * r = (b n + i) n + j with sym = 1, y[r,:] = (lut[a_ij,:] + lut[a_ji,:]) / 2 -- the prologue MLP of a one-hot row is a row of the
+ * [classes, D] table lut = act(W2 act(W1[:,l] + b1) + b2) the host computes from the weights; D == 128, classes <= 16. */
+int dg_embed_labels_fwd(const void* labels, int label_bytes, const float* lut, float* y, long long rows, int n, int classes,
+                        int D, int sym, void* stream);
+/* its backward: dlut[l,:] += sum_r dy[r,:] ([a_ij = l] + [a_ji = l]) / 2   (sym = 0: sum over rows with labels[r] = l); zero first. */
+int dg_embed_labels_bwd(const void* labels, int label_bytes, const float* dy, float* dlut, long long rows, int n, int classes,
+                        int D, int sym, void* stream);
+/* loss.py:21-26 with the real side given as labels: out[r,c] = eps[b] * [labels[r] == c] + (1 - eps[b]) * fake[r,c],
+ * b = r / rows_per_mol; rounded exactly as torch's mul / rsub / mul / add kernels round (no FMA contraction). */
+int dg_gp_interp(const void* labels, int label_bytes, const float* fake, const float* eps, float* out, long long rows,
+                 long long rows_per_mol, int classes, void* stream);
+/* loss.py:42-47: penalty[0] = mean_b (|g_b| - 1)^2 with |g_b| the L2 norm over concat(g_node[b,:], g_edge[b,:]);
+ * coef[b] = 2 (|g_b| - 1) / (batch |g_b|) for the backward; sq_scratch[batch] is workspace. */
+int dg_gp_penalty(const float* g_node, const float* g_edge, float* penalty, float* coef, float* sq_scratch, int batch,
+                  long long len_node, long long len_edge, void* stream);
+/* d penalty / d g: out[b,i] = upstream[0] * coef[b] * g[b,i]   (g = g_node or g_edge, per_mol elements per molecule). */
+int dg_gp_penalty_bwd(const float* g, const float* coef, const float* upstream, float* out, int batch, long long per_mol,
+                      void* stream);
+/* models.py:100-101 + inference.py:197-198 in one pass over x[rows, D]: logits[rows, classes] = x w^T + bias (NULL to skip) and
+ * idx[rows] = first maximal class as int64 (idx_bytes 8) or uint8 (idx_bytes 1) (NULL to skip); D == 128, classes <= 16. */
+int dg_readout_argmax(const float* x, const float* w, const float* bias, float* logits, void* idx, int idx_bytes, long long rows,
+                      int D, int classes, void* stream);
+/* train.py:213-214 torch.optim.AdamW over ONE flat buffer per network: p, g, m (exp_avg), v (exp_avg_sq) are parallel fp32 arrays;
+ * segs[nseg] (device) = { int64 begin, end; float bias_correction1, sqrt(bias_correction2); int32 active, pad } per parameter tensor:
+ * inactive tensors (gradient None) are untouched, exactly as torch skips them. */
+int dg_adamw_flat(float* p, const float* g, float* m, float* v, const void* segs, int nseg, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, void* stream);
 
 /* debug: with a device buffer of 148*64 int64 set, every chain-kernel launch (dg_mlp_*, dg_attn_edge_fwd) writes
  * per-CTA phase cycle counters [CTA][4 roles][16 phases] (tools/chain_profile.py); NULL switches it off. */

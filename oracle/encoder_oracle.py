@@ -22,6 +22,7 @@ import math
 from typing import Dict, Tuple
 
 import torch
+import torch.nn.functional as F
 
 Params = Dict[str, torch.Tensor]
 
@@ -34,13 +35,13 @@ _ACTS = {
 
 
 def _affine(t, p: Params, name: str):
-    return t @ p[name + ".weight"].transpose(0, 1) + p[name + ".bias"]
+    # nn.Linear.forward == F.linear (addmm), the op the reference modules dispatch to
+    return F.linear(t, p[name + ".weight"], p[name + ".bias"])
 
 
 def _layernorm(t, p: Params, name: str, eps: float = 1e-5):
-    mu = t.mean(dim=-1, keepdim=True)
-    var = ((t - mu) ** 2).mean(dim=-1, keepdim=True)
-    return (t - mu) / torch.sqrt(var + eps) * p[name + ".weight"] + p[name + ".bias"]
+    # nn.LayerNorm.forward == F.layer_norm (native_layer_norm), as in the reference
+    return F.layer_norm(t, (t.shape[-1],), p[name + ".weight"], p[name + ".bias"], eps)
 
 
 def block_forward(x, y, p: Params, prefix: str, heads: int):
@@ -166,15 +167,25 @@ class OracleGAN:
     def g_loss(self, mol_adj, mol_annot):
         return generator_loss(self.G, self.D, mol_adj, mol_annot)
 
-    def step(self, drug_adj, drug_annot, mol_adj, mol_annot, eps_edge, eps_node):
-        """One train.py:351-384 iteration.  Returns (d_loss, g_loss) as floats."""
+    def step(self, drug_adj, drug_annot, mol_adj, mol_annot, eps_edge, eps_node, skip_dead_d_grads: bool = False):
+        """One train.py:351-384 iteration.  Returns (d_loss, g_loss) as floats.
+        ``skip_dead_d_grads``: do not compute the Discriminator weight gradients of the G-step, which train.py:371-377
+        computes and reset_grad (train.py:352) discards unread -- the same switch as GANTrainer's, so that bench.py's two
+        arms do the same work."""
         self._zero()
         d = self.d_loss(drug_adj, drug_annot, mol_adj, mol_annot, eps_edge, eps_node)
         d_val = d.item()
         d.backward()
         self.d_opt.step()
         self._zero()
-        g = self.g_loss(mol_adj, mol_annot)
+        if skip_dead_d_grads:
+            for t in self.dp_.values():
+                t.requires_grad_(False)
+        try:
+            g = self.g_loss(mol_adj, mol_annot)
+        finally:
+            for t in self.dp_.values():
+                t.requires_grad_(True)
         g_val = g.item()
         g.backward()
         self.g_opt.step()

@@ -218,3 +218,53 @@ class EmulBackend:
 
     def argmax_last(self, x, out):
         out.copy_(torch.max(x, -1)[1])
+
+    # ---- either side of the encoder
+    def embed_labels_fwd(self, labels, lut, y, n, sym):
+        t = lut[labels.long()]
+        y.copy_((t + t.transpose(1, 2)) / 2 if sym else t)
+
+    def embed_labels_bwd(self, labels, dy, dlut, n, sym):
+        lab = labels.long()
+        d = dy.shape[-1]
+        if sym:
+            dlut.index_add_(0, lab.reshape(-1), dy.reshape(-1, d) * 0.5)
+            dlut.index_add_(0, lab.transpose(1, 2).reshape(-1), dy.reshape(-1, d) * 0.5)
+        else:
+            dlut.index_add_(0, lab.reshape(-1), dy.reshape(-1, d))
+
+    def gp_interp(self, labels, fake, eps, out, rows_per_mol):
+        real = torch.nn.functional.one_hot(labels.long(), fake.shape[-1]).to(fake.dtype)
+        e = eps.reshape([-1] + [1] * (fake.dim() - 1))
+        out.copy_(e * real + (1 - e) * fake)
+
+    def gp_penalty(self, g_node, g_edge, penalty, coef, scratch):
+        b = g_node.shape[0]
+        nrm = torch.cat([g_node.reshape(b, -1), g_edge.reshape(b, -1)], 1).norm(2, dim=1)
+        penalty.copy_(((nrm - 1) ** 2).mean().reshape(1))
+        coef.copy_(torch.where(nrm > 0, 2 * (nrm - 1) / (b * nrm), torch.zeros_like(nrm)))
+
+    def gp_penalty_bwd(self, g, coef, upstream, out):
+        out.copy_(upstream.reshape(()) * coef.reshape([-1] + [1] * (g.dim() - 1)) * g)
+
+    def readout_argmax(self, x, w, bias, logits, idx):
+        lg = x @ w.t() + bias
+        if logits is not None:
+            logits.copy_(lg)
+        if idx is not None:
+            idx.copy_(torch.max(lg, -1)[1])
+
+    def adamw_flat(self, p, g, m, v, segs, nseg, lr, beta1, beta2, eps, wd):
+        import numpy as np
+        from druggen_b200.optim import SEG_DTYPE
+        for s in np.frombuffer(segs.cpu().numpy().tobytes(), dtype=SEG_DTYPE):
+            if not s["active"]:
+                continue
+            sl = slice(int(s["begin"]), int(s["end"]))
+            p[sl].mul_(1 - lr * wd)
+            m[sl].lerp_(g[sl], 1 - beta1)
+            v[sl].mul_(beta2).addcmul_(g[sl], g[sl], value=1 - beta2)
+            p[sl].addcdiv_(m[sl], v[sl].sqrt() / float(s["bc2_sqrt"]) + eps, value=-lr / float(s["bc1"]))
+
+    def label_error(self, clear=True):
+        return 0

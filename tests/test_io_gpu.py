@@ -50,3 +50,18 @@ def test_argmax_decode_bit_exact_incl_ties_and_nan(cuda_dev, rows, C):
         assert torch.equal(dg.argmax_last(tn.to(cuda_dev)).cpu(), torch.max(tn, -1)[1])
     shaped = t.view(-1, 1, C) if rows else t.view(0, 1, C)
     assert dg.argmax_last(shaped.to(cuda_dev)).shape == shaped.shape[:-1]
+
+
+@pytest.mark.parametrize("dtype", [torch.int64, torch.uint8])
+def test_label2onehot_rejects_out_of_range_like_scatter(cuda_dev, dtype):
+    """src/data/utils.py:21 scatter_ raises on an index outside [0, dim); so does the kernel path (device flag -> RuntimeError)"""
+    labels = torch.tensor([[0, 1, 7, 2]], dtype=dtype)
+    with pytest.raises(RuntimeError):
+        ref_label2onehot(labels.long(), 5)
+    with pytest.raises(RuntimeError):
+        dg.label2onehot(labels.to(cuda_dev), 5)
+    dg.label2onehot(torch.tensor([[0, 4]], dtype=dtype, device=cuda_dev), 5)         # the flag was cleared by the raise
+    deferred = dg.label2onehot(labels.to(cuda_dev), 5, validate=False)               # no sync here ...
+    assert deferred.shape == (1, 4, 5)
+    with pytest.raises(RuntimeError):
+        dg.kernels.check_labels()                                                     # ... the error surfaces at the next check

@@ -262,3 +262,71 @@ def test_bf16_mode_depth8_error_and_decode_flips_reported(cuda_dev, capsys):
                   f"edge argmax flips {100 * fl:.2f} %")
     assert res["fp32"][0] < PARITY_TOL and res["fp32"][1] < PARITY_TOL and res["fp32"][2] < 2e-3
     assert res["bf16"][1] < 5e-2 and res["bf16"][2] < 0.05
+
+
+# measured on B200 (printed by the test below, profiles/r02_parity_depth8.json); the bounds are ~2x the measurement
+DEPTH8_BOUNDS = {
+    # mode: (loss rel, D-grad rel-L2 over the whole parameter vector, G-grad rel-L2 over the whole parameter vector)
+    "fp32": (1e-3, 5e-3, 1e-3),
+    "bf16x3": (1e-3, 5e-3, 1e-3),
+    "bf16": (5e-2, 3e-1, 3e-1),
+}
+
+
+def _flat(grads):
+    return torch.cat([g.double().flatten().cpu() for g in grads])
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16x3", "bf16"])
+def test_gan_step_depth8_n45_vs_oracle(cuda_dev, mode, capsys):
+    """The step the bench times -- depth 8, N = 45, D loss with the gradient penalty's double backward, G loss -- in EVERY
+    precision mode against the fp32 CPU oracle: both losses, every Discriminator gradient of the D-step (gradient penalty
+    included), every Generator gradient of the G-step.  Prints the errors (and stores them for profiles/) and bounds them."""
+    import json
+    import os
+    if mode not in dg.kernels.PRECISIONS:
+        pytest.skip(f"precision {mode} not built")
+    if mode != "fp32" and not _tc_built():
+        pytest.skip("tcgen05 contractions not built")
+    torch.manual_seed(21)
+    n, bsz = 45, 2
+    G = dg.Generator("relu", n, 5, 13, 0.0, dim=128, depth=8, heads=8, mlp_ratio=3)
+    D = dg.Discriminator("relu", n, 5, 13, 0.0, dim=128, depth=8, heads=8, mlp_ratio=3)
+    ref = orc.OracleGAN(dict(G.state_dict()), dict(D.state_dict()), 8, 8, 8)
+    a, x = orc.synthetic_batch(bsz, n, 13, 5, seed=3)
+    da, dx = orc.synthetic_batch(bsz, n, 13, 5, seed=4)
+    eps_e, eps_n = torch.rand(bsz, 1, 1, 1), torch.rand(bsz, 1, 1)
+    d_ref = ref.d_loss(da, dx, a, x, eps_e, eps_n)
+    d_ref.backward()
+    gD_ref = {k: v.grad.clone() for k, v in ref.dp_.items() if v.grad is not None and float(v.grad.abs().max()) > 0}
+    ref._zero()
+    g_ref = ref.g_loss(a, x)
+    g_ref.backward()
+    gG_ref = {k: v.grad.clone() for k, v in ref.gp_.items()}
+    G.to(cuda_dev), D.to(cuda_dev)
+    dev = lambda t: t.to(cuda_dev)  # noqa: E731
+    with dg.precision(mode):
+        d = orc.discriminator_loss(G, D, dev(da), dev(dx), dev(a), dev(x), dev(eps_e), dev(eps_n), 10.0)
+        d.backward()
+        gD = {k: v.grad.clone() for k, v in D.named_parameters() if v.grad is not None}
+        G.zero_grad(set_to_none=True), D.zero_grad(set_to_none=True)
+        g = orc.generator_loss(G, D, dev(a), dev(x))
+        g.backward()
+        gG = {k: v.grad.clone() for k, v in G.named_parameters()}
+    assert set(gD) == set(gD_ref)
+    rec = {"mode": mode, "depth": 8, "atoms": n, "batch": bsz,
+           "d_loss_rel": abs(d.item() - d_ref.item()) / max(1.0, abs(d_ref.item())),
+           "g_loss_rel": abs(g.item() - g_ref.item()) / max(1.0, abs(g_ref.item())),
+           "D_grads_rel_l2_all": rel_l2(_flat(gD[k] for k in gD_ref), _flat(gD_ref.values())),
+           "G_grads_rel_l2_all": rel_l2(_flat(gG[k] for k in gG_ref), _flat(gG_ref.values())),
+           "D_grads_rel_l2_worst_tensor": max(rel_l2(gD[k], v) for k, v in gD_ref.items()),
+           "G_grads_rel_l2_worst_tensor": max(rel_l2(gG[k], v) for k, v in gG_ref.items())}
+    with capsys.disabled():
+        print("\n[parity depth8] " + json.dumps(rec))
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "parity_depth8.jsonl"), "a") as f:
+            f.write(json.dumps(rec) + "\n")
+    b_loss, b_d, b_g = DEPTH8_BOUNDS[mode]
+    assert rec["d_loss_rel"] < b_loss and rec["g_loss_rel"] < b_loss, rec
+    assert rec["D_grads_rel_l2_all"] < b_d and rec["G_grads_rel_l2_all"] < b_g, rec

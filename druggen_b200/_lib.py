@@ -12,7 +12,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdruggen_b200.so")
-PREC = {"fp32": 0, "bf16": 1}
+PREC = {"fp32": 0, "bf16": 1, "bf16x3": 2}
 
 _P, _LL, _I, _F = C.c_void_p, C.c_longlong, C.c_int, C.c_float
 

@@ -41,7 +41,7 @@ extern "C" int dg_rows_gemm(const void* a, const float* w, int w_is_nk, const fl
     if (flags) return fail("dg_rows_gemm: bf16 storage flags need the tensor-core precision");
     return rows_gemm_fp32((const float*)a, w, w_is_nk, bias, relu, (const float*)gate, resid, (float*)out, R, K, N, (cudaStream_t)stream);
   }
-  if (prec == DG_PREC_BF16)
+  if (prec == DG_PREC_BF16 || prec == DG_PREC_BF16X3)
     return rows_gemm_tc(a, w, w_is_nk, bias, relu, gate, resid, out, R, K, N, prec, flags, (cudaStream_t)stream);
   return fail("dg_rows_gemm: unknown precision %d", prec);
 }
@@ -53,7 +53,7 @@ extern "C" int dg_gemm_tn(const void* a, const void* b, float* out, float* colsu
     if (flags) return fail("dg_gemm_tn: bf16 storage flags need the tensor-core precision");
     return gemm_tn_fp32((const float*)a, (const float*)b, out, colsum_a, R, M, N, (cudaStream_t)stream);
   }
-  if (prec == DG_PREC_BF16)
+  if (prec == DG_PREC_BF16 || prec == DG_PREC_BF16X3)
     return gemm_tn_tc(a, b, out, colsum_a, R, M, N, prec, flags, (cudaStream_t)stream);
   return fail("dg_gemm_tn: unknown precision %d", prec);
 }

@@ -28,15 +28,18 @@ constexpr int kStage = 36;                // epilogue transpose row pitch (float
 // =============================================================================================
 constexpr int kRingA = 4;                 // A ring: blocks of [128 rows][64 ch]
 constexpr int kAccBufs = 4;               // 4 x 128 TMEM columns
+constexpr int kResidPre = 256;            // internal flag: resid is added before the ReLU / gate (K-sliced launches)
 
 struct RowsSmem {                         // offsets into dynamic smem (1024-aligned base)
   int w, a, stage, bars, total;
 };
-__host__ __device__ inline RowsSmem rows_smem(int K, int N) {
+// split (DG_PREC_BF16X3): every operand block exists twice (hi, lo); the A ring is then 3 deep so that it all still fits
+__host__ __device__ inline int rows_ring(int split) { return split ? 3 : kRingA; }
+__host__ __device__ inline RowsSmem rows_smem(int K, int N, int split = 0) {
   RowsSmem s;
   s.w = 0;
-  s.a = N * K * 2;
-  s.stage = s.a + kRingA * kBlk;
+  s.a = N * K * 2 * (split ? 2 : 1);
+  s.stage = s.a + rows_ring(split) * kBlk * (split ? 2 : 1);
   s.bars = s.stage + 8 * 32 * kStage * 4;
   s.total = s.bars + 256;
   return s;
@@ -46,7 +49,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 rows_gemm_tc_kernel(const float* __restrict__ a, const float* __restrict__ w, int w_is_nk,
                     const float* __restrict__ bias, int relu, const float* __restrict__ gate,
                     const float* __restrict__ resid, float* __restrict__ out, long long R, int K, int N, int flags,
-                    int prefetch) {
+                    int prefetch, int lda, int ldw, int ldo, int split) {
+  // lda / ldw / ldo: row pitches (elements) of a, w and of out / resid / gate -- a launch may work on a column slice of wider
+  // tensors (the split-precision mode runs H = 384 shapes as 128-wide slices).  split: bf16x3 operands (hi + lo blocks).
   const uint16_t* a16 = reinterpret_cast<const uint16_t*>(a);        // bf16 views (flags select which are live)
   const uint16_t* gate16 = reinterpret_cast<const uint16_t*>(gate);
   uint16_t* out16 = reinterpret_cast<uint16_t*>(out);
@@ -54,12 +59,15 @@ rows_gemm_tc_kernel(const float* __restrict__ a, const float* __restrict__ w, in
   // 1024-byte alignment as an OFFSET from the __shared__ array: a pointer rebuilt from an integer loses its address
   // space and every access through it compiles to generic LD/ST (LSU long-scoreboard path) instead of LDS/STS
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const RowsSmem L = rows_smem(K, N);
+  const RowsSmem L = rows_smem(K, N, split);
+  const int ring = rows_ring(split);
+  const int a_stage = split ? 2 * kBlk : kBlk;          // ring stage: [hi block][lo block]
+  const int w_lo = N * K * 2;                           // offset of the lo copy of the weights
   uint8_t* sW = smem + L.w;
   uint8_t* sA = smem + L.a;
   float* sStage = reinterpret_cast<float*>(smem + L.stage);
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + L.bars);
-  uint64_t* a_empty = a_full + kRingA;
+  uint64_t* a_empty = a_full + kRingA;                   // (barrier slots are laid out for the deepest ring)
   uint64_t* acc_full = a_empty + kRingA;
   uint64_t* acc_empty = acc_full + kAccBufs;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccBufs);
@@ -80,15 +88,16 @@ rows_gemm_tc_kernel(const float* __restrict__ a, const float* __restrict__ w, in
     float4 lo, hi;
     if (w_is_nk) {
       n = idx / (K / 8); c8 = idx % (K / 8);
-      const float* p = w + (long long)n * K + c8 * 8;
+      const float* p = w + (long long)n * ldw + c8 * 8;
       lo = ld4(p); hi = ld4(p + 4);
     } else {
       n = idx % N; c8 = idx / N;
-      const float* p = w + (long long)(c8 * 8) * N + n;
-      lo = make_float4(p[0], p[N], p[2 * N], p[3 * N]);
-      hi = make_float4(p[4 * N], p[5 * N], p[6 * N], p[7 * N]);
+      const float* p = w + (long long)(c8 * 8) * ldw + n;
+      lo = make_float4(p[0], p[ldw], p[2 * ldw], p[3 * ldw]);
+      hi = make_float4(p[4 * ldw], p[5 * ldw], p[6 * ldw], p[7 * ldw]);
     }
-    st_block_chunk(sW + (c8 >> 3) * (N * 128), n, c8 & 7, lo, hi);
+    if (split) st_block_chunk_split(sW + (c8 >> 3) * (N * 128), sW + w_lo + (c8 >> 3) * (N * 128), n, c8 & 7, lo, hi);
+    else st_block_chunk(sW + (c8 >> 3) * (N * 128), n, c8 & 7, lo, hi);
   }
   fence_async_smem();
   tc_fence_before();
@@ -111,8 +120,8 @@ rows_gemm_tc_kernel(const float* __restrict__ a, const float* __restrict__ w, in
           if (prow0 >= R) break;
           const long long prows = R - prow0 < 128 ? R - prow0 : 128;
           if (grp == 0) {
-            bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(a) + prow0 * K * ((flags & DG_A_BF16) ? 2 : 4), prows * K * ((flags & DG_A_BF16) ? 2 : 4));
-          } else {
+            if (lda == K) bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(a) + prow0 * K * ((flags & DG_A_BF16) ? 2 : 4), prows * K * ((flags & DG_A_BF16) ? 2 : 4));
+          } else if (ldo == N) {
             if (resid) bulk_prefetch_l2(resid + prow0 * N, prows * N * 4);
             if (gate) bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(gate) + prow0 * N * ((flags & DG_GATE_BF16) ? 2 : 4), prows * N * ((flags & DG_GATE_BF16) ? 2 : 4));
           }
@@ -120,15 +129,15 @@ rows_gemm_tc_kernel(const float* __restrict__ a, const float* __restrict__ w, in
       }
       for (int kb = 0; kb < KB; ++kb, ++chunk) {
         if ((int)(chunk & 1) != grp) continue;
-        const int st = chunk % kRingA;
-        mbar_wait(&a_empty[st], ((chunk / kRingA) & 1) ^ 1);
-        uint8_t* blk = sA + st * kBlk;
+        const int st = chunk % ring;
+        mbar_wait(&a_empty[st], ((chunk / ring) & 1) ^ 1);
+        uint8_t* blk = sA + st * a_stage;
         if (flags & DG_A_BF16) {            // operand already bf16 in HBM: plain 16-byte chunk copies
           uint4 c16[8];
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             int item = it * 128 + lt, r = item >> 3, j = item & 7;
-            c16[it] = (row0 + r < R) ? *reinterpret_cast<const uint4*>(a16 + (row0 + r) * K + kb * 64 + j * 8) : make_uint4(0, 0, 0, 0);
+            c16[it] = (row0 + r < R) ? *reinterpret_cast<const uint4*>(a16 + (row0 + r) * lda + kb * 64 + j * 8) : make_uint4(0, 0, 0, 0);
           }
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
@@ -144,7 +153,7 @@ rows_gemm_tc_kernel(const float* __restrict__ a, const float* __restrict__ w, in
         for (int it = 0; it < 8; ++it) {
           int item = it * 128 + lt, r = item >> 3, j = item & 7;
           if (row0 + r < R) {
-            ld8(a + (row0 + r) * K + kb * 64 + j * 8, v[2 * it], v[2 * it + 1]);
+            ld8(a + (row0 + r) * lda + kb * 64 + j * 8, v[2 * it], v[2 * it + 1]);
           } else {
             v[2 * it] = v[2 * it + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
@@ -152,7 +161,8 @@ rows_gemm_tc_kernel(const float* __restrict__ a, const float* __restrict__ w, in
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           int item = it * 128 + lt;
-          st_block_chunk(blk, item >> 3, item & 7, v[2 * it], v[2 * it + 1]);
+          if (split) st_block_chunk_split(blk, blk + kBlk, item >> 3, item & 7, v[2 * it], v[2 * it + 1]);
+          else st_block_chunk(blk, item >> 3, item & 7, v[2 * it], v[2 * it + 1]);
         }
         fence_async_smem();
         mbar_arrive(&a_full[st]);
@@ -170,17 +180,22 @@ rows_gemm_tc_kernel(const float* __restrict__ a, const float* __restrict__ w, in
           tc_fence_after();
           for (int kb = 0; kb < KB; ++kb) {
             const uint32_t chunk = chunk0 + kb;
-            const int st = chunk % kRingA;
+            const int st = chunk % ring;
             if (nc == 0) {
-              mbar_wait(&a_full[st], (chunk / kRingA) & 1);
+              mbar_wait(&a_full[st], (chunk / ring) & 1);
               tc_fence_after();
             }
-            const uint32_t a_addr = smem_u32(sA + st * kBlk);
+            const uint32_t a_addr = smem_u32(sA + st * a_stage);
             const uint32_t b_addr = smem_u32(sW + kb * (N * 128) + nc * kBlk);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
+            for (int k = 0; k < 4; ++k) {
               umma_bf16(tmem_base + buf * 128, make_sdesc(a_addr + k * 32, 16, 1024), make_sdesc(b_addr + k * 32, 16, 1024),
                         idesc, (kb | k) ? 1u : 0u);
+              if (split) {       // + a_hi . w_lo + a_lo . w_hi into the same fp32 accumulator
+                umma_bf16(tmem_base + buf * 128, make_sdesc(a_addr + k * 32, 16, 1024), make_sdesc(b_addr + w_lo + k * 32, 16, 1024), idesc, 1u);
+                umma_bf16(tmem_base + buf * 128, make_sdesc(a_addr + kBlk + k * 32, 16, 1024), make_sdesc(b_addr + k * 32, 16, 1024), idesc, 1u);
+              }
+            }
             if (nc == NC - 1) umma_commit(&a_empty[st]);
           }
           umma_commit(&acc_full[buf]);
@@ -207,7 +222,7 @@ rows_gemm_tc_kernel(const float* __restrict__ a, const float* __restrict__ w, in
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
               const long long grow = row0 + it * 8 + (lane >> 2);
-              gq[(cg & 1) * 4 + it] = (grow < R) ? *reinterpret_cast<const uint4*>(gate16 + grow * N + nc * 128 + cg * 32 + c8)
+              gq[(cg & 1) * 4 + it] = (grow < R) ? *reinterpret_cast<const uint4*>(gate16 + grow * ldo + nc * 128 + cg * 32 + c8)
                                                  : make_uint4(0, 0, 0, 0);
             }
           };
@@ -246,7 +261,7 @@ rows_gemm_tc_kernel(const float* __restrict__ a, const float* __restrict__ w, in
                 }
               }
               if (grow < R)
-                *reinterpret_cast<uint4*>(out16 + grow * N + col) =
+                *reinterpret_cast<uint4*>(out16 + grow * ldo + col) =
                     make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
             }
             if (gate && cg + 2 < 4) gate_fetch(cg + 2);
@@ -279,8 +294,8 @@ rows_gemm_tc_kernel(const float* __restrict__ a, const float* __restrict__ w, in
               const int r = (half * 4 + u) * 4 + (lane >> 3);
               const long long grow = row0 + r;
               o[u] = ld4(stg + r * kStage + (lane & 7) * 4);
-              gz[u] = (gate && grow < R) ? ld4(gate + grow * N + col) : make_float4(1.f, 1.f, 1.f, 1.f);
-              rz[u] = (resid && grow < R) ? ld4(resid + grow * N + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+              gz[u] = (gate && grow < R) ? ld4(gate + grow * ldo + col) : make_float4(1.f, 1.f, 1.f, 1.f);
+              rz[u] = (resid && grow < R) ? ld4(resid + grow * ldo + col) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -288,12 +303,16 @@ rows_gemm_tc_kernel(const float* __restrict__ a, const float* __restrict__ w, in
               const long long grow = row0 + r;
               float4 v4 = o[u];
               v4.x += bz.x; v4.y += bz.y; v4.z += bz.z; v4.w += bz.w;
+              if (flags & kResidPre) {     // resid = the partial sum of earlier K slices: it belongs INSIDE the ReLU / gate
+                v4.x += rz[u].x; v4.y += rz[u].y; v4.z += rz[u].z; v4.w += rz[u].w;
+                rz[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
               if (relu) { v4.x = fmaxf(v4.x, 0.f); v4.y = fmaxf(v4.y, 0.f); v4.z = fmaxf(v4.z, 0.f); v4.w = fmaxf(v4.w, 0.f); }
               v4.x = (gz[u].x > 0.f ? v4.x : 0.f) + rz[u].x;
               v4.y = (gz[u].y > 0.f ? v4.y : 0.f) + rz[u].y;
               v4.z = (gz[u].z > 0.f ? v4.z : 0.f) + rz[u].z;
               v4.w = (gz[u].w > 0.f ? v4.w : 0.f) + rz[u].w;
-              if (grow < R) st4(out + grow * N + col, v4);
+              if (grow < R) st4(out + grow * ldo + col, v4);
             }
           }
           __syncwarp();
@@ -318,13 +337,16 @@ constexpr int kTnBlk = kTnRows * 128;     // [64 rows][64 ch] block, bytes
 __global__ void __launch_bounds__(kTnThreads, 1)
 gemm_tn_tc_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
                   float* __restrict__ colsum_a, long long R, int M, int N, long long tiles_per_cta, int stages, int flags,
-                  int prefetch) {
+                  int prefetch, int lda, int ldb, int ldo, int split) {
+  // lda / ldb / ldo: row pitches (elements) of a, b, out (column slices of wider tensors); split: bf16x3 operands -- every
+  // stage holds the hi blocks of a and b followed by their lo blocks
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment as an OFFSET from the __shared__ array: a pointer rebuilt from an integer loses its address
   // space and every access through it compiles to generic LD/ST (LSU long-scoreboard path) instead of LDS/STS
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int nblk = (M + N) / 64;                       // operand blocks per stage: a's first, then b's
-  const int stage_bytes = nblk * kTnBlk;
+  const int lo_off = nblk * kTnBlk;                    // split: offset of the lo copies inside a stage
+  const int stage_bytes = nblk * kTnBlk * (split ? 2 : 1);
   uint8_t* sOp = smem;
   float* sStage = reinterpret_cast<float*>(smem + stages * stage_bytes);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes + 4 * 32 * kStage * 4);
@@ -365,8 +387,8 @@ gemm_tn_tc_kernel(const float* __restrict__ a, const float* __restrict__ b, floa
         const long long p0 = (tile + (it_ < 2 ? 1 : 4)) * kTnRows, p1 = (tile + 5 < t1 ? tile + 5 : t1) * kTnRows;
         const long long pe = p1 < R ? p1 : R;
         if (pe > p0) {
-          bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(a) + p0 * M * ((flags & DG_A_BF16) ? 2 : 4), (pe - p0) * M * ((flags & DG_A_BF16) ? 2 : 4));
-          bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(b) + p0 * N * ((flags & DG_OUT_BF16) ? 2 : 4), (pe - p0) * N * ((flags & DG_OUT_BF16) ? 2 : 4));
+          if (lda == M) bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(a) + p0 * M * ((flags & DG_A_BF16) ? 2 : 4), (pe - p0) * M * ((flags & DG_A_BF16) ? 2 : 4));
+          if (ldb == N) bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(b) + p0 * N * ((flags & DG_OUT_BF16) ? 2 : 4), (pe - p0) * N * ((flags & DG_OUT_BF16) ? 2 : 4));
         }
       }
       const int st = it_ % stages;
@@ -380,7 +402,7 @@ gemm_tn_tc_kernel(const float* __restrict__ a, const float* __restrict__ b, floa
 #pragma unroll
       for (int seg = 0; seg < 2; ++seg) {
         const float* src = seg == 0 ? a : b;
-        const int ld = seg == 0 ? M : N, nb = seg == 0 ? MA : nblk - MA, blk_off = seg == 0 ? 0 : MA;
+        const int ld = seg == 0 ? lda : ldb, nb = seg == 0 ? MA : nblk - MA, blk_off = seg == 0 ? 0 : MA;
         const bool src16 = seg == 0 ? (flags & DG_A_BF16) : (flags & DG_OUT_BF16);
         const bool sum = seg == 0 && colsum_a != nullptr;
         if (src16) {
@@ -436,7 +458,9 @@ gemm_tn_tc_kernel(const float* __restrict__ a, const float* __restrict__ b, floa
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 int item = q * 128 + lt;
-                st_block_chunk(base + (blk_off + g0 + h) * kTnBlk, item >> 3, item & 7, v[h * 8 + 2 * q], v[h * 8 + 2 * q + 1]);
+                uint8_t* bp = base + (blk_off + g0 + h) * kTnBlk;
+                if (split) st_block_chunk_split(bp, bp + lo_off, item >> 3, item & 7, v[h * 8 + 2 * q], v[h * 8 + 2 * q + 1]);
+                else st_block_chunk(bp, item >> 3, item & 7, v[h * 8 + 2 * q], v[h * 8 + 2 * q + 1]);
               }
               if (sum && g0 + h < 6) {
                 float* acc = cs[g0 + h];
@@ -484,6 +508,12 @@ gemm_tn_tc_kernel(const float* __restrict__ a, const float* __restrict__ b, floa
               const int nn = N - n0 < 256 ? N - n0 : 256;
               const uint64_t db = make_sdesc(b_addr + (n0 / 64) * kTnBlk + ks * 2048, kTnBlk, 1024);
               umma_bf16(tmem_base + mb * N + n0, da, db, make_idesc(128, nn, 1, 1), (it_ | ks) ? 1u : 0u);
+              if (split) {       // + a_hi^T b_lo + a_lo^T b_hi into the same fp32 accumulator
+                umma_bf16(tmem_base + mb * N + n0, da, make_sdesc(b_addr + lo_off + (n0 / 64) * kTnBlk + ks * 2048, kTnBlk, 1024),
+                          make_idesc(128, nn, 1, 1), 1u);
+                umma_bf16(tmem_base + mb * N + n0, make_sdesc(a_addr + lo_off + mb * 2 * kTnBlk + ks * 2048, kTnBlk, 1024), db,
+                          make_idesc(128, nn, 1, 1), 1u);
+              }
             }
           }
         }
@@ -511,7 +541,7 @@ gemm_tn_tc_kernel(const float* __restrict__ a, const float* __restrict__ b, floa
             const int r = rr * 4 + (lane >> 3);
             const int m = mb * 128 + warp * 32 + r;
             float4 o = ld4(stg + r * kStage + (lane & 7) * 4);
-            float* dst = out + (long long)m * N + cg * 32 + (lane & 7) * 4;
+            float* dst = out + (long long)m * ldo + cg * 32 + (lane & 7) * 4;
             atomicAdd(dst + 0, o.x); atomicAdd(dst + 1, o.y); atomicAdd(dst + 2, o.z); atomicAdd(dst + 3, o.w);
           }
           __syncwarp();
@@ -540,20 +570,10 @@ static bool rows_tc_ok(int K, int N) {
   return tc::rows_smem(K, N).total + 1024 <= 227 * 1024;
 }
 
-int rows_gemm_tc(const void* a_, const float* w, int w_is_nk, const float* bias, int relu, const void* gate_,
-                 const float* resid, void* out_, long long R, int K, int N, int prec, int flags, cudaStream_t s) {
-  const float* a = (const float*)a_;
-  const float* gate = (const float*)gate_;
-  float* out = (float*)out_;
-  if (!rows_tc_ok(K, N)) {
-    if (flags) return fail("dg_rows_gemm: bf16 storage is only available for the tcgen05 shapes (K=%d N=%d)", K, N);
-    return rows_gemm_fp32(a, w, w_is_nk, bias, relu, gate, resid, out, R, K, N, s);
-  }
-  if ((flags & DG_OUT_BF16) && (resid || (gate && !(flags & DG_GATE_BF16))))
-    return fail("dg_rows_gemm: a bf16 output takes no resid and only a bf16 gate");
-  if (!(flags & DG_OUT_BF16) && (flags & DG_GATE_BF16)) return fail("dg_rows_gemm: a bf16 gate needs a bf16 output");
-  if (!(flags & DG_A_BF16) && (reinterpret_cast<uintptr_t>(a) & 31)) return fail("dg_rows_gemm: a must be 32-byte aligned (256-bit loads)");
-  const int smem = tc::rows_smem(K, N).total + 1024;
+static int rows_gemm_tc_launch(const float* a, const float* w, int w_is_nk, const float* bias, int relu, const float* gate,
+                               const float* resid, float* out, long long R, int K, int N, int flags, int lda, int ldw, int ldo,
+                               int split, cudaStream_t s) {
+  const int smem = tc::rows_smem(K, N, split).total + 1024;
   {   // per-device attribute: set on every launch (a host-side table lookup) so that every device of the process is configured
     cudaError_t e = cudaFuncSetAttribute(tc::rows_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail("cudaFuncSetAttribute(rows_gemm_tc): %s", cudaGetErrorString(e));
@@ -561,22 +581,52 @@ int rows_gemm_tc(const void* a_, const float* w, int w_is_nk, const float* bias,
   long long tiles = (R + 127) / 128;
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   tc::rows_gemm_tc_kernel<<<grid, tc::kThreads, smem, s>>>(a, w, w_is_nk, bias, relu, gate, resid, out, R, K, N, flags,
-                                                           opt_get(DG_OPT_L2_PREFETCH) & DG_PF_ROWS_GEMM);
-  return check_launch("dg_rows_gemm(bf16)");
+                                                           opt_get(DG_OPT_L2_PREFETCH) & DG_PF_ROWS_GEMM, lda, ldw, ldo, split);
+  return check_launch(split ? "dg_rows_gemm(bf16x3)" : "dg_rows_gemm(bf16)");
 }
 
-int gemm_tn_tc(const void* a_, const void* b_, float* out, float* colsum_a, long long R, int M, int N, int prec, int flags,
-               cudaStream_t s) {
+int rows_gemm_tc(const void* a_, const float* w, int w_is_nk, const float* bias, int relu, const void* gate_,
+                 const float* resid, void* out_, long long R, int K, int N, int prec, int flags, cudaStream_t s) {
   const float* a = (const float*)a_;
-  const float* b = (const float*)b_;
-  const bool ok = M % 128 == 0 && N % 128 == 0 && M >= 128 && N >= 128 && (M / 128) * N <= 512 && N <= 384 && M <= 384;
-  if (!ok) {
-    if (flags) return fail("dg_gemm_tn: bf16 storage is only available for the tcgen05 shapes (M=%d N=%d)", M, N);
-    return gemm_tn_fp32(a, b, out, colsum_a, R, M, N, s);
+  const float* gate = (const float*)gate_;
+  float* out = (float*)out_;
+  const bool split = prec == DG_PREC_BF16X3;
+  if (!rows_tc_ok(K, N) || (split && (K % 128 || N % 128))) {
+    if (flags) return fail("dg_rows_gemm: bf16 storage is only available for the tcgen05 shapes (K=%d N=%d)", K, N);
+    return rows_gemm_fp32(a, w, w_is_nk, bias, relu, gate, resid, out, R, K, N, s);
   }
-  if ((!(flags & DG_A_BF16) && (reinterpret_cast<uintptr_t>(a) & 31)) || (!(flags & DG_OUT_BF16) && (reinterpret_cast<uintptr_t>(b) & 31)))
-    return fail("dg_gemm_tn: fp32 operands must be 32-byte aligned (256-bit loads)");
-  const int stage_bytes = (M + N) / 64 * tc::kTnBlk;
+  if (!(flags & DG_A_BF16) && (reinterpret_cast<uintptr_t>(a) & 31)) return fail("dg_rows_gemm: a must be 32-byte aligned (256-bit loads)");
+  if (split) {
+    // Split-precision parity mode: three bf16 MMAs per product term on hi / lo operand blocks, fp32 everywhere else.  Twice the
+    // shared memory per operand, so a launch takes a 128 x 128 weight block: wider shapes run as column slices -- N slices are
+    // independent, K slices accumulate through the resid path (the epilogue must then be linear: no ReLU / gate on K > 128).
+    if (flags) return fail("dg_rows_gemm: the bf16x3 mode keeps every tensor fp32 (no bf16 storage flags)");
+    const bool nonlinear = relu || gate;
+    if (K > 128 && nonlinear && resid) return fail("dg_rows_gemm(bf16x3): resid together with a ReLU / gate epilogue needs K == 128, got K=%d", K);
+    const int ldw = w_is_nk ? K : N;
+    for (int n0 = 0; n0 < N; n0 += 128)
+      for (int k0 = 0; k0 < K; k0 += 128) {
+        const bool first = k0 == 0, last = k0 + 128 >= K;
+        const float* ws = w_is_nk ? w + (long long)n0 * K + k0 : w + (long long)k0 * N + n0;
+        // K slices accumulate through the resid path: out = slice + what is there.  A nonlinear epilogue runs on the LAST slice
+        // only, with the earlier partial sums added inside it (kResidPre); a linear one takes the caller's resid on the first.
+        const float* rs = first ? (resid ? resid + n0 : nullptr) : out + n0;
+        const bool epi = nonlinear && last;
+        if (rows_gemm_tc_launch(a + k0, ws, w_is_nk, (bias && first) ? bias + n0 : nullptr, epi ? relu : 0, (epi && gate) ? gate + n0 : nullptr,
+                                rs, out + n0, R, 128, 128, (epi && !first) ? tc::kResidPre : 0, K, ldw, N, 1, s))
+          return 1;
+      }
+    return 0;
+  }
+  if ((flags & DG_OUT_BF16) && (resid || (gate && !(flags & DG_GATE_BF16))))
+    return fail("dg_rows_gemm: a bf16 output takes no resid and only a bf16 gate");
+  if (!(flags & DG_OUT_BF16) && (flags & DG_GATE_BF16)) return fail("dg_rows_gemm: a bf16 gate needs a bf16 output");
+  return rows_gemm_tc_launch(a, w, w_is_nk, bias, relu, gate, resid, out, R, K, N, flags, K, w_is_nk ? K : N, N, 0, s);
+}
+
+static int gemm_tn_tc_launch(const float* a, const float* b, float* out, float* colsum_a, long long R, int M, int N, int flags,
+                             int lda, int ldb, int ldo, int split, cudaStream_t s) {
+  const int stage_bytes = (M + N) / 64 * tc::kTnBlk * (split ? 2 : 1);
   int stages = (200 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) return fail("dg_gemm_tn: shape does not fit shared memory");
@@ -590,8 +640,33 @@ int gemm_tn_tc(const void* a_, const void* b_, float* out, float* colsum_a, long
   long long per = (tiles + ctas - 1) / ctas;
   ctas = (tiles + per - 1) / per;
   tc::gemm_tn_tc_kernel<<<(int)ctas, tc::kTnThreads, smem, s>>>(a, b, out, colsum_a, R, M, N, per, stages, flags,
-                                                                opt_get(DG_OPT_L2_PREFETCH) & (M + N == 256 ? DG_PF_GEMM_TN : DG_PF_GEMM_TN_WIDE));
-  return check_launch("dg_gemm_tn(bf16)");
+                                                                opt_get(DG_OPT_L2_PREFETCH) & (M + N == 256 ? DG_PF_GEMM_TN : DG_PF_GEMM_TN_WIDE),
+                                                                lda, ldb, ldo, split);
+  return check_launch(split ? "dg_gemm_tn(bf16x3)" : "dg_gemm_tn(bf16)");
+}
+
+int gemm_tn_tc(const void* a_, const void* b_, float* out, float* colsum_a, long long R, int M, int N, int prec, int flags,
+               cudaStream_t s) {
+  const float* a = (const float*)a_;
+  const float* b = (const float*)b_;
+  const bool split = prec == DG_PREC_BF16X3;
+  const bool ok = M % 128 == 0 && N % 128 == 0 && M >= 128 && N >= 128 && (M / 128) * N <= 512 && N <= 384 && M <= 384;
+  if (!ok) {
+    if (flags) return fail("dg_gemm_tn: bf16 storage is only available for the tcgen05 shapes (M=%d N=%d)", M, N);
+    return gemm_tn_fp32(a, b, out, colsum_a, R, M, N, s);
+  }
+  if ((!(flags & DG_A_BF16) && (reinterpret_cast<uintptr_t>(a) & 31)) || (!(flags & DG_OUT_BF16) && (reinterpret_cast<uintptr_t>(b) & 31)))
+    return fail("dg_gemm_tn: fp32 operands must be 32-byte aligned (256-bit loads)");
+  if (split) {      // 128 x 128 output blocks per launch (twice the operand bytes per stage); the bias gradient rides on the first N slice
+    if (flags) return fail("dg_gemm_tn: the bf16x3 mode keeps every tensor fp32 (no bf16 storage flags)");
+    for (int m0 = 0; m0 < M; m0 += 128)
+      for (int n0 = 0; n0 < N; n0 += 128)
+        if (gemm_tn_tc_launch(a + m0, b + n0, out + (long long)m0 * N + n0, (colsum_a && n0 == 0) ? colsum_a + m0 : nullptr, R, 128, 128, 0,
+                              M, N, N, 1, s))
+          return 1;
+    return 0;
+  }
+  return gemm_tn_tc_launch(a, b, out, colsum_a, R, M, N, flags, M, N, N, 0, s);
 }
 
 }  // namespace dg

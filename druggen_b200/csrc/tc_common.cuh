@@ -139,5 +139,20 @@ __device__ __forceinline__ void st_block_chunk(uint8_t* blk, int r, int j, float
   *reinterpret_cast<uint4*>(blk + r * 128 + ((j ^ (r & 7)) << 4)) = v;
 }
 
+// split-precision operands (DG_PREC_BF16X3): x = hi + lo with hi = bf16(x), lo = bf16(x - hi) -- 16 mantissa bits between them;
+// a . b ~= a_hi b_hi + a_hi b_lo + a_lo b_hi accumulated in fp32 (the dropped a_lo b_lo term is 2^-18 relative)
+__device__ __forceinline__ void split_bf16(float x, float& hi, float& lo) {
+  hi = __bfloat162float(__float2bfloat16_rn(x));
+  lo = x - hi;
+}
+__device__ __forceinline__ void st_block_chunk_split(uint8_t* blk_hi, uint8_t* blk_lo, int r, int j, float4 a, float4 b) {
+  float h[8], l[8];
+  split_bf16(a.x, h[0], l[0]); split_bf16(a.y, h[1], l[1]); split_bf16(a.z, h[2], l[2]); split_bf16(a.w, h[3], l[3]);
+  split_bf16(b.x, h[4], l[4]); split_bf16(b.y, h[5], l[5]); split_bf16(b.z, h[6], l[6]); split_bf16(b.w, h[7], l[7]);
+  const int off = r * 128 + ((j ^ (r & 7)) << 4);
+  *reinterpret_cast<uint4*>(blk_hi + off) = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+  *reinterpret_cast<uint4*>(blk_lo + off) = make_uint4(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]), pack_bf16(l[4], l[5]), pack_bf16(l[6], l[7]));
+}
+
 }  // namespace tc
 }  // namespace dg

@@ -19,8 +19,10 @@ from . import _lib
 
 # precision of the dense contractions (GEMMs).  Everything else is always fp32.
 #   fp32   : CUDA-core fp32 FMA GEMM (parity mode; bit-for-bit fp32 accumulate)
-#   bf16   : tcgen05 bf16 x bf16 -> fp32 (TMEM accumulators)           -- throughput mode
-PRECISIONS = ("fp32", "bf16")
+#   bf16x3 : tcgen05 split precision -- every fp32 operand as hi + lo bf16, three MMAs per product, fp32 accumulation in TMEM
+#            (tensor-core parity mode: 16 operand mantissa bits; everything stays fp32 in HBM)
+#   bf16   : tcgen05 bf16 x bf16 -> fp32 (TMEM accumulators), fused chains, bf16 storage of operand-only tensors -- throughput mode
+PRECISIONS = ("fp32", "bf16x3", "bf16")
 _precision = os.environ.get("DRUGGEN_B200_PRECISION", "bf16")
 
 

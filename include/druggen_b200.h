@@ -15,6 +15,9 @@
  *   - `prec` selects the arithmetic of the dense contractions only:
  *       DG_PREC_FP32   CUDA-core fp32 FMA                     (parity mode)
  *       DG_PREC_BF16   tcgen05.mma kind::f16 bf16 x bf16 -> fp32 in TMEM   (throughput mode)
+ *       DG_PREC_BF16X3 tcgen05 split precision: every fp32 operand x = hi + lo (two bf16), a.b = a_hi b_hi + a_hi b_lo + a_lo b_hi
+ *                      accumulated in fp32 in TMEM -- 16 operand mantissa bits on the tensor cores (tensor-core parity mode);
+ *                      all tensors stay fp32 in HBM, shapes wider than 128 run as 128-wide slices
  *     every other operation (LayerNorm, softmax, modulation, reductions) is fp32 in all modes.
  */
 #ifndef DRUGGEN_B200_H
@@ -27,6 +30,7 @@ extern "C" {
 #define DG_ABI_VERSION 3
 #define DG_PREC_FP32 0
 #define DG_PREC_BF16 1
+#define DG_PREC_BF16X3 2
 
 int dg_abi_version(void);
 /* Thread-local text of the last rejected call. */

@@ -21,6 +21,10 @@ class EmulBackend:
     def _mm(self, a, b, prec):
         if self.emulate_bf16 and prec == "bf16":
             return _bf16r(a) @ _bf16r(b)
+        if self.emulate_bf16 and prec == "bf16x3":       # hi + lo operands, three products, wide accumulation (csrc/gemm_tc.cu)
+            ah, bh = _bf16r(a), _bf16r(b)
+            al, bl = _bf16r(a - ah), _bf16r(b - bh)
+            return (ah.double() @ bh.double() + ah.double() @ bl.double() + al.double() @ bh.double()).to(a.dtype)
         return a @ b
 
     # ---- dense

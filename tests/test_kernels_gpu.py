@@ -23,7 +23,7 @@ def _opr(t, tc):
     return (t.to(torch.bfloat16) if tc else t).double()
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "bf16x3"])
 @pytest.mark.parametrize("R,Kd,Nd", [(1, 128, 128), (257, 128, 384), (1000, 384, 128), (2025 * 3, 128, 128), (77, 32, 32),
                                      (128 * 148 * 3 + 5, 128, 128), (40000, 128, 384), (40000, 384, 128)])
 def test_rows_gemm(cuda_dev, prec, R, Kd, Nd):
@@ -34,15 +34,21 @@ def test_rows_gemm(cuda_dev, prec, R, Kd, Nd):
             w = rnd(cuda_dev, Nd, Kd, seed=1) if w_is_nk else rnd(cuda_dev, Kd, Nd, seed=1)
             tc = prec == "bf16" and Kd % 64 == 0 and Nd % 128 == 0
             ref = _opr(a, tc) @ (_opr(w, tc).t() if w_is_nk else _opr(w, tc))
-            assert rel_l2(K.rows_gemm(a, w, w_is_nk), ref) < 2e-6
+            # bf16x3: operands carry 16 mantissa bits (hi + lo), the a_lo w_lo term is dropped: ~1e-5 on a K = 128..384 dot product
+            tol = 3e-5 if prec == "bf16x3" else 2e-6
+            assert rel_l2(K.rows_gemm(a, w, w_is_nk), ref) < tol
             got = K.rows_gemm(a, w, w_is_nk, bias, True, gate)
             want = torch.relu(ref + bias.double()) * (gate > 0)
-            assert rel_l2(got, want) < 2e-6
+            assert rel_l2(got, want) < tol
+            if prec == "bf16x3" and Kd > 128:                                    # (K-sliced launches: resid only with a linear epilogue)
+                got = K.rows_gemm(a, w, w_is_nk, bias, resid=gate)
+                assert rel_l2(got, ref + bias.double() + gate.double()) < tol
+                continue
             got = K.rows_gemm(a, w, w_is_nk, None, False, gate, resid=gate)      # fused gradient accumulation
-            assert rel_l2(got, ref * (gate > 0) + gate.double()) < 2e-6
+            assert rel_l2(got, ref * (gate > 0) + gate.double()) < tol
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "bf16x3"])
 @pytest.mark.parametrize("R,M,N", [(1, 128, 128), (333, 128, 384), (2025 * 4 + 5, 384, 128), (50, 32, 64),
                                    (64 * 148 * 5 + 3, 128, 128), (100000, 128, 384), (100000, 384, 128)])
 def test_gemm_tn(cuda_dev, prec, R, M, N):
@@ -51,10 +57,11 @@ def test_gemm_tn(cuda_dev, prec, R, M, N):
         got = K.gemm_tn(a, b)
         tc = prec == "bf16" and M % 128 == 0 and N % 128 == 0
         ref = _opr(a, tc).t() @ _opr(b, tc)
-        assert rel_l2(got, ref) < 5e-6
+        tol = 3e-5 if prec == "bf16x3" else 5e-6
+        assert rel_l2(got, ref) < tol
         cs = torch.zeros(M, device=cuda_dev)
         acc = K.gemm_tn(a, b, out=got.clone(), colsum_a=cs)
-        assert rel_l2(acc, 2 * ref) < 5e-6
+        assert rel_l2(acc, 2 * ref) < tol
         assert rel_l2(cs, a.double().sum(0)) < 5e-6          # bias gradient from the same pass, exact fp32 inputs
 
 

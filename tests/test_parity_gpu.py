@@ -14,6 +14,12 @@ from oracle import encoder_oracle as orc
 
 pytestmark = pytest.mark.gpu
 PARITY_TOL = 1e-3
+# Parameter gradients are discontinuous at ReLU sign changes (layers.py:52): a forward perturbation eps flips ~eps of the hidden
+# units and moves the gradients by ~sqrt(eps).  The fp32 reference evaluated with 8 threads instead of 1 already differs from the
+# fp64 truth by 2.2e-3 on the depth-8 G-step gradients (tools/oracle_noise.py, profiles/r02_oracle_noise.json).  The fp32 mode
+# (forward error 1.5e-7) happens to stay under 1e-3; the tensor-core parity mode bf16x3 (forward error 2e-6, losses 1e-6) is bounded
+# at 5e-3 per gradient tensor -- the reference's own fp32 noise level.
+GRAD_TOL = {"fp32": 1e-3, "bf16x3": 5e-3}
 
 
 def _tc_built():
@@ -26,7 +32,7 @@ def _tc_built():
         return False
 
 
-@pytest.fixture(params=["fp32"])
+@pytest.fixture(params=["fp32", "bf16x3"])
 def parity_mode(request):
     if request.param != "fp32" and not _tc_built():
         pytest.skip("tcgen05 contractions not built")
@@ -88,7 +94,7 @@ def test_encoder_n45_depth2_fwd_bwd_vs_oracle(cuda_dev, parity_mode):
     assert rel_l2(xo, xr) < PARITY_TOL and rel_l2(yo, yr) < PARITY_TOL
     assert rel_l2(xg.grad, x.grad) < PARITY_TOL and rel_l2(yg.grad, y.grad) < PARITY_TOL
     for k, v in enc.named_parameters():
-        assert rel_l2(v.grad, p[k].grad) < PARITY_TOL, k
+        assert rel_l2(v.grad, p[k].grad) < GRAD_TOL[parity_mode], k
 
 
 def _models(g, dev):
@@ -139,7 +145,7 @@ def test_gan_step_golden(cuda_dev, parity_mode):
     g_loss.backward()
     assert abs(g_loss.item() - float(g["g_loss"])) < PARITY_TOL * max(1.0, abs(float(g["g_loss"])))
     for k, v in G.named_parameters():
-        assert rel_l2(v.grad, g["gG_G::" + k]) < PARITY_TOL, k
+        assert rel_l2(v.grad, g["gG_G::" + k]) < GRAD_TOL[parity_mode], k
 
 
 def test_bf16_mode_error_is_reported(cuda_dev):
@@ -267,9 +273,9 @@ def test_bf16_mode_depth8_error_and_decode_flips_reported(cuda_dev, capsys):
 # measured on B200 (printed by the test below, profiles/r02_parity_depth8.json); the bounds are ~2x the measurement
 DEPTH8_BOUNDS = {
     # mode: (loss rel, D-grad rel-L2 over the whole parameter vector, G-grad rel-L2 over the whole parameter vector)
-    "fp32": (1e-3, 5e-3, 1e-3),
-    "bf16x3": (1e-3, 5e-3, 1e-3),
-    "bf16": (5e-2, 3e-1, 3e-1),
+    "fp32": (1e-3, 5e-3, 1e-3),           # measured 1e-7 / 1.1e-6 / 5.2e-7
+    "bf16x3": (1e-3, 5e-3, 5e-3),         # measured 7e-7 / 5.5e-4 / 2.4e-3  (ReLU-flip limited, see GRAD_TOL)
+    "bf16": (1e-3, 6e-2, 8e-2),           # measured 2.7e-4 / 2.6e-2 / 3.6e-2
 }
 
 
@@ -280,7 +286,7 @@ def _flat(grads):
 @pytest.mark.parametrize("mode", ["fp32", "bf16x3", "bf16"])
 def test_gan_step_depth8_n45_vs_oracle(cuda_dev, mode, capsys):
     """The step the bench times -- depth 8, N = 45, D loss with the gradient penalty's double backward, G loss -- in EVERY
-    precision mode against the fp32 CPU oracle: both losses, every Discriminator gradient of the D-step (gradient penalty
+    precision mode against the CPU oracle evaluated in fp64: both losses, every Discriminator gradient of the D-step (gradient penalty
     included), every Generator gradient of the G-step.  Prints the errors (and stores them for profiles/) and bounds them."""
     import json
     import os
@@ -292,15 +298,17 @@ def test_gan_step_depth8_n45_vs_oracle(cuda_dev, mode, capsys):
     n, bsz = 45, 2
     G = dg.Generator("relu", n, 5, 13, 0.0, dim=128, depth=8, heads=8, mlp_ratio=3)
     D = dg.Discriminator("relu", n, 5, 13, 0.0, dim=128, depth=8, heads=8, mlp_ratio=3)
-    ref = orc.OracleGAN(dict(G.state_dict()), dict(D.state_dict()), 8, 8, 8)
+    # the oracle in fp64: the fp32 oracle's own gradients carry up to 2e-3 of thread-count-dependent noise (GRAD_TOL above)
+    f64 = lambda t: t.double()  # noqa: E731
+    ref = orc.OracleGAN({k: f64(v) for k, v in G.state_dict().items()}, {k: f64(v) for k, v in D.state_dict().items()}, 8, 8, 8)
     a, x = orc.synthetic_batch(bsz, n, 13, 5, seed=3)
     da, dx = orc.synthetic_batch(bsz, n, 13, 5, seed=4)
     eps_e, eps_n = torch.rand(bsz, 1, 1, 1), torch.rand(bsz, 1, 1)
-    d_ref = ref.d_loss(da, dx, a, x, eps_e, eps_n)
+    d_ref = ref.d_loss(f64(da), f64(dx), f64(a), f64(x), f64(eps_e), f64(eps_n))
     d_ref.backward()
-    gD_ref = {k: v.grad.clone() for k, v in ref.dp_.items() if v.grad is not None and float(v.grad.abs().max()) > 0}
+    gD_ref = {k: v.grad.clone() for k, v in ref.dp_.items() if v.grad is not None and float(v.grad.abs().max()) > 1e-12}
     ref._zero()
-    g_ref = ref.g_loss(a, x)
+    g_ref = ref.g_loss(f64(a), f64(x))
     g_ref.backward()
     gG_ref = {k: v.grad.clone() for k, v in ref.gp_.items()}
     G.to(cuda_dev), D.to(cuda_dev)
@@ -313,7 +321,7 @@ def test_gan_step_depth8_n45_vs_oracle(cuda_dev, mode, capsys):
         g = orc.generator_loss(G, D, dev(a), dev(x))
         g.backward()
         gG = {k: v.grad.clone() for k, v in G.named_parameters()}
-    assert set(gD) == set(gD_ref)
+    assert set(gD_ref) <= set(gD)       # (node_mlp.6.bias: exactly 0 in the oracle -- fake - real + gp -- and rounding noise here)
     rec = {"mode": mode, "depth": 8, "atoms": n, "batch": bsz,
            "d_loss_rel": abs(d.item() - d_ref.item()) / max(1.0, abs(d_ref.item())),
            "g_loss_rel": abs(g.item() - g_ref.item()) / max(1.0, abs(g_ref.item())),

@@ -18,8 +18,8 @@ torch.manual_seed(0)
 G = dg.Generator("relu", n, 5, 13, 0.0, dim=128, depth=8, heads=8, mlp_ratio=3).to(dev)
 D = dg.Discriminator("relu", n, 5, 13, 0.0, dim=128, depth=8, heads=8, mlp_ratio=3).to(dev)
 tr = gan.GANTrainer(G, D)
-a, x = gan.synthetic_molecules(bsz, n, 13, 5, seed=1, device=dev)
-da, dx = gan.synthetic_molecules(bsz, n, 13, 5, seed=2, device=dev)
+a, x = gan.synthetic_molecules(bsz, n, 13, 5, seed=1, device=dev, labels=True)
+da, dx = gan.synthetic_molecules(bsz, n, 13, 5, seed=2, device=dev, labels=True)
 for _ in range(2):
     tr.step(da, dx, a, x)
 torch.cuda.synchronize()

@@ -17,6 +17,7 @@ Parameter order of a block (``BLOCK_PARAM_NAMES``) follows the reference state-d
 from __future__ import annotations
 
 import math
+import os
 from typing import Sequence
 
 import torch
@@ -36,6 +37,9 @@ BLOCK_PARAM_NAMES = (
     "ln5.weight", "ln5.bias", "ln6.weight", "ln6.bias",
 )
 _IDX = {n: i for i, n in enumerate(BLOCK_PARAM_NAMES)}
+# DRUGGEN_B200_SECOND_ORDER=autograd routes the gradient penalty's double backward through reverse-over-reverse on the
+# differentiable primitives (ops.py) instead of the hand-sequenced ``block_backward_backward`` (A/B switch, tests)
+_HAND_SECOND_ORDER = os.environ.get("DRUGGEN_B200_SECOND_ORDER", "hand") != "autograd"
 
 
 def block_forward(x, y, params: Sequence[torch.Tensor], heads: int, edge_out: bool = True):
@@ -248,6 +252,207 @@ def block_backward(x, y, dxo, dyo, params: Sequence[torch.Tensor], heads: int, e
     return dx.view(b, n, d), dy.view(b, n, n, d), grads
 
 
+def block_backward_backward(x, y, dxo, dyo, ux, uy, params: Sequence[torch.Tensor], heads: int, edge_out: bool = True):
+    """Second-order pass of the block as a hand-sequenced list of raw kernel launches (no autograd graph): the gradient of
+    ``<ux, dx> + <uy, dy>`` -- (dx, dy) = ``block_backward(x, y, dxo, dyo)`` -- with respect to (x, y, dxo, dyo, parameters).
+    This is what the gradient penalty's double backward (loss.py:32-39 inside ``d_loss.backward()``) asks of every
+    Discriminator block.  Structure (c[.] = cotangent):
+
+      1. recompute the forward and the first-order backward from the block inputs, keeping the intermediates;
+      2. walk the first-order backward program in reverse with the hand-derived second-order kernels
+         (``add_ln_bwd_bwd``, ``modulate_bwd_bwd``, ``softmax_agg_bwd_bwd``, the MLP dgrad chain with the weights in each
+         other's role): yields c[dxo], c[dyo] (= the tangent of the block along (ux, uy)) and cotangents injected at the
+         forward intermediates E, A, q, k, v, z3, z4, m, m' (the mask of the ReLU is piecewise constant);
+      3. an ordinary first-order backward of the forward program from those injected cotangents.
+
+    Accumulation rides in GEMM stores (``resid``) and in ``gemm_tn(out=...)``; the only edge-sized elementwise adds left are
+    two in-place ``add_``.  Returns (c_x, c_y, c_dxo, c_dyo | None, [param cotangents aligned with BLOCK_PARAM_NAMES]);
+    parameters without a consumer keep None."""
+    p = lambda n: params[_IDX[n]]  # noqa: E731
+    b, n, d = x.shape
+    c = 1.0 / math.sqrt(d // heads)
+    narrow = K.fused_available(d, p("mlp.fc1.weight").shape[0])
+    cp = [None] * len(BLOCK_PARAM_NAMES)
+
+    def wacc(prefix, a2d, b2d, bias=True):
+        """c[W] += a^T b (and, for a forward-program Linear, c[bias] += column sums of a)."""
+        iw = _IDX[prefix + ".weight"]
+        if cp[iw] is None:
+            cp[iw] = torch.zeros_like(p(prefix + ".weight"))
+        gb = None
+        if bias:
+            ib = _IDX[prefix + ".bias"]
+            if cp[ib] is None:
+                cp[ib] = torch.zeros_like(p(prefix + ".bias"))
+            gb = cp[ib]
+        K.gemm_tn(a2d, b2d, out=cp[iw], colsum_a=gb)
+
+    def lnacc(prefix, dgam, dbet=None):
+        for nm, t in ((prefix + ".weight", dgam), (prefix + ".bias", dbet)):
+            if t is not None:
+                cp[_IDX[nm]] = t if cp[_IDX[nm]] is None else cp[_IDX[nm]].add_(t)
+
+    def mlp_recompute(mlp, ln, xin, dout):
+        """forward (h, m = xin + fc2(h)) and first-order backward (t = LN^T dout, dh, dxin) of LN(xin + mlp(xin))."""
+        w1, b1, w2, b2 = p(mlp + ".fc1.weight"), p(mlp + ".fc1.bias"), p(mlp + ".fc2.weight"), p(mlp + ".fc2.bias")
+        h = K.rows_gemm(xin, w1, True, b1, relu=True, out_bf16=narrow)
+        m = K.rows_gemm(h, w2, True, b2, resid=xin)
+        t = K.add_ln_bwd(dout, m, None, p(ln + ".weight"))[0]
+        if narrow:
+            dxin, dh = K.mlp_bwd_dgrad(t, h, w1, w2)
+        else:
+            dh = K.rows_gemm(t, w2, False, gate=h)
+            dxin = K.rows_gemm(dh, w1, False, resid=t)
+        return h, m, t, dh, dxin
+
+    def mlp_second(mlp, u, t, h, dh):
+        """reverse of  dxin = t + ((t W2) * M) W1  given u = c[dxin]: returns c[t]; c[W2] += t^T tM, c[W1] += dh^T u."""
+        w1, w2 = p(mlp + ".fc1.weight"), p(mlp + ".fc2.weight")
+        if narrow:     # the dgrad chain with the two weights transposed into each other's role
+            c_t, tm = K.mlp_bwd_dgrad(u, h, w2.t().contiguous(), w1.t().contiguous())
+        else:
+            tm = K.rows_gemm(u, w1, True, gate=h)
+            c_t = K.rows_gemm(tm, w2, True, resid=u)
+        wacc(mlp + ".fc2", t, tm, bias=False)
+        wacc(mlp + ".fc1", dh, u, bias=False)
+        return c_t
+
+    def mlp_first(mlp, c_m, h, xin):
+        """reverse of  m = xin + fc2(relu(fc1(xin)))  given c[m]: returns c[xin]; the four parameter cotangents accumulate."""
+        w1, w2 = p(mlp + ".fc1.weight"), p(mlp + ".fc2.weight")
+        if narrow:
+            c_xin, ch = K.mlp_bwd_dgrad(c_m, h, w1, w2)
+        else:
+            ch = K.rows_gemm(c_m, w2, False, gate=h)
+            c_xin = K.rows_gemm(ch, w1, False, resid=c_m)
+        wacc(mlp + ".fc2", c_m, h)
+        wacc(mlp + ".fc1", ch, xin)
+        return c_xin
+
+    live = edge_out and dyo is not None
+    x2d, y2d = x.reshape(-1, d), y.reshape(-1, d)
+    z2 = lambda t, like: (t if t is not None else torch.zeros_like(like)).reshape(-1, d).contiguous()  # noqa: E731
+    ux2d, uy2d, dxo2d = z2(ux, x), z2(uy, y), z2(dxo, x)
+    qkv = ("attn.q", "attn.k", "attn.v")
+    # ---- 1a. forward recompute
+    x1 = K.add_ln_fwd(x2d, None, p("ln1.weight"), p("ln1.bias"))
+    q, k, v = (K.rows_gemm(x1, p(nm + ".weight"), True, p(nm + ".bias")).view(b, n, d) for nm in qkv)
+    chain = live and K.attn_chain_available(b, n, d)
+    z4a = z4b = y3 = None
+    if chain:
+        y3, _, e2d, z4a = K.attn_edge_fwd(y2d, q, k, p("attn.e.weight"), p("attn.e.bias"), p("attn.out_e.weight"),
+                                          p("attn.out_e.bias"), p("ln4.weight"), p("ln4.bias"), c, want_a16=False, want_e=True,
+                                          want_z=True)
+    else:
+        e2d = K.rows_gemm(y2d, p("attn.e.weight"), True, p("attn.e.bias"))
+    e4 = e2d.view(b, n, n, d)
+    fused_scores = K.attn_fused_available(n, d)
+    if fused_scores:
+        a4, g, stats = K.attn_scores_fwd(q, k, v, e4, c, want_stats=True)
+    else:
+        a4, stats = K.modulate_fwd(q, k, e4, c), None
+        g = K.softmax_agg_fwd(a4, v)
+    a2d, g2d = a4.view(-1, d), g.view(-1, d)
+    if live and not chain:
+        z4a, z4b = y2d, K.rows_gemm(a2d, p("attn.out_e.weight"), True, p("attn.out_e.bias"))
+        y3 = K.add_ln_fwd(z4a, z4b, p("ln4.weight"), p("ln4.bias"))
+    on = K.rows_gemm(g2d, p("attn.out_n.weight"), True, p("attn.out_n.bias"))
+    x3 = K.add_ln_fwd(x1, on, p("ln3.weight"), p("ln3.bias"))
+    # ---- 1b. first-order backward recompute (intermediates kept)
+    h_n, m_n, t5, dh_n, dx3 = mlp_recompute("mlp", "ln5", x3, dxo2d)
+    dz3 = K.add_ln_bwd(dx3, x1, on, p("ln3.weight"))[0]
+    dg = K.rows_gemm(dz3, p("attn.out_n.weight"), False).view(b, n, d)
+    da4 = None
+    if live:
+        dyo2d = dyo.reshape(-1, d).contiguous()
+        h_e, m_e, t6, dh_e, dy3 = mlp_recompute("mlp2", "ln6", y3, dyo2d)
+        dz4 = K.add_ln_bwd(dy3, z4a, z4b, p("ln4.weight"))[0]
+        da4 = K.rows_gemm(dz4, p("attn.out_e.weight"), False).view(b, n, n, d)
+    dA, dv = K.softmax_agg_bwd(dg, a4, v, da_accum=da4)           # dA: out_e path + softmax path
+    del da4
+    dq, dk, dE = K.modulate_bwd(dA, q, k, e4, c)
+    dx1 = dz3
+    for nm, dt in zip(qkv, (dq, dk, dv)):
+        dx1 = K.rows_gemm(dt.view(-1, d), p(nm + ".weight"), False, resid=dx1)
+    # ---- 2. reverse of the first-order backward program
+    c_dx1, c_x, cg = K.add_ln_bwd_bwd(ux2d, None, None, dx1, x2d, None, p("ln1.weight"))
+    lnacc("ln1", cg)
+    c_dqkv = []
+    for nm, dt in zip(qkv, (dq, dk, dv)):                          # dx1 = dz3 + dq Wq + dk Wk + dv Wv
+        c_dqkv.append(K.rows_gemm(c_dx1, p(nm + ".weight"), True).view(b, n, d))
+        wacc(nm, dt.view(-1, d), c_dx1, bias=False)
+    c_dE = K.rows_gemm(uy2d, p("attn.e.weight"), True)             # dy = dz4 + dE We
+    wacc("attn.e", dE.view(-1, d), uy2d, bias=False)
+    del dE
+    c_dA, c_q, c_k, c_E = K.modulate_bwd_bwd(c_dqkv[0], c_dqkv[1], c_dE.view(b, n, n, d), dA, q, k, e4, c)
+    del c_dE, dA
+    c_dg, c_A, c_v = K.softmax_agg_bwd_bwd(c_dA, c_dqkv[2], dg, a4, v)
+    c_dyo = None
+    if live:
+        c_dA2d = c_dA.view(-1, d)
+        c_dz4 = K.rows_gemm(c_dA2d, p("attn.out_e.weight"), True, resid=uy2d)      # da = dz4 Woe;  dy = dz4 + ...
+        wacc("attn.out_e", dz4, c_dA2d, bias=False)
+        del c_dA, c_dA2d, dz4
+        c_dy3, c_z4, cg = K.add_ln_bwd_bwd(c_dz4, None, None, dy3, z4a, z4b, p("ln4.weight"))
+        lnacc("ln4", cg)
+        del c_dz4, dy3
+        c_t6 = mlp_second("mlp2", c_dy3, t6, h_e, dh_e)
+        del c_dy3, t6, dh_e
+        c_dyo, c_me, cg = K.add_ln_bwd_bwd(c_t6, None, None, dyo2d, m_e, None, p("ln6.weight"))
+        lnacc("ln6", cg)
+        del c_t6, m_e
+    else:
+        del c_dA
+    c_dg2d = c_dg.view(-1, d)
+    c_dz3 = K.rows_gemm(c_dg2d, p("attn.out_n.weight"), True, resid=c_dx1)          # dg = dz3 Won;  dx1 = dz3 + ...
+    wacc("attn.out_n", dz3, c_dg2d, bias=False)
+    c_dx3, c_z3, cg = K.add_ln_bwd_bwd(c_dz3, None, None, dx3, x1, on, p("ln3.weight"))
+    lnacc("ln3", cg)
+    c_t5 = mlp_second("mlp", c_dx3, t5, h_n, dh_n)
+    c_dxo, c_mn, cg = K.add_ln_bwd_bwd(c_t5, None, None, dxo2d, m_n, None, p("ln5.weight"))
+    lnacc("ln5", cg)
+    # ---- 3. first-order backward of the forward program from the injected cotangents
+    c_A2d = c_A.view(-1, d)
+    if live:
+        c_y3 = mlp_first("mlp2", c_me, h_e, y3)
+        del c_me, h_e, y3
+        dz, dgam, dbet = K.add_ln_bwd(c_y3, z4a, z4b, p("ln4.weight"))
+        lnacc("ln4", dgam, dbet)
+        c_z4.add_(dz)
+        del dz, c_y3, z4a, z4b
+        c_A2d = K.rows_gemm(c_z4, p("attn.out_e.weight"), False, resid=c_A2d)       # y1 = A Woe^T + boe
+        wacc("attn.out_e", c_z4, a2d)
+    c_x3 = mlp_first("mlp", c_mn, h_n, x3)
+    dz, dgam, dbet = K.add_ln_bwd(c_x3, x1, on, p("ln3.weight"))
+    lnacc("ln3", dgam, dbet)
+    c_z3.add_(dz)
+    c_g = K.rows_gemm(c_z3, p("attn.out_n.weight"), False).view(b, n, d)              # on = g Won^T + bon
+    wacc("attn.out_n", c_z3, g2d)
+    c_A4 = c_A2d.view(b, n, n, d)
+    if fused_scores:
+        dE2, dq2, dk2, dv2 = K.attn_scores_bwd(c_g, c_A4, q, k, v, e4, c, stats)
+    else:
+        c_A4, dv2 = K.softmax_agg_bwd(c_g, a4, v, da_accum=c_A4)
+        dq2, dk2, dE2 = K.modulate_bwd(c_A4, q, k, e4, c)
+    del c_A4, c_A2d, c_A, a4, a2d
+    c_E.add_(dE2)
+    del dE2
+    c_q.add_(dq2), c_k.add_(dk2), c_v.add_(dv2)
+    c_E2d = c_E.view(-1, d)
+    c_y = K.rows_gemm(c_E2d, p("attn.e.weight"), False, resid=c_z4 if live else None)   # E = y We^T + be;  z4 = y + y1
+    wacc("attn.e", c_E2d, y2d)
+    c_x1 = c_z3
+    for nm, ct in zip(qkv, (c_q, c_k, c_v)):
+        ct2d = ct.view(-1, d)
+        wacc(nm, ct2d, x1)
+        c_x1 = K.rows_gemm(ct2d, p(nm + ".weight"), False, resid=c_x1)
+    dz, dgam, dbet = K.add_ln_bwd(c_x1, x2d, None, p("ln1.weight"))
+    lnacc("ln1", dgam, dbet)
+    c_x.add_(dz)
+    return (c_x.view(b, n, d), c_y.view(b, n, n, d), c_dxo.view(b, n, d),
+            c_dyo.view(b, n, n, d) if c_dyo is not None else None, cp)
+
+
 def _params_wanted(ctx_node, first_param_input: int) -> bool:
     """Inside a backward: will the engine consume any parameter gradient of this node?  During the
     gradient penalty's ``autograd.grad(inputs=[int_node, int_edge])`` (loss.py:32-39) it will not, and
@@ -319,6 +524,11 @@ class EncoderBlockBwdFn(Function):
     def backward(ctx, *u):
         x, y, dxo, dyo, *params = ctx.saved_tensors
         heads, edge_out = ctx.heads, ctx.edge_out
+        if all(ui is None for ui in u[2:]) and dxo is not None and _HAND_SECOND_ORDER:
+            # the gradient-penalty case (cotangents on dx / dy only): the hand-sequenced second-order pass
+            with torch.no_grad():
+                c_x, c_y, c_dxo, c_dyo, cp = block_backward_backward(x, y, dxo, dyo, u[0], u[1], params, heads, edge_out)
+            return (c_x, c_y, c_dxo, c_dyo if (dyo is not None and edge_out) else None, None, None, None) + tuple(cp)
         with torch.enable_grad():
             leaves, outs, gouts = _recompute(x, y, dxo, dyo, params, heads, edge_out, True)
             # only the first-order gradients that actually received a cotangent are rebuilt with a graph: in the

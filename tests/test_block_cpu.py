@@ -262,3 +262,44 @@ def test_io_wrappers_on_the_emulation():
         dg.label2onehot(labels.float(), 5)
     t = torch.randn(3, 7, 5)
     assert torch.equal(dg.argmax_last(t), torch.max(t, -1)[1])
+
+
+@pytest.mark.parametrize("mode,d,tol", [("fp32", 32, 1e-9), ("bf16", 128, 1e-6)])
+@pytest.mark.parametrize("edge_out", [True, False])
+def test_hand_sequenced_second_order_equals_autograd_path(monkeypatch, mode, d, tol, edge_out):
+    """block_backward_backward (the hand-sequenced second-order pass the gradient penalty takes) against reverse-over-reverse
+    on the differentiable primitives: same cotangents for x, y and every parameter.  The bf16 case runs the narrow code paths
+    (bf16-stored h / dh, the dgrad chain in both weight roles, the fused edge-attention recompute) on the emulation."""
+    from druggen_b200 import block as blk
+    n, b, heads = 4, 2, 8
+    p = _block_params(d=d)
+    g = torch.Generator().manual_seed(7)
+    x0 = torch.randn(b, n, d, generator=g, dtype=torch.float64)
+    y0 = torch.randn(b, n, n, d, generator=g, dtype=torch.float64)
+    wx = torch.randn(b, n, d, generator=g, dtype=torch.float64)
+    wy = torch.randn(b, n, n, d, generator=g, dtype=torch.float64)
+    calls = []
+    real = blk.block_backward_backward
+    monkeypatch.setattr(blk, "block_backward_backward", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+
+    def run(hand):
+        monkeypatch.setattr(blk, "_HAND_SECOND_ORDER", hand)
+        x, y = x0.clone().requires_grad_(True), y0.clone().requires_grad_(True)
+        pp = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
+        xo, yo = encoder_block(x, y, [pp[k] for k in BLOCK_PARAM_NAMES], heads, edge_out)
+        out = (xo * wx).sum() + ((yo * wy).sum() if edge_out else 0.0)
+        gx, gy = torch.autograd.grad(out, [x, y], create_graph=True)
+        pen = ((torch.cat([gx.reshape(b, -1), gy.reshape(b, -1)], 1).norm(2, dim=1) - 1) ** 2).mean()
+        pen.backward()                     # the second-order terms alone
+        return x.grad, y.grad, {k: v.grad for k, v in pp.items()}
+
+    with kernels.precision(mode):
+        ref = run(False)
+        assert not calls
+        got = run(True)
+        assert calls
+    assert rel_l2(got[0], ref[0]) < tol and rel_l2(got[1], ref[1]) < tol
+    for k in BLOCK_PARAM_NAMES:
+        assert (got[2][k] is None) == (ref[2][k] is None), k
+        if ref[2][k] is not None and float(ref[2][k].abs().max()) > 0:
+            assert rel_l2(got[2][k], ref[2][k]) < tol, k

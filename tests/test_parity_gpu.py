@@ -273,7 +273,10 @@ def test_bf16_mode_depth8_error_and_decode_flips_reported(cuda_dev, capsys):
 # measured on B200 (printed by the test below, profiles/r02_parity_depth8.json); the bounds are ~2x the measurement
 DEPTH8_BOUNDS = {
     # mode: (loss rel, D-grad rel-L2 over the whole parameter vector, G-grad rel-L2 over the whole parameter vector)
-    "fp32": (1e-3, 5e-3, 1e-3),           # measured 1e-7 / 1.1e-6 / 5.2e-7
+    # fp32: measured 1e-7 / 1.1e-6..3.1e-4 / 5.2e-7 on one box and 8e-8 / 3.1e-4 / 2.19e-3 on another: the second is the SAME single ReLU
+    # sign flip the multi-threaded fp32 CPU oracle makes against fp64 (2.192e-3, profiles/r02_oracle_noise.json) -- the atomic
+    # flush order of the weight-gradient kernels decides whether a 1e-7 forward perturbation crosses that pre-activation's zero
+    "fp32": (1e-3, 5e-3, 5e-3),
     "bf16x3": (1e-3, 5e-3, 5e-3),         # measured 7e-7 / 5.5e-4 / 2.4e-3  (ReLU-flip limited, see GRAD_TOL)
     "bf16": (1e-3, 6e-2, 8e-2),           # measured 2.7e-4 / 2.6e-2 / 3.6e-2
 }

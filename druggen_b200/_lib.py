@@ -23,7 +23,7 @@ SIGNATURES = {
     "dg_colsum": [_P, _P, _LL, _I, _P],
     "dg_gate_mul": [_P, _P, _P, _LL, _P],
     "dg_add_ln_fwd": [_P, _P, _P, _P, _P, _LL, _I, _F, _P],
-    "dg_add_ln_bwd": [_P, _P, _P, _P, _P, _P, _P, _LL, _I, _F, _P],
+    "dg_add_ln_bwd": [_P, _P, _P, _P, _P, _P, _P, _LL, _I, _F, _I, _P],
     "dg_add_ln_bwd_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _F, _P],
     "dg_modulate_fwd": [_P, _P, _P, _F, _P, _I, _I, _I, _P],
     "dg_modulate_bwd": [_P, _P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _P],
@@ -35,8 +35,8 @@ SIGNATURES = {
     "dg_attn_scores_bwd": [_P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "dg_softmax_agg16_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
     "dg_attn_edge_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _I, _I, _I, _F, _P, _LL, _P],
-    "dg_mlp_bwd_ln": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _F, _P, _LL, _P],
-    "dg_mlp_bwd_dgrad": [_P, _P, _P, _P, _P, _P, _LL, _I, _I, _P, _LL, _P],
+    "dg_mlp_bwd_ln": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _F, _P, _LL, _P],
+    "dg_mlp_bwd_dgrad": [_P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _P, _LL, _P],
     "dg_mlp_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _F, _P, _LL, _P],
     "dg_label2onehot": [_P, _I, _P, _LL, _I, _P],
     "dg_argmax_last": [_P, _P, _LL, _I, _P],
@@ -50,7 +50,7 @@ SIGNATURES = {
 }
 INFO_SYMBOLS = ("dg_abi_version", "dg_last_error", "dg_has_tcgen05", "dg_set_option", "dg_get_option", "dg_debug_chain_profile",
                 "dg_label_error")
-ABI_VERSION = 3
+ABI_VERSION = 4
 OPT_L2_PREFETCH = 0
 PF_ALL, PF_DEFAULT, PF_CHAIN_KEEP = 63, 12, 64        # DG_PF_* bit masks (include/druggen_b200.h)
 
@@ -182,10 +182,10 @@ class CudaBackend:
         self._call("dg_add_ln_fwd", ("add_ln_fwd", 0, _nbytes(a, b, out), "hbm"), _ptr(a), _ptr(b), _ptr(gamma), _ptr(beta),
                    _ptr(out), a.numel() // d, d, eps)
 
-    def add_ln_bwd(self, dy, a, b, gamma, dz, dgamma, dbeta, eps):
+    def add_ln_bwd(self, dy, a, b, gamma, dz, dgamma, dbeta, eps, accumulate=False):
         d = a.shape[-1]
-        self._call("dg_add_ln_bwd", ("add_ln_bwd", 0, _nbytes(dy, a, b, dz), "hbm"), _ptr(dy), _ptr(a), _ptr(b), _ptr(gamma),
-                   _ptr(dz), _ptr(dgamma), _ptr(dbeta), a.numel() // d, d, eps)
+        self._call("dg_add_ln_bwd", ("add_ln_bwd", 0, _nbytes(dy, a, b, dz) + (_nbytes(dz) if accumulate else 0), "hbm"), _ptr(dy), _ptr(a),
+                   _ptr(b), _ptr(gamma), _ptr(dz), _ptr(dgamma), _ptr(dbeta), a.numel() // d, d, eps, int(accumulate))
 
     def add_ln_bwd_bwd(self, u, vg, vb, dy, a, b, gamma, g_dy, g_z, g_gamma, eps):
         d = a.shape[-1]
@@ -237,13 +237,14 @@ def _attn_scores_fwd(self, q, k, v, e, c, a, g, stats=None):
                _ptr(a), _ptr(g), _ptr(sm), _ptr(si), b, n, d)
 
 
-def _attn_scores_bwd(self, dg, da_in, q, k, v, e, c, de, dq, dk, dv, stats=None, scores_bf16=False):
+def _attn_scores_bwd(self, dg, da_in, q, k, v, e, c, de, dq, dk, dv, stats=None, scores_bf16=False, accumulate_de=False):
     b, n, d = q.shape
     sm, si, g = stats if stats is not None else (None, None, None)
     de16 = de.dtype == torch.bfloat16
-    self._call("dg_attn_scores_bwd", ("attn_scores_bwd[fused%s]" % (",de16" if de16 else ""), 0, _nbytes(e, da_in, de), "hbm"), _ptr(dg),
+    da16 = da_in is not None and da_in.dtype == torch.bfloat16
+    self._call("dg_attn_scores_bwd", ("attn_scores_bwd[fused%s%s]" % (",de16" if de16 else "", ",da16" if da16 else ""), 0, _nbytes(e, da_in, de), "hbm"), _ptr(dg),
                _ptr(da_in), _ptr(q), _ptr(k), _ptr(v), _ptr(e), c, _ptr(sm), _ptr(si), _ptr(g), _ptr(de), _ptr(dq), _ptr(dk), _ptr(dv),
-               b, n, d, int(de16) | (2 if scores_bf16 else 0))
+               b, n, d, int(de16) | (2 if scores_bf16 else 0) | (4 if da16 else 0) | (8 if accumulate_de else 0))
 
 
 def _softmax_agg16_fwd(self, a16, v, g, stats=None):
@@ -262,20 +263,23 @@ def _attn_edge_fwd(self, y, q, k, we, be, woe, boe, gamma, beta, c, out, a16, e_
                c, _ptr(out), _ptr(a16), _ptr(e_out), _ptr(z_out), b, n, d, eps, _ptr(workspace), workspace.numel())
 
 
-def _mlp_bwd_ln(self, x, dout, w1, b1, w2, b2, gamma, dz, h16, dgamma, dbeta, eps, workspace):
+def _mlp_bwd_ln(self, x, dout, w1, b1, w2, b2, gamma, dz, h16, dgamma, dbeta, eps, workspace, mask=None):
     r, d = x.shape
     h = w1.shape[0]
-    meta = (f"mlp_bwd_ln[R={r},H={h},fused]", 4 * r * d * h, _nbytes(x, dout, dz, h16), "hbm", _nbytes(x, dout, dz))
+    tag = ("" if h16 is not None else ",no h") + (",mask" if mask is not None else "")
+    meta = (f"mlp_bwd_ln[R={r},H={h},fused{tag}]", 4 * r * d * h, _nbytes(x, dout, dz, h16, mask), "hbm", _nbytes(x, dout, dz))
     self._call("dg_mlp_bwd_ln", meta, _ptr(x), _ptr(dout), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(gamma), _ptr(dz),
-               _ptr(h16), _ptr(dgamma), _ptr(dbeta), r, d, h, eps, _ptr(workspace), workspace.numel())
+               _ptr(h16), _ptr(mask), _ptr(dgamma), _ptr(dbeta), r, d, h, eps, _ptr(workspace), workspace.numel())
 
 
-def _mlp_bwd_dgrad(self, dz, h16, w1, w2, dx, dh16, workspace):
+def _mlp_bwd_dgrad(self, dz, h16, w1, w2, dx, dh16, workspace, mask=None):
     r, d = dz.shape
     h = w1.shape[0]
-    meta = (f"mlp_bwd_dgrad[R={r},H={h},fused]", 4 * r * d * h, _nbytes(dz, h16, dx, dh16), "hbm", _nbytes(dz, dx))
-    self._call("dg_mlp_bwd_dgrad", meta, _ptr(dz), _ptr(h16), _ptr(w1), _ptr(w2), _ptr(dx), _ptr(dh16), r, d, h,
-               _ptr(workspace), workspace.numel())
+    tag = (",mask" if mask is not None else "") + ("" if dh16 is not None else ",no dh")
+    gate = mask if mask is not None else h16
+    meta = (f"mlp_bwd_dgrad[R={r},H={h},fused{tag}]", 4 * r * d * h, _nbytes(dz, gate, dx, dh16), "hbm", _nbytes(dz, dx))
+    self._call("dg_mlp_bwd_dgrad", meta, _ptr(dz), _ptr(None if mask is not None else h16), _ptr(mask), _ptr(w1), _ptr(w2), _ptr(dx),
+               _ptr(dh16), r, d, h, _ptr(workspace), workspace.numel())
 
 
 def _label2onehot(self, labels, out, classes):

@@ -166,14 +166,16 @@ def block_backward(x, y, dxo, dyo, params: Sequence[torch.Tensor], heads: int, e
     def mlp_bwd(mlp, ln, xin, dout2d):
         """Backward of  LN(xin + fc2(relu(fc1(xin))))  given d(out): returns d(xin); fills the six parameter grads."""
         w1, b1, w2, b2 = p(mlp + ".fc1.weight"), p(mlp + ".fc1.bias"), p(mlp + ".fc2.weight"), p(mlp + ".fc2.bias")
-        if h16:      # two fused tcgen05 chains; h and dh cross HBM once each, as bf16, for the weight gradients
-            dz, hh, dgam, dbet = K.mlp_bwd_ln(xin, dout2d, w1, b1, w2, b2, p(ln + ".weight"))
+        if h16:      # two fused tcgen05 chains; h and dh cross HBM once each, as bf16, ONLY for the weight gradients: the
+            # dgrad chain takes the ReLU sign from a bit mask (H/8 bytes per row instead of the 2H-byte bf16 h)
+            dz, hh, dgam, dbet, mask = K.mlp_bwd_ln(xin, dout2d, w1, b1, w2, b2, p(ln + ".weight"), want_h=want_params,
+                                                    want_mask=True)
             if want_params:
                 put(ln + ".weight", dgam)
                 put(ln + ".bias", dbet)
             wgrad(mlp + ".fc2", dz, hh)
-            dxin, dh = K.mlp_bwd_dgrad(dz, hh, w1, w2)
             del hh
+            dxin, dh = K.mlp_bwd_dgrad(dz, None, w1, w2, mask=mask, want_dh=want_params)
             wgrad(mlp + ".fc1", dh, xin)
             return dxin
         hh = K.rows_gemm(xin, w1, True, b1, relu=True)
@@ -230,7 +232,8 @@ def block_backward(x, y, dxo, dyo, params: Sequence[torch.Tensor], heads: int, e
             dz4 = ln_bwd("ln4", dy3, y2d, y1)              # gradient of both y (residual) and out_e(a)
             del dy3, y1, y3
         wgrad("attn.out_e", dz4, a2d)
-        da = K.rows_gemm(dz4, p("attn.out_e.weight"), False).view(b, n, n, d)
+        # (tensor-core mode: this gradient is added to the softmax term and leaves as the bf16 dE -- bf16 storage halves its trip)
+        da = K.rows_gemm(dz4, p("attn.out_e.weight"), False, out_bf16=h16 and K.attn_fused_available(n, d)).view(b, n, n, d)
     # ---- attention: softmax-aggregate, modulation, q/k/v/e projections
     if h16 and K.attn_fused_available(n, d):
         # de is only ever a contraction operand (dWe, dy): bf16 storage in the tensor-core mode
@@ -265,8 +268,8 @@ def block_backward_backward(x, y, dxo, dyo, ux, uy, params: Sequence[torch.Tenso
          forward intermediates E, A, q, k, v, z3, z4, m, m' (the mask of the ReLU is piecewise constant);
       3. an ordinary first-order backward of the forward program from those injected cotangents.
 
-    Accumulation rides in GEMM stores (``resid``) and in ``gemm_tn(out=...)``; the only edge-sized elementwise adds left are
-    two in-place ``add_``.  Returns (c_x, c_y, c_dxo, c_dyo | None, [param cotangents aligned with BLOCK_PARAM_NAMES]);
+    Accumulation rides in GEMM stores (``resid``), in ``gemm_tn(out=...)`` and in the stores of the LayerNorm / attention
+    backward kernels (``dz_accum``, ``de_accum``): no edge-sized elementwise add is launched.  Returns (c_x, c_y, c_dxo, c_dyo | None, [param cotangents aligned with BLOCK_PARAM_NAMES]);
     parameters without a consumer keep None."""
     p = lambda n: params[_IDX[n]]  # noqa: E731
     b, n, d = x.shape
@@ -416,27 +419,25 @@ def block_backward_backward(x, y, dxo, dyo, ux, uy, params: Sequence[torch.Tenso
     if live:
         c_y3 = mlp_first("mlp2", c_me, h_e, y3)
         del c_me, h_e, y3
-        dz, dgam, dbet = K.add_ln_bwd(c_y3, z4a, z4b, p("ln4.weight"))
+        _, dgam, dbet = K.add_ln_bwd(c_y3, z4a, z4b, p("ln4.weight"), dz_accum=c_z4)     # c[z4] += LN4^T c[y3]
         lnacc("ln4", dgam, dbet)
-        c_z4.add_(dz)
-        del dz, c_y3, z4a, z4b
+        del c_y3, z4a, z4b
         c_A2d = K.rows_gemm(c_z4, p("attn.out_e.weight"), False, resid=c_A2d)       # y1 = A Woe^T + boe
         wacc("attn.out_e", c_z4, a2d)
     c_x3 = mlp_first("mlp", c_mn, h_n, x3)
-    dz, dgam, dbet = K.add_ln_bwd(c_x3, x1, on, p("ln3.weight"))
+    _, dgam, dbet = K.add_ln_bwd(c_x3, x1, on, p("ln3.weight"), dz_accum=c_z3)
     lnacc("ln3", dgam, dbet)
-    c_z3.add_(dz)
     c_g = K.rows_gemm(c_z3, p("attn.out_n.weight"), False).view(b, n, d)              # on = g Won^T + bon
     wacc("attn.out_n", c_z3, g2d)
     c_A4 = c_A2d.view(b, n, n, d)
     if fused_scores:
-        dE2, dq2, dk2, dv2 = K.attn_scores_bwd(c_g, c_A4, q, k, v, e4, c, stats)
+        _, dq2, dk2, dv2 = K.attn_scores_bwd(c_g, c_A4, q, k, v, e4, c, stats, de_accum=c_E)        # c[E] += in the store
     else:
         c_A4, dv2 = K.softmax_agg_bwd(c_g, a4, v, da_accum=c_A4)
         dq2, dk2, dE2 = K.modulate_bwd(c_A4, q, k, e4, c)
+        c_E.add_(dE2)
+        del dE2
     del c_A4, c_A2d, c_A, a4, a2d
-    c_E.add_(dE2)
-    del dE2
     c_q.add_(dq2), c_k.add_(dk2), c_v.add_(dv2)
     c_E2d = c_E.view(-1, d)
     c_y = K.rows_gemm(c_E2d, p("attn.e.weight"), False, resid=c_z4 if live else None)   # E = y We^T + be;  z4 = y + y1
@@ -446,9 +447,8 @@ def block_backward_backward(x, y, dxo, dyo, ux, uy, params: Sequence[torch.Tenso
         ct2d = ct.view(-1, d)
         wacc(nm, ct2d, x1)
         c_x1 = K.rows_gemm(ct2d, p(nm + ".weight"), False, resid=c_x1)
-    dz, dgam, dbet = K.add_ln_bwd(c_x1, x2d, None, p("ln1.weight"))
+    _, dgam, dbet = K.add_ln_bwd(c_x1, x2d, None, p("ln1.weight"), dz_accum=c_x)
     lnacc("ln1", dgam, dbet)
-    c_x.add_(dz)
     return (c_x.view(b, n, d), c_y.view(b, n, n, d), c_dxo.view(b, n, d),
             c_dyo.view(b, n, n, d) if c_dyo is not None else None, cp)
 

@@ -59,6 +59,8 @@ __device__ __forceinline__ void combine4(const float* pm, const float* ps, const
 
 // kMode 0: forward from e, scores written (a_out);  1: backward.  (The forward variants that do not write the scores --
 // from e, or from the bf16 scores of dg_attn_edge_fwd -- are attn_fwd_warp_kernel below.)
+// (Backward, measured on B200 and not kept: requesting the next batch of (e, da) rows before the current one is reduced costs
+// 168 registers / three CTAs per SM and ran 20 % slower; bf16 da_in halves its bytes but the sweep is latency-bound -- 1.5 %.)
 template <int kMode>
 __global__ void __launch_bounds__(128, 4)
 attn_scores_kernel(const float* __restrict__ dg, const float* __restrict__ da_in, const float* __restrict__ q,
@@ -142,15 +144,28 @@ attn_scores_kernel(const float* __restrict__ dg, const float* __restrict__ da_in
     // ---- sweep 2 (backward): gradients for my key atoms
     const float4 dgi = ld4(dg + bi);
     float4 sq = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int j = jlo; j < jhi; j += kJU) {
-      const int n = min(kJU, jhi - j);
-      float4 ev[kJU], din[kJU];
+    const uint16_t* da16 = reinterpret_cast<const uint16_t*>(da_in);
+    const bool da_is_bf16 = (de_bf16 & 4) != 0;
+    float4 ev[kJU], din[kJU];
+    auto fetch = [&](int j, float4* pe, float4* pd) {
 #pragma unroll
       for (int u = 0; u < kJU; ++u)
-        if (u < n) {
-          ev[u] = ld4(e + base + (long long)(j + u) * D);
-          din[u] = da_in ? ld4(da_in + base + (long long)(j + u) * D) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j + u < jhi) {
+          pe[u] = ld4(e + base + (long long)(j + u) * D);
+          if (da_in == nullptr) {
+            pd[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          } else if (da_is_bf16) {       // the out_e path's gradient stored as bf16 (tensor-core mode): 8 bytes per lane
+            const uint2 r = *reinterpret_cast<const uint2*>(da16 + base + (long long)(j + u) * D);
+            pd[u] = make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xFFFF0000u), __uint_as_float(r.y << 16),
+                                __uint_as_float(r.y & 0xFFFF0000u));
+          } else {
+            pd[u] = ld4(da_in + base + (long long)(j + u) * D);
+          }
         }
+    };
+    for (int j = jlo; j < jhi; j += kJU) {
+      const int n = min(kJU, jhi - j);
+      fetch(j, ev, din);
 #pragma unroll
       for (int u = 0; u < kJU; ++u)
         if (u < n) {
@@ -173,12 +188,24 @@ attn_scores_kernel(const float* __restrict__ dg, const float* __restrict__ da_in
           if (de_bf16 & 1)  // de is only ever a contraction operand (dWe, dy): bf16 storage loses nothing in the tensor-core mode
             *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(de) + base + (long long)(j + u) * D) =
                 make_uint2(pack2_bf16(o.x, o.y), pack2_bf16(o.z, o.w));
-          else
+          else {
+            if (de_bf16 & 8) {           // de += : the cotangent of E already holds the second-order terms (block_backward_backward)
+              const float4 pr = ld4(de + base + (long long)(j + u) * D);
+              o.x += pr.x; o.y += pr.y; o.z += pr.z; o.w += pr.w;
+            }
             st4(de + base + (long long)(j + u) * D, o);
+          }
           float4 ak = ld4(sdk + (j + u) * D + ch), avv = ld4(sdv + (j + u) * D + ch);
           st4(sdk + (j + u) * D + ch, make_float4(ak.x + gk.x, ak.y + gk.y, ak.z + gk.z, ak.w + gk.w));
           st4(sdv + (j + u) * D + ch, make_float4(avv.x + gv.x, avv.y + gv.y, avv.z + gv.z, avv.w + gv.w));
         }
+    }
+    if (have_stats) {
+      // statistics came from the forward: nothing in this query atom needs the other warps -- the four partial sums of
+      // dq_i go out as one reduction each (dq zero-filled by the caller) and the warps never meet until the flush (-6 %)
+      float* pq = dq + bi;
+      atomicAdd(pq, c * sq.x); atomicAdd(pq + 1, c * sq.y); atomicAdd(pq + 2, c * sq.z); atomicAdd(pq + 3, c * sq.w);
+      continue;
     }
     // dq_i = c * sum over all key atoms: combine the 4 warps (reuse the m-slot of the other parity)
     float* rq = red + 12 * D;
@@ -329,13 +356,13 @@ extern "C" int dg_attn_scores_bwd(const float* dg_, const float* da_in, const fl
                                   void* de, float* dq, float* dk, float* dv, int B, int N, int D, int de_bf16, void* stream) {
   if (attn_ok(B, N, D)) return 1;
   const size_t smem = (size_t)(16 + 2 * N) * D * 4;
+  const int irows = attn_irows(B, N, 4);
+  dim3 grid((N + irows - 1) / irows, B);
+  if (stat_m != nullptr && (stat_inv == nullptr || g == nullptr)) return fail("dg_attn_scores_bwd: statistics need stat_inv and g too");
   if (smem > 48 * 1024) {
     cudaError_t er = cudaFuncSetAttribute(attn_scores_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (er != cudaSuccess) return fail("cudaFuncSetAttribute: %s", cudaGetErrorString(er));
   }
-  const int irows = attn_irows(B, N, 4);
-  dim3 grid((N + irows - 1) / irows, B);
-  if (stat_m != nullptr && (stat_inv == nullptr || g == nullptr)) return fail("dg_attn_scores_bwd: statistics need stat_inv and g too");
   attn_scores_kernel<1><<<grid, 128, smem, (cudaStream_t)stream>>>(dg_, da_in, q, k, v, e, c, nullptr, nullptr, (float*)de, dq, dk, dv,
                                                                     const_cast<float*>(stat_m), const_cast<float*>(stat_inv), g, N, irows,
                                                                     opt_get(DG_OPT_L2_PREFETCH) & DG_PF_ATTN_BWD, de_bf16);

@@ -50,7 +50,9 @@ struct MlpArgs {
   const float* dout;       // BWD_A: upstream gradient [R,128]
   float* out;              // FWD: y;  BWD_A: dz;  BWD_B: dx     [R,128]
   uint16_t* spill;         // BWD_A: h out [R,H] bf16;  BWD_B: dh out [R,H] bf16
-  const uint16_t* gate;    // BWD_B: h in [R,H] bf16
+  const uint16_t* gate;    // BWD_B: h in [R,H] bf16 (sign mask source when mask_in is NULL)
+  unsigned long long* mask_out;       // BWD_A: optional ReLU sign mask [R][H/64] (bit i of word (c*2+hf): h[c*128+hf*64+i] > 0)
+  const unsigned long long* mask_in;  // BWD_B: optional, replaces the 2 H bytes per row of `gate` by H/8
   float* dgamma;           // BWD_A: += [128]
   float* dbeta;            // BWD_A: += [128]
   long long R;
@@ -208,7 +210,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long num_tiles = (R + 127) / 128;
   const long long my_tiles = blockIdx.x < num_tiles ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const bool spill = kMode == kBwdA || kMode == kBwdB || (kMode == kAttn && A.spill != nullptr);
+  const bool spill = (kMode == kBwdA || kMode == kBwdB || kMode == kAttn) && A.spill != nullptr;
+  const bool use_mask = kMode == kBwdB && A.mask_in != nullptr;
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -390,7 +393,11 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
         // bf16 [R,H] side tensors viewed as 32-bit words: pitch H/2, this warp-half's 64 columns = 32 words
         const int wcol = (c * 128 + hf * 64) >> 1;
         float4 gq[8];
-        if (kMode == kBwdB) gather_issue(reinterpret_cast<const float*>(A.gate), wrow0, R, H >> 1, wcol, 2, lane, gq);
+        unsigned long long mk = 0ull;                 // BWD_B: this row-half's 64 ReLU sign bits of chunk c (one 8-byte load)
+        if (kMode == kBwdB) {
+          if (use_mask) { if (wrow0 + lane < R) mk = __ldg(A.mask_in + (wrow0 + lane) * (2 * HC) + c * 2 + hf); }
+          else gather_issue(reinterpret_cast<const float*>(A.gate), wrow0, R, H >> 1, wcol, 2, lane, gq);
+        }
         // ATTN: q / k rows of the 4 staged rows this lane serves (row r = ((b N + i) N + j) -> q row b N + i, k row b N + j),
         // and the first 16-channel group of both, requested before the accumulator is waited for
         unsigned qoff[4], koff[4];                     // element offsets (B N 128 < 2^31)
@@ -423,7 +430,14 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
         __syncwarp();
         if (lane == 0) mbar_arrive(&hacc_empty[c]);
         DG_PROF(3)
-        if (kMode == kBwdB) {
+        if (kMode == kBwdB && use_mask) {
+          const uint32_t mlo = (uint32_t)mk, mhi = (uint32_t)(mk >> 32);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            v[i] = (mlo >> i) & 1u ? v[i] : 0.f;
+            v[32 + i] = (mhi >> i) & 1u ? v[32 + i] : 0.f;
+          }
+        } else if (kMode == kBwdB) {
           float gw[32];                                              // 64 bf16 sign masks of this row
           gather_finish(gq, 2, stg, lane, gw);
 #pragma unroll
@@ -493,6 +507,16 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
             const float4 b4 = ld4(bb + i);
             v[i] = fmaxf(v[i] + b4.x, 0.f); v[i + 1] = fmaxf(v[i + 1] + b4.y, 0.f);
             v[i + 2] = fmaxf(v[i + 2] + b4.z, 0.f); v[i + 3] = fmaxf(v[i + 3] + b4.w, 0.f);
+          }
+          if (kMode == kBwdA && A.mask_out != nullptr && wrow0 + lane < R) {
+            // the sign of h is all the dgrad chain needs of it: 8 bytes per row-half instead of 128
+            uint32_t mlo = 0u, mhi = 0u;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              mlo |= (v[i] > 0.f ? 1u : 0u) << i;
+              mhi |= (v[32 + i] > 0.f ? 1u : 0u) << i;
+            }
+            A.mask_out[(wrow0 + lane) * (2 * HC) + c * 2 + hf] = ((unsigned long long)mhi << 32) | mlo;
           }
         }
         if (kDedIO) {
@@ -802,28 +826,33 @@ extern "C" int dg_mlp_fwd(const float* x, const float* w1, const float* b1, cons
   if (mlp_check("dg_mlp_fwd", x, R, D, H, workspace, workspace_bytes)) return 1;
   cudaStream_t s = (cudaStream_t)stream;
   tc::mlp_pack_weights_kernel<<<48, 256, 0, s>>>(w1, w2, (uint8_t*)workspace, H, 0);
-  tc::MlpArgs a{x, (const uint8_t*)workspace, b1, b2, gamma, beta, nullptr, out, nullptr, nullptr, nullptr, nullptr, R, H / 128, eps};
+  tc::MlpArgs a{x, (const uint8_t*)workspace, b1, b2, gamma, beta, nullptr, out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, R, H / 128, eps};
   return tc::launch_chain<tc::kFwd>(a, s);
 }
 
 extern "C" int dg_mlp_bwd_ln(const float* x, const float* dout, const float* w1, const float* b1, const float* w2,
-                             const float* b2, const float* gamma, float* dz, void* h_bf16, float* dgamma, float* dbeta,
-                             long long R, int D, int H, float eps, void* workspace, long long workspace_bytes, void* stream) {
+                             const float* b2, const float* gamma, float* dz, void* h_bf16, void* relu_mask, float* dgamma,
+                             float* dbeta, long long R, int D, int H, float eps, void* workspace, long long workspace_bytes,
+                             void* stream) {
   if (mlp_check("dg_mlp_bwd_ln", x, R, D, H, workspace, workspace_bytes)) return 1;
+  if (reinterpret_cast<uintptr_t>(relu_mask) & 7) return fail("dg_mlp_bwd_ln: the sign mask must be 8-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
   tc::mlp_pack_weights_kernel<<<48, 256, 0, s>>>(w1, w2, (uint8_t*)workspace, H, 0);
-  tc::MlpArgs a{x, (const uint8_t*)workspace, b1, b2, gamma, nullptr, dout, dz, (uint16_t*)h_bf16, nullptr, dgamma, dbeta, R, H / 128, eps};
+  tc::MlpArgs a{x, (const uint8_t*)workspace, b1, b2, gamma, nullptr, dout, dz, (uint16_t*)h_bf16, nullptr,
+                (unsigned long long*)relu_mask, nullptr, dgamma, dbeta, R, H / 128, eps};
   return tc::launch_chain<tc::kBwdA>(a, s);
 }
 
-extern "C" int dg_mlp_bwd_dgrad(const float* dz, const void* h_bf16, const float* w1, const float* w2, float* dx,
-                                void* dh_bf16, long long R, int D, int H, void* workspace, long long workspace_bytes,
+extern "C" int dg_mlp_bwd_dgrad(const float* dz, const void* h_bf16, const void* relu_mask, const float* w1, const float* w2,
+                                float* dx, void* dh_bf16, long long R, int D, int H, void* workspace, long long workspace_bytes,
                                 void* stream) {
   if (mlp_check("dg_mlp_bwd_dgrad", dz, R, D, H, workspace, workspace_bytes)) return 1;
+  if (h_bf16 == nullptr && relu_mask == nullptr) return fail("dg_mlp_bwd_dgrad: needs h (bf16) or its sign mask");
+  if (reinterpret_cast<uintptr_t>(relu_mask) & 7) return fail("dg_mlp_bwd_dgrad: the sign mask must be 8-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
   tc::mlp_pack_weights_kernel<<<48, 256, 0, s>>>(w1, w2, (uint8_t*)workspace, H, 1);
   tc::MlpArgs a{dz, (const uint8_t*)workspace, nullptr, nullptr, nullptr, nullptr, nullptr, dx, (uint16_t*)dh_bf16,
-                (const uint16_t*)h_bf16, nullptr, nullptr, R, H / 128, 0.f};
+                (const uint16_t*)h_bf16, nullptr, (const unsigned long long*)relu_mask, nullptr, nullptr, R, H / 128, 0.f};
   return tc::launch_chain<tc::kBwdB>(a, s);
 }
 
@@ -837,8 +866,8 @@ extern "C" int dg_attn_edge_fwd(const float* y, const float* q, const float* k, 
   if (mlp_check("dg_attn_edge_fwd", y, R, D, 128, workspace, workspace_bytes)) return 1;
   cudaStream_t s = (cudaStream_t)stream;
   tc::mlp_pack_weights_kernel<<<48, 256, 0, s>>>(we, woe, (uint8_t*)workspace, 128, 0);
-  tc::MlpArgs a{y, (const uint8_t*)workspace, be, boe, gamma, beta, nullptr, out, (uint16_t*)a_bf16, nullptr, nullptr, nullptr, R, 1, eps,
-                q, k, e_out, z_out, N, c, 0};
+  tc::MlpArgs a{y, (const uint8_t*)workspace, be, boe, gamma, beta, nullptr, out, (uint16_t*)a_bf16, nullptr, nullptr, nullptr, nullptr, nullptr,
+                R, 1, eps, q, k, e_out, z_out, N, c, 0};
   return tc::launch_chain<tc::kAttn>(a, s);
 }
 

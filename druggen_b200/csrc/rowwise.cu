@@ -104,7 +104,7 @@ template <int V>
 __global__ void __launch_bounds__(kRowWarps * 32)
 add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ a, const float* __restrict__ b,
                   const float* __restrict__ gamma, float* __restrict__ dz, float* __restrict__ dgamma,
-                  float* __restrict__ dbeta, long long R, int D, float eps) {
+                  float* __restrict__ dbeta, long long R, int D, float eps, int accumulate) {
   extern __shared__ float sm[];
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   RowVecT<V> accg, accb;
@@ -129,8 +129,12 @@ add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ a, con
     float c1 = warp_sum(s1) / D, c2 = warp_sum(s2) / D;
     for_each_chunk_t<V>(D, lane, [&](int t, int c) {
       float4 h = gh.v[t], x = xh.v[t];
-      st4(dz + row * D + c, make_float4(r * (h.x - c1 - x.x * c2), r * (h.y - c1 - x.y * c2),
-                                        r * (h.z - c1 - x.z * c2), r * (h.w - c1 - x.w * c2)));
+      float4 o = make_float4(r * (h.x - c1 - x.x * c2), r * (h.y - c1 - x.y * c2), r * (h.z - c1 - x.z * c2), r * (h.w - c1 - x.w * c2));
+      if (accumulate) {                  // dz += : a cotangent that already holds another path's contribution
+        const float4 p = ld4(dz + row * D + c);
+        o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+      }
+      st4(dz + row * D + c, o);
     });
   }
   flush_columns(accg, dgamma, D, lane, warp, sm);
@@ -256,10 +260,10 @@ extern "C" int dg_add_ln_fwd(const float* a, const float* b, const float* gamma,
 }
 
 extern "C" int dg_add_ln_bwd(const float* dy, const float* a, const float* b, const float* gamma, float* dz,
-                             float* dgamma, float* dbeta, long long R, int D, float eps, void* stream) {
+                             float* dgamma, float* dbeta, long long R, int D, float eps, int accumulate, void* stream) {
   if (ln_ok(R, D)) return 1;
   DG_DISPATCH_V(D, (add_ln_bwd_kernel<V><<<row_grid(R), kRowWarps * 32, kRowWarps * D * sizeof(float), (cudaStream_t)stream>>>(
-      dy, a, b, gamma, dz, dgamma, dbeta, R, D, eps)));
+      dy, a, b, gamma, dz, dgamma, dbeta, R, D, eps, accumulate)));
   return check_launch("dg_add_ln_bwd");
 }
 

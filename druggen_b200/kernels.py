@@ -156,14 +156,14 @@ def add_ln_fwd(a, b, gamma, beta, eps: float = 1e-5):
     return out
 
 
-def add_ln_bwd(dy, a, b, gamma, eps: float = 1e-5):
-    """-> (dz, dgamma, dbeta) with z = a + b recomputed."""
-    _chk(dy, a, b, gamma)
-    dz = torch.empty_like(a)
+def add_ln_bwd(dy, a, b, gamma, eps: float = 1e-5, dz_accum=None):
+    """-> (dz, dgamma, dbeta) with z = a + b recomputed.  ``dz_accum`` given => dz is added into it in place (and returned)."""
+    _chk(dy, a, b, gamma, dz_accum)
+    dz = torch.empty_like(a) if dz_accum is None else dz_accum
     dgamma = torch.zeros_like(gamma)
     dbeta = torch.zeros_like(gamma)
     if a.numel():
-        _be().add_ln_bwd(dy, a, b, gamma, dz, dgamma, dbeta, eps)
+        _be().add_ln_bwd(dy, a, b, gamma, dz, dgamma, dbeta, eps, accumulate=dz_accum is not None)
     return dz, dgamma, dbeta
 
 
@@ -256,26 +256,31 @@ def _mlp_ws(w1):
     return torch.empty(2 * (w1.shape[0] // 128) * 32768, dtype=torch.uint8, device=w1.device)
 
 
-def mlp_bwd_ln(x, dout, w1, b1, w2, b2, gamma, eps: float = 1e-5):
+def mlp_bwd_ln(x, dout, w1, b1, w2, b2, gamma, eps: float = 1e-5, want_h: bool = True, want_mask: bool = False):
     """Recompute the residual MLP from x and take the LayerNorm backward of ``dout``.
-    -> (dz [R,128] fp32, h [R,H] bf16, dgamma, dbeta)."""
+    -> (dz [R,128] fp32, h [R,H] bf16 | None, dgamma, dbeta[, mask]).  ``want_mask``: also the ReLU sign mask [R, H/64] int64
+    (H/8 bytes per row) -- all ``mlp_bwd_dgrad`` needs of h; ``want_h=False`` skips the bf16 h (only the fc2 weight gradient
+    reads it)."""
     _chk(x, dout, w1, b1, w2, b2, gamma)
     dz = torch.empty_like(x)
-    h16 = torch.empty((x.shape[0], w1.shape[0]), dtype=torch.bfloat16, device=x.device)
+    h16 = torch.empty((x.shape[0], w1.shape[0]), dtype=torch.bfloat16, device=x.device) if want_h else None
+    mask = torch.empty((x.shape[0], w1.shape[0] // 64), dtype=torch.int64, device=x.device) if want_mask else None
     dgamma, dbeta = torch.zeros_like(gamma), torch.zeros_like(gamma)
     if x.numel():
-        _be().mlp_bwd_ln(x, dout, w1, b1, w2, b2, gamma, dz, h16, dgamma, dbeta, eps, _mlp_ws(w1))
-    return dz, h16, dgamma, dbeta
+        _be().mlp_bwd_ln(x, dout, w1, b1, w2, b2, gamma, dz, h16, dgamma, dbeta, eps, _mlp_ws(w1), mask=mask)
+    return (dz, h16, dgamma, dbeta, mask) if want_mask else (dz, h16, dgamma, dbeta)
 
 
-def mlp_bwd_dgrad(dz, h16, w1, w2):
-    """-> (dx = dz + dh.W1 [R,128] fp32, dh = (dz.W2)*(h>0) [R,H] bf16)."""
+def mlp_bwd_dgrad(dz, h16, w1, w2, mask=None, want_dh: bool = True):
+    """-> (dx = dz + dh.W1 [R,128] fp32, dh = (dz.W2)*(h>0) [R,H] bf16 | None).  The sign of h comes from ``mask``
+    (``mlp_bwd_ln(want_mask=True)``) when given, else from ``h16``; ``want_dh=False`` skips the bf16 dh (only the fc1
+    weight gradient reads it)."""
     _chk(dz, w1, w2)
     _chk(h16, bf16_ok=True)
     dx = torch.empty_like(dz)
-    dh16 = torch.empty_like(h16)
+    dh16 = torch.empty((dz.shape[0], w1.shape[0]), dtype=torch.bfloat16, device=dz.device) if want_dh else None
     if dz.numel():
-        _be().mlp_bwd_dgrad(dz, h16, w1, w2, dx, dh16, _mlp_ws(w1))
+        _be().mlp_bwd_dgrad(dz, h16, w1, w2, dx, dh16, _mlp_ws(w1), mask=mask)
     return dx, dh16
 
 
@@ -296,15 +301,17 @@ def attn_scores_fwd(q, k, v, e, c: float, want_stats: bool = False, store_a: boo
     return (a, g, stats + (g,)) if want_stats else (a, g)
 
 
-def attn_scores_bwd(dg, da_in, q, k, v, e, c: float, stats=None, de_bf16: bool = False, scores_bf16: bool = False):
+def attn_scores_bwd(dg, da_in, q, k, v, e, c: float, stats=None, de_bf16: bool = False, scores_bf16: bool = False, de_accum=None):
     """-> (de, dq, dk, dv) from dg (softmax path) and da_in (out_e path; may be None).  ``stats`` from the forward
     skips the statistics sweep.  ``de_bf16``: de is stored as bf16 (it is only ever a contraction operand).
     ``scores_bf16``: the statistics were taken from bf16-stored scores (softmax_agg16_fwd); the recomputed scores are rounded alike."""
-    _chk(dg, da_in, q, k, v, e)
-    de, dq = torch.empty_like(e, dtype=torch.bfloat16 if de_bf16 else e.dtype), torch.empty_like(q)
-    dk, dv = torch.zeros_like(k), torch.zeros_like(v)
+    _chk(dg, q, k, v, e)
+    _chk(da_in, bf16_ok=True)          # (bf16 da: the out_e dgrad GEMM stored it with out_bf16 -- tensor-core mode)
+    _chk(de_accum)                     # (fp32, same shape as e: de is added into it in place and returned)
+    de = de_accum if de_accum is not None else torch.empty_like(e, dtype=torch.bfloat16 if de_bf16 else e.dtype)
+    dq, dk, dv = torch.zeros_like(q), torch.zeros_like(k), torch.zeros_like(v)
     if e.numel():
-        _be().attn_scores_bwd(dg, da_in, q, k, v, e, c, de, dq, dk, dv, stats, scores_bf16)
+        _be().attn_scores_bwd(dg, da_in, q, k, v, e, c, de, dq, dk, dv, stats, scores_bf16, accumulate_de=de_accum is not None)
     return de, dq, dk, dv
 
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DG_ABI_VERSION 3
+#define DG_ABI_VERSION 4
 #define DG_PREC_FP32 0
 #define DG_PREC_BF16 1
 #define DG_PREC_BF16X3 2
@@ -79,9 +79,10 @@ int dg_gate_mul(const float* x, const float* ref, float* out, long long n, void*
 /* out = LN(a + b) * gamma + beta over D; b may be NULL. */
 int dg_add_ln_fwd(const float* a, const float* b, const float* gamma, const float* beta, float* out,
                   long long R, int D, float eps, void* stream);
-/* dz[R,D]; dgamma[D] += , dbeta[D] +=   (z = a + b recomputed). */
+/* dz[R,D] written (accumulate != 0: dz += , the add of another path's cotangent rides in the store);
+ * dgamma[D] += , dbeta[D] +=   (z = a + b recomputed). */
 int dg_add_ln_bwd(const float* dy, const float* a, const float* b, const float* gamma, float* dz,
-                  float* dgamma, float* dbeta, long long R, int D, float eps, void* stream);
+                  float* dgamma, float* dbeta, long long R, int D, float eps, int accumulate, void* stream);
 /* Second order: gradient of <u,dz> + <vg,dgamma> + <vb,dbeta> w.r.t. dy, z, gamma.
  * vg, vb may be NULL.  g_gamma[D] += . */
 int dg_add_ln_bwd_bwd(const float* u, const float* vg, const float* vb, const float* dy, const float* a,
@@ -116,14 +117,16 @@ int dg_attn_scores_fwd(const float* q, const float* k, const float* v, const flo
                        float* g, float* stat_m, float* stat_inv, int B, int N, int D, void* stream);
 /* (stat_m, stat_inv: optional [B,N,D] outputs = per-channel softmax max and 1/sum, for the backward.)
  * First-order backward of the pair: de written from dg (softmax path) + da_in (out_e path, may be NULL);
- * dq written; dk, dv += (zero first).  Scores are recomputed from e, q, k; with (stat_m, stat_inv, g) from the
- * forward the statistics sweep is skipped, with NULLs it is redone. */
+ * dq, dk, dv += (zero all three first).  Scores are recomputed from e, q, k; with (stat_m, stat_inv, g) from the
+ * forward the statistics sweep is skipped (and the warps of a molecule never synchronise), with NULLs it is redone. */
 int dg_attn_scores_bwd(const float* dg, const float* da_in, const float* q, const float* k, const float* v,
                        const float* e, float c, const float* stat_m, const float* stat_inv, const float* g,
                        void* de, float* dq, float* dk, float* dv, int B, int N, int D, int de_bf16, void* stream);
 /* (de_bf16 bit 0: de is written as bf16 [B,N,N,D] -- it is only ever a contraction operand (dWe, dy), so in the
  * tensor-core mode nothing is lost.  bit 1: the recomputed scores are rounded to bf16 before the softmax term, matching
- * statistics that were taken from the bf16 scores of dg_attn_edge_fwd / dg_softmax_agg16_fwd.)
+ * statistics that were taken from the bf16 scores of dg_attn_edge_fwd / dg_softmax_agg16_fwd.  bit 2: da_in is bf16
+ * [B,N,N,D] -- the out_e path's gradient as dg_rows_gemm stores it with a bf16 output.  bit 3: de (fp32) += instead of
+ * being written.)
  * g and the statistics from bf16 scores a[B,N,N,D] (the side output of dg_attn_edge_fwd) -- the forward's
  * softmax-aggregate (layers.py:130-134) at 256 B per edge row. */
 int dg_softmax_agg16_fwd(const void* a_bf16, const float* v, float* g, float* stat_m, float* stat_inv, int B, int N,
@@ -138,15 +141,19 @@ int dg_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2
                void* workspace, long long workspace_bytes, void* stream);
 
 /* First half of the residual-MLP backward in one kernel: recompute h = relu(fc1(x)+b1) and z = x + fc2(h) + b2,
- * then the LayerNorm backward of `dout` through z.  Writes dz[R,D] (fp32), h_bf16[R,H] (bf16, for the dgrad and
- * weight-gradient passes); dgamma[D], dbeta[D] += (zero first).  Same workspace contract as dg_mlp_fwd. */
+ * then the LayerNorm backward of `dout` through z.  Writes dz[R,D] (fp32); optional side outputs (NULL to skip):
+ * h_bf16[R,H] (bf16: the operand of the fc2 weight gradient) and relu_mask[R][H/64] (uint64, 8-byte aligned: bit i of
+ * word w = (h[w*64+i] > 0) -- all that dg_mlp_bwd_dgrad needs of h, H/8 bytes per row instead of 2H);
+ * dgamma[D], dbeta[D] += (zero first).  Same workspace contract as dg_mlp_fwd. */
 int dg_mlp_bwd_ln(const float* x, const float* dout, const float* w1, const float* b1, const float* w2,
-                  const float* b2, const float* gamma, float* dz, void* h_bf16, float* dgamma, float* dbeta,
-                  long long R, int D, int H, float eps, void* workspace, long long workspace_bytes, void* stream);
-/* Second half: dh = (dz . W2) * (h > 0) written as bf16 [R,H]; dx = dz + dh . W1 written [R,D] (fp32).
- * (threshold_backward + the two dgrad `mm`s + the residual add of layers.py:51-54,191-192.) */
-int dg_mlp_bwd_dgrad(const float* dz, const void* h_bf16, const float* w1, const float* w2, float* dx,
-                     void* dh_bf16, long long R, int D, int H, void* workspace, long long workspace_bytes,
+                  const float* b2, const float* gamma, float* dz, void* h_bf16, void* relu_mask, float* dgamma,
+                  float* dbeta, long long R, int D, int H, float eps, void* workspace, long long workspace_bytes,
+                  void* stream);
+/* Second half: dh = (dz . W2) * (h > 0) written as bf16 [R,H] (dh_bf16, NULL to skip: only the fc1 weight gradient reads
+ * it); dx = dz + dh . W1 written [R,D] (fp32).  The sign of h comes from relu_mask (dg_mlp_bwd_ln's layout) when given,
+ * else from h_bf16.  (threshold_backward + the two dgrad `mm`s + the residual add of layers.py:51-54,191-192.) */
+int dg_mlp_bwd_dgrad(const float* dz, const void* h_bf16, const void* relu_mask, const float* w1, const float* w2,
+                     float* dx, void* dh_bf16, long long R, int D, int H, void* workspace, long long workspace_bytes,
                      void* stream);
 
 /* The edge half of the attention block in one tcgen05 kernel (layers.py:116,123-127 + the residual and LayerNorm of

@@ -75,9 +75,13 @@ class EmulBackend:
         xh, _ = self._stats(a, b, eps)
         out.copy_(xh * gamma + beta)
 
-    def add_ln_bwd(self, dy, a, b, gamma, dz, dgamma, dbeta, eps):
+    def add_ln_bwd(self, dy, a, b, gamma, dz, dgamma, dbeta, eps, accumulate=False):
         xh, r = self._stats(a, b, eps)
-        dz.copy_(r * self._proj(dy * gamma, xh))
+        val = r * self._proj(dy * gamma, xh)
+        if accumulate:
+            dz.add_(val)
+        else:
+            dz.copy_(val)
         d = a.shape[-1]
         dgamma.copy_((dy * xh).reshape(-1, d).sum(0))
         dbeta.copy_(dy.reshape(-1, d).sum(0))
@@ -166,7 +170,7 @@ class EmulBackend:
             stats[0].copy_(m)
             stats[1].copy_(1.0 / torch.exp(a - m[:, :, None, :]).sum(2))
 
-    def attn_scores_bwd(self, dg, da_in, q, k, v, e, c, de, dq, dk, dv, stats=None, scores_bf16=False):
+    def attn_scores_bwd(self, dg, da_in, q, k, v, e, c, de, dq, dk, dv, stats=None, scores_bf16=False, accumulate_de=False):
         a = torch.empty_like(e)
         self.modulate_fwd(q, k, e, c, a)
         if scores_bf16:
@@ -174,24 +178,38 @@ class EmulBackend:
         da = torch.empty_like(e)
         self.softmax_agg_bwd(dg, a, v, da, dv)
         if da_in is not None:
-            da = da + da_in
-        if de.dtype != e.dtype:
-            de32 = torch.empty_like(e)
-            self.modulate_bwd(da, q, k, e, c, dq, dk, de32)
-            de.copy_(de32)
+            da = da + da_in.to(da.dtype)
+        de32 = torch.empty_like(e)
+        self.modulate_bwd(da, q, k, e, c, dq, dk, de32)
+        if accumulate_de:
+            de.add_(de32)
         else:
-            self.modulate_bwd(da, q, k, e, c, dq, dk, de)
+            de.copy_(de32)
 
-    def mlp_bwd_ln(self, x, dout, w1, b1, w2, b2, gamma, dz, h16, dgamma, dbeta, eps, workspace):
+    def mlp_bwd_ln(self, x, dout, w1, b1, w2, b2, gamma, dz, h16, dgamma, dbeta, eps, workspace, mask=None):
         h = torch.relu(self._mm(x, w1.t(), "bf16") + b1)
-        h16.copy_(h)
-        m = self._mm(h16.to(x.dtype), w2.t(), "bf16") + b2
+        hq = h.to(torch.bfloat16)
+        if h16 is not None:
+            h16.copy_(hq)
+        if mask is not None:          # bit i of word w = h[w*64+i] > 0
+            bits = (h > 0).view(h.shape[0], -1, 64).to(torch.int64)
+            w = torch.zeros(h.shape[0], h.shape[1] // 64, dtype=torch.int64)
+            for i in range(64):
+                w |= bits[:, :, i] << i         # (bit 63 wraps into the sign: same 64 bits)
+            mask.copy_(w)
+        m = self._mm(hq.to(x.dtype), w2.t(), "bf16") + b2
         self.add_ln_bwd(dout, x, m, gamma, dz, dgamma, dbeta, eps)
 
-    def mlp_bwd_dgrad(self, dz, h16, w1, w2, dx, dh16, workspace):
-        dh = self._mm(dz, w2, "bf16") * (h16 > 0).to(dz.dtype)
-        dh16.copy_(dh)
-        dx.copy_(dz + self._mm(dh16.to(dz.dtype), w1, "bf16"))
+    def mlp_bwd_dgrad(self, dz, h16, w1, w2, dx, dh16, workspace, mask=None):
+        if mask is not None:
+            gate = torch.stack([(mask >> i) & 1 for i in range(64)], dim=2).reshape(mask.shape[0], -1).to(dz.dtype)
+        else:
+            gate = (h16 > 0).to(dz.dtype)
+        dh = self._mm(dz, w2, "bf16") * gate
+        dhq = dh.to(torch.bfloat16)
+        if dh16 is not None:
+            dh16.copy_(dhq)
+        dx.copy_(dz + self._mm(dhq.to(dz.dtype), w1, "bf16"))
 
     def softmax_agg16_fwd(self, a16, v, g, stats=None):
         a = a16.to(v.dtype).view(v.shape[0], v.shape[1], v.shape[1], v.shape[2])

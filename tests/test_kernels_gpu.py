@@ -236,3 +236,34 @@ def test_fused_mlp_bwd(cuda_dev, R, H):
         dh_ref = (bf(dz) @ bf(w2)) * (h16.double() > 0)
         assert rel_l2(dh16.double(), bf(dh_ref.float())) < 3e-3
         assert rel_l2(dx, dz.double() + dh16.double() @ bf(w1)) < 2e-5
+        # the ReLU sign as a bit mask (H/8 bytes per row): same dz; mask bits == (h > 0); the dgrad chain driven by the mask,
+        # with and without the dh side output, gives the same dx / dh bit for bit as the one driven by the bf16 h
+        dz2, h_none, _, _, mask = K.mlp_bwd_ln(x, dout, w1, b1, w2, b2, gamma, want_h=False, want_mask=True)
+        assert h_none is None and torch.equal(dz2, dz)
+        bits = torch.stack([(mask >> i) & 1 for i in range(64)], dim=2).reshape(R, H).bool()
+        assert torch.equal(bits, h16.float() > 0)
+        dx2, dh2 = K.mlp_bwd_dgrad(dz, None, w1, w2, mask=mask)
+        assert torch.equal(dx2, dx) and torch.equal(dh2, dh16)
+        dx3, dh3 = K.mlp_bwd_dgrad(dz, None, w1, w2, mask=mask, want_dh=False)
+        assert dh3 is None and torch.equal(dx3, dx)
+
+
+def test_accumulating_stores(cuda_dev):
+    """add_ln_bwd(dz_accum=...) and attn_scores_bwd(de_accum=...) add their result into a cotangent that already holds another
+    path's contribution (block_backward_backward), instead of a separate elementwise add."""
+    R, D, B, N, c = 777, 128, 3, 9, 0.25
+    dy, a, b = rnd(cuda_dev, R, D), rnd(cuda_dev, R, D, seed=1), rnd(cuda_dev, R, D, seed=2)
+    gamma = rnd(cuda_dev, D, seed=3, scale=0.1) + 1.0
+    base = rnd(cuda_dev, R, D, seed=4)
+    dz, dgam, dbet = K.add_ln_bwd(dy, a, b, gamma)
+    acc = base.clone()
+    dz2, dgam2, dbet2 = K.add_ln_bwd(dy, a, b, gamma, dz_accum=acc)
+    assert dz2 is acc and torch.equal(acc, base + dz) and rel_l2(dgam2, dgam) < 1e-6 and rel_l2(dbet2, dbet) < 1e-6
+    q, k, v = rnd(cuda_dev, B, N, D), rnd(cuda_dev, B, N, D, seed=1), rnd(cuda_dev, B, N, D, seed=2)
+    e, dg_, da_in = rnd(cuda_dev, B, N, N, D, seed=3), rnd(cuda_dev, B, N, D, seed=4), rnd(cuda_dev, B, N, N, D, seed=5)
+    _, _, stats = K.attn_scores_fwd(q, k, v, e, c, want_stats=True)
+    de, dq, dk, dv = K.attn_scores_bwd(dg_, da_in, q, k, v, e, c, stats)
+    base = rnd(cuda_dev, B, N, N, D, seed=6)
+    acc = base.clone()
+    de2, dq2, dk2, dv2 = K.attn_scores_bwd(dg_, da_in, q, k, v, e, c, stats, de_accum=acc)
+    assert de2 is acc and torch.equal(acc, base + de) and rel_l2(dq2, dq) < 1e-6 and rel_l2(dk2, dk) < 1e-6

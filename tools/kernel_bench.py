@@ -69,7 +69,7 @@ def main():
     x4 = x.view(b, n, n, d)
 
     with dg.precision("bf16"):
-        dz, h16, _, _ = K.mlp_bwd_ln(x, dout, w1, b1, w2, b2, gamma)
+        dz, h16, _, _, mask = K.mlp_bwd_ln(x, dout, w1, b1, w2, b2, gamma, want_mask=True)
         _, a16, _, _ = K.attn_edge_fwd(x, q, k, w, b2, w, b2, gamma, beta, 0.25)
         _, _, stats = K.attn_scores_fwd(q, k, v, x4, 0.25, want_stats=True, store_a=False)
 
@@ -92,6 +92,13 @@ def main():
             ("mlp_fwd[fused,H=384]", lambda: K.mlp_fwd(x, w1, b1, w2, b2, gamma, beta), 2 * r * d * 4, 4.0 * r * d * h),
             ("mlp_bwd_ln[fused,H=384]", lambda: K.mlp_bwd_ln(x, dout, w1, b1, w2, b2, gamma), r * (3 * d * 4 + h * 2), 4.0 * r * d * h),
             ("mlp_bwd_dgrad[fused,H=384]", lambda: K.mlp_bwd_dgrad(dz, h16, w1, w2), r * (2 * d * 4 + 2 * h * 2), 4.0 * r * d * h),
+            ("mlp_bwd_ln[fused,H=384,+mask]", lambda: K.mlp_bwd_ln(x, dout, w1, b1, w2, b2, gamma, want_mask=True),
+             r * (3 * d * 4 + h * 2 + h // 8), 4.0 * r * d * h),
+            ("mlp_bwd_ln[fused,H=384,mask only]", lambda: K.mlp_bwd_ln(x, dout, w1, b1, w2, b2, gamma, want_h=False, want_mask=True),
+             r * (3 * d * 4 + h // 8), 4.0 * r * d * h),
+            ("mlp_bwd_dgrad[fused,H=384,mask]", lambda: K.mlp_bwd_dgrad(dz, None, w1, w2, mask=mask), r * (2 * d * 4 + h * 2 + h // 8), 4.0 * r * d * h),
+            ("mlp_bwd_dgrad[fused,H=384,mask,no dh]", lambda: K.mlp_bwd_dgrad(dz, None, w1, w2, mask=mask, want_dh=False),
+             r * (2 * d * 4 + h // 8), 4.0 * r * d * h),
             ("attn_edge_fwd[fused,+a16]", lambda: K.attn_edge_fwd(x, q, k, w, b2, w, b2, gamma, beta, 0.25), r * d * 10, 4.0 * r * d * d),
             ("attn_edge_fwd[fused,+a16+e+z]", lambda: K.attn_edge_fwd(x, q, k, w, b2, w, b2, gamma, beta, 0.25, True, True, True),
              r * d * 18, 4.0 * r * d * d),
@@ -103,6 +110,9 @@ def main():
             ("attn_scores_bwd[fused,stats]", lambda: K.attn_scores_bwd(dgn, dout.view(b, n, n, d), q, k, v, x4, 0.25, stats), 3 * r * d * 4, 0.0),
             ("attn_scores_bwd[fused,stats,de16]", lambda: K.attn_scores_bwd(dgn, dout.view(b, n, n, d), q, k, v, x4, 0.25, stats, True),
              r * d * 10, 0.0),
+            ("attn_scores_bwd[fused,stats,de16,da16]", lambda: K.attn_scores_bwd(dgn, a16.view(b, n, n, d), q, k, v, x4, 0.25, stats, True),
+             r * d * 8, 0.0),
+            ("rows_gemm[K=128,N=128,o16]", lambda: K.rows_gemm(x, w, False, out_bf16=True), r * d * 6, 2.0 * r * d * d),
             ("mlp_fwd[unfused: 2 rows_gemm + add_ln]", unfused, 2 * r * d * 4, 4.0 * r * d * h),
             ("rows_gemm[K=128,N=128]", lambda: K.rows_gemm(x, w, True, b2), 2 * r * d * 4, 2.0 * r * d * d),
             ("rows_gemm[K=128,N=128,+resid]", lambda: K.rows_gemm(x, w, True, b2, resid=dout), 3 * r * d * 4, 2.0 * r * d * d),

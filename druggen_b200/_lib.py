@@ -38,6 +38,7 @@ SIGNATURES = {
     "dg_mlp_bwd_ln": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _F, _P, _LL, _P],
     "dg_mlp_bwd_dgrad": [_P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _P, _LL, _P],
     "dg_mlp_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _F, _P, _LL, _P],
+    "dg_symmetrize": [_P, _P, _I, _I, _I, _P],
     "dg_label2onehot": [_P, _I, _P, _LL, _I, _P],
     "dg_argmax_last": [_P, _P, _LL, _I, _P],
     "dg_embed_labels_fwd": [_P, _I, _P, _P, _LL, _I, _I, _I, _I, _P],
@@ -282,6 +283,11 @@ def _mlp_bwd_dgrad(self, dz, h16, w1, w2, dx, dh16, workspace, mask=None):
                _ptr(dh16), r, d, h, _ptr(workspace), workspace.numel())
 
 
+def _symmetrize(self, e, out):
+    b, n, _, d = e.shape
+    self._call("dg_symmetrize", ("symmetrize", 0, _nbytes(e, e, out), "hbm"), _ptr(e), _ptr(out), b, n, d)
+
+
 def _label2onehot(self, labels, out, classes):
     self._call("dg_label2onehot", ("label2onehot", 0, _nbytes(labels, out), "hbm"), _ptr(labels), labels.element_size(), _ptr(out),
                labels.numel(), classes)
@@ -334,6 +340,7 @@ def _label_error(self, clear=True):
     return self.lib.dg_label_error(int(clear))
 
 
+CudaBackend.symmetrize = _symmetrize
 CudaBackend.embed_labels_fwd = _embed_labels_fwd
 CudaBackend.embed_labels_bwd = _embed_labels_bwd
 CudaBackend.gp_interp = _gp_interp

@@ -638,6 +638,9 @@ static int gemm_tn_tc_launch(const float* a, const float* b, float* out, float* 
   long long tiles = (R + tc::kTnRows - 1) / tc::kTnRows;
   long long ctas = tiles < sm_count() ? tiles : sm_count();
   long long per = (tiles + ctas - 1) / ctas;
+  // every CTA ends with an atomic flush of the whole [M,N] block: on node-sized inputs (R = B N rows, ~10 tiles per CTA) the
+  // 148 flushes into the same 64-192 KB cost more than the contraction -- give a CTA at least 32 tiles (2048 rows)
+  if (per < 32) per = tiles < 32 ? tiles : 32;
   ctas = (tiles + per - 1) / per;
   tc::gemm_tn_tc_kernel<<<(int)ctas, tc::kTnThreads, smem, s>>>(a, b, out, colsum_a, R, M, N, per, stages, flags,
                                                                 opt_get(DG_OPT_L2_PREFETCH) & (M + N == 256 ? DG_PF_GEMM_TN : DG_PF_GEMM_TN_WIDE),

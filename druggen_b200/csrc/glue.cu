@@ -266,6 +266,23 @@ static int grid_for(long long work_items, int per_block) {
   return (int)(blocks < 1 ? 1 : blocks);
 }
 
+// models.py:94 for DENSE inputs (the Discriminator on generated / interpolated molecules): out_ij = (e_ij + e_ji) / 2, one pass
+// (the reference's permute + add + div are three).  Self-adjoint: its backward is the same launch on the gradient.
+__global__ void __launch_bounds__(256) symmetrize_kernel(const float* __restrict__ e, float* __restrict__ out, long long rows, int n, int D) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long nn = (long long)n * n;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    const long long b = r / nn, ij = r - b * nn;
+    const int i = (int)(ij / n), j = (int)(ij - (long long)i * n);
+    const long long rt = b * nn + (long long)j * n + i;
+    for (int c = lane * 4; c < D; c += 128) {
+      const float4 a = ld4(e + r * D + c), t = ld4(e + rt * D + c);
+      st4(out + r * D + c, make_float4((a.x + t.x) / 2.f, (a.y + t.y) / 2.f, (a.z + t.z) / 2.f, (a.w + t.w) / 2.f));
+    }
+  }
+}
+
 }  // namespace dg
 
 using namespace dg;
@@ -289,6 +306,15 @@ static int embed_check(const char* who, long long rows, int n, int classes, int 
   if (label_bytes != 1 && label_bytes != 8) return fail("%s: labels are uint8 or int64 (label_bytes=%d)", who, label_bytes);
   if (sym && rows % ((long long)n * n)) return fail("%s: symmetric rows must be a multiple of n*n", who);
   return 0;
+}
+
+extern "C" int dg_symmetrize(const float* e, float* out, int B, int N, int D, void* stream) {
+  if (B <= 0 || N <= 0 || D <= 0 || (D & 3)) return fail("dg_symmetrize: bad shape B=%d N=%d D=%d (D must be a multiple of 4)", B, N, D);
+  if (e == out) return fail("dg_symmetrize: in-place is not supported (row ij reads row ji)");
+  const long long rows = (long long)B * N * N;
+  long long blocks = (rows + 7) / 8, cap = (long long)sm_count() * 16;
+  symmetrize_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(e, out, rows, N, D);
+  return check_launch("dg_symmetrize");
 }
 
 extern "C" int dg_embed_labels_fwd(const void* labels, int label_bytes, const float* lut, float* y, long long rows, int n,

@@ -403,6 +403,16 @@ def argmax_last(t):
     return out
 
 
+def symmetrize(e):
+    """models.py:94: (e + e.permute(0, 2, 1, 3)) / 2 for e:[B,N,N,D] in one pass."""
+    _chk(e)
+    assert e.dim() == 4 and e.shape[1] == e.shape[2], e.shape
+    out = torch.empty_like(e)
+    if e.numel():
+        _be().symmetrize(e, out)
+    return out
+
+
 def embed_labels_fwd(labels, lut, sym: bool):
     """Prologue of a one-hot batch given as labels (models.py:91-94): labels [B,N] -> lut[labels] [B,N,D]; ``sym`` (edges,
     labels [B,N,N]) -> (lut[a_ij] + lut[a_ji]) / 2 [B,N,N,D].  lut:[classes,D] = the prologue MLP applied to the identity."""

@@ -340,6 +340,19 @@ class EmbedLabels(Function):
         return K.embed_labels_bwd(labels, _c(dy), ctx.classes, ctx.sym), None, None
 
 
+class Symmetrize(Function):
+    """models.py:94 for dense inputs: (e + e^T) / 2 over the two atom axes.  Linear and self-adjoint, so every order of its
+    derivative is the same launch."""
+
+    @staticmethod
+    def forward(ctx, e):
+        return K.symmetrize(e.contiguous())
+
+    @staticmethod
+    def backward(ctx, dy):
+        return Symmetrize.apply(dy)
+
+
 class GradPenalty(Function):
     """loss.py:42-47: (g_node [B,...], g_edge [B,...]) -> mean_b (|concat(g_node_b, g_edge_b)|_2 - 1)^2 in two small
     launches; its backward scales the two gradient tensors by 2 (|g_b| - 1) / (B |g_b|)."""

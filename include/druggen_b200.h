@@ -178,6 +178,10 @@ int dg_label_error(int clear);
 /* inference.py:197-198 torch.max(t, -1)[1]: out[rows] int64 = index of the first maximum of each row of x[rows, C]
  * (a NaN wins; the first NaN), i.e. ATen's CPU result, bit for bit. */
 int dg_argmax_last(const float* x, long long* out, long long rows, int C, void* stream);
+/* models.py:94 / :199 for dense inputs: out[b,i,j,:] = (e[b,i,j,:] + e[b,j,i,:]) / 2 in one pass ([B,N,N,D] fp32, D % 4 == 0,
+ * out != e).  Self-adjoint: the backward is the same call on the gradient. */
+int dg_symmetrize(const float* e, float* out, int B, int N, int D, void* stream);
+
 /* models.py:91-94 / 196-199 for one-hot inputs given as labels: y[r,:] = lut[labels[r],:] (node rows, sym = 0) or, for edge rows
  * r = (b n + i) n + j with sym = 1, y[r,:] = (lut[a_ij,:] + lut[a_ji,:]) / 2 -- the prologue MLP of a one-hot row is a row of the
  * [classes, D] table lut = act(W2 act(W1[:,l] + b1) + b2) the host computes from the weights; D == 128, classes <= 16. */

@@ -234,6 +234,9 @@ class EmulBackend:
             z_out.copy_(z)
         self.add_ln_fwd(z, None, gamma, beta, out, eps)
 
+    def symmetrize(self, e, out):
+        out.copy_((e + e.permute(0, 2, 1, 3)) / 2)
+
     def label2onehot(self, labels, out, classes):
         out.zero_()
         out.scatter_(out.dim() - 1, labels.long().unsqueeze(-1), 1.0)

@@ -137,3 +137,32 @@ def test_trainer_labels_equal_onehots_fp32(cuda_dev):
         assert abs(l0[0] - l1[0]) < 1e-4 * max(1.0, abs(l0[0])) and abs(l0[1] - l1[1]) < 1e-4 * max(1.0, abs(l0[1]))
     for p0, p1 in zip(res[0][1], res[1][1]):
         assert rel_l2(p1, p0) < 1e-4
+
+
+@pytest.mark.parametrize("B,N,D", [(1, 1, 128), (3, 9, 128), (2, 45, 128), (2, 7, 64)])
+def test_symmetrize_bit_exact_and_self_adjoint(cuda_dev, B, N, D):
+    """models.py:94 on a dense tensor: same two roundings as torch's add + div; the primitive's backward is the same launch."""
+    e = torch.randn(B, N, N, D, generator=torch.Generator().manual_seed(N)).to(cuda_dev)
+    want = (e + e.permute(0, 2, 1, 3)) / 2
+    assert torch.equal(K.symmetrize(e), want)
+    x = e.clone().requires_grad_(True)
+    w = torch.randn_like(e)
+    (ops.Symmetrize.apply(x) * w).sum().backward()
+    assert torch.equal(x.grad, (w + w.permute(0, 2, 1, 3)) / 2)
+
+
+def test_dense_prologue_matches_torch_modules(cuda_dev):
+    """Discriminator on dense (generated-like) inputs: the fused prologue path (two Linear+ReLU primitives + one symmetrise pass)
+    against the nn.Sequential + permute/add/div statement of models.py:92-94 in the fp32 parity mode, outputs and input gradients."""
+    torch.manual_seed(0)
+    D = dg.Discriminator("relu", 9, 5, 13, 0.0, dim=128, depth=1, heads=8, mlp_ratio=3).to(cuda_dev)
+    z_e = torch.rand(4, 9, 9, 5, device=cuda_dev).requires_grad_(True)
+    z_n = torch.rand(4, 9, 13, device=cuda_dev)
+    with dg.precision("fp32"):
+        out = D(z_e, z_n)
+        (g1,) = torch.autograd.grad(out.sum(), z_e)
+        edge = D.edge_layers(z_e)
+        edge = (edge + edge.permute(0, 2, 1, 3)) / 2
+        ref = D.node_mlp(D.TransformerEncoder(D.node_layers(z_n), edge)[0].reshape(4, -1))
+        (g2,) = torch.autograd.grad(ref.sum(), z_e)
+    assert rel_l2(out, ref) < 1e-5 and rel_l2(g1, g2) < 1e-4

@@ -121,6 +121,9 @@ def main():
             ("gemm_tn[M=128,N=128]", lambda: K.gemm_tn(x, dout), 2 * r * d * 4, 2.0 * r * d * d),
             ("gemm_tn[M=128,N=128,b16]", lambda: K.gemm_tn(x, a16), r * d * 6, 2.0 * r * d * d),
             ("gemm_tn[M=384,N=128,a16]", lambda: K.gemm_tn(h16, x), r * (h * 2 + d * 4), 2.0 * r * d * h),
+            ("gemm_tn[node rows R=92160,M=128,N=128]", lambda: K.gemm_tn(x[:92160], dout[:92160]), 2 * 92160 * d * 4, 2.0 * 92160 * d * d),
+            ("rows_gemm[node rows R=92160,K=128,N=128]", lambda: K.rows_gemm(x[:92160], w, True, b2), 2 * 92160 * d * 4, 2.0 * 92160 * d * d),
+            ("symmetrize", lambda: K.symmetrize(x4), 3 * r * d * 4, 0.0),
             ("add_ln_fwd", lambda: K.add_ln_fwd(x, dout, gamma, beta), 3 * r * d * 4, 0.0),
             ("add_ln_bwd", lambda: K.add_ln_bwd(x, dout, None, gamma), 3 * r * d * 4, 0.0),
         ]

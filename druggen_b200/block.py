@@ -83,14 +83,19 @@ def _scores_bwd(dg, da_in, a, q, k, v, e, c, stats=None):
     return de, dq, dk, dv
 
 
-def block_forward_nograd(x, y, params: Sequence[torch.Tensor], heads: int, edge_out: bool = True):
+def block_forward_nograd(x, y, params: Sequence[torch.Tensor], heads: int, edge_out: bool = True, want_stats: bool = False):
     """Same function as ``block_forward`` for callers that need no graph (inference, the checkpointed
-    forward): uses the fused tcgen05 kernels where they exist, raw kernels otherwise."""
+    forward): uses the fused tcgen05 kernels where they exist, raw kernels otherwise.
+    ``want_stats``: returns (x_out, y_out, stats) with stats = the softmax statistics (max, 1/sum, g) per (molecule, query atom,
+    channel) when the fused chain computed them (else None) -- three NODE-sized tensors the checkpointed backward keeps so that
+    it does not have to re-run the softmax over the recomputed scores."""
     p = lambda n: params[_IDX[n]]  # noqa: E731
     b, n, d = x.shape
     hid = p("mlp.fc1.weight").shape[0]
+    stats = None
     if not K.fused_available(d, hid):
-        return block_forward(x, y, params, heads, edge_out)
+        out = block_forward(x, y, params, heads, edge_out)
+        return out + (None,) if want_stats else out
     c = 1.0 / math.sqrt(d // heads)
     x1 = K.add_ln_fwd(x.reshape(-1, d), None, p("ln1.weight"), p("ln1.bias"))
     q = K.rows_gemm(x1, p("attn.q.weight"), True, p("attn.q.bias")).view(b, n, d)
@@ -103,7 +108,10 @@ def block_forward_nograd(x, y, params: Sequence[torch.Tensor], heads: int, edge_
         s16 = K.softmax_scores_bf16()
         y3, a16, e, _ = K.attn_edge_fwd(y2d, q, k, p("attn.e.weight"), p("attn.e.bias"), p("attn.out_e.weight"),
                                         p("attn.out_e.bias"), p("ln4.weight"), p("ln4.bias"), c, want_a16=s16, want_e=not s16)
-        g = K.softmax_agg16_fwd(a16, v) if s16 else K.attn_scores_fwd(q, k, v, e.view(b, n, n, d), c, store_a=False)[1]
+        if s16 and want_stats:
+            g, stats = K.softmax_agg16_fwd(a16, v, want_stats=True)
+        else:
+            g = K.softmax_agg16_fwd(a16, v) if s16 else K.attn_scores_fwd(q, k, v, e.view(b, n, n, d), c, store_a=False)[1]
         del a16, e
     else:
         e = K.rows_gemm(y2d, p("attn.e.weight"), True, p("attn.e.bias"))
@@ -114,7 +122,7 @@ def block_forward_nograd(x, y, params: Sequence[torch.Tensor], heads: int, edge_
     x_out = K.mlp_fwd(x3, p("mlp.fc1.weight"), p("mlp.fc1.bias"), p("mlp.fc2.weight"), p("mlp.fc2.bias"),
                       p("ln5.weight"), p("ln5.bias")).view(b, n, d)
     if not edge_out:
-        return x_out, None
+        return (x_out, None, stats) if want_stats else (x_out, None)
     if not chain:
         y1 = K.rows_gemm(a.view(-1, d), p("attn.out_e.weight"), True, p("attn.out_e.bias"))
         del a
@@ -122,11 +130,11 @@ def block_forward_nograd(x, y, params: Sequence[torch.Tensor], heads: int, edge_
         del y1
     y_out = K.mlp_fwd(y3, p("mlp2.fc1.weight"), p("mlp2.fc1.bias"), p("mlp2.fc2.weight"), p("mlp2.fc2.bias"),
                       p("ln6.weight"), p("ln6.bias")).view(b, n, n, d)
-    return x_out, y_out
+    return (x_out, y_out, stats) if want_stats else (x_out, y_out)
 
 
 def block_backward(x, y, dxo, dyo, params: Sequence[torch.Tensor], heads: int, edge_out: bool = True,
-                   want_params: bool = True):
+                   want_params: bool = True, fwd_stats=None):
     """First-order backward of the block as a hand-sequenced list of raw kernel launches (no autograd
     graph): recompute from the block inputs, then the chain of Appendix-B of SURVEY.md.  Gradient
     accumulation is fused into GEMM epilogues (``resid``), the ReLU derivative into the dgrad epilogue
@@ -201,7 +209,9 @@ def block_backward(x, y, dxo, dyo, params: Sequence[torch.Tensor], heads: int, e
                                          p("attn.out_e.bias"), p("ln4.weight"), p("ln4.bias"), c, want_a16=True, want_e=True,
                                          want_z=True)
         a = None
-        if K.softmax_scores_bf16():
+        if K.softmax_scores_bf16() and fwd_stats is not None:
+            g, sm_stats = fwd_stats[2], fwd_stats                           # kept by the checkpointed forward (node-sized)
+        elif K.softmax_scores_bf16():
             g, sm_stats = K.softmax_agg16_fwd(a2d, v, want_stats=True)     # the same bf16 scores the forward's softmax saw
         else:
             _, g, sm_stats = K.attn_scores_fwd(q, k, v, e.view(b, n, n, d), c, want_stats=True, store_a=False)
@@ -298,21 +308,24 @@ def block_backward_backward(x, y, dxo, dyo, ux, uy, params: Sequence[torch.Tenso
     def mlp_recompute(mlp, ln, xin, dout):
         """forward (h, m = xin + fc2(h)) and first-order backward (t = LN^T dout, dh, dxin) of LN(xin + mlp(xin))."""
         w1, b1, w2, b2 = p(mlp + ".fc1.weight"), p(mlp + ".fc1.bias"), p(mlp + ".fc2.weight"), p(mlp + ".fc2.bias")
-        h = K.rows_gemm(xin, w1, True, b1, relu=True, out_bf16=narrow)
+        if narrow:     # the first chain of the first-order backward gives t, h (bf16) and the ReLU sign mask in one launch
+            t, h, _, _, mask = K.mlp_bwd_ln(xin, dout, w1, b1, w2, b2, p(ln + ".weight"), want_mask=True)
+            m = K.rows_gemm(h, w2, True, b2, resid=xin)
+            dxin, dh = K.mlp_bwd_dgrad(t, None, w1, w2, mask=mask)
+            return (h, mask), m, t, dh, dxin
+        h = K.rows_gemm(xin, w1, True, b1, relu=True)
         m = K.rows_gemm(h, w2, True, b2, resid=xin)
         t = K.add_ln_bwd(dout, m, None, p(ln + ".weight"))[0]
-        if narrow:
-            dxin, dh = K.mlp_bwd_dgrad(t, h, w1, w2)
-        else:
-            dh = K.rows_gemm(t, w2, False, gate=h)
-            dxin = K.rows_gemm(dh, w1, False, resid=t)
-        return h, m, t, dh, dxin
+        dh = K.rows_gemm(t, w2, False, gate=h)
+        dxin = K.rows_gemm(dh, w1, False, resid=t)
+        return (h, None), m, t, dh, dxin
 
-    def mlp_second(mlp, u, t, h, dh):
+    def mlp_second(mlp, u, t, hm, dh):
         """reverse of  dxin = t + ((t W2) * M) W1  given u = c[dxin]: returns c[t]; c[W2] += t^T tM, c[W1] += dh^T u."""
         w1, w2 = p(mlp + ".fc1.weight"), p(mlp + ".fc2.weight")
+        h, mask = hm
         if narrow:     # the dgrad chain with the two weights transposed into each other's role
-            c_t, tm = K.mlp_bwd_dgrad(u, h, w2.t().contiguous(), w1.t().contiguous())
+            c_t, tm = K.mlp_bwd_dgrad(u, None, w2.t().contiguous(), w1.t().contiguous(), mask=mask)
         else:
             tm = K.rows_gemm(u, w1, True, gate=h)
             c_t = K.rows_gemm(tm, w2, True, resid=u)
@@ -320,11 +333,12 @@ def block_backward_backward(x, y, dxo, dyo, ux, uy, params: Sequence[torch.Tenso
         wacc(mlp + ".fc1", dh, u, bias=False)
         return c_t
 
-    def mlp_first(mlp, c_m, h, xin):
+    def mlp_first(mlp, c_m, hm, xin):
         """reverse of  m = xin + fc2(relu(fc1(xin)))  given c[m]: returns c[xin]; the four parameter cotangents accumulate."""
         w1, w2 = p(mlp + ".fc1.weight"), p(mlp + ".fc2.weight")
+        h, mask = hm
         if narrow:
-            c_xin, ch = K.mlp_bwd_dgrad(c_m, h, w1, w2)
+            c_xin, ch = K.mlp_bwd_dgrad(c_m, None, w1, w2, mask=mask)
         else:
             ch = K.rows_gemm(c_m, w2, False, gate=h)
             c_xin = K.rows_gemm(ch, w1, False, resid=c_m)
@@ -486,10 +500,11 @@ class EncoderBlockFn(Function):
     @staticmethod
     def forward(ctx, x, y, heads, edge_out, *params):
         ctx.heads, ctx.edge_out = heads, edge_out
-        ctx.save_for_backward(x, y, *params)
         ctx.set_materialize_grads(False)
         with torch.no_grad():
-            xo, yo = block_forward_nograd(x, y, params, heads, edge_out)
+            xo, yo, stats = block_forward_nograd(x, y, params, heads, edge_out, want_stats=True)
+        ctx.nstats = 0 if stats is None else len(stats)
+        ctx.save_for_backward(x, y, *params, *(stats or ()))
         if yo is None:
             yo = y.new_empty(0)
             ctx.mark_non_differentiable(yo)
@@ -498,12 +513,15 @@ class EncoderBlockFn(Function):
     @staticmethod
     def backward(ctx, dxo, dyo):
         x, y, *params = ctx.saved_tensors
+        stats = None
+        if ctx.nstats:
+            params, stats = params[:-ctx.nstats], tuple(params[-ctx.nstats:])
         if not ctx.edge_out:
             dyo = None
         if dxo is None and dyo is None:
             return (None,) * (4 + len(params))
         want = _params_wanted(ctx, 4) if torch.is_grad_enabled() else any(ctx.needs_input_grad[4:])
-        outs = EncoderBlockBwdFn.apply(x, y, dxo, dyo, ctx.heads, ctx.edge_out, want, *params)
+        outs = EncoderBlockBwdFn.apply(x, y, dxo, dyo, ctx.heads, ctx.edge_out, want, stats, *params)
         return (outs[0], outs[1], None, None) + tuple(outs[2:])
 
 
@@ -513,11 +531,11 @@ class EncoderBlockBwdFn(Function):
     reference, ``.grad`` stays None and AdamW leaves those tensors untouched)."""
 
     @staticmethod
-    def forward(ctx, x, y, dxo, dyo, heads, edge_out, want_params, *params):
+    def forward(ctx, x, y, dxo, dyo, heads, edge_out, want_params, fwd_stats, *params):
         ctx.heads, ctx.edge_out = heads, edge_out
         ctx.save_for_backward(x, y, dxo, dyo, *params)
         ctx.set_materialize_grads(False)
-        dx, dy, pgrads = block_backward(x, y, dxo, dyo, params, heads, edge_out, want_params)
+        dx, dy, pgrads = block_backward(x, y, dxo, dyo, params, heads, edge_out, want_params, fwd_stats)
         return (dx, dy) + tuple(pgrads)
 
     @staticmethod
@@ -528,7 +546,7 @@ class EncoderBlockBwdFn(Function):
             # the gradient-penalty case (cotangents on dx / dy only): the hand-sequenced second-order pass
             with torch.no_grad():
                 c_x, c_y, c_dxo, c_dyo, cp = block_backward_backward(x, y, dxo, dyo, u[0], u[1], params, heads, edge_out)
-            return (c_x, c_y, c_dxo, c_dyo if (dyo is not None and edge_out) else None, None, None, None) + tuple(cp)
+            return (c_x, c_y, c_dxo, c_dyo if (dyo is not None and edge_out) else None, None, None, None, None) + tuple(cp)
         with torch.enable_grad():
             leaves, outs, gouts = _recompute(x, y, dxo, dyo, params, heads, edge_out, True)
             # only the first-order gradients that actually received a cotangent are rebuilt with a graph: in the
@@ -546,7 +564,7 @@ class EncoderBlockBwdFn(Function):
         tail = second[2 + n:]
         g_dxo = tail.pop(0) if dxo is not None else None
         g_dyo = tail.pop(0) if (dyo is not None and edge_out) else None
-        return (second[0], second[1], g_dxo, g_dyo, None, None, None) + tuple(second[2:2 + n])
+        return (second[0], second[1], g_dxo, g_dyo, None, None, None, None) + tuple(second[2:2 + n])
 
 
 class _ParamGate(Function):

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Launch each hot-path kernel twice at the bench size (B=512, N=45) so ncu can capture it:
     ncu --set full --clock-control none --import-source on \\
-        -k regex:'mlp_chain|rows_gemm_tc|gemm_tn_tc|attn_scores|attn_fwd_warp|add_ln_bwd_kernel|bwd_bwd' -s 18 -c 18 -o gpurun_out/prof python tools/profile_one.py
+        -k regex:'mlp_chain|rows_gemm_tc|gemm_tn_tc|attn_scores|attn_fwd_warp|add_ln_bwd_kernel|bwd_bwd' -s 21 -c 21 -o gpurun_out/prof python tools/profile_one.py
 """
 import os
 import sys
@@ -30,8 +30,10 @@ with dg.precision("bf16"):
         K.rows_gemm(x, wd, True, b2)                                    # 128x128 projection
         h16 = K.rows_gemm(x, w1, True, b1, relu=True, out_bf16=True)    # fc1 + ReLU -> bf16 hidden
         K.rows_gemm(dy, w2, False, gate=h16, out_bf16=True)             # dgrad with fused ReLU gate
-        dz, hh, _, _ = K.mlp_bwd_ln(x, dy, w1, b1, w2, b2, gamma)        # fused: recompute + LayerNorm backward + h spill
-        K.mlp_bwd_dgrad(dz, hh, w1, w2)                                 # fused: gated dgrad + residual + dh spill
+        dz, hh, _, _, mask = K.mlp_bwd_ln(x, dy, w1, b1, w2, b2, gamma, want_mask=True)   # fused: recompute + LayerNorm backward + h spill + sign mask
+        K.mlp_bwd_dgrad(dz, None, w1, w2, mask=mask)                    # fused: mask-gated dgrad + residual + dh spill
+        K.mlp_bwd_dgrad(dz, hh, w1, w2)                                 # ... gated by the bf16 h (second-order pass before the mask)
+        K.mlp_bwd_dgrad(dz, None, w1, w2, mask=mask, want_dh=False)     # ... dgrad-only passes (no weight gradients wanted)
         K.gemm_tn(dy, x)                                                # weight gradient 128x128
         K.gemm_tn(dy, h16)                                              # weight gradient 128x384 (bf16 operand)
         K.add_ln_bwd(dy, x, x, gamma)
@@ -41,7 +43,8 @@ with dg.precision("bf16"):
         y3, a16, _, _ = K.attn_edge_fwd(x, q, k, wd, b2, wd, b2, gamma, beta, 0.25)            # fused edge attention chain (forward)
         K.attn_edge_fwd(x, q, k, wd, b2, wd, b2, gamma, beta, 0.25, True, True, True)          # ... with the backward's side outputs
         _, st = K.softmax_agg16_fwd(a16, v, want_stats=True)                                    # softmax-aggregate from the bf16 scores
-        K.attn_scores_bwd(dg_, dy.view(b, n, n, d), q, k, v, e4, 0.25, st, de_bf16=True, scores_bf16=True)
+        da16 = K.rows_gemm(dy, wd, False, out_bf16=True)                                         # out_e dgrad, bf16 output
+        K.attn_scores_bwd(dg_, da16.view(b, n, n, d), q, k, v, e4, 0.25, st, de_bf16=True, scores_bf16=True)
         K.rows_gemm(a16, wd, False, resid=dy)                                                    # dgrad with bf16 operand + fused accumulation
         K.modulate_bwd_bwd(q, k, e4, dy.view(b, n, n, d), q, k, e4, 0.25)   # second-order kernels of the gradient penalty
         K.softmax_agg_bwd_bwd(dy.view(b, n, n, d), v, dg_, e4, v)

@@ -177,7 +177,7 @@ def block_backward(x, y, dxo, dyo, params: Sequence[torch.Tensor], heads: int, e
         if h16:      # two fused tcgen05 chains; h and dh cross HBM once each, as bf16, ONLY for the weight gradients: the
             # dgrad chain takes the ReLU sign from a bit mask (H/8 bytes per row instead of the 2H-byte bf16 h)
             dz, hh, dgam, dbet, mask = K.mlp_bwd_ln(xin, dout2d, w1, b1, w2, b2, p(ln + ".weight"), want_h=want_params,
-                                                    want_mask=True)
+                                                    want_mask=True, want_affine=want_params)
             if want_params:
                 put(ln + ".weight", dgam)
                 put(ln + ".bias", dbet)
@@ -309,7 +309,7 @@ def block_backward_backward(x, y, dxo, dyo, ux, uy, params: Sequence[torch.Tenso
         """forward (h, m = xin + fc2(h)) and first-order backward (t = LN^T dout, dh, dxin) of LN(xin + mlp(xin))."""
         w1, b1, w2, b2 = p(mlp + ".fc1.weight"), p(mlp + ".fc1.bias"), p(mlp + ".fc2.weight"), p(mlp + ".fc2.bias")
         if narrow:     # the first chain of the first-order backward gives t, h (bf16) and the ReLU sign mask in one launch
-            t, h, _, _, mask = K.mlp_bwd_ln(xin, dout, w1, b1, w2, b2, p(ln + ".weight"), want_mask=True)
+            t, h, _, _, mask = K.mlp_bwd_ln(xin, dout, w1, b1, w2, b2, p(ln + ".weight"), want_mask=True, want_affine=False)
             m = K.rows_gemm(h, w2, True, b2, resid=xin)
             dxin, dh = K.mlp_bwd_dgrad(t, None, w1, w2, mask=mask)
             return (h, mask), m, t, dh, dxin

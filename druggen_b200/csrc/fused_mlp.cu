@@ -212,6 +212,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
   const long long my_tiles = blockIdx.x < num_tiles ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const bool spill = (kMode == kBwdA || kMode == kBwdB || kMode == kAttn) && A.spill != nullptr;
   const bool use_mask = kMode == kBwdB && A.mask_in != nullptr;
+  const bool want_affine = kMode == kBwdA && A.dgamma != nullptr;      // BWD_A: the LayerNorm's dgamma / dbeta are wanted
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -677,8 +678,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
           const float h0 = g4.x * d4.x, h1 = g4.y * d4.y, h2 = g4.z * d4.z, h3 = g4.w * d4.w;
           sg += (h0 + h1) + (h2 + h3);
           sgx = fmaf(h0, xh[0], fmaf(h1, xh[1], fmaf(h2, xh[2], fmaf(h3, xh[3], sgx))));
-          st4(stg + stg_off(lane, i), make_float4(d4.x * xh[0], d4.y * xh[1], d4.z * xh[2], d4.w * xh[3]));
+          if (want_affine) st4(stg + stg_off(lane, i), make_float4(d4.x * xh[0], d4.y * xh[1], d4.z * xh[2], d4.w * xh[3]));
         }
+        if (!want_affine) continue;                                   // (dgrad-only passes: no dgamma / dbeta column sums)
         __syncwarp();
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {                              // lane: chunk lane&3, rows (lane>>2)*4 .. +3
@@ -690,6 +692,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
       // dbeta: column sums of this warp's own dout slab, straight from the tile (lane: chunk lane&15, rows (lane>>4)*16 .. +15)
 #pragma unroll
       for (int rr = 0; rr < 16; ++rr) {
+        if (!want_affine) break;
         const int r = (lane >> 4) * 16 + rr, j = lane & 15;
         const float4 t = ld4(reinterpret_cast<const float*>(ioslab + (j >> 3) * kBlkBytes + r * 128 + (((j & 7) ^ (r & 7)) << 4)));
         acc_b.x += t.x; acc_b.y += t.y; acc_b.z += t.z; acc_b.w += t.w;
@@ -719,7 +722,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
       DG_PROF(11)
     }
     if (lane == 0) bulk_wait0();                                      // outstanding TMA stores complete before the CTA retires
-    if (kMode == kBwdA) {
+    if (kMode == kBwdA && want_affine) {
 #pragma unroll
       for (int g16 = 0; g16 < 4; ++g16) {                            // dgamma: fold the 8 row groups (lane>>2), lanes 0-3 flush
         float v4[4] = {acc_g[g16].x, acc_g[g16].y, acc_g[g16].z, acc_g[g16].w};
@@ -836,6 +839,7 @@ extern "C" int dg_mlp_bwd_ln(const float* x, const float* dout, const float* w1,
                              void* stream) {
   if (mlp_check("dg_mlp_bwd_ln", x, R, D, H, workspace, workspace_bytes)) return 1;
   if (reinterpret_cast<uintptr_t>(relu_mask) & 7) return fail("dg_mlp_bwd_ln: the sign mask must be 8-byte aligned");
+  if ((dgamma == nullptr) != (dbeta == nullptr)) return fail("dg_mlp_bwd_ln: pass both dgamma and dbeta or neither");
   cudaStream_t s = (cudaStream_t)stream;
   tc::mlp_pack_weights_kernel<<<48, 256, 0, s>>>(w1, w2, (uint8_t*)workspace, H, 0);
   tc::MlpArgs a{x, (const uint8_t*)workspace, b1, b2, gamma, nullptr, dout, dz, (uint16_t*)h_bf16, nullptr,

@@ -256,7 +256,8 @@ def _mlp_ws(w1):
     return torch.empty(2 * (w1.shape[0] // 128) * 32768, dtype=torch.uint8, device=w1.device)
 
 
-def mlp_bwd_ln(x, dout, w1, b1, w2, b2, gamma, eps: float = 1e-5, want_h: bool = True, want_mask: bool = False):
+def mlp_bwd_ln(x, dout, w1, b1, w2, b2, gamma, eps: float = 1e-5, want_h: bool = True, want_mask: bool = False,
+               want_affine: bool = True):
     """Recompute the residual MLP from x and take the LayerNorm backward of ``dout``.
     -> (dz [R,128] fp32, h [R,H] bf16 | None, dgamma, dbeta[, mask]).  ``want_mask``: also the ReLU sign mask [R, H/64] int64
     (H/8 bytes per row) -- all ``mlp_bwd_dgrad`` needs of h; ``want_h=False`` skips the bf16 h (only the fc2 weight gradient
@@ -265,7 +266,7 @@ def mlp_bwd_ln(x, dout, w1, b1, w2, b2, gamma, eps: float = 1e-5, want_h: bool =
     dz = torch.empty_like(x)
     h16 = torch.empty((x.shape[0], w1.shape[0]), dtype=torch.bfloat16, device=x.device) if want_h else None
     mask = torch.empty((x.shape[0], w1.shape[0] // 64), dtype=torch.int64, device=x.device) if want_mask else None
-    dgamma, dbeta = torch.zeros_like(gamma), torch.zeros_like(gamma)
+    dgamma, dbeta = (torch.zeros_like(gamma), torch.zeros_like(gamma)) if want_affine else (None, None)   # (None: column sums skipped)
     if x.numel():
         _be().mlp_bwd_ln(x, dout, w1, b1, w2, b2, gamma, dz, h16, dgamma, dbeta, eps, _mlp_ws(w1), mask=mask)
     return (dz, h16, dgamma, dbeta, mask) if want_mask else (dz, h16, dgamma, dbeta)

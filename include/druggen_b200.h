@@ -144,7 +144,8 @@ int dg_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2
  * then the LayerNorm backward of `dout` through z.  Writes dz[R,D] (fp32); optional side outputs (NULL to skip):
  * h_bf16[R,H] (bf16: the operand of the fc2 weight gradient) and relu_mask[R][H/64] (uint64, 8-byte aligned: bit i of
  * word w = (h[w*64+i] > 0) -- all that dg_mlp_bwd_dgrad needs of h, H/8 bytes per row instead of 2H);
- * dgamma[D], dbeta[D] += (zero first).  Same workspace contract as dg_mlp_fwd. */
+ * dgamma[D], dbeta[D] += (zero first; pass NULL for both to skip the column sums -- dgrad-only passes).  Same workspace
+ * contract as dg_mlp_fwd. */
 int dg_mlp_bwd_ln(const float* x, const float* dout, const float* w1, const float* b1, const float* w2,
                   const float* b2, const float* gamma, float* dz, void* h_bf16, void* relu_mask, float* dgamma,
                   float* dbeta, long long R, int D, int H, float eps, void* workspace, long long workspace_bytes,

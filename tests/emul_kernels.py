@@ -198,6 +198,8 @@ class EmulBackend:
                 w |= bits[:, :, i] << i         # (bit 63 wraps into the sign: same 64 bits)
             mask.copy_(w)
         m = self._mm(hq.to(x.dtype), w2.t(), "bf16") + b2
+        if dgamma is None:
+            dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(gamma)
         self.add_ln_bwd(dout, x, m, gamma, dz, dgamma, dbeta, eps)
 
     def mlp_bwd_dgrad(self, dz, h16, w1, w2, dx, dh16, workspace, mask=None):

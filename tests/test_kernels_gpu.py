@@ -246,6 +246,9 @@ def test_fused_mlp_bwd(cuda_dev, R, H):
         assert torch.equal(dx2, dx) and torch.equal(dh2, dh16)
         dx3, dh3 = K.mlp_bwd_dgrad(dz, None, w1, w2, mask=mask, want_dh=False)
         assert dh3 is None and torch.equal(dx3, dx)
+        # dgrad-only passes skip the dgamma / dbeta column sums: same dz
+        dz4, _, g_none, b_none = K.mlp_bwd_ln(x, dout, w1, b1, w2, b2, gamma, want_affine=False)
+        assert g_none is None and b_none is None and torch.equal(dz4, dz)
 
 
 def test_accumulating_stores(cuda_dev):

@@ -42,11 +42,20 @@ _IDX = {n: i for i, n in enumerate(BLOCK_PARAM_NAMES)}
 _HAND_SECOND_ORDER = os.environ.get("DRUGGEN_B200_SECOND_ORDER", "hand") != "autograd"
 
 
-def block_forward(x, y, params: Sequence[torch.Tensor], heads: int, edge_out: bool = True):
+def block_forward(x, y, params: Sequence[torch.Tensor], heads: int, edge_out: bool = True, drop_p: float = 0.0):
     """x:[B,N,D], y:[B,N,N,D] -> (x_out, y_out).  ``edge_out=False`` skips the edge half that has
-    no consumer (the last Discriminator block, models.py:202-207) and returns y_out=None."""
+    no consumer (the last Discriminator block, models.py:202-207) and returns y_out=None.
+    ``drop_p`` > 0: training-mode dropout on the two MLP outputs (layers.py:54, the only dropout the reference block
+    applies -- MHA ignores its ``attention_dropout``, layers.py:69)."""
     p = lambda n: params[_IDX[n]]  # noqa: E731
     d = x.shape[-1]
+
+    def res_mlp(t, pre):      # t + dropout(mlp(t))
+        w = [p(pre + s) for s in (".fc1.weight", ".fc1.bias", ".fc2.weight", ".fc2.bias")]
+        if drop_p > 0.0:
+            return t + torch.nn.functional.dropout(ops.mlp(t, *w, residual=False), drop_p, True)
+        return ops.mlp(t, *w, residual=True)                                 # x3 + mlp(x3): one primitive
+
     c = 1.0 / math.sqrt(d // heads)                                          # layers.py:124
     x1 = ops.add_ln(x, None, p("ln1.weight"), p("ln1.bias"))                 # :185
     q = ops.linear(x1, p("attn.q.weight"), p("attn.q.bias"))                 # :111
@@ -57,26 +66,24 @@ def block_forward(x, y, params: Sequence[torch.Tensor], heads: int, edge_out: bo
     g = ops.SoftmaxAgg.apply(a, v)                                           # :130-134
     x3 = ops.add_ln(x1, ops.linear(g, p("attn.out_n.weight"), p("attn.out_n.bias")),
                     p("ln3.weight"), p("ln3.bias"))                          # :135,187,189
-    x_out = ops.add_ln(ops.mlp(x3, p("mlp.fc1.weight"), p("mlp.fc1.bias"), p("mlp.fc2.weight"), p("mlp.fc2.bias"), residual=True),
-                       None, p("ln5.weight"), p("ln5.bias"))                 # :51-53,191 (x3 + mlp(x3): one primitive)
+    x_out = ops.add_ln(res_mlp(x3, "mlp"), None, p("ln5.weight"), p("ln5.bias"))        # :51-54,191
     if not edge_out:
         return x_out, None
     y1 = ops.linear(a, p("attn.out_e.weight"), p("attn.out_e.bias"))         # :127 (pre-softmax scores)
     y3 = ops.add_ln(y, y1, p("ln4.weight"), p("ln4.bias"))                   # :188,190
-    y_out = ops.add_ln(ops.mlp(y3, p("mlp2.fc1.weight"), p("mlp2.fc1.bias"), p("mlp2.fc2.weight"), p("mlp2.fc2.bias"), residual=True),
-                       None, p("ln6.weight"), p("ln6.bias"))                 # :192
+    y_out = ops.add_ln(res_mlp(y3, "mlp2"), None, p("ln6.weight"), p("ln6.bias"))       # :192
     return x_out, y_out
 
 
 def _scores_fwd(q, k, v, e, c, want_stats=False):
-    if K.attn_fused_available(q.shape[1], q.shape[2]):
+    if K.attn_fused_available(q.shape[1], q.shape[2], q.shape[0]):
         return K.attn_scores_fwd(q, k, v, e, c, want_stats)
     a = K.modulate_fwd(q, k, e, c)
     return (a, K.softmax_agg_fwd(a, v), None) if want_stats else (a, K.softmax_agg_fwd(a, v))
 
 
 def _scores_bwd(dg, da_in, a, q, k, v, e, c, stats=None):
-    if K.attn_fused_available(q.shape[1], q.shape[2]):
+    if K.attn_fused_available(q.shape[1], q.shape[2], q.shape[0]):
         return K.attn_scores_bwd(dg, da_in, q, k, v, e, c, stats)
     da, dv = K.softmax_agg_bwd(dg, a, v, da_accum=da_in)
     dq, dk, de = K.modulate_bwd(da, q, k, e, c)
@@ -243,9 +250,9 @@ def block_backward(x, y, dxo, dyo, params: Sequence[torch.Tensor], heads: int, e
             del dy3, y1, y3
         wgrad("attn.out_e", dz4, a2d)
         # (tensor-core mode: this gradient is added to the softmax term and leaves as the bf16 dE -- bf16 storage halves its trip)
-        da = K.rows_gemm(dz4, p("attn.out_e.weight"), False, out_bf16=h16 and K.attn_fused_available(n, d)).view(b, n, n, d)
+        da = K.rows_gemm(dz4, p("attn.out_e.weight"), False, out_bf16=h16 and K.attn_fused_available(n, d, b)).view(b, n, n, d)
     # ---- attention: softmax-aggregate, modulation, q/k/v/e projections
-    if h16 and K.attn_fused_available(n, d):
+    if h16 and K.attn_fused_available(n, d, b):
         # de is only ever a contraction operand (dWe, dy): bf16 storage in the tensor-core mode
         de, dq, dk, dv = K.attn_scores_bwd(dg, da, q, k, v, e.view(b, n, n, d), c, sm_stats, de_bf16=True,
                                            scores_bf16=chain and K.softmax_scores_bf16())
@@ -363,7 +370,7 @@ def block_backward_backward(x, y, dxo, dyo, ux, uy, params: Sequence[torch.Tenso
     else:
         e2d = K.rows_gemm(y2d, p("attn.e.weight"), True, p("attn.e.bias"))
     e4 = e2d.view(b, n, n, d)
-    fused_scores = K.attn_fused_available(n, d)
+    fused_scores = K.attn_fused_available(n, d, b)
     if fused_scores:
         a4, g, stats = K.attn_scores_fwd(q, k, v, e4, c, want_stats=True)
     else:
@@ -582,8 +589,13 @@ class _ParamGate(Function):
         return grads
 
 
-def encoder_block(x, y, params: Sequence[torch.Tensor], heads: int, edge_out: bool = True):
-    """Checkpointed block used by ``layers.Encoder_Block``."""
+def encoder_block(x, y, params: Sequence[torch.Tensor], heads: int, edge_out: bool = True, drop_p: float = 0.0):
+    """Checkpointed block used by ``layers.Encoder_Block``.  ``drop_p`` > 0 (training-mode dropout, the reference's
+    --dropout / --ddropout): the block runs on the differentiable primitives with torch's dropout on the two MLP outputs --
+    not checkpointed (a recomputation would have to replay the masks) and not fused; the reference default is 0."""
+    if drop_p > 0.0:
+        xo, yo = block_forward(x, y, params, heads, edge_out, drop_p)
+        return xo, yo
     needs_graph = torch.is_grad_enabled() and (
         x.requires_grad or y.requires_grad or any(p.requires_grad for p in params))
     if not needs_graph:

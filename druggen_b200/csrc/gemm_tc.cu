@@ -591,18 +591,20 @@ int rows_gemm_tc(const void* a_, const float* w, int w_is_nk, const float* bias,
   const float* gate = (const float*)gate_;
   float* out = (float*)out_;
   const bool split = prec == DG_PREC_BF16X3;
-  if (!rows_tc_ok(K, N) || (split && (K % 128 || N % 128))) {
+  // shapes wider than one launch takes (mlp_ratio = 4: H = 512) run as 128-wide column slices, like the split-precision mode
+  const bool sliced = split || (!rows_tc_ok(K, N) && K % 128 == 0 && N % 128 == 0 && K >= 128 && N >= 128 && !flags);
+  if ((!sliced && !rows_tc_ok(K, N)) || (split && (K % 128 || N % 128))) {
     if (flags) return fail("dg_rows_gemm: bf16 storage is only available for the tcgen05 shapes (K=%d N=%d)", K, N);
     return rows_gemm_fp32(a, w, w_is_nk, bias, relu, gate, resid, out, R, K, N, s);
   }
   if (!(flags & DG_A_BF16) && (reinterpret_cast<uintptr_t>(a) & 31)) return fail("dg_rows_gemm: a must be 32-byte aligned (256-bit loads)");
-  if (split) {
+  if (sliced) {
     // Split-precision parity mode: three bf16 MMAs per product term on hi / lo operand blocks, fp32 everywhere else.  Twice the
     // shared memory per operand, so a launch takes a 128 x 128 weight block: wider shapes run as column slices -- N slices are
     // independent, K slices accumulate through the resid path (the epilogue must then be linear: no ReLU / gate on K > 128).
     if (flags) return fail("dg_rows_gemm: the bf16x3 mode keeps every tensor fp32 (no bf16 storage flags)");
     const bool nonlinear = relu || gate;
-    if (K > 128 && nonlinear && resid) return fail("dg_rows_gemm(bf16x3): resid together with a ReLU / gate epilogue needs K == 128, got K=%d", K);
+    if (K > 128 && nonlinear && resid) return fail("dg_rows_gemm(sliced): resid together with a ReLU / gate epilogue needs K == 128, got K=%d", K);
     const int ldw = w_is_nk ? K : N;
     for (int n0 = 0; n0 < N; n0 += 128)
       for (int k0 = 0; k0 < K; k0 += 128) {
@@ -613,7 +615,7 @@ int rows_gemm_tc(const void* a_, const float* w, int w_is_nk, const float* bias,
         const float* rs = first ? (resid ? resid + n0 : nullptr) : out + n0;
         const bool epi = nonlinear && last;
         if (rows_gemm_tc_launch(a + k0, ws, w_is_nk, (bias && first) ? bias + n0 : nullptr, epi ? relu : 0, (epi && gate) ? gate + n0 : nullptr,
-                                rs, out + n0, R, 128, 128, (epi && !first) ? tc::kResidPre : 0, K, ldw, N, 1, s))
+                                rs, out + n0, R, 128, 128, (epi && !first) ? tc::kResidPre : 0, K, ldw, N, split ? 1 : 0, s))
           return 1;
       }
     return 0;
@@ -653,19 +655,21 @@ int gemm_tn_tc(const void* a_, const void* b_, float* out, float* colsum_a, long
   const float* a = (const float*)a_;
   const float* b = (const float*)b_;
   const bool split = prec == DG_PREC_BF16X3;
-  const bool ok = M % 128 == 0 && N % 128 == 0 && M >= 128 && N >= 128 && (M / 128) * N <= 512 && N <= 384 && M <= 384;
-  if (!ok) {
+  const bool blocks = M % 128 == 0 && N % 128 == 0 && M >= 128 && N >= 128;
+  const bool ok = blocks && (M / 128) * N <= 512 && N <= 384 && M <= 384;
+  const bool sliced = split || (!ok && blocks && !flags);        // wider than one launch takes (H = 512): 128 x 128 output blocks
+  if (!ok && !sliced) {
     if (flags) return fail("dg_gemm_tn: bf16 storage is only available for the tcgen05 shapes (M=%d N=%d)", M, N);
     return gemm_tn_fp32(a, b, out, colsum_a, R, M, N, s);
   }
   if ((!(flags & DG_A_BF16) && (reinterpret_cast<uintptr_t>(a) & 31)) || (!(flags & DG_OUT_BF16) && (reinterpret_cast<uintptr_t>(b) & 31)))
     return fail("dg_gemm_tn: fp32 operands must be 32-byte aligned (256-bit loads)");
-  if (split) {      // 128 x 128 output blocks per launch (twice the operand bytes per stage); the bias gradient rides on the first N slice
+  if (sliced) {     // 128 x 128 output blocks per launch (twice the operand bytes per stage when split); the bias gradient rides on the first N slice
     if (flags) return fail("dg_gemm_tn: the bf16x3 mode keeps every tensor fp32 (no bf16 storage flags)");
     for (int m0 = 0; m0 < M; m0 += 128)
       for (int n0 = 0; n0 < N; n0 += 128)
         if (gemm_tn_tc_launch(a + m0, b + n0, out + (long long)m0 * N + n0, (colsum_a && n0 == 0) ? colsum_a + m0 : nullptr, R, 128, 128, 0,
-                              M, N, N, 1, s))
+                              M, N, N, split ? 1 : 0, s))
           return 1;
     return 0;
   }

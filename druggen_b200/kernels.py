@@ -286,8 +286,11 @@ def mlp_bwd_dgrad(dz, h16, w1, w2, mask=None, want_dh: bool = True):
 
 
 # ----------------------------------------------------------------------------- fused attention scores (fp32)
-def attn_fused_available(n: int, d: int) -> bool:
-    return d == 128 and n >= 4
+def attn_fused_available(n: int, d: int, b: int = 1) -> bool:
+    """Shapes the fused per-molecule score kernels take (the host-side limits of ``attn_ok`` in csrc/attn_scores.cu): D = 128,
+    N >= 4, the per-CTA dk / dv accumulators (2 N + 16) * 512 B within 220 KB (N <= 212), B within the grid.y limit.
+    Anything else runs the generic modulate / softmax-aggregate kernels (still CUDA, never a CPU path)."""
+    return d == 128 and 4 <= n <= 212 and 0 < b <= 65535
 
 
 def attn_scores_fwd(q, k, v, e, c: float, want_stats: bool = False, store_a: bool = True):
@@ -319,7 +322,9 @@ def attn_scores_bwd(dg, da_in, q, k, v, e, c: float, stats=None, de_bf16: bool =
 # ----------------------------------------------------------------------------- fused tcgen05 edge-attention chain
 def attn_chain_available(b: int, n: int, d: int) -> bool:
     """E-projection -> modulation -> out_e projection -> residual -> LN4 as one tcgen05 kernel (throughput mode)."""
-    return _precision == "bf16" and d == 128 and n >= 4 and b <= 65535 and os.environ.get("DRUGGEN_B200_ATTN_CHAIN", "1") != "0"
+    # (host-side limits of dg_attn_edge_fwd / dg_softmax_agg16_fwd: 32-bit row and element offsets, grid.y)
+    return (_precision == "bf16" and d == 128 and 4 <= n <= 212 and 0 < b <= 65535 and b * n * n < 2 ** 31 and b * n * 128 < 2 ** 31
+            and os.environ.get("DRUGGEN_B200_ATTN_CHAIN", "1") != "0")
 
 
 def softmax_scores_bf16() -> bool:

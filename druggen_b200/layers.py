@@ -20,13 +20,6 @@ from . import ops
 from .block import BLOCK_PARAM_NAMES, encoder_block
 
 
-def _no_train_dropout(module: nn.Module, p: float):
-    if p > 0.0 and module.training:
-        raise NotImplementedError(
-            "druggen_b200: dropout > 0 in training mode is not implemented in the fused encoder "
-            "(the reference default is 0, train.py:419-420); call .eval() or use dropout=0")
-
-
 class MLP(nn.Module):
     """fc2(relu(fc1(x))); output dropout (layers.py:41-54)."""
 
@@ -40,9 +33,8 @@ class MLP(nn.Module):
         self.droprateout = nn.Dropout(dropout)
 
     def forward(self, x):
-        _no_train_dropout(self, self.droprateout.p)
         h = ops.linear(x.contiguous(), self.fc1.weight, self.fc1.bias, relu=True)
-        return ops.linear(h, self.fc2.weight, self.fc2.bias)
+        return self.droprateout(ops.linear(h, self.fc2.weight, self.fc2.bias))      # layers.py:54
 
 
 class MHA(nn.Module):
@@ -100,8 +92,9 @@ class Encoder_Block(nn.Module):
         return out
 
     def forward(self, x, y, _edge_out: bool = True):
-        _no_train_dropout(self, self._drop)
-        return encoder_block(x.contiguous(), y.contiguous(), self._params(), self.attn.heads, _edge_out)
+        # training-mode dropout (reference --dropout / --ddropout, default 0): layers.py:54 on both MLP outputs
+        drop = self._drop if (self.training and self._drop > 0.0) else 0.0
+        return encoder_block(x.contiguous(), y.contiguous(), self._params(), self.attn.heads, _edge_out, drop)
 
 
 class TransformerEncoder(nn.Module):

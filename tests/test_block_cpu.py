@@ -162,12 +162,24 @@ def test_product_refuses_cpu_without_test_backend():
         dg.TransformerEncoder(128, 1, 8, None, 3, 0.0)(torch.zeros(1, 2, 128), torch.zeros(1, 2, 2, 128))
 
 
-def test_training_dropout_raises():
-    enc = dg.TransformerEncoder(128, 1, 8, None, 3, 0.1)
-    with pytest.raises(NotImplementedError):
-        enc(torch.zeros(1, 2, 128), torch.zeros(1, 2, 2, 128))
+def test_training_dropout_runs_and_matches_reference_semantics():
+    """--dropout / --ddropout > 0 in training mode (reference default 0): the block applies torch dropout to the two MLP outputs
+    (layers.py:54), nothing else.  p > 0 in train() differs from eval(), is differentiable, and with p -> 0 equals eval()."""
+    torch.manual_seed(0)
+    enc = dg.TransformerEncoder(32, 2, 4, None, 3, 0.5).double()
+    x = torch.randn(2, 4, 32, dtype=torch.float64, requires_grad=True)
+    y = torch.randn(2, 4, 4, 32, dtype=torch.float64, requires_grad=True)
+    xo_t, yo_t = enc(x, y)                                  # train(): dropout active
+    (xo_t.sum() + yo_t.sum()).backward()
+    assert x.grad is not None and all(p.grad is not None for p in enc.parameters())
     enc.eval()
-    enc(torch.zeros(1, 2, 128), torch.zeros(1, 2, 2, 128))
+    xo_e, yo_e = enc(x, y)
+    assert rel_l2(xo_t, xo_e) > 1e-3                        # the masks did something
+    enc.train()
+    for blk in enc.Encoder_Blocks:
+        blk._drop = 1e-12                                   # keeps every element with probability ~1: the dropout path, no masking
+    xo_p, yo_p = enc(x, y)
+    assert rel_l2(xo_p, xo_e) < 1e-9 and rel_l2(yo_p, yo_e) < 1e-9
 
 
 def test_fused_branch_wiring_in_throughput_mode():

@@ -25,7 +25,8 @@ def _opr(t, tc):
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16", "bf16x3"])
 @pytest.mark.parametrize("R,Kd,Nd", [(1, 128, 128), (257, 128, 384), (1000, 384, 128), (2025 * 3, 128, 128), (77, 32, 32),
-                                     (128 * 148 * 3 + 5, 128, 128), (40000, 128, 384), (40000, 384, 128)])
+                                     (128 * 148 * 3 + 5, 128, 128), (40000, 128, 384), (40000, 384, 128),
+                                     (777, 128, 512), (777, 512, 128)])     # mlp_ratio = 4: 128-wide column slices
 def test_rows_gemm(cuda_dev, prec, R, Kd, Nd):
     a, bias = rnd(cuda_dev, R, Kd), rnd(cuda_dev, Nd, seed=3)
     gate = rnd(cuda_dev, R, Nd, seed=4)
@@ -40,7 +41,7 @@ def test_rows_gemm(cuda_dev, prec, R, Kd, Nd):
             got = K.rows_gemm(a, w, w_is_nk, bias, True, gate)
             want = torch.relu(ref + bias.double()) * (gate > 0)
             assert rel_l2(got, want) < tol
-            if prec == "bf16x3" and Kd > 128:                                    # (K-sliced launches: resid only with a linear epilogue)
+            if (prec == "bf16x3" and Kd > 128) or (prec == "bf16" and Kd > 384):    # (K-sliced launches: resid only with a linear epilogue)
                 got = K.rows_gemm(a, w, w_is_nk, bias, resid=gate)
                 assert rel_l2(got, ref + bias.double() + gate.double()) < tol
                 continue
@@ -50,7 +51,8 @@ def test_rows_gemm(cuda_dev, prec, R, Kd, Nd):
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16", "bf16x3"])
 @pytest.mark.parametrize("R,M,N", [(1, 128, 128), (333, 128, 384), (2025 * 4 + 5, 384, 128), (50, 32, 64),
-                                   (64 * 148 * 5 + 3, 128, 128), (100000, 128, 384), (100000, 384, 128)])
+                                   (64 * 148 * 5 + 3, 128, 128), (100000, 128, 384), (100000, 384, 128),
+                                   (999, 128, 512), (999, 512, 128)])       # mlp_ratio = 4: 128 x 128 output blocks
 def test_gemm_tn(cuda_dev, prec, R, M, N):
     a, b = rnd(cuda_dev, R, M), rnd(cuda_dev, R, N, seed=1)
     with K.precision(prec):

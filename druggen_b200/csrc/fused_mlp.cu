@@ -72,6 +72,7 @@ struct MlpArgs {
   alignas(64) CUtensorMap tm_x;
   alignas(64) CUtensorMap tm_out;
   alignas(64) CUtensorMap tm_z;
+  alignas(64) CUtensorMap tm_e;      // ATTN: e_out
   alignas(64) CUtensorMap tm_dout;   // BWD_A: the upstream gradient rows
   // the bf16 side output [R,H] (h / dh / the scores): box = [128 rows][64 channels] = one operand block, 128-byte swizzle --
   // it leaves straight out of the GEMM2 operand buffer the epilogue has just filled
@@ -455,15 +456,29 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
             const float4 b4 = ld4(bb + i);
             v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
           }
+          // dedicated I/O tile: the previous tile's stores (issued >= 1.5 k cycles ago) have been read by now.  The same wait
+          // makes this warp's operand rows reusable.
+          if (lane == 0 && ti > 0) bulk_wait_read0();
           if (A.e_out != nullptr) {
+            // E (fp32, for the backward) leaves as a TMA tile too: own row into the I/O tile (conflict-free, no transposition),
+            // one elected store per warp -- it used to be four staged 16-column transposes (~4 k cycles per tile)
+            __syncwarp();
+            uint8_t* erow = sIO + (2 * hf) * kBlkBytes + row * 128;
 #pragma unroll
-            for (int g16 = 0; g16 < 4; ++g16) scatter_rows16(A.e_out, wrow0, R, 128, hf * 64 + g16 * 16, stg, lane, v + g16 * 16);
+            for (int j = 0; j < 16; ++j)
+              st4(reinterpret_cast<float*>(erow + (j >> 3) * kBlkBytes + (((j & 7) ^ (row & 7)) << 4)),
+                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&A.tm_e, hf * 64, (int)wrow0, ioslab);
+              tma_store_2d(&A.tm_e, hf * 64 + 32, (int)wrow0, ioslab + kBlkBytes);
+              bulk_commit();
+              bulk_wait_read0();                     // (shared memory read: the residual rows may land on top of it)
+            }
           }
-          // dedicated I/O tile: this tile's residual rows are requested here -- the previous tile's stores (issued >= 1.5 k
-          // cycles ago) have been read by now, and the rows land while the modulation below runs.  The same wait makes this
-          // warp's operand rows reusable.
+          // this tile's residual rows are requested here and land while the modulation below runs
           if (lane == 0) {
-            if (ti > 0) bulk_wait_read0();
             mbar_expect_tx(&io_full[warp], 2 * 32 * 128);
             tma_load_2d(ioslab, &A.tm_x, hf * 64, (int)wrow0, &io_full[warp]);
             tma_load_2d(ioslab + kBlkBytes, &A.tm_x, hf * 64 + 32, (int)wrow0, &io_full[warp]);
@@ -802,6 +817,7 @@ static int launch_chain(const MlpArgs& a, cudaStream_t s) {
   if (make_row_tmap(&b.tm_out, a.out, a.R)) return 1;
   if (kMode == kBwdA && make_row_tmap(&b.tm_dout, a.dout, a.R)) return 1;
   if (kMode == kAttn && a.z_out != nullptr && make_row_tmap(&b.tm_z, a.z_out, a.R)) return 1;
+  if (kMode == kAttn && a.e_out != nullptr && make_row_tmap(&b.tm_e, a.e_out, a.R)) return 1;
   if (a.spill != nullptr && make_spill_tmap(&b.tm_spill, a.spill, a.R, a.HC * 128)) return 1;
   b.prefetch = (opt_get(DG_OPT_L2_PREFETCH) & DG_PF_CHAIN) | ((opt_get(DG_OPT_L2_PREFETCH) & DG_PF_CHAIN_KEEP) ? 2 : 0);
   b.prof = g_chain_prof;

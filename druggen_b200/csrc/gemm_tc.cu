@@ -657,7 +657,7 @@ int gemm_tn_tc(const void* a_, const void* b_, float* out, float* colsum_a, long
   const bool split = prec == DG_PREC_BF16X3;
   const bool blocks = M % 128 == 0 && N % 128 == 0 && M >= 128 && N >= 128;
   const bool ok = blocks && (M / 128) * N <= 512 && N <= 384 && M <= 384;
-  const bool sliced = split || (!ok && blocks && !flags);        // wider than one launch takes (H = 512): 128 x 128 output blocks
+  const bool sliced = blocks && (split || (!ok && !flags));      // wider than one launch takes (H = 512): 128 x 128 output blocks
   if (!ok && !sliced) {
     if (flags) return fail("dg_gemm_tn: bf16 storage is only available for the tcgen05 shapes (M=%d N=%d)", M, N);
     return gemm_tn_fp32(a, b, out, colsum_a, R, M, N, s);

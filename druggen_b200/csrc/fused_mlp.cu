@@ -17,11 +17,12 @@
 // The final epilogue's rows come in (residual / upstream gradient) and go out as 128-byte-swizzled TMA boxes that each
 // epilogue warp loads, rewrites in place and stores for its own 32 rows.
 //
-// Persistent CTA per SM, 448 threads, warp-specialised:
-//   warps 0-7   epilogue : thread = half a row (TMEM lane quarter w&3, column half w>>2)
-//   warps 8-11  loader   : fp32 LDG.E.256 -> bf16 -> swizzled operand blocks (double-buffered tiles; single in ATTN)
-//   warp  12    MMA      : one thread issues tcgen05.mma; GEMM2 of tile t interleaved with GEMM1 of t+1
-//   warp  13    W loader : one thread streams pre-packed bf16 weight stages (32 KB) with
+// Persistent CTA per SM, 704 threads, warp-specialised:
+//   warps 0-15  epilogue : thread = a quarter of a row (TMEM lane quarter w&3, 32-column part w>>2); one TMA box
+//                          [32 rows][32 channels] of the I/O tile per warp, bf16 side outputs stored per warp PAIR
+//   warps 16-19 loader   : fp32 LDG.E.256 -> bf16 -> swizzled operand blocks (x tile single-buffered)
+//   warp  20    MMA      : one thread issues tcgen05.mma; GEMM1 of tile t+1 issued right after the last GEMM2 of tile t
+//   warp  21    W loader : one thread streams pre-packed bf16 weight stages (32 KB) with
 //                          cp.async.bulk into a 2-stage ring (weights live in L2: 192 KB per net; ATTN: both stages resident)
 // TMEM: columns [0,384) three GEMM1 chunk accumulators, [384,512) the GEMM2 accumulator.
 #include <cuda.h>
@@ -31,12 +32,23 @@
 namespace dg {
 namespace tc {
 
-constexpr int kMlpThreads = 448;
+// Epilogue geometry: 16 warps = TMEM lane quarter (w & 3: rows 32q..32q+31 of the tile) x column part (w >> 2: 32 of the 128
+// columns).  A thread = (row, 32 columns): half the dependent work per phase of the former 8-warp / 64-column layout, whose
+// serial per-tile epilogue (not the tensor pipe, not HBM) bounded all four kernels (profiles/r02a_chain_phases.jsonl).
+constexpr int kEpiWarps = 16;
+constexpr int kParts = kEpiWarps / 4;            // column parts of a row
+constexpr int kCW = 128 / kParts;                // columns per epilogue thread = one TMA box [32 rows][32 channels] per warp
+constexpr int kEpiThreads = kEpiWarps * 32;      // 512
+constexpr int kLdWarp0 = kEpiWarps;              // loader warps 16..19
+constexpr int kMmaWarp = kEpiWarps + 4;          // 20
+constexpr int kWWarp = kEpiWarps + 5;            // 21
+constexpr int kMlpThreads = (kEpiWarps + 6) * 32;   // 704
+static_assert(kCW == 32, "the epilogue below is written for 32 columns per thread");
 constexpr int kWStage = 2 * kBlkBytes;   // one packed weight stage: [2 kb][128 rows][128 B] = 32 KB
-constexpr int kStgPitch = 16;            // epilogue transpose: 32 rows x 16 words per warp, XOR-swizzled (no padding)
-// word offset of the 4-float chunk c4 of row r in a staging tile: conflict-free both for the coalesced side (8 lanes = 2
-// rows x 4 chunks) and for the thread-per-row side (8 lanes = 8 consecutive rows, same chunk)
-__device__ __forceinline__ int stg_off(int r, int c4) { return r * kStgPitch + ((c4 ^ ((r >> 1) & 3)) << 2); }
+constexpr int kStgPitch = 8;             // epilogue transpose: 32 rows x 8 words per warp, XOR-swizzled (no padding)
+// word offset of the 4-float chunk c2 (0..1) of row r in a staging tile: conflict-free both for the coalesced side (8 lanes = 4
+// rows x 2 chunks) and for the thread-per-row side (8 lanes = 8 consecutive rows, same chunk)
+__device__ __forceinline__ int stg_off(int r, int c2) { return r * kStgPitch + ((c2 ^ ((r >> 2) & 1)) << 2); }
 
 enum { kFwd = 0, kBwdA = 1, kBwdB = 2, kAttn = 3 };
 
@@ -123,74 +135,66 @@ __global__ void mlp_pack_weights_kernel(const float* __restrict__ w1, const floa
 }
 
 struct MlpSmem {
-  static constexpr int xb = 0;                          // 2 x 32 KB   (ATTN cuts these 192 KB differently: see kDedIO)
-  static constexpr int hb = xb + 2 * kWStage;           // 2 x 32 KB
-  static constexpr int wb = hb + 2 * kWStage;           // 2 x 32 KB
-  static constexpr int stage = wb + 2 * kWStage;        // 8 warps x 32 x kStgPitch words
-  static constexpr int stats = stage + 8 * 32 * kStgPitch * 4;   // [2 parity][2 halves][128 rows] float2, twice (BWD_A)
-  static constexpr int vec = stats + 2 * 2 * 2 * 128 * 8;        // b1[384] b2[128] gamma[128] beta[128]
+  // tile buffers, 32 KB units: x (single-buffered) | operand blocks 2 x 32 KB (ATTN: 1) | weight stages 2 x 32 KB |
+  // ATTN only: a dedicated 64 KB I/O tile (the other modes stage their I/O tile in the two operand buffers)
+  static constexpr int tiles = 0;
+  static constexpr int stage = 6 * kWStage;                          // 16 warps x 32 x kStgPitch words
+  static constexpr int stats = stage + kEpiWarps * 32 * kStgPitch * 4;   // 2 x [4 parts][128 rows] float2 (see the epilogue)
+  static constexpr int vec = stats + 2 * kParts * 128 * 8;           // b1[384] b2[128] gamma[128] beta[128]
   static constexpr int bars = vec + (384 + 3 * 128) * 4;
-  static constexpr int prof = bars + 256;                        // 4 roles x 16 counters (debug)
+  static constexpr int prof = bars + 512;                            // 4 roles x 16 counters (debug)
   static constexpr int total = prof + 4 * 16 * 8;
 };
 
-// warp-cooperative transposes through a [32][kStgPitch] staging tile, 16 words (columns) at a time:
-// global rows <-> "thread = row" registers.  Global accesses are 64 B contiguous per row (pitch in words).
+// warp-cooperative transposes through a [32][kStgPitch] staging tile, 8 words (columns) at a time:
+// global rows <-> "thread = row" registers.  Global accesses are 32 B contiguous per row (pitch in words); the coalesced side
+// is lane = (row it * 16 + (lane >> 1), 16-byte half lane & 1).
 __device__ __forceinline__ void gather_issue(const float* __restrict__ src, long long row_base, long long R, int pitch, int col,
-                                             int ngroups, int lane, float4* xq) {
+                                             int nrounds, int lane, float4* xq) {
 #pragma unroll
-  for (int g16 = 0; g16 < 4; ++g16)
-    if (g16 < ngroups) {
+  for (int g = 0; g < 4; ++g)
+    if (g < nrounds) {
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int r = it * 8 + (lane >> 2);
-        xq[g16 * 4 + it] = (row_base + r < R) ? ld4(src + (row_base + r) * pitch + col + g16 * 16 + (lane & 3) * 4)
-                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int it = 0; it < 2; ++it) {
+        const int r = it * 16 + (lane >> 1);
+        xq[g * 2 + it] = (row_base + r < R) ? ld4(src + (row_base + r) * pitch + col + g * 8 + (lane & 1) * 4)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
 }
-__device__ __forceinline__ void gather_finish(const float4* xq, int ngroups, float* stg, int lane, float* dst) {
+__device__ __forceinline__ void gather_finish(const float4* xq, int nrounds, float* stg, int lane, float* dst) {
 #pragma unroll
-  for (int g16 = 0; g16 < 4; ++g16)
-    if (g16 < ngroups) {
+  for (int g = 0; g < 4; ++g)
+    if (g < nrounds) {
 #pragma unroll
-      for (int it = 0; it < 4; ++it) st4(stg + stg_off(it * 8 + (lane >> 2), lane & 3), xq[g16 * 4 + it]);
+      for (int it = 0; it < 2; ++it) st4(stg + stg_off(it * 16 + (lane >> 1), lane & 1), xq[g * 2 + it]);
       __syncwarp();
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 2; ++i) {
         float4 v = ld4(stg + stg_off(lane, i));
-        dst[g16 * 16 + 4 * i] = v.x; dst[g16 * 16 + 4 * i + 1] = v.y; dst[g16 * 16 + 4 * i + 2] = v.z; dst[g16 * 16 + 4 * i + 3] = v.w;
+        dst[g * 8 + 4 * i] = v.x; dst[g * 8 + 4 * i + 1] = v.y; dst[g * 8 + 4 * i + 2] = v.z; dst[g * 8 + 4 * i + 3] = v.w;
       }
       __syncwarp();
     }
-}
-__device__ __forceinline__ void scatter_rows16(float* __restrict__ dst, long long row_base, long long R, int pitch, int col,
-                                               float* stg, int lane, const float* src16) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) st4(stg + stg_off(lane, i), make_float4(src16[4 * i], src16[4 * i + 1], src16[4 * i + 2], src16[4 * i + 3]));
-  __syncwarp();
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int r = it * 8 + (lane >> 2);
-    if (row_base + r < R) st4(dst + (row_base + r) * pitch + col + (lane & 3) * 4, ld4(stg + stg_off(r, lane & 3)));
-  }
-  __syncwarp();
 }
 
+// 22 warps = 6 on two of the SM's four register-file partitions (16 384 registers each): 80 registers per thread is the ceiling
+// (6 x 32 x 88 does not fit -- "too many resources requested"), which ptxas picks under this launch bound.
 template <int kMode>
 __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __grid_constant__ MlpArgs A) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment as an OFFSET from the __shared__ array: a pointer rebuilt from an integer loses its address
   // space and every access through it compiles to generic LD/ST (LSU long-scoreboard path) instead of LDS/STS
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  // ATTN has ONE hidden chunk and two weight stages in all: its 192 KB of tile buffers are cut differently -- x and the
-  // operand block single-buffered, both weight stages resident, and a DEDICATED 64 KB I/O tile, so the residual rows of a
-  // tile are requested a whole chunk phase before they are needed (in the other modes the I/O tile aliases the two operand
-  // buffers and can only be requested after the tile's last GEMM2: ~3 k cycles of exposed TMA latency per tile)
+  // ATTN has ONE hidden chunk and two weight stages in all: both weight stages stay resident, the operand block is
+  // single-buffered, and the 64 KB I/O tile is DEDICATED, so the residual rows of a tile are requested a whole chunk phase
+  // before they are needed (in the other modes the I/O tile aliases the two operand buffers and can only be requested after
+  // the tile's last GEMM2: ~2.5 k cycles of exposed TMA latency per tile).  The x tile is single-buffered in every mode: the
+  // loader has a whole tile period between GEMM1 of tile t and GEMM1 of tile t+1 (issued after tile t's last GEMM2).
   constexpr bool kDedIO = kMode == kAttn;
-  uint8_t* sX = smem + MlpSmem::xb;
-  uint8_t* sH = smem + (kDedIO ? kWStage : MlpSmem::hb);
-  uint8_t* sW = smem + (kDedIO ? 2 * kWStage : MlpSmem::wb);
+  uint8_t* sX = smem;
+  uint8_t* sH = smem + kWStage;
+  uint8_t* sW = smem + (kDedIO ? 2 : 3) * kWStage;
   uint8_t* sIO = kDedIO ? smem + 4 * kWStage : sH;
   float* sStage = reinterpret_cast<float*>(smem + MlpSmem::stage);
   float2* sStats = reinterpret_cast<float2*>(smem + MlpSmem::stats);
@@ -199,10 +203,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
   float* sG = sB2 + 128;
   float* sBe = sG + 128;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MlpSmem::bars);
-  uint64_t *x_full = bars, *x_empty = bars + 2, *w_full = bars + 4, *w_empty = bars + 6, *hacc_full = bars + 8,
-           *hacc_empty = bars + 11, *hb_full = bars + 14, *hb_empty = bars + 16, *z_full = bars + 18, *z_empty = bars + 19,
-           *io_full = bars + 20 /* [8]: one per epilogue warp */, *sp_done = bars + 28;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
+  uint64_t *x_full = bars, *x_empty = bars + 1, *w_full = bars + 2, *w_empty = bars + 4, *hacc_full = bars + 6,
+           *hacc_empty = bars + 9, *hb_full = bars + 12, *hb_empty = bars + 14, *z_full = bars + 16, *z_empty = bars + 17,
+           *sp_done = bars + 18, *io_full = bars + 19 /* [kEpiWarps]: one per epilogue warp */;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19 + kEpiWarps);
   long long* sProf = reinterpret_cast<long long*>(smem + MlpSmem::prof);
 
   const float* __restrict__ x = A.x;
@@ -216,21 +220,22 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
   const bool want_affine = kMode == kBwdA && A.dgamma != nullptr;      // BWD_A: the LayerNorm's dgamma / dbeta are wanted
 
   if (tid == 0) {
+    mbar_init(x_full, 128); mbar_init(x_empty, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&x_full[i], 128); mbar_init(&x_empty[i], 1);
       mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1);
-      mbar_init(&hb_full[i], 8); mbar_init(&hb_empty[i], 1);
+      mbar_init(&hb_full[i], kEpiWarps); mbar_init(&hb_empty[i], 1);
     }
-    for (int i = 0; i < 3; ++i) { mbar_init(&hacc_full[i], 1); mbar_init(&hacc_empty[i], 8); }
-    mbar_init(z_full, 1); mbar_init(z_empty, 8);     // epilogue barriers: one elected arrival per warp
-    for (int i = 0; i < 8; ++i) mbar_init(&io_full[i], 1);
-    mbar_init(sp_done, 8);
+    for (int i = 0; i < 3; ++i) { mbar_init(&hacc_full[i], 1); mbar_init(&hacc_empty[i], kEpiWarps); }
+    mbar_init(z_full, 1); mbar_init(z_empty, kEpiWarps);     // epilogue barriers: one elected arrival per warp
+    for (int i = 0; i < kEpiWarps; ++i) mbar_init(&io_full[i], 1);
+    mbar_init(sp_done, kEpiWarps);
     fence_barrier_init();
   }
-  if (warp == 12) tmem_alloc(tmem_slot, 512);
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, 512);
   if (tid < 64) sProf[tid] = 0;
-  const int prof_slot = warp == 0 ? 0 : warp == 4 ? 1 : warp == 8 ? 2 : 3;   // (only those warps and the MMA warp record)
-  const bool prof_on = A.prof != nullptr && lane == 0 && (warp == 0 || warp == 4 || warp == 8 || warp == 12);
+  // (only epilogue warps 0 and 4 -- column parts 0 and 1 of lane quarter 0 --, the first loader warp and the MMA warp record)
+  const int prof_slot = warp == 0 ? 0 : warp == 4 ? 1 : warp == kLdWarp0 ? 2 : 3;
+  const bool prof_on = A.prof != nullptr && lane == 0 && (warp == 0 || warp == 4 || warp == kLdWarp0 || warp == kMmaWarp);
   long long t_prev = clock64();
   if (kMode != kBwdB) {
     for (int i = tid; i < H; i += kMlpThreads) sB1[i] = A.b1[i];
@@ -245,12 +250,11 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 8 && warp < 12) {
+  if (warp >= kLdWarp0 && warp < kLdWarp0 + 4) {
     // ------------------------------------------------------------------ input-tile loader
-    const int lt = tid - 256;
+    const int lt = tid - kEpiThreads;
     for (long long ti = 0; ti < my_tiles; ++ti) {
       const long long row0 = (blockIdx.x + ti * gridDim.x) * 128;
-      const int xs = kDedIO ? 0 : (ti & 1);
       if ((A.prefetch & 1) && (lt == 0 || lt == 32)) {
         // TMA-engine L2 prefetch of whole (contiguous) row tiles ahead of the register-staged loads:
         // thread 0: the input tiles ti+1, ti+2;  thread 32: what the epilogue gathers for tile ti+1 (dout / bf16 gate)
@@ -260,15 +264,15 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
           const long long prows = R - prow0 < 128 ? R - prow0 : 128;
           if (lt == 0) bulk_prefetch_l2(x + prow0 * 128, prows * 512);
           else if (kMode == kBwdA) bulk_prefetch_l2(A.dout + prow0 * 128, prows * 512);
-          else if (kMode == kBwdB) bulk_prefetch_l2(A.gate + prow0 * H, prows * H * 2);
+          else if (kMode == kBwdB && !use_mask) bulk_prefetch_l2(A.gate + prow0 * H, prows * H * 2);
         }
       }
       DG_PROF(0)
-      mbar_wait(&x_empty[xs], (kDedIO ? (ti & 1) : ((ti >> 1) & 1)) ^ 1);
+      mbar_wait(x_empty, (ti & 1) ^ 1);
       DG_PROF(1)
 #pragma unroll 1
       for (int kb = 0; kb < 2; ++kb) {
-        uint8_t* blk = sX + xs * kWStage + kb * kBlkBytes;
+        uint8_t* blk = sX + kb * kBlkBytes;
         float4 v[16];
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
@@ -287,10 +291,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
         }
       }
       fence_async_smem();
-      mbar_arrive(&x_full[xs]);
+      mbar_arrive(x_full);
       DG_PROF(2)
     }
-  } else if (warp == 13) {
+  } else if (warp == kWWarp) {
     // ------------------------------------------------------------------ weight streamer (one thread)
     if (lane == 0 && my_tiles > 0) {
       uint32_t wcount = 0;
@@ -303,19 +307,15 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
       };
       for (int c = 0; c < HC; ++c) push(c);                         // GEMM1 of the first tile
       if (kDedIO) push(1);                                          // ATTN: stage 1 (out_e) into slot 1 -- both stay resident
-      // consumption order per tile: GEMM2(0), GEMM1'(0), GEMM2(1..), GEMM1'(1..)  ('= next tile).  With the GEMM2 stages of the
-      // later chunks AHEAD of the next tile's GEMM1 stages, the tile's last GEMM2 finds its weights resident a chunk early
-      // instead of waiting ~2-3 k cycles of TMA latency on the critical path to z_full.
+      // consumption order per tile: GEMM2(0..HC-1), then GEMM1 of the next tile (0..HC-1)
       for (long long ti = 0; !kDedIO && ti < my_tiles; ++ti) {
-        push(HC);                                                   // GEMM2 chunk 0 of tile ti
-        if (ti + 1 < my_tiles) push(0);                             // GEMM1 chunk 0 of tile ti+1
-        for (int c = 1; c < HC; ++c) push(HC + c);
+        for (int c = 0; c < HC; ++c) push(HC + c);
         if (ti + 1 < my_tiles)
-          for (int c = 1; c < HC; ++c) push(c);
+          for (int c = 0; c < HC; ++c) push(c);
       }
     }
     __syncwarp();
-  } else if (warp == 12) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0 && my_tiles > 0) {
       const uint32_t idesc = make_idesc(128, 128, 0, 0);
@@ -337,16 +337,15 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
         ++wcount;
       };
       auto gemm1 = [&](long long ti, int c) {
-        const int xs = kDedIO ? 0 : (ti & 1);
         DG_PROF(0)
-        if (c == 0) { mbar_wait(&x_full[xs], kDedIO ? (ti & 1) : ((ti >> 1) & 1)); tc_fence_after(); }
+        if (c == 0) { mbar_wait(x_full, ti & 1); tc_fence_after(); }
         DG_PROF(2)
         mbar_wait(&hacc_empty[c], (ti & 1) ^ 1);
         DG_PROF(3)
         tc_fence_after();
-        mma_chunk(smem_u32(sX + xs * kWStage), c * 128, true);
+        mma_chunk(smem_u32(sX), c * 128, true);
         umma_commit(&hacc_full[c]);
-        if (c == HC - 1) umma_commit(&x_empty[xs]);
+        if (c == HC - 1) umma_commit(x_empty);
       };
       for (int c = 0; c < HC; ++c) gemm1(0, c);
       for (long long ti = 0; ti < my_tiles; ++ti) {
@@ -362,56 +361,63 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
           umma_commit(&hb_empty[hs]);
           ++hcount;
           if (c == HC - 1) umma_commit(z_full);      // before the next tile's GEMM1 is even issued: the final epilogue does not wait for it
-          if (c == 0 && ti + 1 < my_tiles) gemm1(ti + 1, 0);
         }
+        // GEMM1 of the next tile runs while the epilogue warps are in this tile's final epilogue
         if (ti + 1 < my_tiles)
-          for (int c = 1; c < HC; ++c) gemm1(ti + 1, c);
+          for (int c = 0; c < HC; ++c) gemm1(ti + 1, c);
       }
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 0-7)
-    // warp w: TMEM lane quarter q = w & 3 (rows 32q..32q+31 of the tile), column half hf = w >> 2
-    const int q = warp & 3, hf = warp >> 2;
+    // ------------------------------------------------------------------ epilogue (warps 0-15)
+    // warp w: TMEM lane quarter q = w & 3 (rows 32q..32q+31 of the tile), column part cp = w >> 2 (columns 32cp..32cp+31)
+    const int q = warp & 3, cp = warp >> 2;
     float* stg = sStage + warp * 32 * kStgPitch;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int row = q * 32 + lane;
+    // the bf16 side output is stored per operand block = 64 columns = TWO warps' rows: the pair (cp even, cp odd) of a lane
+    // quarter meets at its own named barrier and the even one issues the TMA store
+    const bool issuer = (cp & 1) == 0;
+    const int pair_bar_id = 2 + q + 4 * (cp >> 1);
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair_bar_id) : "memory"); };
     uint32_t hcount = 0;
-    // BWD_A column sums, kept per lane over all tiles: dgamma -- lane = (4-column chunk lane&3, row group lane>>2) of each
-    // 16-column group; dbeta -- lane = (4-column chunk lane&15 of this warp's 64 columns, row half lane>>4)
+    // BWD_A column sums, kept per lane over all tiles: dgamma -- lane = (4-column chunk lane&1, rows lane>>1 and 16 + lane>>1) of
+    // each 8-column round; dbeta -- lane = (4-column chunk lane&7 of this warp's 32 columns, row quarter lane>>3)
     float4 acc_g[4], acc_b = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc_g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (long long ti = 0; ti < my_tiles; ++ti) {
       const long long row0 = (blockIdx.x + ti * gridDim.x) * 128;
       const long long wrow0 = row0 + q * 32;                          // first global row of this warp
-      uint8_t* ioslab = sIO + (2 * hf) * kBlkBytes + q * 32 * 128;    // this warp's rows of its two boxes of the I/O tile
-      if (kMode == kBwdA && wrow0 + lane < R) {                       // the LayerNorm-backward gathers of dout come from L2
-        const float* pd = A.dout + (wrow0 + lane) * 128 + hf * 64;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(pd));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(pd + 32));
-      }
+      uint8_t* iobox = sIO + cp * kBlkBytes + q * 32 * 128;           // this warp's box [32 rows][32 channels] of the I/O tile
+      uint8_t* iorow = sIO + cp * kBlkBytes + row * 128;              // this thread's row of it
+      auto io_chunk = [&](int j) -> float* {                          // 16-byte chunk j (4 channels) of this thread's 32 columns
+        return reinterpret_cast<float*>(iorow + ((j ^ (row & 7)) << 4));
+      };
+      if (kMode == kBwdA && wrow0 + lane < R)                         // the LayerNorm-backward's dout rows come from L2
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(A.dout + (wrow0 + lane) * 128 + cp * kCW));
       for (int c = 0; c < HC; ++c) {
-        // bf16 [R,H] side tensors viewed as 32-bit words: pitch H/2, this warp-half's 64 columns = 32 words
-        const int wcol = (c * 128 + hf * 64) >> 1;
-        float4 gq[8];
-        unsigned long long mk = 0ull;                 // BWD_B: this row-half's 64 ReLU sign bits of chunk c (one 8-byte load)
+        float4 gq[4];
+        uint32_t mk = 0u;                              // BWD_B: this thread's 32 ReLU sign bits of chunk c (one 4-byte load)
         if (kMode == kBwdB) {
-          if (use_mask) { if (wrow0 + lane < R) mk = __ldg(A.mask_in + (wrow0 + lane) * (2 * HC) + c * 2 + hf); }
-          else gather_issue(reinterpret_cast<const float*>(A.gate), wrow0, R, H >> 1, wcol, 2, lane, gq);
+          if (use_mask) {
+            if (wrow0 + lane < R) mk = __ldg(reinterpret_cast<const uint32_t*>(A.mask_in) + (wrow0 + lane) * (4 * HC) + c * 4 + cp);
+          } else {   // bf16 [R,H] viewed as 32-bit words: pitch H/2, this thread's 32 columns = 16 words
+            gather_issue(reinterpret_cast<const float*>(A.gate), wrow0, R, H >> 1, (c * 128 + cp * kCW) >> 1, 2, lane, gq);
+          }
         }
-        // ATTN: q / k rows of the 4 staged rows this lane serves (row r = ((b N + i) N + j) -> q row b N + i, k row b N + j),
-        // and the first 16-channel group of both, requested before the accumulator is waited for
-        unsigned qoff[4], koff[4];                     // element offsets (B N 128 < 2^31)
-        float4 qc[4], kc[4];
+        // ATTN: q / k rows of the 2 staged rows this lane serves (row r = ((b N + i) N + j) -> q row b N + i, k row b N + j),
+        // and the first 8-channel group of both, requested before the accumulator is waited for
+        unsigned qoff[2], koff[2];                     // element offsets (B N 128 < 2^31)
+        float4 qc[2], kc[2];
         if (kMode == kAttn) {
 #pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            long long r = wrow0 + it * 8 + (lane >> 2);
+          for (int it = 0; it < 2; ++it) {
+            long long r = wrow0 + it * 16 + (lane >> 1);
             if (r >= R) r = R - 1;
             const unsigned n = (unsigned)A.natoms, bi = (unsigned)r / n, jj = (unsigned)r - bi * n;
-            qoff[it] = bi * 128u + hf * 64 + (lane & 3) * 4;
-            koff[it] = ((bi / n) * n + jj) * 128u + hf * 64 + (lane & 3) * 4;
+            qoff[it] = bi * 128u + cp * kCW + (lane & 1) * 4;
+            koff[it] = ((bi / n) * n + jj) * 128u + cp * kCW + (lane & 1) * 4;
             qc[it] = __ldg(reinterpret_cast<const float4*>(A.q + qoff[it]));
             kc[it] = __ldg(reinterpret_cast<const float4*>(A.k + koff[it]));
           }
@@ -423,203 +429,185 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
         mbar_wait(&hb_empty[hs], (kDedIO ? (hcount & 1) : ((hcount >> 1) & 1)) ^ 1);
         DG_PROF(2)
         tc_fence_after();
-        uint8_t* hblk = sH + hs * kWStage + hf * kBlkBytes;          // this half's 64 hidden columns = one operand block
-        float v[64];
-        tmem_ld32(tmem_base + lane_base + c * 128 + hf * 64, v);
-        tmem_ld32(tmem_base + lane_base + c * 128 + hf * 64 + 32, v + 32);
+        uint8_t* hblk = sH + hs * kWStage + (cp >> 1) * kBlkBytes;   // the operand block (64 hidden columns) this warp's 32 belong to
+        float v[32];
+        tmem_ld32(tmem_base + lane_base + c * 128 + cp * kCW, v);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&hacc_empty[c]);
         DG_PROF(3)
         if (kMode == kBwdB && use_mask) {
-          const uint32_t mlo = (uint32_t)mk, mhi = (uint32_t)(mk >> 32);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            v[i] = (mlo >> i) & 1u ? v[i] : 0.f;
-            v[32 + i] = (mhi >> i) & 1u ? v[32 + i] : 0.f;
-          }
+          for (int i = 0; i < 32; ++i) v[i] = (mk >> i) & 1u ? v[i] : 0.f;
         } else if (kMode == kBwdB) {
-          float gw[32];                                              // 64 bf16 sign masks of this row
+          float gw[16];                                              // 32 bf16 sign masks of this row
           gather_finish(gq, 2, stg, lane, gw);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
+          for (int i = 0; i < 16; ++i) {
             const uint32_t bits = __float_as_uint(gw[i]);
             v[2 * i] = (short)(bits & 0xFFFF) > 0 ? v[2 * i] : 0.f;
             v[2 * i + 1] = (short)(bits >> 16) > 0 ? v[2 * i + 1] : 0.f;
           }
         } else if (kMode == kAttn) {
           // E = acc + be;  A = ((q_i k_j) c) (E + 1) E   (layers.py:116,123-125);  this thread's row r = ((b N + i) N + j)
-          const float* bb = sB1 + hf * 64;
+          const float* bb = sB1 + cp * kCW;
 #pragma unroll
-          for (int i = 0; i < 64; i += 4) {
+          for (int i = 0; i < 32; i += 4) {
             const float4 b4 = ld4(bb + i);
             v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
           }
           // dedicated I/O tile: the previous tile's stores (issued >= 1.5 k cycles ago) have been read by now.  The same wait
-          // makes this warp's operand rows reusable.
+          // (the issuer's, then the pair barrier) makes the pair's operand rows reusable.
           if (lane == 0 && ti > 0) bulk_wait_read0();
+          if (spill) pair_sync(); else __syncwarp();
           if (A.e_out != nullptr) {
             // E (fp32, for the backward) leaves as a TMA tile too: own row into the I/O tile (conflict-free, no transposition),
-            // one elected store per warp -- it used to be four staged 16-column transposes (~4 k cycles per tile)
-            __syncwarp();
-            uint8_t* erow = sIO + (2 * hf) * kBlkBytes + row * 128;
+            // one elected store per warp
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              st4(reinterpret_cast<float*>(erow + (j >> 3) * kBlkBytes + (((j & 7) ^ (row & 7)) << 4)),
-                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+            for (int j = 0; j < 8; ++j) st4(io_chunk(j), make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
             fence_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(&A.tm_e, hf * 64, (int)wrow0, ioslab);
-              tma_store_2d(&A.tm_e, hf * 64 + 32, (int)wrow0, ioslab + kBlkBytes);
+              tma_store_2d(&A.tm_e, cp * kCW, (int)wrow0, iobox);
               bulk_commit();
               bulk_wait_read0();                     // (shared memory read: the residual rows may land on top of it)
             }
           }
           // this tile's residual rows are requested here and land while the modulation below runs
           if (lane == 0) {
-            mbar_expect_tx(&io_full[warp], 2 * 32 * 128);
-            tma_load_2d(ioslab, &A.tm_x, hf * 64, (int)wrow0, &io_full[warp]);
-            tma_load_2d(ioslab + kBlkBytes, &A.tm_x, hf * 64 + 32, (int)wrow0, &io_full[warp]);
+            mbar_expect_tx(&io_full[warp], 32 * 128);
+            tma_load_2d(iobox, &A.tm_x, cp * kCW, (int)wrow0, &io_full[warp]);
           }
           __syncwarp();
-          // S = c q_i k_j is formed on the COALESCED side of the staging transpose (lane = 16 bytes of one of 8 rows: the
-          // k rows of consecutive j are consecutive in memory, the q row is shared by ~N rows), 16 channels at a time, the
+          // S = c q_i k_j is formed on the COALESCED side of the staging transpose (lane = 16 bytes of one of 16 rows: the
+          // k rows of consecutive j are consecutive in memory, the q row is shared by ~N rows), 8 channels at a time, the
           // next group's loads in flight; a thread-per-row read of k would touch 32 different lines per instruction
           const float cs = A.cscale;
 #pragma unroll
-          for (int g16 = 0; g16 < 4; ++g16) {
-            float4 qn[4], kn[4];
-            if (g16 < 3) {
+          for (int g = 0; g < 4; ++g) {
+            float4 qn[2], kn[2];
+            if (g < 3) {
 #pragma unroll
-              for (int it = 0; it < 4; ++it) {
-                qn[it] = __ldg(reinterpret_cast<const float4*>(A.q + qoff[it] + (g16 + 1) * 16));
-                kn[it] = __ldg(reinterpret_cast<const float4*>(A.k + koff[it] + (g16 + 1) * 16));
+              for (int it = 0; it < 2; ++it) {
+                qn[it] = __ldg(reinterpret_cast<const float4*>(A.q + qoff[it] + (g + 1) * 8));
+                kn[it] = __ldg(reinterpret_cast<const float4*>(A.k + koff[it] + (g + 1) * 8));
               }
             }
 #pragma unroll
-            for (int it = 0; it < 4; ++it)
-              st4(stg + stg_off(it * 8 + (lane >> 2), lane & 3), make_float4(qc[it].x * kc[it].x * cs, qc[it].y * kc[it].y * cs,
-                                                                            qc[it].z * kc[it].z * cs, qc[it].w * kc[it].w * cs));
+            for (int it = 0; it < 2; ++it)
+              st4(stg + stg_off(it * 16 + (lane >> 1), lane & 1), make_float4(qc[it].x * kc[it].x * cs, qc[it].y * kc[it].y * cs,
+                                                                             qc[it].z * kc[it].z * cs, qc[it].w * kc[it].w * cs));
             __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < 2; ++i) {
               const float4 s4 = ld4(stg + stg_off(lane, i));
-              float* vv = v + g16 * 16 + 4 * i;
+              float* vv = v + g * 8 + 4 * i;
               vv[0] = s4.x * fmaf(vv[0], vv[0], vv[0]); vv[1] = s4.y * fmaf(vv[1], vv[1], vv[1]);
               vv[2] = s4.z * fmaf(vv[2], vv[2], vv[2]); vv[3] = s4.w * fmaf(vv[3], vv[3], vv[3]);
             }
             __syncwarp();
-            if (g16 < 3) {
+            if (g < 3) {
 #pragma unroll
-              for (int it = 0; it < 4; ++it) { qc[it] = qn[it]; kc[it] = kn[it]; }
+              for (int it = 0; it < 2; ++it) { qc[it] = qn[it]; kc[it] = kn[it]; }
             }
           }
         } else {
-          const float* bb = sB1 + c * 128 + hf * 64;
+          const float* bb = sB1 + c * 128 + cp * kCW;
 #pragma unroll
-          for (int i = 0; i < 64; i += 4) {
+          for (int i = 0; i < 32; i += 4) {
             const float4 b4 = ld4(bb + i);
             v[i] = fmaxf(v[i] + b4.x, 0.f); v[i + 1] = fmaxf(v[i + 1] + b4.y, 0.f);
             v[i + 2] = fmaxf(v[i + 2] + b4.z, 0.f); v[i + 3] = fmaxf(v[i + 3] + b4.w, 0.f);
           }
           if (kMode == kBwdA && A.mask_out != nullptr && wrow0 + lane < R) {
-            // the sign of h is all the dgrad chain needs of it: 8 bytes per row-half instead of 128
-            uint32_t mlo = 0u, mhi = 0u;
+            // the sign of h is all the dgrad chain needs of it: 4 bytes per thread instead of 64
+            uint32_t m32 = 0u;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              mlo |= (v[i] > 0.f ? 1u : 0u) << i;
-              mhi |= (v[32 + i] > 0.f ? 1u : 0u) << i;
-            }
-            A.mask_out[(wrow0 + lane) * (2 * HC) + c * 2 + hf] = ((unsigned long long)mhi << 32) | mlo;
+            for (int i = 0; i < 32; ++i) m32 |= (v[i] > 0.f ? 1u : 0u) << i;
+            reinterpret_cast<uint32_t*>(A.mask_out)[(wrow0 + lane) * (4 * HC) + c * 4 + cp] = m32;
           }
         }
         if (kDedIO) {
-          // (own stores of the previous tile were waited for at the top of the tile; nothing is shared across warps)
+          // (the stores of the previous tile were waited for at the top of the tile)
         } else if (c == 0 && ti > 0) {
           // the previous tile's output left through TMA out of the operand buffers (see the final epilogue): they may be
           // overwritten once every warp's store has finished READING shared memory
           if (lane == 0) bulk_wait_read0();
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         } else if (spill) {
-          if (lane == 0) bulk_wait_read1();          // my side-output store out of this buffer (two chunks ago) has been read
-          __syncwarp();
+          if (issuer && lane == 0) bulk_wait_read1();   // the pair's side-output store out of this buffer (two chunks ago) has been read
+          pair_sync();
         }
+        const int j0 = (cp & 1) * 4;                    // this warp's four 16-byte chunks of the block's 128-byte rows
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          st_block_chunk(hblk, row, j, make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
+        for (int j = 0; j < 4; ++j)
+          st_block_chunk(hblk, row, j0 + j, make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
                          make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]));
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&hb_full[hs]);
-          if (spill) {
-            // the bf16 operand rows this warp just wrote ARE its rows of the side output (h / dh / scores): TMA-store them
-            // from here -- box [32 rows][64 channels], nothing else to wait for
-            tma_store_2d(&A.tm_spill, c * 128 + hf * 64, (int)wrow0, hblk + q * 32 * 128);
+        if (lane == 0) mbar_arrive(&hb_full[hs]);
+        if (spill) {
+          // the bf16 operand rows the pair just wrote ARE its rows of the side output (h / dh / scores): TMA-store them
+          // from here -- box [32 rows][64 channels]
+          pair_sync();
+          if (issuer && lane == 0) {
+            tma_store_2d(&A.tm_spill, c * 128 + (cp >> 1) * 64, (int)wrow0, hblk + q * 32 * 128);
             bulk_commit();
           }
         }
         DG_PROF(4)
         ++hcount;
       }
-      // ---- final epilogue: this thread = one row, 64 columns [hf*64, +64)
+      // ---- final epilogue: this thread = one row, 32 columns [cp*32, +32)
       DG_PROF(5)
       // The residual rows come in, and the output rows leave, as a TMA tile: 4 boxes [128 rows][32 channels] with the
       // 128-byte swizzle, staged in the two operand buffers sH[0..1] (64 KB), which are idle from the completion of the
       // tile's last GEMM2 (z_full) until the next tile's first chunk is stored.  A thread reads and later overwrites only
-      // its own row halves, so the tile needs no transposition and no bank conflicts (8 consecutive rows = 8 swizzle slots).
-      float a[64];
-      float4 xq[kMode == kBwdA ? 16 : 1];
-      if (kMode == kBwdA) gather_issue(x, wrow0, R, 128, hf * 64, 4, lane, xq);   // residual x: in flight across the wait below
+      // its own row part, so the tile needs no transposition and no bank conflicts (8 consecutive rows = 8 swizzle slots).
+      float a[32];
+      float4 xq[kMode == kBwdA ? 8 : 1];
+      if (kMode == kBwdA) gather_issue(x, wrow0, R, 128, cp * kCW, 4, lane, xq);   // residual x: in flight across the wait below
       mbar_wait(z_full, ti & 1);
       DG_PROF(7)
       tc_fence_after();
-      if (spill && !kDedIO) {                        // every warp's side-output stores have finished reading the operand buffers
+      if (spill && !kDedIO) {                        // every pair's side-output stores have finished reading the operand buffers
         if (lane == 0) { bulk_wait_read0(); mbar_arrive(sp_done); }
         mbar_wait(sp_done, ti & 1);
       }
       if (!kDedIO && lane == 0) {
-        mbar_expect_tx(&io_full[warp], 2 * 32 * 128);
+        mbar_expect_tx(&io_full[warp], 32 * 128);
         const CUtensorMap* tin = kMode == kBwdA ? &A.tm_dout : &A.tm_x;   // FWD/ATTN: residual x;  BWD_B: residual dz;  BWD_A: dout
-        tma_load_2d(ioslab, tin, hf * 64, (int)wrow0, &io_full[warp]);
-        tma_load_2d(ioslab + kBlkBytes, tin, hf * 64 + 32, (int)wrow0, &io_full[warp]);
+        tma_load_2d(iobox, tin, cp * kCW, (int)wrow0, &io_full[warp]);
       }
-      uint8_t* iorow = sIO + (2 * hf) * kBlkBytes + row * 128;
-      auto io_chunk = [&](int j) -> float* {         // 16-byte chunk j (4 channels) of this thread's row half in the I/O tile
-        return reinterpret_cast<float*>(iorow + (j >> 3) * kBlkBytes + (((j & 7) ^ (row & 7)) << 4));
-      };
       float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
       if (kMode == kBwdA) {
         gather_finish(xq, 4, stg, lane, a);          // (the dout tile lands meanwhile)
         DG_PROF(6)
+        float v[32];
+        tmem_ld32(tmem_base + lane_base + 384 + cp * kCW, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(z_empty);
+        const float* bb = sB2 + cp * kCW;
 #pragma unroll
-        for (int cgl = 0; cgl < 2; ++cgl) {
-          float v[32];
-          tmem_ld32(tmem_base + lane_base + 384 + hf * 64 + cgl * 32, v);
-          tmem_ld_wait();
-          if (cgl == 1) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(z_empty); }
-          const float* bb = sB2 + hf * 64 + cgl * 32;
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float t0 = a[cgl * 32 + i] + v[i] + bb[i], t1 = a[cgl * 32 + i + 1] + v[i + 1] + bb[i + 1];
-            a[cgl * 32 + i] = t0; a[cgl * 32 + i + 1] = t1;
-            s1a += t0; s1b += t1; s2a = fmaf(t0, t0, s2a); s2b = fmaf(t1, t1, s2b);
-          }
+        for (int i = 0; i < 32; i += 2) {
+          const float t0 = a[i] + v[i] + bb[i], t1 = a[i + 1] + v[i + 1] + bb[i + 1];
+          a[i] = t0; a[i + 1] = t1;
+          s1a += t0; s1b += t1; s2a = fmaf(t0, t0, s2a); s2b = fmaf(t1, t1, s2b);
         }
       } else {
         // accumulator (+ bias) into registers while the residual tile is in flight, then the residual on top of it
-        tmem_ld32(tmem_base + lane_base + 384 + hf * 64, a);
-        tmem_ld32(tmem_base + lane_base + 384 + hf * 64 + 32, a + 32);
+        tmem_ld32(tmem_base + lane_base + 384 + cp * kCW, a);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(z_empty);
         if (kMode != kBwdB) {
-          const float* bb = sB2 + hf * 64;
+          const float* bb = sB2 + cp * kCW;
 #pragma unroll
-          for (int i = 0; i < 64; i += 4) {
+          for (int i = 0; i < 32; i += 4) {
             const float4 b4 = ld4(bb + i);
             a[i] += b4.x; a[i + 1] += b4.y; a[i + 2] += b4.z; a[i + 3] += b4.w;
           }
@@ -627,7 +615,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
         mbar_wait(&io_full[warp], ti & 1);
         DG_PROF(6)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 8; ++j) {
           const float4 t = ld4(io_chunk(j));
           const float t0 = a[4 * j] + t.x, t1 = a[4 * j + 1] + t.y, t2 = a[4 * j + 2] + t.z, t3 = a[4 * j + 3] + t.w;
           a[4 * j] = t0; a[4 * j + 1] = t1; a[4 * j + 2] = t2; a[4 * j + 3] = t3;
@@ -636,15 +624,14 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
         }
       }
       DG_PROF(8)
-      // rows -> the I/O tile (own row, in place) -> one elected thread issues the TMA store of the 4 boxes
+      // rows -> the I/O tile (own row, in place) -> one elected thread issues the TMA store of the warp's box
       auto store_tile = [&](const CUtensorMap* tm, bool wait_read) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) st4(io_chunk(j), make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]));
+        for (int j = 0; j < 8; ++j) st4(io_chunk(j), make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]));
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {                             // this warp's rows only: no CTA-wide barrier on the way out
-          tma_store_2d(tm, hf * 64, (int)wrow0, ioslab);
-          tma_store_2d(tm, hf * 64 + 32, (int)wrow0, ioslab + kBlkBytes);
+          tma_store_2d(tm, cp * kCW, (int)wrow0, iobox);
           bulk_commit();
           if (wait_read) bulk_wait_read0();
         }
@@ -655,19 +642,24 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
         DG_PROF(11)
         continue;
       }
-      float2* st = sStats + (ti & 1) * 512;
-      st[hf * 128 + row] = make_float2(s1a + s1b, s2a + s2b);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // per-row statistics across the four column parts: [part][row] float2.  Modes whose I/O tile aliases the operand buffers
+      // pass a CTA-wide barrier before the next tile's first operand store, so one copy is enough (and BWD_A's second exchange
+      // uses the second 4 KB); ATTN has no such barrier: its single exchange alternates between the two copies.
+      float2* st = sStats + (kDedIO ? (int)(ti & 1) * (kParts * 128) : 0);
+      st[cp * 128 + row] = make_float2(s1a + s1b, s2a + s2b);
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       DG_PROF(9)
-      const float2 other = st[(hf ^ 1) * 128 + row];
-      const float mean = (s1a + s1b + other.x) * (1.f / 128.f);
-      const float rstd = rsqrtf(fmaxf((s2a + s2b + other.y) * (1.f / 128.f) - mean * mean, 0.f) + A.eps);
-      const float* gg = sG + hf * 64;
+      float sum1 = 0.f, sum2 = 0.f;
+#pragma unroll
+      for (int p = 0; p < kParts; ++p) { const float2 o = st[p * 128 + row]; sum1 += o.x; sum2 += o.y; }
+      const float mean = sum1 * (1.f / 128.f);
+      const float rstd = rsqrtf(fmaxf(sum2 * (1.f / 128.f) - mean * mean, 0.f) + A.eps);
+      const float* gg = sG + cp * kCW;
       if (kMode == kAttn && A.z_out != nullptr) store_tile(&A.tm_z, true);   // pre-LayerNorm sum, for the LayerNorm backward
       if (kMode == kFwd || kMode == kAttn) {
-        const float* be = sBe + hf * 64;
+        const float* be = sBe + cp * kCW;
 #pragma unroll
-        for (int i = 0; i < 64; i += 4) {
+        for (int i = 0; i < 32; i += 4) {
           const float4 g4 = ld4(gg + i), e4 = ld4(be + i);
           a[i] = (a[i] - mean) * rstd * g4.x + e4.x; a[i + 1] = (a[i + 1] - mean) * rstd * g4.y + e4.y;
           a[i + 2] = (a[i + 2] - mean) * rstd * g4.z + e4.z; a[i + 3] = (a[i + 3] - mean) * rstd * g4.w + e4.w;
@@ -679,17 +671,17 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
       // ---- BWD_A: LayerNorm backward.  xh = (z - mean) rstd;  gh = gamma * dout;
       //      dz = rstd * (gh - mean(gh) - xh * mean(gh * xh));  dgamma += dout * xh, dbeta += dout (column sums)
 #pragma unroll
-      for (int i = 0; i < 64; ++i) a[i] = (a[i] - mean) * rstd;      // a := xh
+      for (int i = 0; i < 32; ++i) a[i] = (a[i] - mean) * rstd;      // a := xh
       float sg = 0.f, sgx = 0.f;
       mbar_wait(&io_full[warp], ti & 1);                              // this warp's dout rows are in the I/O tile
       // pass 1: row sums of gh and gh*xh; dout*xh goes through the warp's staging tile for the dgamma column sums
 #pragma unroll
-      for (int g16 = 0; g16 < 4; ++g16) {
+      for (int g = 0; g < 4; ++g) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 d4 = ld4(io_chunk(g16 * 4 + i));
-          const float* xh = a + g16 * 16 + 4 * i;
-          const float4 g4 = ld4(gg + g16 * 16 + 4 * i);
+        for (int i = 0; i < 2; ++i) {
+          const float4 d4 = ld4(io_chunk(g * 2 + i));
+          const float* xh = a + g * 8 + 4 * i;
+          const float4 g4 = ld4(gg + g * 8 + 4 * i);
           const float h0 = g4.x * d4.x, h1 = g4.y * d4.y, h2 = g4.z * d4.z, h3 = g4.w * d4.w;
           sg += (h0 + h1) + (h2 + h3);
           sgx = fmaf(h0, xh[0], fmaf(h1, xh[1], fmaf(h2, xh[2], fmaf(h3, xh[3], sgx))));
@@ -698,31 +690,33 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
         if (!want_affine) continue;                                   // (dgrad-only passes: no dgamma / dbeta column sums)
         __syncwarp();
 #pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {                              // lane: chunk lane&3, rows (lane>>2)*4 .. +3
-          const float4 t = ld4(stg + stg_off((lane >> 2) * 4 + rr, lane & 3));
-          acc_g[g16].x += t.x; acc_g[g16].y += t.y; acc_g[g16].z += t.z; acc_g[g16].w += t.w;
+        for (int rr = 0; rr < 2; ++rr) {                              // lane: chunk lane&1, rows lane>>1 and 16 + (lane>>1)
+          const float4 t = ld4(stg + stg_off(rr * 16 + (lane >> 1), lane & 1));
+          acc_g[g].x += t.x; acc_g[g].y += t.y; acc_g[g].z += t.z; acc_g[g].w += t.w;
         }
         __syncwarp();
       }
-      // dbeta: column sums of this warp's own dout slab, straight from the tile (lane: chunk lane&15, rows (lane>>4)*16 .. +15)
+      // dbeta: column sums of this warp's own dout box, straight from the tile (lane: chunk lane&7, rows (lane>>3)*8 .. +7)
 #pragma unroll
-      for (int rr = 0; rr < 16; ++rr) {
+      for (int rr = 0; rr < 8; ++rr) {
         if (!want_affine) break;
-        const int r = (lane >> 4) * 16 + rr, j = lane & 15;
-        const float4 t = ld4(reinterpret_cast<const float*>(ioslab + (j >> 3) * kBlkBytes + r * 128 + (((j & 7) ^ (r & 7)) << 4)));
+        const int r = (lane >> 3) * 8 + rr, j = lane & 7;
+        const float4 t = ld4(reinterpret_cast<const float*>(iobox + r * 128 + ((j ^ (r & 7)) << 4)));
         acc_b.x += t.x; acc_b.y += t.y; acc_b.z += t.z; acc_b.w += t.w;
       }
       DG_PROF(10)
-      float2* st2 = sStats + (ti & 1) * 512 + 256;
-      st2[hf * 128 + row] = make_float2(sg, sgx);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      float2* st2 = sStats + kParts * 128;
+      st2[cp * 128 + row] = make_float2(sg, sgx);
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       DG_PROF(9)
-      const float2 o2 = st2[(hf ^ 1) * 128 + row];
-      const float c1 = (sg + o2.x) * (1.f / 128.f), c2 = (sgx + o2.y) * (1.f / 128.f);
-      // pass 2: dz over dout, in place, then out through TMA
-      __syncwarp();                                                   // (the dbeta readers of this slab are done)
+      float tg = 0.f, tgx = 0.f;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int p = 0; p < kParts; ++p) { const float2 o = st2[p * 128 + row]; tg += o.x; tgx += o.y; }
+      const float c1 = tg * (1.f / 128.f), c2 = tgx * (1.f / 128.f);
+      // pass 2: dz over dout, in place, then out through TMA
+      __syncwarp();                                                   // (the dbeta readers of this box are done)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
         const float4 d4 = ld4(io_chunk(j)), g4 = ld4(gg + 4 * j);
         st4(io_chunk(j), make_float4(rstd * (g4.x * d4.x - c1 - a[4 * j] * c2), rstd * (g4.y * d4.y - c1 - a[4 * j + 1] * c2),
                                      rstd * (g4.z * d4.z - c1 - a[4 * j + 2] * c2), rstd * (g4.w * d4.w - c1 - a[4 * j + 3] * c2)));
@@ -730,8 +724,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
       fence_async_smem();
       __syncwarp();
       if (lane == 0) {
-        tma_store_2d(&A.tm_out, hf * 64, (int)wrow0, ioslab);
-        tma_store_2d(&A.tm_out, hf * 64 + 32, (int)wrow0, ioslab + kBlkBytes);
+        tma_store_2d(&A.tm_out, cp * kCW, (int)wrow0, iobox);
         bulk_commit();
       }
       DG_PROF(11)
@@ -739,26 +732,28 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
     if (lane == 0) bulk_wait0();                                      // outstanding TMA stores complete before the CTA retires
     if (kMode == kBwdA && want_affine) {
 #pragma unroll
-      for (int g16 = 0; g16 < 4; ++g16) {                            // dgamma: fold the 8 row groups (lane>>2), lanes 0-3 flush
-        float v4[4] = {acc_g[g16].x, acc_g[g16].y, acc_g[g16].z, acc_g[g16].w};
+      for (int g = 0; g < 4; ++g) {                                  // dgamma: fold the 16 row pairs (lane>>1), lanes 0-1 flush
+        float v4[4] = {acc_g[g].x, acc_g[g].y, acc_g[g].z, acc_g[g].w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           float t = v4[e];
-          t += __shfl_xor_sync(0xffffffffu, t, 4); t += __shfl_xor_sync(0xffffffffu, t, 8); t += __shfl_xor_sync(0xffffffffu, t, 16);
-          if (lane < 4) atomicAdd(A.dgamma + hf * 64 + g16 * 16 + lane * 4 + e, t);
+          t += __shfl_xor_sync(0xffffffffu, t, 2); t += __shfl_xor_sync(0xffffffffu, t, 4);
+          t += __shfl_xor_sync(0xffffffffu, t, 8); t += __shfl_xor_sync(0xffffffffu, t, 16);
+          if (lane < 2) atomicAdd(A.dgamma + cp * kCW + g * 8 + lane * 4 + e, t);
         }
       }
       float b4[4] = {acc_b.x, acc_b.y, acc_b.z, acc_b.w};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {                                  // dbeta: fold the two row halves, lanes 0-15 flush
-        const float t = b4[e] + __shfl_xor_sync(0xffffffffu, b4[e], 16);
-        if (lane < 16) atomicAdd(A.dbeta + hf * 64 + lane * 4 + e, t);
+      for (int e = 0; e < 4; ++e) {                                  // dbeta: fold the four row quarters, lanes 0-7 flush
+        float t = b4[e];
+        t += __shfl_xor_sync(0xffffffffu, t, 8); t += __shfl_xor_sync(0xffffffffu, t, 16);
+        if (lane < 8) atomicAdd(A.dbeta + cp * kCW + lane * 4 + e, t);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }

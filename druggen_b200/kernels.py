@@ -55,6 +55,7 @@ class precision:
 
 
 _test_backend = None
+_debug_hold = []
 
 
 def _install_backend_for_tests(backend) -> None:
@@ -342,6 +343,12 @@ def attn_edge_fwd(y, q, k, we, be, woe, boe, gamma, beta, c: float, want_a16: bo
     _chk(y, q, k, we, be, woe, boe, gamma, beta)
     b, n, d = q.shape
     assert y.shape == (b * n * n, d), (y.shape, q.shape)
+    if os.environ.get("DG_DEBUG_ATTN_UNFUSED"):          # debug: the same outputs from the unfused kernels
+        e_ = rows_gemm(y, we, True, be)
+        a_ = modulate_fwd(q, k, e_.view(b, n, n, d), c).view(-1, d)
+        y1 = rows_gemm(a_, woe, True, boe)
+        return (add_ln_fwd(y, y1, gamma, beta), a_.to(torch.bfloat16) if want_a16 else None, e_ if want_e else None,
+                (y + y1) if want_z else None)
     out = torch.empty_like(y)
     a16 = torch.empty_like(y, dtype=torch.bfloat16) if want_a16 else None
     e = torch.empty_like(y) if want_e else None
@@ -349,6 +356,39 @@ def attn_edge_fwd(y, q, k, we, be, woe, boe, gamma, beta, c: float, want_a16: bo
     if y.numel():
         ws = torch.empty(2 * 32768, dtype=torch.uint8, device=y.device)
         _be().attn_edge_fwd(y, q, k, we, be, woe, boe, gamma, beta, c, out, a16, e, z, eps, ws)
+    if os.environ.get("DG_DEBUG_HOLD"):                    # debug: keep every output alive (no allocator reuse of their storage)
+        _debug_hold.append((out, a16, e, z, ws if y.numel() else None)[: int(os.environ["DG_DEBUG_HOLD"])])
+        _debug_hold.append(("clone", out, out.clone(), y, y.clone()))
+    if os.environ.get("DG_DEBUG_ATTN_COMPARE"):           # debug: compare every output with the unfused kernels
+        e_ = rows_gemm(y, we, True, be)
+        a_ = modulate_fwd(q, k, e_.view(b, n, n, d), c).view(-1, d)
+        y1 = rows_gemm(a_, woe, True, boe)
+        rl = lambda g, r: float((g.float() - r.float()).norm() / r.float().norm().clamp_min(1e-30))  # noqa: E731
+        msg = "attn_edge_fwd[%s%s%s] y3 %.2e" % ("a" if want_a16 else "", "e" if want_e else "", "z" if want_z else "",
+                                                  rl(out, add_ln_fwd(y, y1, gamma, beta)))
+        ref_out = add_ln_fwd(y, y1, gamma, beta)
+        dd = (out - ref_out).abs()
+        msg += " maxabs %.2e n>1e-5 %d argmax_row %d col %d" % (float(dd.max()), int((dd > 1e-5).sum()), int(dd.max(1).values.argmax()),
+                                                                 int(dd.max(0).values.argmax()))
+        if want_a16:
+            msg += " a16 %.2e" % rl(a16, a_.to(torch.bfloat16))
+        if want_e:
+            msg += " E %.2e" % rl(e, e_)
+        if want_z:
+            msg += " z %.2e" % rl(z, y + y1)
+        if os.environ.get("DG_DEBUG_ATTN_QUIET") is None:
+            print(msg + "  |y| %.2e nonfinite %d" % (float(y.abs().max()), int((~torch.isfinite(out)).sum())))
+        sub = int(os.environ.get("DG_DEBUG_ATTN_SUBST", "0"))
+        if sub & 1:
+            out = add_ln_fwd(y, y1, gamma, beta)
+            if os.environ.get("DG_DEBUG_NOISE"):
+                out = out * (1.0 + float(os.environ["DG_DEBUG_NOISE"]) * torch.randn_like(out))
+        if sub & 2 and want_a16:
+            a16 = a_.to(torch.bfloat16)
+        if sub & 4 and want_e:
+            e = e_
+        if sub & 8 and want_z:
+            z = y + y1
     return out, a16, e, z
 
 

@@ -278,8 +278,13 @@ DEPTH8_BOUNDS = {
     # flush order of the weight-gradient kernels decides whether a 1e-7 forward perturbation crosses that pre-activation's zero
     "fp32": (1e-3, 5e-3, 5e-3),
     "bf16x3": (1e-3, 5e-3, 5e-3),         # measured 7e-7 / 5.5e-4 / 2.4e-3  (ReLU-flip limited, see GRAD_TOL)
-    "bf16": (1e-3, 6e-2, 8e-2),           # measured 2.7e-4 / 2.6e-2 / 3.6e-2
+    # bf16 (throughput mode), measured at 8 molecules over four seeds (tools/parity_sweep.py, profiles/r02_parity_sweep.jsonl):
+    # loss 1.6e-4..2.2e-3, D grads 2.9e-2..8.2e-2, G grads 2.7e-2..7.5e-2.  At 2 molecules the same mode ranges 3.7e-2..3.1e-1 from
+    # seed to seed -- and moves by as much when ANY input is perturbed in its last fp32 bit (a Discriminator-head ReLU unit a
+    # rounding error away from zero carries a macroscopic share of a 2-molecule gradient) -- so this mode is bounded at batch 8
+    "bf16": (1e-2, 0.16, 0.16),
 }
+DEPTH8_BATCH = {"fp32": 2, "bf16x3": 2, "bf16": 8}
 
 
 def _flat(grads):
@@ -298,7 +303,7 @@ def test_gan_step_depth8_n45_vs_oracle(cuda_dev, mode, capsys):
     if mode != "fp32" and not _tc_built():
         pytest.skip("tcgen05 contractions not built")
     torch.manual_seed(21)
-    n, bsz = 45, 2
+    n, bsz = 45, DEPTH8_BATCH[mode]
     G = dg.Generator("relu", n, 5, 13, 0.0, dim=128, depth=8, heads=8, mlp_ratio=3)
     D = dg.Discriminator("relu", n, 5, 13, 0.0, dim=128, depth=8, heads=8, mlp_ratio=3)
     # the oracle in fp64: the fp32 oracle's own gradients carry up to 2e-3 of thread-count-dependent noise (GRAD_TOL above)

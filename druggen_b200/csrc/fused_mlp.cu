@@ -270,18 +270,26 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
       DG_PROF(0)
       mbar_wait(x_empty, (ti & 1) ^ 1);
       DG_PROF(1)
+      // this thread: rows (lt >> 3) + 16 it, 32-byte chunk lt & 7 of each 64-channel half -- one base pointer, immediate offsets
+      const float* xt = x + row0 * 128 + (lt >> 3) * 128 + (lt & 7) * 8;
+      const bool full_tile = row0 + 128 <= R;          // (every tile but the last: no row predicates in the load burst)
 #pragma unroll 1
       for (int kb = 0; kb < 2; ++kb) {
         uint8_t* blk = sX + kb * kBlkBytes;
         float4 v[16];
+        if (full_tile && !(A.prefetch & 2)) {
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          int item = it * 128 + lt, r = item >> 3, j = item & 7;
-          if (row0 + r < R) {
-            if (A.prefetch & 2) ld8_keep(x + (row0 + r) * 128 + kb * 64 + j * 8, v[2 * it], v[2 * it + 1]);   // x is re-read as the residual
-            else ld8(x + (row0 + r) * 128 + kb * 64 + j * 8, v[2 * it], v[2 * it + 1]);
-          } else {
-            v[2 * it] = v[2 * it + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int it = 0; it < 8; ++it) ld8(xt + it * 2048 + kb * 64, v[2 * it], v[2 * it + 1]);
+        } else {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 16 + (lt >> 3);
+            if (row0 + r < R) {
+              if (A.prefetch & 2) ld8_keep(xt + it * 2048 + kb * 64, v[2 * it], v[2 * it + 1]);   // x is re-read as the residual
+              else ld8(xt + it * 2048 + kb * 64, v[2 * it], v[2 * it + 1]);
+            } else {
+              v[2 * it] = v[2 * it + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
           }
         }
 #pragma unroll
@@ -528,6 +536,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
             reinterpret_cast<uint32_t*>(A.mask_out)[(wrow0 + lane) * (4 * HC) + c * 4 + cp] = m32;
           }
         }
+        DG_PROF(12)
         if (kDedIO) {
           // (the stores of the previous tile were waited for at the top of the tile)
         } else if (c == 0 && ti > 0) {
@@ -539,11 +548,13 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
           if (issuer && lane == 0) bulk_wait_read1();   // the pair's side-output store out of this buffer (two chunks ago) has been read
           pair_sync();
         }
+        DG_PROF(13)
         const int j0 = (cp & 1) * 4;                    // this warp's four 16-byte chunks of the block's 128-byte rows
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           st_block_chunk(hblk, row, j0 + j, make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
                          make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]));
+        DG_PROF(14)
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&hb_full[hs]);

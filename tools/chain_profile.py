@@ -14,8 +14,8 @@ sys.path.insert(0, ROOT)
 import druggen_b200 as dg  # noqa: E402
 from druggen_b200 import _lib, kernels as K  # noqa: E402
 
-EPI = ["chunk:pre", "wait hacc_full", "wait hb_empty", "tmem_ld", "chunk math+st_block", "chunk tail", "gather resid", "wait z_full",
-       "final tmem+sum", "stats bar", "lnbwd pass1", "final scatter", "spill"]
+EPI = ["chunk:pre", "wait hacc_full", "wait hb_empty", "tmem_ld", "chunk fence+arrive+spill", "chunk tail", "gather resid", "wait z_full",
+       "final tmem+sum", "stats bar", "lnbwd pass1", "final scatter", "chunk math", "chunk reuse waits", "chunk st_block"]
 LOAD = ["loop/prefetch", "wait x_empty", "load+convert+store"]
 MMA = ["issue", "wait w_full", "wait x_full", "wait hacc_empty", "wait hb_full", "wait z_empty"]
 

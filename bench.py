@@ -296,6 +296,8 @@ def main():
         "e2e": {"value": total / (ms_e2e / 1e3), "unit": "molecules/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8},
         "gpu_launches": launches, "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
         "reserved_mem_gb": round(torch.cuda.max_memory_reserved() / 2 ** 30, 1),
+        "allocator": {k: torch.cuda.memory_stats().get(v, 0) for k, v in (("alloc_retries", "num_alloc_retries"), ("ooms", "num_ooms"),
+                                                                          ("device_mallocs", "num_device_alloc"), ("device_frees", "num_device_free"))},
         "losses": {"d": losses[0], "g": losses[1]},
     }
     if args.kernel_table:

@@ -53,6 +53,7 @@ INFO_SYMBOLS = ("dg_abi_version", "dg_last_error", "dg_has_tcgen05", "dg_set_opt
                 "dg_label_error")
 ABI_VERSION = 4
 OPT_L2_PREFETCH = 0
+OPT_ATTN_BWD = 1                                      # 0 = TMA-fed ring kernel where it applies (default), 1 = 4-warp kernel
 PF_ALL, PF_DEFAULT, PF_CHAIN_KEEP = 63, 12, 64        # DG_PF_* bit masks (include/druggen_b200.h)
 
 _lib = None
@@ -82,6 +83,8 @@ def load():
             raise RuntimeError("libdruggen_b200.so ABI version mismatch")
         if os.environ.get("DRUGGEN_B200_L2_PREFETCH") is not None:       # tuning switch, default on
             lib.dg_set_option(OPT_L2_PREFETCH, int(os.environ["DRUGGEN_B200_L2_PREFETCH"]))
+        if os.environ.get("DRUGGEN_B200_ATTN_BWD") is not None:
+            lib.dg_set_option(OPT_ATTN_BWD, int(os.environ["DRUGGEN_B200_ATTN_BWD"]))
         _lib = lib
     return _lib
 

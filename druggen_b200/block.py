@@ -41,6 +41,42 @@ _IDX = {n: i for i, n in enumerate(BLOCK_PARAM_NAMES)}
 # differentiable primitives (ops.py) instead of the hand-sequenced ``block_backward_backward`` (A/B switch, tests)
 _HAND_SECOND_ORDER = os.environ.get("DRUGGEN_B200_SECOND_ORDER", "hand") != "autograd"
 
+# ---- activation policy of the checkpointed block -------------------------------------------------------------------------
+# Default: a block keeps only its INPUTS and its backward recomputes the forward (one more pass of the fused edge-attention
+# chain over the edge tensor: ~7 % of a GAN step).  Inside ``keep_intermediates()`` a block ALSO keeps what that recomputation
+# would produce (x1, q, k, v, out_n, x3: node-sized;  y3, E, y + out_e(A): fp32 edge-sized;  the scores: bf16) -- 3.5 edge
+# tensors more per block -- as long as the device has room for them beyond a safety margin; the decision is taken per block from
+# the allocator's state, so a pass keeps as many blocks as fit and recomputes the rest.  Results are bit-identical either way
+# (the kept tensors are the outputs of the same launches the recomputation would run).
+_KEEP = {"on": False, "headroom": float(os.environ.get("DRUGGEN_B200_KEEP_HEADROOM_GB", "40")) * 2 ** 30}
+
+
+class keep_intermediates:
+    """Context manager: blocks run inside it keep their forward intermediates for the backward when memory allows."""
+
+    def __init__(self, on: bool = True):
+        self.on = on
+
+    def __enter__(self):
+        self.prev, _KEEP["on"] = _KEEP["on"], self.on and os.environ.get("DRUGGEN_B200_KEEP", "1") != "0"
+        return self
+
+    def __exit__(self, *exc):
+        _KEEP["on"] = self.prev
+        return False
+
+
+def _keep_fits(x, y) -> bool:
+    """Room for this block's kept intermediates (3.5 edge tensors + 6 node tensors) beyond the safety margin?"""
+    if not _KEEP["on"]:
+        return False
+    if not y.is_cuda:
+        return True                                   # (CPU test backend)
+    need = int(3.5 * y.numel() * 4 + 6 * x.numel() * 4)
+    free, _ = torch.cuda.mem_get_info(y.device)
+    cached = torch.cuda.memory_reserved(y.device) - torch.cuda.memory_allocated(y.device)
+    return free + cached - need > _KEEP["headroom"]
+
 
 def block_forward(x, y, params: Sequence[torch.Tensor], heads: int, edge_out: bool = True, drop_p: float = 0.0):
     """x:[B,N,D], y:[B,N,N,D] -> (x_out, y_out).  ``edge_out=False`` skips the edge half that has
@@ -90,19 +126,22 @@ def _scores_bwd(dg, da_in, a, q, k, v, e, c, stats=None):
     return de, dq, dk, dv
 
 
-def block_forward_nograd(x, y, params: Sequence[torch.Tensor], heads: int, edge_out: bool = True, want_stats: bool = False):
+def block_forward_nograd(x, y, params: Sequence[torch.Tensor], heads: int, edge_out: bool = True, want_stats: bool = False,
+                         want_saved=None):
     """Same function as ``block_forward`` for callers that need no graph (inference, the checkpointed
     forward): uses the fused tcgen05 kernels where they exist, raw kernels otherwise.
     ``want_stats``: returns (x_out, y_out, stats) with stats = the softmax statistics (max, 1/sum, g) per (molecule, query atom,
     channel) when the fused chain computed them (else None) -- three NODE-sized tensors the checkpointed backward keeps so that
-    it does not have to re-run the softmax over the recomputed scores."""
+    it does not have to re-run the softmax over the recomputed scores.
+    ``want_saved`` not None (with ``want_stats``): returns a fourth value -- True: the intermediates ``block_backward`` would
+    otherwise recompute (dict, see ``keep_intermediates``), or None where the fused chain did not run; False: None."""
     p = lambda n: params[_IDX[n]]  # noqa: E731
     b, n, d = x.shape
     hid = p("mlp.fc1.weight").shape[0]
-    stats = None
+    stats = saved = None
     if not K.fused_available(d, hid):
         out = block_forward(x, y, params, heads, edge_out)
-        return out + (None,) if want_stats else out
+        return (out + (None, None) if want_saved is not None else out + (None,)) if want_stats else out
     c = 1.0 / math.sqrt(d // heads)
     x1 = K.add_ln_fwd(x.reshape(-1, d), None, p("ln1.weight"), p("ln1.bias"))
     q = K.rows_gemm(x1, p("attn.q.weight"), True, p("attn.q.bias")).view(b, n, d)
@@ -113,23 +152,30 @@ def block_forward_nograd(x, y, params: Sequence[torch.Tensor], heads: int, edge_
     if chain:
         # one tcgen05 kernel: E-projection, modulation, out_e projection, residual, LN4; the scores leave the SM once, as bf16
         s16 = K.softmax_scores_bf16()
-        y3, a16, e, _ = K.attn_edge_fwd(y2d, q, k, p("attn.e.weight"), p("attn.e.bias"), p("attn.out_e.weight"),
-                                        p("attn.out_e.bias"), p("ln4.weight"), p("ln4.bias"), c, want_a16=s16, want_e=not s16)
+        keep = want_saved and want_stats and s16
+        y3, a16, e, z4 = K.attn_edge_fwd(y2d, q, k, p("attn.e.weight"), p("attn.e.bias"), p("attn.out_e.weight"),
+                                         p("attn.out_e.bias"), p("ln4.weight"), p("ln4.bias"), c, want_a16=s16, want_e=keep or not s16,
+                                         want_z=keep)
         if s16 and want_stats:
             g, stats = K.softmax_agg16_fwd(a16, v, want_stats=True)
         else:
             g = K.softmax_agg16_fwd(a16, v) if s16 else K.attn_scores_fwd(q, k, v, e.view(b, n, n, d), c, store_a=False)[1]
-        del a16, e
+        if keep:
+            saved = {"x1": x1, "q": q, "k": k, "v": v, "y3": y3, "a16": a16, "e": e, "z4": z4}
+        del a16, e, z4
     else:
         e = K.rows_gemm(y2d, p("attn.e.weight"), True, p("attn.e.bias"))
         a, g = _scores_fwd(q, k, v, e.view(b, n, n, d), c)
         del e
     on = K.rows_gemm(g.view(-1, d), p("attn.out_n.weight"), True, p("attn.out_n.bias"))
     x3 = K.add_ln_fwd(x1, on, p("ln3.weight"), p("ln3.bias"))
+    if saved is not None:
+        saved["on"], saved["x3"] = on, x3
     x_out = K.mlp_fwd(x3, p("mlp.fc1.weight"), p("mlp.fc1.bias"), p("mlp.fc2.weight"), p("mlp.fc2.bias"),
                       p("ln5.weight"), p("ln5.bias")).view(b, n, d)
+    ret = lambda yo: ((x_out, yo, stats, saved) if want_saved is not None else (x_out, yo, stats)) if want_stats else (x_out, yo)  # noqa: E731
     if not edge_out:
-        return (x_out, None, stats) if want_stats else (x_out, None)
+        return ret(None)
     if not chain:
         y1 = K.rows_gemm(a.view(-1, d), p("attn.out_e.weight"), True, p("attn.out_e.bias"))
         del a
@@ -137,21 +183,23 @@ def block_forward_nograd(x, y, params: Sequence[torch.Tensor], heads: int, edge_
         del y1
     y_out = K.mlp_fwd(y3, p("mlp2.fc1.weight"), p("mlp2.fc1.bias"), p("mlp2.fc2.weight"), p("mlp2.fc2.bias"),
                       p("ln6.weight"), p("ln6.bias")).view(b, n, n, d)
-    return (x_out, y_out, stats) if want_stats else (x_out, y_out)
+    return ret(y_out)
 
 
 def block_backward(x, y, dxo, dyo, params: Sequence[torch.Tensor], heads: int, edge_out: bool = True,
-                   want_params: bool = True, fwd_stats=None):
+                   want_params: bool = True, fwd_stats=None, fwd_saved=None):
     """First-order backward of the block as a hand-sequenced list of raw kernel launches (no autograd
     graph): recompute from the block inputs, then the chain of Appendix-B of SURVEY.md.  Gradient
     accumulation is fused into GEMM epilogues (``resid``), the ReLU derivative into the dgrad epilogue
     (``gate``), bias gradients into the weight-gradient pass (``colsum_a``), and the softmax path adds
     into the out_e path in place.  Returns (dx, dy, [param grads aligned with BLOCK_PARAM_NAMES]);
-    parameter grads are None when ``want_params`` is False or the parameter has no consumer."""
+    parameter grads are None when ``want_params`` is False or the parameter has no consumer.
+    ``fwd_saved``: the forward's intermediates (``keep_intermediates``): the recomputation is skipped."""
     p = lambda n: params[_IDX[n]]  # noqa: E731
     b, n, d = x.shape
     c = 1.0 / math.sqrt(d // heads)
     grads = [None] * len(BLOCK_PARAM_NAMES)
+    kept = fwd_saved is not None and fwd_stats is not None and edge_out and dyo is not None
 
     def put(name, t):
         grads[_IDX[name]] = t
@@ -202,14 +250,21 @@ def block_backward(x, y, dxo, dyo, params: Sequence[torch.Tensor], heads: int, e
         del hh
         wgrad(mlp + ".fc1", dh, xin)
         return K.rows_gemm(dh, w1, False, resid=dz)
-    # ---- recompute (node stream, attention scores)
-    x1 = K.add_ln_fwd(x2d, None, p("ln1.weight"), p("ln1.bias"))
-    q = K.rows_gemm(x1, p("attn.q.weight"), True, p("attn.q.bias")).view(b, n, d)
-    k = K.rows_gemm(x1, p("attn.k.weight"), True, p("attn.k.bias")).view(b, n, d)
-    v = K.rows_gemm(x1, p("attn.v.weight"), True, p("attn.v.bias")).view(b, n, d)
+    # ---- recompute (node stream, attention scores) -- or take what the forward kept
+    if kept:
+        x1, q, k, v = (fwd_saved[nm] for nm in ("x1", "q", "k", "v"))
+    else:
+        x1 = K.add_ln_fwd(x2d, None, p("ln1.weight"), p("ln1.bias"))
+        q = K.rows_gemm(x1, p("attn.q.weight"), True, p("attn.q.bias")).view(b, n, d)
+        k = K.rows_gemm(x1, p("attn.k.weight"), True, p("attn.k.bias")).view(b, n, d)
+        v = K.rows_gemm(x1, p("attn.v.weight"), True, p("attn.v.bias")).view(b, n, d)
     live_edge = edge_out and dyo is not None
     chain = live_edge and K.attn_chain_available(b, n, d)
-    if chain:
+    if kept:
+        y3, a2d, e, z4 = (fwd_saved[nm] for nm in ("y3", "a16", "e", "z4"))
+        a, g, sm_stats = None, fwd_stats[2], fwd_stats
+        chain = True
+    elif chain:
         # recompute of the edge half in one tcgen05 kernel; side outputs: E (fp32), the scores (bf16: only ever an
         # operand) and y + out_e(A) (fp32, what LN4's backward needs); g and the softmax statistics from the bf16 scores
         y3, a2d, e, z4 = K.attn_edge_fwd(y2d, q, k, p("attn.e.weight"), p("attn.e.bias"), p("attn.out_e.weight"),
@@ -227,8 +282,12 @@ def block_backward(x, y, dxo, dyo, params: Sequence[torch.Tensor], heads: int, e
         a, g, sm_stats = _scores_fwd(q, k, v, e.view(b, n, n, d), c, want_stats=True)
         a2d = a.view(-1, d)
     g2d = g.view(-1, d)
-    on = K.rows_gemm(g2d, p("attn.out_n.weight"), True, p("attn.out_n.bias"))
-    x3 = K.add_ln_fwd(x1, on, p("ln3.weight"), p("ln3.bias"))
+    if kept:
+        on, x3 = fwd_saved["on"], fwd_saved["x3"]
+    else:
+        on = K.rows_gemm(g2d, p("attn.out_n.weight"), True, p("attn.out_n.bias"))
+        x3 = K.add_ln_fwd(x1, on, p("ln3.weight"), p("ln3.bias"))
+    fwd_saved = None                                      # (the dict must not pin the edge tensors past their last use below)
     # ---- node MLP + LN5, LN3, out_n
     dxo2d = (dxo if dxo is not None else torch.zeros_like(x)).reshape(-1, d).contiguous()
     dx3 = mlp_bwd("mlp", "ln5", x3, dxo2d)
@@ -272,7 +331,8 @@ def block_backward(x, y, dxo, dyo, params: Sequence[torch.Tensor], heads: int, e
     return dx.view(b, n, d), dy.view(b, n, n, d), grads
 
 
-def block_backward_backward(x, y, dxo, dyo, ux, uy, params: Sequence[torch.Tensor], heads: int, edge_out: bool = True):
+def block_backward_backward(x, y, dxo, dyo, ux, uy, params: Sequence[torch.Tensor], heads: int, edge_out: bool = True,
+                            fwd_saved=None):
     """Second-order pass of the block as a hand-sequenced list of raw kernel launches (no autograd graph): the gradient of
     ``<ux, dx> + <uy, dy>`` -- (dx, dy) = ``block_backward(x, y, dxo, dyo)`` -- with respect to (x, y, dxo, dyo, parameters).
     This is what the gradient penalty's double backward (loss.py:32-39 inside ``d_loss.backward()``) asks of every
@@ -358,12 +418,19 @@ def block_backward_backward(x, y, dxo, dyo, ux, uy, params: Sequence[torch.Tenso
     z2 = lambda t, like: (t if t is not None else torch.zeros_like(like)).reshape(-1, d).contiguous()  # noqa: E731
     ux2d, uy2d, dxo2d = z2(ux, x), z2(uy, y), z2(dxo, x)
     qkv = ("attn.q", "attn.k", "attn.v")
-    # ---- 1a. forward recompute
-    x1 = K.add_ln_fwd(x2d, None, p("ln1.weight"), p("ln1.bias"))
-    q, k, v = (K.rows_gemm(x1, p(nm + ".weight"), True, p(nm + ".bias")).view(b, n, d) for nm in qkv)
+    # ---- 1a. forward recompute (the node projections and the edge chain's outputs may come from the forward: keep_intermediates)
+    kept = fwd_saved is not None and live
+    if kept:
+        x1, q, k, v = (fwd_saved[nm] for nm in ("x1", "q", "k", "v"))
+    else:
+        x1 = K.add_ln_fwd(x2d, None, p("ln1.weight"), p("ln1.bias"))
+        q, k, v = (K.rows_gemm(x1, p(nm + ".weight"), True, p(nm + ".bias")).view(b, n, d) for nm in qkv)
     chain = live and K.attn_chain_available(b, n, d)
     z4a = z4b = y3 = None
-    if chain:
+    if kept:
+        y3, e2d, z4a = fwd_saved["y3"], fwd_saved["e"], fwd_saved["z4"]
+        chain = True
+    elif chain:
         y3, _, e2d, z4a = K.attn_edge_fwd(y2d, q, k, p("attn.e.weight"), p("attn.e.bias"), p("attn.out_e.weight"),
                                           p("attn.out_e.bias"), p("ln4.weight"), p("ln4.bias"), c, want_a16=False, want_e=True,
                                           want_z=True)
@@ -509,9 +576,11 @@ class EncoderBlockFn(Function):
         ctx.heads, ctx.edge_out = heads, edge_out
         ctx.set_materialize_grads(False)
         with torch.no_grad():
-            xo, yo, stats = block_forward_nograd(x, y, params, heads, edge_out, want_stats=True)
+            xo, yo, stats, saved = block_forward_nograd(x, y, params, heads, edge_out, want_stats=True,
+                                                        want_saved=bool(edge_out) and _keep_fits(x, y))
         ctx.nstats = 0 if stats is None else len(stats)
-        ctx.save_for_backward(x, y, *params, *(stats or ()))
+        ctx.saved_names = () if saved is None else tuple(saved)
+        ctx.save_for_backward(x, y, *params, *(stats or ()), *(saved or {}).values())
         if yo is None:
             yo = y.new_empty(0)
             ctx.mark_non_differentiable(yo)
@@ -520,7 +589,10 @@ class EncoderBlockFn(Function):
     @staticmethod
     def backward(ctx, dxo, dyo):
         x, y, *params = ctx.saved_tensors
-        stats = None
+        stats = saved = None
+        if ctx.saved_names:
+            nk = len(ctx.saved_names)
+            params, saved = params[:-nk], dict(zip(ctx.saved_names, params[-nk:]))
         if ctx.nstats:
             params, stats = params[:-ctx.nstats], tuple(params[-ctx.nstats:])
         if not ctx.edge_out:
@@ -528,7 +600,7 @@ class EncoderBlockFn(Function):
         if dxo is None and dyo is None:
             return (None,) * (4 + len(params))
         want = _params_wanted(ctx, 4) if torch.is_grad_enabled() else any(ctx.needs_input_grad[4:])
-        outs = EncoderBlockBwdFn.apply(x, y, dxo, dyo, ctx.heads, ctx.edge_out, want, stats, *params)
+        outs = EncoderBlockBwdFn.apply(x, y, dxo, dyo, ctx.heads, ctx.edge_out, want, (stats, saved, torch.is_grad_enabled()), *params)
         return (outs[0], outs[1], None, None) + tuple(outs[2:])
 
 
@@ -538,21 +610,32 @@ class EncoderBlockBwdFn(Function):
     reference, ``.grad`` stays None and AdamW leaves those tensors untouched)."""
 
     @staticmethod
-    def forward(ctx, x, y, dxo, dyo, heads, edge_out, want_params, fwd_stats, *params):
+    def forward(ctx, x, y, dxo, dyo, heads, edge_out, want_params, fwd_kept, *params):
         ctx.heads, ctx.edge_out = heads, edge_out
-        ctx.save_for_backward(x, y, dxo, dyo, *params)
         ctx.set_materialize_grads(False)
-        dx, dy, pgrads = block_backward(x, y, dxo, dyo, params, heads, edge_out, want_params, fwd_stats)
+        # (softmax statistics, kept intermediates | None) of the checkpointed forward; with_graph: a graph is being recorded over
+        # this backward (the gradient penalty) -- the second-order pass then reuses the kept intermediates too (they stay alive
+        # until then anyway: the forward's node holds them while the graph is retained)
+        fwd_stats, fwd_saved, with_graph = fwd_kept
+        ctx.saved_names = ()
+        if fwd_saved is not None and with_graph:
+            ctx.saved_names = tuple(nm for nm in ("x1", "q", "k", "v", "y3", "e", "z4") if nm in fwd_saved)
+        ctx.save_for_backward(x, y, dxo, dyo, *params, *(fwd_saved[nm] for nm in ctx.saved_names))
+        dx, dy, pgrads = block_backward(x, y, dxo, dyo, params, heads, edge_out, want_params, fwd_stats, fwd_saved)
         return (dx, dy) + tuple(pgrads)
 
     @staticmethod
     def backward(ctx, *u):
         x, y, dxo, dyo, *params = ctx.saved_tensors
+        saved = None
+        if ctx.saved_names:
+            nk = len(ctx.saved_names)
+            params, saved = params[:-nk], dict(zip(ctx.saved_names, params[-nk:]))
         heads, edge_out = ctx.heads, ctx.edge_out
         if all(ui is None for ui in u[2:]) and dxo is not None and _HAND_SECOND_ORDER:
             # the gradient-penalty case (cotangents on dx / dy only): the hand-sequenced second-order pass
             with torch.no_grad():
-                c_x, c_y, c_dxo, c_dyo, cp = block_backward_backward(x, y, dxo, dyo, u[0], u[1], params, heads, edge_out)
+                c_x, c_y, c_dxo, c_dyo, cp = block_backward_backward(x, y, dxo, dyo, u[0], u[1], params, heads, edge_out, saved)
             return (c_x, c_y, c_dxo, c_dyo if (dyo is not None and edge_out) else None, None, None, None, None) + tuple(cp)
         with torch.enable_grad():
             leaves, outs, gouts = _recompute(x, y, dxo, dyo, params, heads, edge_out, True)

@@ -12,7 +12,7 @@ int gemm_tn_tc(const void*, const void*, float*, float*, long long, int, int, in
 using namespace dg;
 
 // run-time options: plain process-wide ints, read on the host at launch time and passed to the kernel by value
-static int g_opts[DG_OPT_COUNT] = {/*DG_OPT_L2_PREFETCH*/ DG_PF_GEMM_TN | DG_PF_ATTN_FWD};
+static int g_opts[DG_OPT_COUNT] = {/*DG_OPT_L2_PREFETCH*/ DG_PF_GEMM_TN | DG_PF_ATTN_FWD, /*DG_OPT_ATTN_BWD*/ 0};
 namespace dg {
 int opt_get(int key) { return key >= 0 && key < DG_OPT_COUNT ? g_opts[key] : 0; }
 }  // namespace dg

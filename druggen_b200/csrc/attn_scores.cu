@@ -16,6 +16,7 @@
 // inside the loop) and are flushed to global with one atomicAdd per element per CTA.
 #include <cuda_bf16.h>
 #include "common.cuh"
+#include "tc_common.cuh"
 #include "../../include/druggen_b200.h"
 
 namespace dg {
@@ -229,6 +230,150 @@ attn_scores_kernel(const float* __restrict__ dg, const float* __restrict__ da_in
   }
 }
 
+
+// ---- backward with the forward's statistics, TMA-fed ("ring" kernel) -----------------------------------------------------
+// The 4-warp kernel above is latency-bound (2.1 TB/s): a warp has 4 rows in flight and stops loading while it reduces them.
+// Here the rows never pass through registers on their way in.  Persistent CTA per SM, 8 warps, no CTA-wide synchronisation
+// at all: warp w owns the key atoms j in [w JC, w JC + JC) of every molecule the CTA visits, so
+//   * k_j, v_j and the dk_j / dv_j accumulators of its JC key atoms live in REGISTERS for a whole molecule (no shared-memory
+//     read-modify-write, no atomics: one plain store per molecule),
+//   * per query atom i the warp's rows (b, i, j0 .. j0+JC-1) are CONTIGUOUS in e / da: one cp.async.bulk each lands them in the
+//     warp's private ring of `depth` stages (mbarrier complete_tx), issued `depth` query atoms ahead by the warp's own lane 0
+//     the moment a stage has been read -- ~150 KB per SM in flight independent of the register budget,
+//   * dq_i partials (sum over the warp's key atoms) leave as one vector reduction per lane (red.global.add.v4.f32).
+// Flags as in attn_scores_kernel<1> (de_bf16 bits: 1 de stored bf16, 2 scores rounded to bf16, 4 da is bf16, 8 de += ).
+constexpr int kRingWarps = 8;
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int JC>
+__global__ void __launch_bounds__(kRingWarps * 32, 1)
+attn_scores_bwd_ring_kernel(const float* __restrict__ dg, const void* __restrict__ da_in, const float* __restrict__ q,
+                            const float* __restrict__ k, const float* __restrict__ v, const float* __restrict__ e, float c,
+                            void* __restrict__ de, float* __restrict__ dq, float* __restrict__ dk, float* __restrict__ dv,
+                            const float* __restrict__ stat_m, const float* __restrict__ stat_inv, const float* __restrict__ g_in,
+                            int B, int N, int depth, int da_row_bytes, int flags) {
+  constexpr int D = 128;
+  extern __shared__ __align__(128) uint8_t ring_raw[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, ch = lane * 4;
+  const int j0 = w * JC, rows = min(JC, N - j0);
+  if (rows <= 0) return;                                  // (no CTA-wide barrier anywhere below)
+  const int stage_bytes = JC * (512 + da_row_bytes);
+  uint8_t* ring = ring_raw + (size_t)w * depth * stage_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring_raw + (size_t)kRingWarps * depth * stage_bytes) + w * depth;
+  if (lane == 0) {
+    for (int s = 0; s < depth; ++s) tc::mbar_init(&full[s], 1);
+    tc::fence_barrier_init();
+  }
+  __syncwarp();
+  const int nb = blockIdx.x < B ? (B - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;      // molecules of this CTA
+  const long long total = (long long)nb * N;                                             // (molecule, query atom) units
+  const uint32_t tx = (uint32_t)rows * (512 + da_row_bytes);
+  auto issue = [&](long long n) {                          // lane 0: unit n -> stage n % depth
+    const int t = (int)(n / N), i = (int)(n - (long long)t * N), s = (int)(n % depth);
+    const long long row = ((long long)(blockIdx.x + t * gridDim.x) * N + i) * N + j0;
+    uint8_t* dst = ring + s * stage_bytes;
+    tc::mbar_expect_tx(&full[s], tx);
+    tc::bulk_g2s(dst, e + row * D, rows * 512, &full[s]);
+    if (da_row_bytes)
+      tc::bulk_g2s(dst + JC * 512, reinterpret_cast<const uint8_t*>(da_in) + row * da_row_bytes, rows * da_row_bytes, &full[s]);
+  };
+  if (lane == 0)
+    for (long long n = 0; n < depth && n < total; ++n) issue(n);
+
+  float4 kj[JC], vj[JC], ak[JC], av[JC];
+  float4 cq, dgi, M, inv, g;
+  auto load_node = [&](long long bi, float4& a0, float4& a1, float4& a2, float4& a3, float4& a4) {
+    a0 = ld4(q + bi); a1 = ld4(dg + bi); a2 = ld4(stat_m + bi); a3 = ld4(stat_inv + bi); a4 = ld4(g_in + bi);
+  };
+  if (total > 0) load_node((long long)blockIdx.x * N * D + ch, cq, dgi, M, inv, g);
+  int t = 0, i = 0, s = 0;
+  uint32_t par = 0;
+  for (long long n = 0; n < total; ++n) {
+    const int b = blockIdx.x + t * gridDim.x;
+    const long long bi = ((long long)b * N + i) * D + ch;
+    if (i == 0) {                                          // new molecule: my key atoms' k, v rows; fresh accumulators
+#pragma unroll
+      for (int r = 0; r < JC; ++r) {
+        const long long o = ((long long)b * N + min(j0 + r, N - 1)) * D + ch;
+        kj[r] = ld4(k + o); vj[r] = ld4(v + o);
+        ak[r] = make_float4(0.f, 0.f, 0.f, 0.f); av[r] = ak[r];
+      }
+    }
+    // the next unit's node vectors are requested before this unit's rows are waited for
+    float4 ncq = cq, ndg = dgi, nM = M, ninv = inv, ng = g;
+    if (n + 1 < total) {
+      const int ni = i + 1 == N ? 0 : i + 1, nt = i + 1 == N ? t + 1 : t;
+      load_node(((long long)(blockIdx.x + nt * gridDim.x) * N + ni) * D + ch, ncq, ndg, nM, ninv, ng);
+    }
+    const float4 cqs = f4s(cq, c);
+    tc::mbar_wait(&full[s], par);
+    const uint8_t* st = ring + s * stage_bytes;
+    const long long row0 = ((long long)b * N + i) * N + j0;
+    float4 sq = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < JC; ++r)
+      if (r < rows) {
+        const float4 ev = *reinterpret_cast<const float4*>(st + r * 512 + lane * 16);
+        float4 din = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (da_row_bytes == 256) {
+          const uint2 rr = *reinterpret_cast<const uint2*>(st + JC * 512 + r * 256 + lane * 8);
+          din = make_float4(__uint_as_float(rr.x << 16), __uint_as_float(rr.x & 0xFFFF0000u), __uint_as_float(rr.y << 16),
+                            __uint_as_float(rr.y & 0xFFFF0000u));
+        } else if (da_row_bytes == 512) {
+          din = *reinterpret_cast<const float4*>(st + JC * 512 + r * 512 + lane * 16);
+        }
+        float4 o;
+#define DG_RGRAD(chn)                                                             \
+  {                                                                               \
+    const float phi = ev.chn * ev.chn + ev.chn;                                   \
+    float ar = cqs.chn * kj[r].chn * phi;                                         \
+    if (flags & 2) ar = __bfloat162float(__float2bfloat16_rn(ar));                \
+    const float p = __expf(ar - M.chn) * inv.chn;                                 \
+    const float da = din.chn + p * dgi.chn * (vj[r].chn - g.chn);                 \
+    o.chn = da * cqs.chn * kj[r].chn * (2.f * ev.chn + 1.f);                      \
+    sq.chn = fmaf(da * phi, kj[r].chn, sq.chn);                                   \
+    ak[r].chn = fmaf(da * phi, cqs.chn, ak[r].chn);                               \
+    av[r].chn = fmaf(p, dgi.chn, av[r].chn);                                      \
+  }
+        DG_RGRAD(x) DG_RGRAD(y) DG_RGRAD(z) DG_RGRAD(w)
+#undef DG_RGRAD
+        const long long off = (row0 + r) * D + ch;
+        if (flags & 1) {
+          *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(de) + off) = make_uint2(pack2_bf16(o.x, o.y), pack2_bf16(o.z, o.w));
+        } else {
+          float* dp = reinterpret_cast<float*>(de) + off;
+          if (flags & 8) {
+            const float4 pr = ld4(dp);
+            o.x += pr.x; o.y += pr.y; o.z += pr.z; o.w += pr.w;
+          }
+          st4(dp, o);
+        }
+      }
+    __syncwarp();                                          // every lane has read the stage
+    if (lane == 0 && n + depth < total) {
+      tc::fence_async_smem();                              // (generic-proxy reads before the async-proxy refill)
+      issue(n + depth);
+    }
+    red_add_v4(dq + bi, c * sq.x, c * sq.y, c * sq.z, c * sq.w);
+    if (i + 1 == N) {                                      // molecule done: my key atoms' dk, dv (exclusive rows: plain stores)
+#pragma unroll
+      for (int r = 0; r < JC; ++r)
+        if (r < rows) {
+          const long long o = ((long long)b * N + j0 + r) * D + ch;
+          st4(dk + o, ak[r]); st4(dv + o, av[r]);
+        }
+      i = 0; ++t;
+    } else {
+      ++i;
+    }
+    if (++s == depth) { s = 0; par ^= 1u; }
+    cq = ncq; dgi = ndg; M = nM; inv = ninv; g = ng;
+  }
+}
+
 // Forward, warp per query atom: one warp owns all N key atoms of its (b, i) -- no shared memory, no barrier; lane = 4
 // channels; rows in batches of kFU with the NEXT batch's loads issued before the current batch is reduced (the exp-heavy
 // reduction of one batch covers the latency of the next).  kSrc 0: scores recomputed from e (a_out optional); 1: bf16 a16.
@@ -355,10 +500,27 @@ extern "C" int dg_attn_scores_bwd(const float* dg_, const float* da_in, const fl
                                   const float* e, float c, const float* stat_m, const float* stat_inv, const float* g,
                                   void* de, float* dq, float* dk, float* dv, int B, int N, int D, int de_bf16, void* stream) {
   if (attn_ok(B, N, D)) return 1;
+  if (stat_m != nullptr && (stat_inv == nullptr || g == nullptr)) return fail("dg_attn_scores_bwd: statistics need stat_inv and g too");
+  if (stat_m != nullptr && N <= kRingWarps * 6 && opt_get(DG_OPT_ATTN_BWD) == 0) {
+    // statistics known and <= 6 key atoms per warp: the TMA-fed ring kernel
+    const int jc = (N + kRingWarps - 1) / kRingWarps;
+    const int JC = jc <= 2 ? 2 : jc <= 4 ? 4 : 6;
+    const int da_row = da_in == nullptr ? 0 : ((de_bf16 & 4) ? 256 : 512);
+    const int stage = JC * (512 + da_row);
+    int depth = (200 * 1024) / (kRingWarps * stage);
+    if (depth > 8) depth = 8;
+    const size_t smem_ring = (size_t)kRingWarps * depth * stage + kRingWarps * 8 * 8;
+    auto kern = JC == 2 ? attn_scores_bwd_ring_kernel<2> : JC == 4 ? attn_scores_bwd_ring_kernel<4> : attn_scores_bwd_ring_kernel<6>;
+    cudaError_t er = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ring);
+    if (er != cudaSuccess) return fail("cudaFuncSetAttribute(attn_scores_bwd_ring): %s", cudaGetErrorString(er));
+    const int grid_r = B < sm_count() ? B : sm_count();
+    kern<<<grid_r, kRingWarps * 32, smem_ring, (cudaStream_t)stream>>>(dg_, da_in, q, k, v, e, c, de, dq, dk, dv, stat_m, stat_inv, g, B, N,
+                                                                      depth, da_row, de_bf16);
+    return check_launch("dg_attn_scores_bwd(ring)");
+  }
   const size_t smem = (size_t)(16 + 2 * N) * D * 4;
   const int irows = attn_irows(B, N, 4);
   dim3 grid((N + irows - 1) / irows, B);
-  if (stat_m != nullptr && (stat_inv == nullptr || g == nullptr)) return fail("dg_attn_scores_bwd: statistics need stat_inv and g too");
   if (smem > 48 * 1024) {
     cudaError_t er = cudaFuncSetAttribute(attn_scores_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (er != cudaSuccess) return fail("cudaFuncSetAttribute: %s", cudaGetErrorString(er));

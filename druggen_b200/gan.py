@@ -16,14 +16,17 @@ import torch
 
 from . import kernels as K
 from . import ops, parallel
+from .block import keep_intermediates
 from .optim import FlatAdamW
 
 
-def gradient_penalty(D, real_node, real_edge, fake_node, fake_edge, batch_size, device):
+def gradient_penalty(D, real_node, real_edge, fake_node, fake_edge, batch_size, device, keep: bool = False):
     """WGAN-GP term, loss.py:4-49 (eps_edge is drawn before eps_node, as there).  The glue around the double backward runs in
     three small kernels: the interpolation straight from the real side's labels when those are what the
     caller holds (``dg_gp_interp``, bit-identical to loss.py:21-26 on the one-hot tensor), and the per-sample norm /
-    ``mean((|g| - 1)^2)`` with its gradient (``dg_gp_penalty``, ``dg_gp_penalty_bwd``: loss.py:42-47)."""
+    ``mean((|g| - 1)^2)`` with its gradient (``dg_gp_penalty``, ``dg_gp_penalty_bwd``: loss.py:42-47).
+    ``keep``: the blocks of this pass may keep their forward intermediates (block.keep_intermediates) for the input-gradient
+    pass and the second-order pass."""
     eps_edge = torch.rand(batch_size, 1, 1, 1, device=device)
     eps_node = torch.rand(batch_size, 1, 1, device=device)
     if torch.is_floating_point(real_node):
@@ -32,7 +35,8 @@ def gradient_penalty(D, real_node, real_edge, fake_node, fake_edge, batch_size, 
     else:
         int_node = K.gp_interp(real_node, fake_node.contiguous(), eps_node).requires_grad_(True)
         int_edge = K.gp_interp(real_edge, fake_edge.contiguous(), eps_edge).requires_grad_(True)
-    logits = D(int_edge, int_node)
+    with keep_intermediates(keep):
+        logits = D(int_edge, int_node)
     g_node, g_edge = torch.autograd.grad(logits, [int_node, int_edge], torch.ones_like(logits),
                                          create_graph=True, retain_graph=True)
     return ops.GradPenalty.apply(g_node, g_edge)
@@ -87,8 +91,15 @@ class GANTrainer:
     """Generator + Discriminator + two AdamW optimizers, stepped as train.py:351-384."""
 
     def __init__(self, G, D, lr_g: float = 1e-5, lr_d: float = 1e-5, betas=(0.9, 0.999), lambda_gp: float = 10.0,
-                 process_group: Optional[object] = None, skip_dead_d_grads: bool = True):
+                 process_group: Optional[object] = None, skip_dead_d_grads: bool = True, sequenced: bool = True):
         self.G, self.D, self.lambda_gp = G, D, lambda_gp
+        # train.py:353-359 builds d_loss = fake + real + lambda * gp and calls ONE backward, so the graphs of all three
+        # Discriminator passes are alive at once.  ``sequenced`` backpropagates the three terms one after the other into the same
+        # .grad buffers (the gradient of a sum is the sum of the gradients; the accumulation order differs in the last fp32 bit):
+        # a pass's activations die before the next pass starts, and the memory that frees lets the blocks of the plain passes keep
+        # their forward intermediates instead of recomputing them in the backward (block.keep_intermediates).  The Generator's
+        # forward inside the D step runs without a graph (loss.py:57-58 detaches its outputs anyway).
+        self.sequenced = sequenced
         # train.py:371-377: g_loss.backward() also fills D's .grad, which nothing consumes (reset_grad, train.py:352,
         # zeroes it before the next D step; d_optimizer is not stepped).  With skip_dead_d_grads the Discriminator is
         # frozen while the G-step graph is built: the gradient still flows THROUGH D to G (dgrad), D's weight-gradient
@@ -110,14 +121,33 @@ class GANTrainer:
         (``load_molecules``' output) or, equivalently, integer labels [B,N,N] / [B,N] -- the 1-byte wire format."""
         bsz, dev = mol_annot.shape[0], mol_annot.device
         self.reset_grad()
-        _, _, d_loss = discriminator_loss(self.G, self.D, drug_adj, drug_annot, mol_adj, mol_annot, bsz, dev, self.lambda_gp)
-        d_val = d_loss.item()
-        d_loss.backward()
+        if self.sequenced:
+            d_val = self._d_step_sequenced(drug_adj, drug_annot, mol_adj, mol_annot, bsz, dev)
+        else:
+            _, _, d_loss = discriminator_loss(self.G, self.D, drug_adj, drug_annot, mol_adj, mol_annot, bsz, dev, self.lambda_gp)
+            d_val = d_loss.item()
+            d_loss.backward()
         self.d_optimizer.step()                 # (all-reduce of the D gradients inside, world > 1)
         self.reset_grad()
-        with (frozen(self.D) if self.skip_dead_d_grads else contextlib.nullcontext()):
-            g_loss = generator_loss(self.G, self.D, mol_adj, mol_annot, bsz)[0]
-        g_val = g_loss.item()
-        g_loss.backward()
+        with keep_intermediates(self.sequenced):
+            with (frozen(self.D) if self.skip_dead_d_grads else contextlib.nullcontext()):
+                g_loss = generator_loss(self.G, self.D, mol_adj, mol_annot, bsz)[0]
+            g_val = g_loss.item()
+            g_loss.backward()
         self.g_optimizer.step()                 # (all-reduce of the G gradients inside, world > 1)
         return d_val, g_val
+
+    def _d_step_sequenced(self, drug_adj, drug_annot, mol_adj, mol_annot, bsz, dev) -> float:
+        """loss.py:52-72 + ``d_loss.backward()`` term by term, in the reference's order of evaluation (real, G, fake, GP: the
+        GP's eps draws are the only random numbers of the step).  Returns d_loss as a Python float (train.py:364)."""
+        with keep_intermediates():
+            real = -self.D(drug_adj, drug_annot).mean()
+            real.backward()
+            with torch.no_grad():
+                _, _, node_sample, edge_sample = self.G(mol_adj, mol_annot)
+            fake = self.D(edge_sample, node_sample).mean()
+            fake.backward()
+        gp = gradient_penalty(self.D, drug_annot, drug_adj, node_sample, edge_sample, bsz, dev, keep=True)
+        d_val = (fake.detach() + real.detach() + self.lambda_gp * gp.detach()).item()     # (the sync of train.py:364, before the
+        (self.lambda_gp * gp).backward()                                                  #  second-order pass is queued)
+        return d_val

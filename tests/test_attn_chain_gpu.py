@@ -195,3 +195,38 @@ def test_block_chain_vs_unfused_attention(cuda_dev, B, N, scores):
     tol = 4e-2 if scores == "bf16" else 1.5e-2
     for i, (a, b) in enumerate(zip(got, ref)):
         assert rel_l2(a, b) < tol, (i, scores, rel_l2(a, b))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,N", [(1, 4), (3, 9), (2, 45), (300, 45), (150, 17), (5, 48)])
+def test_attn_scores_bwd_ring_equals_four_warp_kernel(cuda_dev, B, N):
+    """dg_attn_scores_bwd with the forward's statistics runs the TMA-fed ring kernel (persistent CTAs, a warp owns <= 6 key
+    atoms of every molecule, rows land in per-warp rings through cp.async.bulk); DG_OPT_ATTN_BWD = 1 forces the 4-warp
+    register-staged kernel.  Same arithmetic per row; dq / dk / dv differ in the summation order only.  Every storage variant:
+    da fp32 / bf16 / absent, de fp32 / bf16 / accumulated, scores rounded to bf16."""
+    D, c = 128, 0.25
+    q, k, v = rnd(cuda_dev, B, N, D), rnd(cuda_dev, B, N, D, seed=1), rnd(cuda_dev, B, N, D, seed=2)
+    e, dg, da_in = rnd(cuda_dev, B, N, N, D, seed=3), rnd(cuda_dev, B, N, D, seed=4), rnd(cuda_dev, B, N, N, D, seed=5)
+    _, _, stats = K.attn_scores_fwd(q, k, v, e, c, want_stats=True)
+    acc0 = rnd(cuda_dev, B, N, N, D, seed=6)
+    variants = [dict(da=da_in), dict(da=None), dict(da=da_in.to(torch.bfloat16), de_bf16=True, scores_bf16=True),
+                dict(da=da_in, de_bf16=True), dict(da=da_in, accum=True)]
+
+    def run(opt):
+        K.set_option(_lib.OPT_ATTN_BWD, opt)
+        out = []
+        for vr in variants:
+            acc = acc0.clone() if vr.get("accum") else None
+            out.append(K.attn_scores_bwd(dg, vr["da"], q, k, v, e, c, stats, de_bf16=vr.get("de_bf16", False),
+                                         scores_bf16=vr.get("scores_bf16", False), de_accum=acc))
+        return out
+    try:
+        old = run(1)
+        new = run(0)
+    finally:
+        K.set_option(_lib.OPT_ATTN_BWD, 0)
+    for vi, (o, n_) in enumerate(zip(old, new)):
+        # per-row arithmetic is the same expression (the compiler may contract its FMAs differently in the two kernels)
+        assert rel_l2(n_[0].float(), o[0].float()) < (2e-4 if n_[0].dtype == torch.bfloat16 else 1e-6), ("de", vi)
+        for nm, a_, b_ in zip(("dq", "dk", "dv"), n_[1:], o[1:]):
+            assert rel_l2(a_, b_) < 2e-6, (nm, vi, rel_l2(a_, b_))

@@ -315,3 +315,73 @@ def test_hand_sequenced_second_order_equals_autograd_path(monkeypatch, mode, d, 
         assert (got[2][k] is None) == (ref[2][k] is None), k
         if ref[2][k] is not None and float(ref[2][k].abs().max()) > 0:
             assert rel_l2(got[2][k], ref[2][k]) < tol, k
+
+
+def test_kept_intermediates_equal_recomputation():
+    """block.keep_intermediates(): the checkpointed block keeps what its backward would recompute (the fused chain's outputs).
+    Same launches, same inputs -> outputs and every gradient bit-identical to the recomputing path; and the kept path really
+    skips the chain's second run."""
+    from druggen_b200 import block as blk
+    kernels.set_precision("bf16")
+    d, n, b, heads = 128, 5, 2, 8
+    p = _block_params(dtype=torch.float32, d=d)
+    g = torch.Generator().manual_seed(16)
+    x0, y0 = torch.randn(b, n, d, generator=g), torch.randn(b, n, n, d, generator=g)
+    wx, wy = torch.randn(b, n, d, generator=g), torch.randn(b, n, n, d, generator=g)
+    calls = []
+    be = kernels._test_backend
+    orig = be.attn_edge_fwd
+    be.attn_edge_fwd = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+
+    def run(keep):
+        calls.clear()
+        x, y = x0.clone().requires_grad_(True), y0.clone().requires_grad_(True)
+        pp = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
+        with blk.keep_intermediates(keep):
+            xo, yo = encoder_block(x, y, [pp[k] for k in BLOCK_PARAM_NAMES], heads, True)
+        ((xo * wx).sum() + (yo * wy).sum()).backward()
+        return len(calls), [xo.detach(), yo.detach(), x.grad, y.grad] + [pp[k].grad for k in BLOCK_PARAM_NAMES]
+
+    try:
+        n_re, ref = run(False)
+        n_keep, got = run(True)
+    finally:
+        be.attn_edge_fwd = orig
+    assert (n_re, n_keep) == (2, 1)
+    for i, (a_, b_) in enumerate(zip(got, ref)):
+        assert torch.equal(a_, b_), i
+
+
+@pytest.mark.parametrize("mode,dim", [("fp32", 32), ("bf16", 128)])
+def test_sequenced_d_step_equals_single_backward(mode, dim):
+    """GANTrainer(sequenced=True) backpropagates real, fake and the gradient penalty one after the other (and lets the plain
+    passes keep their intermediates): same losses and the same Discriminator gradients at the optimizer step as train.py's
+    single d_loss.backward(), up to the fp32 accumulation order of the three terms.  (The Generator step then sees D weights
+    that differ in the last bits -- AdamW's first step divides by |g| -- so its gradients are compared loosely.)"""
+    from druggen_b200 import gan
+    kernels.set_precision(mode)
+
+    def run(seq):
+        torch.manual_seed(0)
+        G = dg.Generator("relu", 5, 5, 13, 0.0, dim=dim, depth=2, heads=4, mlp_ratio=3)
+        D = dg.Discriminator("relu", 5, 5, 13, 0.0, dim=dim, depth=2, heads=4, mlp_ratio=3)
+        tr = gan.GANTrainer(G, D, lr_g=1e-3, lr_d=1e-3, sequenced=seq)
+        rec = {}
+        for nm, opt, net in (("d", tr.d_optimizer, D), ("g", tr.g_optimizer, G)):
+            def step(orig=opt.step, nm=nm, net=net):
+                rec[nm] = [None if p.grad is None else p.grad.detach().clone() for p in net.parameters()]
+                return orig()
+            opt.step = step
+        a, x = gan.synthetic_molecules(4, 5, 13, 5, seed=7)
+        da, dx = gan.synthetic_molecules(4, 5, 13, 5, seed=8)
+        torch.manual_seed(5)                      # the gradient penalty's eps draws
+        return tr.step(da, dx, a, x), rec
+
+    (d0, g0), r0 = run(False)
+    (d1, g1), r1 = run(True)
+    assert abs(d0 - d1) <= 1e-5 * max(1.0, abs(d0)) and abs(g0 - g1) <= 1e-4 * max(1.0, abs(g0))
+    for nm, tol in (("d", 1e-6), ("g", 2e-3)):
+        for a_, b_ in zip(r0[nm], r1[nm]):
+            assert (a_ is None) == (b_ is None)
+            if a_ is not None:
+                assert rel_l2(b_, a_) < tol, (nm, rel_l2(b_, a_))

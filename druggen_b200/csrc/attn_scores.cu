@@ -242,13 +242,16 @@ attn_scores_kernel(const float* __restrict__ dg, const float* __restrict__ da_in
 //     the moment a stage has been read -- ~150 KB per SM in flight independent of the register budget,
 //   * dq_i partials (sum over the warp's key atoms) leave as one vector reduction per lane (red.global.add.v4.f32).
 // Flags as in attn_scores_kernel<1> (de_bf16 bits: 1 de stored bf16, 2 scores rounded to bf16, 4 da is bf16, 8 de += ).
-constexpr int kRingWarps = 8;
+// Warps per CTA: 8 with <= 6 key atoms per warp (216 registers; default) or 16 with <= 3.  ncu on the 8-warp form: 148 warp
+// instructions per row, issue slots 46 % used with two warps per scheduler (stalls: fixed-latency dependencies, MUFU / LDS
+// scoreboards) -- yet the 16-warp form measured SLOWER (0.449 vs 0.387 ms per 1.04 M rows): the per-unit work (node vectors, mbarrier
+// wait, refill, dq reduction) is paid per 3 rows instead of per 6.  The kernel is instruction-bound, not HBM-bound (DRAM 38 %).
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int JC>
+template <int JC, int kRingWarps>
 __global__ void __launch_bounds__(kRingWarps * 32, 1)
 attn_scores_bwd_ring_kernel(const float* __restrict__ dg, const void* __restrict__ da_in, const float* __restrict__ q,
                             const float* __restrict__ k, const float* __restrict__ v, const float* __restrict__ e, float c,
@@ -501,21 +504,24 @@ extern "C" int dg_attn_scores_bwd(const float* dg_, const float* da_in, const fl
                                   void* de, float* dq, float* dk, float* dv, int B, int N, int D, int de_bf16, void* stream) {
   if (attn_ok(B, N, D)) return 1;
   if (stat_m != nullptr && (stat_inv == nullptr || g == nullptr)) return fail("dg_attn_scores_bwd: statistics need stat_inv and g too");
-  if (stat_m != nullptr && N <= kRingWarps * 6 && opt_get(DG_OPT_ATTN_BWD) == 0) {
-    // statistics known and <= 6 key atoms per warp: the TMA-fed ring kernel
-    const int jc = (N + kRingWarps - 1) / kRingWarps;
-    const int JC = jc <= 2 ? 2 : jc <= 4 ? 4 : 6;
+  const int ring_opt = opt_get(DG_OPT_ATTN_BWD);
+  if (stat_m != nullptr && N <= 48 && ring_opt != 1) {
+    // statistics known and N <= 48: the TMA-fed ring kernel, 8 warps x <= 6 key atoms (default) or 16 warps x <= 3 (option 2)
+    const int warps = ring_opt == 2 ? 16 : 8;
+    const int jc = (N + warps - 1) / warps;
+    const int JC = warps == 8 ? (jc <= 2 ? 2 : jc <= 4 ? 4 : 6) : jc;
     const int da_row = da_in == nullptr ? 0 : ((de_bf16 & 4) ? 256 : 512);
     const int stage = JC * (512 + da_row);
-    int depth = (200 * 1024) / (kRingWarps * stage);
+    int depth = (200 * 1024) / (warps * stage);
     if (depth > 8) depth = 8;
-    const size_t smem_ring = (size_t)kRingWarps * depth * stage + kRingWarps * 8 * 8;
-    auto kern = JC == 2 ? attn_scores_bwd_ring_kernel<2> : JC == 4 ? attn_scores_bwd_ring_kernel<4> : attn_scores_bwd_ring_kernel<6>;
+    const size_t smem_ring = (size_t)warps * depth * stage + warps * 8 * 8;
+    auto kern = warps == 8 ? (JC == 2 ? attn_scores_bwd_ring_kernel<2, 8> : JC == 4 ? attn_scores_bwd_ring_kernel<4, 8> : attn_scores_bwd_ring_kernel<6, 8>)
+                           : (JC == 1 ? attn_scores_bwd_ring_kernel<1, 16> : JC == 2 ? attn_scores_bwd_ring_kernel<2, 16> : attn_scores_bwd_ring_kernel<3, 16>);
     cudaError_t er = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ring);
     if (er != cudaSuccess) return fail("cudaFuncSetAttribute(attn_scores_bwd_ring): %s", cudaGetErrorString(er));
     const int grid_r = B < sm_count() ? B : sm_count();
-    kern<<<grid_r, kRingWarps * 32, smem_ring, (cudaStream_t)stream>>>(dg_, da_in, q, k, v, e, c, de, dq, dk, dv, stat_m, stat_inv, g, B, N,
-                                                                      depth, da_row, de_bf16);
+    kern<<<grid_r, warps * 32, smem_ring, (cudaStream_t)stream>>>(dg_, da_in, q, k, v, e, c, de, dq, dk, dv, stat_m, stat_inv, g, B, N,
+                                                                 depth, da_row, de_bf16);
     return check_launch("dg_attn_scores_bwd(ring)");
   }
   const size_t smem = (size_t)(16 + 2 * N) * D * 4;

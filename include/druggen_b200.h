@@ -49,7 +49,8 @@ int dg_has_tcgen05(void);
 #define DG_PF_GEMM_TN_WIDE 32 /* dg_gemm_tn with M or N > 128 */
 #define DG_PF_CHAIN_KEEP 64 /* chain kernels: the loader's reads of x carry L2::evict_last (x is re-read as the residual) */
 #define DG_OPT_ATTN_BWD 1    /* dg_attn_scores_bwd with the forward's statistics: 0 (default) = the TMA-fed ring kernel where it applies
-                              * (N <= 48), 1 = always the 4-warp register-staged kernel (A/B switch) */
+                              * (N <= 48; 8 warps x <= 6 key atoms), 2 = the ring kernel with 16 warps x <= 3 key atoms,
+                              * 1 = always the 4-warp register-staged kernel (A/B switches) */
 #define DG_OPT_COUNT 2
 int dg_set_option(int key, int value);
 int dg_get_option(int key);

@@ -223,9 +223,10 @@ def test_attn_scores_bwd_ring_equals_four_warp_kernel(cuda_dev, B, N):
     try:
         old = run(1)
         new = run(0)
+        new16 = run(2)                                              # (the 16-warp form of the ring kernel)
     finally:
         K.set_option(_lib.OPT_ATTN_BWD, 0)
-    for vi, (o, n_) in enumerate(zip(old, new)):
+    for vi, (o, n_) in enumerate(list(zip(old, new)) + list(zip(old, new16))):
         # per-row arithmetic is the same expression (the compiler may contract its FMAs differently in the two kernels)
         assert rel_l2(n_[0].float(), o[0].float()) < (2e-4 if n_[0].dtype == torch.bfloat16 else 1e-6), ("de", vi)
         for nm, a_, b_ in zip(("dq", "dk", "dv"), n_[1:], o[1:]):

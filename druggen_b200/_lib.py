@@ -48,10 +48,14 @@ SIGNATURES = {
     "dg_gp_penalty_bwd": [_P, _P, _P, _P, _I, _LL, _P],
     "dg_readout_argmax": [_P, _P, _P, _P, _P, _I, _LL, _I, _I, _P],
     "dg_adamw_flat": [_P, _P, _P, _P, _P, _I, _F, _F, _F, _F, _F, _P],
+    "dg_to_dense_adj": [_P, _P, _P, _P, _P, _LL, _LL, _I, _I, _P],
+    "dg_narrow_labels": [_P, _P, _LL, _I, _P],
+    "dg_pack_bits": [_P, _I, _P, _P, _LL, _I, _P],
+    "dg_tanimoto_agg": [_P, _P, _LL, _P, _P, _LL, _I, _I, _F, _P, _P, _P],
 }
 INFO_SYMBOLS = ("dg_abi_version", "dg_last_error", "dg_has_tcgen05", "dg_set_option", "dg_get_option", "dg_debug_chain_profile",
                 "dg_label_error")
-ABI_VERSION = 4
+ABI_VERSION = 5
 OPT_L2_PREFETCH = 0
 OPT_ATTN_BWD = 1                                      # 0 = TMA-fed ring kernel where it applies (default), 1 = 4-warp kernel
 PF_ALL, PF_DEFAULT, PF_CHAIN_KEEP = 63, 12, 64        # DG_PF_* bit masks (include/druggen_b200.h)
@@ -339,6 +343,26 @@ def _adamw_flat(self, p, g, m, v, segs, nseg, lr, beta1, beta2, eps, wd):
                _ptr(segs), nseg, lr, beta1, beta2, eps, wd)
 
 
+def _to_dense_adj(self, edge_index, batch, edge_attr, adj, cum):
+    b, n = adj.shape[0], adj.shape[1]
+    self._call("dg_to_dense_adj", ("to_dense_adj", 0, _nbytes(edge_index, batch, edge_attr, adj), "hbm"), _ptr(edge_index), _ptr(batch),
+               _ptr(edge_attr), _ptr(adj), _ptr(cum), edge_index.shape[1], batch.numel(), b, n)
+
+
+def _narrow_labels(self, adj, out, classes):
+    self._call("dg_narrow_labels", ("narrow_labels", 0, _nbytes(adj, out), "hbm"), _ptr(adj), _ptr(out), adj.numel(), classes)
+
+
+def _pack_bits(self, vecs, bits, cnt):
+    self._call("dg_pack_bits", ("pack_bits", 0, _nbytes(vecs, bits), "hbm"), _ptr(vecs), vecs.element_size(), _ptr(bits), _ptr(cnt),
+               vecs.shape[0], vecs.shape[1])
+
+
+def _tanimoto_agg(self, sbits, scnt, gbits, gcnt, agg, p, out_max, out_sum):
+    self._call("dg_tanimoto_agg", ("tanimoto_agg", 0, _nbytes(sbits, gbits), "hbm"), _ptr(sbits), _ptr(scnt), sbits.shape[0], _ptr(gbits),
+               _ptr(gcnt), gbits.shape[0], sbits.shape[1], agg, p, _ptr(out_max), _ptr(out_sum))
+
+
 def _label_error(self, clear=True):
     return self.lib.dg_label_error(int(clear))
 
@@ -352,6 +376,10 @@ CudaBackend.gp_penalty_bwd = _gp_penalty_bwd
 CudaBackend.readout_argmax = _readout_argmax
 CudaBackend.adamw_flat = _adamw_flat
 CudaBackend.label_error = _label_error
+CudaBackend.to_dense_adj = _to_dense_adj
+CudaBackend.narrow_labels = _narrow_labels
+CudaBackend.pack_bits = _pack_bits
+CudaBackend.tanimoto_agg = _tanimoto_agg
 CudaBackend.label2onehot = _label2onehot
 CudaBackend.argmax_last = _argmax_last
 CudaBackend.mlp_fwd = _mlp_fwd

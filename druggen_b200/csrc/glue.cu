@@ -413,3 +413,187 @@ extern "C" int dg_argmax_last(const float* x, long long* out, long long rows, in
   argmax_last_kernel<<<grid_for(rows, 256), 256, 0, (cudaStream_t)stream>>>(x, out, rows, C);
   return check_launch("dg_argmax_last");
 }
+
+// ---- the producer of the path's inputs: load_molecules, src/data/utils.py:128-143 ---------------
+// torch_geometric.utils.to_dense_adj (PyG 2.2.0, the reference's pinned dependency; not vendored) restated:
+//   num_nodes[b] = #{v : batch[v] = b};  cum = exclusive prefix sum;  for every edge (s, t) with attribute a (1 when absent):
+//   adj[batch[s], s - cum[batch[s]], t - cum[batch[t]]] += a, edges whose local index reaches max_num_nodes dropped.
+// Integer scatter-add into [B,N,N] int32 (duplicate edges add, as PyG's scatter(reduce='add')), then narrowed to the 1-byte label
+// wire format with the class-range check label2onehot's scatter_ would make.  HBM-bound integer work: one pass over the edge list.
+namespace dg {
+
+__global__ void count_nodes_kernel(const long long* __restrict__ batch, unsigned long long* __restrict__ counts, long long V, int B) {
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (long long)gridDim.x * blockDim.x) {
+    const long long b = batch[v];
+    if (b < 0 || b >= B) atomicOr(&g_label_error, 2);
+    else atomicAdd(&counts[b + 1], 1ull);
+  }
+}
+// in-place inclusive scan of counts[1..B] (counts[0] = 0) -> cum[b] = first node of graph b; one block, B is a batch size
+__global__ void __launch_bounds__(1024) scan_nodes_kernel(unsigned long long* __restrict__ cum, int B) {
+  __shared__ unsigned long long part[1024];
+  const int per = (B + 1023) / 1024, lo = 1 + threadIdx.x * per, hi = min(B + 1, lo + per);
+  unsigned long long s = 0;
+  for (int i = lo; i < hi; ++i) s += cum[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long run = 0;
+    for (int i = 0; i < 1024; ++i) { const unsigned long long t = part[i]; part[i] = run; run += t; }
+  }
+  __syncthreads();
+  unsigned long long run = part[threadIdx.x];
+  for (int i = lo; i < hi; ++i) { run += cum[i]; cum[i] = run; }
+}
+__global__ void dense_adj_kernel(const long long* __restrict__ edge_index, const long long* __restrict__ batch,
+                                 const long long* __restrict__ edge_attr, const unsigned long long* __restrict__ cum,
+                                 int* __restrict__ adj, long long E, long long V, int B, int N) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (long long)gridDim.x * blockDim.x) {
+    const long long s = edge_index[e], t = edge_index[E + e];
+    if (s < 0 || s >= V || t < 0 || t >= V) { atomicOr(&g_label_error, 2); continue; }
+    const long long bs = batch[s], bt = batch[t];
+    if (bs < 0 || bs >= B || bt < 0 || bt >= B) continue;          // (flagged by count_nodes_kernel)
+    const long long i1 = s - (long long)cum[bs], i2 = t - (long long)cum[bt];
+    if (i1 >= N || i2 >= N) continue;                                // to_dense_adj's max_num_nodes mask
+    atomicAdd(&adj[(bs * N + i1) * N + i2], edge_attr ? (int)edge_attr[e] : 1);
+  }
+}
+__global__ void narrow_labels_kernel(const int* __restrict__ adj, unsigned char* __restrict__ out, long long n, int classes) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int a = adj[i];
+    if (a < 0 || a >= classes) atomicOr(&g_label_error, 1);          // label2onehot's scatter_ would raise on it
+    out[i] = (unsigned char)a;
+  }
+}
+
+// ---- SNN / internal-diversity metric: average_agg_tanimoto, src/util/utils.py:566-611 ------------------------
+// The reference multiplies 0/1 fingerprint matrices as fp32 (torch.mm) to count common bits.  Here fingerprints are bit-packed
+// (F/64 words of 64 bits), tp = popcount(x & y) -- exact integers, as the fp32 GEMM's are below 2^24 -- and
+// jac = tp / (|x| + |y| - tp) is ONE IEEE fp32 division of the same integers (0/0 -> 1 as the reference's NaN patch): bit-exact.
+// Thread = one generated fingerprint in registers; the stock fingerprints pass through shared memory as broadcast reads.
+constexpr int kTanWords = 32;          // up to 2048-bit fingerprints
+constexpr int kTanTile = 128;          // stock fingerprints per shared-memory tile
+
+template <typename T>
+__global__ void pack_bits_kernel(const T* __restrict__ vecs, unsigned long long* __restrict__ bits, int* __restrict__ cnt,
+                                 long long rows, int F, int words) {
+  const long long total = rows * words;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / words;
+    const int w = (int)(i - r * words);
+    unsigned long long word = 0;
+    const int nb = min(64, F - w * 64);
+    for (int k = 0; k < nb; ++k) word |= (unsigned long long)(vecs[r * F + w * 64 + k] != (T)0) << k;
+    bits[i] = word;
+    if (word) atomicAdd(&cnt[r], __popcll(word));
+  }
+}
+
+template <int W>
+__global__ void __launch_bounds__(128) tanimoto_agg_kernel(const unsigned long long* __restrict__ stock, const int* __restrict__ stock_cnt,
+                                                           long long S, const unsigned long long* __restrict__ gen,
+                                                           const int* __restrict__ gen_cnt, long long G, int agg, float p,
+                                                           float* __restrict__ out_max, double* __restrict__ out_sum, int s_chunk) {
+  __shared__ unsigned long long sS[kTanTile * W];
+  __shared__ int sC[kTanTile];
+  const long long g = (long long)blockIdx.x * 128 + threadIdx.x;
+  unsigned long long y[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) y[w] = g < G ? gen[g * W + w] : 0ull;
+  const int yc = g < G ? gen_cnt[g] : 0;
+  const long long s_lo = (long long)blockIdx.y * s_chunk, s_hi = min(S, s_lo + s_chunk);
+  float best = 0.f;                                          // (agg_tanimoto starts from zeros: utils.py:584)
+  double sum = 0.0;
+  for (long long s0 = s_lo; s0 < s_hi; s0 += kTanTile) {
+    const int ns = (int)min((long long)kTanTile, s_hi - s0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < ns * W; i += 128) sS[i] = stock[s0 * W + i];
+    for (int i = threadIdx.x; i < ns; i += 128) sC[i] = stock_cnt[s0 + i];
+    __syncthreads();
+    float part = 0.f;
+    for (int s = 0; s < ns; ++s) {
+      int tp = 0;
+#pragma unroll
+      for (int w = 0; w < W; ++w) tp += __popcll(sS[s * W + w] & y[w]);
+      const int den = sC[s] + yc - tp;
+      float jac = den == 0 ? 1.f : __fdiv_rn((float)tp, (float)den);      // utils.py:596-597 (NaN -> 1)
+      if (agg == 0) best = fmaxf(best, jac);
+      else part += (p == 1.f ? jac : powf(jac, p));                          // utils.py:598-599, :604
+    }
+    sum += (double)part;
+  }
+  if (g < G) {
+    if (agg == 0) atomicMax(reinterpret_cast<int*>(out_max) + g, __float_as_int(best));   // (non-negative floats order as ints)
+    else atomicAdd(out_sum + g, sum);
+  }
+}
+
+}  // namespace dg
+
+extern "C" int dg_to_dense_adj(const long long* edge_index, const long long* batch, const long long* edge_attr, int* adj,
+                               unsigned long long* cum_nodes, long long E, long long V, int B, int N, void* stream) {
+  if (E < 0 || V < 0 || B <= 0 || N <= 0) return fail("dg_to_dense_adj: bad shape E=%lld V=%lld B=%d N=%d", E, V, B, N);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cudaMemsetAsync(adj, 0, (size_t)B * N * N * sizeof(int), s) != cudaSuccess ||
+      cudaMemsetAsync(cum_nodes, 0, (size_t)(B + 1) * sizeof(unsigned long long), s) != cudaSuccess)
+    return fail("dg_to_dense_adj: memset failed");
+  if (V > 0) count_nodes_kernel<<<grid_for(V, 256), 256, 0, s>>>(batch, cum_nodes, V, B);
+  scan_nodes_kernel<<<1, 1024, 0, s>>>(cum_nodes, B);
+  if (E > 0) dense_adj_kernel<<<grid_for(E, 256), 256, 0, s>>>(edge_index, batch, edge_attr, cum_nodes, adj, E, V, B, N);
+  return check_launch("dg_to_dense_adj");
+}
+
+extern "C" int dg_narrow_labels(const int* adj, unsigned char* out, long long n, int classes, void* stream) {
+  if (n < 0 || classes <= 0 || classes > 256) return fail("dg_narrow_labels: bad shape n=%lld classes=%d", n, classes);
+  if (n == 0) return 0;
+  narrow_labels_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(adj, out, n, classes);
+  return check_launch("dg_narrow_labels");
+}
+
+extern "C" int dg_pack_bits(const void* vecs, int elem_bytes, unsigned long long* bits, int* popcounts, long long rows, int F,
+                            void* stream) {
+  if (rows < 0 || F <= 0) return fail("dg_pack_bits: bad shape rows=%lld F=%d", rows, F);
+  if (elem_bytes != 1 && elem_bytes != 4) return fail("dg_pack_bits: elements are uint8 or float32 (elem_bytes=%d)", elem_bytes);
+  if (rows == 0) return 0;
+  const int words = (F + 63) / 64;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cudaMemsetAsync(popcounts, 0, (size_t)rows * sizeof(int), s) != cudaSuccess) return fail("dg_pack_bits: memset failed");
+  if (elem_bytes == 1)
+    pack_bits_kernel<unsigned char><<<grid_for(rows * words, 256), 256, 0, s>>>((const unsigned char*)vecs, bits, popcounts, rows, F, words);
+  else
+    pack_bits_kernel<float><<<grid_for(rows * words, 256), 256, 0, s>>>((const float*)vecs, bits, popcounts, rows, F, words);
+  return check_launch("dg_pack_bits");
+}
+
+extern "C" int dg_tanimoto_agg(const unsigned long long* stock_bits, const int* stock_cnt, long long S,
+                               const unsigned long long* gen_bits, const int* gen_cnt, long long G, int words, int agg, float p,
+                               float* out_max, double* out_sum, void* stream) {
+  if (S < 0 || G < 0 || words <= 0 || words > kTanWords) return fail("dg_tanimoto_agg: bad shape S=%lld G=%lld words=%d (<= %d)", S, G, words, kTanWords);
+  if (agg != 0 && agg != 1) return fail("dg_tanimoto_agg: agg is 0 (max) or 1 (sum)");
+  if ((agg == 0 ? (void*)out_max : (void*)out_sum) == nullptr) return fail("dg_tanimoto_agg: the output of this aggregation is NULL");
+  if (S == 0 || G == 0) return 0;
+  // enough CTAs for the machine: split the stock set when there are few generated fingerprints
+  const long long gx = (G + 127) / 128;
+  long long sy = (2LL * sm_count() + gx - 1) / gx;
+  const long long max_sy = (S + kTanTile - 1) / kTanTile;
+  if (sy > max_sy) sy = max_sy;
+  if (sy < 1) sy = 1;
+  if (sy > 65535) sy = 65535;
+  long long chunk = (S + sy - 1) / sy;
+  chunk = (chunk + kTanTile - 1) / kTanTile * kTanTile;
+  sy = (S + chunk - 1) / chunk;
+  dim3 grid((unsigned)gx, (unsigned)sy);
+  cudaStream_t s = (cudaStream_t)stream;
+#define DG_TAN(Wn) tanimoto_agg_kernel<Wn><<<grid, 128, 0, s>>>(stock_bits, stock_cnt, S, gen_bits, gen_cnt, G, agg, p, out_max, out_sum, (int)chunk)
+  switch (words) {
+    case 1: DG_TAN(1); break;
+    case 2: DG_TAN(2); break;
+    case 4: DG_TAN(4); break;
+    case 8: DG_TAN(8); break;
+    case 16: DG_TAN(16); break;
+    case 32: DG_TAN(32); break;
+    default: return fail("dg_tanimoto_agg: words must be a power of two <= %d (pad the fingerprints with zero words), got %d", kTanWords, words);
+  }
+#undef DG_TAN
+  return check_launch("dg_tanimoto_agg");
+}

@@ -421,7 +421,10 @@ def _chk_labels(labels):
 def check_labels() -> None:
     """Raise if any label-consuming launch since the last check met a label outside [0, classes) -- where the reference's
     ``scatter_`` (src/data/utils.py:21) raises.  Synchronises with the device."""
-    if _test_backend is None and _be().label_error(True) == 1:
+    flag = _be().label_error(True) if _test_backend is None else 0
+    if flag > 0 and flag & 2:
+        raise RuntimeError("druggen_b200: node or graph index out of range in to_dense_adj (edge_index / batch)")
+    if flag > 0:
         raise RuntimeError("druggen_b200: label outside [0, classes) (the reference's label2onehot scatter_ raises here)")
 
 
@@ -438,6 +441,82 @@ def label2onehot(labels, dim: int, device=None, validate: bool = True):
         if validate:
             check_labels()
     return out
+
+
+def to_dense_adj(edge_index, batch, edge_attr=None, max_num_nodes: int = None, batch_size: int = None):
+    """torch_geometric.utils.to_dense_adj (PyG 2.2.0) for integer edge attributes, as load_molecules calls it
+    (src/data/utils.py:130-135): -> int32 [B, N, N].  ``batch_size`` / ``max_num_nodes`` default to PyG's (batch.max() + 1 and
+    the largest graph: both need a device sync; load_molecules passes them)."""
+    _chk_ints(edge_index, batch, edge_attr)
+    if batch_size is None:
+        batch_size = int(batch.max()) + 1 if batch.numel() else 1
+    if max_num_nodes is None:
+        max_num_nodes = int(torch.bincount(batch, minlength=batch_size).max()) if batch.numel() else 0
+    adj = torch.empty(batch_size, max_num_nodes, max_num_nodes, dtype=torch.int32, device=batch.device)
+    cum = torch.empty(batch_size + 1, dtype=torch.int64, device=batch.device)
+    if adj.numel():
+        _be().to_dense_adj(edge_index.contiguous(), batch.contiguous(), None if edge_attr is None else edge_attr.contiguous(), adj, cum)
+    return adj
+
+
+def _chk_ints(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if _test_backend is None and not t.is_cuda:
+            raise RuntimeError("druggen_b200 kernels run on CUDA tensors only (no CPU fallback)")
+        if t.dtype != torch.int64:
+            raise RuntimeError(f"edge_index / batch / edge_attr are int64 (PyG's layout), got {t.dtype}")
+
+
+def narrow_labels(adj, classes: int, validate: bool = True):
+    """int32 labels -> uint8 (the 1-byte wire format); values outside [0, classes) raise like label2onehot's scatter_."""
+    if _test_backend is None and not adj.is_cuda:
+        raise RuntimeError("druggen_b200 kernels run on CUDA tensors only (no CPU fallback)")
+    assert adj.dtype == torch.int32 and adj.is_contiguous()
+    out = torch.empty(adj.shape, dtype=torch.uint8, device=adj.device)
+    if adj.numel():
+        _be().narrow_labels(adj, out, classes)
+        if validate:
+            check_labels()
+    return out
+
+
+def pack_bits(vecs):
+    """0/1 fingerprint matrix [rows, F] (uint8 or float32; non-zero = set) -> (bits uint64-as-int64 [rows, W], popcounts int32 [rows]),
+    W = F / 64 rounded up to a power of two (zero words appended)."""
+    if _test_backend is None and not vecs.is_cuda:
+        raise RuntimeError("druggen_b200 kernels run on CUDA tensors only (no CPU fallback)")
+    assert vecs.dim() == 2 and vecs.dtype in (torch.uint8, torch.float32) and vecs.is_contiguous(), (vecs.shape, vecs.dtype)
+    rows, f = vecs.shape
+    w0 = (f + 63) // 64
+    w = 1
+    while w < w0:
+        w *= 2
+    if w > 32:
+        raise RuntimeError(f"fingerprints of {f} bits exceed the kernel's 2048")
+    bits = torch.zeros(rows, w, dtype=torch.int64, device=vecs.device)
+    cnt = torch.zeros(rows, dtype=torch.int32, device=vecs.device)
+    if rows:
+        if w == w0:
+            _be().pack_bits(vecs, bits, cnt)
+        else:                                   # (packed at the natural width, then copied into the zero-padded rows)
+            tight = torch.zeros(rows, w0, dtype=torch.int64, device=vecs.device)
+            _be().pack_bits(vecs, tight, cnt)
+            bits[:, :w0] = tight
+    return bits, cnt
+
+
+def tanimoto_agg(stock, gen, agg: str = "max", p: float = 1.0):
+    """stock / gen = ``pack_bits`` results.  agg 'max' -> float32 [G] max_s jac(s, g) (>= 0);  agg 'sum' -> float64 [G] sum_s jac^p."""
+    (sb, sc), (gb, gc) = stock, gen
+    assert sb.shape[1] == gb.shape[1], "fingerprint widths differ"
+    g = gb.shape[0]
+    out_max = torch.zeros(g, dtype=torch.float32, device=gb.device) if agg == "max" else None
+    out_sum = torch.zeros(g, dtype=torch.float64, device=gb.device) if agg != "max" else None
+    if g and sb.shape[0]:
+        _be().tanimoto_agg(sb, sc, gb, gc, 0 if agg == "max" else 1, float(p), out_max, out_sum)
+    return out_max if agg == "max" else out_sum
 
 
 def argmax_last(t):

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DG_ABI_VERSION 4
+#define DG_ABI_VERSION 5
 #define DG_PREC_FP32 0
 #define DG_PREC_BF16 1
 #define DG_PREC_BF16X3 2
@@ -214,6 +214,30 @@ int dg_readout_argmax(const float* x, const float* w, const float* bias, float* 
  * inactive tensors (gradient None) are untouched, exactly as torch skips them. */
 int dg_adamw_flat(float* p, const float* g, float* m, float* v, const void* segs, int nseg, float lr, float beta1, float beta2,
                   float eps, float weight_decay, void* stream);
+
+/* ---- the producer of the path's inputs and the evaluation metric ------------------------ */
+/* load_molecules, src/data/utils.py:128-143: torch_geometric.utils.to_dense_adj (PyG 2.2.0, the reference's pinned dependency)
+ * on the device.  edge_index [2,E] int64 (row 0 sources, row 1 targets, global node ids), batch [V] int64 (graph of each node,
+ * sorted), edge_attr [E] int64 bond labels or NULL (ones) -> adj [B,N,N] int32, zeroed here: adj[batch[s], s - first(batch[s]),
+ * t - first(batch[t])] += attr, edges whose local index is >= N dropped (max_num_nodes), duplicate edges add.
+ * cum_nodes: workspace of (B + 1) uint64 (receives the first node id of every graph).  A node or graph id out of range raises the
+ * dg_label_error() flag (bit 2). */
+int dg_to_dense_adj(const long long* edge_index, const long long* batch, const long long* edge_attr, int* adj,
+                    unsigned long long* cum_nodes, long long E, long long V, int B, int N, void* stream);
+/* int32 labels -> the 1-byte label wire format (input of dg_embed_labels_fwd / dg_label2onehot / dg_gp_interp); a value outside
+ * [0, classes) raises the dg_label_error() flag, as label2onehot's scatter_ (src/data/utils.py:21) would raise on it. */
+int dg_narrow_labels(const int* adj, unsigned char* out, long long n, int classes, void* stream);
+/* average_agg_tanimoto, src/util/utils.py:566-611, on bit-packed fingerprints.  dg_pack_bits: vecs [rows,F] of uint8 (elem_bytes 1)
+ * or float32 (elem_bytes 4), non-zero = bit set -> bits [rows, ceil(F/64)] uint64 (bit k of word w = element 64 w + k) and
+ * popcounts [rows] int32. */
+int dg_pack_bits(const void* vecs, int elem_bytes, unsigned long long* bits, int* popcounts, long long rows, int F, void* stream);
+/* For every generated fingerprint g: jac(s,g) = |s & g| / (|s| + |g| - |s & g|) over all S stock fingerprints (0/0 -> 1, utils.py:597;
+ * the division is one IEEE fp32 division of exact integers: bit-equal to the reference's fp32 GEMM + division), aggregated as
+ * agg 0: out_max[g] = max(out_max[g], max_s jac)      (float32 [G]; start from zeros, utils.py:584)
+ * agg 1: out_sum[g] += sum_s jac^p                    (float64 [G]; the caller divides by the count, utils.py:604-607)
+ * words = uint64 words per fingerprint: a power of two <= 32 (pad with zero words). */
+int dg_tanimoto_agg(const unsigned long long* stock_bits, const int* stock_cnt, long long S, const unsigned long long* gen_bits,
+                    const int* gen_cnt, long long G, int words, int agg, float p, float* out_max, double* out_sum, void* stream);
 
 /* debug: with a device buffer of 148*64 int64 set, every chain-kernel launch (dg_mlp_*, dg_attn_edge_fwd) writes
  * per-CTA phase cycle counters [CTA][4 roles][16 phases] (tools/chain_profile.py); NULL switches it off. */

@@ -295,3 +295,37 @@ class EmulBackend:
 
     def label_error(self, clear=True):
         return 0
+
+    # ---- producer of the inputs / metric (restated through the oracle: csrc/glue.cu)
+    def to_dense_adj(self, edge_index, batch, edge_attr, adj, cum):
+        from oracle import data_oracle as orc
+        b, n = adj.shape[0], adj.shape[1]
+        adj.copy_(torch.from_numpy(orc.to_dense_adj(edge_index.numpy(), batch.numpy(), None if edge_attr is None else edge_attr.numpy(),
+                                                    max_num_nodes=n, batch_size=b)).to(adj.dtype))
+
+    def narrow_labels(self, adj, out, classes):
+        out.copy_(adj.to(torch.uint8))
+
+    def pack_bits(self, vecs, bits, cnt):
+        import numpy as np
+        v = (vecs.numpy() != 0)
+        rows, f = v.shape
+        w = bits.shape[1]
+        pad = np.zeros((rows, w * 64), bool)
+        pad[:, :f] = v
+        words = (pad.reshape(rows, w, 64).astype(np.uint64) << np.arange(64, dtype=np.uint64)).sum(-1, dtype=np.uint64)
+        bits.copy_(torch.from_numpy(words.view(np.int64)))
+        cnt.copy_(torch.from_numpy(v.sum(1).astype(np.int32)))
+
+    def tanimoto_agg(self, sbits, scnt, gbits, gcnt, agg, p, out_max, out_sum):
+        import numpy as np
+        unpack = lambda b: ((b.numpy().view(np.uint64)[:, :, None] >> np.arange(64, dtype=np.uint64)) & np.uint64(1)).reshape(b.shape[0], -1).astype(np.float32)  # noqa: E731
+        xs, yg = unpack(sbits), unpack(gbits)
+        tp = xs @ yg.T
+        with np.errstate(invalid="ignore", divide="ignore"):
+            jac = tp / (xs.sum(1, keepdims=True) + yg.sum(1)[None, :] - tp)
+        jac[np.isnan(jac)] = 1
+        if agg == 0:
+            out_max.copy_(torch.maximum(out_max, torch.from_numpy(jac.max(0))))
+        else:
+            out_sum.add_(torch.from_numpy((jac.astype(np.float64) ** p).sum(0)))

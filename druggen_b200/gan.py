@@ -115,6 +115,20 @@ class GANTrainer:
         self.g_optimizer.zero_grad(set_to_none=True)
         self.d_optimizer.zero_grad(set_to_none=True)
 
+    # ---- checkpoint I/O, train.py:250-263: the reference's file names and contents (plain state_dicts with the reference's keys),
+    # so checkpoints move between the two implementations in both directions
+    def save_model(self, model_directory, idx, i):
+        import os
+        torch.save(self.G.state_dict(), os.path.join(model_directory, '{}-{}-G.ckpt'.format(idx + 1, i + 1)))
+        torch.save(self.D.state_dict(), os.path.join(model_directory, '{}-{}-D.ckpt'.format(idx + 1, i + 1)))
+
+    def restore_model(self, epoch, iteration, model_directory):
+        import os
+        for net, tag in ((self.G, "G"), (self.D, "D")):
+            path = os.path.join(model_directory, '{}-{}-{}.ckpt'.format(epoch, iteration, tag))
+            net.load_state_dict(torch.load(path, map_location=lambda storage, loc: storage))
+        # the flat AdamW buckets alias the parameters: load_state_dict copies in place, nothing to rebuild
+
     def step(self, drug_adj, drug_annot, mol_adj, mol_annot):
         """One iteration on this rank's shard; returns (d_loss, g_loss) as Python floats
         (the two ``.item()`` syncs of train.py:364,380 included).  The four tensors are the reference's fp32 one-hots

@@ -37,6 +37,43 @@ class _GraphNet(nn.Module):
         self.TransformerEncoder = TransformerEncoder(dim=dim, depth=depth, heads=heads, act=act,
                                                      mlp_ratio=mlp_ratio, drop_rate=dropout)
 
+    def _on_kernels(self, x) -> bool:
+        return (x.is_cuda or K._test_backend is not None) and x.dtype == torch.float32 and not (self.training and self.dropout > 0)
+
+    def _linear(self, x, layer, act: bool = False):
+        """``layer(x)`` (then the activation) on the twice-differentiable row-GEMM primitive (ops.linear): the small Linears
+        either side of the encoder (K, N = 5 / 13 / 16 / 1 ...) are padded to multiples of 4 with zero rows / columns -- bit-for-bit
+        neutral -- and a ReLU rides in the GEMM store.  No cuBLAS / cutlass launch is left on the path.  (The primitives remember
+        the precision mode of their forward: every derivative of these layers, the gradient penalty's included, is fp32 too.)"""
+        w, b = layer.weight, layer.bias
+        n, k = w.shape
+        pk, pn = (-k) % 4, (-n) % 4
+        if pk:
+            x, w = nn.functional.pad(x, (0, pk)), nn.functional.pad(w, (0, pk))
+        if pn:
+            w, b = nn.functional.pad(w, (0, 0, 0, pn)), nn.functional.pad(b, (0, pn))
+        relu = act and isinstance(self._act, nn.ReLU)
+        with K.precision("fp32"):          # a few MFLOP per molecule: fp32 FMA in every precision mode (as the reference's sgemm)
+            y = ops.linear(x.contiguous(), w, b, relu=relu)
+        if pn:
+            y = y[..., :n]
+        return self._act(y) if act and not relu else y
+
+    def _seq(self, x, seq):
+        """An ``nn.Sequential`` of Linear / activation / Dropout(p = 0 or eval) layers through ``_linear``."""
+        mods = list(seq)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, nn.Linear):
+                act = i + 1 < len(mods) and mods[i + 1] is self._act
+                x = self._linear(x, m, act)
+                i += 2 if act else 1
+            else:
+                x = m(x)
+                i += 1
+        return x
+
     def _embed(self, z_e, z_n):
         """Prologue + encoder.  ``z_e`` / ``z_n`` are the reference's fp32 tensors [B,N,N,edges] / [B,N,nodes], or -- the
         label wire format -- integer (uint8 / int64) labels [B,N,N] / [B,N] of one-hot molecules:
@@ -52,7 +89,7 @@ class _GraphNet(nn.Module):
                 return self.TransformerEncoder(node, edge)
             z_e = K.label2onehot(z_e, self.edges, validate=False)
             z_n = K.label2onehot(z_n, self.nodes, validate=False)
-        node = self.node_layers(z_n)                       # models.py:91
+        node = self._seq(z_n, self.node_layers) if self._on_kernels(z_n) else self.node_layers(z_n)     # models.py:91
         if (isinstance(self._act, nn.ReLU) and (z_e.is_cuda or K._test_backend is not None) and not (self.training and self.dropout > 0)
                 and self.dim % 4 == 0):
             # dense inputs (generated / interpolated molecules): both prologue Linears with their ReLU in the GEMM store
@@ -80,6 +117,8 @@ class Generator(_GraphNet):
 
     def forward(self, z_e, z_n):
         node, edge = self._embed(z_e, z_n)
+        if self._on_kernels(node):                         # models.py:100-101 on the row-GEMM primitive (N = 13 / 5 padded to 16 / 8)
+            return node, edge, self._linear(node, self.readout_n), self._linear(edge, self.readout_e)
         return node, edge, self.readout_n(node), self.readout_e(edge)
 
     @torch.no_grad()
@@ -109,4 +148,5 @@ class Discriminator(_GraphNet):
 
     def forward(self, z_e, z_n):
         node, _ = self._embed(z_e, z_n)
-        return self.node_mlp(node.reshape(z_n.shape[0], -1))
+        flat = node.reshape(z_n.shape[0], -1)
+        return self._seq(flat, self.node_mlp) if self._on_kernels(flat) else self.node_mlp(flat)          # models.py:207-208

@@ -29,6 +29,7 @@ class RowsGemm(Function):
     def forward(ctx, a, w, w_is_nk):
         ctx.save_for_backward(a, w)
         ctx.w_is_nk = w_is_nk
+        ctx.prec = K.get_precision()       # the derivatives of a contraction run in the precision mode its forward ran in
         return K.rows_gemm(a, w, w_is_nk)
 
     @staticmethod
@@ -36,10 +37,11 @@ class RowsGemm(Function):
         a, w = ctx.saved_tensors
         dout = _c(dout)
         da = dw = None
-        if ctx.needs_input_grad[0]:
-            da = RowsGemm.apply(dout, w, not ctx.w_is_nk)
-        if ctx.needs_input_grad[1]:
-            dw = GemmTN.apply(dout, a) if ctx.w_is_nk else GemmTN.apply(a, dout)
+        with K.precision(ctx.prec):
+            if ctx.needs_input_grad[0]:
+                da = RowsGemm.apply(dout, w, not ctx.w_is_nk)
+            if ctx.needs_input_grad[1]:
+                dw = GemmTN.apply(dout, a) if ctx.w_is_nk else GemmTN.apply(a, dout)
         return da, dw, None
 
 
@@ -49,6 +51,7 @@ class GemmTN(Function):
     @staticmethod
     def forward(ctx, a, b):
         ctx.save_for_backward(a, b)
+        ctx.prec = K.get_precision()
         return K.gemm_tn(a, b)
 
     @staticmethod
@@ -56,10 +59,11 @@ class GemmTN(Function):
         a, b = ctx.saved_tensors
         dout = _c(dout)
         da = db = None
-        if ctx.needs_input_grad[0]:
-            da = RowsGemm.apply(b, dout, True)
-        if ctx.needs_input_grad[1]:
-            db = RowsGemm.apply(a, dout, False)
+        with K.precision(ctx.prec):
+            if ctx.needs_input_grad[0]:
+                da = RowsGemm.apply(b, dout, True)
+            if ctx.needs_input_grad[1]:
+                db = RowsGemm.apply(a, dout, False)
         return da, db
 
 
@@ -95,6 +99,7 @@ class Linear(Function):
     def forward(ctx, x, w, b, relu):
         y = K.rows_gemm(x, w, True, b, relu)
         ctx.relu = relu
+        ctx.prec = K.get_precision()
         ctx.save_for_backward(x, w, y if relu else None)
         return y
 
@@ -102,11 +107,12 @@ class Linear(Function):
     def backward(ctx, dy):
         x, w, y = ctx.saved_tensors
         dy = _c(dy)
-        if ctx.relu:
-            dy = GateMul.apply(dy, y)
-        dx = RowsGemm.apply(dy, w, False) if ctx.needs_input_grad[0] else None
-        dw = GemmTN.apply(dy, x) if ctx.needs_input_grad[1] else None
-        db = ColSum.apply(dy) if ctx.needs_input_grad[2] else None
+        with K.precision(ctx.prec):
+            if ctx.relu:
+                dy = GateMul.apply(dy, y)
+            dx = RowsGemm.apply(dy, w, False) if ctx.needs_input_grad[0] else None
+            dw = GemmTN.apply(dy, x) if ctx.needs_input_grad[1] else None
+            db = ColSum.apply(dy) if ctx.needs_input_grad[2] else None
         return dx, dw, db, None
 
 

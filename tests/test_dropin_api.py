@@ -43,3 +43,31 @@ def test_state_dict_keys_and_attributes_match_reference_checkpoint():
     assert G.features == 9 * 9 * 5 + 9 * 13 and D.node_features == 9 * 128
     for act in ("relu", "leaky", "sigmoid", "tanh"):
         dg.Discriminator(act, 9, 5, 13, 0.0, dim=128, depth=1, heads=8, mlp_ratio=3)
+
+
+def test_trainer_checkpoint_files_follow_the_reference(tmp_path):
+    """GANTrainer.save_model / restore_model (train.py:250-263): the reference's file names, plain state_dicts with the reference's
+    keys; restoring lands in the flat AdamW buckets the parameters alias."""
+    import torch
+    import druggen_b200 as dg
+    from druggen_b200 import gan, kernels
+    from emul_kernels import EmulBackend
+    kernels._install_backend_for_tests(EmulBackend())
+    try:
+        torch.manual_seed(0)
+        mk = lambda cls: cls("relu", 5, 5, 13, 0.0, dim=32, depth=1, heads=4, mlp_ratio=3)  # noqa: E731
+        tr = gan.GANTrainer(mk(dg.Generator), mk(dg.Discriminator))
+        tr.save_model(str(tmp_path), 2, 9)
+        assert sorted(p.name for p in tmp_path.iterdir()) == ["3-10-D.ckpt", "3-10-G.ckpt"]
+        want = {k: v.clone() for k, v in tr.G.state_dict().items()}
+        assert "TransformerEncoder.Encoder_Blocks.0.attn.out_e.weight" in want and "readout_e.bias" in want
+        with torch.no_grad():
+            for p in tr.G.parameters():
+                p.add_(1.0)
+        tr.restore_model(3, 10, str(tmp_path))
+        for k, v in tr.G.state_dict().items():
+            assert torch.equal(v, want[k]), k
+        p0 = next(tr.G.parameters())
+        assert p0.data_ptr() == tr.g_optimizer.flat_p.data_ptr()          # still a view of the optimizer's flat buffer
+    finally:
+        kernels._install_backend_for_tests(None)

@@ -231,3 +231,4 @@ def test_attn_scores_bwd_ring_equals_four_warp_kernel(cuda_dev, B, N):
         assert rel_l2(n_[0].float(), o[0].float()) < (2e-4 if n_[0].dtype == torch.bfloat16 else 1e-6), ("de", vi)
         for nm, a_, b_ in zip(("dq", "dk", "dv"), n_[1:], o[1:]):
             assert rel_l2(a_, b_) < 2e-6, (nm, vi, rel_l2(a_, b_))
+

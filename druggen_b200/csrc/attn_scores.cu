@@ -251,6 +251,8 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// (Measured and not kept: fixing the storage variant at compile time -- no per-row tests, the six rows of a unit one basic block that
+// the compiler interleaves, 255 registers -- ran within 1 % of this form.)
 template <int JC, int kRingWarps>
 __global__ void __launch_bounds__(kRingWarps * 32, 1)
 attn_scores_bwd_ring_kernel(const float* __restrict__ dg, const void* __restrict__ da_in, const float* __restrict__ q,
@@ -274,17 +276,21 @@ attn_scores_bwd_ring_kernel(const float* __restrict__ dg, const void* __restrict
   const int nb = blockIdx.x < B ? (B - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;      // molecules of this CTA
   const long long total = (long long)nb * N;                                             // (molecule, query atom) units
   const uint32_t tx = (uint32_t)rows * (512 + da_row_bytes);
-  auto issue = [&](long long n) {                          // lane 0: unit n -> stage n % depth
-    const int t = (int)(n / N), i = (int)(n - (long long)t * N), s = (int)(n % depth);
-    const long long row = ((long long)(blockIdx.x + t * gridDim.x) * N + i) * N + j0;
-    uint8_t* dst = ring + s * stage_bytes;
-    tc::mbar_expect_tx(&full[s], tx);
-    tc::bulk_g2s(dst, e + row * D, rows * 512, &full[s]);
+  // lane 0 issues the units in order, `depth` ahead of the one being reduced: (it_, ii_, is_) = (molecule slot, query atom, stage) of
+  // the NEXT unit to issue, advanced incrementally (a 64-bit division per unit costs more than a row of the reduction)
+  int it_ = 0, ii_ = 0, is_ = 0;
+  auto issue_next = [&]() {
+    const long long row = ((long long)(blockIdx.x + it_ * gridDim.x) * N + ii_) * N + j0;
+    uint8_t* dst = ring + is_ * stage_bytes;
+    tc::mbar_expect_tx(&full[is_], tx);
+    tc::bulk_g2s(dst, e + row * D, rows * 512, &full[is_]);
     if (da_row_bytes)
-      tc::bulk_g2s(dst + JC * 512, reinterpret_cast<const uint8_t*>(da_in) + row * da_row_bytes, rows * da_row_bytes, &full[s]);
+      tc::bulk_g2s(dst + JC * 512, reinterpret_cast<const uint8_t*>(da_in) + row * da_row_bytes, rows * da_row_bytes, &full[is_]);
+    if (++ii_ == N) { ii_ = 0; ++it_; }
+    if (++is_ == depth) is_ = 0;
   };
   if (lane == 0)
-    for (long long n = 0; n < depth && n < total; ++n) issue(n);
+    for (long long n = 0; n < depth && n < total; ++n) issue_next();
 
   float4 kj[JC], vj[JC], ak[JC], av[JC];
   float4 cq, dgi, M, inv, g;
@@ -358,7 +364,7 @@ attn_scores_bwd_ring_kernel(const float* __restrict__ dg, const void* __restrict
     __syncwarp();                                          // every lane has read the stage
     if (lane == 0 && n + depth < total) {
       tc::fence_async_smem();                              // (generic-proxy reads before the async-proxy refill)
-      issue(n + depth);
+      issue_next();
     }
     red_add_v4(dq + bi, c * sq.x, c * sq.y, c * sq.z, c * sq.w);
     if (i + 1 == N) {                                      // molecule done: my key atoms' dk, dv (exclusive rows: plain stores)

@@ -82,8 +82,11 @@ class _GraphNet(nn.Module):
         if not torch.is_floating_point(z_e):
             if self.dim == 128 and not (self.training and self.dropout > 0):
                 w = self.edge_layers[0].weight
-                lut_e = self.edge_layers(torch.eye(self.edges, dtype=w.dtype, device=w.device))    # models.py:92 on the identity
-                lut_n = self.node_layers(torch.eye(self.nodes, dtype=w.dtype, device=w.device))    # models.py:91
+                eye_e = torch.eye(self.edges, dtype=w.dtype, device=w.device)
+                eye_n = torch.eye(self.nodes, dtype=w.dtype, device=w.device)
+                on_k = self._on_kernels(eye_e)
+                lut_e = self._seq(eye_e, self.edge_layers) if on_k else self.edge_layers(eye_e)    # models.py:92 on the identity
+                lut_n = self._seq(eye_n, self.node_layers) if on_k else self.node_layers(eye_n)    # models.py:91
                 edge = ops.EmbedLabels.apply(lut_e, z_e, True)                                     # + models.py:94
                 node = ops.EmbedLabels.apply(lut_n, z_n, False)
                 return self.TransformerEncoder(node, edge)

@@ -46,8 +46,9 @@ _HAND_SECOND_ORDER = os.environ.get("DRUGGEN_B200_SECOND_ORDER", "hand") != "aut
 # chain over the edge tensor: ~7 % of a GAN step).  Inside ``keep_intermediates()`` a block ALSO keeps what that recomputation
 # would produce (x1, q, k, v, out_n, x3: node-sized;  y3, E, y + out_e(A): fp32 edge-sized;  the scores: bf16) -- 3.5 edge
 # tensors more per block -- as long as the device has room for them beyond a safety margin; the decision is taken per block from
-# the allocator's state, so a pass keeps as many blocks as fit and recomputes the rest.  Results are bit-identical either way
-# (the kept tensors are the outputs of the same launches the recomputation would run).
+# the allocator's state, so a pass keeps as many blocks as fit and recomputes the rest.  Results are the same either way:
+# the kept tensors are the outputs of the same launches the recomputation would run (gradients then differ only in the order of the
+# kernels' atomic reductions, as two runs of one path do).
 _KEEP = {"on": False, "headroom": float(os.environ.get("DRUGGEN_B200_KEEP_HEADROOM_GB", "40")) * 2 ** 30}
 
 

@@ -232,3 +232,53 @@ def test_attn_scores_bwd_ring_equals_four_warp_kernel(cuda_dev, B, N):
         for nm, a_, b_ in zip(("dq", "dk", "dv"), n_[1:], o[1:]):
             assert rel_l2(a_, b_) < 2e-6, (nm, vi, rel_l2(a_, b_))
 
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,N", [(3, 9), (2, 45)])
+def test_kept_intermediates_on_the_gpu(cuda_dev, B, N):
+    """block.keep_intermediates() in the throughput mode on the device: the block's backward takes what the forward kept (the
+    fused edge chain is not launched a second time) and lands on the gradients of the recomputing path -- up to the order of the
+    kernels' atomic reductions (dq, weight-gradient flushes), which also separates two runs of the same path."""
+    from druggen_b200 import block as blk
+    d, heads = 128, 8
+    g = torch.Generator().manual_seed(21)
+    mk = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc).to(cuda_dev)  # noqa: E731
+    params = []
+    for nme in BLOCK_PARAM_NAMES:
+        if nme.startswith("ln"):
+            params.append(mk(d, sc=0.1) + (1.0 if nme.endswith("weight") else 0.0))
+        elif "fc1.weight" in nme:
+            params.append(mk(3 * d, d, sc=d ** -0.5))
+        elif "fc1.bias" in nme:
+            params.append(mk(3 * d, sc=0.1))
+        elif "fc2.weight" in nme:
+            params.append(mk(d, 3 * d, sc=(3 * d) ** -0.5))
+        elif nme.endswith("weight"):
+            params.append(mk(d, d, sc=d ** -0.5))
+        else:
+            params.append(mk(d, sc=0.1))
+    x0, y0, wx, wy = mk(B, N, d), mk(B, N, N, d), mk(B, N, d), mk(B, N, N, d)
+    be = K._be()
+    calls = []
+    orig = be.attn_edge_fwd
+    be.attn_edge_fwd = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+
+    def run(keep):
+        calls.clear()
+        x, y = x0.clone().requires_grad_(True), y0.clone().requires_grad_(True)
+        pp = [p.clone().requires_grad_(True) for p in params]
+        with K.precision("bf16"), blk.keep_intermediates(keep):
+            xo, yo = encoder_block(x, y, pp, heads, True)
+            ((xo * wx).sum() + (yo * wy).sum()).backward()
+        torch.cuda.synchronize()
+        return len(calls), [xo.detach(), yo.detach(), x.grad, y.grad] + [p.grad for p in pp]
+    try:
+        n_re, ref = run(False)
+        n_keep, got = run(True)
+    finally:
+        be.attn_edge_fwd = orig
+    assert (n_re, n_keep) == (2, 1)
+    assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1])          # forward: the same launches
+    for i, (a_, b_) in enumerate(zip(got[2:], ref[2:])):
+        assert rel_l2(a_, b_) < 1e-5, (i, rel_l2(a_, b_))

@@ -44,11 +44,23 @@ __device__ __forceinline__ void flush_acc(const float* acc, float* dst, int N, c
   }
 }
 
+// the edge rows of query atom i + 2 of up to three edge-sized inputs -> L2 (TMA engine; N contiguous rows each): these kernels keep
+// 4 rows per warp in flight and 12-16 warps per SM, i.e. they see the loaded HBM latency on every batch (DG_PF_SECOND)
+__device__ __forceinline__ void prefetch_rows_ahead(int pf, const Ctx& c, int i, int N, const float* t0, const float* t1 = nullptr,
+                                                    const float* t2 = nullptr) {
+  if (pf && threadIdx.x == 0 && i + 2 < c.i1) {
+    const long long pb = (((long long)c.b * N + i + 2) * N) * D;
+    bulk_prefetch_l2(t0 + pb, (long long)N * D * 4);
+    if (t1) bulk_prefetch_l2(t1 + pb, (long long)N * D * 4);
+    if (t2) bulk_prefetch_l2(t2 + pb, (long long)N * D * 4);
+  }
+}
+
 // ---- modulate backward: de = da c q k (2e+1); dq_i = c sum_j da phi k_j; dk_j += c sum_i da phi q_i
 __global__ void __launch_bounds__(128, 4)
 modulate_bwd_kernel(const float* __restrict__ da, const float* __restrict__ q, const float* __restrict__ k,
                     const float* __restrict__ e, float cc, float* __restrict__ dq, float* __restrict__ dk,
-                    float* __restrict__ de, int N, int irows) {
+                    float* __restrict__ de, int N, int irows, int pf) {
   extern __shared__ __align__(16) float sm[];
   float* red = sm;              // [4][128]
   float* sdk = sm + 4 * D;      // [N][128]
@@ -59,6 +71,7 @@ modulate_bwd_kernel(const float* __restrict__ da, const float* __restrict__ q, c
     const long long bi = ((long long)c.b * N + i) * D + c.ch;
     const float4 qi = ld4(q + bi);
     const long long base = (((long long)c.b * N + i) * N) * D + c.ch;
+    prefetch_rows_ahead(pf, c, i, N, e, da);
     float4 sq = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int j = c.jlo; j < c.jhi; j += JU) {
       const int n = min(JU, c.jhi - j);
@@ -95,7 +108,7 @@ __global__ void __launch_bounds__(128, 3)
 modulate_bwd_bwd_kernel(const float* __restrict__ uq, const float* __restrict__ uk, const float* __restrict__ ue,
                         const float* __restrict__ da, const float* __restrict__ q, const float* __restrict__ k,
                         const float* __restrict__ e, float cc, float* __restrict__ g_da, float* __restrict__ g_q,
-                        float* __restrict__ g_k, float* __restrict__ g_e, int N, int irows) {
+                        float* __restrict__ g_k, float* __restrict__ g_e, int N, int irows, int pf) {
   extern __shared__ __align__(16) float sm[];
   float* red = sm;
   float* sgk = sm + 4 * D;
@@ -107,6 +120,7 @@ modulate_bwd_bwd_kernel(const float* __restrict__ uq, const float* __restrict__ 
     const long long bi = ((long long)c.b * N + i) * D + c.ch;
     const float4 qi = ld4(q + bi), uqi = ld4(uq + bi);
     const long long base = (((long long)c.b * N + i) * N) * D + c.ch;
+    prefetch_rows_ahead(pf, c, i, N, e, da, ue);
     float4 sq = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int j = c.jlo; j < c.jhi; j += JU) {
       const int n = min(JU, c.jhi - j);
@@ -163,7 +177,7 @@ __device__ __forceinline__ void combine_runs(const float* pm, const float* ps, i
 // ---- softmax-aggregate backward: da = p dg (v - g) (+ da when accumulate); dv_j += sum_i p dg
 __global__ void __launch_bounds__(128, 4)
 softmax_agg_bwd_kernel(const float* __restrict__ dg, const float* __restrict__ a, const float* __restrict__ v,
-                       float* __restrict__ da, float* __restrict__ dv, int accumulate, int N, int irows) {
+                       float* __restrict__ da, float* __restrict__ dv, int accumulate, int N, int irows, int pf) {
   extern __shared__ __align__(16) float sm[];
   float* red = sm;              // [3][4][128]: m, s, sv
   float* sdv = sm + 12 * D;     // [N][128]
@@ -173,6 +187,7 @@ softmax_agg_bwd_kernel(const float* __restrict__ dg, const float* __restrict__ a
   for (int i = c.i0; i < c.i1; ++i) {
     const long long bi = ((long long)c.b * N + i) * D + c.ch;
     const long long base = (((long long)c.b * N + i) * N) * D + c.ch;
+    prefetch_rows_ahead(pf, c, i, N, a, accumulate ? da : nullptr);
     float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), s = make_float4(0.f, 0.f, 0.f, 0.f), sv = s;
     for (int j = c.jlo; j < c.jhi; j += JU) {
       const int n = min(JU, c.jhi - j);
@@ -245,7 +260,7 @@ softmax_agg_bwd_kernel(const float* __restrict__ dg, const float* __restrict__ a
 __global__ void __launch_bounds__(128, 3)
 softmax_agg_bwd_bwd_kernel(const float* __restrict__ ua, const float* __restrict__ uv, const float* __restrict__ dg,
                            const float* __restrict__ a, const float* __restrict__ v, float* __restrict__ g_dg,
-                           float* __restrict__ g_a, float* __restrict__ g_v, int N, int irows) {
+                           float* __restrict__ g_a, float* __restrict__ g_v, int N, int irows, int pf) {
   extern __shared__ __align__(16) float sm[];
   float* red = sm;              // [6][4][128]: m, s, sv, su, suv, sw
   float* sgv = sm + 24 * D;     // [N][128]
@@ -256,6 +271,7 @@ softmax_agg_bwd_bwd_kernel(const float* __restrict__ ua, const float* __restrict
   for (int i = c.i0; i < c.i1; ++i) {
     const long long bi = ((long long)c.b * N + i) * D + c.ch;
     const long long base = (((long long)c.b * N + i) * N) * D + c.ch;
+    prefetch_rows_ahead(pf, c, i, N, a, ua);
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), s = z4, sv = z4, su = z4, suv = z4, sw = z4;
     for (int j = c.jlo; j < c.jhi; j += JU) {
@@ -360,7 +376,7 @@ int modulate_bwd_v4(const float* da, const float* q, const float* k, const float
   if (v4::smem_attr(v4::modulate_bwd_kernel, smem)) return 1;
   const int irows = v4::irows_for(B, N, 4);
   dim3 grid((N + irows - 1) / irows, B);
-  v4::modulate_bwd_kernel<<<grid, 128, smem, s>>>(da, q, k, e, c, dq, dk, de, N, irows);
+  v4::modulate_bwd_kernel<<<grid, 128, smem, s>>>(da, q, k, e, c, dq, dk, de, N, irows, opt_get(DG_OPT_L2_PREFETCH) & DG_PF_SECOND);
   return check_launch("dg_modulate_bwd");
 }
 int modulate_bwd_bwd_v4(const float* uq, const float* uk, const float* ue, const float* da, const float* q, const float* k,
@@ -369,7 +385,7 @@ int modulate_bwd_bwd_v4(const float* uq, const float* uk, const float* ue, const
   if (v4::smem_attr(v4::modulate_bwd_bwd_kernel, smem)) return 1;
   const int irows = v4::irows_for(B, N, 3);
   dim3 grid((N + irows - 1) / irows, B);
-  v4::modulate_bwd_bwd_kernel<<<grid, 128, smem, s>>>(uq, uk, ue, da, q, k, e, c, g_da, g_q, g_k, g_e, N, irows);
+  v4::modulate_bwd_bwd_kernel<<<grid, 128, smem, s>>>(uq, uk, ue, da, q, k, e, c, g_da, g_q, g_k, g_e, N, irows, opt_get(DG_OPT_L2_PREFETCH) & DG_PF_SECOND);
   return check_launch("dg_modulate_bwd_bwd");
 }
 int softmax_agg_bwd_v4(const float* dg_, const float* a, const float* v, float* da, float* dv, int accumulate, int B, int N,
@@ -378,7 +394,7 @@ int softmax_agg_bwd_v4(const float* dg_, const float* a, const float* v, float* 
   if (v4::smem_attr(v4::softmax_agg_bwd_kernel, smem)) return 1;
   const int irows = v4::irows_for(B, N, 4);
   dim3 grid((N + irows - 1) / irows, B);
-  v4::softmax_agg_bwd_kernel<<<grid, 128, smem, s>>>(dg_, a, v, da, dv, accumulate, N, irows);
+  v4::softmax_agg_bwd_kernel<<<grid, 128, smem, s>>>(dg_, a, v, da, dv, accumulate, N, irows, opt_get(DG_OPT_L2_PREFETCH) & DG_PF_SECOND);
   return check_launch("dg_softmax_agg_bwd");
 }
 int softmax_agg_bwd_bwd_v4(const float* ua, const float* uv, const float* dg_, const float* a, const float* v, float* g_dg,
@@ -387,7 +403,7 @@ int softmax_agg_bwd_bwd_v4(const float* ua, const float* uv, const float* dg_, c
   if (v4::smem_attr(v4::softmax_agg_bwd_bwd_kernel, smem)) return 1;
   const int irows = v4::irows_for(B, N, 3);
   dim3 grid((N + irows - 1) / irows, B);
-  v4::softmax_agg_bwd_bwd_kernel<<<grid, 128, smem, s>>>(ua, uv, dg_, a, v, g_dg, g_a, g_v, N, irows);
+  v4::softmax_agg_bwd_bwd_kernel<<<grid, 128, smem, s>>>(ua, uv, dg_, a, v, g_dg, g_a, g_v, N, irows, opt_get(DG_OPT_L2_PREFETCH) & DG_PF_SECOND);
   return check_launch("dg_softmax_agg_bwd_bwd");
 }
 

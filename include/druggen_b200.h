@@ -51,6 +51,8 @@ int dg_has_tcgen05(void);
 #define DG_OPT_ATTN_BWD 1    /* dg_attn_scores_bwd with the forward's statistics: 0 (default) = the TMA-fed ring kernel where it applies
                               * (N <= 48; 8 warps x <= 6 key atoms), 2 = the ring kernel with 16 warps x <= 3 key atoms,
                               * 1 = always the 4-warp register-staged kernel (A/B switches) */
+#define DG_PF_SECOND 128   /* second-order attention kernels (dg_modulate_bwd*, dg_softmax_agg_bwd*): next query atom's rows.  Off by
+                              * default: measured 20-27 % slower on the modulate kernels, neutral on the softmax ones (B200) */
 #define DG_OPT_COUNT 2
 int dg_set_option(int key, int value);
 int dg_get_option(int key);

@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--atoms", type=int, default=45)
     ap.add_argument("--depth", type=int, default=8)
     ap.add_argument("--keep-ab", action="store_true", help="time every kernel without / with L2::evict_last on the chain loaders' x reads")
+    ap.add_argument("--pf", type=int, default=None, help="A/B: the default L2-prefetch mask against this one")
     ap.add_argument("--prefetch-ab", action="store_true", help="time every kernel with the L2-prefetch option off and on")
     args = ap.parse_args()
     try:
@@ -126,8 +127,14 @@ def main():
             ("symmetrize", lambda: K.symmetrize(x4), 3 * r * d * 4, 0.0),
             ("add_ln_fwd", lambda: K.add_ln_fwd(x, dout, gamma, beta), 3 * r * d * 4, 0.0),
             ("add_ln_bwd", lambda: K.add_ln_bwd(x, dout, None, gamma), 3 * r * d * 4, 0.0),
+            # second-order kernels of the gradient penalty (block_backward_backward)
+            ("add_ln_bwd_bwd", lambda: K.add_ln_bwd_bwd(dout, None, None, x, x, None, gamma), 5 * r * d * 4, 0.0),
+            ("modulate_bwd_bwd", lambda: K.modulate_bwd_bwd(q, k, x4, dout.view(b, n, n, d), q, k, x4, 0.25), 5 * r * d * 4, 0.0),
+            ("softmax_agg_bwd_bwd", lambda: K.softmax_agg_bwd_bwd(dout.view(b, n, n, d), v, dgn, x4, v), 4 * r * d * 4, 0.0),
+            ("softmax_agg_bwd", lambda: K.softmax_agg_bwd(dgn, x4, v), 3 * r * d * 4, 0.0),
+            ("modulate_bwd", lambda: K.modulate_bwd(dout.view(b, n, n, d), q, k, x4, 0.25), 3 * r * d * 4, 0.0),
         ]
-        for pf in ((0, _lib.PF_ALL) if args.prefetch_ab else ((_lib.PF_DEFAULT, _lib.PF_DEFAULT | _lib.PF_CHAIN_KEEP) if args.keep_ab else (_lib.PF_DEFAULT,))):
+        for pf in ((_lib.PF_DEFAULT, args.pf) if args.pf is not None else (0, _lib.PF_ALL) if args.prefetch_ab else ((_lib.PF_DEFAULT, _lib.PF_DEFAULT | _lib.PF_CHAIN_KEEP) if args.keep_ab else (_lib.PF_DEFAULT,))):
             K.set_option(_lib.OPT_L2_PREFETCH, pf)
             for name, fn, nbytes, flops in benches:
                 report(name, timeit(fn), nbytes, flops, l2_prefetch=pf)

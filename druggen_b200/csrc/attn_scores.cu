@@ -265,7 +265,8 @@ attn_scores_bwd_ring_kernel(const float* __restrict__ dg, const void* __restrict
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, ch = lane * 4;
   const int j0 = w * JC, rows = min(JC, N - j0);
   if (rows <= 0) return;                                  // (no CTA-wide barrier anywhere below)
-  const int stage_bytes = JC * (512 + da_row_bytes);
+  const int acc_row_bytes = (flags & 8) ? 512 : 0;        // de += : the prior de rows ride in the ring too (no load inside the row loop)
+  const int stage_bytes = JC * (512 + da_row_bytes + acc_row_bytes);
   uint8_t* ring = ring_raw + (size_t)w * depth * stage_bytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(ring_raw + (size_t)kRingWarps * depth * stage_bytes) + w * depth;
   if (lane == 0) {
@@ -275,7 +276,7 @@ attn_scores_bwd_ring_kernel(const float* __restrict__ dg, const void* __restrict
   __syncwarp();
   const int nb = blockIdx.x < B ? (B - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;      // molecules of this CTA
   const long long total = (long long)nb * N;                                             // (molecule, query atom) units
-  const uint32_t tx = (uint32_t)rows * (512 + da_row_bytes);
+  const uint32_t tx = (uint32_t)rows * (512 + da_row_bytes + acc_row_bytes);
   // lane 0 issues the units in order, `depth` ahead of the one being reduced: (it_, ii_, is_) = (molecule slot, query atom, stage) of
   // the NEXT unit to issue, advanced incrementally (a 64-bit division per unit costs more than a row of the reduction)
   int it_ = 0, ii_ = 0, is_ = 0;
@@ -286,6 +287,8 @@ attn_scores_bwd_ring_kernel(const float* __restrict__ dg, const void* __restrict
     tc::bulk_g2s(dst, e + row * D, rows * 512, &full[is_]);
     if (da_row_bytes)
       tc::bulk_g2s(dst + JC * 512, reinterpret_cast<const uint8_t*>(da_in) + row * da_row_bytes, rows * da_row_bytes, &full[is_]);
+    if (acc_row_bytes)
+      tc::bulk_g2s(dst + JC * (512 + da_row_bytes), reinterpret_cast<const float*>(de) + row * D, rows * 512, &full[is_]);
     if (++ii_ == N) { ii_ = 0; ++it_; }
     if (++is_ == depth) is_ = 0;
   };
@@ -355,7 +358,7 @@ attn_scores_bwd_ring_kernel(const float* __restrict__ dg, const void* __restrict
         } else {
           float* dp = reinterpret_cast<float*>(de) + off;
           if (flags & 8) {
-            const float4 pr = ld4(dp);
+            const float4 pr = *reinterpret_cast<const float4*>(st + JC * (512 + da_row_bytes) + r * 512 + lane * 16);
             o.x += pr.x; o.y += pr.y; o.z += pr.z; o.w += pr.w;
           }
           st4(dp, o);
@@ -523,7 +526,7 @@ extern "C" int dg_attn_scores_bwd(const float* dg_, const float* da_in, const fl
     const int jc = (N + warps - 1) / warps;
     const int JC = warps == 8 ? (jc <= 2 ? 2 : jc <= 4 ? 4 : 6) : jc;
     const int da_row = da_in == nullptr ? 0 : ((de_bf16 & 4) ? 256 : 512);
-    const int stage = JC * (512 + da_row);
+    const int stage = JC * (512 + da_row + ((de_bf16 & 8) ? 512 : 0));
     int depth = (200 * 1024) / (warps * stage);
     if (depth > 8) depth = 8;
     const size_t smem_ring = (size_t)warps * depth * stage + warps * 8 * 8;

@@ -67,6 +67,7 @@ def main():
     w = rn(d, d, sc=d ** -0.5)
     q, k, v = rn(b, n, d), rn(b, n, d), rn(b, n, d)
     dgn = rn(b, n, d)
+    acc4 = torch.zeros(b, n, n, d, device=dev)
     x4 = x.view(b, n, n, d)
 
     with dg.precision("bf16"):
@@ -109,6 +110,8 @@ def main():
             ("attn_scores_fwd[fused]", lambda: K.attn_scores_fwd(q, k, v, x4, 0.25), 2 * r * d * 4, 0.0),
             ("attn_scores_fwd[stats only]", lambda: K.attn_scores_fwd(q, k, v, x4, 0.25, True, False), r * d * 4, 0.0),
             ("attn_scores_bwd[fused,stats]", lambda: K.attn_scores_bwd(dgn, dout.view(b, n, n, d), q, k, v, x4, 0.25, stats), 3 * r * d * 4, 0.0),
+            ("attn_scores_bwd[fused,stats,de+=]", lambda: K.attn_scores_bwd(dgn, dout.view(b, n, n, d), q, k, v, x4, 0.25, stats, de_accum=acc4),
+             4 * r * d * 4, 0.0),
             ("attn_scores_bwd[fused,stats,de16]", lambda: K.attn_scores_bwd(dgn, dout.view(b, n, n, d), q, k, v, x4, 0.25, stats, True),
              r * d * 10, 0.0),
             ("attn_scores_bwd[fused,stats,de16,da16]", lambda: K.attn_scores_bwd(dgn, a16.view(b, n, n, d), q, k, v, x4, 0.25, stats, True),

@@ -52,10 +52,21 @@ SIGNATURES = {
     "dg_narrow_labels": [_P, _P, _LL, _I, _P],
     "dg_pack_bits": [_P, _I, _P, _P, _LL, _I, _P],
     "dg_tanimoto_agg": [_P, _P, _LL, _P, _P, _LL, _I, _I, _F, _P, _P, _P],
+    # block-level entry points: (io table, params table[, grads table], B, N, D, H, heads, flags, eps, workspace, bytes)
+    "dg_block_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _LL, _P],
+    "dg_block_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _LL, _P],
+    "dg_encoder_fwd": [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _F, _P, _LL, _P],
 }
 INFO_SYMBOLS = ("dg_abi_version", "dg_last_error", "dg_has_tcgen05", "dg_set_option", "dg_get_option", "dg_debug_chain_profile",
-                "dg_label_error")
-ABI_VERSION = 5
+                "dg_label_error", "dg_native_launches", "dg_probe_set", "dg_probe_read")
+# slots of the block-level entry points' buffer table, in the order of the DG_BLK_* enum of include/druggen_b200.h
+BLK_SLOTS = ("X", "Y", "X_OUT", "Y_OUT", "X1", "Q", "K", "V", "G", "ON", "X3", "STAT_M", "STAT_INV", "Y3", "A16", "E", "Z4",
+             "DXO", "DYO", "DX", "DY", "N_DZ", "N_DX3", "N_DZ3", "N_DG", "N_DQ", "N_DK", "N_DV", "N_T0", "N_T1", "N_H", "N_MASK",
+             "E_A", "E_B", "E_H", "E_MASK", "SCRATCH")
+BLK = {name: i for i, name in enumerate(BLK_SLOTS)}
+BLKF_EDGE_OUT, BLKF_KEEP, BLKF_STATS = 1, 2, 4
+BLOCK_PARAMS = 30
+ABI_VERSION = 6
 OPT_L2_PREFETCH = 0
 OPT_ATTN_BWD = 1                                      # 0 = TMA-fed ring kernel where it applies (default), 1 = 4-warp kernel
 PF_ALL, PF_DEFAULT, PF_CHAIN_KEEP = 63, 12, 64        # DG_PF_* bit masks (include/druggen_b200.h)
@@ -83,6 +94,9 @@ def load():
         lib.dg_get_option.argtypes, lib.dg_get_option.restype = [_I], _I
         lib.dg_debug_chain_profile.argtypes, lib.dg_debug_chain_profile.restype = [_P], _I
         lib.dg_label_error.argtypes, lib.dg_label_error.restype = [_I], _I
+        lib.dg_native_launches.argtypes, lib.dg_native_launches.restype = [], _LL
+        lib.dg_probe_set.argtypes, lib.dg_probe_set.restype = [C.c_char_p], _I
+        lib.dg_probe_read.argtypes, lib.dg_probe_read.restype = [C.POINTER(_LL), C.POINTER(C.c_double)], _I
         if lib.dg_abi_version() != ABI_VERSION:
             raise RuntimeError("libdruggen_b200.so ABI version mismatch")
         if os.environ.get("DRUGGEN_B200_L2_PREFETCH") is not None:       # tuning switch, default on
@@ -110,14 +124,32 @@ class CudaBackend:
 
     def __init__(self, lib):
         self.lib = lib
-        self.launches = 0          # kernel launches issued through this table (bench.py reports it)
+        self._py_launches = 0      # kernel launches issued one by one through this table
+        self._native0 = lib.dg_native_launches()
         self.device = None         # device of the tensors of the launch being issued (set by kernels._chk)
         self.profile_all = False
-        self.profile_only = None
+        self._profile_only = None
         self._prof = {}
+        self._per_launch = {}      # key -> (flops, bytes, algorithmic bytes, bound) of ONE launch (for launches the library issues itself)
+
+    @property
+    def launches(self):
+        """Kernel launches so far (bench.py reports it): those issued from Python plus those the block-level entry points
+        (dg_block_fwd / dg_block_bwd / dg_encoder_fwd) issued themselves."""
+        return self._py_launches + self.lib.dg_native_launches() - self._native0
+
+    @property
+    def profile_only(self):
+        return self._profile_only
+
+    @profile_only.setter
+    def profile_only(self, key):
+        self._profile_only = key
+        self.lib.dg_probe_set(key.encode() if key else None)     # the same key times the launches the library issues itself
 
     def profile_reset(self):
         self._prof = {}
+        self.lib.dg_probe_read(None, None)
 
     def profile_summary(self):
         torch.cuda.synchronize()
@@ -126,17 +158,68 @@ class CudaBackend:
             ms = sum(a.elapsed_time(b) for a, b in rec["events"])
             out[key] = {"key": key, "n": len(rec["events"]), "ms": ms, "bytes": rec["bytes"], "alg_bytes": rec["alg_bytes"],
                         "flops": rec["flops"], "bound": rec["bound"]}
+        key = self._profile_only
+        if key is not None and key in self._per_launch:
+            n, ms = _LL(0), C.c_double(0.0)
+            self.lib.dg_probe_read(C.byref(n), C.byref(ms))
+            if n.value:
+                flops, nbytes, alg, bound = self._per_launch[key]
+                rec = out.setdefault(key, {"key": key, "n": 0, "ms": 0.0, "bytes": 0, "alg_bytes": 0, "flops": 0, "bound": bound})
+                rec["n"] += n.value
+                rec["ms"] += ms.value
+                rec["bytes"] += nbytes * n.value
+                rec["alg_bytes"] += alg * n.value
+                rec["flops"] += flops * n.value
         return out
+
+    def native_blocks(self) -> bool:
+        """May the block-level entry points run?  Not while every launch is being timed from Python (bench.py's kernel table)."""
+        return not self.profile_all
+
+    def _native(self, name, *args):
+        dev = self.device
+        if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+            with torch.cuda.device(dev):
+                rc = getattr(self.lib, name)(*args, torch.cuda.current_stream().cuda_stream)
+        else:
+            rc = getattr(self.lib, name)(*args, torch.cuda.current_stream().cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f"{name} rejected: {self.lib.dg_last_error().decode()}")
+
+    @staticmethod
+    def _table(io):
+        tab = (C.c_void_p * len(BLK_SLOTS))()
+        for name, t in io.items():
+            if t is not None:
+                tab[BLK[name]] = t.data_ptr()
+        return tab
+
+    @staticmethod
+    def _ptrs(ts):
+        return (C.c_void_p * len(ts))(*[None if t is None else t.data_ptr() for t in ts])
+
+    def block_fwd(self, io, params, b, n, d, h, heads, flags, eps, ws):
+        self._native("dg_block_fwd", self._table(io), self._ptrs(params), b, n, d, h, heads, flags, eps, _ptr(ws), ws.numel())
+
+    def block_bwd(self, io, params, grads, b, n, d, h, heads, flags, eps, ws):
+        self._native("dg_block_bwd", self._table(io), self._ptrs(params), None if grads is None else self._ptrs(grads), b, n, d, h,
+                     heads, flags, eps, _ptr(ws), ws.numel())
+
+    def encoder_fwd(self, x, y, x_out, y_out, params, depth, scratch, b, n, d, h, heads, last_edge_out, eps, ws):
+        self._native("dg_encoder_fwd", _ptr(x), _ptr(y), _ptr(x_out), _ptr(y_out), self._ptrs(params), depth, self._table(scratch),
+                     b, n, d, h, heads, int(last_edge_out), eps, _ptr(ws), ws.numel())
 
     @staticmethod
     def profile_name(rec):
         return rec["key"]
 
     def _call(self, name, meta, *args):
-        self.launches += 1
+        self._py_launches += 1
         key, flops, nbytes, bound = meta[:4]
         alg = meta[4] if len(meta) > 4 else nbytes          # SURVEY 8(d) bytes: the kernel's inputs and outputs, no operand spills
-        timed = self.profile_all or (self.profile_only is not None and self.profile_only == key)
+        timed = self.profile_all or (self._profile_only is not None and self._profile_only == key)
+        if timed:
+            self._per_launch[key] = (flops, nbytes, alg, bound)
         dev = self.device
         if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
             # tensors on a device that is not the current one (nn.DataParallel replicas, models on cuda:1 without

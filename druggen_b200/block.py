@@ -143,6 +143,8 @@ def block_forward_nograd(x, y, params: Sequence[torch.Tensor], heads: int, edge_
     if not K.fused_available(d, hid):
         out = block_forward(x, y, params, heads, edge_out)
         return (out + (None, None) if want_saved is not None else out + (None,)) if want_stats else out
+    if K.native_block_available(b, n, d, hid):
+        return _native_forward(x, y, params, heads, edge_out, want_stats, want_saved)
     c = 1.0 / math.sqrt(d // heads)
     x1 = K.add_ln_fwd(x.reshape(-1, d), None, p("ln1.weight"), p("ln1.bias"))
     q = K.rows_gemm(x1, p("attn.q.weight"), True, p("attn.q.bias")).view(b, n, d)
@@ -187,6 +189,186 @@ def block_forward_nograd(x, y, params: Sequence[torch.Tensor], heads: int, edge_
     return ret(y_out)
 
 
+def _native_forward(x, y, params, heads, edge_out, want_stats, want_saved):
+    """``block_forward_nograd`` as ONE library call (``dg_block_fwd``): the same launches with the same arguments, sequenced in C
+    over the buffers allocated here.  Same return convention."""
+    from ._lib import BLKF_EDGE_OUT, BLKF_KEEP, BLKF_STATS
+    b, n, d = x.shape
+    hid = params[_IDX["mlp.fc1.weight"]].shape[0]
+    bn, r = b * n, b * n * n
+    f32 = dict(dtype=torch.float32, device=x.device)
+    stats_on = bool(want_stats and edge_out)
+    keep = bool(want_saved and stats_on)
+    node = torch.empty((9 if stats_on else 7, bn, d), **f32)
+    x1, q, k, v, g, on, x3 = node[:7].unbind(0)
+    x_out = torch.empty((bn, d), **f32)
+    io = {"X": x.reshape(bn, d), "Y": y.reshape(r, d), "X_OUT": x_out, "X1": x1, "Q": q, "K": k, "V": v, "G": g, "ON": on, "X3": x3}
+    flags = 0
+    if stats_on:
+        io["STAT_M"], io["STAT_INV"] = node[7], node[8]
+        flags |= BLKF_STATS
+    if edge_out:
+        y_out = torch.empty((r, d), **f32)
+        io["Y_OUT"], io["Y3"] = y_out, torch.empty((r, d), **f32)
+        io["A16"] = torch.empty((r, d), dtype=torch.bfloat16, device=x.device)
+        flags |= BLKF_EDGE_OUT
+        if keep:
+            io["E"], io["Z4"] = torch.empty((r, d), **f32), torch.empty((r, d), **f32)
+            flags |= BLKF_KEEP
+    else:
+        y_out = None
+        io["E"], io["Y3"] = torch.empty((r, d), **f32), torch.empty((r, d), **f32)       # (Y3: scratch for the scores)
+    K.block_fwd(io, list(params), b, n, d, hid, heads, flags)
+    xo, yo = x_out.view(b, n, d), (y_out.view(b, n, n, d) if edge_out else None)
+    if not want_stats:
+        return xo, yo
+    stats = (io["STAT_M"].view(b, n, d), io["STAT_INV"].view(b, n, d), g.view(b, n, d)) if stats_on else None
+    if want_saved is None:
+        return xo, yo, stats
+    saved = None
+    if keep:
+        saved = {"x1": x1, "q": q.view(b, n, d), "k": k.view(b, n, d), "v": v.view(b, n, d), "y3": io["Y3"], "a16": io["A16"],
+                 "e": io["E"], "z4": io["Z4"], "on": on, "x3": x3}
+    return xo, yo, stats, saved
+
+
+# Small encoder forwards are launch-bound even with the library sequencing its own launches (8 layers x 10 launches of a few
+# microseconds each): below this edge-tensor size the whole ``dg_encoder_fwd`` call is captured ONCE into a CUDA graph per
+# (shape, weights) and replayed -- inputs copied into the graph's static buffers, outputs cloned out of them.
+_GRAPH = {"on": os.environ.get("DRUGGEN_B200_GRAPH", "1") != "0",
+          "max_edge_bytes": int(float(os.environ.get("DRUGGEN_B200_GRAPH_MAX_MB", "64")) * 2 ** 20), "cache": {}, "max_entries": 8}
+
+
+def _encoder_buffers(b, n, d, depth, last_edge_out, dev):
+    bn, r = b * n, b * n * n
+    f32 = dict(dtype=torch.float32, device=dev)
+    node = torch.empty((8, bn, d), **f32)
+    scratch = dict(zip(("X1", "Q", "K", "V", "G", "ON", "X3", "X_OUT"), node.unbind(0)))
+    scratch["Y3"] = torch.empty((r, d), **f32)
+    scratch["A16"] = torch.empty((r, d), dtype=torch.bfloat16, device=dev)
+    if depth > 1:
+        scratch["Y_OUT"] = torch.empty((r, d), **f32)
+    if not last_edge_out:
+        scratch["E"] = torch.empty((r, d), **f32)
+    x_out = torch.empty((bn, d), **f32)
+    y_out = torch.empty((r, d), **f32) if (last_edge_out or depth > 2) else None
+    return scratch, x_out, y_out
+
+
+def _encoder_graph(x2d, y2d, flat, b, n, d, depth, hid, heads, last_edge_out):
+    """-> (x_out, y_out | None) through a cached CUDA graph of ``dg_encoder_fwd``, or None when capture is not possible."""
+    key = (x2d.device, b, n, depth, hid, heads, last_edge_out, K.get_precision(), tuple(t.data_ptr() for t in flat))
+    cache = _GRAPH["cache"]
+    ent = cache.get(key)
+    if ent is None:
+        sx, sy = torch.empty_like(x2d), torch.empty_like(y2d)
+        scratch, xo, yo = _encoder_buffers(b, n, d, depth, last_edge_out, x2d.device)
+        ws = K._mlp_ws(flat[_IDX["mlp.fc1.weight"]])
+        run = lambda: K.encoder_fwd(sx, sy, xo, yo, flat, depth, scratch, b, n, d, hid, heads, last_edge_out, ws=ws)  # noqa: E731
+        sx.copy_(x2d), sy.copy_(y2d)
+        run()                                     # outside the capture first: per-device function attributes, driver entry points
+        graph = torch.cuda.CUDAGraph()
+        try:
+            with torch.cuda.graph(graph):
+                run()
+        except Exception:                         # (a driver / torch that refuses the capture: plain launches from here on)
+            _GRAPH["on"] = False
+            return None
+        if len(cache) >= _GRAPH["max_entries"]:
+            cache.pop(next(iter(cache)))
+        ent = cache[key] = (graph, sx, sy, xo, yo, scratch, ws, list(flat))
+    graph, sx, sy, xo, yo = ent[:5]
+    sx.copy_(x2d), sy.copy_(y2d)
+    graph.replay()
+    return xo.clone(), (yo.clone() if last_edge_out else None)
+
+
+def encoder_forward_nograd(x, y, blocks_params, heads: int, last_edge_out: bool = True):
+    """TransformerEncoder.forward (layers.py:221-234) without a graph as ONE library call (``dg_encoder_fwd``) where the
+    block-level entry points apply, else block by block.  ``blocks_params``: one BLOCK_PARAM_NAMES-ordered list per block."""
+    b, n, d = x.shape
+    depth = len(blocks_params)
+    hid = blocks_params[0][_IDX["mlp.fc1.weight"]].shape[0]
+    if not (depth and K.native_block_available(b, n, d, hid)):
+        for i, params in enumerate(blocks_params):
+            x, y = block_forward_nograd(x, y, params, heads, last_edge_out or i < depth - 1)
+        return x, y
+    bn, r = b * n, b * n * n
+    flat = [t for params in blocks_params for t in params]
+    x2d, y2d = x.reshape(bn, d), y.reshape(r, d)
+    out = None
+    if _GRAPH["on"] and r * d * 4 <= _GRAPH["max_edge_bytes"] and not torch.cuda.is_current_stream_capturing():
+        out = _encoder_graph(x2d, y2d, flat, b, n, d, depth, hid, heads, last_edge_out)
+    if out is None:
+        scratch, x_out, y_out = _encoder_buffers(b, n, d, depth, last_edge_out, x.device)
+        K.encoder_fwd(x2d, y2d, x_out, y_out, flat, depth, scratch, b, n, d, hid, heads, last_edge_out)
+        out = (x_out, y_out if last_edge_out else None)
+    return out[0].view(b, n, d), (out[1].view(b, n, n, d) if last_edge_out else None)
+
+
+def _native_backward(x, y, dxo, dyo, params, heads, edge_out, want_params, fwd_stats, fwd_saved):
+    """``block_backward`` as ONE library call (``dg_block_bwd``).  Same return convention; the parameter gradients are views of
+    one zeroed flat buffer (one fill instead of thirty)."""
+    from ._lib import BLKF_EDGE_OUT, BLKF_KEEP, BLKF_STATS
+    b, n, d = x.shape
+    hid = params[_IDX["mlp.fc1.weight"]].shape[0]
+    bn, r = b * n, b * n * n
+    dev = x.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    live = edge_out and dyo is not None
+    kept = fwd_saved is not None and fwd_stats is not None and live
+    flags = BLKF_EDGE_OUT if edge_out else 0
+    io = {"X": x.reshape(bn, d), "Y": y.reshape(r, d)}
+    c2 = lambda t: t.reshape(-1, d)  # noqa: E731
+    if kept:
+        for slot, nm in (("X1", "x1"), ("Q", "q"), ("K", "k"), ("V", "v"), ("ON", "on"), ("X3", "x3"), ("Y3", "y3"), ("A16", "a16"),
+                         ("E", "e"), ("Z4", "z4")):
+            io[slot] = c2(fwd_saved[nm])
+        flags |= BLKF_KEEP
+    else:
+        node_f = torch.empty((6, bn, d), **f32)
+        io["X1"], io["Q"], io["K"], io["V"], io["ON"], io["X3"] = node_f.unbind(0)
+        io["E"] = torch.empty((r, d), **f32)
+        if live:
+            io["Y3"], io["Z4"] = torch.empty((r, d), **f32), torch.empty((r, d), **f32)
+            io["A16"] = torch.empty((r, d), dtype=torch.bfloat16, device=dev)
+        else:
+            io["Y3"] = torch.empty((r, d), **f32)                                            # (scratch for the scores)
+    if live and fwd_stats is not None:
+        io["STAT_M"], io["STAT_INV"], io["G"] = (c2(t) for t in fwd_stats)
+        flags |= BLKF_STATS
+    else:
+        io["STAT_M"], io["STAT_INV"], io["G"] = torch.empty((3, bn, d), **f32).unbind(0)
+    io["DXO"] = None if dxo is None else dxo.reshape(bn, d).contiguous()
+    io["DYO"] = dyo.reshape(r, d).contiguous() if live else None
+    dx, dy = torch.empty((bn, d), **f32), torch.empty((r, d), **f32)
+    io["DX"], io["DY"] = dx, dy
+    node_s = torch.empty((9, bn, d), **f32)
+    for slot, t in zip(("N_DZ", "N_DX3", "N_DZ3", "N_DG", "N_DQ", "N_DK", "N_DV", "N_T0", "N_T1"), node_s.unbind(0)):
+        io[slot] = t
+    io["N_MASK"] = torch.empty((bn, hid // 64), dtype=torch.int64, device=dev)
+    if want_params:
+        io["N_H"] = torch.empty((bn, hid), dtype=torch.bfloat16, device=dev)
+    if live:
+        io["E_A"], io["E_B"] = torch.empty((r, d), **f32), torch.empty((r, d), **f32)
+        io["E_MASK"] = torch.empty((r, hid // 64), dtype=torch.int64, device=dev)
+    # bf16: h, then dh of the edge MLP (weight gradients only), then dE
+    io["E_H"] = torch.empty((r, hid if (want_params and live) else d), dtype=torch.bfloat16, device=dev)
+    io["SCRATCH"] = torch.empty(2 * d, **f32)
+    grads = None
+    if want_params:
+        dead = () if live else ("attn.out_e.", "ln4.", "mlp2.", "ln6.")
+        sizes = [0 if nm.startswith(dead) else params[i].numel() for i, nm in enumerate(BLOCK_PARAM_NAMES)] if dead else \
+                [t.numel() for t in params]
+        flat = torch.zeros(sum(sizes), **f32)
+        grads, o = [], 0
+        for t, sz in zip(params, sizes):
+            grads.append(flat[o:o + sz].view_as(t) if sz else None)
+            o += sz
+    K.block_bwd(io, list(params), grads, b, n, d, hid, heads, flags)
+    return dx.view(b, n, d), dy.view(b, n, n, d), (grads if grads is not None else [None] * len(BLOCK_PARAM_NAMES))
+
+
 def block_backward(x, y, dxo, dyo, params: Sequence[torch.Tensor], heads: int, edge_out: bool = True,
                    want_params: bool = True, fwd_stats=None, fwd_saved=None):
     """First-order backward of the block as a hand-sequenced list of raw kernel launches (no autograd
@@ -198,6 +380,8 @@ def block_backward(x, y, dxo, dyo, params: Sequence[torch.Tensor], heads: int, e
     ``fwd_saved``: the forward's intermediates (``keep_intermediates``): the recomputation is skipped."""
     p = lambda n: params[_IDX[n]]  # noqa: E731
     b, n, d = x.shape
+    if K.native_block_available(b, n, d, p("mlp.fc1.weight").shape[0]):
+        return _native_backward(x, y, dxo, dyo, params, heads, edge_out, want_params, fwd_stats, fwd_saved)
     c = 1.0 / math.sqrt(d // heads)
     grads = [None] * len(BLOCK_PARAM_NAMES)
     kept = fwd_saved is not None and fwd_stats is not None and edge_out and dyo is not None

@@ -403,6 +403,46 @@ def softmax_agg16_fwd(a16, v, want_stats: bool = False):
     return (g, stats + (g,)) if want_stats else g
 
 
+# ----------------------------------------------------------------------------- block-level entry points
+def native_block_available(b: int, n: int, d: int, h: int) -> bool:
+    """One C call per direction of an encoder block (``dg_block_fwd`` / ``dg_block_bwd``: the library sequences its own launches
+    over buffers allocated here) -- exists for the throughput mode on the fused-chain path; everything else, and bench.py's
+    per-launch kernel table, runs the same launches one by one from ``block.py``.  DRUGGEN_B200_NATIVE_BLOCK=0 switches it off."""
+    return (_test_backend is None and fused_available(d, h) and attn_chain_available(b, n, d) and softmax_scores_bf16()
+            and os.environ.get("DRUGGEN_B200_NATIVE_BLOCK", "1") != "0" and not os.environ.get("DG_DEBUG_ATTN_UNFUSED")
+            and not os.environ.get("DG_DEBUG_ATTN_COMPARE") and not os.environ.get("DG_DEBUG_HOLD") and _lib.cuda_backend().native_blocks())
+
+
+def _chk_buffers(ts, dev):
+    for t in ts:
+        if t is not None and (t.device != dev or not t.is_contiguous()):
+            raise RuntimeError("druggen_b200 block entry points take contiguous tensors of the parameters' device")
+
+
+def block_fwd(io: dict, params, b: int, n: int, d: int, h: int, heads: int, flags: int, eps: float = 1e-5) -> None:
+    """``dg_block_fwd`` over the named buffers of ``io`` (``_lib.BLK_SLOTS``)."""
+    _chk(*params)
+    _chk_buffers(io.values(), params[0].device)
+    _be().block_fwd(io, params, b, n, d, h, heads, flags, eps, _mlp_ws(params[18]))
+
+
+def block_bwd(io: dict, params, grads, b: int, n: int, d: int, h: int, heads: int, flags: int, eps: float = 1e-5) -> None:
+    """``dg_block_bwd`` over the named buffers of ``io``; ``grads``: 30 zeroed tensors (None where no consumer) or None."""
+    _chk(*params, *([] if grads is None else grads))
+    _chk_buffers(io.values(), params[0].device)
+    _be().block_bwd(io, params, grads, b, n, d, h, heads, flags, eps, _mlp_ws(params[18]))
+
+
+def encoder_fwd(x, y, x_out, y_out, params, depth: int, scratch: dict, b: int, n: int, d: int, h: int, heads: int, last_edge_out: bool,
+                eps: float = 1e-5, ws=None) -> None:
+    """``dg_encoder_fwd``: ``depth`` blocks in one call; ``params`` = depth x 30 tensors, ``scratch`` = named DG_BLK_* buffers;
+    ``ws``: the packed-weight workspace (``_mlp_ws``), allocated here unless given (CUDA-graph capture: nothing may be allocated)."""
+    _chk(x, y, x_out, y_out, *params)
+    _chk_buffers(scratch.values(), x.device)
+    _be().encoder_fwd(x, y, x_out, y_out, params, depth, scratch, b, n, d, h, heads, last_edge_out, eps,
+                      _mlp_ws(params[18]) if ws is None else ws)
+
+
 def set_option(key: int, value: int) -> None:
     """Process-wide tuning switches of the library (``_lib.OPT_*``)."""
     if _test_backend is None:

@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .block import BLOCK_PARAM_NAMES, encoder_block
+from .block import BLOCK_PARAM_NAMES, encoder_block, encoder_forward_nograd
 
 
 class MLP(nn.Module):
@@ -109,6 +109,14 @@ class TransformerEncoder(nn.Module):
 
     def forward(self, x, y):
         last = len(self.Encoder_Blocks) - 1
+        blocks = list(self.Encoder_Blocks)
+        no_graph = not torch.is_grad_enabled() or not (
+            x.requires_grad or y.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if no_graph and blocks and not any(b.training and b._drop > 0.0 for b in blocks):
+            # inference / no-grad passes: the whole encoder as one library call where the block-level entry points apply
+            with torch.no_grad():
+                return encoder_forward_nograd(x.contiguous(), y.contiguous(), [b._params() for b in blocks], blocks[0].attn.heads,
+                                              not self._discard_final_edge)
         for i, block in enumerate(self.Encoder_Blocks):
             x, y = block(x, y, not (self._discard_final_edge and i == last))
         return x, y

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DG_ABI_VERSION 5
+#define DG_ABI_VERSION 6
 #define DG_PREC_FP32 0
 #define DG_PREC_BF16 1
 #define DG_PREC_BF16X3 2
@@ -240,6 +240,70 @@ int dg_pack_bits(const void* vecs, int elem_bytes, unsigned long long* bits, int
  * words = uint64 words per fingerprint: a power of two <= 32 (pad with zero words). */
 int dg_tanimoto_agg(const unsigned long long* stock_bits, const int* stock_cnt, long long S, const unsigned long long* gen_bits,
                     const int* gen_cnt, long long G, int words, int agg, float p, float* out_max, double* out_sum, void* stream);
+
+/* ---- block-level entry points (dg_block_fwd / dg_block_bwd) ------------------------------------------------------
+ * One host call per direction of an encoder block, Encoder_Block.forward (layers.py:174-193) and its autograd backward, in the
+ * tensor-core throughput mode (DG_PREC_BF16; D == 128, H in {128,256,384}, 4 <= N <= 212): a fixed sequence of the launches
+ * above on the caller's stream over caller-owned buffers -- no allocation, no synchronisation, capturable into a CUDA graph.
+ * `params`: the block's DG_BLOCK_PARAMS device pointers in the reference's state-dict order: ln1.{weight,bias},
+ * attn.{q,k,v,e,out_e,out_n}.{weight,bias}, ln3.*, ln4.*, mlp.{fc1,fc2}.*, mlp2.{fc1,fc2}.*, ln5.*, ln6.*.
+ * `io`: DG_BLK_COUNT device pointers (NULL where a call does not need the buffer).  Node-sized buffers are [B*N, D] fp32,
+ * edge-sized ones [B*N*N, D] fp32 unless noted.  workspace: >= 2 * (H/128) * 32768 bytes, 128-byte aligned. */
+#define DG_BLOCK_PARAMS 30
+enum {
+  DG_BLK_X = 0,    /* in : block input x */
+  DG_BLK_Y,        /* in : block input y (edge) */
+  DG_BLK_X_OUT,    /* fwd out */
+  DG_BLK_Y_OUT,    /* fwd out (edge); unused without DG_BLKF_EDGE_OUT */
+  DG_BLK_X1,       /* LN1(x)                                   fwd: scratch or kept;  bwd: kept input or scratch (recomputed) */
+  DG_BLK_Q, DG_BLK_K, DG_BLK_V,      /* projections of x1     (same) */
+  DG_BLK_G,        /* softmax-aggregate g                      (same; with DG_BLKF_STATS the backward reads the forward's) */
+  DG_BLK_ON,       /* out_n(g)                                 (same) */
+  DG_BLK_X3,       /* LN3(x1 + on)                             (same) */
+  DG_BLK_STAT_M, DG_BLK_STAT_INV,    /* softmax max and 1/sum per (molecule, query atom, channel); fwd: written with DG_BLKF_STATS */
+  DG_BLK_Y3,       /* LN4(y + out_e(A)) (edge)                 fwd: scratch or kept; without a live edge output: scratch for the scores */
+  DG_BLK_A16,      /* the scores A, bf16 (edge, 2 bytes)       (same) */
+  DG_BLK_E,        /* E = e(y) (edge)                          fwd: written with DG_BLKF_KEEP, and by a block without edge output */
+  DG_BLK_Z4,       /* y + out_e(A) (edge)                      fwd: written with DG_BLKF_KEEP */
+  DG_BLK_DXO,      /* bwd in : d x_out (NULL = zeros) */
+  DG_BLK_DYO,      /* bwd in : d y_out (NULL = the edge output has no consumer) */
+  DG_BLK_DX,       /* bwd out */
+  DG_BLK_DY,       /* bwd out (edge) */
+  DG_BLK_N_DZ, DG_BLK_N_DX3, DG_BLK_N_DZ3, DG_BLK_N_DG, DG_BLK_N_DQ, DG_BLK_N_DK, DG_BLK_N_DV, DG_BLK_N_T0, DG_BLK_N_T1, /* bwd scratch, node */
+  DG_BLK_N_H,      /* bwd scratch [B*N, H] bf16 (only with weight gradients) */
+  DG_BLK_N_MASK,   /* bwd scratch [B*N, H/64] uint64 */
+  DG_BLK_E_A, DG_BLK_E_B,            /* bwd scratch, edge fp32 (only with a live edge output) */
+  DG_BLK_E_H,      /* bwd scratch, bf16: [B*N*N, H] with weight gradients and a live edge output, else [B*N*N, D] */
+  DG_BLK_E_MASK,   /* bwd scratch [B*N*N, H/64] uint64 (only with a live edge output) */
+  DG_BLK_SCRATCH,  /* bwd scratch, 2 D floats */
+  DG_BLK_COUNT
+};
+#define DG_BLKF_EDGE_OUT 1 /* the block's edge output has a consumer (every block but the Discriminator's last, models.py:202-207) */
+#define DG_BLKF_KEEP 2     /* fwd: also write E and Z4 (the caller keeps X1..X3, Y3, A16, E, Z4 for dg_block_bwd); bwd: they are valid */
+#define DG_BLKF_STATS 4    /* fwd: write STAT_M / STAT_INV; bwd: G / STAT_M / STAT_INV hold the forward's values */
+/* x_out, y_out = Encoder_Block.forward(x, y). */
+int dg_block_fwd(void* const* io, const float* const* params, int B, int N, int D, int H, int heads, int flags, float eps,
+                 void* workspace, long long workspace_bytes, void* stream);
+/* dx, dy and the parameter gradients of one block from d x_out / d y_out (what autograd runs for layers.py:174-193).  Without
+ * DG_BLKF_KEEP the forward intermediates are recomputed from (x, y) into their io slots first.  `grads`: DG_BLOCK_PARAMS device
+ * pointers, ZEROED by the caller, accumulated into (+=); NULL = no parameter gradients (dgrad-only pass: the gradient penalty's
+ * input gradient, the Generator step's pass through the Discriminator).  Entries of parameters without a consumer (out_e, ln4,
+ * mlp2, ln6 when the edge output is not live) may be NULL and are left untouched. */
+int dg_block_bwd(void* const* io, const float* const* params, float* const* grads, int B, int N, int D, int H, int heads, int flags,
+                 float eps, void* workspace, long long workspace_bytes, void* stream);
+/* TransformerEncoder.forward (layers.py:221-234) without a graph: `depth` blocks, params = depth x DG_BLOCK_PARAMS pointers.
+ * `scratch`: a DG_BLK_* table holding X1..X3, Y3, A16 (E when !last_edge_out) and, for depth > 1, ping-pong buffers in the
+ * X_OUT / Y_OUT slots; x_out / y_out also serve as ping-pong buffers (y_out may be NULL only if depth <= 2 and !last_edge_out). */
+int dg_encoder_fwd(const float* x, const float* y, float* x_out, float* y_out, const float* const* params, int depth,
+                   void* const* scratch, int B, int N, int D, int H, int heads, int last_edge_out, float eps, void* workspace,
+                   long long workspace_bytes, void* stream);
+/* Launches issued by the block-level entry points so far (process-wide). */
+long long dg_native_launches(void);
+/* Launch probe: every launch issued by the block-level entry points whose key (the text druggen_b200/_lib.py gives the same
+ * launch, e.g. "mlp_bwd_ln[R=4147200,H=384,fused,mask]") equals `key` is bracketed by CUDA events on its stream; NULL / "" stops.
+ * dg_probe_read: waits for the recorded launches, returns their number and summed duration, and forgets them. */
+int dg_probe_set(const char* key);
+int dg_probe_read(long long* launches, double* total_ms);
 
 /* debug: with a device buffer of 148*64 int64 set, every chain-kernel launch (dg_mlp_*, dg_attn_edge_fwd) writes
  * per-CTA phase cycle counters [CTA][4 roles][16 phases] (tools/chain_profile.py); NULL switches it off. */

@@ -55,6 +55,7 @@ SIGNATURES = {
     # block-level entry points: (io table, params table[, grads table], B, N, D, H, heads, flags, eps, workspace, bytes)
     "dg_block_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _LL, _P],
     "dg_block_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _LL, _P],
+    "dg_block_bwd_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _LL, _P],
     "dg_encoder_fwd": [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _F, _P, _LL, _P],
 }
 INFO_SYMBOLS = ("dg_abi_version", "dg_last_error", "dg_has_tcgen05", "dg_set_option", "dg_get_option", "dg_debug_chain_profile",
@@ -62,7 +63,9 @@ INFO_SYMBOLS = ("dg_abi_version", "dg_last_error", "dg_has_tcgen05", "dg_set_opt
 # slots of the block-level entry points' buffer table, in the order of the DG_BLK_* enum of include/druggen_b200.h
 BLK_SLOTS = ("X", "Y", "X_OUT", "Y_OUT", "X1", "Q", "K", "V", "G", "ON", "X3", "STAT_M", "STAT_INV", "Y3", "A16", "E", "Z4",
              "DXO", "DYO", "DX", "DY", "N_DZ", "N_DX3", "N_DZ3", "N_DG", "N_DQ", "N_DK", "N_DV", "N_T0", "N_T1", "N_H", "N_MASK",
-             "E_A", "E_B", "E_H", "E_MASK", "SCRATCH")
+             "E_A", "E_B", "E_H", "E_MASK", "SCRATCH", "UX", "UY", "C_X", "C_Y", "C_DXO", "C_DYO", "N_ARENA", "N_H2", "N_H3",
+             "ES0", "ES1", "ES2", "ES3", "ES4", "ES5", "ES6", "ES7", "ES8", "E_H2", "E_H3", "WT")
+BB_NODE_SLOTS = 28
 BLK = {name: i for i, name in enumerate(BLK_SLOTS)}
 BLKF_EDGE_OUT, BLKF_KEEP, BLKF_STATS = 1, 2, 4
 BLOCK_PARAMS = 30
@@ -204,6 +207,10 @@ class CudaBackend:
     def block_bwd(self, io, params, grads, b, n, d, h, heads, flags, eps, ws):
         self._native("dg_block_bwd", self._table(io), self._ptrs(params), None if grads is None else self._ptrs(grads), b, n, d, h,
                      heads, flags, eps, _ptr(ws), ws.numel())
+
+    def block_bwd_bwd(self, io, params, grads, b, n, d, h, heads, flags, eps, ws):
+        self._native("dg_block_bwd_bwd", self._table(io), self._ptrs(params), self._ptrs(grads), b, n, d, h, heads, flags, eps,
+                     _ptr(ws), ws.numel())
 
     def encoder_fwd(self, x, y, x_out, y_out, params, depth, scratch, b, n, d, h, heads, last_edge_out, eps, ws):
         self._native("dg_encoder_fwd", _ptr(x), _ptr(y), _ptr(x_out), _ptr(y_out), self._ptrs(params), depth, self._table(scratch),

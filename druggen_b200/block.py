@@ -355,16 +355,7 @@ def _native_backward(x, y, dxo, dyo, params, heads, edge_out, want_params, fwd_s
     # bf16: h, then dh of the edge MLP (weight gradients only), then dE
     io["E_H"] = torch.empty((r, hid if (want_params and live) else d), dtype=torch.bfloat16, device=dev)
     io["SCRATCH"] = torch.empty(2 * d, **f32)
-    grads = None
-    if want_params:
-        dead = () if live else ("attn.out_e.", "ln4.", "mlp2.", "ln6.")
-        sizes = [0 if nm.startswith(dead) else params[i].numel() for i, nm in enumerate(BLOCK_PARAM_NAMES)] if dead else \
-                [t.numel() for t in params]
-        flat = torch.zeros(sum(sizes), **f32)
-        grads, o = [], 0
-        for t, sz in zip(params, sizes):
-            grads.append(flat[o:o + sz].view_as(t) if sz else None)
-            o += sz
+    grads = _flat_grads(params, live, dev) if want_params else None
     K.block_bwd(io, list(params), grads, b, n, d, hid, heads, flags)
     return dx.view(b, n, d), dy.view(b, n, n, d), (grads if grads is not None else [None] * len(BLOCK_PARAM_NAMES))
 
@@ -516,6 +507,64 @@ def block_backward(x, y, dxo, dyo, params: Sequence[torch.Tensor], heads: int, e
     return dx.view(b, n, d), dy.view(b, n, n, d), grads
 
 
+def _flat_grads(params, live, dev, second_order=False):
+    """30 gradient tensors as views of ONE zeroed buffer (None for the parameters a block without a live edge output never
+    touches: out_e, ln4, mlp2, ln6 -- and, in the second-order pass, for ln5.bias / ln6.bias: the backward program does not
+    depend on the output LayerNorms' shifts)."""
+    dead = (() if live else ("attn.out_e.", "ln4.", "mlp2.", "ln6.")) + (("ln5.bias", "ln6.bias") if second_order else ())
+    sizes = [0 if (dead and nm.startswith(dead)) else params[i].numel() for i, nm in enumerate(BLOCK_PARAM_NAMES)]
+    flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+    grads, o = [], 0
+    for t, sz in zip(params, sizes):
+        grads.append(flat[o:o + sz].view_as(t) if sz else None)
+        o += sz
+    return grads
+
+
+def _native_backward_backward(x, y, dxo, dyo, ux, uy, params, heads, edge_out, fwd_saved):
+    """``block_backward_backward`` as ONE library call (``dg_block_bwd_bwd``).  Same return convention."""
+    from ._lib import BB_NODE_SLOTS, BLKF_EDGE_OUT, BLKF_KEEP
+    b, n, d = x.shape
+    hid = params[_IDX["mlp.fc1.weight"]].shape[0]
+    bn, r = b * n, b * n * n
+    dev = x.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    bf16 = dict(dtype=torch.bfloat16, device=dev)
+    live = edge_out and dyo is not None
+    kept = fwd_saved is not None and live
+    z2 = lambda t, like: (t if t is not None else torch.zeros_like(like)).reshape(-1, d).contiguous()  # noqa: E731
+    io = {"X": x.reshape(bn, d), "Y": y.reshape(r, d), "UX": z2(ux, x), "UY": z2(uy, y), "DXO": z2(dxo, x),
+          "DYO": dyo.reshape(r, d).contiguous() if live else None}
+    flags = BLKF_EDGE_OUT if edge_out else 0
+    node_f = torch.empty((9, bn, d), **f32)
+    io["G"], io["STAT_M"], io["STAT_INV"], io["ON"], io["X3"] = node_f[:5].unbind(0)
+    if kept:
+        for slot, nm in (("X1", "x1"), ("Q", "q"), ("K", "k"), ("V", "v"), ("Y3", "y3"), ("E", "e"), ("Z4", "z4")):
+            io[slot] = fwd_saved[nm].reshape(-1, d)
+        flags |= BLKF_KEEP
+    else:
+        io["X1"], io["Q"], io["K"], io["V"] = node_f[5:].unbind(0)
+        io["E"] = torch.empty((r, d), **f32)
+        if live:
+            io["Y3"], io["Z4"] = torch.empty((r, d), **f32), torch.empty((r, d), **f32)
+    io["N_ARENA"] = torch.empty((BB_NODE_SLOTS, bn, d), **f32)
+    io["N_H"], io["N_H2"], io["N_H3"] = (torch.empty((bn, hid), **bf16) for _ in range(3))
+    io["N_MASK"] = torch.empty((bn, hid // 64), dtype=torch.int64, device=dev)
+    for i in ((0, 1, 2, 3, 4, 5, 6, 7, 8) if live else (0, 5, 6, 7, 8)):
+        io[f"ES{i}"] = torch.empty((r, d), **f32)
+    if live:
+        io["E_H"], io["E_H2"], io["E_H3"] = (torch.empty((r, hid), **bf16) for _ in range(3))
+        io["E_MASK"] = torch.empty((r, hid // 64), dtype=torch.int64, device=dev)
+    io["WT"] = torch.empty(2 * hid * d, **f32)
+    io["SCRATCH"] = torch.empty(2 * d, **f32)
+    c_x, c_y, c_dxo = torch.empty((bn, d), **f32), torch.empty((r, d), **f32), torch.empty((bn, d), **f32)
+    c_dyo = torch.empty((r, d), **f32) if live else None
+    io["C_X"], io["C_Y"], io["C_DXO"], io["C_DYO"] = c_x, c_y, c_dxo, c_dyo
+    cp = _flat_grads(params, live, dev, second_order=True)
+    K.block_bwd_bwd(io, list(params), cp, b, n, d, hid, heads, flags)
+    return (c_x.view(b, n, d), c_y.view(b, n, n, d), c_dxo.view(b, n, d), c_dyo.view(b, n, n, d) if live else None, cp)
+
+
 def block_backward_backward(x, y, dxo, dyo, ux, uy, params: Sequence[torch.Tensor], heads: int, edge_out: bool = True,
                             fwd_saved=None):
     """Second-order pass of the block as a hand-sequenced list of raw kernel launches (no autograd graph): the gradient of
@@ -535,6 +584,8 @@ def block_backward_backward(x, y, dxo, dyo, ux, uy, params: Sequence[torch.Tenso
     parameters without a consumer keep None."""
     p = lambda n: params[_IDX[n]]  # noqa: E731
     b, n, d = x.shape
+    if K.native_block_available(b, n, d, p("mlp.fc1.weight").shape[0]):
+        return _native_backward_backward(x, y, dxo, dyo, ux, uy, params, heads, edge_out, fwd_saved)
     c = 1.0 / math.sqrt(d // heads)
     narrow = K.fused_available(d, p("mlp.fc1.weight").shape[0])
     cp = [None] * len(BLOCK_PARAM_NAMES)

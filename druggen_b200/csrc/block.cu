@@ -359,3 +359,232 @@ extern "C" int dg_block_bwd(void* const* io, const float* const* P, float* const
           "add_ln_bwd");
   return q.done();
 }
+
+// ---- second-order pass ----------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+  // out[c, r] = in[r, c]; the MLP weights (<= 384 x 128): a few dozen KB, one pass
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows * cols; i += gridDim.x * blockDim.x) {
+    const int r = i / cols, c = i - r * cols;
+    out[(long long)c * rows + r] = in[i];
+  }
+}
+
+// a[i] += b[i] over three equally sized pairs in one launch (c[q], c[k], c[v] += their second contributions)
+__global__ void add3_kernel(float4* a0, const float4* b0, float4* a1, const float4* b1, float4* a2, const float4* b2, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 x = a0[i], y = b0[i];
+    a0[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+    x = a1[i]; y = b1[i];
+    a1[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+    x = a2[i]; y = b2[i];
+    a2[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+  }
+}
+
+int zero(Seq& q, void* p, long long bytes) {
+  if (!q.rc && cudaMemsetAsync(p, 0, (size_t)bytes, q.s) != cudaSuccess) q.rc = dg::fail("dg_block_bwd_bwd: memset failed");
+  return q.rc;
+}
+
+// node-sized scratch slots of dg_block_bwd_bwd inside DG_BLK_N_ARENA
+enum {
+  nT5, nM, nDX3, nDZ3, nDG, nDV, nDQ, nDK, nP0, nP1, nCDX1, nCDQ, nCDK, nCDV, nCQ, nCK, nCV, nCDG, nCDZ3, nCDX3, nCZ3, nCT5, nCMN,
+  nCX3, nCG, nDQ2, nDK2, nDV2, kNodeSlots
+};
+static_assert(kNodeSlots == DG_BLK_BB_NODE_SLOTS, "node arena");
+
+// forward m = xin + fc2(h) and the first-order backward (t = LN^T dout, dh, dxin) of LN(xin + mlp(xin)), intermediates kept
+void mlp_recompute(Seq& q, const float* xin, const float* dout, const float* const* P, int fc1, int ln, float* t, void* h, void* mask,
+                   float* m, float* dxin, void* dh, long long rows, int D, int H, float eps, void* ws, long long wsb) {
+  DG_STEP(q, dg_mlp_bwd_ln(xin, dout, P[fc1], P[fc1 + 1], P[fc1 + 2], P[fc1 + 3], P[ln], t, h, mask, nullptr, nullptr, rows, D, H, eps, ws, wsb, q.s),
+          "mlp_bwd_ln[R=%lld,H=%d,fused,mask]", rows, H);
+  DG_STEP(q, dg_rows_gemm(h, P[fc1 + 2], 1, P[fc1 + 3], 0, nullptr, xin, m, rows, H, D, kP, DG_A_BF16, q.s),
+          "rows_gemm[R=%lld,K=%d,N=%d,%s+resid,a16]", rows, H, D, kPrec);
+  DG_STEP(q, dg_mlp_bwd_dgrad(t, nullptr, mask, P[fc1], P[fc1 + 2], dxin, dh, rows, D, H, ws, wsb, q.s), "mlp_bwd_dgrad[R=%lld,H=%d,fused,mask]", rows, H);
+}
+
+// reverse of dxin = t + ((t W2) * M) W1 given u = c[dxin]: c[t] into c_t; c[W2] += t^T tM, c[W1] += dh^T u
+void mlp_second(Seq& q, const float* u, const float* t, const void* mask, const void* dh, const float* const* P, int fc1, float* const* grads,
+                float* c_t, void* tm, float* wt, long long rows, int D, int H, void* ws, long long wsb) {
+  if (!q.rc) {      // the dgrad chain with the two weights transposed into each other's role
+    transpose_kernel<<<96, 256, 0, q.s>>>(P[fc1 + 2], wt, D, H);                  // W2 [D,H] -> [H,D]
+    transpose_kernel<<<96, 256, 0, q.s>>>(P[fc1], wt + (long long)H * D, H, D);   // W1 [H,D] -> [D,H]
+  }
+  DG_STEP(q, dg_mlp_bwd_dgrad(u, nullptr, mask, wt, wt + (long long)H * D, c_t, tm, rows, D, H, ws, wsb, q.s),
+          "mlp_bwd_dgrad[R=%lld,H=%d,fused,mask]", rows, H);
+  DG_STEP(q, dg_gemm_tn(t, tm, grads[fc1 + 2], nullptr, rows, D, H, kP, DG_OUT_BF16, q.s), "gemm_tn[R=%lld,M=%d,N=%d,%s,b16]", rows, D, H, kPrec);
+  DG_STEP(q, dg_gemm_tn(dh, u, grads[fc1], nullptr, rows, H, D, kP, DG_A_BF16, q.s), "gemm_tn[R=%lld,M=%d,N=%d,%s,a16]", rows, H, D, kPrec);
+}
+
+// reverse of m = xin + fc2(relu(fc1(xin))) given c[m]: c[xin] into c_xin; the four parameter cotangents accumulate
+void mlp_first(Seq& q, const float* c_m, const void* h, const void* mask, const float* xin, const float* const* P, int fc1,
+               float* const* grads, float* c_xin, void* ch, long long rows, int D, int H, void* ws, long long wsb) {
+  DG_STEP(q, dg_mlp_bwd_dgrad(c_m, nullptr, mask, P[fc1], P[fc1 + 2], c_xin, ch, rows, D, H, ws, wsb, q.s),
+          "mlp_bwd_dgrad[R=%lld,H=%d,fused,mask]", rows, H);
+  DG_STEP(q, dg_gemm_tn(c_m, h, grads[fc1 + 2], grads[fc1 + 3], rows, D, H, kP, DG_OUT_BF16, q.s), "gemm_tn[R=%lld,M=%d,N=%d,%s,b16]", rows, D, H, kPrec);
+  DG_STEP(q, dg_gemm_tn(ch, xin, grads[fc1], grads[fc1 + 1], rows, H, D, kP, DG_A_BF16, q.s), "gemm_tn[R=%lld,M=%d,N=%d,%s,a16]", rows, H, D, kPrec);
+}
+
+}  // namespace
+
+extern "C" int dg_block_bwd_bwd(void* const* io, const float* const* P, float* const* grads, int B, int N, int D, int H, int heads,
+                                int flags, float eps, void* ws, long long wsb, void* stream) {
+  const char* who = "dg_block_bwd_bwd";
+  if (shape_check(who, B, N, D, H, heads, wsb, ws)) return 1;
+  const bool edge_out = flags & DG_BLKF_EDGE_OUT, kept = flags & DG_BLKF_KEEP;
+  const bool live = edge_out && io[DG_BLK_DYO] != nullptr;
+  if (kept && !live) return dg::fail("%s: kept intermediates need a live edge output", who);
+  if (grads == nullptr) return dg::fail("%s: the parameter cotangent table is required", who);
+  if (need(who, io, {DG_BLK_X, DG_BLK_Y, DG_BLK_DXO, DG_BLK_UX, DG_BLK_UY, DG_BLK_X1, DG_BLK_Q, DG_BLK_K, DG_BLK_V, DG_BLK_G, DG_BLK_STAT_M,
+                     DG_BLK_STAT_INV, DG_BLK_ON, DG_BLK_X3, DG_BLK_E, DG_BLK_C_X, DG_BLK_C_Y, DG_BLK_C_DXO, DG_BLK_N_ARENA, DG_BLK_N_H,
+                     DG_BLK_N_H2, DG_BLK_N_H3, DG_BLK_N_MASK, DG_BLK_ES0, DG_BLK_ES5, DG_BLK_ES6, DG_BLK_ES7, DG_BLK_ES8, DG_BLK_WT,
+                     DG_BLK_SCRATCH}))
+    return 1;
+  if (live && need(who, io, {DG_BLK_Y3, DG_BLK_Z4, DG_BLK_C_DYO, DG_BLK_ES1, DG_BLK_ES2, DG_BLK_ES3, DG_BLK_ES4, DG_BLK_E_H, DG_BLK_E_H2,
+                             DG_BLK_E_H3, DG_BLK_E_MASK}))
+    return 1;
+  for (int i = 0; i < kNumParams; ++i) {
+    const bool edge_only = i == OE_W || i == OE_B || i == LN4_W || i == LN4_B || (i >= FC1E_W && i <= FC2E_B) || i == LN6_W || i == LN6_B;
+    if (i == LN5_B || i == LN6_B) continue;            // (the backward program does not depend on the output LayerNorms' shifts)
+    if (grads[i] == nullptr && (live || !edge_only)) return dg::fail("%s: cotangent buffer %d is missing", who, i);
+  }
+  const long long BN = (long long)B * N, R = BN * N, nb = BN * D * (long long)sizeof(float);
+  const float c = 1.0f / std::sqrt((float)(D / heads));
+  float* scratch = at(io, DG_BLK_SCRATCH);
+  float* arena = at(io, DG_BLK_N_ARENA);
+  auto ns = [&](int slot) { return arena + (long long)slot * BN * D; };
+  const float *x = at(io, DG_BLK_X), *y = at(io, DG_BLK_Y), *dxo = at(io, DG_BLK_DXO), *dyo = at(io, DG_BLK_DYO), *ux = at(io, DG_BLK_UX),
+              *uy = at(io, DG_BLK_UY);
+  float *x1 = at(io, DG_BLK_X1), *qq = at(io, DG_BLK_Q), *kk = at(io, DG_BLK_K), *vv = at(io, DG_BLK_V), *g = at(io, DG_BLK_G),
+        *sm = at(io, DG_BLK_STAT_M), *si = at(io, DG_BLK_STAT_INV), *on = at(io, DG_BLK_ON), *x3 = at(io, DG_BLK_X3), *e = at(io, DG_BLK_E),
+        *y3 = at(io, DG_BLK_Y3), *z4 = at(io, DG_BLK_Z4);
+  float *s0 = at(io, DG_BLK_ES0), *s1 = at(io, DG_BLK_ES1), *s2 = at(io, DG_BLK_ES2), *s3 = at(io, DG_BLK_ES3), *s4 = at(io, DG_BLK_ES4),
+        *s5 = at(io, DG_BLK_ES5), *s6 = at(io, DG_BLK_ES6), *s7 = at(io, DG_BLK_ES7), *s8 = at(io, DG_BLK_ES8);
+  float* wt = at(io, DG_BLK_WT);
+  const int w3[3] = {Q_W, K_W, V_W};
+  Seq q(stream);
+  // ---- 1a. forward recompute (the node projections and the edge chain's outputs may come from the forward)
+  if (!kept) {
+    node_prologue(q, io, P, BN, D, eps);
+    if (live)
+      DG_STEP(q, dg_attn_edge_fwd(y, qq, kk, P[E_W], P[E_B], P[OE_W], P[OE_B], P[LN4_W], P[LN4_B], c, y3, nullptr, e, z4, B, N, D, eps, ws, wsb, q.s),
+              "attn_edge_fwd[fused+e+z]");
+    else
+      DG_STEP(q, dg_rows_gemm(y, P[E_W], 1, P[E_B], 0, nullptr, nullptr, e, R, D, D, kP, 0, q.s), "rows_gemm[R=%lld,K=%d,N=%d,%s]", R, D, D, kPrec);
+  }
+  float* a4 = s0;      // fp32 scores: the second-order kernels differentiate the softmax of THESE
+  DG_STEP(q, dg_attn_scores_fwd(qq, kk, vv, e, c, a4, g, sm, si, B, N, D, q.s), "attn_scores_fwd[fused]");
+  node_epilogue(q, io, P, BN, D, eps);
+  // ---- 1b. first-order backward recompute (intermediates kept)
+  mlp_recompute(q, x3, dxo, P, FC1_W, LN5_W, ns(nT5), io[DG_BLK_N_H], io[DG_BLK_N_MASK], ns(nM), ns(nDX3), io[DG_BLK_N_H2], BN, D, H, eps, ws, wsb);
+  DG_STEP(q, dg_add_ln_bwd(ns(nDX3), x1, on, P[LN3_W], ns(nDZ3), scratch, scratch + D, BN, D, eps, 0, q.s), "add_ln_bwd");
+  DG_STEP(q, dg_rows_gemm(ns(nDZ3), P[ON_W], 0, nullptr, 0, nullptr, nullptr, ns(nDG), BN, D, D, kP, 0, q.s), "rows_gemm[R=%lld,K=%d,N=%d,%s]", BN, D, D, kPrec);
+  float *t6 = s1, *m_e = s2, *dy3 = s3, *dz4 = s4, *dA = s5;
+  if (live) {
+    mlp_recompute(q, y3, dyo, P, FC1E_W, LN6_W, t6, io[DG_BLK_E_H], io[DG_BLK_E_MASK], m_e, dy3, io[DG_BLK_E_H2], R, D, H, eps, ws, wsb);
+    DG_STEP(q, dg_add_ln_bwd(dy3, z4, nullptr, P[LN4_W], dz4, scratch, scratch + D, R, D, eps, 0, q.s), "add_ln_bwd");
+    DG_STEP(q, dg_rows_gemm(dz4, P[OE_W], 0, nullptr, 0, nullptr, nullptr, dA, R, D, D, kP, 0, q.s), "rows_gemm[R=%lld,K=%d,N=%d,%s]", R, D, D, kPrec);
+  }
+  zero(q, ns(nDV), nb);
+  DG_STEP(q, dg_softmax_agg_bwd(ns(nDG), a4, vv, dA, ns(nDV), live ? 1 : 0, B, N, D, q.s), "softmax_agg_bwd");      // dA: out_e path + softmax path
+  zero(q, ns(nDK), nb);
+  float* dE = s6;
+  DG_STEP(q, dg_modulate_bwd(dA, qq, kk, e, c, ns(nDQ), ns(nDK), dE, B, N, D, q.s), "modulate_bwd");
+  const float* dx1 = ns(nDZ3);
+  {
+    const int dt[3] = {nDQ, nDK, nDV}, out[3] = {nP0, nP1, nP0};
+    for (int i = 0; i < 3; ++i) {
+      DG_STEP(q, dg_rows_gemm(ns(dt[i]), P[w3[i]], 0, nullptr, 0, nullptr, dx1, ns(out[i]), BN, D, D, kP, 0, q.s),
+              "rows_gemm[R=%lld,K=%d,N=%d,%s+resid]", BN, D, D, kPrec);
+      dx1 = ns(out[i]);
+    }
+  }
+  // ---- 2. reverse of the first-order backward program
+  float* c_x = at(io, DG_BLK_C_X);
+  DG_STEP(q, dg_add_ln_bwd_bwd(ux, nullptr, nullptr, dx1, x, nullptr, P[LN1_W], ns(nCDX1), c_x, grads[LN1_W], BN, D, eps, q.s), "add_ln_bwd_bwd");
+  {
+    const int dt[3] = {nDQ, nDK, nDV}, cd[3] = {nCDQ, nCDK, nCDV};
+    for (int i = 0; i < 3; ++i) {                       // dx1 = dz3 + dq Wq + dk Wk + dv Wv
+      DG_STEP(q, dg_rows_gemm(ns(nCDX1), P[w3[i]], 1, nullptr, 0, nullptr, nullptr, ns(cd[i]), BN, D, D, kP, 0, q.s),
+              "rows_gemm[R=%lld,K=%d,N=%d,%s]", BN, D, D, kPrec);
+      DG_STEP(q, dg_gemm_tn(ns(dt[i]), ns(nCDX1), grads[w3[i]], nullptr, BN, D, D, kP, 0, q.s), "gemm_tn[R=%lld,M=%d,N=%d,%s]", BN, D, D, kPrec);
+    }
+  }
+  float* c_dE = s7;                                      // dy = dz4 + dE We
+  DG_STEP(q, dg_rows_gemm(uy, P[E_W], 1, nullptr, 0, nullptr, nullptr, c_dE, R, D, D, kP, 0, q.s), "rows_gemm[R=%lld,K=%d,N=%d,%s]", R, D, D, kPrec);
+  DG_STEP(q, dg_gemm_tn(dE, uy, grads[E_W], nullptr, R, D, D, kP, 0, q.s), "gemm_tn[R=%lld,M=%d,N=%d,%s]", R, D, D, kPrec);
+  float *c_dA = s6, *c_E = s8;                           // (dE is dead: its slot takes c[dA])
+  zero(q, ns(nCK), nb);
+  DG_STEP(q, dg_modulate_bwd_bwd(ns(nCDQ), ns(nCDK), c_dE, dA, qq, kk, e, c, c_dA, ns(nCQ), ns(nCK), c_E, B, N, D, q.s), "modulate_bwd_bwd");
+  float* c_A = s5;                                       // (dA is dead)
+  zero(q, ns(nCV), nb);
+  DG_STEP(q, dg_softmax_agg_bwd_bwd(c_dA, ns(nCDV), ns(nDG), a4, vv, ns(nCDG), c_A, ns(nCV), B, N, D, q.s), "softmax_agg_bwd_bwd");
+  float *c_z4 = nullptr, *c_me = nullptr;
+  if (live) {
+    float* c_dz4 = s7;                                   // da = dz4 Woe;  dy = dz4 + ...   (c[dE] is dead)
+    DG_STEP(q, dg_rows_gemm(c_dA, P[OE_W], 1, nullptr, 0, nullptr, uy, c_dz4, R, D, D, kP, 0, q.s), "rows_gemm[R=%lld,K=%d,N=%d,%s+resid]", R, D, D, kPrec);
+    DG_STEP(q, dg_gemm_tn(dz4, c_dA, grads[OE_W], nullptr, R, D, D, kP, 0, q.s), "gemm_tn[R=%lld,M=%d,N=%d,%s]", R, D, D, kPrec);
+    float* c_dy3 = s4;                                   // (dz4 and c[dA] are dead)
+    c_z4 = s6;
+    DG_STEP(q, dg_add_ln_bwd_bwd(c_dz4, nullptr, nullptr, dy3, z4, nullptr, P[LN4_W], c_dy3, c_z4, grads[LN4_W], R, D, eps, q.s), "add_ln_bwd_bwd");
+    float* c_t6 = s3;                                    // (dy3 is dead)
+    mlp_second(q, c_dy3, t6, io[DG_BLK_E_MASK], io[DG_BLK_E_H2], P, FC1E_W, grads, c_t6, io[DG_BLK_E_H3], wt, R, D, H, ws, wsb);
+    c_me = s1;                                           // (t6 is dead)
+    DG_STEP(q, dg_add_ln_bwd_bwd(c_t6, nullptr, nullptr, dyo, m_e, nullptr, P[LN6_W], at(io, DG_BLK_C_DYO), c_me, grads[LN6_W], R, D, eps, q.s),
+            "add_ln_bwd_bwd");
+  }
+  // dg = dz3 Won;  dx1 = dz3 + ...
+  DG_STEP(q, dg_rows_gemm(ns(nCDG), P[ON_W], 1, nullptr, 0, nullptr, ns(nCDX1), ns(nCDZ3), BN, D, D, kP, 0, q.s),
+          "rows_gemm[R=%lld,K=%d,N=%d,%s+resid]", BN, D, D, kPrec);
+  DG_STEP(q, dg_gemm_tn(ns(nDZ3), ns(nCDG), grads[ON_W], nullptr, BN, D, D, kP, 0, q.s), "gemm_tn[R=%lld,M=%d,N=%d,%s]", BN, D, D, kPrec);
+  DG_STEP(q, dg_add_ln_bwd_bwd(ns(nCDZ3), nullptr, nullptr, ns(nDX3), x1, on, P[LN3_W], ns(nCDX3), ns(nCZ3), grads[LN3_W], BN, D, eps, q.s),
+          "add_ln_bwd_bwd");
+  mlp_second(q, ns(nCDX3), ns(nT5), io[DG_BLK_N_MASK], io[DG_BLK_N_H2], P, FC1_W, grads, ns(nCT5), io[DG_BLK_N_H3], wt, BN, D, H, ws, wsb);
+  DG_STEP(q, dg_add_ln_bwd_bwd(ns(nCT5), nullptr, nullptr, dxo, ns(nM), nullptr, P[LN5_W], at(io, DG_BLK_C_DXO), ns(nCMN), grads[LN5_W], BN, D, eps,
+                               q.s),
+          "add_ln_bwd_bwd");
+  // ---- 3. first-order backward of the forward program from the injected cotangents
+  if (live) {
+    float* c_y3 = s2;                                    // (m_e is dead)
+    mlp_first(q, c_me, io[DG_BLK_E_H], io[DG_BLK_E_MASK], y3, P, FC1E_W, grads, c_y3, io[DG_BLK_E_H3], R, D, H, ws, wsb);
+    DG_STEP(q, dg_add_ln_bwd(c_y3, z4, nullptr, P[LN4_W], c_z4, grads[LN4_W], grads[LN4_B], R, D, eps, 1, q.s), "add_ln_bwd");   // c[z4] += LN4^T c[y3]
+    float* c_A2 = s4;                                    // y1 = A Woe^T + boe   (c[dy3] is dead)
+    DG_STEP(q, dg_rows_gemm(c_z4, P[OE_W], 0, nullptr, 0, nullptr, c_A, c_A2, R, D, D, kP, 0, q.s), "rows_gemm[R=%lld,K=%d,N=%d,%s+resid]", R, D, D, kPrec);
+    DG_STEP(q, dg_gemm_tn(c_z4, a4, grads[OE_W], grads[OE_B], R, D, D, kP, 0, q.s), "gemm_tn[R=%lld,M=%d,N=%d,%s]", R, D, D, kPrec);
+    c_A = c_A2;
+  }
+  mlp_first(q, ns(nCMN), io[DG_BLK_N_H], io[DG_BLK_N_MASK], x3, P, FC1_W, grads, ns(nCX3), io[DG_BLK_N_H3], BN, D, H, ws, wsb);
+  DG_STEP(q, dg_add_ln_bwd(ns(nCX3), x1, on, P[LN3_W], ns(nCZ3), grads[LN3_W], grads[LN3_B], BN, D, eps, 1, q.s), "add_ln_bwd");
+  DG_STEP(q, dg_rows_gemm(ns(nCZ3), P[ON_W], 0, nullptr, 0, nullptr, nullptr, ns(nCG), BN, D, D, kP, 0, q.s), "rows_gemm[R=%lld,K=%d,N=%d,%s]", BN, D, D, kPrec);
+  DG_STEP(q, dg_gemm_tn(ns(nCZ3), g, grads[ON_W], grads[ON_B], BN, D, D, kP, 0, q.s), "gemm_tn[R=%lld,M=%d,N=%d,%s]", BN, D, D, kPrec);
+  // attention backward from (c[g], c[A]): c[E] += in the store; its dq / dk / dv (the ring kernel STORES dk and dv) are added to
+  // c[q] / c[k] / c[v] in one small launch
+  zero(q, ns(nDQ2), 3 * nb);
+  DG_STEP(q, dg_attn_scores_bwd(ns(nCG), c_A, qq, kk, vv, e, c, sm, si, g, c_E, ns(nDQ2), ns(nDK2), ns(nDV2), B, N, D, 8, q.s), "attn_scores_bwd[fused]");
+  if (!q.rc) {
+    const long long n4 = BN * D / 4;
+    const long long blocks = (n4 + 255) / 256, cap = (long long)dg::sm_count() * 8;
+    add3_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, q.s>>>(reinterpret_cast<float4*>(ns(nCQ)), reinterpret_cast<const float4*>(ns(nDQ2)),
+                                                                     reinterpret_cast<float4*>(ns(nCK)), reinterpret_cast<const float4*>(ns(nDK2)),
+                                                                     reinterpret_cast<float4*>(ns(nCV)), reinterpret_cast<const float4*>(ns(nDV2)), n4);
+    q.rc = dg::check_launch("dg_block_bwd_bwd(add3)");
+  }
+  // E = y We^T + be;  z4 = y + y1
+  DG_STEP(q, dg_rows_gemm(c_E, P[E_W], 0, nullptr, 0, nullptr, live ? c_z4 : nullptr, io[DG_BLK_C_Y], R, D, D, kP, 0, q.s),
+          "rows_gemm[R=%lld,K=%d,N=%d,%s%s]", R, D, D, kPrec, live ? "+resid" : "");
+  DG_STEP(q, dg_gemm_tn(c_E, y, grads[E_W], grads[E_B], R, D, D, kP, 0, q.s), "gemm_tn[R=%lld,M=%d,N=%d,%s]", R, D, D, kPrec);
+  const float* c_x1 = ns(nCZ3);
+  {
+    const int ct[3] = {nCQ, nCK, nCV}, out[3] = {nP0, nP1, nP0};
+    for (int i = 0; i < 3; ++i) {
+      DG_STEP(q, dg_gemm_tn(ns(ct[i]), x1, grads[w3[i]], grads[w3[i] + 1], BN, D, D, kP, 0, q.s), "gemm_tn[R=%lld,M=%d,N=%d,%s]", BN, D, D, kPrec);
+      DG_STEP(q, dg_rows_gemm(ns(ct[i]), P[w3[i]], 0, nullptr, 0, nullptr, c_x1, ns(out[i]), BN, D, D, kP, 0, q.s),
+              "rows_gemm[R=%lld,K=%d,N=%d,%s+resid]", BN, D, D, kPrec);
+      c_x1 = ns(out[i]);
+    }
+  }
+  DG_STEP(q, dg_add_ln_bwd(c_x1, x, nullptr, P[LN1_W], c_x, grads[LN1_W], grads[LN1_B], BN, D, eps, 1, q.s), "add_ln_bwd");
+  return q.done();
+}

@@ -433,6 +433,13 @@ def block_bwd(io: dict, params, grads, b: int, n: int, d: int, h: int, heads: in
     _be().block_bwd(io, params, grads, b, n, d, h, heads, flags, eps, _mlp_ws(params[18]))
 
 
+def block_bwd_bwd(io: dict, params, grads, b: int, n: int, d: int, h: int, heads: int, flags: int, eps: float = 1e-5) -> None:
+    """``dg_block_bwd_bwd`` (the gradient penalty's second-order pass of one block) over the named buffers of ``io``."""
+    _chk(*params, *grads)
+    _chk_buffers(io.values(), params[0].device)
+    _be().block_bwd_bwd(io, params, grads, b, n, d, h, heads, flags, eps, _mlp_ws(params[18]))
+
+
 def encoder_fwd(x, y, x_out, y_out, params, depth: int, scratch: dict, b: int, n: int, d: int, h: int, heads: int, last_edge_out: bool,
                 eps: float = 1e-5, ws=None) -> None:
     """``dg_encoder_fwd``: ``depth`` blocks in one call; ``params`` = depth x 30 tensors, ``scratch`` = named DG_BLK_* buffers;

@@ -122,7 +122,8 @@ int dg_attn_scores_fwd(const float* q, const float* k, const float* v, const flo
                        float* g, float* stat_m, float* stat_inv, int B, int N, int D, void* stream);
 /* (stat_m, stat_inv: optional [B,N,D] outputs = per-channel softmax max and 1/sum, for the backward.)
  * First-order backward of the pair: de written from dg (softmax path) + da_in (out_e path, may be NULL);
- * dq, dk, dv += (zero all three first).  Scores are recomputed from e, q, k; with (stat_m, stat_inv, g) from the
+ * dq, dk, dv: zero all three first and do not count on accumulation (dq is reduced into; dk / dv are reduced into by the
+ * 4-warp kernel and STORED by the ring kernel, whose CTA owns all rows of a molecule).  Scores are recomputed from e, q, k; with (stat_m, stat_inv, g) from the
  * forward the statistics sweep is skipped (and the warps of a molecule never synchronise), with NULLs it is redone. */
 int dg_attn_scores_bwd(const float* dg, const float* da_in, const float* q, const float* k, const float* v,
                        const float* e, float c, const float* stat_m, const float* stat_inv, const float* g,
@@ -276,8 +277,22 @@ enum {
   DG_BLK_E_H,      /* bwd scratch, bf16: [B*N*N, H] with weight gradients and a live edge output, else [B*N*N, D] */
   DG_BLK_E_MASK,   /* bwd scratch [B*N*N, H/64] uint64 (only with a live edge output) */
   DG_BLK_SCRATCH,  /* bwd scratch, 2 D floats */
+  /* ---- dg_block_bwd_bwd only */
+  DG_BLK_UX,       /* in : cotangent of dx */
+  DG_BLK_UY,       /* in : cotangent of dy (edge) */
+  DG_BLK_C_X,      /* out: cotangent of x */
+  DG_BLK_C_Y,      /* out: cotangent of y (edge) */
+  DG_BLK_C_DXO,    /* out: cotangent of d x_out */
+  DG_BLK_C_DYO,    /* out: cotangent of d y_out (edge; only with a live edge output) */
+  DG_BLK_N_ARENA,  /* scratch: DG_BLK_BB_NODE_SLOTS node-sized fp32 buffers, contiguous */
+  DG_BLK_N_H2, DG_BLK_N_H3,          /* scratch [B*N, H] bf16 */
+  DG_BLK_ES0, DG_BLK_ES1, DG_BLK_ES2, DG_BLK_ES3, DG_BLK_ES4, DG_BLK_ES5, DG_BLK_ES6, DG_BLK_ES7, DG_BLK_ES8, /* scratch, edge fp32
+                    * (without a live edge output only ES0 and ES5..ES8 are used) */
+  DG_BLK_E_H2, DG_BLK_E_H3,          /* scratch [B*N*N, H] bf16 (only with a live edge output) */
+  DG_BLK_WT,       /* scratch, 2 H D floats (transposed MLP weights) */
   DG_BLK_COUNT
 };
+#define DG_BLK_BB_NODE_SLOTS 28
 #define DG_BLKF_EDGE_OUT 1 /* the block's edge output has a consumer (every block but the Discriminator's last, models.py:202-207) */
 #define DG_BLKF_KEEP 2     /* fwd: also write E and Z4 (the caller keeps X1..X3, Y3, A16, E, Z4 for dg_block_bwd); bwd: they are valid */
 #define DG_BLKF_STATS 4    /* fwd: write STAT_M / STAT_INV; bwd: G / STAT_M / STAT_INV hold the forward's values */
@@ -291,6 +306,15 @@ int dg_block_fwd(void* const* io, const float* const* params, int B, int N, int 
  * mlp2, ln6 when the edge output is not live) may be NULL and are left untouched. */
 int dg_block_bwd(void* const* io, const float* const* params, float* const* grads, int B, int N, int D, int H, int heads, int flags,
                  float eps, void* workspace, long long workspace_bytes, void* stream);
+/* Second-order pass of one block for the gradient penalty's double backward (loss.py:32-39 inside d_loss.backward()): the
+ * gradient of <ux, dx> + <uy, dy>, (dx, dy) = dg_block_bwd(x, y, dxo, dyo), with respect to x, y, dxo, dyo and the parameters --
+ * hand-sequenced (no autograd graph): recompute the forward and the first-order backward, walk the backward program in reverse
+ * with the second-order kernels, then one first-order backward from the cotangents injected at the forward intermediates.
+ * DG_BLKF_KEEP: X1, Q, K, V, Y3, E, Z4 hold the forward's values (else recomputed into their slots); G, STAT_M, STAT_INV, ON, X3 are
+ * always scratch here (the softmax is retaken from fp32 scores).  UX, UY, DXO are required (zeros where there is no cotangent);
+ * DYO NULL = the edge output is not live.  `grads`: as for dg_block_bwd (zeroed by the caller, accumulated into), required. */
+int dg_block_bwd_bwd(void* const* io, const float* const* params, float* const* grads, int B, int N, int D, int H, int heads,
+                     int flags, float eps, void* workspace, long long workspace_bytes, void* stream);
 /* TransformerEncoder.forward (layers.py:221-234) without a graph: `depth` blocks, params = depth x DG_BLOCK_PARAMS pointers.
  * `scratch`: a DG_BLK_* table holding X1..X3, Y3, A16 (E when !last_edge_out) and, for depth > 1, ping-pong buffers in the
  * X_OUT / Y_OUT slots; x_out / y_out also serve as ping-pong buffers (y_out may be NULL only if depth <= 2 and !last_edge_out). */

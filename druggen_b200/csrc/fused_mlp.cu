@@ -20,7 +20,8 @@
 // Persistent CTA per SM, 704 threads, warp-specialised:
 //   warps 0-15  epilogue : thread = a quarter of a row (TMEM lane quarter w&3, 32-column part w>>2); one TMA box
 //                          [32 rows][32 channels] of the I/O tile per warp, bf16 side outputs stored per warp PAIR
-//   warps 16-19 loader   : fp32 LDG.E.256 -> bf16 -> swizzled operand blocks (x tile single-buffered)
+//   warps 16-19 loader   : fp32 LDG.E.256 -> bf16 -> swizzled operand blocks (x tile and operand block single-buffered; the
+//                          64 KB I/O tile of the final epilogue is dedicated in every mode, see kDedIO)
 //   warp  20    MMA      : one thread issues tcgen05.mma; GEMM1 of tile t+1 issued right after the last GEMM2 of tile t
 //   warp  21    W loader : one thread streams pre-packed bf16 weight stages (32 KB) with
 //                          cp.async.bulk into a 2-stage ring (weights live in L2: 192 KB per net; ATTN: both stages resident)
@@ -139,8 +140,8 @@ __global__ void mlp_pack_weights_kernel(const float* __restrict__ w1, const floa
 }
 
 struct MlpSmem {
-  // tile buffers, 32 KB units: x (single-buffered) | operand blocks 2 x 32 KB (ATTN: 1) | weight stages 2 x 32 KB |
-  // ATTN only: a dedicated 64 KB I/O tile (the other modes stage their I/O tile in the two operand buffers)
+  // tile buffers, 32 KB units: x (single-buffered) | operand block | weight stages 2 x 32 KB | the dedicated 64 KB I/O tile
+  // (DG_CHAIN_DEDICATED_IO=0: two operand buffers in the H = 384 modes, which then also stage their I/O tile)
   static constexpr int tiles = 0;
   static constexpr int stage = 6 * kWStage;                          // 16 warps x 32 x kStgPitch words
   static constexpr int stats = stage + kEpiWarps * 32 * kStgPitch * 4;   // 2 x [4 parts][128 rows] float2 (see the epilogue)

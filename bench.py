@@ -37,7 +37,7 @@ def ncu_traffic(kernel_key, rows):
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
     (profiles/r01b_traffic.json, taken at 1 036 800 edge rows), scaled linearly to this run's rows; None if not captured."""
     tab = None
-    for name in ("r02b_traffic.json", "r02_traffic.json", "r01b_traffic.json", "r01_traffic.json"):         # newest capture first
+    for name in ("r02e_traffic.json", "r02b_traffic.json", "r02_traffic.json", "r01b_traffic.json", "r01_traffic.json"):         # newest capture first
         try:
             tab = json.load(open(os.path.join(ROOT, "profiles", name)))
             break

@@ -59,7 +59,7 @@ SIGNATURES = {
     "dg_encoder_fwd": [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _F, _P, _LL, _P],
 }
 INFO_SYMBOLS = ("dg_abi_version", "dg_last_error", "dg_has_tcgen05", "dg_set_option", "dg_get_option", "dg_debug_chain_profile",
-                "dg_label_error", "dg_native_launches", "dg_probe_set", "dg_probe_read")
+                "dg_label_error", "dg_native_launches", "dg_probe_set", "dg_probe_read", "dg_debug_trace", "dg_debug_trace_read")
 # slots of the block-level entry points' buffer table, in the order of the DG_BLK_* enum of include/druggen_b200.h
 BLK_SLOTS = ("X", "Y", "X_OUT", "Y_OUT", "X1", "Q", "K", "V", "G", "ON", "X3", "STAT_M", "STAT_INV", "Y3", "A16", "E", "Z4",
              "DXO", "DYO", "DX", "DY", "N_DZ", "N_DX3", "N_DZ3", "N_DG", "N_DQ", "N_DK", "N_DV", "N_T0", "N_T1", "N_H", "N_MASK",
@@ -100,6 +100,8 @@ def load():
         lib.dg_native_launches.argtypes, lib.dg_native_launches.restype = [], _LL
         lib.dg_probe_set.argtypes, lib.dg_probe_set.restype = [C.c_char_p], _I
         lib.dg_probe_read.argtypes, lib.dg_probe_read.restype = [C.POINTER(_LL), C.POINTER(C.c_double)], _I
+        lib.dg_debug_trace.argtypes, lib.dg_debug_trace.restype = [_I], _I
+        lib.dg_debug_trace_read.argtypes, lib.dg_debug_trace_read.restype = [C.c_char_p, _LL], _LL
         if lib.dg_abi_version() != ABI_VERSION:
             raise RuntimeError("libdruggen_b200.so ABI version mismatch")
         if os.environ.get("DRUGGEN_B200_L2_PREFETCH") is not None:       # tuning switch, default on

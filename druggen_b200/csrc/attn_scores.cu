@@ -483,6 +483,7 @@ using namespace dg;
 
 extern "C" int dg_attn_scores_fwd(const float* q, const float* k, const float* v, const float* e, float c, float* a,
                                   float* g, float* stat_m, float* stat_inv, int B, int N, int D, void* stream) {
+  DG_TRACE("dg_attn_scores_fwd", q, k, v, e, c, a, g, stat_m, stat_inv, B, N, D);
   if (attn_ok(B, N, D)) return 1;
   const size_t smem = (size_t)24 * D * 4;
   const int irows = max(4, attn_irows(B, N, 8));        // one query atom per warp at a time: at least 4 per CTA
@@ -503,6 +504,7 @@ extern "C" int dg_attn_scores_fwd(const float* q, const float* k, const float* v
 
 extern "C" int dg_softmax_agg16_fwd(const void* a_bf16, const float* v, float* g, float* stat_m, float* stat_inv, int B, int N,
                                     int D, void* stream) {
+  DG_TRACE("dg_softmax_agg16_fwd", a_bf16, v, g, stat_m, stat_inv, B, N, D);
   if (attn_ok(B, N, D)) return 1;
   const size_t smem = (size_t)24 * D * 4;
   const int irows = max(4, attn_irows(B, N, 8));        // one query atom per warp at a time: at least 4 per CTA
@@ -517,6 +519,7 @@ extern "C" int dg_softmax_agg16_fwd(const void* a_bf16, const float* v, float* g
 extern "C" int dg_attn_scores_bwd(const float* dg_, const float* da_in, const float* q, const float* k, const float* v,
                                   const float* e, float c, const float* stat_m, const float* stat_inv, const float* g,
                                   void* de, float* dq, float* dk, float* dv, int B, int N, int D, int de_bf16, void* stream) {
+  DG_TRACE("dg_attn_scores_bwd", dg_, da_in, q, k, v, e, c, stat_m, stat_inv, g, de, dq, dk, dv, B, N, D, de_bf16);
   if (attn_ok(B, N, D)) return 1;
   if (stat_m != nullptr && (stat_inv == nullptr || g == nullptr)) return fail("dg_attn_scores_bwd: statistics need stat_inv and g too");
   const int ring_opt = opt_get(DG_OPT_ATTN_BWD);

@@ -105,6 +105,13 @@ int need(const char* who, void* const* io, std::initializer_list<int> idx) {
   return 0;
 }
 
+int zero(Seq& q, void* p, long long bytes) {
+  if (q.rc) return q.rc;
+  if (dg::trace_on()) return dg::trace_call("memset0", (const void*)p, bytes);
+  if (cudaMemsetAsync(p, 0, (size_t)bytes, q.s) != cudaSuccess) q.rc = dg::fail("dg_block: memset failed");
+  return q.rc;
+}
+
 // x1 = LN1(x); q, k, v = their projections (layers.py:185,111-113)
 void node_prologue(Seq& q, void* const* io, const float* const* P, long long BN, int D, float eps) {
   DG_STEP(q, dg_add_ln_fwd(at(io, DG_BLK_X), nullptr, P[LN1_W], P[LN1_B], at(io, DG_BLK_X1), BN, D, eps, q.s), "add_ln_fwd");
@@ -297,7 +304,7 @@ extern "C" int dg_block_bwd(void* const* io, const float* const* P, float* const
   // ---- node stream: MLP + LN5, LN3, out_n
   const float* dxo = at(io, DG_BLK_DXO);
   if (dxo == nullptr) {
-    if (!q.rc && cudaMemsetAsync(io[DG_BLK_N_T0], 0, BN * D * sizeof(float), q.s) != cudaSuccess) q.rc = dg::fail("dg_block_bwd: memset failed");
+    zero(q, io[DG_BLK_N_T0], BN * D * (long long)sizeof(float));
     dxo = at(io, DG_BLK_N_T0);
   }
   mlp_backward(q, at(io, DG_BLK_X3), dxo, P, FC1_W, LN5_W, wp ? grads : nullptr, at(io, DG_BLK_N_DZ), io[DG_BLK_N_H], io[DG_BLK_N_MASK],
@@ -329,12 +336,7 @@ extern "C" int dg_block_bwd(void* const* io, const float* const* P, float* const
     da = dy3;
   }
   // ---- attention: softmax-aggregate + modulation backward (dE as bf16: only ever a contraction operand)
-  if (!q.rc) {
-    cudaError_t e0 = cudaMemsetAsync(io[DG_BLK_N_DQ], 0, BN * D * sizeof(float), q.s);
-    cudaError_t e1 = cudaMemsetAsync(io[DG_BLK_N_DK], 0, BN * D * sizeof(float), q.s);
-    cudaError_t e2 = cudaMemsetAsync(io[DG_BLK_N_DV], 0, BN * D * sizeof(float), q.s);
-    if (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess) q.rc = dg::fail("dg_block_bwd: memset failed");
-  }
+  for (int slot : {DG_BLK_N_DQ, DG_BLK_N_DK, DG_BLK_N_DV}) zero(q, io[slot], BN * D * (long long)sizeof(float));
   void* de = io[DG_BLK_E_H];
   DG_STEP(q, dg_attn_scores_bwd(at(io, DG_BLK_N_DG), (const float*)da, at(io, DG_BLK_Q), at(io, DG_BLK_K), at(io, DG_BLK_V), at(io, DG_BLK_E), c,
                                 at(io, DG_BLK_STAT_M), at(io, DG_BLK_STAT_INV), at(io, DG_BLK_G), de, at(io, DG_BLK_N_DQ), at(io, DG_BLK_N_DK),
@@ -383,11 +385,6 @@ __global__ void add3_kernel(float4* a0, const float4* b0, float4* a1, const floa
   }
 }
 
-int zero(Seq& q, void* p, long long bytes) {
-  if (!q.rc && cudaMemsetAsync(p, 0, (size_t)bytes, q.s) != cudaSuccess) q.rc = dg::fail("dg_block_bwd_bwd: memset failed");
-  return q.rc;
-}
-
 // node-sized scratch slots of dg_block_bwd_bwd inside DG_BLK_N_ARENA
 enum {
   nT5, nM, nDX3, nDZ3, nDG, nDV, nDQ, nDK, nP0, nP1, nCDX1, nCDQ, nCDK, nCDV, nCQ, nCK, nCV, nCDG, nCDZ3, nCDX3, nCZ3, nCT5, nCMN,
@@ -408,7 +405,10 @@ void mlp_recompute(Seq& q, const float* xin, const float* dout, const float* con
 // reverse of dxin = t + ((t W2) * M) W1 given u = c[dxin]: c[t] into c_t; c[W2] += t^T tM, c[W1] += dh^T u
 void mlp_second(Seq& q, const float* u, const float* t, const void* mask, const void* dh, const float* const* P, int fc1, float* const* grads,
                 float* c_t, void* tm, float* wt, long long rows, int D, int H, void* ws, long long wsb) {
-  if (!q.rc) {      // the dgrad chain with the two weights transposed into each other's role
+  if (!q.rc && dg::trace_on()) {
+    dg::trace_call("transpose", (const void*)P[fc1 + 2], (const void*)wt, D, H);
+    dg::trace_call("transpose", (const void*)P[fc1], (const void*)(wt + (long long)H * D), H, D);
+  } else if (!q.rc) {      // the dgrad chain with the two weights transposed into each other's role
     transpose_kernel<<<96, 256, 0, q.s>>>(P[fc1 + 2], wt, D, H);                  // W2 [D,H] -> [H,D]
     transpose_kernel<<<96, 256, 0, q.s>>>(P[fc1], wt + (long long)H * D, H, D);   // W1 [H,D] -> [D,H]
   }
@@ -563,7 +563,10 @@ extern "C" int dg_block_bwd_bwd(void* const* io, const float* const* P, float* c
   // c[q] / c[k] / c[v] in one small launch
   zero(q, ns(nDQ2), 3 * nb);
   DG_STEP(q, dg_attn_scores_bwd(ns(nCG), c_A, qq, kk, vv, e, c, sm, si, g, c_E, ns(nDQ2), ns(nDK2), ns(nDV2), B, N, D, 8, q.s), "attn_scores_bwd[fused]");
-  if (!q.rc) {
+  if (!q.rc && dg::trace_on()) {
+    dg::trace_call("add3", (const void*)ns(nCQ), (const void*)ns(nDQ2), (const void*)ns(nCK), (const void*)ns(nDK2), (const void*)ns(nCV),
+                   (const void*)ns(nDV2), BN * D);
+  } else if (!q.rc) {
     const long long n4 = BN * D / 4;
     const long long blocks = (n4 + 255) / 256, cap = (long long)dg::sm_count() * 8;
     add3_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, q.s>>>(reinterpret_cast<float4*>(ns(nCQ)), reinterpret_cast<const float4*>(ns(nDQ2)),

@@ -40,6 +40,36 @@ inline int sm_count() {           // of the CURRENT device (one process may driv
 // ---- run-time options (dg_set_option) --------------------------------------------------------
 int opt_get(int key);   // api.cu
 
+// ---- dry-run trace (dg_debug_trace, tests) ----------------------------------------------------
+// With the trace on, a kernel entry point records its name and arguments and returns without touching the device: the launch
+// programs of the block-level entry points (block.cu) can be listed -- and pinned by a test -- on a box without a GPU.
+bool trace_on();                    // api.cu
+void trace_add(const char* line);   // api.cu
+struct TraceLine {
+  char buf[640];
+  int n = 0;
+  void put(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    if (n < (int)sizeof buf) n += vsnprintf(buf + n, sizeof buf - n, fmt, ap);
+    va_end(ap);
+  }
+  void add(const void* p) { put(" p:%llx", (unsigned long long)reinterpret_cast<uintptr_t>(p)); }
+  void add(long long v) { put(" i:%lld", v); }
+  void add(int v) { put(" i:%d", v); }
+  void add(float v) { put(" f:%g", (double)v); }
+};
+template <class... A>
+inline int trace_call(const char* name, A... a) {
+  TraceLine t;
+  t.put("%s", name);
+  (t.add(a), ...);
+  trace_add(t.buf);
+  return 0;
+}
+#define DG_TRACE(...) \
+  if (dg::trace_on()) return dg::trace_call(__VA_ARGS__)
+
 // ---- device helpers --------------------------------------------------------------------------
 // L2 prefetch of a contiguous global range by the TMA engine (UBLKPF.L2: no registers, no shared memory, the
 // issuing thread does not wait).  `src` 16-byte aligned, `bytes` a multiple of 16.  Used one or two tiles ahead of

@@ -874,6 +874,7 @@ static int mlp_check(const char* who, const void* x, long long R, int D, int H, 
 extern "C" int dg_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                           const float* gamma, const float* beta, float* out, long long R, int D, int H, float eps,
                           void* workspace, long long workspace_bytes, void* stream) {
+  DG_TRACE("dg_mlp_fwd", x, w1, b1, w2, b2, gamma, beta, out, R, D, H, eps, workspace);
   if (mlp_check("dg_mlp_fwd", x, R, D, H, workspace, workspace_bytes)) return 1;
   cudaStream_t s = (cudaStream_t)stream;
   tc::mlp_pack_weights_kernel<<<48, 256, 0, s>>>(w1, w2, (uint8_t*)workspace, H, 0);
@@ -885,6 +886,7 @@ extern "C" int dg_mlp_bwd_ln(const float* x, const float* dout, const float* w1,
                              const float* b2, const float* gamma, float* dz, void* h_bf16, void* relu_mask, float* dgamma,
                              float* dbeta, long long R, int D, int H, float eps, void* workspace, long long workspace_bytes,
                              void* stream) {
+  DG_TRACE("dg_mlp_bwd_ln", x, dout, w1, b1, w2, b2, gamma, dz, h_bf16, relu_mask, dgamma, dbeta, R, D, H, eps, workspace);
   if (mlp_check("dg_mlp_bwd_ln", x, R, D, H, workspace, workspace_bytes)) return 1;
   if (reinterpret_cast<uintptr_t>(relu_mask) & 7) return fail("dg_mlp_bwd_ln: the sign mask must be 8-byte aligned");
   if ((dgamma == nullptr) != (dbeta == nullptr)) return fail("dg_mlp_bwd_ln: pass both dgamma and dbeta or neither");
@@ -898,6 +900,7 @@ extern "C" int dg_mlp_bwd_ln(const float* x, const float* dout, const float* w1,
 extern "C" int dg_mlp_bwd_dgrad(const float* dz, const void* h_bf16, const void* relu_mask, const float* w1, const float* w2,
                                 float* dx, void* dh_bf16, long long R, int D, int H, void* workspace, long long workspace_bytes,
                                 void* stream) {
+  DG_TRACE("dg_mlp_bwd_dgrad", dz, h_bf16, relu_mask, w1, w2, dx, dh_bf16, R, D, H, workspace);
   if (mlp_check("dg_mlp_bwd_dgrad", dz, R, D, H, workspace, workspace_bytes)) return 1;
   if (h_bf16 == nullptr && relu_mask == nullptr) return fail("dg_mlp_bwd_dgrad: needs h (bf16) or its sign mask");
   if (reinterpret_cast<uintptr_t>(relu_mask) & 7) return fail("dg_mlp_bwd_dgrad: the sign mask must be 8-byte aligned");
@@ -912,6 +915,7 @@ extern "C" int dg_attn_edge_fwd(const float* y, const float* q, const float* k, 
                                 const float* woe, const float* boe, const float* gamma, const float* beta, float c,
                                 float* out, void* a_bf16, float* e_out, float* z_out, int B, int N, int D, float eps,
                                 void* workspace, long long workspace_bytes, void* stream) {
+  DG_TRACE("dg_attn_edge_fwd", y, q, k, we, be, woe, boe, gamma, beta, c, out, a_bf16, e_out, z_out, B, N, D, eps, workspace);
   if (B <= 0 || N <= 0) return fail("dg_attn_edge_fwd: bad shape B=%d N=%d", B, N);
   if ((long long)B * N * N >= (1ll << 31) || (long long)B * N * 128 >= (1ll << 31)) return fail("dg_attn_edge_fwd: B*N*N and B*N*128 must be < 2^31 (split the batch)");
   const long long R = (long long)B * N * N;

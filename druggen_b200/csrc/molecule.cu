@@ -230,6 +230,7 @@ extern "C" int dg_modulate_fwd(const float* q, const float* k, const float* e, f
 
 extern "C" int dg_modulate_bwd(const float* da, const float* q, const float* k, const float* e, float c, float* dq,
                                float* dk, float* de, int B, int N, int D, void* stream) {
+  DG_TRACE("dg_modulate_bwd", da, q, k, e, c, dq, dk, de, B, N, D);
   if (mol_ok(B, N, D, true)) return 1;
   if (attn_second_ok(B, N, D)) return modulate_bwd_v4(da, q, k, e, c, dq, dk, de, B, N, (cudaStream_t)stream);
   int irows = pick_irows(B, N);
@@ -243,6 +244,7 @@ extern "C" int dg_modulate_bwd(const float* da, const float* q, const float* k, 
 extern "C" int dg_modulate_bwd_bwd(const float* uq, const float* uk, const float* ue, const float* da,
                                    const float* q, const float* k, const float* e, float c, float* g_da, float* g_q,
                                    float* g_k, float* g_e, int B, int N, int D, void* stream) {
+  DG_TRACE("dg_modulate_bwd_bwd", uq, uk, ue, da, q, k, e, c, g_da, g_q, g_k, g_e, B, N, D);
   if (mol_ok(B, N, D, true)) return 1;
   if (attn_second_ok(B, N, D)) return modulate_bwd_bwd_v4(uq, uk, ue, da, q, k, e, c, g_da, g_q, g_k, g_e, B, N, (cudaStream_t)stream);
   int irows = pick_irows(B, N);
@@ -263,6 +265,7 @@ extern "C" int dg_softmax_agg_fwd(const float* a, const float* v, float* g, int 
 
 extern "C" int dg_softmax_agg_bwd(const float* dg_, const float* a, const float* v, float* da, float* dv, int accumulate,
                                   int B, int N, int D, void* stream) {
+  DG_TRACE("dg_softmax_agg_bwd", dg_, a, v, da, dv, accumulate, B, N, D);
   if (mol_ok(B, N, D, true)) return 1;
   if (attn_second_ok(B, N, D)) return softmax_agg_bwd_v4(dg_, a, v, da, dv, accumulate, B, N, (cudaStream_t)stream);
   int irows = pick_irows(B, N);
@@ -276,6 +279,7 @@ extern "C" int dg_softmax_agg_bwd(const float* dg_, const float* a, const float*
 extern "C" int dg_softmax_agg_bwd_bwd(const float* ua, const float* uv, const float* dg_, const float* a,
                                       const float* v, float* g_dg, float* g_a, float* g_v, int B, int N, int D,
                                       void* stream) {
+  DG_TRACE("dg_softmax_agg_bwd_bwd", ua, uv, dg_, a, v, g_dg, g_a, g_v, B, N, D);
   if (mol_ok(B, N, D, true)) return 1;
   if (attn_second_ok(B, N, D)) return softmax_agg_bwd_bwd_v4(ua, uv, dg_, a, v, g_dg, g_a, g_v, B, N, (cudaStream_t)stream);
   int irows = pick_irows(B, N);

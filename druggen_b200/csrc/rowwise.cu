@@ -260,6 +260,7 @@ using namespace dg;
 
 extern "C" int dg_add_ln_fwd(const float* a, const float* b, const float* gamma, const float* beta, float* out,
                              long long R, int D, float eps, void* stream) {
+  DG_TRACE("dg_add_ln_fwd", a, b, gamma, beta, out, R, D, eps);
   if (ln_ok(R, D)) return 1;
   DG_DISPATCH_V(D, (add_ln_fwd_kernel<V><<<row_grid(R), kRowWarps * 32, 0, (cudaStream_t)stream>>>(a, b, gamma, beta, out, R, D, eps)));
   return check_launch("dg_add_ln_fwd");
@@ -267,6 +268,7 @@ extern "C" int dg_add_ln_fwd(const float* a, const float* b, const float* gamma,
 
 extern "C" int dg_add_ln_bwd(const float* dy, const float* a, const float* b, const float* gamma, float* dz,
                              float* dgamma, float* dbeta, long long R, int D, float eps, int accumulate, void* stream) {
+  DG_TRACE("dg_add_ln_bwd", dy, a, b, gamma, dz, dgamma, dbeta, R, D, eps, accumulate);
   if (ln_ok(R, D)) return 1;
   DG_DISPATCH_V(D, (add_ln_bwd_kernel<V><<<row_grid(R), kRowWarps * 32, kRowWarps * D * sizeof(float), (cudaStream_t)stream>>>(
       dy, a, b, gamma, dz, dgamma, dbeta, R, D, eps, accumulate)));
@@ -276,6 +278,7 @@ extern "C" int dg_add_ln_bwd(const float* dy, const float* a, const float* b, co
 extern "C" int dg_add_ln_bwd_bwd(const float* u, const float* vg, const float* vb, const float* dy, const float* a,
                                  const float* b, const float* gamma, float* g_dy, float* g_z, float* g_gamma,
                                  long long R, int D, float eps, void* stream) {
+  DG_TRACE("dg_add_ln_bwd_bwd", u, vg, vb, dy, a, b, gamma, g_dy, g_z, g_gamma, R, D, eps);
   if (ln_ok(R, D)) return 1;
   DG_DISPATCH_V(D, (add_ln_bwd_bwd_kernel<V><<<row_grid(R), kRowWarps * 32, kRowWarps * D * sizeof(float), (cudaStream_t)stream>>>(
       u, vg, vb, dy, a, b, gamma, g_dy, g_z, g_gamma, R, D, eps)));

@@ -329,6 +329,13 @@ long long dg_native_launches(void);
 int dg_probe_set(const char* key);
 int dg_probe_read(long long* launches, double* total_ms);
 
+/* debug / tests: dry-run trace.  With the trace on, every kernel entry point above records one line -- its name and its arguments
+ * (p:<hex pointer>, i:<integer>, f:<float>) -- and returns 0 WITHOUT touching the device; the block-level entry points then list
+ * their launch programs (plus memset0 / transpose / add3 lines for their own small launches), which tests/test_native_trace.py
+ * pins on a box without a GPU.  dg_debug_trace_read copies the text recorded so far (NUL-terminated, at most cap - 1 bytes) and
+ * clears it; returns its length. */
+int dg_debug_trace(int on);
+long long dg_debug_trace_read(char* buf, long long cap);
 /* debug: with a device buffer of 148*64 int64 set, every chain-kernel launch (dg_mlp_*, dg_attn_edge_fwd) writes
  * per-CTA phase cycle counters [CTA][4 roles][16 phases] (tools/chain_profile.py); NULL switches it off. */
 int dg_debug_chain_profile(void* device_buf);

@@ -25,3 +25,20 @@ def test_header_symbols_exported():
         assert hasattr(lib, n), n
     assert set(names) == set(_lib.SIGNATURES) | set(_lib.INFO_SYMBOLS)
     assert lib.dg_abi_version() == _lib.ABI_VERSION
+
+
+def test_block_slot_table_matches_header():
+    """The DG_BLK_* enum of the header (the buffer table of dg_block_fwd / dg_block_bwd / dg_block_bwd_bwd / dg_encoder_fwd) and
+    its Python mirror agree slot by slot, as do the flag values and the node-arena size."""
+    text = open(os.path.join(ROOT, "include", "druggen_b200.h")).read()
+    start = text.index("DG_BLK_X = 0")
+    body = text[start:text.index("DG_BLK_COUNT", start)]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = re.findall(r"DG_BLK_([A-Z0-9_]+)", body)
+    assert tuple(names) == tuple(_lib.BLK_SLOTS)
+    assert _lib.BLK["X"] == 0 and len(set(names)) == len(names)
+    for name, val in (("DG_BLKF_EDGE_OUT", _lib.BLKF_EDGE_OUT), ("DG_BLKF_KEEP", _lib.BLKF_KEEP), ("DG_BLKF_STATS", _lib.BLKF_STATS),
+                      ("DG_BLOCK_PARAMS", _lib.BLOCK_PARAMS), ("DG_BLK_BB_NODE_SLOTS", _lib.BB_NODE_SLOTS)):
+        assert int(re.search(r"#define %s (\d+)" % name, text).group(1)) == val, name
+    from druggen_b200.block import BLOCK_PARAM_NAMES
+    assert len(BLOCK_PARAM_NAMES) == _lib.BLOCK_PARAMS

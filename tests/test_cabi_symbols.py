@@ -42,3 +42,21 @@ def test_block_slot_table_matches_header():
         assert int(re.search(r"#define %s (\d+)" % name, text).group(1)) == val, name
     from druggen_b200.block import BLOCK_PARAM_NAMES
     assert len(BLOCK_PARAM_NAMES) == _lib.BLOCK_PARAMS
+
+
+def test_header_binds_from_plain_c(tmp_path):
+    """include/druggen_b200.h is a C header: examples/block_fwd_trace.c compiles with gcc -std=c99, links against the library and --
+    in the dry-run trace, so without a GPU -- lists the ten launches of dg_block_fwd."""
+    import shutil
+    import subprocess
+    if not os.path.exists(_lib.LIB_PATH) or shutil.which("gcc") is None:
+        pytest.skip("needs the built library and gcc")
+    exe = str(tmp_path / "block_fwd_trace")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "block_fwd_trace.c"),
+                    "-L" + libdir, "-ldruggen_b200", "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    launches = [l.split(" ")[0] for l in out[:-1]]
+    assert launches == ["dg_add_ln_fwd", "dg_rows_gemm", "dg_rows_gemm", "dg_rows_gemm", "dg_attn_edge_fwd", "dg_softmax_agg16_fwd",
+                        "dg_rows_gemm", "dg_add_ln_fwd", "dg_mlp_fwd", "dg_mlp_fwd"]
+    assert out[-1].startswith("abi %d, 10 launches" % _lib.ABI_VERSION)

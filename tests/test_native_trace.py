@@ -100,6 +100,10 @@ def test_data_flow(programs, case):
             if int(args[flag_pos]) & mask:
                 accs.append(pos)
         ptr = lambda i: args[i] if i < len(args) else "0"  # noqa: E731
+        # no launch writes (other than by a declared accumulation) a buffer it also reads: the kernels are not in-place safe
+        rd = {ptr(i) for i in reads} - {"0"}
+        wr = {ptr(i) for i in writes if i not in accs} - {"0", "WS"}
+        assert not (rd & wr), (line, "output aliases an input: %s" % sorted(rd & wr))
         for i in list(reads) + accs:
             b = ptr(i)
             assert not b.startswith("0x"), (line, "unknown address")

@@ -614,8 +614,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_tc_kernel(const __gr
       // ---- final epilogue: this thread = one row, 32 columns [cp*32, +32)
       DG_PROF(5)
       // The residual rows come in, and the output rows leave, as a TMA tile: 4 boxes [128 rows][32 channels] with the
-      // 128-byte swizzle, staged in the two operand buffers sH[0..1] (64 KB), which are idle from the completion of the
-      // tile's last GEMM2 (z_full) until the next tile's first chunk is stored.  A thread reads and later overwrites only
+      // 128-byte swizzle, in the dedicated I/O tile sIO (64 KB; requested after the tile's first chunk, see above) -- or, built with
+      // DG_CHAIN_DEDICATED_IO=0, staged in the two operand buffers sH[0..1], which are idle from the completion of the tile's
+      // last GEMM2 (z_full) until the next tile's first chunk is stored.  A thread reads and later overwrites only
       // its own row part, so the tile needs no transposition and no bank conflicts (8 consecutive rows = 8 swizzle slots).
       float a[32];
       float4 xq[kMode == kBwdA ? 8 : 1];

@@ -297,7 +297,7 @@ def encoder_forward_nograd(x, y, blocks_params, heads: int, last_edge_out: bool 
     flat = [t for params in blocks_params for t in params]
     x2d, y2d = x.reshape(bn, d), y.reshape(r, d)
     out = None
-    if _GRAPH["on"] and r * d * 4 <= _GRAPH["max_edge_bytes"] and not torch.cuda.is_current_stream_capturing():
+    if _GRAPH["on"] and x.is_cuda and r * d * 4 <= _GRAPH["max_edge_bytes"] and not torch.cuda.is_current_stream_capturing():
         out = _encoder_graph(x2d, y2d, flat, b, n, d, depth, hid, heads, last_edge_out)
     if out is None:
         scratch, x_out, y_out = _encoder_buffers(b, n, d, depth, last_edge_out, x.device)

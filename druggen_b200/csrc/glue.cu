@@ -288,6 +288,7 @@ __global__ void __launch_bounds__(256) symmetrize_kernel(const float* __restrict
 using namespace dg;
 
 extern "C" int dg_label_error(int clear) {
+  if (dg::trace_on()) return 0;      // (dry run: nothing was launched, nothing to read back)
   int v = 0;
   if (cudaMemcpyFromSymbol(&v, g_label_error, sizeof(int)) != cudaSuccess) {
     fail("dg_label_error: cannot read the device flag");
@@ -309,6 +310,7 @@ static int embed_check(const char* who, long long rows, int n, int classes, int 
 }
 
 extern "C" int dg_symmetrize(const float* e, float* out, int B, int N, int D, void* stream) {
+  DG_TRACE("dg_symmetrize", e, out, B, N, D);
   if (B <= 0 || N <= 0 || D <= 0 || (D & 3)) return fail("dg_symmetrize: bad shape B=%d N=%d D=%d (D must be a multiple of 4)", B, N, D);
   if (e == out) return fail("dg_symmetrize: in-place is not supported (row ij reads row ji)");
   const long long rows = (long long)B * N * N;
@@ -319,6 +321,7 @@ extern "C" int dg_symmetrize(const float* e, float* out, int B, int N, int D, vo
 
 extern "C" int dg_embed_labels_fwd(const void* labels, int label_bytes, const float* lut, float* y, long long rows, int n,
                                    int classes, int D, int sym, void* stream) {
+  DG_TRACE("dg_embed_labels_fwd", labels, label_bytes, lut, y, rows, n, classes, D, sym);
   if (embed_check("dg_embed_labels_fwd", rows, n, classes, D, label_bytes, sym)) return 1;
   if (rows == 0) return 0;
   const int grid = grid_for(rows, 8 * 4);
@@ -331,6 +334,7 @@ extern "C" int dg_embed_labels_fwd(const void* labels, int label_bytes, const fl
 
 extern "C" int dg_embed_labels_bwd(const void* labels, int label_bytes, const float* dy, float* dlut, long long rows, int n,
                                    int classes, int D, int sym, void* stream) {
+  DG_TRACE("dg_embed_labels_bwd", labels, label_bytes, dy, dlut, rows, n, classes, D, sym);
   if (embed_check("dg_embed_labels_bwd", rows, n, classes, D, label_bytes, sym)) return 1;
   if (rows == 0) return 0;
   int grid = grid_for(rows, 4 * 4 * 8);
@@ -344,6 +348,7 @@ extern "C" int dg_embed_labels_bwd(const void* labels, int label_bytes, const fl
 
 extern "C" int dg_gp_interp(const void* labels, int label_bytes, const float* fake, const float* eps, float* out, long long rows,
                             long long rows_per_mol, int classes, void* stream) {
+  DG_TRACE("dg_gp_interp", labels, label_bytes, fake, eps, out, rows, rows_per_mol, classes);
   if (rows < 0 || rows_per_mol <= 0 || classes <= 0 || rows % rows_per_mol) return fail("dg_gp_interp: bad shape rows=%lld rows_per_mol=%lld classes=%d", rows, rows_per_mol, classes);
   if (label_bytes != 1 && label_bytes != 8) return fail("dg_gp_interp: labels are uint8 or int64 (label_bytes=%d)", label_bytes);
   if (rows == 0) return 0;
@@ -358,6 +363,7 @@ extern "C" int dg_gp_interp(const void* labels, int label_bytes, const float* fa
 
 extern "C" int dg_gp_penalty(const float* g_node, const float* g_edge, float* penalty, float* coef, float* sq_scratch, int batch,
                              long long len_node, long long len_edge, void* stream) {
+  DG_TRACE("dg_gp_penalty", g_node, g_edge, penalty, coef, sq_scratch, batch, len_node, len_edge);
   if (batch <= 0 || len_node < 0 || len_edge < 0) return fail("dg_gp_penalty: bad shape batch=%d", batch);
   gp_sqnorm_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(g_node, g_edge, sq_scratch, len_node, len_edge);
   gp_finish_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(sq_scratch, penalty, coef, batch);
@@ -366,6 +372,7 @@ extern "C" int dg_gp_penalty(const float* g_node, const float* g_edge, float* pe
 
 extern "C" int dg_gp_penalty_bwd(const float* g, const float* coef, const float* upstream, float* out, int batch, long long per_mol,
                                  void* stream) {
+  DG_TRACE("dg_gp_penalty_bwd", g, coef, upstream, out, batch, per_mol);
   if (batch <= 0 || per_mol <= 0) return fail("dg_gp_penalty_bwd: bad shape batch=%d per_mol=%lld", batch, per_mol);
   const long long total = (long long)batch * per_mol;
   gp_scale_kernel<<<grid_for(total, 256 * 4), 256, 0, (cudaStream_t)stream>>>(g, coef, upstream, out, total, per_mol);
@@ -374,6 +381,7 @@ extern "C" int dg_gp_penalty_bwd(const float* g, const float* coef, const float*
 
 extern "C" int dg_readout_argmax(const float* x, const float* w, const float* bias, float* logits, void* idx, int idx_bytes,
                                  long long rows, int D, int classes, void* stream) {
+  DG_TRACE("dg_readout_argmax", x, w, bias, logits, idx, idx_bytes, rows, D, classes);
   if (rows < 0 || classes <= 0 || classes > kEmbMaxC) return fail("dg_readout_argmax: bad shape rows=%lld classes=%d (classes <= %d)", rows, classes, kEmbMaxC);
   if (D != kEmbD) return fail("dg_readout_argmax: needs D == 128, got %d", D);
   if (idx != nullptr && idx_bytes != 1 && idx_bytes != 8) return fail("dg_readout_argmax: indices are uint8 or int64 (idx_bytes=%d)", idx_bytes);
@@ -388,6 +396,7 @@ extern "C" int dg_readout_argmax(const float* x, const float* w, const float* bi
 
 extern "C" int dg_adamw_flat(float* p, const float* g, float* m, float* v, const void* segs, int nseg, float lr, float beta1,
                              float beta2, float eps, float weight_decay, void* stream) {
+  DG_TRACE("dg_adamw_flat", p, g, m, v, segs, nseg, lr, beta1, beta2, eps, weight_decay);
   if (nseg <= 0 || nseg > 65535) return fail("dg_adamw_flat: segments must be in [1, 65535], got %d", nseg);
   dim3 grid(8, nseg);
   adamw_flat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (const AdamSeg*)segs, nseg, lr, beta1, beta2, eps, weight_decay);
@@ -395,6 +404,7 @@ extern "C" int dg_adamw_flat(float* p, const float* g, float* m, float* v, const
 }
 
 extern "C" int dg_label2onehot(const void* labels, int label_bytes, float* out, long long n, int classes, void* stream) {
+  DG_TRACE("dg_label2onehot", labels, label_bytes, out, n, classes);
   if (n < 0 || classes <= 0) return fail("dg_label2onehot: bad shape n=%lld classes=%d", n, classes);
   if (label_bytes != 1 && label_bytes != 8) return fail("dg_label2onehot: labels are uint8 or int64 (label_bytes=%d)", label_bytes);
   if (n == 0) return 0;
@@ -408,6 +418,7 @@ extern "C" int dg_label2onehot(const void* labels, int label_bytes, float* out, 
 }
 
 extern "C" int dg_argmax_last(const float* x, long long* out, long long rows, int C, void* stream) {
+  DG_TRACE("dg_argmax_last", x, out, rows, C);
   if (rows < 0 || C <= 0) return fail("dg_argmax_last: bad shape rows=%lld C=%d", rows, C);
   if (rows == 0) return 0;
   argmax_last_kernel<<<grid_for(rows, 256), 256, 0, (cudaStream_t)stream>>>(x, out, rows, C);

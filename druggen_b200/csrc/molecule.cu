@@ -221,6 +221,7 @@ using namespace dg;
 
 extern "C" int dg_modulate_fwd(const float* q, const float* k, const float* e, float c, float* out, int B, int N,
                                int D, void* stream) {
+  DG_TRACE("dg_modulate_fwd", q, k, e, c, out, B, N, D);
   if (mol_ok(B, N, D, false)) return 1;
   long long total4 = (long long)B * N * N * (D / 4);
   long long blocks = (total4 + 255) / 256, cap = (long long)sm_count() * 16;
@@ -256,6 +257,7 @@ extern "C" int dg_modulate_bwd_bwd(const float* uq, const float* uk, const float
 }
 
 extern "C" int dg_softmax_agg_fwd(const float* a, const float* v, float* g, int B, int N, int D, void* stream) {
+  DG_TRACE("dg_softmax_agg_fwd", a, v, g, B, N, D);
   if (mol_ok(B, N, D, false)) return 1;
   int irows = pick_irows(B, N);
   dim3 grid((N + irows - 1) / irows, B);

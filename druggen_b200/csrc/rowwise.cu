@@ -286,6 +286,7 @@ extern "C" int dg_add_ln_bwd_bwd(const float* u, const float* vg, const float* v
 }
 
 extern "C" int dg_gate_mul(const float* x, const float* ref, float* out, long long n, void* stream) {
+  DG_TRACE("dg_gate_mul", x, ref, out, n);
   if (n <= 0) return fail("n must be > 0");
   long long n4 = n / 4;
   long long blocks = (n4 + 255) / 256;
@@ -296,6 +297,7 @@ extern "C" int dg_gate_mul(const float* x, const float* ref, float* out, long lo
 }
 
 extern "C" int dg_colsum(const float* a, float* out, long long R, int N, void* stream) {
+  DG_TRACE("dg_colsum", a, out, R, N);
   if (R <= 0 || N <= 0) return fail("bad shape");
   long long want = (R + 63) / 64;
   long long cap = (long long)sm_count() * 4;

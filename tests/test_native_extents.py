@@ -116,6 +116,10 @@ class TraceBackend(_lib.CudaBackend):
         self._remember(io, params, grads, ws)
         super().block_bwd_bwd(io, params, grads, b, n, d, h, heads, flags, eps, ws)
 
+    def encoder_fwd(self, x, y, x_out, y_out, params, depth, scratch, b, n, d, h, heads, last_edge_out, eps, ws):
+        self._remember(dict(scratch, _x=x, _y=y, _xo=x_out, _yo=y_out), params, None, ws)
+        super().encoder_fwd(x, y, x_out, y_out, params, depth, scratch, b, n, d, h, heads, last_edge_out, eps, ws)
+
 
 @pytest.fixture()
 def traced(monkeypatch):
@@ -235,17 +239,9 @@ def test_encoder_forward_buffers(traced, monkeypatch):
     for depth in (1, 2, 3, 4):
         for last_edge_out in (True, False):
             blocks = [make_params(384) for _ in range(depth)]
-            captured = []
-            orig = traced.encoder_fwd
-
-            def enc(x_, y_, xo, yo, params, depth_, scratch, *a, _orig=orig, _cap=captured):
-                traced.tensors += [t for t in [x_, y_, xo, yo] + list(params) + list(scratch.values()) + [a[-1]] if t is not None]
-                return _orig(x_, y_, xo, yo, params, depth_, scratch, *a)
-            monkeypatch.setattr(traced, "encoder_fwd", enc)
             block.encoder_forward_nograd(x, y, blocks, HEADS, last_edge_out)
             launches, checked = check_bounds(traced)
             assert launches == 10 * depth - (0 if last_edge_out else 1)
-            monkeypatch.setattr(traced, "encoder_fwd", orig)
 
 
 # ---- the C launch programs against block.py's launch lists, structurally -----------------------------------------------
@@ -466,3 +462,100 @@ def test_second_order_program_equals_python_list(both, edge_out, kept):
                  "y3": torch.randn(243, D), "e": torch.randn(243, D), "z4": torch.randn(243, D)}
         named.update({nm.upper(): t for nm, t in saved.items()})
     assert_same(both(lambda: block.block_backward_backward(x, y, dxo, dyo, ux, uy, params, HEADS, edge_out, saved), named))
+
+
+# ---- a whole GAN step through the dry run -------------------------------------------------------------------------------
+def extents_glue(name, a):
+    if name == "dg_symmetrize":
+        return [(a[0], a[2] * a[3] * a[3] * a[4] * 4), (a[1], a[2] * a[3] * a[3] * a[4] * 4)]
+    if name in ("dg_embed_labels_fwd", "dg_embed_labels_bwd"):
+        rows, classes, d = a[4], a[6], a[7]
+        return [(a[0], rows * a[1]), (a[2], (classes if name.endswith("fwd") else rows) * d * 4), (a[3], (rows if name.endswith("fwd") else classes) * d * 4)]
+    if name == "dg_gp_interp":
+        rows, per, classes = a[5], a[6], a[7]
+        return [(a[0], rows * a[1]), (a[2], rows * classes * 4), (a[3], rows // per * 4), (a[4], rows * classes * 4)]
+    if name == "dg_gp_penalty":
+        return [(a[0], a[5] * a[6] * 4), (a[1], a[5] * a[7] * 4), (a[2], 4), (a[3], a[5] * 4), (a[4], a[5] * 4)]
+    if name == "dg_gp_penalty_bwd":
+        return [(a[0], a[4] * a[5] * 4), (a[1], a[4] * 4), (a[2], 4), (a[3], a[4] * a[5] * 4)]
+    if name == "dg_readout_argmax":
+        rows, d, classes = a[6], a[7], a[8]
+        return [(a[0], rows * d * 4), (a[1], classes * d * 4), (a[2], classes * 4), (a[3], rows * classes * 4), (a[4], rows * a[5])]
+    if name == "dg_adamw_flat":
+        return [(a[i], 4) for i in range(4)] + [(a[4], a[5] * 32)]          # (the segment table describes the four flat buffers)
+    if name == "dg_label2onehot":
+        return [(a[0], a[3] * a[1]), (a[2], a[3] * a[4] * 4)]
+    if name == "dg_argmax_last":
+        return [(a[0], a[2] * a[3] * 4), (a[1], a[2] * 8)]
+    if name == "dg_gate_mul":
+        return [(a[i], a[3] * 4) for i in range(3)]
+    if name == "dg_colsum":
+        return [(a[0], a[2] * a[3] * 4), (a[1], a[3] * 4)]
+    if name == "dg_modulate_fwd":
+        b, n, d = a[5], a[6], a[7]
+        return [(a[0], b * n * d * 4), (a[1], b * n * d * 4), (a[2], b * n * n * d * 4), (a[4], b * n * n * d * 4)]
+    if name == "dg_softmax_agg_fwd":
+        b, n, d = a[3], a[4], a[5]
+        return [(a[0], b * n * n * d * 4), (a[1], b * n * d * 4), (a[2], b * n * d * 4)]
+    return extents(name, a)
+
+
+@pytest.mark.parametrize("native", [True, False])
+def test_whole_gan_step_bounds(monkeypatch, native):
+    """One GANTrainer.step (D step with the gradient penalty's double backward, G step, both AdamW updates) on CPU tensors through
+    the dry run: every launch of the step -- issued by the block-level entry points or one by one from block.py -- touches only
+    memory inside the tensors it was handed, given the shapes it was told."""
+    import druggen_b200 as dg
+    from druggen_b200 import gan
+    be = PyTraceBackend()
+    seen = []
+    orig_ptr = _lib._ptr
+
+    def ptr(t):
+        if t is not None:
+            seen.append(t)
+        return orig_ptr(t)
+    monkeypatch.setattr(_lib, "_ptr", ptr)
+    monkeypatch.setattr(_lib, "_backend", be)
+    monkeypatch.setattr(_lib, "cuda_backend", lambda: be)
+
+    def chk(*ts, bf16_ok=False):                          # kernels._chk minus "is on a CUDA device"
+        for t in ts:
+            assert t is None or (t.is_contiguous() and (t.dtype == torch.float32 or (bf16_ok and t.dtype == torch.bfloat16)))
+    monkeypatch.setattr(K, "_chk", chk)
+    monkeypatch.setattr(K, "_chk_buffers", lambda ts, dev: None)
+    monkeypatch.setattr(K, "_chk_labels", lambda l: l.contiguous())
+    monkeypatch.setattr(K, "_precision", "bf16")
+    monkeypatch.setenv("DRUGGEN_B200_NATIVE_BLOCK", "1" if native else "0")
+
+    def aligned_ws(w1):
+        nbytes = 2 * (w1.shape[0] // 128) * 32768
+        raw = torch.empty(nbytes + 128, dtype=torch.uint8)
+        off = (-raw.data_ptr()) % 128
+        return raw[off:off + nbytes]
+    monkeypatch.setattr(K, "_mlp_ws", aligned_ws)
+    torch.manual_seed(0)
+    n, bsz = 9, 4
+    G = dg.Generator("relu", n, 5, 13, 0.0, dim=D, depth=2, heads=HEADS, mlp_ratio=3)
+    Dn = dg.Discriminator("relu", n, 5, 13, 0.0, dim=D, depth=2, heads=HEADS, mlp_ratio=3)
+    tr = gan.GANTrainer(G, Dn)
+    a, x = gan.synthetic_molecules(bsz, n, 13, 5, seed=3, labels=True)
+    be.lib.dg_debug_trace(1)
+    try:
+        tr.step(a, x, a, x)
+        prog = read_trace(be)
+    finally:
+        be.lib.dg_debug_trace(0)
+    names = [p[0] for p in prog]
+    assert ("add3" in names) == native and names.count("dg_adamw_flat") == 2 and names.count("dg_gp_penalty") == 1
+    assert names.count("dg_attn_edge_fwd") >= 6 and names.count("dg_add_ln_bwd_bwd") == 8        # 2 D blocks x 4 LayerNorms, second order
+    ranges = sorted({(t.data_ptr(), t.data_ptr() + t.numel() * t.element_size()) for t in seen + be.tensors if t.numel()})
+    checked = 0
+    for name, vals in prog:
+        for p, nbytes in extents_glue(name, vals):
+            if p == 0 or nbytes == 0:
+                continue
+            assert any(lo <= p and p + nbytes <= hi for lo, hi in ranges), \
+                "%s touches [%x, +%d) which is not inside any tensor it was handed: %s" % (name, p, nbytes, vals)
+            checked += 1
+    assert checked > 2000

@@ -82,14 +82,16 @@ class Encoder_Block(nn.Module):
 
     def _params(self):
         """The block's 30 tensors in BLOCK_PARAM_NAMES order, looked up by attribute on every call so it stays correct
-        after .to()/.cuda(), load_state_dict and in nn.DataParallel replicas (whose parameters are plain attributes)."""
-        out = []
-        for name in BLOCK_PARAM_NAMES:
-            obj = self
-            for part in name.split("."):
-                obj = getattr(obj, part)
-            out.append(obj)
-        return out
+        after .to()/.cuda(), load_state_dict and in nn.DataParallel replicas (whose parameters are plain attributes).  Written out
+        (one attribute chain per sub-module instead of thirty dotted-name walks: 70 -> 30 us per call, which is half of a small
+        graph-replayed encoder forward); ``tests/test_dropin_api.py`` holds it against the names."""
+        a, m, m2 = self.attn, self.mlp, self.mlp2
+        ln1, ln3, ln4, ln5, ln6 = self.ln1, self.ln3, self.ln4, self.ln5, self.ln6
+        q, k, v, e, oe, on = a.q, a.k, a.v, a.e, a.out_e, a.out_n
+        f1, f2, g1, g2 = m.fc1, m.fc2, m2.fc1, m2.fc2
+        return [ln1.weight, ln1.bias, q.weight, q.bias, k.weight, k.bias, v.weight, v.bias, e.weight, e.bias, oe.weight, oe.bias,
+                on.weight, on.bias, ln3.weight, ln3.bias, ln4.weight, ln4.bias, f1.weight, f1.bias, f2.weight, f2.bias,
+                g1.weight, g1.bias, g2.weight, g2.bias, ln5.weight, ln5.bias, ln6.weight, ln6.bias]
 
     def forward(self, x, y, _edge_out: bool = True):
         # training-mode dropout (reference --dropout / --ddropout, default 0): layers.py:54 on both MLP outputs

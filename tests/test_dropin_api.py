@@ -71,3 +71,16 @@ def test_trainer_checkpoint_files_follow_the_reference(tmp_path):
         assert p0.data_ptr() == tr.g_optimizer.flat_p.data_ptr()          # still a view of the optimizer's flat buffer
     finally:
         kernels._install_backend_for_tests(None)
+
+
+def test_block_params_follow_the_state_dict_names():
+    """Encoder_Block._params() (written out for speed) is BLOCK_PARAM_NAMES, name by name."""
+    import druggen_b200 as dg
+    from druggen_b200.block import BLOCK_PARAM_NAMES
+    blk = dg.Encoder_Block(128, 8, None, mlp_ratio=3, drop_rate=0.0)
+    named = dict(blk.named_parameters())
+    assert list(named) != [] and set(named) == set(BLOCK_PARAM_NAMES)
+    got = blk._params()
+    assert len(got) == len(BLOCK_PARAM_NAMES)
+    for nm, t in zip(BLOCK_PARAM_NAMES, got):
+        assert t is named[nm], nm

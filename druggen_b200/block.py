@@ -507,18 +507,23 @@ def block_backward(x, y, dxo, dyo, params: Sequence[torch.Tensor], heads: int, e
     return dx.view(b, n, d), dy.view(b, n, n, d), grads
 
 
+_GRAD_LAYOUT = {}      # (shapes of the 30 parameters, live, second_order) -> (sizes, shapes) of the flat gradient buffer's segments
+
+
 def _flat_grads(params, live, dev, second_order=False):
     """30 gradient tensors as views of ONE zeroed buffer (None for the parameters a block without a live edge output never
     touches: out_e, ln4, mlp2, ln6 -- and, in the second-order pass, for ln5.bias / ln6.bias: the backward program does not
     depend on the output LayerNorms' shifts)."""
-    dead = (() if live else ("attn.out_e.", "ln4.", "mlp2.", "ln6.")) + (("ln5.bias", "ln6.bias") if second_order else ())
-    sizes = [0 if (dead and nm.startswith(dead)) else params[i].numel() for i, nm in enumerate(BLOCK_PARAM_NAMES)]
-    flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
-    grads, o = [], 0
-    for t, sz in zip(params, sizes):
-        grads.append(flat[o:o + sz].view_as(t) if sz else None)
-        o += sz
-    return grads
+    key = (tuple(t.shape for t in params), bool(live), bool(second_order))
+    lay = _GRAD_LAYOUT.get(key)
+    if lay is None:
+        dead = (() if live else ("attn.out_e.", "ln4.", "mlp2.", "ln6.")) + (("ln5.bias", "ln6.bias") if second_order else ())
+        keep = [not (dead and nm.startswith(dead)) for nm in BLOCK_PARAM_NAMES]
+        lay = _GRAD_LAYOUT[key] = (keep, [t.numel() for t, k in zip(params, keep) if k], [t.shape for t, k in zip(params, keep) if k])
+    keep, sizes, shapes = lay
+    parts = iter(torch.zeros(sum(sizes), dtype=torch.float32, device=dev).split(sizes))      # one fill, one split
+    shp = iter(shapes)
+    return [next(parts).view(next(shp)) if k else None for k in keep]
 
 
 def _native_backward_backward(x, y, dxo, dyo, ux, uy, params, heads, edge_out, fwd_saved):

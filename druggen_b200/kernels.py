@@ -428,14 +428,14 @@ def block_fwd(io: dict, params, b: int, n: int, d: int, h: int, heads: int, flag
 
 def block_bwd(io: dict, params, grads, b: int, n: int, d: int, h: int, heads: int, flags: int, eps: float = 1e-5) -> None:
     """``dg_block_bwd`` over the named buffers of ``io``; ``grads``: 30 zeroed tensors (None where no consumer) or None."""
-    _chk(*params, *([] if grads is None else grads))
+    _chk(*params)                 # (the gradient tensors are the caller's own fresh views: block._flat_grads)
     _chk_buffers(io.values(), params[0].device)
     _be().block_bwd(io, params, grads, b, n, d, h, heads, flags, eps, _mlp_ws(params[18]))
 
 
 def block_bwd_bwd(io: dict, params, grads, b: int, n: int, d: int, h: int, heads: int, flags: int, eps: float = 1e-5) -> None:
     """``dg_block_bwd_bwd`` (the gradient penalty's second-order pass of one block) over the named buffers of ``io``."""
-    _chk(*params, *grads)
+    _chk(*params)
     _chk_buffers(io.values(), params[0].device)
     _be().block_bwd_bwd(io, params, grads, b, n, d, h, heads, flags, eps, _mlp_ws(params[18]))
 

@@ -560,3 +560,14 @@ def test_whole_gan_step_bounds(monkeypatch, precision, native):
                 "%s touches [%x, +%d) which is not inside any tensor it was handed: %s" % (name, p, nbytes, vals)
             checked += 1
     assert checked > 2000
+
+
+@pytest.mark.parametrize("depth,last_edge_out", [(1, True), (2, True), (3, True), (4, True), (1, False), (2, False), (3, False), (4, False)])
+def test_encoder_program_equals_python_list(both, depth, last_edge_out):
+    """dg_encoder_fwd (ping-pong buffers between layers, the caller's outputs used as one of them) against block.py's layer loop."""
+    blocks = [make_params(384) for _ in range(depth)]
+    x, y = data(3, 9)
+    named = {"X": x, "Y": y}
+    for l, params in enumerate(blocks):
+        named.update({"P%d.%d" % (l, i): p for i, p in enumerate(params)})
+    assert_same(both(lambda: block.encoder_forward_nograd(x, y, blocks, HEADS, last_edge_out), named))

@@ -234,7 +234,9 @@ def _native_forward(x, y, params, heads, edge_out, want_stats, want_saved):
 
 # Small encoder forwards are launch-bound even with the library sequencing its own launches (8 layers x 10 launches of a few
 # microseconds each): below this edge-tensor size the whole ``dg_encoder_fwd`` call is captured ONCE into a CUDA graph per
-# (shape, weights) and replayed -- inputs copied into the graph's static buffers, outputs cloned out of them.
+# (shape, weights) and replayed -- inputs copied into the graph's static buffers, outputs cloned out of them.  Copies, replay and
+# clones are ordered on the caller's current stream; callers that run the same shape on several streams AT ONCE share those static
+# buffers and must switch the replay off (DRUGGEN_B200_GRAPH=0).
 _GRAPH = {"on": os.environ.get("DRUGGEN_B200_GRAPH", "1") != "0",
           "max_edge_bytes": int(float(os.environ.get("DRUGGEN_B200_GRAPH_MAX_MB", "64")) * 2 ** 20), "cache": {}, "max_entries": 8}
 
